@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py — HYPELCNN forward+backward+Adam patches/s on synthetic GRSS2013-shaped batches.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun)
+  python bench.py --impl reference --gpus N --steps K --warmup W   (CPU arm, rank 0 only)
+
+One "step" = one optimize_nn train step (common/common_nn_ops.py:208-240 of the reference):
+training forward, loss, backward, [gradient all-reduce over NCCL], Adam — on one batch of
+`--batch` synthetic patches per GPU (default 4096, BASELINE.json configs[1]).  Prints ONE
+JSON line (rank 0).  See DESIGN.md §Measurement for how each field is produced.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG = {"batch_size": 4096, "drop_out_ratio": 0.70, "filter_count": 480, "learning_rate": 0.0003,
+       "learning_rate_decay_factor": 0.96, "learning_rate_decay_step": 350, "lrelu_alpha": 0.18,
+       "optimizer": "AdamOptimizer", "bn_decay": 0.95, "l2regularizer_scale": 0.00001,
+       "spectral_hierarchy_level": 3, "spatial_hierarchy_level": 3, "degradation_coeff": 3, "use_residual": True}
+WORKLOADS = {  # name -> (patch, channels, classes)
+    "c2_grss2013": (7, 145, 15),
+    "c3_grss2018": (11, 49, 20),
+    "c5_gulfport": (3, 65, 11),
+}
+METRIC = "HSI+LiDAR patches/sec fwd+bwd (HYPELCNN, GRSS2013 shape)"
+FWD_BWD_MFLOP = {"c2_grss2013": 469.8, "c3_grss2018": 3550.3, "c5_gulfport": 37.0}  # SURVEY §8d, per patch
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        if self.nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": float(numpy.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------
+def oracle_cpu_rate(workload, batch, steps, warmup=1):
+    """patches/s of the CPU oracle (restatement of the reference's TF graph) doing the same
+    train step on the host cores.  Returns (rate, seconds, threads)."""
+    import torch
+    from oracle import hypelcnn_ref as R
+    P, C, classes = WORKLOADS[workload]
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    alg = {**ALG, "batch_size": batch, "drop_out_ratio": 0.0}
+    v = R.init_variables(P, C, classes, alg, seed=1234)
+    rng = numpy.random.default_rng(1234)
+    x = torch.tensor(rng.random((batch, P, P, C), dtype=numpy.float32))
+    y = torch.tensor(rng.integers(0, classes, batch))
+    opt = {}
+    for i in range(warmup):
+        _, v, opt, _ = R.train_step(v, opt, x, y, classes, alg, i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        _, v, opt, _ = R.train_step(v, opt, x, y, classes, alg, warmup + i)
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = args.ref_batch
+    rate, dt, threads = oracle_cpu_rate(args.workload, batch, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "patches/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "per_step_sample": f"{batch} patches (bounded sample of the "
+                   f"{args.batch}-patch step)", "note": "CPU oracle = restatement of the reference's TF graph on "
+                   "torch-CPU; TensorFlow is not installable in this image"},
+        "cpu_baseline": {"value": rate, "unit": "patches/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} train steps of {batch} patches, dropout off"},
+        "e2e": {"value": rate, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+def profile_table(N):
+    out = {}
+    name = ctypes.create_string_buffer(64)
+    ms, fl, by, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+    i = 0
+    while N.lib().hyp_profile_get(i, name, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(fl), ctypes.byref(by)) == 0:
+        out[name.value.decode()] = {"ms": ms.value, "launches": n.value, "flops": fl.value, "bytes": by.value}
+        i += 1
+    return out
+
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    from hypelcnn_b200 import _native as N
+    from hypelcnn_b200 import engine as E
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    P, C, classes = WORKLOADS[args.workload]
+    B = args.batch
+    alg = {**ALG, "batch_size": B}
+    eng = E.PatchEngine(P, C, classes, alg, max_batch=B, precision=args.precision)
+    eng.init_variables(1234)  # same seed on every rank == broadcast initial weights
+    rng = numpy.random.default_rng(1234 + rank)
+    nb = args.input_batches
+    host_x = [torch.from_numpy(rng.random((B, P, P, C), dtype=numpy.float32)).pin_memory() for _ in range(nb)]
+    host_y = [torch.from_numpy(rng.integers(0, classes, B).astype(numpy.uint8)).pin_memory() for _ in range(nb)]
+    dev_x = [t.cuda() for t in host_x]
+    dev_y = [t.cuda() for t in host_y]
+
+    def allreduce(grads):
+        dist.all_reduce(grads)  # one NCCL all-reduce over the flat gradient buffer
+        return 1.0 / world
+    ar = allreduce if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`) ----
+    for i in range(args.warmup):
+        eng.train_step(dev_x[i % nb], dev_y[i % nb], allreduce=ar)
+    barrier()
+    N.lib().hyp_launch_count(1)
+    N.check(N.lib().hyp_profile_enable(1 if rank == 0 else 0))
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        loss = eng.train_step(dev_x[i % nb], dev_y[i % nb], allreduce=ar)
+    ev1.record()
+    barrier()
+    clocks = sampler.result()
+    launches = int(N.lib().hyp_launch_count(0))
+    ms = ev0.elapsed_time(ev1)
+    prof = profile_table(N) if rank == 0 else {}
+    N.lib().hyp_profile_enable(0)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    value = world * B * args.steps / (ms / 1e3)
+    final_loss = loss.cpu().tolist()
+
+    # ---- end to end through the public API with HOST buffers (`e2e`) ----
+    from hypelcnn_b200.common import common_nn_ops as ops
+    trainer = ops.HostBatchTrainer(eng, allreduce=ar)
+    for i in range(2):
+        trainer.step(host_x[i % nb], host_y[i % nb])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        host_loss = trainer.step(host_x[i % nb], host_y[i % nb])  # H2D copy, step, D2H loss read
+    e1.record()
+    barrier()
+    ems = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ems], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ems = t.item()
+    e2e = {"value": world * B * args.steps / (ems / 1e3), "unit": "patches/s",
+           "h2d_bytes_per_step": host_x[0].numel() * 4 + host_y[0].numel(), "d2h_bytes_per_step": 12,
+           "ms_per_step": ems / args.steps, "api": "common_nn_ops.HostBatchTrainer.step (optimize_nn equivalent)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = measured_peaks()
+    # dominant kernel = kernel function with the largest summed device time in the timed region
+    by_kernel = {}
+    for tag, r in prof.items():
+        k = tag.split("/")[0]
+        a = by_kernel.setdefault(k, {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0})
+        for f in a:
+            a[f] += r[f]
+    total_prof_ms = sum(r["ms"] for r in by_kernel.values()) or 1.0
+    dom = max(by_kernel, key=lambda k: by_kernel[k]["ms"]) if by_kernel else None
+    roofline = None
+    if dom:
+        d = by_kernel[dom]
+        if d["flops"] > 0:
+            achieved = d["flops"] / (d["ms"] / 1e3) / 1e12
+            peak = peaks["bf16_tflops_sustained"]
+            roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                        "frac": achieved / peak, "traffic": None, "kernel": dom,
+                        "avg_launch_ms": d["ms"] / d["launches"], "share_of_step": d["ms"] / total_prof_ms,
+                        "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step); "
+                                       "this kernel computes in fp32 FFMA"}
+        else:
+            achieved = d["bytes"] / (d["ms"] / 1e3) / 1e9
+            roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": achieved / peaks["hbm_gbs"], "traffic": None, "kernel": dom,
+                        "avg_launch_ms": d["ms"] / d["launches"], "share_of_step": d["ms"] / total_prof_ms,
+                        "peak_source": peaks["source"]}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, dt, threads = oracle_cpu_rate(args.workload, args.ref_batch, 3, 1)
+        cpu = {"value": rate, "unit": "patches/s", "cores": threads, "kind": "port",
+               "sample": f"3 train steps of {args.ref_batch} patches on the CPU oracle ({dt:.1f} s)"}
+    step_tflops = FWD_BWD_MFLOP[args.workload] * 1e6 * B * world / (ms / args.steps / 1e3) / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": {"fp32": "f32", "3xtf32": "tf32x3", "bf16": "bf16"}[args.precision],
+        "data": "synthetic",
+        "config": {"workload": args.workload, "per_gpu_batch": B, "global_batch": B * world, "patch": P, "channels": C,
+                   "classes": classes, "precision_mode": args.precision,
+                   "parallelism": f"dp{world}: 1 NCCL all-reduce of {eng.params.numel()} fp32 grads/step" if world > 1 else "single GPU",
+                   "l2": f"per-step working set {eng.workspace_bytes / 1e9:.1f} GB >> 126 MB L2; inputs rotate over "
+                         f"{nb} resident batches ({nb * host_x[0].numel() * 4 / 1e6:.0f} MB)"},
+        "step_tflops_useful": step_tflops, "step_frac_of_bf16_peak": step_tflops / (peaks["bf16_tflops_sustained"] * world),
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": launches,
+        "final_loss": final_loss,
+        "kernel_breakdown_ms_per_step": {k: round(v["ms"] / args.steps, 4) for k, v in
+                                         sorted(by_kernel.items(), key=lambda kv: -kv[1]["ms"])},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="c2_grss2013", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=4096, help="patches per GPU per step")
+    ap.add_argument("--ref-batch", type=int, default=256, help="patches per step of the CPU arm (bounded sample)")
+    ap.add_argument("--input-batches", type=int, default=4)
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "3xtf32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "native":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,905 @@
+// hypelcnn_b200 engine: builds the HYPELCNN layer plan from a descriptor, lays out the
+// caller-owned parameter / state / workspace buffers, and drives the CUDA kernels for
+// forward, loss, backward, Adam, metrics and the patch gather.  C ABI in
+// include/hypelcnn_b200.h.  No CPU fallback: every compute entry point needs a CUDA device.
+//
+// Reference behaviour restated here (never copied): nnmodel/HYPELCNNModel.py:34-183,
+// common/common_nn_ops.py:208-240,546-564.
+#include <cmath>
+#include <map>
+#include <memory>
+#include <vector>
+
+#include "hyp_common.cuh"
+#include "hyp_gemm_simt.cuh"
+#include "hyp_kernels.cuh"
+
+namespace hyp {
+thread_local std::string g_last_error;
+thread_local int64_t g_launch_count = 0;
+thread_local Profiler g_prof;
+
+struct Variable {
+  std::string name;
+  int kind;  // 0 weights 1 beta 2 moving_mean 3 moving_variance
+  int64_t offset;
+  int shape[4];
+  int rank;
+};
+
+struct Resid {
+  int src;          // tensor id
+  bool identity;
+  int* idx = nullptr;  // device [Cout]   out channel -> src channel
+  int* lo = nullptr;   // device [Csrc]   src channel -> [lo, hi) out channels (idx is monotone)
+  int* hi = nullptr;
+};
+
+struct Tensor {
+  std::string name;
+  int C;              // channels per row
+  int rows_per_sample;
+  size_t a_off = 0;   // byte offsets in workspace
+  size_t g_off = 0;
+  bool external = false;  // the input x
+  bool needs_grad = true;
+};
+
+struct Layer {
+  std::string scope;      // level layers: "connector_0" (individual convs are named per kernel)
+  bool is_fc;
+  int P;                  // spatial edge for shifts (1 for FC)
+  int in_t, out_t;
+  int Cin, Cout;
+  int rows_per_sample;
+  std::vector<int> ksizes;     // conv kernels of a level (1x1 conv: {1}); FC: {1}
+  int f;                       // channels per kernel
+  std::vector<std::string> kscopes;
+  int act;
+  bool dropout;
+  std::vector<Resid> res;
+  // parameter offsets (elements)
+  std::vector<int64_t> w_off;  // per kernel
+  int64_t beta_off, mm_off;    // beta in params; moving mean/var in state (mv = mm + Cout)
+  // workspace byte offsets
+  size_t z_off, wt_off, stats_off, bstats_off, mean_off, rstd_off, s1_off, s2_off;
+  int seg_begin, seg_count;
+  std::vector<int> kseg_begin;  // first segment of kernel j
+  uint32_t drop_stream;
+};
+
+}  // namespace hyp
+
+using namespace hyp;
+
+struct hyp_model {
+  hyp_model_desc d;
+  std::vector<Tensor> tensors;
+  std::vector<Layer> layers;
+  std::vector<Variable> vars;
+  std::map<std::string, int> tensor_by_name;
+  int64_t n_params = 0, n_state = 0;
+  size_t ws_bytes = 0;
+  size_t gz_off = 0, ce_off = 0, mse_off = 0, stats_region_off = 0, stats_region_bytes = 0;
+  size_t bstats_region_off = 0, bstats_region_bytes = 0;
+  int logits_t = -1, recon_t = -1, last_eval_layer = -1;
+  // library-owned device metadata
+  Seg* segs_dev = nullptr;
+  std::vector<Seg> segs_host;
+  TransposeJob* tjobs_dev = nullptr;
+  int4* tmap_dev = nullptr;
+  int n_ttiles = 0;
+  std::vector<void*> owned;
+  // bound buffers
+  float *params = nullptr, *grads = nullptr, *state = nullptr;
+  char* ws = nullptr;
+  bool segs_bound = false;
+  // call state
+  int64_t last_B = -1;
+  bool last_training = false;
+  uint64_t last_seed = 0;
+  const float* last_x = nullptr;
+};
+
+namespace hyp {
+
+static std::vector<int> scale_index(int cin, int cout) {
+  // common/common_nn_ops.py:546-564 — double arithmetic and banker's rounding like Python
+  const double ratio = (double)cin / (double)cout;
+  const double inv = 1.0 / ratio;
+  std::vector<int> idx;
+  if (std::floor(inv) == inv) {
+    const int rep = (int)inv;
+    for (int j = 0; j < cin * rep; j++) idx.push_back(j / rep);
+  } else {
+    for (int j = 0; j < cout; j++) {
+      const int t = (int)std::nearbyint((double)j * ratio);  // FE_TONEAREST = half to even
+      idx.push_back(t < cin - 1 ? t : cin - 1);
+    }
+  }
+  return idx;
+}
+
+struct Builder {
+  hyp_model& m;
+  int seg_total = 0;
+  explicit Builder(hyp_model& mm) : m(mm) {}
+
+  int add_tensor(const std::string& name, int C, int rps, bool external = false) {
+    Tensor t;
+    t.name = name;
+    t.C = C;
+    t.rows_per_sample = rps;
+    t.external = external;
+    t.needs_grad = !external;
+    m.tensors.push_back(t);
+    m.tensor_by_name[name] = (int)m.tensors.size() - 1;
+    return (int)m.tensors.size() - 1;
+  }
+
+  int add_resid(Layer& L, int src) {
+    const int cs = m.tensors[src].C;
+    std::vector<int> idx = scale_index(cs, L.Cout);
+    if ((int)idx.size() != L.Cout) return -1;
+    Resid r;
+    r.src = src;
+    r.identity = (cs == L.Cout);
+    if (r.identity)
+      for (int j = 0; j < L.Cout; j++) r.identity = r.identity && idx[j] == j;
+    if (!r.identity) {
+      std::vector<int> lo(cs, 0), hi(cs, 0);
+      for (int c = 0; c < cs; c++) { lo[c] = L.Cout; hi[c] = 0; }
+      for (int j = 0; j < L.Cout; j++) {
+        lo[idx[j]] = std::min(lo[idx[j]], j);
+        hi[idx[j]] = std::max(hi[idx[j]], j + 1);
+      }
+      for (int c = 0; c < cs; c++)
+        if (hi[c] == 0) lo[c] = 0;
+      // monotone index table => each source channel's consumers are contiguous
+      for (int c = 0; c < cs; c++)
+        for (int j = lo[c]; j < hi[c]; j++)
+          if (idx[j] != c) return -1;
+      r.idx = upload(idx);
+      r.lo = upload(lo);
+      r.hi = upload(hi);
+      if (!r.idx || !r.lo || !r.hi) return -2;
+    }
+    L.res.push_back(r);
+    return 0;
+  }
+
+  int* upload(const std::vector<int>& v) {
+    int* d = nullptr;
+    if (cudaMalloc(&d, v.size() * sizeof(int)) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(d, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+    m.owned.push_back(d);
+    return d;
+  }
+
+  // conv level (one or several square kernels sharing the input, outputs concatenated) or FC
+  Layer& add_layer(const std::string& scope, bool fc, int P, int in_t, const std::string& out_name, int f,
+                   const std::vector<int>& ks, const std::vector<std::string>& kscopes, int act, bool dropout) {
+    Layer L;
+    L.scope = scope;
+    L.is_fc = fc;
+    L.P = fc ? 1 : P;
+    L.in_t = in_t;
+    L.Cin = fc ? m.tensors[in_t].C * m.tensors[in_t].rows_per_sample : m.tensors[in_t].C;
+    L.f = f;
+    L.ksizes = ks;
+    L.kscopes = kscopes;
+    L.Cout = f * (int)ks.size();
+    L.rows_per_sample = fc ? 1 : m.tensors[in_t].rows_per_sample;
+    L.act = act;
+    L.dropout = dropout;
+    L.out_t = add_tensor(out_name, L.Cout, L.rows_per_sample);
+    L.drop_stream = (uint32_t)m.layers.size() + 1;
+    L.seg_begin = seg_total;
+    for (int k : ks) {
+      L.kseg_begin.push_back(seg_total);
+      seg_total += k * k;
+    }
+    L.seg_count = seg_total - L.seg_begin;
+    m.layers.push_back(L);
+    return m.layers.back();
+  }
+};
+
+static int build_hypelcnn(hyp_model& m) {
+  const hyp_model_desc& d = m.d;
+  Builder b(m);
+  const int P = d.patch, PP = P * P;
+  const bool res = d.use_residual != 0;
+  int cur = b.add_tensor("x", d.channels, PP, true);
+  const int x_t = cur;
+  // spectral encoder / decoder (HYPELCNNModel.py:146-164, :54-64)
+  for (int enc = 1; enc >= 0; enc--) {
+    const int block_in = cur;
+    for (int i = 0; i < d.spectral_levels; i++) {
+      const int cout = enc ? d.filter_count >> ((d.spectral_levels - 1) - i) : d.filter_count >> i;
+      if (cout <= 0) return fail(HYP_E_INVALID, "filter_count too small for spectral levels");
+      const std::string name = std::string(enc ? "conv_enc_" : "conv_dec_") + std::to_string(i);
+      Layer& L = b.add_layer(name, false, P, cur, name, cout, {1}, {name}, ACT_LRELU, false);
+      if (res) {
+        if (b.add_resid(L, cur)) return fail(HYP_E_INVALID, "residual table for " + name);
+        if (i == d.spectral_levels - 1 && b.add_resid(L, block_in))
+          return fail(HYP_E_INVALID, "block residual table for " + name);
+      }
+      cur = L.out_t;
+    }
+  }
+  const int net2 = cur;
+  // spatial blocks (HYPELCNNModel.py:128-143, :167-183)
+  const int lf = m.tensors[net2].C / 2;
+  for (int i = 0; i < d.spatial_levels; i++) {
+    const int f = lf >> i;
+    if (f <= 0) return fail(HYP_E_INVALID, "filter_count too small for spatial levels");
+    std::vector<int> ks;
+    std::vector<std::string> kn;
+    const std::string lvl = "connector_" + std::to_string(i);
+    for (int k = 1; k <= P; k += 2) {
+      ks.push_back(k);
+      kn.push_back(lvl + "_conv" + std::to_string(k) + "x" + std::to_string(k));
+    }
+    Layer& L = b.add_layer(lvl, false, P, cur, lvl, f, ks, kn, ACT_LRELU, false);
+    if (res && b.add_resid(L, cur)) return fail(HYP_E_INVALID, "residual table for " + lvl);
+    const int lvl_t = L.out_t;
+    const std::string cn = "connector_conv_" + std::to_string(i);
+    Layer& Cn = b.add_layer(cn, false, P, lvl_t, cn, m.tensors[lvl_t].C, {1}, {cn}, ACT_LRELU, false);
+    if (res) {
+      if (b.add_resid(Cn, lvl_t)) return fail(HYP_E_INVALID, "residual table for " + cn);
+      if (i == d.spatial_levels - 1 && b.add_resid(Cn, net2)) return fail(HYP_E_INVALID, "net3 residual table");
+    }
+    cur = Cn.out_t;
+  }
+  // FC block (HYPELCNNModel.py:115-125): stages = floor(log_deg(flat / classes))
+  const int flat = PP * m.tensors[cur].C;
+  if (d.degradation < 2) return fail(HYP_E_INVALID, "degradation_coeff must be >= 2");
+  const int stages = (int)std::floor(std::log((double)flat / (double)d.classes) / std::log((double)d.degradation));
+  int size = flat;
+  for (int i = 0; i < stages - 1; i++) {
+    size = size / d.degradation;
+    const std::string name = "fc_" + std::to_string(i);
+    Layer& L = b.add_layer(name, true, 1, cur, name, size, {1}, {name}, ACT_LRELU, true);
+    cur = L.out_t;
+  }
+  {
+    Layer& L = b.add_layer("fc_final", true, 1, cur, "fc_final", d.classes, {1}, {"fc_final"}, ACT_NONE, false);
+    cur = L.out_t;
+    m.logits_t = cur;
+    m.last_eval_layer = (int)m.layers.size() - 1;
+  }
+  // decoder, training graph only (HYPELCNNModel.py:84-94)
+  int mult = 3;
+  for (int i = 1; i <= 3; i++, mult *= 3) {
+    const std::string name = "image_gen_net_" + std::to_string(i);
+    Layer& L = b.add_layer(name, true, 1, cur, name, d.classes * mult, {1}, {name}, ACT_LRELU, false);
+    cur = L.out_t;
+  }
+  {
+    Layer& L = b.add_layer("image_gen_net_4", true, 1, cur, "image_gen_net_4", PP * d.channels, {1},
+                           {"image_gen_net_4"}, ACT_SIGMOID, false);
+    m.recon_t = L.out_t;
+  }
+  (void)x_t;
+  return HYP_OK;
+}
+
+static int layout(hyp_model& m) {
+  // ---- parameters: per layer W_0..W_{nk-1} (each 128-byte aligned), then beta[Cout] ----
+  int64_t po = 0, so = 0;
+  for (Layer& L : m.layers) {
+    for (size_t j = 0; j < L.ksizes.size(); j++) {
+      const int k = L.ksizes[j];
+      po = (int64_t)align_up((size_t)po, 32);
+      L.w_off.push_back(po);
+      Variable v;
+      v.name = "nn_core/" + L.kscopes[j] + "/weights";
+      v.kind = 0;
+      v.offset = po;
+      if (L.is_fc) {
+        v.rank = 2;
+        v.shape[0] = L.Cin; v.shape[1] = L.f; v.shape[2] = v.shape[3] = 0;
+      } else {
+        v.rank = 4;
+        v.shape[0] = k; v.shape[1] = k; v.shape[2] = L.Cin; v.shape[3] = L.f;
+      }
+      m.vars.push_back(v);
+      po += (int64_t)k * k * L.Cin * L.f;
+    }
+    po = (int64_t)align_up((size_t)po, 32);
+    L.beta_off = po;
+    so = (int64_t)align_up((size_t)so, 32);
+    L.mm_off = so;
+    for (size_t j = 0; j < L.ksizes.size(); j++) {
+      const char* names[3] = {"beta", "moving_mean", "moving_variance"};
+      for (int q = 0; q < 3; q++) {
+        Variable v;
+        v.name = "nn_core/" + L.kscopes[j] + "/BatchNorm/" + names[q];
+        v.kind = 1 + q;
+        v.offset = (q == 0 ? L.beta_off : (q == 1 ? L.mm_off : L.mm_off + L.Cout)) + (int64_t)j * L.f;
+        v.rank = 1;
+        v.shape[0] = L.f; v.shape[1] = v.shape[2] = v.shape[3] = 0;
+        m.vars.push_back(v);
+      }
+    }
+    po += L.Cout;
+    so += 2 * (int64_t)L.Cout;
+  }
+  m.n_params = (int64_t)align_up((size_t)po, 32);
+  m.n_state = (int64_t)align_up((size_t)so, 32);
+
+  // ---- workspace ----
+  const size_t B = (size_t)m.d.max_batch;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    off = align_up(off, 256);
+    const size_t o = off;
+    off += bytes;
+    return o;
+  };
+  for (Tensor& t : m.tensors) {
+    if (t.external) continue;
+    const size_t bytes = B * t.rows_per_sample * t.C * sizeof(float);
+    t.a_off = take(bytes);
+    t.g_off = take(bytes);
+  }
+  size_t gz_max = 0;
+  for (Layer& L : m.layers) {
+    const size_t zb = B * L.rows_per_sample * L.Cout * sizeof(float);
+    L.z_off = take(zb);
+    gz_max = std::max(gz_max, zb);
+    size_t wn = 0;
+    for (int k : L.ksizes) wn += (size_t)k * k * L.Cin * L.f;
+    L.wt_off = take(wn * sizeof(float));
+    L.mean_off = take(L.Cout * sizeof(float));
+    L.rstd_off = take(L.Cout * sizeof(float));
+    L.s1_off = take(L.Cout * sizeof(float));
+    L.s2_off = take(L.Cout * sizeof(float));
+  }
+  m.gz_off = take(gz_max);
+  m.ce_off = take(B * sizeof(float));
+  m.mse_off = take(256);
+  // statistics regions are contiguous so one memset clears them
+  off = align_up(off, 256);
+  m.stats_region_off = off;
+  for (Layer& L : m.layers) L.stats_off = take(2 * (size_t)L.Cout * sizeof(double));
+  m.stats_region_bytes = off - m.stats_region_off;
+  off = align_up(off, 256);
+  m.bstats_region_off = off;
+  for (Layer& L : m.layers) L.bstats_off = take(2 * (size_t)L.Cout * sizeof(double));
+  m.bstats_region_bytes = off - m.bstats_region_off;
+  m.ws_bytes = align_up(off, 256);
+  return HYP_OK;
+}
+
+// segment + transpose tables depend on the bound parameter / workspace pointers
+static int bind_tables(hyp_model& m) {
+  m.segs_host.clear();
+  std::vector<TransposeJob> jobs;
+  std::vector<int4> tmap;
+  for (Layer& L : m.layers) {
+    size_t wt_elems = 0;
+    for (size_t j = 0; j < L.ksizes.size(); j++) {
+      const int k = L.ksizes[j], h = k / 2;
+      const float* w = m.params + L.w_off[j];
+      float* gw = m.grads + L.w_off[j];
+      float* wt = reinterpret_cast<float*>(m.ws + L.wt_off) + wt_elems;
+      for (int ky = 0; ky < k; ky++)
+        for (int kx = 0; kx < k; kx++) {
+          const size_t tap = (size_t)(ky * k + kx) * L.Cin * L.f;
+          Seg s;
+          s.w = w + tap;
+          s.gw = gw + tap;
+          s.wt = wt + tap;
+          s.ldw = L.f;
+          s.ldwt = L.Cin;
+          s.col0 = (int)j * L.f;
+          s.width = L.f;
+          s.dy = ky - h;
+          s.dx = kx - h;
+          m.segs_host.push_back(s);
+          TransposeJob tj;
+          tj.src = s.w;
+          tj.dst = wt + tap;
+          tj.rows = L.Cin;
+          tj.cols = L.f;
+          const int job = (int)jobs.size();
+          jobs.push_back(tj);
+          for (int tr = 0; tr < (int)cdiv(tj.rows, 32); tr++)
+            for (int tc = 0; tc < (int)cdiv(tj.cols, 32); tc++) tmap.push_back(make_int4(job, tr, tc, 0));
+        }
+      wt_elems += (size_t)k * k * L.Cin * L.f;
+    }
+  }
+  if (!m.segs_dev) {
+    HYP_CUDA(cudaMalloc(&m.segs_dev, m.segs_host.size() * sizeof(Seg)));
+    HYP_CUDA(cudaMalloc(&m.tjobs_dev, jobs.size() * sizeof(TransposeJob)));
+    HYP_CUDA(cudaMalloc(&m.tmap_dev, tmap.size() * sizeof(int4)));
+  }
+  HYP_CUDA(cudaMemcpy(m.segs_dev, m.segs_host.data(), m.segs_host.size() * sizeof(Seg), cudaMemcpyHostToDevice));
+  HYP_CUDA(cudaMemcpy(m.tjobs_dev, jobs.data(), jobs.size() * sizeof(TransposeJob), cudaMemcpyHostToDevice));
+  HYP_CUDA(cudaMemcpy(m.tmap_dev, tmap.data(), tmap.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  m.n_ttiles = (int)tmap.size();
+  m.segs_bound = true;
+  return HYP_OK;
+}
+
+// useful MACs*2 of one conv kernel over B samples: SAME-padding zero taps are not counted
+static double conv_flops(int64_t B, int P, int k, int cin, int cout) {
+  int64_t v1 = 0;
+  for (int d = -(k / 2); d <= k / 2; d++) v1 += P - (d < 0 ? -d : d);
+  return 2.0 * (double)B * (double)(v1 * v1) * cin * cout;
+}
+static double layer_flops(const Layer& L, int64_t B) {
+  double f = 0;
+  for (int k : L.ksizes) f += conv_flops(B, L.P, k, L.Cin, L.f);
+  return f;
+}
+#define PROF(name, bytes, launch)             \
+  do {                                        \
+    g_prof.begin(st, name, 0.0, (double)(bytes)); \
+    launch;                                   \
+    g_prof.end(st);                           \
+    HYP_LAUNCHED();                           \
+  } while (0)
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static inline int ew_grid(int64_t total) { return (int)std::min<int64_t>(cdiv(total, 256), 148 * 16); }
+
+static const float* act_ptr(const hyp_model& m, int t, const float* x) {
+  return m.tensors[t].external ? x : reinterpret_cast<const float*>(m.ws + m.tensors[t].a_off);
+}
+static float* grad_ptr(const hyp_model& m, int t) { return reinterpret_cast<float*>(m.ws + m.tensors[t].g_off); }
+
+static int forward_impl(hyp_model& m, const float* x, int64_t B, bool training, bool update_moving, uint64_t seed,
+                        cudaStream_t st) {
+  const int nl = training ? (int)m.layers.size() : m.last_eval_layer + 1;
+  if (training) HYP_CUDA(cudaMemsetAsync(m.ws + m.stats_region_off, 0, m.stats_region_bytes, st));
+  const float keep_prob = 1.f - m.d.drop_out_ratio;
+  for (int li = 0; li < nl; li++) {
+    Layer& L = m.layers[li];
+    const int64_t rows = B * L.rows_per_sample;
+    const float* A = act_ptr(m, L.in_t, x);
+    float* Z = reinterpret_cast<float*>(m.ws + L.z_off);
+    double* stats = reinterpret_cast<double*>(m.ws + L.stats_off);
+    for (size_t j = 0; j < L.ksizes.size(); j++) {
+      RowGemmArgs a;
+      a.A = A; a.lda = L.Cin; a.M = (int)rows; a.P = L.P;
+      a.segs = m.segs_dev + L.kseg_begin[j];
+      a.nseg = L.ksizes[j] * L.ksizes[j];
+      a.mode = 0; a.Kfix = L.Cin;
+      a.C = Z; a.ldc = L.Cout; a.c_col0 = (int)j * L.f; a.N = L.f;
+      a.accumulate = 0;
+      a.stats = training ? stats : nullptr;
+      a.stats_ld = L.Cout;
+      a.a_vec = (L.Cin % 4 == 0) && al16(A);
+      a.b_vec = (L.f % 4 == 0) && al16(m.params + L.w_off[j]) && (((size_t)L.Cin * L.f) % 4 == 0);
+      int rc = launch_rowgemm(a, st, "fwd", conv_flops(B, L.P, L.ksizes[j], L.Cin, L.f));
+      if (rc) return rc;
+    }
+    float* mean = reinterpret_cast<float*>(m.ws + L.mean_off);
+    float* rstd = reinterpret_cast<float*>(m.ws + L.rstd_off);
+    PROF("bn_finalize_kernel", 32.0 * L.Cout,
+         (bn_finalize_kernel<<<(unsigned)cdiv(L.Cout, 128), 128, 0, st>>>(
+             stats, L.Cout, (double)rows, m.d.bn_eps, m.d.bn_decay, m.state + L.mm_off,
+             m.state + L.mm_off + L.Cout, mean, rstd, training ? 1 : 0, (training && update_moving) ? 1 : 0)));
+    ApplyArgs p;
+    p.z = Z; p.mean = mean; p.rstd = rstd; p.beta = m.params + L.beta_off;
+    p.out = reinterpret_cast<float*>(m.ws + m.tensors[L.out_t].a_off);
+    p.rows = rows; p.C = L.Cout; p.act = L.act; p.alpha = m.d.lrelu_alpha;
+    p.keep = (L.dropout && training) ? keep_prob : 1.f;
+    p.seed = seed; p.stream_id = L.drop_stream;
+    p.res0 = p.res1 = nullptr; p.idx0 = p.idx1 = nullptr; p.C0 = p.C1 = 0;
+    if (L.res.size() > 0) {
+      p.res0 = act_ptr(m, L.res[0].src, x); p.idx0 = L.res[0].idx; p.C0 = m.tensors[L.res[0].src].C;
+    }
+    if (L.res.size() > 1) {
+      p.res1 = act_ptr(m, L.res[1].src, x); p.idx1 = L.res[1].idx; p.C1 = m.tensors[L.res[1].src].C;
+    }
+    PROF("bn_apply_fwd_kernel", 4.0 * rows * L.Cout * (2 + L.res.size()),
+         (bn_apply_fwd_kernel<<<ew_grid(rows * L.Cout), 256, 0, st>>>(p)));
+  }
+  return HYP_OK;
+}
+
+static int backward_impl(hyp_model& m, const float* x, const uint8_t* labels, int64_t B, float* loss_out,
+                         cudaStream_t st) {
+  const hyp_model_desc& d = m.d;
+  const int nl = (int)m.layers.size();
+  std::vector<char> ginit(m.tensors.size(), 0);
+  HYP_CUDA(cudaMemsetAsync(m.ws + m.bstats_region_off, 0, m.bstats_region_bytes, st));
+  HYP_CUDA(cudaMemsetAsync(m.grads, 0, (size_t)m.n_params * sizeof(float), st));
+  HYP_CUDA(cudaMemsetAsync(m.ws + m.mse_off, 0, 256, st));
+  // transposed weights for dgrad
+  PROF("transpose_kernel", 8.0 * m.n_params, (transpose_kernel<<<m.n_ttiles, 256, 0, st>>>(m.tjobs_dev, m.tmap_dev)));
+  // losses: mean_B(CE_i + mse)  (HYPELCNNModel.py:101-112, common_nn_ops.py:214)
+  float* ce = reinterpret_cast<float*>(m.ws + m.ce_off);
+  double* mse_acc = reinterpret_cast<double*>(m.ws + m.mse_off);
+  const float* logits = act_ptr(m, m.logits_t, x);
+  PROF("ce_loss_kernel", 8.0 * B * d.classes,
+       (ce_loss_kernel<<<(unsigned)cdiv(B * 32, 256), 256, 0, st>>>(logits, labels, B, d.classes, ce,
+                                                                    grad_ptr(m, m.logits_t), 1.f / (float)B)));
+  ginit[m.logits_t] = 1;
+  const int64_t D = (int64_t)d.patch * d.patch * d.channels;
+  PROF("mse_kernel", 12.0 * B * D,
+       (mse_kernel<<<ew_grid(B * D), 256, 0, st>>>(act_ptr(m, m.recon_t, x), x, B * D, mse_acc,
+                                                   grad_ptr(m, m.recon_t), 1.f / (float)(B * D))));
+  ginit[m.recon_t] = 1;
+  loss_finalize_kernel<<<1, 256, 0, st>>>(ce, B, mse_acc, (double)(B * D), loss_out, nullptr);
+  HYP_LAUNCHED();
+
+  const float keep_prob = 1.f - d.drop_out_ratio;
+  float* gz = reinterpret_cast<float*>(m.ws + m.gz_off);
+  for (int li = nl - 1; li >= 0; li--) {
+    Layer& L = m.layers[li];
+    const int64_t rows = B * L.rows_per_sample;
+    if (!ginit[L.out_t]) return fail(HYP_E_STATE, "backward: no gradient reached " + L.scope);
+    BnBwdArgs p;
+    p.gout = grad_ptr(m, L.out_t);
+    p.z = reinterpret_cast<float*>(m.ws + L.z_off);
+    p.mean = reinterpret_cast<float*>(m.ws + L.mean_off);
+    p.rstd = reinterpret_cast<float*>(m.ws + L.rstd_off);
+    p.beta = m.params + L.beta_off;
+    p.rows = rows; p.C = L.Cout; p.act = L.act; p.alpha = d.lrelu_alpha;
+    p.keep = L.dropout ? keep_prob : 1.f;
+    p.seed = m.last_seed; p.stream_id = L.drop_stream;
+    p.sums = reinterpret_cast<double*>(m.ws + L.bstats_off);
+    float* s1 = reinterpret_cast<float*>(m.ws + L.s1_off);
+    float* s2 = reinterpret_cast<float*>(m.ws + L.s2_off);
+    p.s1 = s1; p.s2 = s2; p.gz = gz;
+    {
+      const int cblocks = (int)cdiv(L.Cout, 32);
+      int rblocks = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(rows, 64), cdiv(148 * 8, cblocks)));
+      const int rpb = (int)cdiv(rows, rblocks);
+      rblocks = (int)cdiv(rows, rpb);
+      PROF("bn_bwd_reduce_kernel", 8.0 * rows * L.Cout,
+           (bn_bwd_reduce_kernel<<<dim3(cblocks, rblocks), 256, 0, st>>>(p, rpb)));
+    }
+    bn_bwd_finalize_kernel<<<(unsigned)cdiv(L.Cout, 128), 128, 0, st>>>(p.sums, L.Cout, (double)rows, s1, s2,
+                                                                         m.grads + L.beta_off);
+    HYP_LAUNCHED();
+    PROF("bn_bwd_apply_kernel", 12.0 * rows * L.Cout,
+         (bn_bwd_apply_kernel<<<ew_grid(rows * L.Cout), 256, 0, st>>>(p)));
+    // residual pushes
+    for (const Resid& r : L.res) {
+      const Tensor& src = m.tensors[r.src];
+      if (!src.needs_grad) continue;
+      PROF("resid_bwd_kernel", 4.0 * rows * (L.Cout + 2.0 * src.C),
+           (resid_bwd_kernel<<<ew_grid(rows * src.C), 256, 0, st>>>(p.gout, L.Cout, grad_ptr(m, r.src), src.C, r.lo,
+                                                                    r.hi, rows, ginit[r.src])));
+      ginit[r.src] = 1;
+    }
+    const float* A = act_ptr(m, L.in_t, x);
+    // wgrad
+    {
+      WgradArgs a;
+      a.A = A; a.lda = L.Cin; a.M = (int)rows; a.P = L.P; a.Cin = L.Cin;
+      a.G = gz; a.ldg = L.Cout;
+      a.segs = m.segs_dev + L.seg_begin; a.nseg = L.seg_count;
+      const int64_t tiles = cdiv(L.Cin, GEMM_BM) * cdiv(L.f, L.f > 64 ? 128 : L.f) * L.seg_count;
+      int ksplit = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(148 * 6, tiles), cdiv(rows, 256)));
+      int rps = (int)cdiv(cdiv(rows, ksplit), GEMM_BK) * GEMM_BK;
+      ksplit = (int)cdiv(rows, rps);
+      a.rows_per_split = rps;
+      a.a_vec = (L.Cin % 4 == 0) && al16(A);
+      a.g_vec = (L.Cout % 4 == 0) && (L.f % 4 == 0) && al16(gz);
+      int rc = launch_wgrad(a, L.f, ksplit, st, layer_flops(L, B));
+      if (rc) return rc;
+    }
+    // dgrad
+    if (m.tensors[L.in_t].needs_grad) {
+      RowGemmArgs a;
+      a.A = gz; a.lda = L.Cout; a.M = (int)rows; a.P = L.P;
+      a.segs = m.segs_dev + L.seg_begin; a.nseg = L.seg_count;
+      a.mode = 1; a.Kfix = 0;
+      a.C = grad_ptr(m, L.in_t); a.ldc = L.Cin; a.c_col0 = 0; a.N = L.Cin;
+      a.accumulate = ginit[L.in_t];
+      a.stats = nullptr; a.stats_ld = 0;
+      a.a_vec = (L.Cout % 4 == 0) && (L.f % 4 == 0) && al16(gz);
+      a.b_vec = (L.Cin % 4 == 0) && al16(m.ws + L.wt_off) && (((size_t)L.Cin * L.f) % 4 == 0);
+      int rc = launch_rowgemm(a, st, "dgrad", layer_flops(L, B));
+      if (rc) return rc;
+      ginit[L.in_t] = 1;
+    }
+  }
+  return HYP_OK;
+}
+
+}  // namespace hyp
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int hyp_version(void) { return HYP_ABI_VERSION; }
+const char* hyp_last_error(void) { return g_last_error.c_str(); }
+int64_t hyp_launch_count(int reset) {
+  const int64_t v = g_launch_count;
+  if (reset) g_launch_count = 0;
+  return v;
+}
+
+int hyp_profile_enable(int on) {
+  g_prof.clear();
+  g_prof.on = on != 0;
+  return HYP_OK;
+}
+
+// aggregates all records per kernel tag (synchronises the device); idx enumerates tags
+int hyp_profile_get(int idx, char name[64], double* total_ms, int64_t* launches, double* flops, double* bytes) {
+  HYP_CHECK_ARG(name && total_ms && launches && flops && bytes, "null argument");
+  if (idx < 0 || idx >= (int)g_prof.names.size()) return fail(HYP_E_INVALID, "hyp_profile_get: index out of range");
+  HYP_CUDA(cudaDeviceSynchronize());
+  double ms = 0, fl = 0, by = 0;
+  int64_t n = 0;
+  for (const ProfRec& r : g_prof.recs) {
+    if (r.tag != idx) continue;
+    float t = 0.f;
+    HYP_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    ms += t; fl += r.flops; by += r.bytes; n++;
+  }
+  strncpy(name, g_prof.names[idx].c_str(), 63);
+  name[63] = 0;
+  *total_ms = ms; *launches = n; *flops = fl; *bytes = by;
+  return HYP_OK;
+}
+
+int hyp_model_create(const hyp_model_desc* desc, hyp_model** out) {
+  HYP_CHECK_ARG(desc && out, "null argument");
+  HYP_CHECK_ARG(desc->kind == HYP_MODEL_HYPELCNN, "unknown model kind");
+  HYP_CHECK_ARG(desc->patch >= 1 && desc->patch % 2 == 1 && desc->patch <= 15, "patch must be odd, 1..15");
+  HYP_CHECK_ARG(desc->channels >= 1 && desc->classes >= 2 && desc->classes <= 255, "channels/classes out of range");
+  HYP_CHECK_ARG(desc->filter_count >= 8 && desc->spectral_levels >= 1 && desc->spatial_levels >= 1,
+                "filter_count/levels out of range");
+  HYP_CHECK_ARG(desc->max_batch >= 1, "max_batch must be positive");
+  HYP_CHECK_ARG(desc->drop_out_ratio >= 0.f && desc->drop_out_ratio < 1.f, "drop_out_ratio in [0,1)");
+  if (desc->precision_mode != HYP_PRECISION_FP32)
+    return fail(HYP_E_UNSUPPORTED, "hyp_model_create: precision mode not built yet");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(HYP_E_CUDA, "hyp_model_create: no CUDA device (this library has no CPU fallback)");
+  std::unique_ptr<hyp_model> m(new hyp_model());
+  m->d = *desc;
+  int rc = build_hypelcnn(*m);
+  if (rc) return rc;
+  rc = layout(*m);
+  if (rc) return rc;
+  if ((int64_t)m->d.max_batch * m->d.patch * m->d.patch > (int64_t)INT32_MAX / 2)
+    return fail(HYP_E_INVALID, "hyp_model_create: max_batch too large");
+  *out = m.release();
+  return HYP_OK;
+}
+
+void hyp_model_destroy(hyp_model* m) {
+  if (!m) return;
+  for (void* p : m->owned) cudaFree(p);
+  if (m->segs_dev) cudaFree(m->segs_dev);
+  if (m->tjobs_dev) cudaFree(m->tjobs_dev);
+  if (m->tmap_dev) cudaFree(m->tmap_dev);
+  delete m;
+}
+
+int hyp_model_sizes(const hyp_model* m, int64_t* n_params, int64_t* n_bn_state, int64_t* workspace_bytes,
+                    int32_t* n_variables) {
+  HYP_CHECK_ARG(m, "null model");
+  if (n_params) *n_params = m->n_params;
+  if (n_bn_state) *n_bn_state = m->n_state;
+  if (workspace_bytes) *workspace_bytes = (int64_t)m->ws_bytes;
+  if (n_variables) *n_variables = (int32_t)m->vars.size();
+  return HYP_OK;
+}
+
+int hyp_model_variable(const hyp_model* m, int idx, char name[128], int32_t* kind, int64_t* offset, int32_t shape[4],
+                       int32_t* rank) {
+  HYP_CHECK_ARG(m && name && kind && offset && shape && rank, "null argument");
+  HYP_CHECK_ARG(idx >= 0 && idx < (int)m->vars.size(), "variable index out of range");
+  const Variable& v = m->vars[idx];
+  strncpy(name, v.name.c_str(), 127);
+  name[127] = 0;
+  *kind = v.kind;
+  *offset = v.offset;
+  for (int i = 0; i < 4; i++) shape[i] = v.shape[i];
+  *rank = v.rank;
+  return HYP_OK;
+}
+
+int hyp_model_bind(hyp_model* m, float* params, float* grads, float* bn_state, void* workspace, size_t ws_bytes) {
+  HYP_CHECK_ARG(m && params && grads && bn_state && workspace, "null argument");
+  HYP_CHECK_ARG(ws_bytes >= m->ws_bytes, "workspace too small");
+  HYP_CHECK_ARG(al16(params) && al16(grads) && al16(bn_state) && ((uintptr_t)workspace & 255) == 0,
+                "buffers must be 16-byte (workspace 256-byte) aligned");
+  m->params = params;
+  m->grads = grads;
+  m->state = bn_state;
+  m->ws = static_cast<char*>(workspace);
+  m->last_B = -1;
+  return bind_tables(*m);
+}
+
+int hyp_model_forward(hyp_model* m, const float* x, int64_t B, int is_training, int update_moving,
+                      uint64_t dropout_seed, float* logits, float* recon, void* stream) {
+  HYP_CHECK_ARG(m && x, "null argument");
+  if (!m->segs_bound) return fail(HYP_E_STATE, "hyp_model_forward: call hyp_model_bind first");
+  HYP_CHECK_ARG(B >= 1 && B <= m->d.max_batch, "B out of range");
+  HYP_CHECK_ARG(!is_training || B >= 2, "training-mode BatchNorm needs B >= 2");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = forward_impl(*m, x, B, is_training != 0, update_moving != 0, dropout_seed, st);
+  if (rc) return rc;
+  m->last_B = B;
+  m->last_training = is_training != 0;
+  m->last_seed = dropout_seed;
+  m->last_x = x;
+  if (logits)
+    HYP_CUDA(cudaMemcpyAsync(logits, act_ptr(*m, m->logits_t, x), (size_t)B * m->d.classes * sizeof(float),
+                             cudaMemcpyDeviceToDevice, st));
+  if (recon) {
+    if (!is_training) return fail(HYP_E_INVALID, "hyp_model_forward: recon only exists in the training graph");
+    const size_t D = (size_t)m->d.patch * m->d.patch * m->d.channels;
+    HYP_CUDA(cudaMemcpyAsync(recon, act_ptr(*m, m->recon_t, x), (size_t)B * D * sizeof(float),
+                             cudaMemcpyDeviceToDevice, st));
+  }
+  return HYP_OK;
+}
+
+int hyp_model_loss(hyp_model* m, const float* logits, const float* recon, const float* x, const uint8_t* labels,
+                   int64_t B, float* per_sample_loss, void* stream) {
+  HYP_CHECK_ARG(m && logits && labels && per_sample_loss, "null argument");
+  HYP_CHECK_ARG(!recon || x, "x is required with recon");
+  if (!m->ws) return fail(HYP_E_STATE, "hyp_model_loss: call hyp_model_bind first");
+  HYP_CHECK_ARG(B >= 1 && B <= m->d.max_batch, "B out of range");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* ce = reinterpret_cast<float*>(m->ws + m->ce_off);
+  double* mse_acc = reinterpret_cast<double*>(m->ws + m->mse_off);
+  HYP_CUDA(cudaMemsetAsync(mse_acc, 0, 256, st));
+  ce_loss_kernel<<<(unsigned)cdiv(B * 32, 256), 256, 0, st>>>(logits, labels, B, m->d.classes, ce, nullptr, 0.f);
+  HYP_LAUNCHED();
+  const int64_t D = (int64_t)m->d.patch * m->d.patch * m->d.channels;
+  if (recon) {
+    mse_kernel<<<ew_grid(B * D), 256, 0, st>>>(recon, x, B * D, mse_acc, nullptr, 0.f);
+    HYP_LAUNCHED();
+  }
+  loss_finalize_kernel<<<1, 256, 0, st>>>(ce, B, recon ? mse_acc : nullptr, (double)(B * D), nullptr, per_sample_loss);
+  HYP_LAUNCHED();
+  return HYP_OK;
+}
+
+int hyp_model_loss_backward(hyp_model* m, const float* x, const uint8_t* labels, int64_t B, float* loss_out,
+                            void* stream) {
+  HYP_CHECK_ARG(m && x && labels && loss_out, "null argument");
+  if (!m->segs_bound) return fail(HYP_E_STATE, "hyp_model_loss_backward: call hyp_model_bind first");
+  if (!m->last_training || m->last_B != B || m->last_x != x)
+    return fail(HYP_E_STATE, "hyp_model_loss_backward: needs the preceding hyp_model_forward(is_training=1) on the same x/B");
+  return backward_impl(*m, x, labels, B, loss_out, static_cast<cudaStream_t>(stream));
+}
+
+int hyp_adam_step(float* params, const float* grads, float* mbuf, float* vbuf, int64_t n, float lr, float b1,
+                  float b2, float eps, int64_t t, float grad_scale, void* stream) {
+  HYP_CHECK_ARG(params && grads && mbuf && vbuf, "null argument");
+  HYP_CHECK_ARG(n >= 0 && t >= 1, "n >= 0 and t >= 1 required");
+  if (n == 0) return HYP_OK;
+  const double lr_t = (double)lr * std::sqrt(1.0 - std::pow((double)b2, (double)t)) / (1.0 - std::pow((double)b1, (double)t));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PROF("adam_kernel", 28.0 * n,
+       (adam_kernel<<<ew_grid(n), 256, 0, st>>>(params, grads, mbuf, vbuf, n, (float)lr_t, 1.f - b1, 1.f - b2, eps,
+                                                grad_scale)));
+  return HYP_OK;
+}
+
+int hyp_argmax_confusion(const float* logits, const uint8_t* labels, int64_t B, int classes, uint8_t* pred,
+                         int32_t* confusion, void* stream) {
+  HYP_CHECK_ARG(logits && (pred || confusion), "null argument");
+  HYP_CHECK_ARG(classes >= 1 && classes <= 256 && B >= 0, "classes/B out of range");
+  HYP_CHECK_ARG(!confusion || labels, "labels are required to accumulate a confusion matrix");
+  if (B == 0) return HYP_OK;
+  argmax_confusion_kernel<<<(unsigned)cdiv(B, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits, labels, B, classes, pred, confusion);
+  HYP_LAUNCHED();
+  return HYP_OK;
+}
+
+int hyp_scatter_class_map(const uint8_t* pred, const int32_t* targets_xy, int64_t N, int H, int W,
+                          uint8_t* class_map, void* stream) {
+  HYP_CHECK_ARG(pred && targets_xy && class_map && H > 0 && W > 0 && N >= 0, "bad argument");
+  if (N == 0) return HYP_OK;
+  scatter_class_map_kernel<<<(unsigned)cdiv(N, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      pred, targets_xy, N, H, W, class_map);
+  HYP_LAUNCHED();
+  return HYP_OK;
+}
+
+int hyp_scene_minmax(const void* cube, int dtype, int H, int W, int C, float* min_out, float* max_out, void* stream) {
+  HYP_CHECK_ARG(cube && min_out && max_out && H > 0 && W > 0 && C > 0, "bad argument");
+  HYP_CHECK_ARG(dtype == HYP_DT_F32 || dtype == HYP_DT_U16, "dtype must be f32 or u16");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned int* bits = nullptr;
+  HYP_CUDA(cudaMallocAsync(&bits, 2 * (size_t)C * sizeof(unsigned int), st));
+  HYP_CUDA(cudaMemsetAsync(bits, 0xff, (size_t)C * sizeof(unsigned int), st));
+  HYP_CUDA(cudaMemsetAsync(bits + C, 0x00, (size_t)C * sizeof(unsigned int), st));
+  const int64_t pixels = (int64_t)H * W;
+  const int ppb = (int)std::max<int64_t>(16, cdiv(pixels, 148 * 8));
+  const unsigned grid = (unsigned)cdiv(pixels, ppb);
+  const int threads = C >= 128 ? 128 : (C >= 64 ? 64 : 32);
+  if (dtype == HYP_DT_U16)
+    scene_min_kernel<unsigned short><<<grid, threads, 0, st>>>((const unsigned short*)cube, pixels, C, ppb, bits);
+  else
+    scene_min_kernel<float><<<grid, threads, 0, st>>>((const float*)cube, pixels, C, ppb, bits);
+  HYP_LAUNCHED();
+  decode_ordered_kernel<<<(unsigned)cdiv(C, 128), 128, 0, st>>>(bits, C, min_out);
+  HYP_LAUNCHED();
+  if (dtype == HYP_DT_U16)
+    scene_max_kernel<unsigned short><<<grid, threads, 0, st>>>((const unsigned short*)cube, pixels, C, ppb, min_out,
+                                                               bits + C);
+  else
+    scene_max_kernel<float><<<grid, threads, 0, st>>>((const float*)cube, pixels, C, ppb, min_out, bits + C);
+  HYP_LAUNCHED();
+  decode_ordered_kernel<<<(unsigned)cdiv(C, 128), 128, 0, st>>>(bits + C, C, max_out);
+  HYP_LAUNCHED();
+  HYP_CUDA(cudaFreeAsync(bits, st));
+  return HYP_OK;
+}
+
+int hyp_gather_patches(const void* casi, int casi_dtype, int Hc, int Wc, int C_hsi, const float* casi_min,
+                       const float* casi_max, const float* lidar, int Hl, int Wl, const float* lidar_minmax,
+                       int neighborhood, int mode, const int32_t* targets_xy, int64_t N, float* out, int out_ld,
+                       void* stream) {
+  HYP_CHECK_ARG(casi && targets_xy && out, "null argument");
+  HYP_CHECK_ARG(casi_dtype == HYP_DT_F32 || casi_dtype == HYP_DT_U16, "casi dtype must be f32 or u16");
+  HYP_CHECK_ARG(Hc > 0 && Wc > 0 && C_hsi > 0 && neighborhood >= 0 && N >= 0, "bad shape");
+  HYP_CHECK_ARG((casi_min == nullptr) == (casi_max == nullptr), "casi_min and casi_max go together");
+  HYP_CHECK_ARG(mode == HYP_GATHER_SAME_RES || mode == HYP_GATHER_GRSS2018, "unknown gather mode");
+  HYP_CHECK_ARG(!lidar || (Hl > 0 && Wl > 0), "bad lidar shape");
+  HYP_CHECK_ARG(mode != HYP_GATHER_GRSS2018 || lidar, "GRSS2018 mode needs the LiDAR raster");
+  HYP_CHECK_ARG(out_ld >= C_hsi + (lidar ? 1 : 0), "out_ld too small");
+  HYP_CHECK_ARG(neighborhood <= Hc && neighborhood <= Wc, "neighborhood larger than the scene");
+  HYP_CHECK_ARG(N <= INT32_MAX, "too many targets for one call");
+  if (N == 0) return HYP_OK;
+  GatherArgs a;
+  a.casi = casi; a.casi_u16 = casi_dtype == HYP_DT_U16; a.Hc = Hc; a.Wc = Wc; a.C = C_hsi;
+  a.cmin = casi_min; a.cmax = casi_max; a.lidar = lidar; a.Hl = Hl; a.Wl = Wl; a.lminmax = lidar_minmax;
+  a.nb = neighborhood; a.mode = mode; a.xy = targets_xy; a.N = N; a.out = out; a.out_ld = out_ld;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const double S2 = (double)(2 * neighborhood + 1) * (2 * neighborhood + 1);
+  PROF("gather_kernel", (double)N * S2 * (4.0 * out_ld + (casi_dtype == HYP_DT_U16 ? 2.0 : 4.0) * C_hsi + (lidar ? 4.0 : 0.0)),
+       (gather_kernel<<<(unsigned)N, 256, 0, st>>>(a)));
+  return HYP_OK;
+}
+
+int hyp_model_debug_tensor(hyp_model* m, const char* name, int what, float** ptr, int64_t* numel) {
+  HYP_CHECK_ARG(m && name && ptr && numel, "null argument");
+  if (!m->ws || m->last_B < 0) return fail(HYP_E_STATE, "hyp_model_debug_tensor: no forward has run");
+  const std::string n(name);
+  if (what == 1) {
+    for (Layer& L : m->layers)
+      if (L.scope == n) {
+        *ptr = reinterpret_cast<float*>(m->ws + L.z_off);
+        *numel = m->last_B * L.rows_per_sample * L.Cout;
+        return HYP_OK;
+      }
+    return fail(HYP_E_INVALID, "hyp_model_debug_tensor: unknown layer " + n);
+  }
+  auto it = m->tensor_by_name.find(n);
+  if (it == m->tensor_by_name.end() || m->tensors[it->second].external)
+    return fail(HYP_E_INVALID, "hyp_model_debug_tensor: unknown tensor " + n);
+  const Tensor& t = m->tensors[it->second];
+  *ptr = reinterpret_cast<float*>(m->ws + (what == 2 ? t.g_off : t.a_off));
+  *numel = m->last_B * t.rows_per_sample * t.C;
+  return HYP_OK;
+}
+
+int hyp_model_dropout_mask(hyp_model* m, const char* layer_scope, uint64_t seed, int64_t B, uint8_t* mask_out,
+                           void* stream) {
+  HYP_CHECK_ARG(m && layer_scope && mask_out && B >= 1, "bad argument");
+  for (Layer& L : m->layers)
+    if (L.scope == layer_scope && L.dropout) {
+      const int64_t n = B * L.rows_per_sample * L.Cout;
+      dropout_mask_kernel<<<(unsigned)cdiv(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+          seed, L.drop_stream, n, 1.f - m->d.drop_out_ratio, mask_out);
+      HYP_LAUNCHED();
+      return HYP_OK;
+    }
+  return fail(HYP_E_INVALID, std::string("hyp_model_dropout_mask: no dropout layer ") + layer_scope);
+}
+
+}  // extern "C"

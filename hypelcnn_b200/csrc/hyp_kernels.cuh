@@ -1,0 +1,410 @@
+// HBM-bound kernels around the GEMMs: BatchNorm (training statistics, apply, backward),
+// LeakyReLU / sigmoid / dropout / channel-resampled residuals, losses, Adam, argmax +
+// confusion, scene min-max and the patch gather.
+#pragma once
+#include "hyp_common.cuh"
+
+namespace hyp {
+
+// ------------------------------------------------------------------------------------------
+// BatchNorm statistics -> (mean, rstd); slim batch_norm: biased variance to normalise,
+// Bessel-corrected variance into the moving average.
+// stats: double [2][C] = (sum z, sum z^2) over `rows` rows.
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, int C, double rows, float eps, float decay,
+                                   float* __restrict__ moving_mean, float* __restrict__ moving_var,
+                                   float* __restrict__ mean_out, float* __restrict__ rstd_out, int is_training,
+                                   int update_moving) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (is_training) {
+    const double mean = stats[c] / rows;
+    double var = stats[C + c] / rows - mean * mean;
+    if (var < 0) var = 0;
+    const float meanf = (float)mean, varf = (float)var;
+    mean_out[c] = meanf;
+    rstd_out[c] = rsqrtf(varf + eps);
+    // rsqrtf is 2 ulp; refine once so the result matches 1/sqrt in fp32 to <= 1 ulp
+    {
+      const float x = varf + eps;
+      float r = rstd_out[c];
+      r = r * (1.5f - 0.5f * x * r * r);
+      rstd_out[c] = r;
+    }
+    if (update_moving) {
+      const double unbiased = var * (rows / fmax(rows - 1.0, 1.0));
+      moving_mean[c] = moving_mean[c] * decay + meanf * (1.f - decay);
+      moving_var[c] = moving_var[c] * decay + (float)unbiased * (1.f - decay);
+    }
+  } else {
+    mean_out[c] = moving_mean[c];
+    const float x = moving_var[c] + eps;
+    float r = rsqrtf(x);
+    r = r * (1.5f - 0.5f * x * r * r);
+    rstd_out[c] = r;
+  }
+}
+
+__device__ __forceinline__ float act_fwd(float y, int act, float alpha) {
+  if (act == ACT_LRELU) return fmaxf(y, alpha * y);
+  if (act == ACT_SIGMOID) return 1.f / (1.f + __expf(-y));
+  return y;
+}
+
+struct ApplyArgs {
+  const float* z;       // [rows, C] pre-BN
+  const float* mean;    // [C]
+  const float* rstd;    // [C]
+  const float* beta;    // [C]
+  float* out;           // [rows, C]
+  int64_t rows;
+  int C;
+  int act;
+  float alpha;
+  float keep;           // dropout keep_prob; 1 -> no dropout
+  uint64_t seed;
+  uint32_t stream_id;
+  const float* res0;    // residual sources [rows, C0] (nullable)
+  const int* idx0;      // nullable -> identity
+  int C0;
+  const float* res1;
+  const int* idx1;
+  int C1;
+};
+
+// out = dropout(act(bn(z))) + res0[:, idx0] + res1[:, idx1]
+__global__ void bn_apply_fwd_kernel(const ApplyArgs p) {
+  const int64_t total = p.rows * p.C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / p.C;
+    const int c = (int)(i - m * p.C);
+    float v = (p.z[i] - p.mean[c]) * p.rstd[c] + p.beta[c];
+    v = act_fwd(v, p.act, p.alpha);
+    if (p.keep < 1.f) v = (philox_uniform(p.seed, p.stream_id, (uint64_t)i) < p.keep) ? v / p.keep : 0.f;
+    if (p.res0) v += p.res0[m * p.C0 + (p.idx0 ? p.idx0[c] : c)];
+    if (p.res1) v += p.res1[m * p.C1 + (p.idx1 ? p.idx1[c] : c)];
+    p.out[i] = v;
+  }
+}
+
+struct BnBwdArgs {
+  const float* gout;  // [rows, C] gradient w.r.t. the layer's output tensor
+  const float* z;     // [rows, C] pre-BN
+  const float* mean;
+  const float* rstd;
+  const float* beta;
+  int64_t rows;
+  int C;
+  int act;
+  float alpha;
+  float keep;
+  uint64_t seed;
+  uint32_t stream_id;
+  double* sums;        // [2][C]: sum g_y, sum g_y*zhat           (reduce)
+  const float* s1;     // [C] mean g_y                            (apply)
+  const float* s2;     // [C] mean g_y*zhat                       (apply)
+  float* gz;           // [rows, C]                               (apply)
+};
+
+__device__ __forceinline__ float bn_gy(const BnBwdArgs& p, int64_t i, int c, float& zhat) {
+  zhat = (p.z[i] - p.mean[c]) * p.rstd[c];
+  const float y = zhat + p.beta[c];
+  float g = p.gout[i];
+  if (p.keep < 1.f) g = (philox_uniform(p.seed, p.stream_id, (uint64_t)i) < p.keep) ? g / p.keep : 0.f;
+  if (p.act == ACT_LRELU) {
+    g = (y > 0.f) ? g : g * p.alpha;
+  } else if (p.act == ACT_SIGMOID) {
+    const float s = 1.f / (1.f + __expf(-y));
+    g = g * s * (1.f - s);
+  }
+  return g;
+}
+
+// block = 32 columns x 8 row lanes; grid = (ceil(C/32), row chunks)
+__global__ void bn_bwd_reduce_kernel(const BnBwdArgs p, int rows_per_block) {
+  __shared__ float sh1[8][33], sh2[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = min((int64_t)p.rows, r0 + rows_per_block);
+  float a1 = 0.f, a2 = 0.f;
+  if (c < p.C) {
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+      float zhat;
+      const float g = bn_gy(p, r * p.C + c, c, zhat);
+      a1 += g;
+      a2 += g * zhat;
+    }
+  }
+  sh1[ty][tx] = a1;
+  sh2[ty][tx] = a2;
+  __syncthreads();
+  if (ty == 0 && c < p.C) {
+#pragma unroll
+    for (int i = 1; i < 8; i++) { a1 += sh1[i][tx]; a2 += sh2[i][tx]; }
+    atomicAdd(&p.sums[c], (double)a1);
+    atomicAdd(&p.sums[p.C + c], (double)a2);
+  }
+}
+
+// sums (double) -> s1, s2 = means (float); gbeta = sum g_y
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, int C, double rows, float* __restrict__ s1,
+                                       float* __restrict__ s2, float* __restrict__ gbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  s1[c] = (float)(sums[c] / rows);
+  s2[c] = (float)(sums[C + c] / rows);
+  gbeta[c] = (float)sums[c];
+}
+
+// gz = rstd * (g_y - mean(g_y) - zhat * mean(g_y * zhat))
+__global__ void bn_bwd_apply_kernel(const BnBwdArgs p) {
+  const int64_t total = p.rows * p.C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % p.C);
+    float zhat;
+    const float g = bn_gy(p, i, c, zhat);
+    p.gz[i] = p.rstd[c] * (g - p.s1[c] - zhat * p.s2[c]);
+  }
+}
+
+// residual backward: gsrc[m, c'] (+)= sum_{j in [lo[c'], hi[c'])} gout[m, j]   (lo == NULL: identity)
+__global__ void resid_bwd_kernel(const float* __restrict__ gout, int Cout, float* __restrict__ gsrc, int Csrc,
+                                 const int* __restrict__ lo, const int* __restrict__ hi, int64_t rows,
+                                 int accumulate) {
+  const int64_t total = rows * Csrc;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / Csrc;
+    const int c = (int)(i - m * Csrc);
+    float v = 0.f;
+    if (lo) {
+      for (int j = lo[c]; j < hi[c]; j++) v += gout[m * Cout + j];
+    } else {
+      v = gout[m * Cout + c];
+    }
+    gsrc[i] = accumulate ? gsrc[i] + v : v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// softmax cross-entropy per row (one warp per row) + gradient (softmax - onehot) * gscale
+__global__ void ce_loss_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ labels, int64_t B,
+                               int classes, float* __restrict__ ce_out, float* __restrict__ glogits, float gscale) {
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const float* lp = logits + row * classes;
+  float mx = -INFINITY;
+  for (int c = lane; c < classes; c += 32) mx = fmaxf(mx, lp[c]);
+  mx = warp_max(mx);
+  float se = 0.f;
+  for (int c = lane; c < classes; c += 32) se += expf(lp[c] - mx);
+  se = warp_sum(se);
+  const float lse = mx + logf(se);
+  const int lab = labels[row];
+  if (lane == 0) ce_out[row] = lse - lp[lab];
+  if (glogits) {
+    for (int c = lane; c < classes; c += 32) {
+      const float sm = expf(lp[c] - lse);
+      glogits[row * classes + c] = (sm - (c == lab ? 1.f : 0.f)) * gscale;
+    }
+  }
+}
+
+// sum (recon - x)^2 -> acc (double); grecon = 2 (recon - x) * gscale
+__global__ void mse_kernel(const float* __restrict__ recon, const float* __restrict__ x, int64_t n,
+                           double* __restrict__ acc, float* __restrict__ grecon, float gscale) {
+  __shared__ float sh[32];
+  float s = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = recon[i] - x[i];
+    s += d * d;
+    if (grecon) grecon[i] = 2.f * d * gscale;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    if (threadIdx.x == 0) atomicAdd(acc, (double)s);
+  }
+}
+
+// loss_out = {mean ce + mse, mean ce, mse}; per_sample[b] = ce[b] + mse (nullable)
+__global__ void loss_finalize_kernel(const float* __restrict__ ce, int64_t B, const double* __restrict__ mse_acc,
+                                     double mse_count, float* __restrict__ loss_out,
+                                     float* __restrict__ per_sample) {
+  __shared__ double sh[256];
+  const double mse = (mse_acc && mse_count > 0) ? *mse_acc / mse_count : 0.0;
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < B; i += blockDim.x) {
+    s += (double)ce[i];
+    if (per_sample) per_sample[i] = ce[i] + (float)mse;
+  }
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && loss_out) {
+    const double mce = sh[0] / (double)B;
+    loss_out[0] = (float)(mce + mse);
+    loss_out[1] = (float)mce;
+    loss_out[2] = (float)mse;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// TF1 ApplyAdam on a flat buffer
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr_t, float one_minus_b1, float one_minus_b2,
+                            float eps, float gscale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float mi = m[i] + (gi - m[i]) * one_minus_b1;
+    const float vi = v[i] + (gi * gi - v[i]) * one_minus_b2;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
+// tf.argmax (first maximum) + confusion[label, pred] += 1
+__global__ void argmax_confusion_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ labels,
+                                        int64_t B, int classes, uint8_t* __restrict__ pred,
+                                        int32_t* __restrict__ confusion) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  const float* lp = logits + i * classes;
+  float best = lp[0];
+  int bi = 0;
+  for (int c = 1; c < classes; c++) {
+    const float v = lp[c];
+    if (v > best) { best = v; bi = c; }
+  }
+  if (pred) pred[i] = (uint8_t)bi;
+  if (confusion && labels) atomicAdd(&confusion[(int)labels[i] * classes + bi], 1);
+}
+
+__global__ void scatter_class_map_kernel(const uint8_t* __restrict__ pred, const int32_t* __restrict__ xy,
+                                         int64_t N, int H, int W, uint8_t* __restrict__ map) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int x = xy[2 * i], y = xy[2 * i + 1];
+  if ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H) map[(size_t)y * W + x] = pred[i];
+}
+
+__global__ void dropout_mask_kernel(uint64_t seed, uint32_t stream_id, int64_t n, float keep,
+                                    uint8_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = philox_uniform(seed, stream_id, (uint64_t)i) < keep ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// scene min / max(value - min): two passes over the cube, channel-coalesced
+template <typename T>
+__global__ void scene_min_kernel(const T* __restrict__ cube, int64_t pixels, int C, int pixels_per_block,
+                                 unsigned int* __restrict__ min_bits) {
+  // float order-preserving encoding so atomicMin on uint works for non-negative and negative values
+  const int64_t p0 = (int64_t)blockIdx.x * pixels_per_block;
+  const int64_t p1 = min(pixels, p0 + pixels_per_block);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mn = INFINITY;
+    for (int64_t px = p0; px < p1; px++) mn = fminf(mn, (float)cube[px * C + c]);
+    unsigned int b = __float_as_uint(mn);
+    b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    atomicMin(&min_bits[c], b);
+  }
+}
+template <typename T>
+__global__ void scene_max_kernel(const T* __restrict__ cube, int64_t pixels, int C, int pixels_per_block,
+                                 const float* __restrict__ mn, unsigned int* __restrict__ max_bits) {
+  const int64_t p0 = (int64_t)blockIdx.x * pixels_per_block;
+  const int64_t p1 = min(pixels, p0 + pixels_per_block);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mx = -INFINITY;
+    const float lo = mn[c];
+    for (int64_t px = p0; px < p1; px++) mx = fmaxf(mx, (float)cube[px * C + c] - lo);
+    unsigned int b = __float_as_uint(mx);
+    b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    atomicMax(&max_bits[c], b);
+  }
+}
+__global__ void decode_ordered_kernel(const unsigned int* __restrict__ bits, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  unsigned int b = bits[c];
+  b = (b & 0x80000000u) ? (b & 0x7fffffffu) : ~b;
+  out[c] = __uint_as_float(b);
+}
+
+// ------------------------------------------------------------------------------------------
+// patch gather.  numpy "symmetric" padding == reflect with the edge repeated.
+__device__ __forceinline__ int reflect_sym(int i, int n) {
+  if (i < 0) i = -i - 1;
+  if (i >= n) i = 2 * n - 1 - i;
+  return i;
+}
+
+struct GatherArgs {
+  const void* casi;
+  int casi_u16;
+  int Hc, Wc, C;
+  const float* cmin;
+  const float* cmax;
+  const float* lidar;
+  int Hl, Wl;
+  const float* lminmax;
+  int nb, mode;
+  const int32_t* xy;
+  int64_t N;
+  float* out;
+  int out_ld;
+};
+
+// one block per patch; threads sweep (pixel, channel) with channel fastest -> coalesced
+__global__ void gather_kernel(const GatherArgs p) {
+  const int64_t n = blockIdx.x;
+  const int S = 2 * p.nb + 1;
+  const int x = p.xy[2 * n], y = p.xy[2 * n + 1];
+  int bx = x, by = y;
+  if (p.mode == HYP_GATHER_GRSS2018) {  // loader/GRSS2018DataLoader.py:23-29 (int() truncation)
+    bx = x / 2 + p.nb - p.nb / 2;
+    by = y / 2 + p.nb - p.nb / 2;
+  }
+  const int per_pixel = p.out_ld;
+  const int total = S * S * per_pixel;
+  float* op = p.out + (size_t)n * total;
+  const float lmin = p.lminmax ? p.lminmax[0] : 0.f, lmax = p.lminmax ? p.lminmax[1] : 1.f;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int pix = i / per_pixel, c = i - pix * per_pixel;
+    const int py = pix / S, px = pix - py * S;
+    float v = 0.f;
+    if (c < p.C) {
+      const int oy = (p.mode == HYP_GATHER_GRSS2018) ? py / 2 : py;
+      const int ox = (p.mode == HYP_GATHER_GRSS2018) ? px / 2 : px;
+      const int ry = reflect_sym(by + oy - p.nb, p.Hc), rx = reflect_sym(bx + ox - p.nb, p.Wc);
+      const size_t off = ((size_t)ry * p.Wc + rx) * p.C + c;
+      if (p.casi_u16) {
+        const unsigned short raw = reinterpret_cast<const unsigned short*>(p.casi)[off];
+        if (p.cmin) {
+          const unsigned short sh = (unsigned short)(raw - (unsigned short)p.cmin[c]);
+          v = __fdiv_rn((float)sh, p.cmax[c]);
+        } else {
+          v = (float)raw;
+        }
+      } else {
+        const float raw = reinterpret_cast<const float*>(p.casi)[off];
+        v = p.cmin ? __fdiv_rn(__fsub_rn(raw, p.cmin[c]), p.cmax[c]) : raw;
+      }
+    } else if (c == p.C && p.lidar) {
+      const int ry = reflect_sym(y + py - p.nb, p.Hl), rx = reflect_sym(x + px - p.nb, p.Wl);
+      const float raw = p.lidar[(size_t)ry * p.Wl + rx];
+      v = p.lminmax ? __fdiv_rn(__fsub_rn(raw, lmin), lmax) : raw;
+    }
+    op[i] = v;
+  }
+}
+
+}  // namespace hyp

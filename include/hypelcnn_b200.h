@@ -1,0 +1,179 @@
+/*
+ * hypelcnn_b200 — C ABI of the B200-native HSI+LiDAR patch engine.
+ *
+ * The reference (aligokalppeker/hypelcnn) has no FFI: its plug-in boundary is four Python
+ * ABCs resolved by name (nnmodel/NNModel.py:4-12, importer/DataImporter.py:4-20,
+ * loader/DataLoader.py:5-47, common/common_nn_ops.py:23-42).  The Python classes in
+ * hypelcnn_b200/{nnmodel,importer,loader,common} keep those interfaces verbatim and call
+ * THIS library through ctypes; each entry point below names the reference code it
+ * replaces.  See INTEGRATION.md for the reference-side binding.
+ *
+ * Conventions
+ *  - every function returns 0 (HYP_OK) or a negative HYP_E_* code; never throws/aborts;
+ *    hyp_last_error() gives a thread-local message for the last failure on this thread.
+ *  - all data pointers are DEVICE pointers owned by the caller (torch.Tensor.data_ptr()),
+ *    fp32, NHWC, C-contiguous; `stream` is a cudaStream_t passed as void*.
+ *  - calls are asynchronous with respect to the host on `stream`.
+ *  - a hyp_model is bound to one device and used from one stream at a time.
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails
+ *    with HYP_E_CUDA.
+ */
+#ifndef HYPELCNN_B200_H
+#define HYPELCNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HYP_ABI_VERSION 1
+
+enum {
+  HYP_OK = 0,
+  HYP_E_INVALID = -1,     /* bad argument (shape, null pointer, range) */
+  HYP_E_CUDA = -2,        /* CUDA runtime error (message carries cudaGetErrorString) */
+  HYP_E_STATE = -3,       /* call order violated (e.g. backward without training forward) */
+  HYP_E_UNSUPPORTED = -4  /* valid request this build does not implement */
+};
+
+typedef struct hyp_model hyp_model;
+
+int hyp_version(void);
+const char* hyp_last_error(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Scene preparation + patch gather.
+ * Replaces BasicDataSet.__init__ normalisation (common/common_nn_ops.py:62-78),
+ * get_data_point_func (common/common_nn_ops.py:169-176), GRSS2018DataSet.get_data_point
+ * (loader/GRSS2018DataLoader.py:10-44) and the per-pixel Python loop of
+ * InMemoryImporter._get_data_with_labels (importer/InMemoryImporter.py:27-38).
+ * The scene stays UNPADDED and un-normalised in HBM; numpy's "symmetric" padding
+ * (common/common_nn_ops.py:55-60) is applied as index reflection inside the kernel.
+ * ------------------------------------------------------------------------------------- */
+enum { HYP_DT_F32 = 0, HYP_DT_U16 = 1 };
+enum { HYP_GATHER_SAME_RES = 0, HYP_GATHER_GRSS2018 = 1 };
+
+/* per-band min and max(value - min) over an [H,W,C] cube -> min_out[C], max_out[C] (float).
+ * max_out is the maximum of the SHIFTED data, exactly as the reference computes it. */
+int hyp_scene_minmax(const void* cube, int dtype, int H, int W, int C,
+                     float* min_out, float* max_out, void* stream);
+
+/* out[n, py, px, 0:C_hsi] = (casi[ry, rx, :] - casi_min) / casi_max   (IEEE division)
+ * out[n, py, px, C_hsi]   = (lidar[ly, lx] - lidar_min) / lidar_max   (if lidar != NULL)
+ * casi_min/casi_max NULL -> no normalisation.  targets_xy: int32 [N,2] = (x=column, y=row)
+ * in scene coordinates (LiDAR resolution in GRSS2018 mode).  out row stride = out_ld floats
+ * per pixel (>= C_hsi + has_lidar), extra channels are written as 0. */
+int hyp_gather_patches(const void* casi, int casi_dtype, int Hc, int Wc, int C_hsi,
+                       const float* casi_min, const float* casi_max,
+                       const float* lidar, int Hl, int Wl,
+                       const float* lidar_minmax /* device float[2] or NULL */,
+                       int neighborhood, int mode,
+                       const int32_t* targets_xy, int64_t N,
+                       float* out, int out_ld, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * NNModel engine.  Replaces the TF graph built by HYPELCNNModel.create_tensor_graph
+ * (nnmodel/HYPELCNNModel.py:34-99), get_loss_func (:101-112) and optimize_nn
+ * (common/common_nn_ops.py:208-240).
+ * ------------------------------------------------------------------------------------- */
+enum { HYP_MODEL_HYPELCNN = 0 };
+enum {
+  HYP_PRECISION_FP32 = 0,    /* fp32 FFMA everywhere (parity mode) */
+  HYP_PRECISION_3XTF32 = 1,  /* tcgen05 kind::tf32, hi/lo split, fp32-accurate */
+  HYP_PRECISION_BF16 = 2     /* tcgen05 kind::f16 bf16 inputs, fp32 accumulate */
+};
+
+typedef struct hyp_model_desc {
+  int32_t kind;             /* HYP_MODEL_* */
+  int32_t patch;            /* P: window edge = 2*neighborhood+1 */
+  int32_t channels;         /* C_in (HSI bands + LiDAR) */
+  int32_t classes;
+  int32_t filter_count;     /* alg_param "filter_count" */
+  int32_t spectral_levels;  /* "spectral_hierarchy_level" */
+  int32_t spatial_levels;   /* "spatial_hierarchy_level" */
+  int32_t degradation;      /* "degradation_coeff" */
+  int32_t use_residual;     /* "use_residual" */
+  int32_t precision_mode;   /* HYP_PRECISION_* */
+  int32_t max_batch;        /* largest B any call will pass */
+  int32_t reserved;
+  float lrelu_alpha;        /* "lrelu_alpha" */
+  float bn_decay;           /* "bn_decay" */
+  float bn_eps;             /* slim default 0.001 */
+  float drop_out_ratio;     /* "drop_out_ratio"; keep_prob = 1 - ratio (HYPELCNNModel.py:123) */
+} hyp_model_desc;
+
+int hyp_model_create(const hyp_model_desc* desc, hyp_model** out);
+void hyp_model_destroy(hyp_model* m);
+
+/* element counts of the flat buffers the caller must allocate (fp32 elements / bytes) */
+int hyp_model_sizes(const hyp_model* m, int64_t* n_params, int64_t* n_bn_state,
+                    int64_t* workspace_bytes, int32_t* n_variables);
+
+/* variable table; names are the reference's TF checkpoint names, e.g.
+ * "nn_core/conv_enc_0/weights" [1,1,145,120], "nn_core/fc_0/BatchNorm/moving_variance".
+ * kind: 0 weights, 1 beta (both in `params`/`grads`), 2 moving_mean, 3 moving_variance
+ * (both in `bn_state`).  offset is in fp32 elements inside the respective buffer. */
+int hyp_model_variable(const hyp_model* m, int idx, char name[128], int32_t* kind,
+                       int64_t* offset, int32_t shape[4], int32_t* rank);
+
+int hyp_model_bind(hyp_model* m, float* params, float* grads, float* bn_state,
+                   void* workspace, size_t workspace_bytes);
+
+/* forward.  is_training: BN uses batch statistics, dropout active (Philox keyed by
+ * dropout_seed), decoder branch runs; update_moving: also update BN moving statistics.
+ * logits [B,classes]; recon [B,P*P*C] (nullable; only produced when is_training). */
+int hyp_model_forward(hyp_model* m, const float* x, int64_t B, int is_training,
+                      int update_moving, uint64_t dropout_seed,
+                      float* logits, float* recon, void* stream);
+
+/* per-sample loss of get_loss_func: CE_i (+ scalar reconstruction MSE when recon != NULL).
+ * labels: uint8 class ids [B] (the argmax of the reference's one-hot rows). */
+int hyp_model_loss(hyp_model* m, const float* logits, const float* recon, const float* x,
+                   const uint8_t* labels, int64_t B, float* per_sample_loss, void* stream);
+
+/* loss = mean_B(per-sample loss) and d loss / d params into `grads`, for the batch of the
+ * immediately preceding hyp_model_forward(is_training=1) call (same x, same B).
+ * loss_out: device float[3] = {total, mean CE, reconstruction MSE}. */
+int hyp_model_loss_backward(hyp_model* m, const float* x, const uint8_t* labels, int64_t B,
+                            float* loss_out, void* stream);
+
+/* TF1 AdamOptimizer (ApplyAdam): lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m += (g-m)(1-b1);
+ * v += (g*g-v)(1-b2); p -= lr_t*m/(sqrt(v)+eps).  g = grads*grad_scale (1/world_size). */
+int hyp_adam_step(float* params, const float* grads, float* m, float* v, int64_t n,
+                  float lr, float b1, float b2, float eps, int64_t t, float grad_scale,
+                  void* stream);
+
+/* tf.argmax (lowest index on ties) + tf.math.confusion_matrix accumulation
+ * (common/common_nn_ops.py:246-262, :318).  labels/confusion nullable.
+ * confusion: int32 [classes,classes], rows = labels, += semantics. */
+int hyp_argmax_confusion(const float* logits, const uint8_t* labels, int64_t B, int classes,
+                         uint8_t* pred, int32_t* confusion, void* stream);
+
+/* perform_prediction's scatter (common/common_nn_ops.py:320-322): map[y*W + x] = pred. */
+int hyp_scatter_class_map(const uint8_t* pred, const int32_t* targets_xy, int64_t N,
+                          int H, int W, uint8_t* class_map, void* stream);
+
+/* ---- introspection used by the parity tests -------------------------------------------- */
+/* device pointer + element count of an internal tensor of the last forward/backward.
+ * what: 0 activation (post BN/act/residual) of tensor `name`, 1 pre-BN output of layer
+ * `name`, 2 gradient w.r.t. activation tensor `name`. */
+int hyp_model_debug_tensor(hyp_model* m, const char* name, int what, float** ptr, int64_t* numel);
+/* the 0/1 keep mask hyp_model_forward applies on dropout layer `layer_scope` for `seed` */
+int hyp_model_dropout_mask(hyp_model* m, const char* layer_scope, uint64_t seed, int64_t B,
+                           uint8_t* mask_out, void* stream);
+/* number of kernels launched by this library on this thread since the last reset */
+int64_t hyp_launch_count(int reset);
+/* per-kernel-class timing with CUDA events around every launch (off by default; bench.py
+ * turns it on for the timed region).  enable(1) clears previous records.  get(idx) sums the
+ * records of kernel tag idx (synchronises the device); returns HYP_E_INVALID past the end.
+ * flops = useful algorithmic FLOPs (GEMM kernels), bytes = algorithmic bytes (HBM kernels). */
+int hyp_profile_enable(int on);
+int hyp_profile_get(int idx, char name[64], double* total_ms, int64_t* launches, double* flops,
+                    double* bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYPELCNN_B200_H */

@@ -1,0 +1,283 @@
+"""GPU parity tests: the CUDA path (through the C ABI / ctypes) against the CPU oracle on the
+same seeded inputs.  Run on the B200 box with ``pytest -m gpu``."""
+import json
+import os
+
+import numpy
+import pytest
+import torch
+
+from oracle import dataset_ref as D
+from oracle import hypelcnn_ref as R
+from tests.util import ALG, ATOL, GOLD, RTOL, assert_close, assert_close_scaled, oracle_variables, synthetic_batch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def E():
+    from hypelcnn_b200 import engine
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return engine
+
+
+def dev(a):
+    return torch.as_tensor(a).cuda().contiguous()
+
+
+# ------------------------------------------------------------------------------------- gather
+def _gather_case(E, casi, lidar, n, pts, mode, normalize=True):
+    casi_d = dev(casi)
+    lidar_d = None if lidar is None else dev(lidar[:, :, 0].copy())
+    cmin = cmax = lmm = None
+    if normalize:
+        cmin, cmax = E.scene_minmax(casi_d)
+        if lidar is not None:
+            lmin, lmax = E.scene_minmax(lidar_d.view(lidar_d.shape[0], lidar_d.shape[1], 1))
+            lmm = torch.cat([lmin, lmax])
+    return E.gather_patches(casi_d, lidar_d, n, dev(pts.astype(numpy.int32)), cmin, cmax, lmm, mode).cpu().numpy()
+
+
+def test_gather_matches_reference_fixture_bit_exact(E):
+    g = numpy.load(os.path.join(GOLD, "dataset_golden.npz"))
+    got = _gather_case(E, g["same_casi"], g["same_lidar"], int(g["same_n"]), g["same_pts"], 0)
+    assert got.dtype == numpy.float32 and numpy.array_equal(got, g["same_patches"])
+    got = _gather_case(E, g["raw_casi"], g["same_lidar"], 1, g["same_pts"], 0, normalize=False)
+    assert numpy.array_equal(got, g["raw_patches"])
+    got = _gather_case(E, g["raw_casi"], None, 1, g["same_pts"], 0)
+    assert numpy.array_equal(got, g["hsi_patches"])
+    for n in (2, 3, 5):
+        got = _gather_case(E, g[f"g18_{n}_casi"], g[f"g18_{n}_lidar"], n, g[f"g18_{n}_pts"], 1)
+        assert numpy.array_equal(got, g[f"g18_{n}_patches"]), n
+
+
+def test_gather_vs_oracle_grss2013_shape(E):
+    rng = numpy.random.default_rng(1234)
+    H, W, C, n = 40, 61, 144, 3
+    casi = rng.integers(0, 16384, (H, W, C)).astype(numpy.uint16)
+    lidar = (rng.random((H, W, 1)) * 50).astype(numpy.float32)
+    pts = numpy.stack([rng.integers(0, W, 300), rng.integers(0, H, 300), rng.integers(0, 15, 300)], 1)
+    pts[:4, :2] = [[0, 0], [W - 1, H - 1], [0, H - 1], [W - 1, 0]]
+    ref, lab = D.gather_patches(D.SceneRef(casi.copy(), lidar.copy(), n, True), pts)
+    got = _gather_case(E, casi, lidar, n, pts[:, :2], 0)
+    assert got.shape == (300, 7, 7, 145) and numpy.array_equal(got, ref)
+    # empty target list
+    assert _gather_case(E, casi, lidar, n, pts[:0, :2], 0).shape == (0, 7, 7, 145)
+
+
+def test_gather_vs_oracle_grss2018_shape(E):
+    rng = numpy.random.default_rng(7)
+    Hc, Wc, C, n = 30, 44, 48, 5
+    casi = rng.random((Hc, Wc, C)).astype(numpy.float32)
+    lidar = rng.random((2 * Hc, 2 * Wc, 1)).astype(numpy.float32)
+    pts = numpy.stack([rng.integers(0, 2 * Wc, 200), rng.integers(0, 2 * Hc, 200), rng.integers(0, 20, 200)], 1)
+    pts[:2, :2] = [[0, 0], [2 * Wc - 1, 2 * Hc - 1]]
+    sc = D.SceneRef2018(casi.copy(), lidar.copy(), n, True)
+    ref = numpy.stack([sc.get_data_point(int(p[0]), int(p[1])) for p in pts]).astype(numpy.float32)
+    got = _gather_case(E, casi, lidar, n, pts[:, :2], 1)
+    assert got.shape == (200, 11, 11, 49) and numpy.array_equal(got, ref)
+
+
+def test_gather_rejects_bad_arguments(E):
+    from hypelcnn_b200 import NativeError
+    casi = dev(numpy.zeros((4, 4, 3), numpy.float32))
+    with pytest.raises(NativeError):
+        E.gather_patches(casi, None, 9, dev(numpy.zeros((1, 2), numpy.int32)))  # neighborhood > scene
+    with pytest.raises(TypeError):
+        E.gather_patches(casi.double(), None, 1, dev(numpy.zeros((1, 2), numpy.int32)))
+    with pytest.raises(TypeError):
+        E.gather_patches(casi.cpu(), None, 1, dev(numpy.zeros((1, 2), numpy.int32)))
+
+
+# ------------------------------------------------------------------------------------- metrics
+def test_argmax_confusion_bit_exact(E):
+    rng = numpy.random.default_rng(3)
+    logits = rng.standard_normal((5000, 15)).astype(numpy.float32)
+    logits[:50, 3] = logits[:50, 7] = 9.0  # ties -> lowest index
+    labels = rng.integers(0, 15, 5000).astype(numpy.uint8)
+    conf = torch.zeros((15, 15), dtype=torch.int32, device="cuda")
+    pred = E.argmax_confusion(dev(logits), dev(labels), conf)
+    ref_pred = D.argmax_lowest(logits)
+    assert numpy.array_equal(pred.cpu().numpy(), ref_pred.astype(numpy.uint8))
+    assert numpy.array_equal(conf.cpu().numpy(), D.confusion_matrix(labels, ref_pred, 15))
+    E.argmax_confusion(dev(logits), dev(labels), conf)  # += semantics (common_nn_ops.py:262)
+    assert numpy.array_equal(conf.cpu().numpy(), 2 * D.confusion_matrix(labels, ref_pred, 15))
+    xy = numpy.stack([rng.permutation(5000) % 100, rng.permutation(5000) // 100], 1).astype(numpy.int32)
+    cmap = torch.full((50, 100), 255, dtype=torch.uint8, device="cuda")
+    E.scatter_class_map(pred, dev(xy), cmap)
+    assert numpy.array_equal(cmap.cpu().numpy(), D.scatter_class_map([50, 100], xy, ref_pred))
+
+
+# ------------------------------------------------------------------------------------- model
+CASES = {
+    "tiny": dict(P=3, C=10, classes=4, alg={**ALG, "filter_count": 32}, B=24),
+    "c5": dict(P=3, C=65, classes=11, alg=ALG, B=32),
+    "c2": dict(P=7, C=145, classes=15, alg=ALG, B=16),
+    "nonres": dict(P=5, C=20, classes=6, alg={**ALG, "filter_count": 64, "use_residual": False}, B=20),
+}
+
+
+def _make(E, case, drop=0.0):
+    c = CASES[case]
+    alg = {**c["alg"], "drop_out_ratio": drop}
+    eng = E.PatchEngine(c["P"], c["C"], c["classes"], alg, max_batch=c["B"])
+    eng.init_variables(seed=1234)
+    x, y = synthetic_batch(c["B"], c["P"], c["C"], c["classes"])
+    return eng, alg, c, x, y
+
+
+@pytest.mark.parametrize("case", ["tiny", "c5", "nonres", "c2"])
+def test_variable_table_matches_reference_names(E, case):
+    eng, alg, c, x, y = _make(E, case)
+    specs = R.variable_specs(c["P"], c["C"], c["classes"], alg)
+    assert set(eng.variables) == {n for n, _, _ in specs}
+    for n, shape, kind in specs:
+        assert tuple(eng.variables[n][2]) == tuple(shape), n
+    assert eng.trainable_count == sum(int(numpy.prod(s)) for _, s, k in specs if k in ("weights", "beta"))
+    if case == "c2":
+        assert eng.trainable_count == 8160297
+
+
+@pytest.mark.parametrize("case", ["tiny", "c5", "nonres", "c2"])
+def test_forward_training_parity_per_layer(E, case):
+    eng, alg, c, x, y = _make(E, case)
+    v = oracle_variables(eng)
+    ref = R.forward(v, torch.tensor(x, dtype=torch.float64), c["classes"], alg, True)
+    logits, recon = eng.forward(dev(x), True, True, seed=0)
+    # walk the layers in order so the first divergence is the one reported
+    for l in R.build_plan(c["P"], c["C"], c["classes"], alg, True):
+        if l.kind == "conv" and l.concat_slot is None or l.kind == "fc":
+            z = eng.debug_tensor(l.scope, 1).cpu().numpy().reshape(ref["pre"][l.scope].shape)
+            assert_close_scaled(z, ref["pre"][l.scope].numpy(), 2e-5, f"pre-BN {l.scope}")
+            a = eng.debug_tensor(l.dst, 0).cpu().numpy().reshape(ref["tensors"][l.dst].shape)
+            assert_close(a, ref["tensors"][l.dst].numpy(), RTOL, 1e-4, f"activation {l.dst}")
+        elif l.kind == "level_end":
+            a = eng.debug_tensor(l.dst, 0).cpu().numpy().reshape(ref["tensors"][l.dst].shape)
+            assert_close(a, ref["tensors"][l.dst].numpy(), RTOL, 1e-4, f"level {l.dst}")
+    assert_close(logits.cpu().numpy(), ref["logits"].numpy(), RTOL, ATOL, "logits")
+    assert_close(recon.cpu().numpy(), ref["recon"].numpy(), RTOL, ATOL, "recon")
+    # BN moving statistics (decay, Bessel-corrected variance)
+    for name in eng.variables:
+        if "moving_" in name:
+            assert_close(eng.variable(name).cpu().numpy(), ref["new_variables"][name].numpy(), 1e-5, 1e-6, name)
+    # integer argmax class map bit-exact
+    pred = E.argmax_confusion(logits)
+    assert numpy.array_equal(pred.cpu().numpy(), D.argmax_lowest(ref["logits"].numpy()).astype(numpy.uint8))
+
+
+@pytest.mark.parametrize("case", ["tiny", "c2"])
+def test_forward_eval_parity(E, case):
+    eng, alg, c, x, y = _make(E, case)
+    # non-trivial moving statistics: run two training forwards first (same on both sides)
+    v = oracle_variables(eng)
+    xt = torch.tensor(x, dtype=torch.float64)
+    for _ in range(2):
+        v = R.forward(v, xt, c["classes"], alg, True)["new_variables"]
+        eng.forward(dev(x), True, True, seed=0)
+    ref = R.forward(v, xt, c["classes"], alg, False)
+    logits, recon = eng.forward(dev(x), False)
+    assert recon is None
+    assert_close(logits.cpu().numpy(), ref["logits"].numpy(), RTOL, ATOL, "eval logits")
+    # batch of one works in eval mode; training mode refuses it
+    l1, _ = eng.forward(dev(x[:1]), False)
+    assert_close(l1.cpu().numpy(), ref["logits"].numpy()[:1], RTOL, ATOL, "eval logits B=1")
+    from hypelcnn_b200 import NativeError
+    with pytest.raises(NativeError):
+        eng.forward(dev(x[:1]), True)
+
+
+@pytest.mark.parametrize("case", ["tiny", "c5", "nonres", "c2"])
+def test_loss_and_gradient_parity(E, case):
+    eng, alg, c, x, y = _make(E, case)
+    v = oracle_variables(eng)
+    loss_ref, g_ref, out = R.loss_and_grads(v, torch.tensor(x, dtype=torch.float64), torch.tensor(y.astype(numpy.int64)),
+                                            c["classes"], alg)
+    xd, yd = dev(x), dev(y)
+    logits, recon = eng.forward(xd, True, True, seed=0)
+    per = eng.per_sample_loss(logits, recon, xd, yd)
+    ref_per = R.per_sample_loss(out["logits"], out["recon"], torch.tensor(x, dtype=torch.float64),
+                                torch.tensor(y.astype(numpy.int64)))
+    assert_close(per.cpu().numpy(), ref_per.detach().numpy(), RTOL, ATOL, "per-sample loss")
+    per_eval = eng.per_sample_loss(logits, None, None, yd)  # eval graph: CE only
+    assert_close(per_eval.cpu().numpy(), (ref_per - ((out["recon"] - torch.tensor(x, dtype=torch.float64).reshape(
+        x.shape[0], -1)) ** 2).mean()).detach().numpy(), RTOL, ATOL, "CE only")
+    loss = eng.loss_backward(xd, yd).cpu().numpy()
+    assert abs(loss[0] - loss_ref.item()) <= RTOL * abs(loss_ref.item()) + ATOL
+    # activation gradients first (localises a failure), then every variable
+    order = [n for n, _, k in R.variable_specs(c["P"], c["C"], c["classes"], alg) if k in ("weights", "beta")]
+    for name in reversed(order):
+        assert_close_scaled(eng.gradient(name).cpu().numpy(), g_ref[name].numpy(), 2e-4, f"grad {name}")
+
+
+def test_backward_requires_training_forward(E):
+    from hypelcnn_b200 import NativeError
+    eng, alg, c, x, y = _make(E, "tiny")
+    xd, yd = dev(x), dev(y)
+    eng.forward(xd, False)
+    with pytest.raises(NativeError) as ei:
+        eng.loss_backward(xd, yd)
+    assert ei.value.code == -3
+
+
+def test_dropout_with_injected_mask_parity(E):
+    eng, alg, c, x, y = _make(E, "c5", drop=0.70)
+    seed = 99
+    xd, yd = dev(x), dev(y)
+    logits, recon = eng.forward(xd, True, True, seed=seed)
+    masks = {}
+    for l in R.build_plan(c["P"], c["C"], c["classes"], alg, True):
+        if l.dropout:
+            m = eng.dropout_mask(l.scope, seed, c["B"]).cpu()
+            assert 0.15 < m.float().mean().item() < 0.45  # keep_prob = 0.30
+            masks[l.scope] = m.double()
+    v = oracle_variables(eng)
+    loss_ref, g_ref, out = R.loss_and_grads(v, torch.tensor(x, dtype=torch.float64), torch.tensor(y.astype(numpy.int64)),
+                                            c["classes"], alg, dropout_masks=masks)
+    assert_close(logits.cpu().numpy(), out["logits"].detach().numpy(), RTOL, ATOL, "logits with dropout")
+    eng.loss_backward(xd, yd)
+    for name in ("nn_core/fc_0/weights", "nn_core/conv_enc_0/weights", "nn_core/connector_0_conv3x3/weights"):
+        assert_close_scaled(eng.gradient(name).cpu().numpy(), g_ref[name].numpy(), 2e-4, f"grad {name}")
+    # a different seed gives a different mask; the same seed the same one
+    assert not torch.equal(eng.dropout_mask("fc_0", seed + 1, c["B"]), eng.dropout_mask("fc_0", seed, c["B"]))
+
+
+def test_adam_matches_tf1_semantics(E):
+    rng = numpy.random.default_rng(5)
+    n = 10007
+    p, g = rng.standard_normal(n).astype(numpy.float32), rng.standard_normal(n).astype(numpy.float32) * 1e-2
+    pd, gd = dev(p), dev(g)
+    m, v = torch.zeros_like(pd), torch.zeros_like(pd)
+    rp, rm, rv = torch.tensor(p, dtype=torch.float64), torch.zeros(n, dtype=torch.float64), torch.zeros(n, dtype=torch.float64)
+    for t in range(1, 6):
+        E.adam_step(pd, gd, m, v, 3e-4, t, grad_scale=0.5)
+        rp, rm, rv = R.adam_tf1(rp, torch.tensor(g, dtype=torch.float64) * 0.5, rm, rv, 3e-4, t)
+    assert_close(pd.cpu().numpy(), rp.numpy(), 1e-6, 1e-7, "adam params")
+    assert_close(m.cpu().numpy(), rm.numpy(), 1e-5, 1e-9, "adam m")
+
+
+@pytest.mark.parametrize("case", ["tiny", "c5"])
+def test_training_trajectory_parity(E, case):
+    """N optimize_nn steps (dropout off): losses and final variables track the fp64 oracle."""
+    eng, alg, c, x, y = _make(E, case)
+    v = oracle_variables(eng)
+    xt, yt = torch.tensor(x, dtype=torch.float64), torch.tensor(y.astype(numpy.int64))
+    xd, yd = dev(x), dev(y)
+    opt = {}
+    for step in range(4):
+        loss_ref, v, opt, _ = R.train_step(v, opt, xt, yt, c["classes"], alg, step)
+        loss = eng.train_step(xd, yd).cpu().numpy()
+        assert abs(loss[0] - loss_ref.item()) <= 5e-4 * abs(loss_ref.item()), (step, loss[0], loss_ref.item())
+    assert eng.global_step == 4
+    for name in ("nn_core/conv_enc_0/weights", "nn_core/fc_final/weights", "nn_core/fc_final/BatchNorm/moving_mean"):
+        assert_close_scaled(eng.variable(name).cpu().numpy(), v[name].numpy(), 2e-3, name)
+
+
+def test_weights_shared_across_calls_and_capacity_growth(E):
+    eng, alg, c, x, y = _make(E, "tiny")
+    before = eng.export_variables()
+    x2, _ = synthetic_batch(c["B"] * 3, c["P"], c["C"], c["classes"], seed=5)
+    la, _ = eng.forward(dev(x2), False)  # larger than max_batch: workspace grows, parameters stay
+    after = eng.export_variables()
+    assert all(numpy.array_equal(before[k], after[k]) for k in before)
+    lb, _ = eng.forward(dev(x2[: c["B"]]), False)
+    assert torch.equal(la[: c["B"]], lb)  # eval mode is per-sample
