@@ -321,6 +321,8 @@ def gather_patches(casi, lidar, neighborhood, targets_xy, casi_min=None, casi_ma
         out = torch.empty((n, S, S, ch), dtype=torch.float32, device=casi.device)
     else:
         require_cuda(out, "out", torch.float32)
+    if n == 0:  # empty target list (the reference's test split with --test_ratio 0): nothing to launch
+        return out
     N.check(N.lib().hyp_gather_patches(_ptr(casi), dt, Hc, Wc, C, _ptr(casi_min), _ptr(casi_max), _ptr(lidar), Hl, Wl,
                                        _ptr(lidar_minmax), neighborhood, mode, _ptr(targets_xy), n, _ptr(out),
                                        out.shape[-1], _stream()))
