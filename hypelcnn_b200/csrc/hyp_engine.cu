@@ -13,6 +13,7 @@
 #include "hyp_common.cuh"
 #include "hyp_gemm_simt.cuh"
 #include "hyp_kernels.cuh"
+#include "hyp_tc.cuh"
 
 namespace hyp {
 thread_local std::string g_last_error;
@@ -68,6 +69,9 @@ struct Layer {
   uint32_t drop_stream;
 };
 
+namespace tc {
+struct TcState;
+}
 }  // namespace hyp
 
 using namespace hyp;
@@ -99,6 +103,7 @@ struct hyp_model {
   bool last_training = false;
   uint64_t last_seed = 0;
   const float* last_x = nullptr;
+  hyp::tc::TcState* tc = nullptr;  // tensor-core engine state (HYP_PRECISION_3XTF32)
 };
 
 namespace hyp {
@@ -608,6 +613,8 @@ static int backward_impl(hyp_model& m, const float* x, const uint8_t* labels, in
 
 }  // namespace hyp
 
+#include "hyp_tc_engine.cuh"
+
 // =============================================================================================
 // C ABI
 // =============================================================================================
@@ -655,7 +662,7 @@ int hyp_model_create(const hyp_model_desc* desc, hyp_model** out) {
                 "filter_count/levels out of range");
   HYP_CHECK_ARG(desc->max_batch >= 1, "max_batch must be positive");
   HYP_CHECK_ARG(desc->drop_out_ratio >= 0.f && desc->drop_out_ratio < 1.f, "drop_out_ratio in [0,1)");
-  if (desc->precision_mode != HYP_PRECISION_FP32)
+  if (desc->precision_mode != HYP_PRECISION_FP32 && desc->precision_mode != HYP_PRECISION_3XTF32)
     return fail(HYP_E_UNSUPPORTED, "hyp_model_create: precision mode not built yet");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -666,6 +673,11 @@ int hyp_model_create(const hyp_model_desc* desc, hyp_model** out) {
   if (rc) return rc;
   rc = layout(*m);
   if (rc) return rc;
+  if (desc->precision_mode == HYP_PRECISION_3XTF32) {
+    rc = hyp::tc::tc_layout(*m);
+    if (rc) { hyp::tc::tc_destroy(*m); return rc; }
+    m->ws_bytes = m->tc->ws_bytes;
+  }
   if ((int64_t)m->d.max_batch * m->d.patch * m->d.patch > (int64_t)INT32_MAX / 2)
     return fail(HYP_E_INVALID, "hyp_model_create: max_batch too large");
   *out = m.release();
@@ -674,6 +686,7 @@ int hyp_model_create(const hyp_model_desc* desc, hyp_model** out) {
 
 void hyp_model_destroy(hyp_model* m) {
   if (!m) return;
+  hyp::tc::tc_destroy(*m);
   for (void* p : m->owned) cudaFree(p);
   if (m->segs_dev) cudaFree(m->segs_dev);
   if (m->tjobs_dev) cudaFree(m->tjobs_dev);
@@ -715,6 +728,10 @@ int hyp_model_bind(hyp_model* m, float* params, float* grads, float* bn_state, v
   m->state = bn_state;
   m->ws = static_cast<char*>(workspace);
   m->last_B = -1;
+  if (m->tc) {
+    m->segs_bound = true;
+    return hyp::tc::tc_bind(*m);
+  }
   return bind_tables(*m);
 }
 
@@ -725,12 +742,27 @@ int hyp_model_forward(hyp_model* m, const float* x, int64_t B, int is_training, 
   HYP_CHECK_ARG(B >= 1 && B <= m->d.max_batch, "B out of range");
   HYP_CHECK_ARG(!is_training || B >= 2, "training-mode BatchNorm needs B >= 2");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int rc = forward_impl(*m, x, B, is_training != 0, update_moving != 0, dropout_seed, st);
+  int rc = m->tc ? hyp::tc::tc_forward(*m, x, B, is_training != 0, update_moving != 0, dropout_seed, st)
+                 : forward_impl(*m, x, B, is_training != 0, update_moving != 0, dropout_seed, st);
   if (rc) return rc;
   m->last_B = B;
   m->last_training = is_training != 0;
   m->last_seed = dropout_seed;
   m->last_x = x;
+  if (m->tc) {  // padded row-major FC outputs -> dense
+    if (logits)
+      HYP_CUDA(cudaMemcpy2DAsync(logits, (size_t)m->d.classes * sizeof(float), hyp::tc::tc_plane0(*m, m->logits_t),
+                                 (size_t)m->tc->tt[m->logits_t].Cp * sizeof(float), (size_t)m->d.classes * sizeof(float),
+                                 (size_t)B, cudaMemcpyDeviceToDevice, st));
+    if (recon) {
+      if (!is_training) return fail(HYP_E_INVALID, "hyp_model_forward: recon only exists in the training graph");
+      const size_t D = (size_t)m->d.patch * m->d.patch * m->d.channels;
+      HYP_CUDA(cudaMemcpy2DAsync(recon, D * sizeof(float), hyp::tc::tc_plane0(*m, m->recon_t),
+                                 (size_t)m->tc->tt[m->recon_t].Cp * sizeof(float), D * sizeof(float), (size_t)B,
+                                 cudaMemcpyDeviceToDevice, st));
+    }
+    return HYP_OK;
+  }
   if (logits)
     HYP_CUDA(cudaMemcpyAsync(logits, act_ptr(*m, m->logits_t, x), (size_t)B * m->d.classes * sizeof(float),
                              cudaMemcpyDeviceToDevice, st));
@@ -750,8 +782,8 @@ int hyp_model_loss(hyp_model* m, const float* logits, const float* recon, const 
   if (!m->ws) return fail(HYP_E_STATE, "hyp_model_loss: call hyp_model_bind first");
   HYP_CHECK_ARG(B >= 1 && B <= m->d.max_batch, "B out of range");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  float* ce = reinterpret_cast<float*>(m->ws + m->ce_off);
-  double* mse_acc = reinterpret_cast<double*>(m->ws + m->mse_off);
+  float* ce = reinterpret_cast<float*>(m->ws + (m->tc ? m->tc->ce_off : m->ce_off));
+  double* mse_acc = reinterpret_cast<double*>(m->ws + (m->tc ? m->tc->mse_off : m->mse_off));
   HYP_CUDA(cudaMemsetAsync(mse_acc, 0, 256, st));
   ce_loss_kernel<<<(unsigned)cdiv(B * 32, 256), 256, 0, st>>>(logits, labels, B, m->d.classes, ce, nullptr, 0.f);
   HYP_LAUNCHED();
@@ -771,6 +803,7 @@ int hyp_model_loss_backward(hyp_model* m, const float* x, const uint8_t* labels,
   if (!m->segs_bound) return fail(HYP_E_STATE, "hyp_model_loss_backward: call hyp_model_bind first");
   if (!m->last_training || m->last_B != B || m->last_x != x)
     return fail(HYP_E_STATE, "hyp_model_loss_backward: needs the preceding hyp_model_forward(is_training=1) on the same x/B");
+  if (m->tc) return hyp::tc::tc_backward(*m, labels, B, loss_out, static_cast<cudaStream_t>(stream));
   return backward_impl(*m, x, labels, B, loss_out, static_cast<cudaStream_t>(stream));
 }
 
@@ -866,10 +899,154 @@ int hyp_gather_patches(const void* casi, int casi_dtype, int Hc, int Wc, int C_h
   return HYP_OK;
 }
 
+// ---- tensor-core building block probe (tests/test_gpu_tc.py) --------------------------------
+// mn = 0: A [M,K], B [N,K] row-major, D = A * B^T.   mn = 1: A [K,M], B [K,N], D = A^T * B.
+// Splits both operands into TF32 (hi, lo) planes, builds tensor maps and tile tables exactly
+// as the engine does, and runs tc_gemm_kernel.  ksplit > 1 (mn = 1 only) splits K over CTAs
+// that accumulate with atomics (D must be zeroed by the caller).
+int hyp_debug_tc_gemm(int mn, const float* A, const float* B, int M, int N, int K, float* D, float* stats,
+                      int raw_hi, int bn, int ksplit, int chunk_kb, void* stream) {
+  using namespace hyp::tc;
+  HYP_CHECK_ARG(A && B && D && M > 0 && N > 0 && K > 0, "bad argument");
+  HYP_CHECK_ARG(N % 4 == 0, "N must be a multiple of 4 (output row alignment)");
+  HYP_CHECK_ARG(ksplit >= 1 && (mn || ksplit == 1), "ksplit needs mn = 1");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int lda_src = mn ? M : K, ldb_src = mn ? N : K;
+  const int64_t a_rows = mn ? K : M, b_rows_src = mn ? K : N;
+  const int ldA = (int)align_up(lda_src, 4), ldB = (int)align_up(ldb_src, 4);
+  float *Ap = nullptr, *Bp = nullptr;
+  HYP_CUDA(cudaMalloc(&Ap, 2 * (size_t)a_rows * ldA * sizeof(float)));
+  HYP_CUDA(cudaMalloc(&Bp, 2 * (size_t)b_rows_src * ldB * sizeof(float)));
+  split_planes_kernel<<<256, 256, 0, st>>>(A, a_rows, lda_src, lda_src, Ap, Ap + a_rows * ldA, ldA, raw_hi);
+  HYP_LAUNCHED();
+  split_planes_kernel<<<256, 256, 0, st>>>(B, b_rows_src, ldb_src, ldb_src, Bp, Bp + b_rows_src * ldB, ldB, raw_hi);
+  HYP_LAUNCHED();
+  const int ntile_n = 256;
+  if (bn <= 0) bn = (int)std::min<int64_t>(256, align_up(N, 16));
+  HYP_CHECK_ARG(bn % 8 == 0 && bn <= 256, "bn must be a multiple of 8, <= 256");
+  CUtensorMap tmA, tmB;
+  int rc;
+  {
+    const uint64_t da[4] = {(uint64_t)lda_src, (uint64_t)a_rows, 1, 2};
+    const uint64_t sa[3] = {(uint64_t)ldA, (uint64_t)a_rows * ldA, (uint64_t)a_rows * ldA};
+    const uint32_t ba[4] = {32, mn ? 32u : 128u, 1, 1};
+    if ((rc = make_map(&tmA, Ap, da, sa, ba, mn != 0))) return rc;
+    const uint64_t db[4] = {(uint64_t)ldb_src, (uint64_t)b_rows_src, 1, 2};
+    const uint64_t sb[3] = {(uint64_t)ldB, (uint64_t)b_rows_src * ldB, (uint64_t)b_rows_src * ldB};
+    const uint32_t bb[4] = {32, mn ? 32u : (uint32_t)bn, 1, 1};
+    if ((rc = make_map(&tmB, Bp, db, sb, bb, mn != 0))) return rc;
+  }
+  std::vector<TcSeg> segs;
+  std::vector<TcTile> tiles;
+  const int mt = (int)cdiv(M, 128), nt = (int)cdiv(N, ntile_n);
+  const int kblocks = (int)cdiv(K, TC_KB);
+  const int kb_per = (int)cdiv(kblocks, ksplit);
+  int max_brows = 0, max_cols = 0;
+  for (int im = 0; im < mt; im++)
+    for (int in = 0; in < nt; in++)
+      for (int ks = 0; ks < ksplit; ks++) {
+        const int kb0 = ks * kb_per, kb1 = std::min(kblocks, kb0 + kb_per);
+        if (kb0 >= kb1) continue;
+        const int n0 = in * ntile_n, nw = std::min(ntile_n, N - n0);
+        TcSeg s{};
+        s.nk = kb1 - kb0;
+        s.n_mma = (int)align_up(nw, 16);
+        if (!mn) {
+          s.a0 = 0; s.a1 = im * 128; s.a2 = 0;
+          s.b0 = 0; s.b1 = n0; s.b2 = 0;
+          s.nb = (int)cdiv(s.n_mma, bn);
+          max_brows = std::max(max_brows, s.nb * bn);
+        } else {
+          s.a0 = im * 128; s.a1 = kb0 * TC_KB; s.a2 = 0;
+          s.b0 = n0; s.b1 = kb0 * TC_KB; s.b2 = 0;
+          s.nb = (int)cdiv(s.n_mma, 32);
+          max_brows = std::max(max_brows, s.nb * 32);
+        }
+        max_cols = std::max(max_cols, (int)align_up(nw, 32));
+        TcTile t{};
+        t.seg_begin = (int)segs.size();
+        t.seg_count = 1;
+        t.total_kb = s.nk;
+        t.m_valid = std::min(128, M - im * 128);
+        t.ncb = 1;
+        t.ld_out = N;
+        t.stats_row = im;
+        t.cb[0].out_off = (int64_t)im * 128 * N + n0;
+        t.cb[0].tcol = 0;
+        t.cb[0].width = nw;
+        t.cb[0].stats_col = n0;
+        segs.push_back(s);
+        tiles.push_back(t);
+      }
+  TcSeg* dsegs = nullptr;
+  TcTile* dtiles = nullptr;
+  HYP_CUDA(cudaMalloc(&dsegs, segs.size() * sizeof(TcSeg)));
+  HYP_CUDA(cudaMalloc(&dtiles, tiles.size() * sizeof(TcTile)));
+  HYP_CUDA(cudaMemcpyAsync(dsegs, segs.data(), segs.size() * sizeof(TcSeg), cudaMemcpyHostToDevice, st));
+  HYP_CUDA(cudaMemcpyAsync(dtiles, tiles.data(), tiles.size() * sizeof(TcTile), cudaMemcpyHostToDevice, st));
+  TcParams p{};
+  p.segs = dsegs; p.tiles = dtiles; p.out = D; p.stats = stats; p.stats_ld = N;
+  p.epi = ksplit > 1 ? EPI_ATOMIC : EPI_STORE;
+  p.b_rows = max_brows; p.bn = bn; p.chunk_kb = chunk_kb; p.stages = 0;
+  (void)max_cols;
+  rc = mn ? launch_tc<true>(tmA, tmB, p, (int)tiles.size(), st) : launch_tc<false>(tmA, tmB, p, (int)tiles.size(), st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(Ap); cudaFree(Bp); cudaFree(dsegs); cudaFree(dtiles);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(HYP_E_CUDA, std::string("hyp_debug_tc_gemm: ") + cudaGetErrorString(e));
+  return HYP_OK;
+}
+
 int hyp_model_debug_tensor(hyp_model* m, const char* name, int what, float** ptr, int64_t* numel) {
   HYP_CHECK_ARG(m && name && ptr && numel, "null argument");
   if (!m->ws || m->last_B < 0) return fail(HYP_E_STATE, "hyp_model_debug_tensor: no forward has run");
   const std::string n(name);
+  if (m->tc) {  // position-major padded tensors -> dense [B][PP][C] in the debug scratch
+    using namespace hyp::tc;
+    TcState& S = *m->tc;
+    int t = -1;
+    const float* src = nullptr;
+    if (what == 3) {
+      for (size_t li = 0; li < m->layers.size(); li++)
+        if (m->layers[li].scope == n) {
+          HYP_CUDA(cudaDeviceSynchronize());
+          *ptr = reinterpret_cast<float*>(m->ws + S.tl[li].mean_off);
+          *numel = m->layers[li].Cout;
+          return HYP_OK;
+        }
+      return fail(HYP_E_INVALID, "hyp_model_debug_tensor: unknown layer " + n);
+    }
+    if (what == 1) {
+      for (size_t li = 0; li < m->layers.size(); li++)
+        if (m->layers[li].scope == n) { t = m->layers[li].out_t; src = reinterpret_cast<float*>(m->ws + S.tl[li].z_off); }
+      if (t < 0) return fail(HYP_E_INVALID, "hyp_model_debug_tensor: unknown layer " + n);
+    } else {
+      auto it = m->tensor_by_name.find(n);
+      if (it == m->tensor_by_name.end()) return fail(HYP_E_INVALID, "hyp_model_debug_tensor: unknown tensor " + n);
+      t = it->second;
+      if (what == 2 && !m->tensors[t].needs_grad) return fail(HYP_E_INVALID, "hyp_model_debug_tensor: tensor has no gradient");
+      src = what == 2 ? tc_grad(*m, t) : tc_plane0(*m, t);
+    }
+    const TcTensor& T = S.tt[t];
+    float* dst = reinterpret_cast<float*>(m->ws + S.dbg_off);
+    const int64_t total = m->last_B * T.PP * T.C;
+    HYP_CUDA(cudaDeviceSynchronize());
+    tc_extract_kernel<<<tc_grid(total), 256>>>(src, T.Cp, (int)m->last_B, T.PP, T.C, dst);
+    HYP_LAUNCHED();
+    HYP_CUDA(cudaDeviceSynchronize());
+    *ptr = dst;
+    *numel = total;
+    return HYP_OK;
+  }
+  if (what == 3) {
+    for (Layer& L : m->layers)
+      if (L.scope == n) {
+        *ptr = reinterpret_cast<float*>(m->ws + L.mean_off);
+        *numel = L.Cout;
+        return HYP_OK;
+      }
+    return fail(HYP_E_INVALID, "hyp_model_debug_tensor: unknown layer " + n);
+  }
   if (what == 1) {
     for (Layer& L : m->layers)
       if (L.scope == n) {

@@ -1,0 +1,770 @@
+// Tensor-core engine (HYP_PRECISION_3XTF32): the same layer plan as the FFMA engine, executed
+// with the tcgen05 segment-GEMM of hyp_tc.cuh on position-major activations.
+//
+// Included by hyp_engine.cu after hyp_model / Layer / Tensor are defined.
+//
+// Layer kinds
+//   rowwise : 1x1 conv or FC fed by an FC          z[r, :]    = a[r, :] W                (one K segment)
+//   level   : the k x k convs of one spatial level z[p, b, :] = sum_taps a[p+tap, b, :] W_tap
+//             all kernel sizes share the A tile; accumulator columns are "slots"
+//             [k_max | ... | 3x3 | 1x1] (fpad columns each) so a tap of ring r = max(|dy|,|dx|)
+//             multiplies the first (R - r) slots only
+//   flatten : FC fed by a conv tensor              z[b, :]    = sum_pos a[pos, b, :] W_pos
+#pragma once
+#include <algorithm>
+
+#include "hyp_tc_kernels.cuh"
+
+namespace hyp {
+namespace tc {
+
+struct TcTensor {
+  int PP, C, Cp;
+  size_t a_off = 0;          // plane 0 (bytes in workspace); plane 1 follows at +plane_elems floats
+  size_t plane_elems = 0;
+  size_t g_off = 0;
+};
+
+struct TcLaunch {
+  CUtensorMap tmA, tmB;
+  int tile0 = 0, ntiles = 0;
+  int b_rows = 0, bn = 0;
+  bool mn = false;
+};
+
+struct TcLayer {
+  int kind = 0;  // 0 rowwise, 1 level, 2 flatten
+  int R = 1, f = 0, fpad = 0, Gp = 0, Kp = 0, Cq = 0;
+  size_t z_off = 0, mean_off = 0, rstd_off = 0, s1_off = 0, s2_off = 0;
+  int64_t wf_off = 0, wd_off = 0;  // packed forward / dgrad weights: element offsets inside a pack plane
+  int wf_rows = 0, wf_ld = 0, wd_rows = 0, wd_ld = 0;
+  TcLaunch fwd, dg, wg;
+  int stats_rows = 0;
+};
+
+struct TcState {
+  std::vector<TcTensor> tt;
+  std::vector<TcLayer> tl;
+  size_t gz_off = 0, gz_plane_elems = 0, part_off = 0, bpart_off = 0, pack_off = 0, pack_plane_elems = 0;
+  size_t ce_off = 0, mse_off = 0, dbg_off = 0, ws_bytes = 0;
+  std::vector<PackJob> jobs;
+  PackJob* jobs_dev = nullptr;
+  int job_blocks = 1;
+  TcSeg* segs_dev = nullptr;
+  TcTile* tiles_dev = nullptr;
+  size_t segs_cap = 0, tiles_cap = 0;
+  int planned_B = -1;
+  bool pack_cleared = false;
+};
+
+inline int r16(int v) { return (int)align_up((size_t)v, 16); }
+inline int r32(int v) { return (int)align_up((size_t)v, 32); }
+inline int r4(int v) { return (int)align_up((size_t)v, 4); }
+
+}  // namespace tc
+}  // namespace hyp
+
+// ---------------------------------------------------------------------------------------------
+namespace hyp {
+namespace tc {
+
+static float* tc_plane0(const hyp_model& m, int t) {
+  return reinterpret_cast<float*>(m.ws + m.tc->tt[t].a_off);
+}
+static float* tc_plane1(const hyp_model& m, int t) { return tc_plane0(m, t) + m.tc->tt[t].plane_elems; }
+static float* tc_grad(const hyp_model& m, int t) { return reinterpret_cast<float*>(m.ws + m.tc->tt[t].g_off); }
+
+// ---- static layout: workspace offsets, packed-weight offsets, pack jobs ------------------------
+static int tc_layout(hyp_model& m) {
+  m.tc = new TcState();
+  TcState& S = *m.tc;
+  const size_t Bm = (size_t)m.d.max_batch;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    off = align_up(off, 256);
+    const size_t o = off;
+    off += bytes;
+    return o;
+  };
+  S.tt.resize(m.tensors.size());
+  for (size_t t = 0; t < m.tensors.size(); t++) {
+    TcTensor& T = S.tt[t];
+    T.PP = m.tensors[t].rows_per_sample;
+    T.C = m.tensors[t].C;
+    T.Cp = r4(T.C);
+    T.plane_elems = align_up(Bm * T.PP * T.Cp, 64);
+    T.a_off = take(2 * T.plane_elems * sizeof(float));
+    if (m.tensors[t].needs_grad) T.g_off = take(T.plane_elems * sizeof(float));
+  }
+  S.tl.resize(m.layers.size());
+  int64_t pk = 0;
+  auto take_pack = [&](int64_t elems) {
+    pk = (int64_t)align_up((size_t)pk, 64);
+    const int64_t o = pk;
+    pk += elems;
+    return o;
+  };
+  size_t gz_max = 0, part_max = 0, bpart_max = 0, dbg_max = 0;
+  const int P = m.d.patch;
+  for (size_t li = 0; li < m.layers.size(); li++) {
+    Layer& L = m.layers[li];
+    TcLayer& T = S.tl[li];
+    const TcTensor& tin = S.tt[L.in_t];
+    const TcTensor& tout = S.tt[L.out_t];
+    const size_t rows_out = Bm * tout.PP;
+    T.z_off = take(rows_out * tout.Cp * sizeof(float));
+    T.mean_off = take(L.Cout * sizeof(float));
+    T.rstd_off = take(L.Cout * sizeof(float));
+    T.s1_off = take(L.Cout * sizeof(float));
+    T.s2_off = take(L.Cout * sizeof(float));
+    dbg_max = std::max(dbg_max, rows_out * (size_t)tout.C);
+    dbg_max = std::max(dbg_max, Bm * tin.PP * (size_t)tin.C);
+    const bool flatten = L.is_fc && tin.PP > 1;
+    const bool level = !L.is_fc && L.ksizes.size() > 0 && !(L.ksizes.size() == 1 && L.ksizes[0] == 1);
+    T.kind = flatten ? 2 : (level ? 1 : 0);
+    if (T.kind == 0) {
+      const int Cin = tin.C;
+      T.Kp = r32(Cin);
+      T.Gp = tout.Cp;
+      T.wf_rows = r16(L.Cout); T.wf_ld = T.Kp;
+      T.wd_rows = r16(Cin); T.wd_ld = r32(L.Cout);
+      T.wf_off = take_pack((int64_t)T.wf_rows * T.wf_ld);
+      T.wd_off = take_pack((int64_t)T.wd_rows * T.wd_ld);
+      PackJob j{};
+      j.src_off = L.w_off[0]; j.dst_off = T.wf_off; j.rows = T.wf_rows; j.cols = T.wf_ld; j.ld = T.wf_ld;
+      j.RD = T.wf_rows; j.RV = L.Cout; j.KD = T.wf_ld; j.KV = Cin; j.sr1 = 0; j.sr0 = 1; j.sk1 = 0; j.sk0 = L.Cout;
+      S.jobs.push_back(j);
+      if (m.tensors[L.in_t].needs_grad) {
+        PackJob d{};
+        d.src_off = L.w_off[0]; d.dst_off = T.wd_off; d.rows = T.wd_rows; d.cols = T.wd_ld; d.ld = T.wd_ld;
+        d.RD = T.wd_rows; d.RV = Cin; d.KD = T.wd_ld; d.KV = L.Cout; d.sr1 = 0; d.sr0 = L.Cout; d.sk1 = 0; d.sk0 = 1;
+        S.jobs.push_back(d);
+      }
+      T.stats_rows = (int)cdiv((int64_t)rows_out, 128);
+    } else if (T.kind == 1) {
+      const int Cin = tin.C;
+      T.R = (int)L.ksizes.size();
+      for (int q = 0; q < T.R; q++)
+        if (L.ksizes[q] != 2 * q + 1) return fail(HYP_E_UNSUPPORTED, "tc engine: level kernels must be 1,3,5,...");
+      T.f = L.f;
+      T.fpad = r16(L.f);
+      T.Kp = r32(Cin);
+      T.Gp = r32(T.R * T.fpad);
+      T.Cq = r16(Cin);
+      const int ntaps = P * P;
+      T.wf_rows = ntaps * T.R * T.fpad; T.wf_ld = T.Kp;
+      T.wd_rows = ntaps * T.Cq; T.wd_ld = T.Gp;
+      T.wf_off = take_pack((int64_t)T.wf_rows * T.wf_ld);
+      T.wd_off = take_pack((int64_t)T.wd_rows * T.wd_ld);
+      const int h = P / 2;
+      for (int dy = -h; dy <= h; dy++)
+        for (int dx = -h; dx <= h; dx++) {
+          const int tap = (dy + h) * P + (dx + h);
+          const int ring = std::max(std::abs(dy), std::abs(dx));
+          for (int slot = 0; slot < T.R; slot++) {
+            const int q = T.R - 1 - slot;
+            if (ring > q) continue;
+            const int k = 2 * q + 1;
+            const int64_t src = L.w_off[q] + (int64_t)((dy + q) * k + (dx + q)) * Cin * L.f;
+            PackJob j{};
+            j.src_off = src; j.dst_off = T.wf_off + (int64_t)((tap * T.R + slot) * T.fpad) * T.Kp;
+            j.rows = T.fpad; j.cols = T.Kp; j.ld = T.Kp;
+            j.RD = T.fpad; j.RV = L.f; j.KD = T.Kp; j.KV = Cin; j.sr0 = 1; j.sk0 = L.f;
+            S.jobs.push_back(j);
+            PackJob d{};
+            d.src_off = src; d.dst_off = T.wd_off + (int64_t)(tap * T.Cq) * T.Gp + slot * T.fpad;
+            d.rows = T.Cq; d.cols = T.fpad; d.ld = T.Gp;
+            d.RD = T.Cq; d.RV = Cin; d.KD = T.fpad; d.KV = L.f; d.sr0 = L.f; d.sk0 = 1;
+            S.jobs.push_back(d);
+          }
+        }
+      T.stats_rows = (int)(tout.PP * cdiv((int64_t)Bm, 128));
+    } else {
+      const int Ct = tin.C;
+      T.Kp = r32(Ct);
+      T.Gp = tout.Cp;
+      T.Cq = r16(Ct);
+      if (T.Cq > 256 || Ct > 128) return fail(HYP_E_UNSUPPORTED, "tc engine: flatten input wider than 128 channels");
+      T.wf_rows = r16(L.Cout); T.wf_ld = tin.PP * T.Kp;
+      T.wd_rows = tin.PP * T.Cq; T.wd_ld = r32(L.Cout);
+      T.wf_off = take_pack((int64_t)T.wf_rows * T.wf_ld);
+      T.wd_off = take_pack((int64_t)T.wd_rows * T.wd_ld);
+      PackJob j{};
+      j.src_off = L.w_off[0]; j.dst_off = T.wf_off; j.rows = T.wf_rows; j.cols = T.wf_ld; j.ld = T.wf_ld;
+      j.RD = T.wf_rows; j.RV = L.Cout; j.KD = T.Kp; j.KV = Ct; j.sr0 = 1; j.sk1 = Ct * L.Cout; j.sk0 = L.Cout;
+      S.jobs.push_back(j);
+      PackJob d{};
+      d.src_off = L.w_off[0]; d.dst_off = T.wd_off; d.rows = T.wd_rows; d.cols = T.wd_ld; d.ld = T.wd_ld;
+      d.RD = T.Cq; d.RV = Ct; d.KD = T.wd_ld; d.KV = L.Cout; d.sr1 = Ct * L.Cout; d.sr0 = L.Cout; d.sk0 = 1;
+      S.jobs.push_back(d);
+      T.stats_rows = (int)cdiv((int64_t)Bm, 128);
+    }
+    gz_max = std::max(gz_max, rows_out * (size_t)T.Gp);
+    part_max = std::max(part_max, (size_t)T.stats_rows * 2 * L.Cout);
+    {
+      const int64_t cblocks = cdiv(L.Cout, 32);
+      const int64_t rblocks = std::max<int64_t>(1, std::min<int64_t>(cdiv((int64_t)rows_out, 64), cdiv(148 * 8, cblocks)));
+      bpart_max = std::max(bpart_max, (size_t)(rblocks + 1) * 2 * L.Cout);
+    }
+  }
+  S.gz_plane_elems = align_up(gz_max, 64);
+  S.gz_off = take(2 * S.gz_plane_elems * sizeof(float));
+  S.part_off = take(part_max * sizeof(float));
+  S.bpart_off = take(bpart_max * sizeof(float));
+  S.pack_plane_elems = align_up((size_t)pk, 64);
+  S.pack_off = take(2 * S.pack_plane_elems * sizeof(float));
+  S.ce_off = take(Bm * sizeof(float));
+  S.mse_off = take(256);
+  S.dbg_off = take(dbg_max * sizeof(float));
+  S.ws_bytes = align_up(off, 256);
+  for (const PackJob& j : S.jobs)
+    S.job_blocks = std::max<int>(S.job_blocks, (int)std::min<int64_t>(64, cdiv((int64_t)j.rows * j.cols, 1024)));
+  return HYP_OK;
+}
+
+static void tc_destroy(hyp_model& m) {
+  if (!m.tc) return;
+  if (m.tc->jobs_dev) cudaFree(m.tc->jobs_dev);
+  if (m.tc->segs_dev) cudaFree(m.tc->segs_dev);
+  if (m.tc->tiles_dev) cudaFree(m.tc->tiles_dev);
+  delete m.tc;
+  m.tc = nullptr;
+}
+
+static int tc_bind(hyp_model& m) {
+  TcState& S = *m.tc;
+  if (!S.jobs_dev) {
+    HYP_CUDA(cudaMalloc(&S.jobs_dev, S.jobs.size() * sizeof(PackJob)));
+    HYP_CUDA(cudaMemcpy(S.jobs_dev, S.jobs.data(), S.jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
+  }
+  HYP_CUDA(cudaMemset(m.ws + S.pack_off, 0, 2 * S.pack_plane_elems * sizeof(float)));
+  S.planned_B = -1;
+  return HYP_OK;
+}
+
+// ---- per-batch-size plan: tensor maps, tiles, segments ------------------------------------------
+struct PlanBuf {
+  std::vector<TcSeg> segs;
+  std::vector<TcTile> tiles;
+};
+
+static TcTile blank_tile() {
+  TcTile t;
+  memset(&t, 0, sizeof(t));
+  return t;
+}
+
+static int map4(CUtensorMap* mp, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2,
+                uint64_t plane, uint32_t b0, uint32_t b1, bool mn) {
+  const uint64_t dims[4] = {d0, d1, d2, 2};
+  const uint64_t strides[3] = {s1, s2, plane};
+  const uint32_t box[4] = {b0, b1, 1, 1};
+  return make_map(mp, base, dims, strides, box, mn);
+}
+
+// split `total` output columns into the fewest tiles of <= 256, each a multiple of 16 wide
+static void n_tiling(int total, int& ntn, int& nw) {
+  ntn = (int)cdiv(total, 256);
+  nw = r16((int)cdiv(total, ntn));
+}
+
+static int tc_plan(hyp_model& m, int64_t B) {
+  TcState& S = *m.tc;
+  if (S.planned_B == B) return HYP_OK;
+  PlanBuf pb;
+  const int P = m.d.patch, h = P / 2;
+  const int nbt = (int)cdiv(B, 128);
+  float* pack0 = reinterpret_cast<float*>(m.ws + S.pack_off);
+  float* gz0 = reinterpret_cast<float*>(m.ws + S.gz_off);
+  int rc;
+  // taps sorted by ring so that the MMA N of a tile's segments never increases
+  std::vector<std::pair<int, int>> taps;
+  for (int ring = 0; ring <= h; ring++)
+    for (int dy = -h; dy <= h; dy++)
+      for (int dx = -h; dx <= h; dx++)
+        if (std::max(std::abs(dy), std::abs(dx)) == ring) taps.push_back({dy, dx});
+
+  for (size_t li = 0; li < m.layers.size(); li++) {
+    Layer& L = m.layers[li];
+    TcLayer& T = S.tl[li];
+    const TcTensor& tin = S.tt[L.in_t];
+    const TcTensor& tout = S.tt[L.out_t];
+    const bool need_dgrad = m.tensors[L.in_t].needs_grad;
+    const float* a0 = tc_plane0(m, L.in_t);
+    const int64_t rows_in = B * tin.PP, rows_out = B * tout.PP;
+    if (T.kind == 0) {
+      const int Cin = tin.C, Cout = L.Cout;
+      // ---------------- forward ----------------
+      int ntn, nw;
+      n_tiling(Cout, ntn, nw);
+      if ((rc = map4(&T.fwd.tmA, a0, Cin, rows_in, 1, tin.Cp, (uint64_t)rows_in * tin.Cp, tin.plane_elems, 32, 128, false))) return rc;
+      if ((rc = map4(&T.fwd.tmB, pack0 + T.wf_off, T.wf_ld, T.wf_rows, 1, T.wf_ld, (uint64_t)T.wf_rows * T.wf_ld,
+                     S.pack_plane_elems, 32, nw, false))) return rc;
+      T.fwd.mn = false; T.fwd.b_rows = nw; T.fwd.bn = nw; T.fwd.tile0 = (int)pb.tiles.size();
+      const int seg0 = (int)pb.segs.size();
+      for (int j = 0; j < ntn; j++) {
+        TcSeg s{};
+        s.b1 = j * nw; s.nk = T.Kp / 32; s.n_mma = r16(std::min(nw, Cout - j * nw)); s.nb = 1;
+        pb.segs.push_back(s);
+      }
+      const int nrt = (int)cdiv(rows_out, 128);
+      for (int rt = 0; rt < nrt; rt++)
+        for (int j = 0; j < ntn; j++) {
+          TcTile t = blank_tile();
+          t.seg_begin = seg0 + j; t.seg_count = 1; t.total_kb = T.Kp / 32;
+          t.m_valid = (int)std::min<int64_t>(128, rows_out - (int64_t)rt * 128);
+          t.ncb = 1; t.ld_out = tout.Cp; t.stats_row = rt; t.a1_add = rt * 128;
+          t.cb[0].out_off = (int64_t)rt * 128 * tout.Cp + j * nw;
+          t.cb[0].width = std::min(nw, Cout - j * nw);
+          t.cb[0].stats_col = j * nw;
+          pb.tiles.push_back(t);
+        }
+      T.fwd.ntiles = (int)pb.tiles.size() - T.fwd.tile0;
+      T.stats_rows = nrt;
+      // ---------------- dgrad ----------------
+      if (need_dgrad) {
+        n_tiling(Cin, ntn, nw);
+        if ((rc = map4(&T.dg.tmA, gz0, Cout, rows_out, 1, T.Gp, (uint64_t)rows_out * T.Gp, S.gz_plane_elems, 32, 128, false))) return rc;
+        if ((rc = map4(&T.dg.tmB, pack0 + T.wd_off, T.wd_ld, T.wd_rows, 1, T.wd_ld, (uint64_t)T.wd_rows * T.wd_ld,
+                       S.pack_plane_elems, 32, nw, false))) return rc;
+        T.dg.mn = false; T.dg.b_rows = nw; T.dg.bn = nw; T.dg.tile0 = (int)pb.tiles.size();
+        const int dseg0 = (int)pb.segs.size();
+        for (int j = 0; j < ntn; j++) {
+          TcSeg s{};
+          s.b1 = j * nw; s.nk = T.wd_ld / 32; s.n_mma = r16(std::min(nw, Cin - j * nw)); s.nb = 1;
+          pb.segs.push_back(s);
+        }
+        for (int rt = 0; rt < nrt; rt++)
+          for (int j = 0; j < ntn; j++) {
+            TcTile t = blank_tile();
+            t.seg_begin = dseg0 + j; t.seg_count = 1; t.total_kb = T.wd_ld / 32;
+            t.m_valid = (int)std::min<int64_t>(128, rows_out - (int64_t)rt * 128);
+            t.ncb = 1; t.ld_out = tin.Cp; t.a1_add = rt * 128;
+            t.cb[0].out_off = (int64_t)rt * 128 * tin.Cp + j * nw;
+            t.cb[0].width = std::min(nw, Cin - j * nw);
+            pb.tiles.push_back(t);
+          }
+        T.dg.ntiles = (int)pb.tiles.size() - T.dg.tile0;
+      }
+      // ---------------- wgrad ----------------
+      {
+        n_tiling(Cout, ntn, nw);
+        const int mt = (int)cdiv(Cin, 128);
+        if ((rc = map4(&T.wg.tmA, a0, Cin, rows_in, 1, tin.Cp, (uint64_t)rows_in * tin.Cp, tin.plane_elems, 32, 32, true))) return rc;
+        if ((rc = map4(&T.wg.tmB, gz0, Cout, rows_out, 1, T.Gp, (uint64_t)rows_out * T.Gp, S.gz_plane_elems, 32, 32, true))) return rc;
+        T.wg.mn = true; T.wg.bn = 32; T.wg.b_rows = 0; T.wg.tile0 = (int)pb.tiles.size();
+        const int kblocks = (int)cdiv(rows_out, 32);
+        int ksplit = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(296, mt * ntn), std::max(1, kblocks / 4)));
+        const int kb_per = (int)cdiv(kblocks, ksplit);
+        for (int im = 0; im < mt; im++)
+          for (int j = 0; j < ntn; j++)
+            for (int kb0 = 0; kb0 < kblocks; kb0 += kb_per) {
+              const int width = std::min(nw, Cout - j * nw);
+              TcSeg s{};
+              s.a0 = im * 128; s.a1 = kb0 * 32; s.b0 = j * nw; s.b1 = kb0 * 32;
+              s.nk = std::min(kb_per, kblocks - kb0); s.n_mma = r16(width); s.nb = (int)cdiv(s.n_mma, 32);
+              T.wg.b_rows = std::max(T.wg.b_rows, s.nb * 32);
+              TcTile t = blank_tile();
+              t.seg_begin = (int)pb.segs.size(); t.seg_count = 1; t.total_kb = s.nk;
+              t.m_valid = std::min(128, Cin - im * 128);
+              t.ncb = 1; t.ld_out = Cout;
+              t.cb[0].out_off = L.w_off[0] + (int64_t)im * 128 * Cout + j * nw;
+              t.cb[0].width = width;
+              pb.segs.push_back(s);
+              pb.tiles.push_back(t);
+            }
+        T.wg.ntiles = (int)pb.tiles.size() - T.wg.tile0;
+      }
+    } else if (T.kind == 1) {
+      const int Cin = tin.C, PP = tin.PP, R = T.R, fpad = T.fpad, f = T.f;
+      const int spg = std::min(std::min(256 / fpad, TC_MAX_CB), R);  // slots per accumulator group
+      const int ngroups = (int)cdiv(R, spg);
+      // ---------------- forward ----------------
+      if ((rc = map4(&T.fwd.tmA, a0, Cin, B, PP, tin.Cp, (uint64_t)B * tin.Cp, tin.plane_elems, 32, 128, false))) return rc;
+      if ((rc = map4(&T.fwd.tmB, pack0 + T.wf_off, T.wf_ld, T.wf_rows, 1, T.wf_ld, (uint64_t)T.wf_rows * T.wf_ld,
+                     S.pack_plane_elems, 32, fpad, false))) return rc;
+      T.fwd.mn = false; T.fwd.b_rows = spg * fpad; T.fwd.bn = fpad; T.fwd.tile0 = (int)pb.tiles.size();
+      for (int p = 0; p < PP; p++) {
+        const int ph = p / P, pw = p % P;
+        for (int g = 0; g < ngroups; g++) {
+          const int s0 = g * spg, s1 = std::min(R, s0 + spg);
+          const int seg0 = (int)pb.segs.size();
+          for (auto& tp : taps) {
+            const int dy = tp.first, dx = tp.second, ring = std::max(std::abs(dy), std::abs(dx));
+            if (ph + dy < 0 || ph + dy >= P || pw + dx < 0 || pw + dx >= P) continue;
+            const int nbx = std::min(s1, R - ring) - s0;
+            if (nbx <= 0) continue;
+            const int tap = (dy + h) * P + (dx + h);
+            TcSeg s{};
+            s.a2 = p + dy * P + dx; s.b1 = tap * R * fpad; s.nk = T.Kp / 32; s.n_mma = nbx * fpad; s.nb = nbx;
+            pb.segs.push_back(s);
+          }
+          const int nseg = (int)pb.segs.size() - seg0;
+          for (int bt = 0; bt < nbt; bt++) {
+            TcTile t = blank_tile();
+            t.seg_begin = seg0; t.seg_count = nseg; t.total_kb = nseg * (T.Kp / 32);
+            t.m_valid = (int)std::min<int64_t>(128, B - (int64_t)bt * 128);
+            t.ld_out = tout.Cp; t.stats_row = p * nbt + bt; t.a1_add = bt * 128; t.b1_add = s0 * fpad;
+            t.ncb = s1 - s0;
+            for (int s = s0; s < s1; s++) {
+              const int q = R - 1 - s;
+              TcColBlock& cb = t.cb[s - s0];
+              cb.tcol = (s - s0) * fpad; cb.width = f;
+              cb.out_off = ((int64_t)p * B + (int64_t)bt * 128) * tout.Cp + q * f;
+              cb.stats_col = q * f;
+            }
+            pb.tiles.push_back(t);
+          }
+        }
+      }
+      T.fwd.ntiles = (int)pb.tiles.size() - T.fwd.tile0;
+      T.stats_rows = PP * nbt;
+      // ---------------- dgrad ----------------
+      if (need_dgrad) {
+        int ntn, nw;
+        n_tiling(Cin, ntn, nw);
+        if ((rc = map4(&T.dg.tmA, gz0, T.Gp, B, PP, T.Gp, (uint64_t)B * T.Gp, S.gz_plane_elems, 32, 128, false))) return rc;
+        if ((rc = map4(&T.dg.tmB, pack0 + T.wd_off, T.wd_ld, T.wd_rows, 1, T.wd_ld, (uint64_t)T.wd_rows * T.wd_ld,
+                       S.pack_plane_elems, 32, nw, false))) return rc;
+        T.dg.mn = false; T.dg.b_rows = nw; T.dg.bn = nw; T.dg.tile0 = (int)pb.tiles.size();
+        for (int p = 0; p < PP; p++) {
+          const int ph = p / P, pw = p % P;
+          for (int j = 0; j < ntn; j++) {
+            const int seg0 = (int)pb.segs.size();
+            int tkb = 0;
+            for (auto& tp : taps) {
+              const int dy = tp.first, dx = tp.second, ring = std::max(std::abs(dy), std::abs(dx));
+              if (ph - dy < 0 || ph - dy >= P || pw - dx < 0 || pw - dx >= P) continue;
+              const int tap = (dy + h) * P + (dx + h);
+              TcSeg s{};
+              s.a2 = p - (dy * P + dx); s.b1 = tap * T.Cq + j * nw;
+              s.nk = (int)cdiv((R - ring) * fpad, 32); s.n_mma = r16(std::min(nw, Cin - j * nw)); s.nb = 1;
+              tkb += s.nk;
+              pb.segs.push_back(s);
+            }
+            const int nseg = (int)pb.segs.size() - seg0;
+            for (int bt = 0; bt < nbt; bt++) {
+              TcTile t = blank_tile();
+              t.seg_begin = seg0; t.seg_count = nseg; t.total_kb = tkb;
+              t.m_valid = (int)std::min<int64_t>(128, B - (int64_t)bt * 128);
+              t.ncb = 1; t.ld_out = tin.Cp; t.a1_add = bt * 128;
+              t.cb[0].out_off = ((int64_t)p * B + (int64_t)bt * 128) * tin.Cp + j * nw;
+              t.cb[0].width = std::min(nw, Cin - j * nw);
+              pb.tiles.push_back(t);
+            }
+          }
+        }
+        T.dg.ntiles = (int)pb.tiles.size() - T.dg.tile0;
+      }
+      // ---------------- wgrad ----------------
+      {
+        if ((rc = map4(&T.wg.tmA, a0, Cin, B, PP, tin.Cp, (uint64_t)B * tin.Cp, tin.plane_elems, 32, 32, true))) return rc;
+        if ((rc = map4(&T.wg.tmB, gz0, T.Gp, B, PP, T.Gp, (uint64_t)B * T.Gp, S.gz_plane_elems, 32, 32, true))) return rc;
+        T.wg.mn = true; T.wg.bn = 32; T.wg.b_rows = 0; T.wg.tile0 = (int)pb.tiles.size();
+        const int mt = (int)cdiv(Cin, 128);
+        const int nkb = (int)cdiv(B, 32);
+        int64_t pairs = 0;
+        for (auto& tp : taps) pairs += (int64_t)(P - std::abs(tp.first)) * (P - std::abs(tp.second));
+        const int pc = (int)std::max<int64_t>(1, cdiv(pairs * mt * ngroups, 296));  // positions per CTA
+        for (auto& tp : taps) {
+          const int dy = tp.first, dx = tp.second, ring = std::max(std::abs(dy), std::abs(dx));
+          std::vector<int> ps;  // output positions whose tap source is inside the patch
+          for (int p = 0; p < PP; p++) {
+            const int ph = p / P, pw = p % P;
+            if (ph + dy >= 0 && ph + dy < P && pw + dx >= 0 && pw + dx < P) ps.push_back(p);
+          }
+          for (int g = 0; g < ngroups; g++) {
+            const int s0 = g * spg, s1 = std::min(std::min(R, s0 + spg), R - ring);
+            if (s1 <= s0) continue;
+            const int ncols = (s1 - s0) * fpad;
+            for (int im = 0; im < mt; im++)
+              for (size_t c0 = 0; c0 < ps.size(); c0 += pc) {
+                TcTile t = blank_tile();
+                t.seg_begin = (int)pb.segs.size();
+                for (size_t ci = c0; ci < std::min(ps.size(), c0 + (size_t)pc); ci++) {
+                  TcSeg s{};
+                  s.a0 = im * 128; s.a2 = ps[ci] + dy * P + dx; s.b0 = s0 * fpad; s.b2 = ps[ci];
+                  s.nk = nkb; s.n_mma = r16(ncols); s.nb = (int)cdiv(s.n_mma, 32);
+                  T.wg.b_rows = std::max(T.wg.b_rows, s.nb * 32);
+                  t.total_kb += s.nk;
+                  pb.segs.push_back(s);
+                }
+                t.seg_count = (int)pb.segs.size() - t.seg_begin;
+                t.m_valid = std::min(128, Cin - im * 128);
+                t.ld_out = f;
+                t.ncb = s1 - s0;
+                for (int s = s0; s < s1; s++) {
+                  const int q = R - 1 - s, k = 2 * q + 1;
+                  TcColBlock& cb = t.cb[s - s0];
+                  cb.tcol = (s - s0) * fpad; cb.width = f;
+                  cb.out_off = L.w_off[q] + (int64_t)((dy + q) * k + (dx + q)) * Cin * f + (int64_t)im * 128 * f;
+                }
+                pb.tiles.push_back(t);
+              }
+          }
+        }
+        T.wg.ntiles = (int)pb.tiles.size() - T.wg.tile0;
+      }
+    } else {
+      const int Ct = tin.C, PP = tin.PP, Cout = L.Cout;
+      int ntn, nw;
+      n_tiling(Cout, ntn, nw);
+      // ---------------- forward ----------------
+      if ((rc = map4(&T.fwd.tmA, a0, Ct, B, PP, tin.Cp, (uint64_t)B * tin.Cp, tin.plane_elems, 32, 128, false))) return rc;
+      if ((rc = map4(&T.fwd.tmB, pack0 + T.wf_off, T.wf_ld, T.wf_rows, 1, T.wf_ld, (uint64_t)T.wf_rows * T.wf_ld,
+                     S.pack_plane_elems, 32, nw, false))) return rc;
+      T.fwd.mn = false; T.fwd.b_rows = nw; T.fwd.bn = nw; T.fwd.tile0 = (int)pb.tiles.size();
+      for (int j = 0; j < ntn; j++) {
+        const int seg0 = (int)pb.segs.size();
+        for (int pos = 0; pos < PP; pos++) {
+          TcSeg s{};
+          s.a2 = pos; s.b0 = pos * T.Kp; s.b1 = j * nw; s.nk = T.Kp / 32;
+          s.n_mma = r16(std::min(nw, Cout - j * nw)); s.nb = 1;
+          pb.segs.push_back(s);
+        }
+        for (int bt = 0; bt < nbt; bt++) {
+          TcTile t = blank_tile();
+          t.seg_begin = seg0; t.seg_count = PP; t.total_kb = PP * (T.Kp / 32);
+          t.m_valid = (int)std::min<int64_t>(128, B - (int64_t)bt * 128);
+          t.ncb = 1; t.ld_out = tout.Cp; t.stats_row = bt; t.a1_add = bt * 128;
+          t.cb[0].out_off = (int64_t)bt * 128 * tout.Cp + j * nw;
+          t.cb[0].width = std::min(nw, Cout - j * nw);
+          t.cb[0].stats_col = j * nw;
+          pb.tiles.push_back(t);
+        }
+      }
+      T.fwd.ntiles = (int)pb.tiles.size() - T.fwd.tile0;
+      T.stats_rows = nbt;
+      // ---------------- dgrad ----------------
+      if (need_dgrad) {
+        if ((rc = map4(&T.dg.tmA, gz0, Cout, B, 1, T.Gp, (uint64_t)B * T.Gp, S.gz_plane_elems, 32, 128, false))) return rc;
+        if ((rc = map4(&T.dg.tmB, pack0 + T.wd_off, T.wd_ld, T.wd_rows, 1, T.wd_ld, (uint64_t)T.wd_rows * T.wd_ld,
+                       S.pack_plane_elems, 32, T.Cq, false))) return rc;
+        T.dg.mn = false; T.dg.b_rows = T.Cq; T.dg.bn = T.Cq; T.dg.tile0 = (int)pb.tiles.size();
+        for (int pos = 0; pos < PP; pos++) {
+          TcSeg s{};
+          s.b1 = pos * T.Cq; s.nk = T.wd_ld / 32; s.n_mma = T.Cq; s.nb = 1;
+          const int sidx = (int)pb.segs.size();
+          pb.segs.push_back(s);
+          for (int bt = 0; bt < nbt; bt++) {
+            TcTile t = blank_tile();
+            t.seg_begin = sidx; t.seg_count = 1; t.total_kb = s.nk;
+            t.m_valid = (int)std::min<int64_t>(128, B - (int64_t)bt * 128);
+            t.ncb = 1; t.ld_out = tin.Cp; t.a1_add = bt * 128;
+            t.cb[0].out_off = ((int64_t)pos * B + (int64_t)bt * 128) * tin.Cp;
+            t.cb[0].width = Ct;
+            pb.tiles.push_back(t);
+          }
+        }
+        T.dg.ntiles = (int)pb.tiles.size() - T.dg.tile0;
+      }
+      // ---------------- wgrad ----------------
+      {
+        if ((rc = map4(&T.wg.tmA, a0, Ct, B, PP, tin.Cp, (uint64_t)B * tin.Cp, tin.plane_elems, 32, 32, true))) return rc;
+        if ((rc = map4(&T.wg.tmB, gz0, Cout, B, 1, T.Gp, (uint64_t)B * T.Gp, S.gz_plane_elems, 32, 32, true))) return rc;
+        T.wg.mn = true; T.wg.bn = 32; T.wg.b_rows = 0; T.wg.tile0 = (int)pb.tiles.size();
+        for (int pos = 0; pos < PP; pos++)
+          for (int j = 0; j < ntn; j++) {
+            const int width = std::min(nw, Cout - j * nw);
+            TcSeg s{};
+            s.a2 = pos; s.b0 = j * nw; s.nk = (int)cdiv(B, 32); s.n_mma = r16(width); s.nb = (int)cdiv(s.n_mma, 32);
+            T.wg.b_rows = std::max(T.wg.b_rows, s.nb * 32);
+            TcTile t = blank_tile();
+            t.seg_begin = (int)pb.segs.size(); t.seg_count = 1; t.total_kb = s.nk;
+            t.m_valid = Ct; t.ncb = 1; t.ld_out = Cout;
+            t.cb[0].out_off = L.w_off[0] + (int64_t)pos * Ct * Cout + j * nw;
+            t.cb[0].width = width;
+            pb.segs.push_back(s);
+            pb.tiles.push_back(t);
+          }
+        T.wg.ntiles = (int)pb.tiles.size() - T.wg.tile0;
+      }
+    }
+  }
+  // upload
+  if (pb.segs.size() > S.segs_cap) {
+    if (S.segs_dev) cudaFree(S.segs_dev);
+    S.segs_cap = pb.segs.size() + pb.segs.size() / 4;
+    HYP_CUDA(cudaMalloc(&S.segs_dev, S.segs_cap * sizeof(TcSeg)));
+  }
+  if (pb.tiles.size() > S.tiles_cap) {
+    if (S.tiles_dev) cudaFree(S.tiles_dev);
+    S.tiles_cap = pb.tiles.size() + pb.tiles.size() / 4;
+    HYP_CUDA(cudaMalloc(&S.tiles_dev, S.tiles_cap * sizeof(TcTile)));
+  }
+  HYP_CUDA(cudaDeviceSynchronize());  // earlier launches may still read the old tables
+  HYP_CUDA(cudaMemcpy(S.segs_dev, pb.segs.data(), pb.segs.size() * sizeof(TcSeg), cudaMemcpyHostToDevice));
+  HYP_CUDA(cudaMemcpy(S.tiles_dev, pb.tiles.data(), pb.tiles.size() * sizeof(TcTile), cudaMemcpyHostToDevice));
+  S.planned_B = (int)B;
+  return HYP_OK;
+}
+
+static int tc_run(hyp_model& m, const TcLaunch& l, float* out, float* stats, int stats_ld, int epi, const char* tag,
+                  double flops, cudaStream_t st) {
+  if (l.ntiles == 0) return HYP_OK;
+  TcState& S = *m.tc;
+  TcParams p{};
+  p.segs = S.segs_dev; p.tiles = S.tiles_dev + l.tile0; p.out = out; p.stats = stats; p.stats_ld = stats_ld;
+  p.epi = epi; p.b_rows = l.b_rows; p.bn = l.bn; p.chunk_kb = 0; p.stages = 0;
+  g_prof.begin(st, tag, flops, 0.0);
+  const int rc = l.mn ? launch_tc<true>(l.tmA, l.tmB, p, l.ntiles, st) : launch_tc<false>(l.tmA, l.tmB, p, l.ntiles, st);
+  g_prof.end(st);
+  return rc;
+}
+
+#define TC_PROF(name, bytes, launch)              \
+  do {                                            \
+    g_prof.begin(st, name, 0.0, (double)(bytes)); \
+    launch;                                       \
+    g_prof.end(st);                               \
+    HYP_LAUNCHED();                               \
+  } while (0)
+
+static inline int tc_grid(int64_t total) { return (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(total, 256), 148 * 16)); }
+
+static int tc_forward(hyp_model& m, const float* x, int64_t B, bool training, bool update_moving, uint64_t seed,
+                      cudaStream_t st) {
+  TcState& S = *m.tc;
+  int rc = tc_plan(m, B);
+  if (rc) return rc;
+  const int nl = training ? (int)m.layers.size() : m.last_eval_layer + 1;
+  float* pack0 = reinterpret_cast<float*>(m.ws + S.pack_off);
+  {
+    const TcTensor& tx = S.tt[0];
+    TC_PROF("tc_prep_input_kernel", 12.0 * B * tx.PP * tx.C,
+            (tc_prep_input_kernel<<<tc_grid(B * tx.PP * tx.C), 256, 0, st>>>(x, (int)B, tx.PP, tx.C, tx.Cp, tc_plane0(m, 0),
+                                                                             tc_plane1(m, 0))));
+    TC_PROF("tc_pack_weights_kernel", 12.0 * S.pack_plane_elems,
+            (tc_pack_weights_kernel<<<dim3(S.job_blocks, (unsigned)S.jobs.size()), 256, 0, st>>>(
+                S.jobs_dev, m.params, pack0, pack0 + S.pack_plane_elems)));
+  }
+  const float keep_prob = 1.f - m.d.drop_out_ratio;
+  float* part = reinterpret_cast<float*>(m.ws + S.part_off);
+  for (int li = 0; li < nl; li++) {
+    Layer& L = m.layers[li];
+    TcLayer& T = S.tl[li];
+    const TcTensor& tout = S.tt[L.out_t];
+    const int64_t rows = B * tout.PP;
+    float* Z = reinterpret_cast<float*>(m.ws + T.z_off);
+    rc = tc_run(m, T.fwd, Z, training ? part : nullptr, L.Cout, EPI_STORE, "tc_gemm_kernel/fwd", layer_flops(L, B), st);
+    if (rc) return rc;
+    float* mean = reinterpret_cast<float*>(m.ws + T.mean_off);
+    float* rstd = reinterpret_cast<float*>(m.ws + T.rstd_off);
+    if (training) {
+      TC_PROF("tc_bn_finalize_kernel", 8.0 * T.stats_rows * L.Cout,
+              (tc_bn_finalize_kernel<<<(unsigned)cdiv(L.Cout, 32), dim3(32, 32), 0, st>>>(
+                  part, T.stats_rows, L.Cout, L.Cout, (double)rows, m.d.bn_eps, m.d.bn_decay, m.state + L.mm_off,
+                  m.state + L.mm_off + L.Cout, mean, rstd, update_moving ? 1 : 0)));
+    } else {
+      TC_PROF("bn_finalize_kernel", 32.0 * L.Cout,
+              (bn_finalize_kernel<<<(unsigned)cdiv(L.Cout, 128), 128, 0, st>>>(
+                  nullptr, L.Cout, (double)rows, m.d.bn_eps, m.d.bn_decay, m.state + L.mm_off,
+                  m.state + L.mm_off + L.Cout, mean, rstd, 0, 0)));
+    }
+    TcApplyArgs p{};
+    p.z = Z; p.ldz = tout.Cp; p.mean = mean; p.rstd = rstd; p.beta = m.params + L.beta_off;
+    p.hi = tc_plane0(m, L.out_t); p.lo = tc_plane1(m, L.out_t); p.ldo = tout.Cp;
+    p.rows = rows; p.C = L.Cout; p.act = L.act; p.alpha = m.d.lrelu_alpha;
+    p.keep = (L.dropout && training) ? keep_prob : 1.f;
+    p.seed = seed; p.stream_id = L.drop_stream;
+    if (L.res.size() > 0) {
+      p.res0 = tc_plane0(m, L.res[0].src); p.idx0 = L.res[0].idx; p.ld0 = S.tt[L.res[0].src].Cp;
+    }
+    if (L.res.size() > 1) {
+      p.res1 = tc_plane0(m, L.res[1].src); p.idx1 = L.res[1].idx; p.ld1 = S.tt[L.res[1].src].Cp;
+    }
+    const double bytes = 4.0 * rows * L.Cout * (3 + L.res.size());
+    if (L.Cout % 4 == 0) {
+      TC_PROF("tc_bn_apply_kernel", bytes, (tc_bn_apply_kernel<4><<<tc_grid(rows * (L.Cout / 4)), 256, 0, st>>>(p)));
+    } else {
+      TC_PROF("tc_bn_apply_kernel", bytes, (tc_bn_apply_kernel<1><<<tc_grid(rows * L.Cout), 256, 0, st>>>(p)));
+    }
+  }
+  return HYP_OK;
+}
+
+static int tc_backward(hyp_model& m, const uint8_t* labels, int64_t B, float* loss_out, cudaStream_t st) {
+  TcState& S = *m.tc;
+  const hyp_model_desc& d = m.d;
+  const int nl = (int)m.layers.size();
+  std::vector<char> ginit(m.tensors.size(), 0);
+  HYP_CUDA(cudaMemsetAsync(m.grads, 0, (size_t)m.n_params * sizeof(float), st));
+  HYP_CUDA(cudaMemsetAsync(m.ws + S.mse_off, 0, 256, st));
+  float* ce = reinterpret_cast<float*>(m.ws + S.ce_off);
+  double* mse_acc = reinterpret_cast<double*>(m.ws + S.mse_off);
+  const TcTensor& tlog = S.tt[m.logits_t];
+  const TcTensor& trec = S.tt[m.recon_t];
+  const TcTensor& tx = S.tt[0];
+  TC_PROF("tc_ce_loss_kernel", 8.0 * B * d.classes,
+          (tc_ce_loss_kernel<<<(unsigned)cdiv(B * 32, 256), 256, 0, st>>>(tc_plane0(m, m.logits_t), tlog.Cp, labels, B,
+                                                                          d.classes, ce, tc_grad(m, m.logits_t), tlog.Cp,
+                                                                          1.f / (float)B)));
+  ginit[m.logits_t] = 1;
+  const int64_t D = (int64_t)tx.PP * tx.C;
+  TC_PROF("tc_mse_kernel", 12.0 * B * D,
+          (tc_mse_kernel<<<tc_grid(B * D), 256, 0, st>>>(tc_plane0(m, m.recon_t), trec.Cp, tc_plane0(m, 0), tx.Cp, (int)B,
+                                                         tx.PP, tx.C, mse_acc, tc_grad(m, m.recon_t), trec.Cp,
+                                                         1.f / (float)(B * D))));
+  ginit[m.recon_t] = 1;
+  loss_finalize_kernel<<<1, 256, 0, st>>>(ce, B, mse_acc, (double)(B * D), loss_out, nullptr);
+  HYP_LAUNCHED();
+
+  const float keep_prob = 1.f - d.drop_out_ratio;
+  float* gz0 = reinterpret_cast<float*>(m.ws + S.gz_off);
+  float* gz1 = gz0 + S.gz_plane_elems;
+  float* bpart = reinterpret_cast<float*>(m.ws + S.bpart_off);
+  for (int li = nl - 1; li >= 0; li--) {
+    Layer& L = m.layers[li];
+    TcLayer& T = S.tl[li];
+    const TcTensor& tout = S.tt[L.out_t];
+    const int64_t rows = B * tout.PP;
+    if (!ginit[L.out_t]) return fail(HYP_E_STATE, "backward: no gradient reached " + L.scope);
+    TcBnBwdArgs p{};
+    p.gout = tc_grad(m, L.out_t); p.ldg = tout.Cp;
+    p.z = reinterpret_cast<float*>(m.ws + T.z_off); p.ldz = tout.Cp;
+    p.mean = reinterpret_cast<float*>(m.ws + T.mean_off);
+    p.rstd = reinterpret_cast<float*>(m.ws + T.rstd_off);
+    p.beta = m.params + L.beta_off;
+    p.rows = rows; p.C = L.Cout; p.act = L.act; p.alpha = d.lrelu_alpha;
+    p.keep = L.dropout ? keep_prob : 1.f;
+    p.seed = m.last_seed; p.stream_id = L.drop_stream;
+    p.part = bpart;
+    float* s1 = reinterpret_cast<float*>(m.ws + T.s1_off);
+    float* s2 = reinterpret_cast<float*>(m.ws + T.s2_off);
+    p.s1 = s1; p.s2 = s2; p.gz_hi = gz0; p.gz_lo = gz1; p.ldgz = T.Gp;
+    p.gcols = T.kind == 1 ? T.Gp : L.Cout;
+    p.fpad = T.kind == 1 ? T.fpad : 0; p.f = T.f; p.R = T.R;
+    const int cblocks = (int)cdiv(L.Cout, 32);
+    int rblocks = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(rows, 64), cdiv(148 * 8, cblocks)));
+    const int rpb = (int)cdiv(rows, rblocks);
+    rblocks = (int)cdiv(rows, rpb);
+    TC_PROF("tc_bn_bwd_reduce_kernel", 8.0 * rows * L.Cout,
+            (tc_bn_bwd_reduce_kernel<<<dim3(cblocks, rblocks), 256, 0, st>>>(p, rpb)));
+    tc_bn_bwd_finalize_kernel<<<(unsigned)cdiv(L.Cout, 32), dim3(32, 32), 0, st>>>(bpart, rblocks, L.Cout, (double)rows, s1,
+                                                                                   s2, m.grads + L.beta_off);
+    HYP_LAUNCHED();
+    TC_PROF("tc_bn_bwd_apply_kernel", 4.0 * rows * (2.0 * L.Cout + 2.0 * p.gcols),
+            (tc_bn_bwd_apply_kernel<<<tc_grid(rows * p.gcols), 256, 0, st>>>(p)));
+    for (const Resid& r : L.res) {
+      const Tensor& src = m.tensors[r.src];
+      if (!src.needs_grad) continue;
+      TC_PROF("tc_resid_bwd_kernel", 4.0 * rows * (L.Cout + 2.0 * src.C),
+              (tc_resid_bwd_kernel<<<tc_grid(rows * src.C), 256, 0, st>>>(p.gout, tout.Cp, tc_grad(m, r.src),
+                                                                          S.tt[r.src].Cp, src.C, r.lo, r.hi, rows,
+                                                                          ginit[r.src])));
+      ginit[r.src] = 1;
+    }
+    int rc = tc_run(m, T.wg, m.grads, nullptr, 0, EPI_ATOMIC, "tc_gemm_kernel/wgrad", layer_flops(L, B), st);
+    if (rc) return rc;
+    if (m.tensors[L.in_t].needs_grad) {
+      rc = tc_run(m, T.dg, tc_grad(m, L.in_t), nullptr, 0, ginit[L.in_t] ? EPI_ACCUM : EPI_STORE, "tc_gemm_kernel/dgrad",
+                  layer_flops(L, B), st);
+      if (rc) return rc;
+      ginit[L.in_t] = 1;
+    }
+  }
+  return HYP_OK;
+}
+
+}  // namespace tc
+}  // namespace hyp

@@ -1,0 +1,343 @@
+// HBM-bound kernels of the tensor-core path.  Activations live position-major:
+//   tensor[pos][b][ld]   (pos = h*P + w of the patch, b = sample, ld = channels padded to 4)
+// so every spatial tap of a k x k conv is a plain row-offset into the same matrix, and they
+// come as two fp32 planes: plane 0 = the value, plane 1 = TF32 rounding of what the tensor
+// core drops from plane 0 (its 13 low mantissa bits) — see hyp_tc.cuh.
+#pragma once
+#include "hyp_kernels.cuh"
+#include "hyp_tc.cuh"
+
+namespace hyp {
+namespace tc {
+
+__device__ __forceinline__ float tf32_lo(float a) {
+  return tf32_rna(a - __uint_as_float(__float_as_uint(a) & 0xffffe000u));
+}
+
+// x [B][PP][C] (NHWC patches as the importer hands them over) -> planes [PP][B][ld]
+__global__ void tc_prep_input_kernel(const float* __restrict__ x, int B, int PP, int C, int ld, float* __restrict__ hi,
+                                     float* __restrict__ lo) {
+  const int64_t total = (int64_t)B * PP * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t bp = i / C;
+    const int c = (int)(i - bp * C);
+    const int b = (int)(bp / PP), pos = (int)(bp - (int64_t)b * PP);
+    const float v = x[i];
+    const int64_t o = ((int64_t)pos * B + b) * ld + c;
+    hi[o] = v;
+    lo[o] = tf32_lo(v);
+  }
+}
+
+// position-major [PP][B][ld] -> dense [B][PP][C] (API outputs, tests)
+__global__ void tc_extract_kernel(const float* __restrict__ src, int ld, int B, int PP, int C, float* __restrict__ dst) {
+  const int64_t total = (int64_t)B * PP * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t bp = i / C;
+    const int c = (int)(i - bp * C);
+    const int b = (int)(bp / PP), pos = (int)(bp - (int64_t)b * PP);
+    dst[i] = src[((int64_t)pos * B + b) * ld + c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// weight packing: dst[r][k] (two planes) = src[r1*sr1 + r0*sr0 + k1*sk1 + k0*sk0] or 0, with
+// r = r1*RD + r0, k = k1*KD + k0, valid iff r0 < RV and k0 < KV.
+struct PackJob {
+  int64_t src_off;  // element offset inside params
+  int64_t dst_off;  // element offset inside one plane of the packed buffer
+  int32_t rows, cols, ld;
+  int32_t RD, RV, KD, KV;
+  int32_t sr1, sr0, sk1, sk0;
+  int32_t pad;
+};
+__global__ void tc_pack_weights_kernel(const PackJob* __restrict__ jobs, const float* __restrict__ params,
+                                       float* __restrict__ hi, float* __restrict__ lo) {
+  const PackJob J = jobs[blockIdx.y];
+  const int64_t total = (int64_t)J.rows * J.cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / J.cols), k = (int)(i - (int64_t)r * J.cols);
+    const int r1 = r / J.RD, r0 = r - r1 * J.RD;
+    const int k1 = k / J.KD, k0 = k - k1 * J.KD;
+    float v = 0.f;
+    if (r0 < J.RV && k0 < J.KV)
+      v = params[J.src_off + (int64_t)r1 * J.sr1 + (int64_t)r0 * J.sr0 + (int64_t)k1 * J.sk1 + (int64_t)k0 * J.sk0];
+    const int64_t o = J.dst_off + (int64_t)r * J.ld + k;
+    hi[o] = v;
+    lo[o] = tf32_lo(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// BatchNorm statistics from the GEMM epilogue's per-tile partial sums part[nrows][2][ld]
+// block = (32 channels, 32 row lanes)
+__global__ void tc_bn_finalize_kernel(const float* __restrict__ part, int nrows, int ld, int C, double count, float eps,
+                                      float decay, float* __restrict__ moving_mean, float* __restrict__ moving_var,
+                                      float* __restrict__ mean_out, float* __restrict__ rstd_out, int update_moving) {
+  __shared__ double sh1[32][33], sh2[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = blockIdx.x * 32 + tx;
+  double a1 = 0, a2 = 0;
+  if (c < C) {
+    for (int r = ty; r < nrows; r += 32) {
+      a1 += (double)part[((size_t)r * 2 + 0) * ld + c];
+      a2 += (double)part[((size_t)r * 2 + 1) * ld + c];
+    }
+  }
+  sh1[ty][tx] = a1;
+  sh2[ty][tx] = a2;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    for (int i = 1; i < 32; i++) { a1 += sh1[i][tx]; a2 += sh2[i][tx]; }
+    const double mean = a1 / count;
+    double var = a2 / count - mean * mean;
+    if (var < 0) var = 0;
+    const float meanf = (float)mean, varf = (float)var;
+    mean_out[c] = meanf;
+    const float x = varf + eps;
+    float r = rsqrtf(x);
+    r = r * (1.5f - 0.5f * x * r * r);
+    rstd_out[c] = r;
+    if (update_moving) {
+      const double unbiased = var * (count / fmax(count - 1.0, 1.0));
+      moving_mean[c] = moving_mean[c] * decay + meanf * (1.f - decay);
+      moving_var[c] = moving_var[c] * decay + (float)unbiased * (1.f - decay);
+    }
+  }
+}
+
+struct TcApplyArgs {
+  const float* z;  // [rows][ldz] pre-BN
+  int ldz;
+  const float *mean, *rstd, *beta;
+  float *hi, *lo;  // output planes [rows][ldo]
+  int ldo;
+  int64_t rows;
+  int C, act;
+  float alpha, keep;
+  uint64_t seed;
+  uint32_t stream_id;
+  const float* res0;  // residual source plane 0 [rows][ld0]; idx0 == NULL: identity
+  const int* idx0;
+  int ld0;
+  const float* res1;
+  const int* idx1;
+  int ld1;
+};
+
+// out = dropout(act(bn(z))) + res0[:, idx0] + res1[:, idx1]; VEC channels per thread
+template <int VEC>
+__global__ void tc_bn_apply_kernel(const TcApplyArgs p) {
+  const int cq = (p.C + VEC - 1) / VEC;
+  const int64_t total = p.rows * cq;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / cq;
+    const int c0 = (int)(i - m * cq) * VEC;
+    float v[VEC];
+    if (VEC == 4) {
+      const float4 t = *reinterpret_cast<const float4*>(p.z + m * p.ldz + c0);
+      v[0] = t.x; v[1 % VEC] = t.y; v[2 % VEC] = t.z; v[3 % VEC] = t.w;
+    } else {
+      v[0] = p.z[m * p.ldz + c0];
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; j++) {
+      const int c = c0 + j;
+      float y = (v[j] - p.mean[c]) * p.rstd[c] + p.beta[c];
+      y = act_fwd(y, p.act, p.alpha);
+      if (p.keep < 1.f) y = (philox_uniform(p.seed, p.stream_id, (uint64_t)(m * p.C + c)) < p.keep) ? y / p.keep : 0.f;
+      if (p.res0) y += p.res0[m * p.ld0 + (p.idx0 ? p.idx0[c] : c)];
+      if (p.res1) y += p.res1[m * p.ld1 + (p.idx1 ? p.idx1[c] : c)];
+      v[j] = y;
+    }
+    if (VEC == 4) {
+      *reinterpret_cast<float4*>(p.hi + m * p.ldo + c0) = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
+      *reinterpret_cast<float4*>(p.lo + m * p.ldo + c0) =
+          make_float4(tf32_lo(v[0]), tf32_lo(v[1 % VEC]), tf32_lo(v[2 % VEC]), tf32_lo(v[3 % VEC]));
+    } else {
+      p.hi[m * p.ldo + c0] = v[0];
+      p.lo[m * p.ldo + c0] = tf32_lo(v[0]);
+    }
+  }
+}
+
+struct TcBnBwdArgs {
+  const float* gout;  // [rows][ldg] gradient w.r.t. the layer's output tensor
+  int ldg;
+  const float* z;     // [rows][ldz]
+  int ldz;
+  const float *mean, *rstd, *beta;
+  int64_t rows;
+  int C, act;
+  float alpha, keep;
+  uint64_t seed;
+  uint32_t stream_id;
+  float* part;        // [row blocks][2][C]   (reduce)
+  const float *s1, *s2;  // [C] means of g_y and g_y*zhat   (apply)
+  float *gz_hi, *gz_lo;  // [rows][ldgz]                   (apply)
+  int ldgz;
+  int gcols;          // columns of gz to write
+  int fpad, f, R;     // level layers: gz column j = slot*fpad + n holds channel (R-1-slot)*f + n; fpad == 0: identity
+};
+
+__device__ __forceinline__ float tc_bn_gy(const TcBnBwdArgs& p, int64_t m, int c, float& zhat) {
+  zhat = (p.z[m * p.ldz + c] - p.mean[c]) * p.rstd[c];
+  const float y = zhat + p.beta[c];
+  float g = p.gout[m * p.ldg + c];
+  if (p.keep < 1.f) g = (philox_uniform(p.seed, p.stream_id, (uint64_t)(m * p.C + c)) < p.keep) ? g / p.keep : 0.f;
+  if (p.act == ACT_LRELU) {
+    g = (y > 0.f) ? g : g * p.alpha;
+  } else if (p.act == ACT_SIGMOID) {
+    const float s = 1.f / (1.f + __expf(-y));
+    g = g * s * (1.f - s);
+  }
+  return g;
+}
+
+// block = 32 columns x 8 row lanes; grid = (ceil(C/32), row blocks); deterministic partials
+__global__ void tc_bn_bwd_reduce_kernel(const TcBnBwdArgs p, int rows_per_block) {
+  __shared__ float sh1[8][33], sh2[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = min((int64_t)p.rows, r0 + rows_per_block);
+  float a1 = 0.f, a2 = 0.f;
+  if (c < p.C) {
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+      float zhat;
+      const float g = tc_bn_gy(p, r, c, zhat);
+      a1 += g;
+      a2 += g * zhat;
+    }
+  }
+  sh1[ty][tx] = a1;
+  sh2[ty][tx] = a2;
+  __syncthreads();
+  if (ty == 0 && c < p.C) {
+#pragma unroll
+    for (int i = 1; i < 8; i++) { a1 += sh1[i][tx]; a2 += sh2[i][tx]; }
+    p.part[((size_t)blockIdx.y * 2 + 0) * p.C + c] = a1;
+    p.part[((size_t)blockIdx.y * 2 + 1) * p.C + c] = a2;
+  }
+}
+
+// block (32, 32): partials -> s1, s2 (means), gbeta (sum)
+__global__ void tc_bn_bwd_finalize_kernel(const float* __restrict__ part, int nblocks, int C, double rows,
+                                          float* __restrict__ s1, float* __restrict__ s2, float* __restrict__ gbeta) {
+  __shared__ double sh1[32][33], sh2[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = blockIdx.x * 32 + tx;
+  double a1 = 0, a2 = 0;
+  if (c < C) {
+    for (int r = ty; r < nblocks; r += 32) {
+      a1 += (double)part[((size_t)r * 2 + 0) * C + c];
+      a2 += (double)part[((size_t)r * 2 + 1) * C + c];
+    }
+  }
+  sh1[ty][tx] = a1;
+  sh2[ty][tx] = a2;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    for (int i = 1; i < 32; i++) { a1 += sh1[i][tx]; a2 += sh2[i][tx]; }
+    s1[c] = (float)(a1 / rows);
+    s2[c] = (float)(a2 / rows);
+    gbeta[c] = (float)a1;
+  }
+}
+
+// gz = rstd * (g_y - mean(g_y) - zhat * mean(g_y * zhat)), written as (value, lo) planes in the
+// column order the dgrad / wgrad GEMMs want
+__global__ void tc_bn_bwd_apply_kernel(const TcBnBwdArgs p) {
+  const int64_t total = p.rows * p.gcols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / p.gcols;
+    const int j = (int)(i - m * p.gcols);
+    int c = j;
+    bool valid = j < p.C;
+    if (p.fpad) {
+      const int slot = j / p.fpad, n = j - slot * p.fpad;
+      valid = n < p.f && slot < p.R;
+      c = (p.R - 1 - slot) * p.f + n;
+    }
+    float v = 0.f;
+    if (valid) {
+      float zhat;
+      const float g = tc_bn_gy(p, m, c, zhat);
+      v = p.rstd[c] * (g - p.s1[c] - zhat * p.s2[c]);
+    }
+    p.gz_hi[m * p.ldgz + j] = v;
+    p.gz_lo[m * p.ldgz + j] = tf32_lo(v);
+  }
+}
+
+// residual backward: gsrc[m, c'] (+)= sum_{j in [lo[c'], hi[c'])} gout[m, j]   (lo == NULL: identity)
+__global__ void tc_resid_bwd_kernel(const float* __restrict__ gout, int ldg, float* __restrict__ gsrc, int lds, int Csrc,
+                                    const int* __restrict__ lo, const int* __restrict__ hi, int64_t rows,
+                                    int accumulate) {
+  const int64_t total = rows * Csrc;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / Csrc;
+    const int c = (int)(i - m * Csrc);
+    float v = 0.f;
+    if (lo) {
+      for (int j = lo[c]; j < hi[c]; j++) v += gout[m * ldg + j];
+    } else {
+      v = gout[m * ldg + c];
+    }
+    float* d = gsrc + m * lds + c;
+    *d = accumulate ? *d + v : v;
+  }
+}
+
+// softmax cross-entropy per row (one warp per row) on padded logits + gradient
+__global__ void tc_ce_loss_kernel(const float* __restrict__ logits, int ld, const uint8_t* __restrict__ labels,
+                                  int64_t B, int classes, float* __restrict__ ce_out, float* __restrict__ glogits,
+                                  int ldg, float gscale) {
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const float* lp = logits + row * ld;
+  float mx = -INFINITY;
+  for (int c = lane; c < classes; c += 32) mx = fmaxf(mx, lp[c]);
+  mx = warp_max(mx);
+  float se = 0.f;
+  for (int c = lane; c < classes; c += 32) se += expf(lp[c] - mx);
+  se = warp_sum(se);
+  const float lse = mx + logf(se);
+  const int lab = labels[row];
+  if (lane == 0) ce_out[row] = lse - lp[lab];
+  if (glogits) {
+    for (int c = lane; c < classes; c += 32) {
+      const float sm = expf(lp[c] - lse);
+      glogits[row * ldg + c] = (sm - (c == lab ? 1.f : 0.f)) * gscale;
+    }
+  }
+}
+
+// sum (recon - x)^2: recon [B][ldr] with feature pos*C + c; x planes position-major [PP][B][ldx]
+__global__ void tc_mse_kernel(const float* __restrict__ recon, int ldr, const float* __restrict__ xin, int ldx, int B,
+                              int PP, int C, double* __restrict__ acc, float* __restrict__ grecon, int ldg,
+                              float gscale) {
+  __shared__ float sh[32];
+  const int64_t D = (int64_t)PP * C, n = (int64_t)B * D;
+  float s = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / D);
+    const int fidx = (int)(i - (int64_t)b * D);
+    const int pos = fidx / C, c = fidx - pos * C;
+    const float d = recon[(int64_t)b * ldr + fidx] - xin[((int64_t)pos * B + b) * ldx + c];
+    s += d * d;
+    if (grecon) grecon[(int64_t)b * ldg + fidx] = 2.f * d * gscale;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    if (threadIdx.x == 0) atomicAdd(acc, (double)s);
+  }
+}
+
+}  // namespace tc
+}  // namespace hyp

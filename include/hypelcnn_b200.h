@@ -158,11 +158,17 @@ int hyp_scatter_class_map(const uint8_t* pred, const int32_t* targets_xy, int64_
 /* ---- introspection used by the parity tests -------------------------------------------- */
 /* device pointer + element count of an internal tensor of the last forward/backward.
  * what: 0 activation (post BN/act/residual) of tensor `name`, 1 pre-BN output of layer
- * `name`, 2 gradient w.r.t. activation tensor `name`. */
+ * `name`, 2 gradient w.r.t. activation tensor `name`, 3 BatchNorm batch mean [Cout] of layer
+ * `name`.  Tensors come back dense, [B][P*P][C]. */
 int hyp_model_debug_tensor(hyp_model* m, const char* name, int what, float** ptr, int64_t* numel);
 /* the 0/1 keep mask hyp_model_forward applies on dropout layer `layer_scope` for `seed` */
 int hyp_model_dropout_mask(hyp_model* m, const char* layer_scope, uint64_t seed, int64_t B,
                            uint8_t* mask_out, void* stream);
+/* probe of the tcgen05/TMA segment-GEMM building block used by the tensor-core precision
+ * modes (3xTF32 split).  mn=0: A[M,K], B[N,K] -> D = A*B^T; mn=1: A[K,M], B[K,N] -> D = A^T*B.
+ * stats (nullable): [ceil(M/128)][2][N] per-tile column sums / sums of squares. */
+int hyp_debug_tc_gemm(int mn, const float* A, const float* B, int M, int N, int K, float* D,
+                      float* stats, int raw_hi, int bn, int ksplit, int chunk_kb, void* stream);
 /* number of kernels launched by this library on this thread since the last reset */
 int64_t hyp_launch_count(int reset);
 /* per-kernel-class timing with CUDA events around every launch (off by default; bench.py

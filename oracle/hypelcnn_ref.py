@@ -239,13 +239,19 @@ def resample(src, cout):
     return src[..., torch.tensor(idx, dtype=torch.long)]
 
 
-def forward(variables, x, classes, alg, is_training, dropout_masks=None, update_moving=True):
+def forward(variables, x, classes, alg, is_training, dropout_masks=None, update_moving=True, lrelu_gates=None):
     """HYPELCNN forward.  x [B,P,P,C].  Returns dict: logits, recon (or None), tensors{name:
     activation}, pre{scope: pre-BN conv output}, new_variables (moving stats updated when
     training), saved BN stats.
 
     dropout_masks: {scope: 0/1 tensor [B,size]} — kept elements; None -> no dropout applied
     when keep_prob==1, else error in training (TF's RNG stream cannot be reproduced).
+    lrelu_gates: optional {scope: bool tensor shaped like the layer output} — which side of
+    the LeakyReLU kink each element is on.  max(y, alpha*y) is not differentiable at y == 0
+    and, among millions of activations, a few land within fp32 rounding of 0; a gradient
+    comparison is only meaningful when both sides take the same branch there, so the parity
+    tests pass the branch the implementation under test took (the forward value changes by
+    at most (1-alpha)*|y| ~ 1e-7 for those elements).
     """
     P, C = x.shape[1], x.shape[3]
     plan = build_plan(P, C, classes, alg, is_training)
@@ -275,7 +281,10 @@ def forward(variables, x, classes, alg, is_training, dropout_masks=None, update_
         if is_training and update_moving:
             newv[bn + "moving_mean"], newv[bn + "moving_variance"] = mm, mv
         if l.act == "lrelu":
-            y = leaky_relu(y, alpha)
+            if lrelu_gates is not None and l.scope in lrelu_gates:
+                y = torch.where(lrelu_gates[l.scope], y, alpha * y)
+            else:
+                y = leaky_relu(y, alpha)
         elif l.act == "sigmoid":
             y = torch.sigmoid(y)
         if l.dropout and is_training and keep < 1.0:  # slim dropout: x*mask/keep_prob (App. A.5)
@@ -302,13 +311,13 @@ def per_sample_loss(logits, recon, x, labels):
     return ce + mse
 
 
-def loss_and_grads(variables, x, labels, classes, alg, dropout_masks=None):
+def loss_and_grads(variables, x, labels, classes, alg, dropout_masks=None, lrelu_gates=None):
     """optimize_nn's loss = mean_B(per-sample loss) (common/common_nn_ops.py:214) and its
     gradients w.r.t. every trainable variable (autograd on the restatement).  L2 regulariser
     terms are NOT part of the optimised loss (App. A.7)."""
     leaf = {k: (v.clone().requires_grad_(True) if ("weights" in k or k.endswith("beta")) else v)
             for k, v in variables.items()}
-    out = forward(leaf, x, classes, alg, True, dropout_masks)
+    out = forward(leaf, x, classes, alg, True, dropout_masks, lrelu_gates=lrelu_gates)
     loss = per_sample_loss(out["logits"], out["recon"], x, labels).mean()
     names = [k for k, v in leaf.items() if v.requires_grad]
     grads = torch.autograd.grad(loss, [leaf[k] for k in names], allow_unused=True)

@@ -119,18 +119,47 @@ CASES = {
 }
 
 
-def _make(E, case, drop=0.0):
+PRECISIONS = ["fp32", "3xtf32"]  # FFMA engine and the tcgen05 3xTF32 engine: same tests, same tolerances
+
+
+@pytest.fixture(params=PRECISIONS)
+def prec(request):
+    return request.param
+
+
+def _make(E, case, drop=0.0, precision="fp32"):
     c = CASES[case]
     alg = {**c["alg"], "drop_out_ratio": drop}
-    eng = E.PatchEngine(c["P"], c["C"], c["classes"], alg, max_batch=c["B"])
+    eng = E.PatchEngine(c["P"], c["C"], c["classes"], alg, max_batch=c["B"], precision=precision)
     eng.init_variables(seed=1234)
     x, y = synthetic_batch(c["B"], c["P"], c["C"], c["classes"])
     return eng, alg, c, x, y
 
 
+def engine_lrelu_gates(eng, c, alg):
+    """Which branch of every LeakyReLU the engine took in its last training forward:
+    y = (z - mean) * rstd + beta with beta == 0 (fresh init) has the sign of fl(z - mean), an
+    exactly reproducible fp32 subtraction of the engine's own z and batch mean."""
+    gates = {}
+    B, P = c["B"], c["P"]
+    for l in R.build_plan(c["P"], c["C"], c["classes"], alg, True):
+        if l.act != "lrelu":
+            continue
+        lscope = l.concat_slot[0] if l.concat_slot is not None else l.scope
+        assert float(eng.variable(f"nn_core/{l.scope}/BatchNorm/beta").abs().max()) == 0.0
+        z = eng.debug_tensor(lscope, 1).cpu()
+        mean = eng.debug_tensor(lscope, 3).cpu()
+        z = z.reshape(B, P, P, -1) if l.kind == "conv" else z.reshape(B, -1)
+        g = (z - mean) > 0
+        if l.concat_slot is not None:
+            g = g[..., l.concat_slot[1]: l.concat_slot[1] + l.cout]
+        gates[l.scope] = g
+    return gates
+
+
 @pytest.mark.parametrize("case", ["tiny", "c5", "nonres", "c2"])
-def test_variable_table_matches_reference_names(E, case):
-    eng, alg, c, x, y = _make(E, case)
+def test_variable_table_matches_reference_names(E, case, prec):
+    eng, alg, c, x, y = _make(E, case, precision=prec)
     specs = R.variable_specs(c["P"], c["C"], c["classes"], alg)
     assert set(eng.variables) == {n for n, _, _ in specs}
     for n, shape, kind in specs:
@@ -141,8 +170,8 @@ def test_variable_table_matches_reference_names(E, case):
 
 
 @pytest.mark.parametrize("case", ["tiny", "c5", "nonres", "c2"])
-def test_forward_training_parity_per_layer(E, case):
-    eng, alg, c, x, y = _make(E, case)
+def test_forward_training_parity_per_layer(E, case, prec):
+    eng, alg, c, x, y = _make(E, case, precision=prec)
     v = oracle_variables(eng)
     ref = R.forward(v, torch.tensor(x, dtype=torch.float64), c["classes"], alg, True)
     logits, recon = eng.forward(dev(x), True, True, seed=0)
@@ -168,8 +197,8 @@ def test_forward_training_parity_per_layer(E, case):
 
 
 @pytest.mark.parametrize("case", ["tiny", "c2"])
-def test_forward_eval_parity(E, case):
-    eng, alg, c, x, y = _make(E, case)
+def test_forward_eval_parity(E, case, prec):
+    eng, alg, c, x, y = _make(E, case, precision=prec)
     # non-trivial moving statistics: run two training forwards first (same on both sides)
     v = oracle_variables(eng)
     xt = torch.tensor(x, dtype=torch.float64)
@@ -194,15 +223,16 @@ def test_forward_eval_parity(E, case):
 
 
 @pytest.mark.parametrize("case", ["tiny", "c5", "nonres", "c2"])
-def test_loss_and_gradient_parity(E, case):
-    eng, alg, c, x, y = _make(E, case)
+def test_loss_and_gradient_parity(E, case, prec):
+    eng, alg, c, x, y = _make(E, case, precision=prec)
     v = oracle_variables(eng)
-    loss_ref, g_ref, out = R.loss_and_grads(v, torch.tensor(x, dtype=torch.float64), torch.tensor(y.astype(numpy.int64)),
-                                            c["classes"], alg)
-    _, g_ref32, _ = R.loss_and_grads(oracle_variables(eng, torch.float32), torch.tensor(x), torch.tensor(y.astype(numpy.int64)),
-                                     c["classes"], alg)
     xd, yd = dev(x), dev(y)
     logits, recon = eng.forward(xd, True, True, seed=0)
+    gates = engine_lrelu_gates(eng, c, alg)  # see hypelcnn_ref.forward: same LeakyReLU branch on both sides
+    loss_ref, g_ref, out = R.loss_and_grads(v, torch.tensor(x, dtype=torch.float64), torch.tensor(y.astype(numpy.int64)),
+                                            c["classes"], alg, lrelu_gates=gates)
+    _, g_ref32, _ = R.loss_and_grads(oracle_variables(eng, torch.float32), torch.tensor(x), torch.tensor(y.astype(numpy.int64)),
+                                     c["classes"], alg, lrelu_gates=gates)
     per = eng.per_sample_loss(logits, recon, xd, yd)
     ref_per = R.per_sample_loss(out["logits"], out["recon"], torch.tensor(x, dtype=torch.float64),
                                 torch.tensor(y.astype(numpy.int64)))
@@ -218,9 +248,9 @@ def test_loss_and_gradient_parity(E, case):
         assert_grad_close(eng.gradient(name).cpu().numpy(), g_ref[name].numpy(), g_ref32[name].numpy(), f"grad {name}")
 
 
-def test_backward_requires_training_forward(E):
+def test_backward_requires_training_forward(E, prec):
     from hypelcnn_b200 import NativeError
-    eng, alg, c, x, y = _make(E, "tiny")
+    eng, alg, c, x, y = _make(E, "tiny", precision=prec)
     xd, yd = dev(x), dev(y)
     eng.forward(xd, False)
     with pytest.raises(NativeError) as ei:
@@ -228,8 +258,8 @@ def test_backward_requires_training_forward(E):
     assert ei.value.code == -3
 
 
-def test_dropout_with_injected_mask_parity(E):
-    eng, alg, c, x, y = _make(E, "c5", drop=0.70)
+def test_dropout_with_injected_mask_parity(E, prec):
+    eng, alg, c, x, y = _make(E, "c5", drop=0.70, precision=prec)
     seed = 99
     xd, yd = dev(x), dev(y)
     logits, recon = eng.forward(xd, True, True, seed=seed)
@@ -240,10 +270,12 @@ def test_dropout_with_injected_mask_parity(E):
             assert 0.15 < m.float().mean().item() < 0.45  # keep_prob = 0.30
             masks[l.scope] = m.double()
     v = oracle_variables(eng)
+    gates = engine_lrelu_gates(eng, c, alg)
     loss_ref, g_ref, out = R.loss_and_grads(v, torch.tensor(x, dtype=torch.float64), torch.tensor(y.astype(numpy.int64)),
-                                            c["classes"], alg, dropout_masks=masks)
+                                            c["classes"], alg, dropout_masks=masks, lrelu_gates=gates)
     _, g_ref32, _ = R.loss_and_grads(oracle_variables(eng, torch.float32), torch.tensor(x), torch.tensor(y.astype(numpy.int64)),
-                                     c["classes"], alg, dropout_masks={k: m.float() for k, m in masks.items()})
+                                     c["classes"], alg, dropout_masks={k: m.float() for k, m in masks.items()},
+                                     lrelu_gates=gates)
     assert_close(logits.cpu().numpy(), out["logits"].detach().numpy(), RTOL, ATOL, "logits with dropout")
     eng.loss_backward(xd, yd)
     for name in ("nn_core/fc_0/weights", "nn_core/conv_enc_0/weights", "nn_core/connector_0_conv3x3/weights"):
@@ -283,8 +315,8 @@ def test_training_trajectory_parity(E, case):
         assert_close_scaled(eng.variable(name).cpu().numpy(), v[name].numpy(), 2e-3, name)
 
 
-def test_weights_shared_across_calls_and_capacity_growth(E):
-    eng, alg, c, x, y = _make(E, "tiny")
+def test_weights_shared_across_calls_and_capacity_growth(E, prec):
+    eng, alg, c, x, y = _make(E, "tiny", precision=prec)
     before = eng.export_variables()
     x2, _ = synthetic_batch(c["B"] * 3, c["P"], c["C"], c["classes"], seed=5)
     la, _ = eng.forward(dev(x2), False)  # larger than max_batch: workspace grows, parameters stay

@@ -1,0 +1,90 @@
+"""GPU tests of the tcgen05/TMA segment-GEMM building block (3xTF32 split) through the C ABI probe
+``hyp_debug_tc_gemm``, against a float64 matmul of the same inputs."""
+import ctypes
+
+import numpy
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def tc_gemm(mn, A, B, raw_hi=0, bn=0, ksplit=1, stats=False, chunk_kb=0):
+    from hypelcnn_b200 import _native as N
+    A, B = A.cuda().contiguous(), B.cuda().contiguous()
+    if mn:
+        K, M = A.shape
+        Nn = B.shape[1]
+    else:
+        M, K = A.shape
+        Nn = B.shape[0]
+    D = torch.zeros((M, Nn), dtype=torch.float32, device="cuda")
+    S = torch.zeros(((M + 127) // 128, 2, Nn), dtype=torch.float32, device="cuda") if stats else None
+    N.check(N.lib().hyp_debug_tc_gemm(mn, ctypes.c_void_p(A.data_ptr()), ctypes.c_void_p(B.data_ptr()), M, Nn, K,
+                                      ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(S.data_ptr() if stats else 0),
+                                      raw_hi, bn, ksplit, chunk_kb, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    return (D.cpu(), S.cpu()) if stats else D.cpu()
+
+
+def rel_err(got, ref):
+    return float((got.double() - ref).abs().max() / ref.abs().max())
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 32), (128, 256, 64), (300, 120, 145), (256, 240, 480), (1000, 480, 240),
+                                   (77, 16, 8), (130, 980, 2940)])
+def test_kmajor_3xtf32_matches_fp64(M, N, K):
+    g = torch.Generator().manual_seed(M * 7 + N)
+    A = torch.randn((M, K), generator=g)
+    B = torch.randn((N, K), generator=g)
+    ref = A.double() @ B.double().T
+    got = tc_gemm(0, A, B)
+    fp32 = rel_err(A @ B.T, ref)
+    err = rel_err(got, ref)
+    assert err < max(3e-6, 4 * fp32), (err, fp32)
+
+
+@pytest.mark.parametrize("bn", [16, 32, 64])
+def test_kmajor_multiple_b_boxes(bn):
+    g = torch.Generator().manual_seed(bn)
+    A = torch.randn((256, 120), generator=g)
+    B = torch.randn((240, 120), generator=g)
+    ref = A.double() @ B.double().T
+    assert rel_err(tc_gemm(0, A, B, bn=bn), ref) < 4e-6
+
+
+@pytest.mark.parametrize("M,N,K,ksplit", [(128, 64, 64, 1), (120, 240, 1000, 1), (480, 480, 4096, 4), (145, 120, 777, 3),
+                                          (60, 16, 200, 1)])
+def test_mnmajor_3xtf32_matches_fp64(M, N, K, ksplit):
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn((K, M), generator=g)
+    B = torch.randn((K, N), generator=g)
+    ref = A.double().T @ B.double()
+    err = rel_err(tc_gemm(1, A, B, ksplit=ksplit), ref)
+    fp32 = rel_err(A.T @ B, ref)
+    assert err < max(3e-6, 4 * fp32), (err, fp32)
+
+
+def test_epilogue_column_statistics():
+    g = torch.Generator().manual_seed(5)
+    A = torch.randn((300, 96), generator=g)
+    B = torch.randn((120, 96), generator=g)
+    D, S = tc_gemm(0, A, B, stats=True)
+    ref = (A.double() @ B.double().T)
+    s1 = S[:, 0, :].double().sum(0)
+    s2 = S[:, 1, :].double().sum(0)
+    assert float((s1 - ref.sum(0)).abs().max()) < 1e-3
+    assert float(((s2 - (ref * ref).sum(0)).abs() / (ref * ref).sum(0)).max()) < 1e-5
+
+
+def test_tensor_core_input_truncation_probe():
+    """Informational: does kind::tf32 ignore the 13 low mantissa bits of raw fp32 operands?
+    (The engine never relies on it: plane 0 is always pre-rounded.)"""
+    g = torch.Generator().manual_seed(9)
+    A = torch.randn((128, 256), generator=g)
+    B = torch.randn((64, 256), generator=g)
+    ref = A.double() @ B.double().T
+    err_raw = rel_err(tc_gemm(0, A, B, raw_hi=1), ref)
+    err_rna = rel_err(tc_gemm(0, A, B, raw_hi=0), ref)
+    print(f"raw-hi rel err {err_raw:.3e}; rna-hi rel err {err_rna:.3e}")
+    assert err_rna < 4e-6
