@@ -244,11 +244,15 @@ def run_native(args):
         if d["flops"] > 0:
             achieved = d["flops"] / (d["ms"] / 1e3) / 1e12
             peak = peaks["bf16_tflops_sustained"]
+            tc = args.precision == "3xtf32"
             roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                         "frac": achieved / peak, "traffic": None, "kernel": dom,
                         "avg_launch_ms": d["ms"] / d["launches"], "share_of_step": d["ms"] / total_prof_ms,
-                        "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step); "
-                                       "this kernel computes in fp32 FFMA"}
+                        "peak_source": f"{peaks['source']} bf16 dense sustained (kernel timed inside a long step)",
+                        "note": ("achieved = useful (algorithmic) FLOPs; the kernel issues 3 kind::tf32 MMAs (half the "
+                                 "bf16 rate) per useful MAC, so tensor_pipe_frac = 6 x frac is the pipe utilisation"
+                                 if tc else "this kernel computes in fp32 FFMA, not on the tensor pipe"),
+                        "tensor_pipe_frac": 6 * achieved / peak if tc else None}
         else:
             achieved = d["bytes"] / (d["ms"] / 1e3) / 1e9
             roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -292,7 +296,8 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="patches per GPU per step")
     ap.add_argument("--ref-batch", type=int, default=256, help="patches per step of the CPU arm (bounded sample)")
     ap.add_argument("--input-batches", type=int, default=4)
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "3xtf32", "bf16"])
+    ap.add_argument("--precision", default="3xtf32", choices=["fp32", "3xtf32"],
+                    help="3xtf32: tcgen05 tensor-core engine (fp32-accurate split); fp32: FFMA engine")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":

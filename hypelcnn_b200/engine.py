@@ -13,6 +13,7 @@ import torch
 from hypelcnn_b200 import _native as N
 
 TRUNC_STD_FIX = 0.87962566103423978  # variance_scaling truncated-normal correction [TF-lib]
+# "3xtf32": tcgen05 tensor-core engine (fp32-accurate TF32 split, the default); "fp32": FFMA engine
 _PRECISIONS = {"fp32": N.HYP_PRECISION_FP32, "3xtf32": N.HYP_PRECISION_3XTF32, "bf16": N.HYP_PRECISION_BF16}
 
 
@@ -39,7 +40,7 @@ class PatchEngine:
     (nnmodel/modelconfigs/alg_param_hypelcnn.json) — a missing key raises KeyError exactly
     like the reference's dict lookups."""
 
-    def __init__(self, patch, channels, classes, algorithm_params, max_batch, device=None, precision="fp32"):
+    def __init__(self, patch, channels, classes, algorithm_params, max_batch, device=None, precision="3xtf32"):
         if not torch.cuda.is_available():
             raise N.NativeError(N.HYP_E_CUDA, "no CUDA device: hypelcnn_b200 has no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)

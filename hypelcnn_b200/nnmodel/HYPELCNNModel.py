@@ -15,7 +15,7 @@ from hypelcnn_b200.nnmodel.NNModel import NNModel
 
 
 class HYPELCNNModel(NNModel):
-    precision = "fp32"
+    precision = "3xtf32"  # tcgen05 tensor-core engine; "fp32" selects the FFMA engine
 
     def __init__(self):
         self.engine = None
