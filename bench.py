@@ -282,6 +282,9 @@ def run_native(args):
                                          sorted(by_kernel.items(), key=lambda kv: -kv[1]["ms"])},
     }
     print(json.dumps(line), flush=True)
+    if args.prof_out:
+        with open(args.prof_out, "w") as f:
+            json.dump({k: {**v, "ms_per_step": v["ms"] / args.steps} for k, v in prof.items()}, f, indent=1)
     if world > 1:
         dist.destroy_process_group()
 
@@ -299,6 +302,8 @@ def main():
     ap.add_argument("--precision", default="3xtf32", choices=["fp32", "3xtf32"],
                     help="3xtf32: tcgen05 tensor-core engine (fp32-accurate split); fp32: FFMA engine")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--prof-out", default=None, help="write the per-tag kernel timing table here (HYP_PROF_LAYERS=1 "
+                    "adds the layer scope to GEMM tags)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3

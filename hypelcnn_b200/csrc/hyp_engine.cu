@@ -904,12 +904,15 @@ int hyp_gather_patches(const void* casi, int casi_dtype, int Hc, int Wc, int C_h
 // Splits both operands into TF32 (hi, lo) planes, builds tensor maps and tile tables exactly
 // as the engine does, and runs tc_gemm_kernel.  ksplit > 1 (mn = 1 only) splits K over CTAs
 // that accumulate with atomics (D must be zeroed by the caller).
-int hyp_debug_tc_gemm(int mn, const float* A, const float* B, int M, int N, int K, float* D, float* stats,
+int hyp_debug_tc_gemm(int mn_flags, const float* A, const float* B, int M, int N, int K, float* D, float* stats,
                       int raw_hi, int bn, int ksplit, int chunk_kb, void* stream) {
   using namespace hyp::tc;
+  const int mn = mn_flags & 1;
+  const int cg = (mn_flags & 2) ? 2 : 1;
   HYP_CHECK_ARG(A && B && D && M > 0 && N > 0 && K > 0, "bad argument");
   HYP_CHECK_ARG(N % 4 == 0, "N must be a multiple of 4 (output row alignment)");
   HYP_CHECK_ARG(ksplit >= 1 && (mn || ksplit == 1), "ksplit needs mn = 1");
+  HYP_CHECK_ARG(!(mn && cg == 2), "cta_group::2 is only built for K-major operands");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int lda_src = mn ? M : K, ldb_src = mn ? N : K;
   const int64_t a_rows = mn ? K : M, b_rows_src = mn ? K : N;
@@ -923,7 +926,7 @@ int hyp_debug_tc_gemm(int mn, const float* A, const float* B, int M, int N, int 
   HYP_LAUNCHED();
   const int ntile_n = 256;
   if (bn <= 0) bn = (int)std::min<int64_t>(256, align_up(N, 16));
-  HYP_CHECK_ARG(bn % 8 == 0 && bn <= 256, "bn must be a multiple of 8, <= 256");
+  HYP_CHECK_ARG(bn % (8 * cg) == 0 && bn <= 256, "bn must be a multiple of 8 per CTA, <= 256");
   CUtensorMap tmA, tmB;
   int rc;
   {
@@ -933,7 +936,7 @@ int hyp_debug_tc_gemm(int mn, const float* A, const float* B, int M, int N, int 
     if ((rc = make_map(&tmA, Ap, da, sa, ba, mn != 0))) return rc;
     const uint64_t db[4] = {(uint64_t)ldb_src, (uint64_t)b_rows_src, 1, 2};
     const uint64_t sb[3] = {(uint64_t)ldB, (uint64_t)b_rows_src * ldB, (uint64_t)b_rows_src * ldB};
-    const uint32_t bb[4] = {32, mn ? 32u : (uint32_t)bn, 1, 1};
+    const uint32_t bb[4] = {32, mn ? 32u : (uint32_t)(bn / cg), 1, 1};
     if ((rc = make_map(&tmB, Bp, db, sb, bb, mn != 0))) return rc;
   }
   std::vector<TcSeg> segs;
@@ -941,33 +944,36 @@ int hyp_debug_tc_gemm(int mn, const float* A, const float* B, int M, int N, int 
   const int mt = (int)cdiv(M, 128), nt = (int)cdiv(N, ntile_n);
   const int kblocks = (int)cdiv(K, TC_KB);
   const int kb_per = (int)cdiv(kblocks, ksplit);
-  int max_brows = 0, max_cols = 0;
-  for (int im = 0; im < mt; im++)
-    for (int in = 0; in < nt; in++)
-      for (int ks = 0; ks < ksplit; ks++) {
-        const int kb0 = ks * kb_per, kb1 = std::min(kblocks, kb0 + kb_per);
-        if (kb0 >= kb1) continue;
-        const int n0 = in * ntile_n, nw = std::min(ntile_n, N - n0);
-        TcSeg s{};
-        s.nk = kb1 - kb0;
-        s.n_mma = (int)align_up(nw, 16);
-        if (!mn) {
-          s.a0 = 0; s.a1 = im * 128; s.a2 = 0;
-          s.b0 = 0; s.b1 = n0; s.b2 = 0;
-          s.nb = (int)cdiv(s.n_mma, bn);
-          max_brows = std::max(max_brows, s.nb * bn);
-        } else {
-          s.a0 = im * 128; s.a1 = kb0 * TC_KB; s.a2 = 0;
-          s.b0 = n0; s.b1 = kb0 * TC_KB; s.b2 = 0;
-          s.nb = (int)cdiv(s.n_mma, 32);
-          max_brows = std::max(max_brows, s.nb * 32);
-        }
-        max_cols = std::max(max_cols, (int)align_up(nw, 32));
+  int max_brows = 0;
+  // one segment per (N tile, K split); the M tiles that share it are consecutive (CTA pairs)
+  for (int in = 0; in < nt; in++)
+    for (int ks = 0; ks < ksplit; ks++) {
+      const int kb0 = ks * kb_per, kb1 = std::min(kblocks, kb0 + kb_per);
+      if (kb0 >= kb1) continue;
+      const int n0 = in * ntile_n, nw = std::min(ntile_n, N - n0);
+      TcSeg s{};
+      s.nk = kb1 - kb0;
+      s.n_mma = (int)align_up(nw, 16);
+      if (!mn) {
+        s.b1 = n0;
+        s.nb = (int)cdiv(s.n_mma, bn);
+        max_brows = std::max(max_brows, s.nb * bn);
+      } else {
+        s.a1 = kb0 * TC_KB;
+        s.b0 = n0; s.b1 = kb0 * TC_KB;
+        s.nb = (int)cdiv(s.n_mma, 32);
+        max_brows = std::max(max_brows, s.nb * 32);
+      }
+      const int sidx = (int)segs.size();
+      segs.push_back(s);
+      const int mt_pad = (int)align_up(mt, cg);
+      for (int im = 0; im < mt_pad; im++) {
         TcTile t{};
-        t.seg_begin = (int)segs.size();
+        t.seg_begin = sidx;
         t.seg_count = 1;
         t.total_kb = s.nk;
-        t.m_valid = std::min(128, M - im * 128);
+        t.m_valid = im < mt ? std::min(128, M - im * 128) : 0;
+        if (mn) t.a0_add = im * 128; else t.a1_add = im * 128;
         t.ncb = 1;
         t.ld_out = N;
         t.stats_row = im;
@@ -975,9 +981,10 @@ int hyp_debug_tc_gemm(int mn, const float* A, const float* B, int M, int N, int 
         t.cb[0].tcol = 0;
         t.cb[0].width = nw;
         t.cb[0].stats_col = n0;
-        segs.push_back(s);
         tiles.push_back(t);
       }
+    }
+  HYP_CHECK_ARG(cg == 1 || bn * (int)cdiv(max_brows, bn) == max_brows, "bad bn");
   TcSeg* dsegs = nullptr;
   TcTile* dtiles = nullptr;
   HYP_CUDA(cudaMalloc(&dsegs, segs.size() * sizeof(TcSeg)));
@@ -988,8 +995,9 @@ int hyp_debug_tc_gemm(int mn, const float* A, const float* B, int M, int N, int 
   p.segs = dsegs; p.tiles = dtiles; p.out = D; p.stats = stats; p.stats_ld = N;
   p.epi = ksplit > 1 ? EPI_ATOMIC : EPI_STORE;
   p.b_rows = max_brows; p.bn = bn; p.chunk_kb = chunk_kb; p.stages = 0;
-  (void)max_cols;
-  rc = mn ? launch_tc<true>(tmA, tmB, p, (int)tiles.size(), st) : launch_tc<false>(tmA, tmB, p, (int)tiles.size(), st);
+  rc = mn ? launch_tc<true, 1>(tmA, tmB, p, (int)tiles.size(), st)
+          : (cg == 2 ? launch_tc<false, 2>(tmA, tmB, p, (int)tiles.size(), st)
+                     : launch_tc<false, 1>(tmA, tmB, p, (int)tiles.size(), st));
   cudaError_t e = cudaStreamSynchronize(st);
   cudaFree(Ap); cudaFree(Bp); cudaFree(dsegs); cudaFree(dtiles);
   if (rc) return rc;

@@ -19,6 +19,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <algorithm>
+
 #include "hyp_common.cuh"
 
 namespace hyp {
@@ -59,7 +61,8 @@ struct alignas(16) TcTile {
   int32_t total_kb;   // sum of nk over the tile's segments
   int32_t a1_add;     // added to every segment's a1 (K-major: first row of the tile)
   int32_t b1_add;     // added to every segment's b1 (K-major: first B row of the tile's N range)
-  int32_t pad[3];
+  int32_t a0_add;     // added to every segment's a0 (MN-major: first A column of the tile)
+  int32_t pad[2];
   TcColBlock cb[TC_MAX_CB];
 };
 
@@ -76,8 +79,10 @@ struct TcParams {
   int32_t bn;         // rows of one B box (K-major); MN-major boxes are 32 columns x 32 rows
   int32_t chunk_kb;   // K blocks the tensor core accumulates before the fp32 register merge
   int32_t stages;
+  int32_t ntiles;     // tiles of this launch (multiple of the CTA group size)
 };
 
+// b_rows = B rows held by ONE CTA per stage and plane
 inline size_t tc_smem_bytes(int b_rows, int stages) {
   return 1024 + (size_t)stages * (2 * TC_PLANE_A + 2 * (size_t)b_rows * 128) + 256 + 2 * 4 * TC_MAX_COLS * sizeof(float);
 }
@@ -85,7 +90,7 @@ inline int tc_pick_stages(int b_rows) {
   const size_t fixed = 1024 + 256 + 2 * 4 * TC_MAX_COLS * sizeof(float);
   const size_t st = 2 * TC_PLANE_A + 2 * (size_t)b_rows * 128;
   int s = (int)((TC_SMEM_LIMIT - fixed) / st);
-  return s > 6 ? 6 : s;
+  return s > 8 ? 8 : s;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -110,26 +115,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
-      : "memory");
-}
 __device__ __forceinline__ void tmem_ld32(uint32_t addr, float (&v)[32]) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
@@ -157,15 +144,15 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)layout << 61;
   return d;
 }
-// instruction descriptor: D fp32, A/B tf32, M = 128
-__device__ __forceinline__ uint32_t make_idesc_tf32(int n, bool mn_major) {
+// instruction descriptor: D fp32, A/B tf32, M = 128 per CTA of the group
+__device__ __forceinline__ uint32_t make_idesc_tf32(int n, bool mn_major, int cg = 1) {
   uint32_t d = 0;
   d |= 1u << 4;
   d |= 2u << 7;
   d |= 2u << 10;
   if (mn_major) d |= (1u << 15) | (1u << 16);
   d |= (uint32_t)(n >> 3) << 17;
-  d |= (uint32_t)(TC_BM >> 4) << 24;
+  d |= (uint32_t)((TC_BM * cg) >> 4) << 24;
   return d;
 }
 
@@ -186,19 +173,87 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 
 // ------------------------------------------------------------------------------------------
 // The tensor core adds each MMA result into the TMEM accumulator with round-toward-zero
-// (measured: scripts/probe_tc_accum.py, profiles/r01_tc_accum_probe.md), so the error of a
+// (measured: scripts/probe_tc_accum.py, profiles/r01_tc_accum_probe.txt), so the error of a
 // long K accumulation grows linearly with the number of MMAs.  The kernel therefore lets the
 // tensor core accumulate at most `chunk_kb` K blocks in one TMEM buffer, and the epilogue
 // warps add the finished chunks into fp32 registers (round-to-nearest FADD) while the next
 // chunk runs in the other buffer.
-template <bool MN>
+//
+// Persistent: CTA (or CTA pair) c works on tiles c, c + G, c + 2G, ...; the smem stage ring and
+// the TMEM chunk ring keep running across tiles, so the producer prefetches the next tile's
+// operands and the tensor core starts its first two chunks while the epilogue warps are still
+// writing the previous tile.
+//
+// CG = 2 (cta_group::2): the two CTAs of a cluster own tiles 2i and 2i+1 which share their B
+// operand (same segment list).  Each CTA loads its own A rows and HALF of the B rows; the
+// leader CTA issues M = 256 MMAs that read both halves, so B crosses L2 -> SM once per pair.
+template <int CG>
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  if (CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+  }
+}
+// arrive on `bar` of every CTA of the group once all MMAs issued so far have completed
+template <int CG>
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  if (CG == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  } else {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  if (CG == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+  } else {  // data lands in this CTA's smem, the transaction bytes are counted on the leader's barrier
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+  }
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <bool MN, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // swizzle atoms are 1024-byte aligned
   uint8_t* gen = smem_raw + (base - raw);
-  const uint32_t b_plane = (uint32_t)p.b_rows * 128u;
+  const uint32_t b_plane = (uint32_t)(p.b_rows / CG) * 128u;  // B rows held by THIS CTA
   const uint32_t stage_bytes = 2u * TC_PLANE_A + 2u * b_plane;
   const uint32_t bar_base = base + (uint32_t)p.stages * stage_bytes;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (size_t)p.stages * stage_bytes + 192);
@@ -209,9 +264,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto tempty_bar = [&](int b) { return bar_base + 8u * (uint32_t)(2 * p.stages + 2 + b); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const TcTile* T = p.tiles + blockIdx.x;
-  const int seg_begin = T->seg_begin, seg_count = T->seg_count;
-  const int total_kb = T->total_kb;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  // tile walk: group g = blockIdx.x / CG handles tile slots g, g + G, ...; slot t = tiles [t*CG, t*CG + CG)
+  const int ngroups = (int)gridDim.x / CG;
+  const int group = (int)blockIdx.x / CG;
+  const int nslots = p.ntiles / CG;
   const int CH = p.chunk_kb;
 
   if (threadIdx.x == 0) {
@@ -223,102 +281,127 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int b = 0; b < 2; b++) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), TC_EPI_WARPS);
+      mbar_init(tempty_bar(b), TC_EPI_WARPS * CG);  // the leader's barrier collects both CTAs' epilogue warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (one per CTA) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const int a1_add = T->a1_add, b1_add = T->b1_add;
-      for (int si = 0; si < seg_count; si++) {
-        TcSeg sg = p.segs[seg_begin + si];
-        sg.a1 += a1_add;
-        sg.b1 += b1_add;
-        const uint32_t b_box_bytes = MN ? 4096u : (uint32_t)p.bn * 128u;
-        const uint32_t tx = 2u * TC_PLANE_A + 2u * (uint32_t)sg.nb * b_box_bytes;
-        for (int kb = 0; kb < sg.nk; kb++) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t fb = full_bar(stage);
-          mbar_expect_tx(fb, tx);
-          const uint32_t a_s = base + (uint32_t)stage * stage_bytes;
-          const uint32_t b_s = a_s + 2u * TC_PLANE_A;
+      for (int slot = group; slot < nslots; slot += ngroups) {
+        const TcTile* T = p.tiles + (size_t)slot * CG + rank;
+        const int seg_begin = T->seg_begin, seg_count = T->seg_count;
+        const int a0_add = T->a0_add, a1_add = T->a1_add, b1_add = T->b1_add;
+        for (int si = 0; si < seg_count; si++) {
+          TcSeg sg = p.segs[seg_begin + si];
+          sg.a0 += a0_add;
+          sg.a1 += a1_add;
+          sg.b1 += b1_add;
+          // B boxes this CTA loads: K-major boxes of bn/CG rows, MN-major boxes of 32 columns
+          const uint32_t b_box_bytes = MN ? 4096u : (uint32_t)(p.bn / CG) * 128u;
+          const int nb = MN ? sg.nb / CG : sg.nb;
+          const int b_first = MN ? (int)rank * nb : 0;                          // first 32-column box
+          const int b_row0 = MN ? 0 : (int)rank * (sg.n_mma / CG);              // first B row
+          const uint32_t tx_cta = 2u * TC_PLANE_A + 2u * (uint32_t)nb * b_box_bytes;
+          for (int kb = 0; kb < sg.nk; kb++) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t fb_local = full_bar(stage);
+            const uint32_t fb = CG == 2 ? mapa_shared(fb_local, 0) : fb_local;
+            if (leader) mbar_expect_tx(fb_local, tx_cta * CG);
+            const uint32_t a_s = base + (uint32_t)stage * stage_bytes;
+            const uint32_t b_s = a_s + 2u * TC_PLANE_A;
 #pragma unroll
-          for (int pl = 0; pl < 2; pl++) {
-            if (!MN) {
-              tma_load_4d(a_s + pl * TC_PLANE_A, &tmA, fb, sg.a0 + kb * TC_KB, sg.a1, sg.a2, pl);
-              for (int j = 0; j < sg.nb; j++)
-                tma_load_4d(b_s + pl * b_plane + j * b_box_bytes, &tmB, fb, sg.b0 + kb * TC_KB, sg.b1 + j * p.bn, sg.b2,
-                            pl);
-            } else {
+            for (int pl = 0; pl < 2; pl++) {
+              if (!MN) {
+                tma_load_4d<CG>(a_s + pl * TC_PLANE_A, &tmA, fb, sg.a0 + kb * TC_KB, sg.a1, sg.a2, pl);
+                for (int j = 0; j < nb; j++)
+                  tma_load_4d<CG>(b_s + pl * b_plane + j * b_box_bytes, &tmB, fb, sg.b0 + kb * TC_KB,
+                                  sg.b1 + b_row0 + j * (p.bn / CG), sg.b2, pl);
+              } else {
 #pragma unroll
-              for (int i = 0; i < 4; i++)
-                tma_load_4d(a_s + pl * TC_PLANE_A + i * 4096, &tmA, fb, sg.a0 + i * 32, sg.a1 + kb * TC_KB, sg.a2, pl);
-              for (int j = 0; j < sg.nb; j++)
-                tma_load_4d(b_s + pl * b_plane + j * 4096, &tmB, fb, sg.b0 + j * 32, sg.b1 + kb * TC_KB, sg.b2, pl);
+                for (int i = 0; i < 4; i++)
+                  tma_load_4d<CG>(a_s + pl * TC_PLANE_A + i * 4096, &tmA, fb, sg.a0 + i * 32, sg.a1 + kb * TC_KB, sg.a2, pl);
+                for (int j = 0; j < nb; j++)
+                  tma_load_4d<CG>(b_s + pl * b_plane + j * 4096, &tmB, fb, sg.b0 + (b_first + j) * 32, sg.b1 + kb * TC_KB,
+                                  sg.b2, pl);
+              }
             }
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && leader) {
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t accum = 0;
-      int kcount = 0;  // K blocks issued so far
-      for (int si = 0; si < seg_count; si++) {
-        const TcSeg sg = p.segs[seg_begin + si];
-        const uint32_t idesc = make_idesc_tf32(sg.n_mma, MN);
-        for (int kb = 0; kb < sg.nk; kb++, kcount++) {
-          const int chunk = kcount / CH, buf = chunk & 1;
-          if (kcount % CH == 0) {  // new chunk: its TMEM buffer must have been drained
-            mbar_wait(tempty_bar(buf), (((uint32_t)chunk >> 1) & 1u) ^ 1u);
-            tc_fence_after();
-            accum = 0;
-          }
-          const uint32_t tmem_d = tmem_base + (uint32_t)buf * TC_MAX_COLS;
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t a_s = base + (uint32_t)stage * stage_bytes;
-          const uint32_t b_s = a_s + 2u * TC_PLANE_A;
-#pragma unroll
-          for (int ks = 0; ks < TC_KB / 8; ks++) {
-            uint64_t a_hi, a_lo, b_hi, b_lo;
-            if (!MN) {  // rows of 128 B, 8-row groups 1024 B apart; K advances 32 B inside the swizzled row
-              a_hi = make_smem_desc(a_s + ks * 32, 16, 1024);
-              a_lo = make_smem_desc(a_s + TC_PLANE_A + ks * 32, 16, 1024);
-              b_hi = make_smem_desc(b_s + ks * 32, 16, 1024);
-              b_lo = make_smem_desc(b_s + b_plane + ks * 32, 16, 1024);
-            } else {    // 32-column atoms 4096 B apart (LBO), 4-row K groups 512 B apart (SBO), 32-byte swizzle
-              a_hi = make_smem_desc(a_s + ks * 1024, 4096, 512, 1);
-              a_lo = make_smem_desc(a_s + TC_PLANE_A + ks * 1024, 4096, 512, 1);
-              b_hi = make_smem_desc(b_s + ks * 1024, 4096, 512, 1);
-              b_lo = make_smem_desc(b_s + b_plane + ks * 1024, 4096, 512, 1);
+      uint32_t gchunk = 0;  // chunks issued so far, all tiles
+      for (int slot = group; slot < nslots; slot += ngroups) {
+        const TcTile* T = p.tiles + (size_t)slot * CG;
+        const int seg_begin = T->seg_begin, seg_count = T->seg_count, total_kb = T->total_kb;
+        uint32_t accum = 0;
+        int kcount = 0;  // K blocks of this tile issued so far
+        uint32_t buf = 0;
+        for (int si = 0; si < seg_count; si++) {
+          const TcSeg sg = p.segs[seg_begin + si];
+          const uint32_t idesc = make_idesc_tf32(sg.n_mma, MN, CG);
+          for (int kb = 0; kb < sg.nk; kb++, kcount++) {
+            if (kcount % CH == 0) {  // new chunk: its TMEM buffer must have been drained
+              buf = gchunk & 1u;
+              mbar_wait(tempty_bar(buf), ((gchunk >> 1) & 1u) ^ 1u);
+              tc_fence_after();
+              accum = 0;
             }
-            mma_tf32(tmem_d, a_lo, b_hi, idesc, accum);
-            mma_tf32(tmem_d, a_hi, b_lo, idesc, 1);
-            mma_tf32(tmem_d, a_hi, b_hi, idesc, 1);
-            accum = 1;
+            const uint32_t tmem_d = tmem_base + buf * TC_MAX_COLS;
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t a_s = base + (uint32_t)stage * stage_bytes;
+            const uint32_t b_s = a_s + 2u * TC_PLANE_A;
+#pragma unroll
+            for (int ks = 0; ks < TC_KB / 8; ks++) {
+              uint64_t a_hi, a_lo, b_hi, b_lo;
+              if (!MN) {  // rows of 128 B, 8-row groups 1024 B apart; K advances 32 B inside the swizzled row
+                a_hi = make_smem_desc(a_s + ks * 32, 16, 1024);
+                a_lo = make_smem_desc(a_s + TC_PLANE_A + ks * 32, 16, 1024);
+                b_hi = make_smem_desc(b_s + ks * 32, 16, 1024);
+                b_lo = make_smem_desc(b_s + b_plane + ks * 32, 16, 1024);
+              } else {    // 32-column atoms 4096 B apart (LBO), 4-row K groups 512 B apart (SBO), 32-byte swizzle
+                a_hi = make_smem_desc(a_s + ks * 1024, 4096, 512, 1);
+                a_lo = make_smem_desc(a_s + TC_PLANE_A + ks * 1024, 4096, 512, 1);
+                b_hi = make_smem_desc(b_s + ks * 1024, 4096, 512, 1);
+                b_lo = make_smem_desc(b_s + b_plane + ks * 1024, 4096, 512, 1);
+              }
+              mma_tf32<CG>(tmem_d, a_lo, b_hi, idesc, accum);
+              mma_tf32<CG>(tmem_d, a_hi, b_lo, idesc, 1);
+              mma_tf32<CG>(tmem_d, a_hi, b_hi, idesc, 1);
+              accum = 1;
+            }
+            tc_commit<CG>(empty_bar(stage));  // frees the stage (in both CTAs) once these MMAs have read it
+            if (kcount % CH == CH - 1 || kcount == total_kb - 1) {
+              tc_commit<CG>(tfull_bar(buf));
+              gchunk++;
+            }
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
-          tc_commit(empty_bar(stage));  // frees the stage once these MMAs have read it
-          if (kcount % CH == CH - 1 || kcount == total_kb - 1) tc_commit(tfull_bar(buf));
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -327,122 +410,139 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
-    const int m_valid = T->m_valid, ld_out = T->ld_out, ncb = T->ncb;
-    const bool rvalid = row < m_valid;
-    float acc[TC_MAX_COLS / 2];
+    uint32_t gchunk = 0;
+    const uint32_t tempty_remote0 = CG == 2 ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
+    const uint32_t tempty_remote1 = CG == 2 ? mapa_shared(tempty_bar(1), 0) : tempty_bar(1);
+    for (int slot = group; slot < nslots; slot += ngroups) {
+      const TcTile* T = p.tiles + (size_t)slot * CG + rank;
+      const int seg_begin = T->seg_begin, seg_count = T->seg_count, total_kb = T->total_kb;
+      const int m_valid = T->m_valid, ld_out = T->ld_out, ncb = T->ncb;
+      const bool rvalid = row < m_valid;
+      float acc[TC_MAX_COLS / 2];
 #pragma unroll
-    for (int i = 0; i < TC_MAX_COLS / 2; i++) acc[i] = 0.f;
-    {
-      const int nchunks = (total_kb + CH - 1) / CH;
-      int si = 0, left = 0;  // segment holding the chunk's first K block; K blocks of it still ahead
-      int n_first = 0;
-      if (seg_count > 0) { left = p.segs[seg_begin].nk; n_first = p.segs[seg_begin].n_mma; }
-      for (int c = 0; c < nchunks; c++) {
-        const int buf = c & 1;
-        const int n_c = n_first;  // segments are ordered by non-increasing n_mma
-        // advance the walker by CH K blocks
-        int adv = CH;
-        while (adv > 0 && si < seg_count) {
-          if (left > adv) { left -= adv; adv = 0; }
-          else {
-            adv -= left;
-            si++;
-            if (si < seg_count) { left = p.segs[seg_begin + si].nk; n_first = p.segs[seg_begin + si].n_mma; }
+      for (int i = 0; i < TC_MAX_COLS / 2; i++) acc[i] = 0.f;
+      {
+        const int nchunks = (total_kb + CH - 1) / CH;
+        int si = 0, left = 0;  // segment holding the chunk's first K block; K blocks of it still ahead
+        int n_first = 0;
+        if (seg_count > 0) { left = p.segs[seg_begin].nk; n_first = p.segs[seg_begin].n_mma; }
+        for (int c = 0; c < nchunks; c++, gchunk++) {
+          const uint32_t buf = gchunk & 1u;
+          const int n_c = n_first;  // segments are ordered by non-increasing n_mma
+          // advance the walker by CH K blocks
+          int adv = CH;
+          while (adv > 0 && si < seg_count) {
+            if (left > adv) { left -= adv; adv = 0; }
+            else {
+              adv -= left;
+              si++;
+              if (si < seg_count) { left = p.segs[seg_begin + si].nk; n_first = p.segs[seg_begin + si].n_mma; }
+            }
+          }
+          mbar_wait(tfull_bar(buf), (gchunk >> 1) & 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int g = 0; g < 4; g++) {
+            const int tc0 = half * (TC_MAX_COLS / 2) + g * 32;
+            if (tc0 < n_c) {
+              float v[32];
+              tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC_MAX_COLS + tc0), v);
+#pragma unroll
+              for (int j = 0; j < 32; j++) acc[g * 32 + j] += (tc0 + j < n_c) ? v[j] : 0.f;
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            const uint32_t tb = buf ? tempty_remote1 : tempty_remote0;
+            if (CG == 2)
+              asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(tb) : "memory");
+            else
+              asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tb) : "memory");
           }
         }
-        mbar_wait(tfull_bar(buf), ((uint32_t)c >> 1) & 1u);
-        tc_fence_after();
-#pragma unroll
-        for (int g = 0; g < 4; g++) {
-          const int tc0 = half * (TC_MAX_COLS / 2) + g * 32;
-          if (tc0 < n_c) {
-            float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC_MAX_COLS + tc0), v);
-#pragma unroll
-            for (int j = 0; j < 32; j++) acc[g * 32 + j] += (tc0 + j < n_c) ? v[j] : 0.f;
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(buf)) : "memory");
       }
-    }
-    // ---- write the tile: column blocks map accumulator columns to output columns ----
+      // ---- write the tile: column blocks map accumulator columns to output columns ----
 #pragma unroll
-    for (int g = 0; g < 4; g++) {
-      const int tc0 = half * (TC_MAX_COLS / 2) + g * 32;
-      float s1 = 0.f, s2 = 0.f;  // lane l: column tc0 + l
-      bool any = false;
-      for (int b = 0; b < ncb; b++) {
-        const TcColBlock cb = T->cb[b];
-        const int lo = max(cb.tcol, tc0) - tc0, hi = min(cb.tcol + cb.width, tc0 + 32) - tc0;
-        if (lo >= hi) continue;
-        any = true;
-        if (rvalid) {
-          // output column of accumulator column tc0 + j is (tc0 + j - cb.tcol)
-          float* orow = p.out + cb.out_off + (int64_t)row * ld_out + (tc0 - cb.tcol);
-          const bool vec = ((cb.out_off | (int64_t)ld_out | (int64_t)(tc0 - cb.tcol)) & 3) == 0;
-          if (p.epi == EPI_ATOMIC) {
-#pragma unroll
-            for (int j = 0; j < 32; j++)
-              if (j >= lo && j < hi) atomicAdd(orow + j, acc[g * 32 + j]);
-          } else {
-            if (p.epi == EPI_ACCUM) {
+      for (int g = 0; g < 4; g++) {
+        const int tc0 = half * (TC_MAX_COLS / 2) + g * 32;
+        float s1 = 0.f, s2 = 0.f;  // lane l: column tc0 + l
+        bool any = false;
+        for (int b = 0; b < ncb; b++) {
+          const TcColBlock cb = T->cb[b];
+          const int lo = max(cb.tcol, tc0) - tc0, hi = min(cb.tcol + cb.width, tc0 + 32) - tc0;
+          if (lo >= hi) continue;
+          any = true;
+          if (rvalid) {
+            // output column of accumulator column tc0 + j is (tc0 + j - cb.tcol)
+            float* orow = p.out + cb.out_off + (int64_t)row * ld_out + (tc0 - cb.tcol);
+            const bool vec = ((cb.out_off | (int64_t)ld_out | (int64_t)(tc0 - cb.tcol)) & 3) == 0;
+            if (p.epi == EPI_ATOMIC) {
 #pragma unroll
               for (int j = 0; j < 32; j++)
-                if (j >= lo && j < hi) acc[g * 32 + j] += orow[j];
-            }
+                if (j >= lo && j < hi) atomicAdd(orow + j, acc[g * 32 + j]);
+            } else {
+              if (p.epi == EPI_ACCUM) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (vec && j >= lo && j + 3 < hi) {
-                *reinterpret_cast<float4*>(orow + j) =
-                    make_float4(acc[g * 32 + j], acc[g * 32 + j + 1], acc[g * 32 + j + 2], acc[g * 32 + j + 3]);
-              } else {
+                for (int j = 0; j < 32; j++)
+                  if (j >= lo && j < hi) acc[g * 32 + j] += orow[j];
+              }
 #pragma unroll
-                for (int t = 0; t < 4; t++)
-                  if (j + t >= lo && j + t < hi) orow[j + t] = acc[g * 32 + j + t];
+              for (int j = 0; j < 32; j += 4) {
+                if (vec && j >= lo && j + 3 < hi) {
+                  *reinterpret_cast<float4*>(orow + j) =
+                      make_float4(acc[g * 32 + j], acc[g * 32 + j + 1], acc[g * 32 + j + 2], acc[g * 32 + j + 3]);
+                } else {
+#pragma unroll
+                  for (int t = 0; t < 4; t++)
+                    if (j + t >= lo && j + t < hi) orow[j + t] = acc[g * 32 + j + t];
+                }
               }
             }
           }
         }
-      }
-      if (p.stats && __any_sync(0xffffffffu, any)) {
-        float v[32], sq[32];
+        if (p.stats && __any_sync(0xffffffffu, any)) {
+          float v[32], sq[32];
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-          v[j] = rvalid ? acc[g * 32 + j] : 0.f;
-          sq[j] = v[j] * v[j];
-        }
-        s1 = warp_transpose_sum(v, lane);
-        s2 = warp_transpose_sum(sq, lane);
-        s_part[(0 * 4 + q) * TC_MAX_COLS + tc0 + lane] = s1;
-        s_part[(1 * 4 + q) * TC_MAX_COLS + tc0 + lane] = s2;
-      }
-    }
-    if (p.stats) {
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const int t = threadIdx.x - 64;
-      float* srow = p.stats + (size_t)T->stats_row * 2 * p.stats_ld;
-      for (int b = 0; b < ncb; b++) {
-        const int c = t - T->cb[b].tcol;
-        if (c >= 0 && c < T->cb[b].width) {
-          float a1 = 0.f, a2 = 0.f;
-#pragma unroll
-          for (int w = 0; w < 4; w++) {
-            a1 += s_part[(0 * 4 + w) * TC_MAX_COLS + t];
-            a2 += s_part[(1 * 4 + w) * TC_MAX_COLS + t];
+          for (int j = 0; j < 32; j++) {
+            v[j] = rvalid ? acc[g * 32 + j] : 0.f;
+            sq[j] = v[j] * v[j];
           }
-          srow[T->cb[b].stats_col + c] = a1;
-          srow[p.stats_ld + T->cb[b].stats_col + c] = a2;
+          s1 = warp_transpose_sum(v, lane);
+          s2 = warp_transpose_sum(sq, lane);
+          s_part[(0 * 4 + q) * TC_MAX_COLS + tc0 + lane] = s1;
+          s_part[(1 * 4 + q) * TC_MAX_COLS + tc0 + lane] = s2;
         }
+      }
+      if (p.stats) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int t = threadIdx.x - 64;
+        float* srow = p.stats + (size_t)T->stats_row * 2 * p.stats_ld;
+        for (int b = 0; b < (m_valid > 0 ? ncb : 0); b++) {  // phantom tiles (m_valid == 0) own no statistics row
+          const int c = t - T->cb[b].tcol;
+          if (c >= 0 && c < T->cb[b].width) {
+            float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+              a1 += s_part[(0 * 4 + w) * TC_MAX_COLS + t];
+              a2 += s_part[(1 * 4 + w) * TC_MAX_COLS + t];
+            }
+            srow[T->cb[b].stats_col + c] = a1;
+            srow[p.stats_ld + T->cb[b].stats_col + c] = a2;
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // s_part is reused by the next tile
       }
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (CG == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -489,19 +589,46 @@ inline int make_map(CUtensorMap* map, const float* base, const uint64_t dims[4],
 
 constexpr int TC_DEFAULT_CHUNK_KB = 4;
 
-template <bool MN>
+inline int tc_sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+// CG = 2: tiles 2i, 2i+1 form a pair sharing its segment list (ntiles even); tmB boxes hold bn/2 rows
+template <bool MN, int CG>
 inline int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, int ntiles, cudaStream_t st) {
   if (ntiles <= 0) return HYP_OK;
-  if (p.stages <= 0) p.stages = tc_pick_stages(p.b_rows);
+  if (ntiles % CG) return fail(HYP_E_INVALID, "tc gemm: tile count is not a multiple of the CTA group size");
+  if (p.b_rows % (8 * CG)) return fail(HYP_E_INVALID, "tc gemm: B rows must be a multiple of 8 per CTA");
+  if (p.stages <= 0) p.stages = tc_pick_stages(p.b_rows / CG);
   if (p.chunk_kb <= 0) p.chunk_kb = TC_DEFAULT_CHUNK_KB;
   if (p.stages < 2) return fail(HYP_E_INVALID, "tc gemm: B tile too large for two pipeline stages");
-  const size_t smem = tc_smem_bytes(p.b_rows, p.stages);
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[MN ? 1 : 0]) {
-    HYP_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
-    attr_set[MN ? 1 : 0] = true;
+  p.ntiles = ntiles;
+  const size_t smem = tc_smem_bytes(p.b_rows / CG, p.stages);
+  static bool attr_set = false;
+  if (!attr_set) {
+    HYP_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    attr_set = true;
   }
-  tc_gemm_kernel<MN><<<ntiles, TC_THREADS, smem, st>>>(tmA, tmB, p);
+  const int groups = std::min(ntiles / CG, tc_sm_count() / CG);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(groups * CG));
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CG > 1 ? 1 : 0;
+  HYP_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<MN, CG>, tmA, tmB, p));
   HYP_LAUNCHED();
   return HYP_OK;
 }

@@ -12,6 +12,7 @@
 //   flatten : FC fed by a conv tensor              z[b, :]    = sum_pos a[pos, b, :] W_pos
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 
 #include "hyp_tc_kernels.cuh"
 
@@ -30,6 +31,7 @@ struct TcLaunch {
   int tile0 = 0, ntiles = 0;
   int b_rows = 0, bn = 0;
   bool mn = false;
+  int cg = 1;  // CTA group size: 2 = tiles come in pairs (2i, 2i+1) that share their B operand
 };
 
 struct TcLayer {
@@ -254,6 +256,18 @@ static TcTile blank_tile() {
   return t;
 }
 
+// K-major launches run as CTA pairs (cta_group::2): consecutive tiles (2i, 2i+1) must share their
+// segment list.  A run of tiles that differ only in their row block is closed with a phantom
+// tile (no valid rows; its A box is out of bounds and reads zeros) when its length is odd.
+constexpr int TC_CG_KMAJOR = 2;
+static void close_pair_run(std::vector<TcTile>& tiles, size_t run_begin, int oob_a1) {
+  if ((tiles.size() - run_begin) % TC_CG_KMAJOR == 0) return;
+  TcTile t = tiles.back();
+  t.m_valid = 0;
+  t.a1_add = oob_a1;
+  tiles.push_back(t);
+}
+
 static int map4(CUtensorMap* mp, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2,
                 uint64_t plane, uint32_t b0, uint32_t b1, bool mn) {
   const uint64_t dims[4] = {d0, d1, d2, 2};
@@ -274,6 +288,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
   PlanBuf pb;
   const int P = m.d.patch, h = P / 2;
   const int nbt = (int)cdiv(B, 128);
+  const int CG = TC_CG_KMAJOR;
   float* pack0 = reinterpret_cast<float*>(m.ws + S.pack_off);
   float* gz0 = reinterpret_cast<float*>(m.ws + S.gz_off);
   int rc;
@@ -299,8 +314,8 @@ static int tc_plan(hyp_model& m, int64_t B) {
       n_tiling(Cout, ntn, nw);
       if ((rc = map4(&T.fwd.tmA, a0, Cin, rows_in, 1, tin.Cp, (uint64_t)rows_in * tin.Cp, tin.plane_elems, 32, 128, false))) return rc;
       if ((rc = map4(&T.fwd.tmB, pack0 + T.wf_off, T.wf_ld, T.wf_rows, 1, T.wf_ld, (uint64_t)T.wf_rows * T.wf_ld,
-                     S.pack_plane_elems, 32, nw, false))) return rc;
-      T.fwd.mn = false; T.fwd.b_rows = nw; T.fwd.bn = nw; T.fwd.tile0 = (int)pb.tiles.size();
+                     S.pack_plane_elems, 32, nw / CG, false))) return rc;
+      T.fwd.mn = false; T.fwd.cg = CG; T.fwd.b_rows = nw; T.fwd.bn = nw; T.fwd.tile0 = (int)pb.tiles.size();
       const int seg0 = (int)pb.segs.size();
       for (int j = 0; j < ntn; j++) {
         TcSeg s{};
@@ -308,16 +323,20 @@ static int tc_plan(hyp_model& m, int64_t B) {
         pb.segs.push_back(s);
       }
       const int nrt = (int)cdiv(rows_out, 128);
-      for (int rt = 0; rt < nrt; rt++)
+      for (int rt2 = 0; rt2 < nrt; rt2 += CG)
         for (int j = 0; j < ntn; j++) {
-          TcTile t = blank_tile();
-          t.seg_begin = seg0 + j; t.seg_count = 1; t.total_kb = T.Kp / 32;
-          t.m_valid = (int)std::min<int64_t>(128, rows_out - (int64_t)rt * 128);
-          t.ncb = 1; t.ld_out = tout.Cp; t.stats_row = rt; t.a1_add = rt * 128;
-          t.cb[0].out_off = (int64_t)rt * 128 * tout.Cp + j * nw;
-          t.cb[0].width = std::min(nw, Cout - j * nw);
-          t.cb[0].stats_col = j * nw;
-          pb.tiles.push_back(t);
+          const size_t run = pb.tiles.size();
+          for (int rt = rt2; rt < std::min(nrt, rt2 + CG); rt++) {
+            TcTile t = blank_tile();
+            t.seg_begin = seg0 + j; t.seg_count = 1; t.total_kb = T.Kp / 32;
+            t.m_valid = (int)std::min<int64_t>(128, rows_out - (int64_t)rt * 128);
+            t.ncb = 1; t.ld_out = tout.Cp; t.stats_row = rt; t.a1_add = rt * 128;
+            t.cb[0].out_off = (int64_t)rt * 128 * tout.Cp + j * nw;
+            t.cb[0].width = std::min(nw, Cout - j * nw);
+            t.cb[0].stats_col = j * nw;
+            pb.tiles.push_back(t);
+          }
+          close_pair_run(pb.tiles, run, nrt * 128);
         }
       T.fwd.ntiles = (int)pb.tiles.size() - T.fwd.tile0;
       T.stats_rows = nrt;
@@ -326,23 +345,27 @@ static int tc_plan(hyp_model& m, int64_t B) {
         n_tiling(Cin, ntn, nw);
         if ((rc = map4(&T.dg.tmA, gz0, Cout, rows_out, 1, T.Gp, (uint64_t)rows_out * T.Gp, S.gz_plane_elems, 32, 128, false))) return rc;
         if ((rc = map4(&T.dg.tmB, pack0 + T.wd_off, T.wd_ld, T.wd_rows, 1, T.wd_ld, (uint64_t)T.wd_rows * T.wd_ld,
-                       S.pack_plane_elems, 32, nw, false))) return rc;
-        T.dg.mn = false; T.dg.b_rows = nw; T.dg.bn = nw; T.dg.tile0 = (int)pb.tiles.size();
+                       S.pack_plane_elems, 32, nw / CG, false))) return rc;
+        T.dg.mn = false; T.dg.cg = CG; T.dg.b_rows = nw; T.dg.bn = nw; T.dg.tile0 = (int)pb.tiles.size();
         const int dseg0 = (int)pb.segs.size();
         for (int j = 0; j < ntn; j++) {
           TcSeg s{};
           s.b1 = j * nw; s.nk = T.wd_ld / 32; s.n_mma = r16(std::min(nw, Cin - j * nw)); s.nb = 1;
           pb.segs.push_back(s);
         }
-        for (int rt = 0; rt < nrt; rt++)
+        for (int rt2 = 0; rt2 < nrt; rt2 += CG)
           for (int j = 0; j < ntn; j++) {
-            TcTile t = blank_tile();
-            t.seg_begin = dseg0 + j; t.seg_count = 1; t.total_kb = T.wd_ld / 32;
-            t.m_valid = (int)std::min<int64_t>(128, rows_out - (int64_t)rt * 128);
-            t.ncb = 1; t.ld_out = tin.Cp; t.a1_add = rt * 128;
-            t.cb[0].out_off = (int64_t)rt * 128 * tin.Cp + j * nw;
-            t.cb[0].width = std::min(nw, Cin - j * nw);
-            pb.tiles.push_back(t);
+            const size_t run = pb.tiles.size();
+            for (int rt = rt2; rt < std::min(nrt, rt2 + CG); rt++) {
+              TcTile t = blank_tile();
+              t.seg_begin = dseg0 + j; t.seg_count = 1; t.total_kb = T.wd_ld / 32;
+              t.m_valid = (int)std::min<int64_t>(128, rows_out - (int64_t)rt * 128);
+              t.ncb = 1; t.ld_out = tin.Cp; t.a1_add = rt * 128;
+              t.cb[0].out_off = (int64_t)rt * 128 * tin.Cp + j * nw;
+              t.cb[0].width = std::min(nw, Cin - j * nw);
+              pb.tiles.push_back(t);
+            }
+            close_pair_run(pb.tiles, run, nrt * 128);
           }
         T.dg.ntiles = (int)pb.tiles.size() - T.dg.tile0;
       }
@@ -382,8 +405,13 @@ static int tc_plan(hyp_model& m, int64_t B) {
       // ---------------- forward ----------------
       if ((rc = map4(&T.fwd.tmA, a0, Cin, B, PP, tin.Cp, (uint64_t)B * tin.Cp, tin.plane_elems, 32, 128, false))) return rc;
       if ((rc = map4(&T.fwd.tmB, pack0 + T.wf_off, T.wf_ld, T.wf_rows, 1, T.wf_ld, (uint64_t)T.wf_rows * T.wf_ld,
-                     S.pack_plane_elems, 32, fpad, false))) return rc;
-      T.fwd.mn = false; T.fwd.b_rows = spg * fpad; T.fwd.bn = fpad; T.fwd.tile0 = (int)pb.tiles.size();
+                     S.pack_plane_elems, 32, fpad / CG, false))) return rc;
+      T.fwd.mn = false; T.fwd.cg = CG; T.fwd.b_rows = spg * fpad; T.fwd.bn = fpad; T.fwd.tile0 = (int)pb.tiles.size();
+      // one segment list per (position, slot group); tiles are emitted batch-pair major so that a wave of
+      // CTAs works on few batch rows x all positions (the A rows stay in L2 across the taps that reuse
+      // them), heaviest positions first (static round-robin over persistent CTAs stays balanced)
+      struct Run { int seg0, nseg, tkb, p, g; };
+      std::vector<Run> runs;
       for (int p = 0; p < PP; p++) {
         const int ph = p / P, pw = p % P;
         for (int g = 0; g < ngroups; g++) {
@@ -400,9 +428,17 @@ static int tc_plan(hyp_model& m, int64_t B) {
             pb.segs.push_back(s);
           }
           const int nseg = (int)pb.segs.size() - seg0;
-          for (int bt = 0; bt < nbt; bt++) {
+          runs.push_back({seg0, nseg, nseg * (T.Kp / 32), p, g});
+        }
+      }
+      std::stable_sort(runs.begin(), runs.end(), [](const Run& a, const Run& b) { return a.tkb > b.tkb; });
+      for (int bt2 = 0; bt2 < nbt; bt2 += CG)
+        for (const Run& rn : runs) {
+          const int s0 = rn.g * spg, s1 = std::min(R, s0 + spg), p = rn.p;
+          const size_t run = pb.tiles.size();
+          for (int bt = bt2; bt < std::min(nbt, bt2 + CG); bt++) {
             TcTile t = blank_tile();
-            t.seg_begin = seg0; t.seg_count = nseg; t.total_kb = nseg * (T.Kp / 32);
+            t.seg_begin = rn.seg0; t.seg_count = rn.nseg; t.total_kb = rn.tkb;
             t.m_valid = (int)std::min<int64_t>(128, B - (int64_t)bt * 128);
             t.ld_out = tout.Cp; t.stats_row = p * nbt + bt; t.a1_add = bt * 128; t.b1_add = s0 * fpad;
             t.ncb = s1 - s0;
@@ -415,8 +451,8 @@ static int tc_plan(hyp_model& m, int64_t B) {
             }
             pb.tiles.push_back(t);
           }
+          close_pair_run(pb.tiles, run, nbt * 128);
         }
-      }
       T.fwd.ntiles = (int)pb.tiles.size() - T.fwd.tile0;
       T.stats_rows = PP * nbt;
       // ---------------- dgrad ----------------
@@ -425,8 +461,10 @@ static int tc_plan(hyp_model& m, int64_t B) {
         n_tiling(Cin, ntn, nw);
         if ((rc = map4(&T.dg.tmA, gz0, T.Gp, B, PP, T.Gp, (uint64_t)B * T.Gp, S.gz_plane_elems, 32, 128, false))) return rc;
         if ((rc = map4(&T.dg.tmB, pack0 + T.wd_off, T.wd_ld, T.wd_rows, 1, T.wd_ld, (uint64_t)T.wd_rows * T.wd_ld,
-                       S.pack_plane_elems, 32, nw, false))) return rc;
-        T.dg.mn = false; T.dg.b_rows = nw; T.dg.bn = nw; T.dg.tile0 = (int)pb.tiles.size();
+                       S.pack_plane_elems, 32, nw / CG, false))) return rc;
+        T.dg.mn = false; T.dg.cg = CG; T.dg.b_rows = nw; T.dg.bn = nw; T.dg.tile0 = (int)pb.tiles.size();
+        struct DRun { int seg0, nseg, tkb, p, j; };
+        std::vector<DRun> druns;
         for (int p = 0; p < PP; p++) {
           const int ph = p / P, pw = p % P;
           for (int j = 0; j < ntn; j++) {
@@ -442,18 +480,24 @@ static int tc_plan(hyp_model& m, int64_t B) {
               tkb += s.nk;
               pb.segs.push_back(s);
             }
-            const int nseg = (int)pb.segs.size() - seg0;
-            for (int bt = 0; bt < nbt; bt++) {
-              TcTile t = blank_tile();
-              t.seg_begin = seg0; t.seg_count = nseg; t.total_kb = tkb;
-              t.m_valid = (int)std::min<int64_t>(128, B - (int64_t)bt * 128);
-              t.ncb = 1; t.ld_out = tin.Cp; t.a1_add = bt * 128;
-              t.cb[0].out_off = ((int64_t)p * B + (int64_t)bt * 128) * tin.Cp + j * nw;
-              t.cb[0].width = std::min(nw, Cin - j * nw);
-              pb.tiles.push_back(t);
-            }
+            druns.push_back({seg0, (int)pb.segs.size() - seg0, tkb, p, j});
           }
         }
+        std::stable_sort(druns.begin(), druns.end(), [](const DRun& a, const DRun& b) { return a.tkb > b.tkb; });
+        for (int bt2 = 0; bt2 < nbt; bt2 += CG)
+          for (const DRun& rn : druns) {
+            const size_t run = pb.tiles.size();
+            for (int bt = bt2; bt < std::min(nbt, bt2 + CG); bt++) {
+              TcTile t = blank_tile();
+              t.seg_begin = rn.seg0; t.seg_count = rn.nseg; t.total_kb = rn.tkb;
+              t.m_valid = (int)std::min<int64_t>(128, B - (int64_t)bt * 128);
+              t.ncb = 1; t.ld_out = tin.Cp; t.a1_add = bt * 128;
+              t.cb[0].out_off = ((int64_t)rn.p * B + (int64_t)bt * 128) * tin.Cp + rn.j * nw;
+              t.cb[0].width = std::min(nw, Cin - rn.j * nw);
+              pb.tiles.push_back(t);
+            }
+            close_pair_run(pb.tiles, run, nbt * 128);
+          }
         T.dg.ntiles = (int)pb.tiles.size() - T.dg.tile0;
       }
       // ---------------- wgrad ----------------
@@ -512,50 +556,59 @@ static int tc_plan(hyp_model& m, int64_t B) {
       // ---------------- forward ----------------
       if ((rc = map4(&T.fwd.tmA, a0, Ct, B, PP, tin.Cp, (uint64_t)B * tin.Cp, tin.plane_elems, 32, 128, false))) return rc;
       if ((rc = map4(&T.fwd.tmB, pack0 + T.wf_off, T.wf_ld, T.wf_rows, 1, T.wf_ld, (uint64_t)T.wf_rows * T.wf_ld,
-                     S.pack_plane_elems, 32, nw, false))) return rc;
-      T.fwd.mn = false; T.fwd.b_rows = nw; T.fwd.bn = nw; T.fwd.tile0 = (int)pb.tiles.size();
-      for (int j = 0; j < ntn; j++) {
-        const int seg0 = (int)pb.segs.size();
+                     S.pack_plane_elems, 32, nw / CG, false))) return rc;
+      T.fwd.mn = false; T.fwd.cg = CG; T.fwd.b_rows = nw; T.fwd.bn = nw; T.fwd.tile0 = (int)pb.tiles.size();
+      const int fseg0 = (int)pb.segs.size();
+      for (int j = 0; j < ntn; j++)
         for (int pos = 0; pos < PP; pos++) {
           TcSeg s{};
           s.a2 = pos; s.b0 = pos * T.Kp; s.b1 = j * nw; s.nk = T.Kp / 32;
           s.n_mma = r16(std::min(nw, Cout - j * nw)); s.nb = 1;
           pb.segs.push_back(s);
         }
-        for (int bt = 0; bt < nbt; bt++) {
-          TcTile t = blank_tile();
-          t.seg_begin = seg0; t.seg_count = PP; t.total_kb = PP * (T.Kp / 32);
-          t.m_valid = (int)std::min<int64_t>(128, B - (int64_t)bt * 128);
-          t.ncb = 1; t.ld_out = tout.Cp; t.stats_row = bt; t.a1_add = bt * 128;
-          t.cb[0].out_off = (int64_t)bt * 128 * tout.Cp + j * nw;
-          t.cb[0].width = std::min(nw, Cout - j * nw);
-          t.cb[0].stats_col = j * nw;
-          pb.tiles.push_back(t);
+      for (int bt2 = 0; bt2 < nbt; bt2 += CG)
+        for (int j = 0; j < ntn; j++) {
+          const size_t run = pb.tiles.size();
+          for (int bt = bt2; bt < std::min(nbt, bt2 + CG); bt++) {
+            TcTile t = blank_tile();
+            t.seg_begin = fseg0 + j * PP; t.seg_count = PP; t.total_kb = PP * (T.Kp / 32);
+            t.m_valid = (int)std::min<int64_t>(128, B - (int64_t)bt * 128);
+            t.ncb = 1; t.ld_out = tout.Cp; t.stats_row = bt; t.a1_add = bt * 128;
+            t.cb[0].out_off = (int64_t)bt * 128 * tout.Cp + j * nw;
+            t.cb[0].width = std::min(nw, Cout - j * nw);
+            t.cb[0].stats_col = j * nw;
+            pb.tiles.push_back(t);
+          }
+          close_pair_run(pb.tiles, run, nbt * 128);
         }
-      }
       T.fwd.ntiles = (int)pb.tiles.size() - T.fwd.tile0;
       T.stats_rows = nbt;
       // ---------------- dgrad ----------------
       if (need_dgrad) {
         if ((rc = map4(&T.dg.tmA, gz0, Cout, B, 1, T.Gp, (uint64_t)B * T.Gp, S.gz_plane_elems, 32, 128, false))) return rc;
         if ((rc = map4(&T.dg.tmB, pack0 + T.wd_off, T.wd_ld, T.wd_rows, 1, T.wd_ld, (uint64_t)T.wd_rows * T.wd_ld,
-                       S.pack_plane_elems, 32, T.Cq, false))) return rc;
-        T.dg.mn = false; T.dg.b_rows = T.Cq; T.dg.bn = T.Cq; T.dg.tile0 = (int)pb.tiles.size();
+                       S.pack_plane_elems, 32, T.Cq / CG, false))) return rc;
+        T.dg.mn = false; T.dg.cg = CG; T.dg.b_rows = T.Cq; T.dg.bn = T.Cq; T.dg.tile0 = (int)pb.tiles.size();
+        const int dseg0 = (int)pb.segs.size();
         for (int pos = 0; pos < PP; pos++) {
           TcSeg s{};
           s.b1 = pos * T.Cq; s.nk = T.wd_ld / 32; s.n_mma = T.Cq; s.nb = 1;
-          const int sidx = (int)pb.segs.size();
           pb.segs.push_back(s);
-          for (int bt = 0; bt < nbt; bt++) {
-            TcTile t = blank_tile();
-            t.seg_begin = sidx; t.seg_count = 1; t.total_kb = s.nk;
-            t.m_valid = (int)std::min<int64_t>(128, B - (int64_t)bt * 128);
-            t.ncb = 1; t.ld_out = tin.Cp; t.a1_add = bt * 128;
-            t.cb[0].out_off = ((int64_t)pos * B + (int64_t)bt * 128) * tin.Cp;
-            t.cb[0].width = Ct;
-            pb.tiles.push_back(t);
-          }
         }
+        for (int bt2 = 0; bt2 < nbt; bt2 += CG)
+          for (int pos = 0; pos < PP; pos++) {
+            const size_t run = pb.tiles.size();
+            for (int bt = bt2; bt < std::min(nbt, bt2 + CG); bt++) {
+              TcTile t = blank_tile();
+              t.seg_begin = dseg0 + pos; t.seg_count = 1; t.total_kb = T.wd_ld / 32;
+              t.m_valid = (int)std::min<int64_t>(128, B - (int64_t)bt * 128);
+              t.ncb = 1; t.ld_out = tin.Cp; t.a1_add = bt * 128;
+              t.cb[0].out_off = ((int64_t)pos * B + (int64_t)bt * 128) * tin.Cp;
+              t.cb[0].width = Ct;
+              pb.tiles.push_back(t);
+            }
+            close_pair_run(pb.tiles, run, nbt * 128);
+          }
         T.dg.ntiles = (int)pb.tiles.size() - T.dg.tile0;
       }
       // ---------------- wgrad ----------------
@@ -600,14 +653,19 @@ static int tc_plan(hyp_model& m, int64_t B) {
 }
 
 static int tc_run(hyp_model& m, const TcLaunch& l, float* out, float* stats, int stats_ld, int epi, const char* tag,
-                  double flops, cudaStream_t st) {
+                  double flops, cudaStream_t st, const char* scope = nullptr) {
   if (l.ntiles == 0) return HYP_OK;
   TcState& S = *m.tc;
   TcParams p{};
   p.segs = S.segs_dev; p.tiles = S.tiles_dev + l.tile0; p.out = out; p.stats = stats; p.stats_ld = stats_ld;
   p.epi = epi; p.b_rows = l.b_rows; p.bn = l.bn; p.chunk_kb = 0; p.stages = 0;
-  g_prof.begin(st, tag, flops, 0.0);
-  const int rc = l.mn ? launch_tc<true>(l.tmA, l.tmB, p, l.ntiles, st) : launch_tc<false>(l.tmA, l.tmB, p, l.ntiles, st);
+  static const bool per_layer = getenv("HYP_PROF_LAYERS") != nullptr;
+  std::string full = tag;
+  if (per_layer && scope) full += std::string("/") + scope;
+  g_prof.begin(st, full.c_str(), flops, 0.0);
+  const int rc = l.mn ? launch_tc<true, 1>(l.tmA, l.tmB, p, l.ntiles, st)
+                      : (l.cg == 2 ? launch_tc<false, 2>(l.tmA, l.tmB, p, l.ntiles, st)
+                                   : launch_tc<false, 1>(l.tmA, l.tmB, p, l.ntiles, st));
   g_prof.end(st);
   return rc;
 }
@@ -646,7 +704,7 @@ static int tc_forward(hyp_model& m, const float* x, int64_t B, bool training, bo
     const TcTensor& tout = S.tt[L.out_t];
     const int64_t rows = B * tout.PP;
     float* Z = reinterpret_cast<float*>(m.ws + T.z_off);
-    rc = tc_run(m, T.fwd, Z, training ? part : nullptr, L.Cout, EPI_STORE, "tc_gemm_kernel/fwd", layer_flops(L, B), st);
+    rc = tc_run(m, T.fwd, Z, training ? part : nullptr, L.Cout, EPI_STORE, "tc_gemm_kernel/fwd", layer_flops(L, B), st, L.scope.c_str());
     if (rc) return rc;
     float* mean = reinterpret_cast<float*>(m.ws + T.mean_off);
     float* rstd = reinterpret_cast<float*>(m.ws + T.rstd_off);
@@ -754,11 +812,11 @@ static int tc_backward(hyp_model& m, const uint8_t* labels, int64_t B, float* lo
                                                                           ginit[r.src])));
       ginit[r.src] = 1;
     }
-    int rc = tc_run(m, T.wg, m.grads, nullptr, 0, EPI_ATOMIC, "tc_gemm_kernel/wgrad", layer_flops(L, B), st);
+    int rc = tc_run(m, T.wg, m.grads, nullptr, 0, EPI_ATOMIC, "tc_gemm_kernel/wgrad", layer_flops(L, B), st, L.scope.c_str());
     if (rc) return rc;
     if (m.tensors[L.in_t].needs_grad) {
       rc = tc_run(m, T.dg, tc_grad(m, L.in_t), nullptr, 0, ginit[L.in_t] ? EPI_ACCUM : EPI_STORE, "tc_gemm_kernel/dgrad",
-                  layer_flops(L, B), st);
+                  layer_flops(L, B), st, L.scope.c_str());
       if (rc) return rc;
       ginit[L.in_t] = 1;
     }

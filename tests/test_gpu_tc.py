@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 def tc_gemm(mn, A, B, raw_hi=0, bn=0, ksplit=1, stats=False, chunk_kb=0):
     from hypelcnn_b200 import _native as N
     A, B = A.cuda().contiguous(), B.cuda().contiguous()
-    if mn:
+    if mn & 1:
         K, M = A.shape
         Nn = B.shape[1]
     else:
@@ -42,6 +42,44 @@ def test_kmajor_3xtf32_matches_fp64(M, N, K):
     fp32 = rel_err(A @ B.T, ref)
     err = rel_err(got, ref)
     assert err < max(3e-6, 4 * fp32), (err, fp32)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (128, 64, 32), (300, 120, 145), (1000, 480, 240), (77, 16, 8),
+                                   (130, 980, 2940), (40000, 240, 480)])
+def test_kmajor_cta_pair_matches_fp64(M, N, K):
+    """cta_group::2: two CTAs share the B tile (each loads half of it); odd tile counts get a phantom tile.
+    The last shape has more tile pairs than SM pairs, so the persistent tile walk wraps."""
+    g = torch.Generator().manual_seed(M * 7 + N + 1)
+    A = torch.randn((M, K), generator=g)
+    B = torch.randn((N, K), generator=g)
+    ref = A.double() @ B.double().T
+    got = tc_gemm(2, A, B)
+    fp32 = rel_err(A @ B.T, ref)
+    err = rel_err(got, ref)
+    assert err < max(3e-6, 4 * fp32), (err, fp32)
+
+
+@pytest.mark.parametrize("bn", [16, 32, 64])
+def test_kmajor_cta_pair_multiple_b_boxes(bn):
+    g = torch.Generator().manual_seed(bn + 100)
+    A = torch.randn((512, 120), generator=g)
+    B = torch.randn((240, 120), generator=g)
+    ref = A.double() @ B.double().T
+    assert rel_err(tc_gemm(2, A, B, bn=bn), ref) < 4e-6
+
+
+def test_kmajor_persistent_wraps_tiles():
+    """more tiles than SMs: every CTA walks several tiles, smem / TMEM rings keep running across them"""
+    g = torch.Generator().manual_seed(77)
+    A = torch.randn((128 * 400, 96), generator=g)
+    B = torch.randn((120, 96), generator=g)
+    ref = A.double() @ B.double().T
+    D, S = tc_gemm(0, A, B, stats=True)
+    assert rel_err(D, ref) < 4e-6
+    assert float((S[:, 0, :].double().sum(0) - ref.sum(0)).abs().max()) < 2e-2
+    D2, S2 = tc_gemm(2, A, B, stats=True)
+    assert rel_err(D2, ref) < 4e-6
+    assert torch.equal(S, S2) or float((S - S2).abs().max()) < 1e-3
 
 
 @pytest.mark.parametrize("bn", [16, 32, 64])
