@@ -981,6 +981,7 @@ int hyp_debug_tc_gemm(int mn_flags, const float* A, const float* B, int M, int N
         t.cb[0].tcol = 0;
         t.cb[0].width = nw;
         t.cb[0].stats_col = n0;
+        t.n_cols = s.n_mma;
         tiles.push_back(t);
       }
     }

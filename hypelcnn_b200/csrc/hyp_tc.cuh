@@ -20,6 +20,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "hyp_common.cuh"
 
@@ -34,6 +35,9 @@ constexpr int TC_PLANE_A = TC_BM * 128;    // bytes of one A plane per stage
 constexpr int TC_MAX_COLS = 256;
 constexpr int TC_MAX_CB = 8;               // column blocks per tile           // accumulator columns per tile
 constexpr int TC_SMEM_LIMIT = 226 * 1024;
+// after the stage ring: barriers + TMEM slot (256 B), statistics partials [2][4][256] floats, epilogue staging
+// [8 warps][32 rows][20 floats]
+constexpr int TC_SMEM_FIXED = 256 + 2 * 4 * TC_MAX_COLS * 4 + TC_EPI_WARPS * 32 * 20 * 4;
 
 struct alignas(16) TcSeg {
   int32_t a0, a1, a2;  // A box coordinates (tensor dims 0..2) at K block 0; dim 3 = plane
@@ -62,7 +66,8 @@ struct alignas(16) TcTile {
   int32_t a1_add;     // added to every segment's a1 (K-major: first row of the tile)
   int32_t b1_add;     // added to every segment's b1 (K-major: first B row of the tile's N range)
   int32_t a0_add;     // added to every segment's a0 (MN-major: first A column of the tile)
-  int32_t pad[2];
+  int32_t n_cols;     // accumulator columns the tile uses (max n_mma of its segments)
+  int32_t pad[1];
   TcColBlock cb[TC_MAX_CB];
 };
 
@@ -80,14 +85,15 @@ struct TcParams {
   int32_t chunk_kb;   // K blocks the tensor core accumulates before the fp32 register merge
   int32_t stages;
   int32_t ntiles;     // tiles of this launch (multiple of the CTA group size)
+  unsigned long long* timing;  // nullable: [CTA][8] cycle counters (HYP_TC_TIMING diagnostics)
 };
 
 // b_rows = B rows held by ONE CTA per stage and plane
 inline size_t tc_smem_bytes(int b_rows, int stages) {
-  return 1024 + (size_t)stages * (2 * TC_PLANE_A + 2 * (size_t)b_rows * 128) + 256 + 2 * 4 * TC_MAX_COLS * sizeof(float);
+  return 1024 + (size_t)stages * (2 * TC_PLANE_A + 2 * (size_t)b_rows * 128) + TC_SMEM_FIXED;
 }
 inline int tc_pick_stages(int b_rows) {
-  const size_t fixed = 1024 + 256 + 2 * 4 * TC_MAX_COLS * sizeof(float);
+  const size_t fixed = 1024 + TC_SMEM_FIXED;
   const size_t st = 2 * TC_PLANE_A + 2 * (size_t)b_rows * 128;
   int s = (int)((TC_SMEM_LIMIT - fixed) / st);
   return s > 8 ? 8 : s;
@@ -246,6 +252,91 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// ---- warp-uniform issue helpers --------------------------------------------------------------
+// The producer and MMA roles run with all 32 lanes in uniform control flow and predicate the
+// single-thread instructions on `pred` (1 on the elected lane).  With every operand provably
+// warp-uniform the compiler keeps descriptors in uniform registers; a `if (lane == 0)` branch
+// instead makes it wrap every UTCHMMA / UTMALDG in an ELECT + R2UR waterfall loop (~20 extra
+// instructions per MMA, measured: the issue loop, not the tensor pipe, paced small-N tiles).
+__device__ __forceinline__ uint32_t elect_one_pred() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, q;\n\t}"
+      : "=r"(pred));
+  return pred;
+}
+template <typename T>
+__device__ __forceinline__ T uni(T v) { return __shfl_sync(0xffffffffu, v, 0); }
+
+template <int CG>
+__device__ __forceinline__ void mma_tf32_u(uint32_t pred, uint32_t tmem_d, uint32_t a_lo32, uint32_t b_lo32, uint32_t desc_hi32,
+                                           uint32_t idesc, uint32_t accum) {
+  if (CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "setp.ne.b32 q, %6, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo32), "r"(b_lo32), "r"(desc_hi32), "r"(idesc), "r"(accum), "r"(pred)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "setp.ne.b32 q, %6, 0;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo32), "r"(b_lo32), "r"(desc_hi32), "r"(idesc), "r"(accum), "r"(pred)
+        : "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tc_commit_u(uint32_t pred, uint32_t bar) {
+  if (CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(bar), "r"(pred) : "memory");
+  } else {
+    const uint16_t mask = 3;
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %2;\n\t}"
+        ::"r"(bar), "r"(pred), "h"(mask) : "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tma_load_4d_u(uint32_t pred, uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                              int c2, int c3) {
+  if (CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %7, 0;\n\t"
+        "@q cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t}"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(pred)
+        : "memory");
+  } else {  // data lands in this CTA's smem, the transaction bytes are counted on the leader's barrier
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %7, 0;\n\t"
+        "@q cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t}"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(pred)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void mbar_expect_tx_u(uint32_t pred, uint32_t bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
+      ::"r"(bar), "r"(bytes), "r"(pred) : "memory");
+}
+
+constexpr int TC_STAGE_LD = 20;                            // floats per staged row (16 + pad, keeps float4 alignment)
+constexpr int TC_STAGE_FLOATS = 32 * TC_STAGE_LD;          // per epilogue warp
+
 template <bool MN, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
@@ -258,12 +349,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t bar_base = base + (uint32_t)p.stages * stage_bytes;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (size_t)p.stages * stage_bytes + 192);
   float* s_part = reinterpret_cast<float*>(gen + (size_t)p.stages * stage_bytes + 256);  // [2][4][TC_MAX_COLS]
+  float* s_stage = s_part + 2 * 4 * TC_MAX_COLS;                                         // [8 warps][32][TC_STAGE_LD]
   auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(p.stages + s); };
   auto tfull_bar = [&](int b) { return bar_base + 8u * (uint32_t)(2 * p.stages + b); };
   auto tempty_bar = [&](int b) { return bar_base + 8u * (uint32_t)(2 * p.stages + 2 + b); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long tm_kernel0 = p.timing ? clock64() : 0;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
   // tile walk: group g = blockIdx.x / CG handles tile slots g, g + G, ...; slot t = tiles [t*CG, t*CG + CG)
@@ -299,110 +392,115 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  const uint32_t tmem_base = uni(*reinterpret_cast<volatile uint32_t*>(tmem_slot));
 
   if (warp == 0) {
-    // ===================== TMA producer (one per CTA) =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int slot = group; slot < nslots; slot += ngroups) {
-        const TcTile* T = p.tiles + (size_t)slot * CG + rank;
-        const int seg_begin = T->seg_begin, seg_count = T->seg_count;
-        const int a0_add = T->a0_add, a1_add = T->a1_add, b1_add = T->b1_add;
-        for (int si = 0; si < seg_count; si++) {
-          TcSeg sg = p.segs[seg_begin + si];
-          sg.a0 += a0_add;
-          sg.a1 += a1_add;
-          sg.b1 += b1_add;
-          // B boxes this CTA loads: K-major boxes of bn/CG rows, MN-major boxes of 32 columns
-          const uint32_t b_box_bytes = MN ? 4096u : (uint32_t)(p.bn / CG) * 128u;
-          const int nb = MN ? sg.nb / CG : sg.nb;
-          const int b_first = MN ? (int)rank * nb : 0;                          // first 32-column box
-          const int b_row0 = MN ? 0 : (int)rank * (sg.n_mma / CG);              // first B row
-          const uint32_t tx_cta = 2u * TC_PLANE_A + 2u * (uint32_t)nb * b_box_bytes;
-          for (int kb = 0; kb < sg.nk; kb++) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t fb_local = full_bar(stage);
-            const uint32_t fb = CG == 2 ? mapa_shared(fb_local, 0) : fb_local;
-            if (leader) mbar_expect_tx(fb_local, tx_cta * CG);
-            const uint32_t a_s = base + (uint32_t)stage * stage_bytes;
-            const uint32_t b_s = a_s + 2u * TC_PLANE_A;
+    // ===================== TMA producer (one warp per CTA, one elected lane issues) =====================
+    const uint32_t pred = elect_one_pred();
+    int stage = 0;
+    uint32_t phase = 0;
+    long long tm_wait_empty = 0;
+    for (int slot = group; slot < nslots; slot += ngroups) {
+      const TcTile* T = p.tiles + (size_t)slot * CG + rank;
+      const int seg_begin = uni(T->seg_begin), seg_count = uni(T->seg_count);
+      const int a0_add = uni(T->a0_add), a1_add = uni(T->a1_add), b1_add = uni(T->b1_add);
+      for (int si = 0; si < seg_count; si++) {
+        const TcSeg* sp = p.segs + seg_begin + si;
+        const int sa0 = uni(sp->a0) + a0_add, sa1 = uni(sp->a1) + a1_add, sa2 = uni(sp->a2);
+        const int sb0 = uni(sp->b0), sb1 = uni(sp->b1) + b1_add, sb2 = uni(sp->b2);
+        const int snk = uni(sp->nk), sn = uni(sp->n_mma), snb = uni(sp->nb);
+        // B boxes this CTA loads: K-major boxes of bn/CG rows, MN-major boxes of 32 columns
+        const uint32_t b_box_bytes = MN ? 4096u : (uint32_t)(p.bn / CG) * 128u;
+        const int nb = MN ? snb / CG : snb;
+        const int b_first = MN ? (int)rank * nb : 0;               // first 32-column box
+        const int b_row0 = MN ? 0 : (int)rank * (sn / CG);          // first B row
+        const uint32_t tx_cta = 2u * TC_PLANE_A + 2u * (uint32_t)nb * b_box_bytes;
+        for (int kb = 0; kb < snk; kb++) {
+          { const long long t0 = p.timing ? clock64() : 0; mbar_wait(empty_bar(stage), phase ^ 1u); if (p.timing) tm_wait_empty += clock64() - t0; }
+          const uint32_t fb_local = full_bar(stage);
+          const uint32_t fb = CG == 2 ? mapa_shared(fb_local, 0) : fb_local;
+          if (leader) mbar_expect_tx_u(pred, fb_local, tx_cta * CG);
+          const uint32_t a_s = base + (uint32_t)stage * stage_bytes;
+          const uint32_t b_s = a_s + 2u * TC_PLANE_A;
 #pragma unroll
-            for (int pl = 0; pl < 2; pl++) {
-              if (!MN) {
-                tma_load_4d<CG>(a_s + pl * TC_PLANE_A, &tmA, fb, sg.a0 + kb * TC_KB, sg.a1, sg.a2, pl);
-                for (int j = 0; j < nb; j++)
-                  tma_load_4d<CG>(b_s + pl * b_plane + j * b_box_bytes, &tmB, fb, sg.b0 + kb * TC_KB,
-                                  sg.b1 + b_row0 + j * (p.bn / CG), sg.b2, pl);
-              } else {
+          for (int pl = 0; pl < 2; pl++) {
+            if (!MN) {
+              tma_load_4d_u<CG>(pred, a_s + pl * TC_PLANE_A, &tmA, fb, sa0 + kb * TC_KB, sa1, sa2, pl);
+              for (int j = 0; j < nb; j++)
+                tma_load_4d_u<CG>(pred, b_s + pl * b_plane + j * b_box_bytes, &tmB, fb, sb0 + kb * TC_KB,
+                                  sb1 + b_row0 + j * (p.bn / CG), sb2, pl);
+            } else {
 #pragma unroll
-                for (int i = 0; i < 4; i++)
-                  tma_load_4d<CG>(a_s + pl * TC_PLANE_A + i * 4096, &tmA, fb, sg.a0 + i * 32, sg.a1 + kb * TC_KB, sg.a2, pl);
-                for (int j = 0; j < nb; j++)
-                  tma_load_4d<CG>(b_s + pl * b_plane + j * 4096, &tmB, fb, sg.b0 + (b_first + j) * 32, sg.b1 + kb * TC_KB,
-                                  sg.b2, pl);
-              }
+              for (int i = 0; i < 4; i++)
+                tma_load_4d_u<CG>(pred, a_s + pl * TC_PLANE_A + i * 4096, &tmA, fb, sa0 + i * 32, sa1 + kb * TC_KB, sa2, pl);
+              for (int j = 0; j < nb; j++)
+                tma_load_4d_u<CG>(pred, b_s + pl * b_plane + j * 4096, &tmB, fb, sb0 + (b_first + j) * 32, sb1 + kb * TC_KB,
+                                  sb2, pl);
             }
-            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
+    if (p.timing && lane == 0) p.timing[blockIdx.x * 8 + 1] = (unsigned long long)tm_wait_empty;
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && leader) {
+    // ===================== MMA issuer (leader CTA only; warp-uniform, elected lane issues) =====================
+    if (leader) {
+      const uint32_t pred = elect_one_pred();
       int stage = 0;
       uint32_t phase = 0;
       uint32_t gchunk = 0;  // chunks issued so far, all tiles
+      long long tm_wait_full = 0, tm_wait_tempty = 0;
+      // smem matrix descriptors: only the 14-bit start address field changes between operands
+      //   K-major : LBO 16 B, SBO 1024 B, SWIZZLE_128B;  MN-major: LBO 4096 B, SBO 512 B, SWIZZLE_128B_BASE32B
+      const uint32_t desc_hi32 = (MN ? (512u >> 4) : (1024u >> 4)) | (1u << 14) | ((MN ? 1u : 2u) << 29);
+      const uint32_t desc_lo_fixed = (MN ? (4096u >> 4) : (16u >> 4)) << 16;
+      const uint32_t ks_step = MN ? (1024u >> 4) : (32u >> 4);  // descriptor address units per K step of 8
       for (int slot = group; slot < nslots; slot += ngroups) {
         const TcTile* T = p.tiles + (size_t)slot * CG;
-        const int seg_begin = T->seg_begin, seg_count = T->seg_count, total_kb = T->total_kb;
+        const int seg_begin = uni(T->seg_begin), seg_count = uni(T->seg_count), total_kb = uni(T->total_kb);
         uint32_t accum = 0;
         int kcount = 0;  // K blocks of this tile issued so far
         uint32_t buf = 0;
         for (int si = 0; si < seg_count; si++) {
-          const TcSeg sg = p.segs[seg_begin + si];
-          const uint32_t idesc = make_idesc_tf32(sg.n_mma, MN, CG);
-          for (int kb = 0; kb < sg.nk; kb++, kcount++) {
+          const TcSeg* sp = p.segs + seg_begin + si;
+          const int snk = uni(sp->nk);
+          const uint32_t idesc = make_idesc_tf32(uni(sp->n_mma), MN, CG);
+          for (int kb = 0; kb < snk; kb++, kcount++) {
             if (kcount % CH == 0) {  // new chunk: its TMEM buffer must have been drained
               buf = gchunk & 1u;
-              mbar_wait(tempty_bar(buf), ((gchunk >> 1) & 1u) ^ 1u);
+              { const long long t0 = p.timing ? clock64() : 0; mbar_wait(tempty_bar(buf), ((gchunk >> 1) & 1u) ^ 1u); if (p.timing) tm_wait_tempty += clock64() - t0; }
               tc_fence_after();
               accum = 0;
             }
             const uint32_t tmem_d = tmem_base + buf * TC_MAX_COLS;
-            mbar_wait(full_bar(stage), phase);
+            { const long long t0 = p.timing ? clock64() : 0; mbar_wait(full_bar(stage), phase); if (p.timing) tm_wait_full += clock64() - t0; }
             tc_fence_after();
             const uint32_t a_s = base + (uint32_t)stage * stage_bytes;
-            const uint32_t b_s = a_s + 2u * TC_PLANE_A;
+            const uint32_t a_hi = desc_lo_fixed | ((a_s & 0x3FFFFu) >> 4);
+            const uint32_t a_lo = a_hi + (TC_PLANE_A >> 4);
+            const uint32_t b_hi = a_hi + (2u * TC_PLANE_A >> 4);
+            const uint32_t b_lo = b_hi + (b_plane >> 4);
 #pragma unroll
             for (int ks = 0; ks < TC_KB / 8; ks++) {
-              uint64_t a_hi, a_lo, b_hi, b_lo;
-              if (!MN) {  // rows of 128 B, 8-row groups 1024 B apart; K advances 32 B inside the swizzled row
-                a_hi = make_smem_desc(a_s + ks * 32, 16, 1024);
-                a_lo = make_smem_desc(a_s + TC_PLANE_A + ks * 32, 16, 1024);
-                b_hi = make_smem_desc(b_s + ks * 32, 16, 1024);
-                b_lo = make_smem_desc(b_s + b_plane + ks * 32, 16, 1024);
-              } else {    // 32-column atoms 4096 B apart (LBO), 4-row K groups 512 B apart (SBO), 32-byte swizzle
-                a_hi = make_smem_desc(a_s + ks * 1024, 4096, 512, 1);
-                a_lo = make_smem_desc(a_s + TC_PLANE_A + ks * 1024, 4096, 512, 1);
-                b_hi = make_smem_desc(b_s + ks * 1024, 4096, 512, 1);
-                b_lo = make_smem_desc(b_s + b_plane + ks * 1024, 4096, 512, 1);
-              }
-              mma_tf32<CG>(tmem_d, a_lo, b_hi, idesc, accum);
-              mma_tf32<CG>(tmem_d, a_hi, b_lo, idesc, 1);
-              mma_tf32<CG>(tmem_d, a_hi, b_hi, idesc, 1);
+              const uint32_t o = (uint32_t)ks * ks_step;
+              mma_tf32_u<CG>(pred, tmem_d, a_lo + o, b_hi + o, desc_hi32, idesc, accum);
+              mma_tf32_u<CG>(pred, tmem_d, a_hi + o, b_lo + o, desc_hi32, idesc, 1);
+              mma_tf32_u<CG>(pred, tmem_d, a_hi + o, b_hi + o, desc_hi32, idesc, 1);
               accum = 1;
             }
-            tc_commit<CG>(empty_bar(stage));  // frees the stage (in both CTAs) once these MMAs have read it
+            tc_commit_u<CG>(pred, empty_bar(stage));  // frees the stage (in both CTAs) once these MMAs have read it
             if (kcount % CH == CH - 1 || kcount == total_kb - 1) {
-              tc_commit<CG>(tfull_bar(buf));
+              tc_commit_u<CG>(pred, tfull_bar(buf));
               gchunk++;
             }
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
         }
+      }
+      if (p.timing && lane == 0) {
+        p.timing[blockIdx.x * 8 + 2] = (unsigned long long)tm_wait_full;
+        p.timing[blockIdx.x * 8 + 3] = (unsigned long long)tm_wait_tempty;
       }
     }
   } else {
@@ -410,14 +508,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
+    float* st = s_stage + (warp - 2) * TC_STAGE_FLOATS;
     uint32_t gchunk = 0;
+    long long tm_wait_tfull = 0, tm_store = 0, tm_drain = 0, tm_tiles = 0;
     const uint32_t tempty_remote0 = CG == 2 ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
     const uint32_t tempty_remote1 = CG == 2 ? mapa_shared(tempty_bar(1), 0) : tempty_bar(1);
     for (int slot = group; slot < nslots; slot += ngroups) {
       const TcTile* T = p.tiles + (size_t)slot * CG + rank;
       const int seg_begin = T->seg_begin, seg_count = T->seg_count, total_kb = T->total_kb;
       const int m_valid = T->m_valid, ld_out = T->ld_out, ncb = T->ncb;
-      const bool rvalid = row < m_valid;
+      // the two column halves split the tile's accumulator columns (multiples of 32 each)
+      const int hw = ((T->n_cols + 63) >> 6) << 5;
+      const int cbase = half * hw;
       float acc[TC_MAX_COLS / 2];
 #pragma unroll
       for (int i = 0; i < TC_MAX_COLS / 2; i++) acc[i] = 0.f;
@@ -439,12 +541,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (si < seg_count) { left = p.segs[seg_begin + si].nk; n_first = p.segs[seg_begin + si].n_mma; }
             }
           }
+          long long t0 = p.timing ? clock64() : 0;
           mbar_wait(tfull_bar(buf), (gchunk >> 1) & 1u);
+          if (p.timing) { const long long t1 = clock64(); tm_wait_tfull += t1 - t0; t0 = t1; }
           tc_fence_after();
 #pragma unroll
           for (int g = 0; g < 4; g++) {
-            const int tc0 = half * (TC_MAX_COLS / 2) + g * 32;
-            if (tc0 < n_c) {
+            const int tc0 = cbase + g * 32;
+            if (g * 32 < hw && tc0 < n_c) {
               float v[32];
               tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC_MAX_COLS + tc0), v);
 #pragma unroll
@@ -455,63 +559,101 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
           if (lane == 0) {
             const uint32_t tb = buf ? tempty_remote1 : tempty_remote0;
-            if (CG == 2)
-              asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(tb) : "memory");
+            if (CG == 2)  // TMEM reads are complete (tcgen05.wait::ld): no memory ordering needed, skip the release fence
+              asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(tb) : "memory");
             else
               asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tb) : "memory");
           }
+          if (p.timing) tm_drain += clock64() - t0;
         }
       }
-      // ---- write the tile: column blocks map accumulator columns to output columns ----
+      const long long t_store0 = p.timing ? clock64() : 0;
+      // ---- write the tile.  Each warp stages 32 rows x 16 columns in smem and writes them back as
+      //      row segments (4 lanes x float4 = 64 contiguous bytes per row, 8 rows per instruction), so
+      //      global stores / read-modify-writes are sector-complete instead of one row per lane.
+      //      Column blocks map accumulator columns to output columns; they start at multiples of 16.
+      const int r_lane = lane >> 2, c4 = (lane & 3) * 4;
 #pragma unroll
       for (int g = 0; g < 4; g++) {
-        const int tc0 = half * (TC_MAX_COLS / 2) + g * 32;
-        float s1 = 0.f, s2 = 0.f;  // lane l: column tc0 + l
-        bool any = false;
-        for (int b = 0; b < ncb; b++) {
-          const TcColBlock cb = T->cb[b];
-          const int lo = max(cb.tcol, tc0) - tc0, hi = min(cb.tcol + cb.width, tc0 + 32) - tc0;
-          if (lo >= hi) continue;
-          any = true;
-          if (rvalid) {
-            // output column of accumulator column tc0 + j is (tc0 + j - cb.tcol)
-            float* orow = p.out + cb.out_off + (int64_t)row * ld_out + (tc0 - cb.tcol);
-            const bool vec = ((cb.out_off | (int64_t)ld_out | (int64_t)(tc0 - cb.tcol)) & 3) == 0;
-            if (p.epi == EPI_ATOMIC) {
+        const int tc0 = cbase + g * 32;
+        if (g * 32 >= hw || tc0 >= T->n_cols) continue;  // warp-uniform
 #pragma unroll
-              for (int j = 0; j < 32; j++)
-                if (j >= lo && j < hi) atomicAdd(orow + j, acc[g * 32 + j]);
-            } else {
-              if (p.epi == EPI_ACCUM) {
+        for (int hh = 0; hh < 2; hh++) {
+          const int c0 = tc0 + hh * 16;  // first accumulator column of this 16-column slab
+          // column block holding the slab (warp-uniform search)
+          int cb_i = -1;
+          for (int b = 0; b < ncb; b++)
+            if (T->cb[b].tcol <= c0 && (cb_i < 0 || T->cb[b].tcol > T->cb[cb_i].tcol)) cb_i = b;
+          if (cb_i < 0) continue;
+          const TcColBlock cb = T->cb[cb_i];
+          if (c0 >= cb.tcol + cb.width) continue;  // padding columns of the block
 #pragma unroll
-                for (int j = 0; j < 32; j++)
-                  if (j >= lo && j < hi) acc[g * 32 + j] += orow[j];
-              }
+          for (int k = 0; k < 4; k++)
+            *reinterpret_cast<float4*>(st + lane * TC_STAGE_LD + 4 * k) =
+                make_float4(acc[g * 32 + hh * 16 + 4 * k], acc[g * 32 + hh * 16 + 4 * k + 1],
+                            acc[g * 32 + hh * 16 + 4 * k + 2], acc[g * 32 + hh * 16 + 4 * k + 3]);
+          __syncwarp();
+          const int ocol = c0 + c4 - cb.tcol;             // output column of this lane's 4 values
+          const int nval = min(4, cb.width - ocol);       // valid values (<= 0: none)
+          float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                if (vec && j >= lo && j + 3 < hi) {
-                  *reinterpret_cast<float4*>(orow + j) =
-                      make_float4(acc[g * 32 + j], acc[g * 32 + j + 1], acc[g * 32 + j + 2], acc[g * 32 + j + 3]);
+          for (int i = 0; i < 4; i++) {
+            const int r = i * 8 + r_lane;
+            const int grow = q * 32 + r;
+            float4 v = *reinterpret_cast<const float4*>(st + r * TC_STAGE_LD + c4);
+            if (grow < m_valid && nval > 0) {
+              float* optr = p.out + cb.out_off + (int64_t)grow * ld_out + ocol;
+              const bool vec = nval == 4 && ((reinterpret_cast<uintptr_t>(optr) & 15) == 0);
+              if (p.epi == EPI_ATOMIC) {
+                if (vec) {
+                  atomicAdd(reinterpret_cast<float4*>(optr), v);
                 } else {
-#pragma unroll
-                  for (int t = 0; t < 4; t++)
-                    if (j + t >= lo && j + t < hi) orow[j + t] = acc[g * 32 + j + t];
+                  atomicAdd(optr, v.x);
+                  if (nval > 1) atomicAdd(optr + 1, v.y);
+                  if (nval > 2) atomicAdd(optr + 2, v.z);
+                  if (nval > 3) atomicAdd(optr + 3, v.w);
                 }
+              } else if (vec) {
+                if (p.epi == EPI_ACCUM) {
+                  const float4 o = *reinterpret_cast<const float4*>(optr);
+                  v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                }
+                *reinterpret_cast<float4*>(optr) = v;
+              } else {
+                if (p.epi == EPI_ACCUM) {
+                  v.x += optr[0];
+                  if (nval > 1) v.y += optr[1];
+                  if (nval > 2) v.z += optr[2];
+                  if (nval > 3) v.w += optr[3];
+                }
+                optr[0] = v.x;
+                if (nval > 1) optr[1] = v.y;
+                if (nval > 2) optr[2] = v.z;
+                if (nval > 3) optr[3] = v.w;
+              }
+              // statistics are taken on the GEMM result itself (EPI_STORE launches only)
+              s1[0] += v.x; s1[1] += v.y; s1[2] += v.z; s1[3] += v.w;
+              s2[0] += v.x * v.x; s2[1] += v.y * v.y; s2[2] += v.z * v.z; s2[3] += v.w * v.w;
+            }
+          }
+          if (p.stats) {
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+#pragma unroll
+              for (int o = 4; o <= 16; o <<= 1) {
+                s1[t] += __shfl_xor_sync(0xffffffffu, s1[t], o);
+                s2[t] += __shfl_xor_sync(0xffffffffu, s2[t], o);
+              }
+            }
+            if (lane < 4) {
+#pragma unroll
+              for (int t = 0; t < 4; t++) {
+                s_part[(0 * 4 + q) * TC_MAX_COLS + c0 + c4 + t] = s1[t];
+                s_part[(1 * 4 + q) * TC_MAX_COLS + c0 + c4 + t] = s2[t];
               }
             }
           }
-        }
-        if (p.stats && __any_sync(0xffffffffu, any)) {
-          float v[32], sq[32];
-#pragma unroll
-          for (int j = 0; j < 32; j++) {
-            v[j] = rvalid ? acc[g * 32 + j] : 0.f;
-            sq[j] = v[j] * v[j];
-          }
-          s1 = warp_transpose_sum(v, lane);
-          s2 = warp_transpose_sum(sq, lane);
-          s_part[(0 * 4 + q) * TC_MAX_COLS + tc0 + lane] = s1;
-          s_part[(1 * 4 + q) * TC_MAX_COLS + tc0 + lane] = s2;
+          __syncwarp();  // the staging rows are rewritten by the next slab
         }
       }
       if (p.stats) {
@@ -533,10 +675,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");  // s_part is reused by the next tile
       }
+      if (p.timing) { tm_store += clock64() - t_store0; tm_tiles++; }
+    }
+    if (p.timing && warp == 2 && lane == 0) {
+      p.timing[blockIdx.x * 8 + 4] = (unsigned long long)tm_wait_tfull;
+      p.timing[blockIdx.x * 8 + 5] = (unsigned long long)tm_store;
+      p.timing[blockIdx.x * 8 + 6] = (unsigned long long)tm_drain;
+      p.timing[blockIdx.x * 8 + 7] = (unsigned long long)tm_tiles;
     }
   }
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (p.timing && threadIdx.x == 0) p.timing[blockIdx.x * 8 + 0] = (unsigned long long)(clock64() - tm_kernel0);
   if (warp == 1) {
     tc_fence_after();
     if (CG == 1)
@@ -589,6 +739,8 @@ inline int make_map(CUtensorMap* map, const float* base, const uint64_t dims[4],
 
 constexpr int TC_DEFAULT_CHUNK_KB = 4;
 
+static thread_local const char* g_tc_timing_tag = nullptr;  // label of the next launch in HYP_TC_TIMING output
+
 inline int tc_sm_count() {
   static int sms = 0;
   if (!sms) {
@@ -628,8 +780,36 @@ inline int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p,
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CG > 1 ? 1 : 0;
+  static const bool timing_on = getenv("HYP_TC_TIMING") != nullptr;
+  unsigned long long* tbuf = nullptr;
+  if (timing_on) {
+    HYP_CUDA(cudaMalloc(&tbuf, (size_t)groups * CG * 8 * sizeof(unsigned long long)));
+    HYP_CUDA(cudaMemsetAsync(tbuf, 0, (size_t)groups * CG * 8 * sizeof(unsigned long long), st));
+    p.timing = tbuf;
+  }
   HYP_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<MN, CG>, tmA, tmB, p));
   HYP_LAUNCHED();
+  if (timing_on) {
+    std::vector<unsigned long long> h((size_t)groups * CG * 8);
+    HYP_CUDA(cudaStreamSynchronize(st));
+    HYP_CUDA(cudaMemcpy(h.data(), tbuf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    cudaFree(tbuf);
+    double s[8] = {0}, mx0 = 0, mn0 = 1e30;
+    const int n = groups * CG;
+    for (int c = 0; c < n; c++) {
+      for (int k = 0; k < 8; k++) s[k] += (double)h[(size_t)c * 8 + k];
+      mx0 = std::max(mx0, (double)h[(size_t)c * 8]);
+      mn0 = std::min(mn0, (double)h[(size_t)c * 8]);
+    }
+    const int nl = n / CG;  // MMA issuers
+    fprintf(stderr,
+            "[tc_timing] %-28s mn=%d cg=%d ctas=%d tiles=%d stages=%d brows=%d | kcyc total avg %.0f min %.0f max %.0f | "
+            "prod_wait_empty %.0f | mma_wait_full %.0f mma_wait_tempty %.0f | epi_wait_tfull %.0f epi_drain %.0f epi_store %.0f | "
+            "tiles/cta %.1f\n",
+            g_tc_timing_tag ? g_tc_timing_tag : "?", (int)MN, CG, n, ntiles, p.stages, p.b_rows, s[0] / n / 1e3, mn0 / 1e3,
+            mx0 / 1e3, s[1] / n / 1e3, s[2] / nl / 1e3, s[3] / nl / 1e3, s[4] / n / 1e3, s[6] / n / 1e3, s[5] / n / 1e3,
+            s[7] / n);
+  }
   return HYP_OK;
 }
 

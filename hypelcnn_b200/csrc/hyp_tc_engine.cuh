@@ -634,6 +634,10 @@ static int tc_plan(hyp_model& m, int64_t B) {
       }
     }
   }
+  for (TcTile& t : pb.tiles) {
+    t.n_cols = 0;
+    for (int i = 0; i < t.seg_count; i++) t.n_cols = std::max(t.n_cols, pb.segs[t.seg_begin + i].n_mma);
+  }
   // upload
   if (pb.segs.size() > S.segs_cap) {
     if (S.segs_dev) cudaFree(S.segs_dev);
@@ -662,6 +666,9 @@ static int tc_run(hyp_model& m, const TcLaunch& l, float* out, float* stats, int
   static const bool per_layer = getenv("HYP_PROF_LAYERS") != nullptr;
   std::string full = tag;
   if (per_layer && scope) full += std::string("/") + scope;
+  static const bool timing_on = getenv("HYP_TC_TIMING") != nullptr;
+  if (timing_on && !per_layer && scope) full += std::string("/") + scope;
+  g_tc_timing_tag = full.c_str();
   g_prof.begin(st, full.c_str(), flops, 0.0);
   const int rc = l.mn ? launch_tc<true, 1>(l.tmA, l.tmB, p, l.ntiles, st)
                       : (l.cg == 2 ? launch_tc<false, 2>(l.tmA, l.tmB, p, l.ntiles, st)
