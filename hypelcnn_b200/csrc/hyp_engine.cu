@@ -981,11 +981,11 @@ int hyp_debug_tc_gemm(int mn_flags, const float* A, const float* B, int M, int N
         t.cb[0].tcol = 0;
         t.cb[0].width = nw;
         t.cb[0].stats_col = n0;
-        t.n_cols = s.n_mma;
         tiles.push_back(t);
       }
     }
   HYP_CHECK_ARG(cg == 1 || bn * (int)cdiv(max_brows, bn) == max_brows, "bad bn");
+  if ((rc = tc_finalize_tiles(tiles, segs))) return rc;
   TcSeg* dsegs = nullptr;
   TcTile* dtiles = nullptr;
   HYP_CUDA(cudaMalloc(&dsegs, segs.size() * sizeof(TcSeg)));

@@ -20,6 +20,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstddef>
 #include <cstdlib>
 
 #include "hyp_common.cuh"
@@ -33,6 +34,8 @@ constexpr int TC_BM = 128;
 constexpr int TC_KB = 32;                  // fp32 elements of K per pipeline stage
 constexpr int TC_PLANE_A = TC_BM * 128;    // bytes of one A plane per stage
 constexpr int TC_MAX_COLS = 256;
+constexpr int TC_MAX_BP = 8;               // distinct MMA widths per tile
+constexpr int TC_MAX_SEGS = 128;           // segments per tile (held in registers across a warp's lanes)
 constexpr int TC_MAX_CB = 8;               // column blocks per tile           // accumulator columns per tile
 constexpr int TC_SMEM_LIMIT = 226 * 1024;
 // after the stage ring: barriers + TMEM slot (256 B), statistics partials [2][4][256] floats, epilogue staging
@@ -49,11 +52,12 @@ struct alignas(16) TcSeg {
 };
 
 struct alignas(16) TcColBlock {
-  int64_t out_off;    // element offset of (tile row 0, block column 0) inside `out`
-  int32_t tcol;       // first accumulator column
+  int32_t tcol;       // first accumulator column (multiple of 16; blocks are listed by increasing tcol)
   int32_t width;      // valid columns
   int32_t stats_col;  // first column in the statistics row
   int32_t pad;
+  int64_t out_off;    // element offset of (tile row 0, block column 0) inside `out`
+  int64_t pad2;
 };
 
 struct alignas(16) TcTile {
@@ -67,7 +71,9 @@ struct alignas(16) TcTile {
   int32_t b1_add;     // added to every segment's b1 (K-major: first B row of the tile's N range)
   int32_t a0_add;     // added to every segment's a0 (MN-major: first A column of the tile)
   int32_t n_cols;     // accumulator columns the tile uses (max n_mma of its segments)
-  int32_t pad[1];
+  int32_t nbp;        // breakpoints below: K block from which the MMA width is bp_n (n_mma never increases)
+  int32_t bp_kb[TC_MAX_BP];
+  int32_t bp_n[TC_MAX_BP];
   TcColBlock cb[TC_MAX_CB];
 };
 
@@ -337,7 +343,7 @@ __device__ __forceinline__ void mbar_expect_tx_u(uint32_t pred, uint32_t bar, ui
 constexpr int TC_STAGE_LD = 20;                            // floats per staged row (16 + pad, keeps float4 alignment)
 constexpr int TC_STAGE_FLOATS = 32 * TC_STAGE_LD;          // per epilogue warp
 
-template <bool MN, int CG>
+template <bool MN, int CG, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -400,15 +406,41 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int stage = 0;
     uint32_t phase = 0;
     long long tm_wait_empty = 0;
+    // tile headers are fetched one tile ahead; a tile's segments are loaded once, spread over the lanes
+    // (segment l + 32 i in register set i of lane l) -- the L1 left beside ~220 KB of smem does not keep
+    // the tables, and an L2 round trip per segment paced short-K tiles
+    int4 hdr0 = make_int4(0, 0, 0, 0), hdrm = hdr0, hdr1 = hdr0;
+    if (group < nslots) {
+      const int4* hp = reinterpret_cast<const int4*>(p.tiles + (size_t)group * CG + rank);
+      hdr0 = __ldg(hp); hdrm = __ldg(hp + 1); hdr1 = __ldg(hp + 2);
+    }
     for (int slot = group; slot < nslots; slot += ngroups) {
-      const TcTile* T = p.tiles + (size_t)slot * CG + rank;
-      const int seg_begin = uni(T->seg_begin), seg_count = uni(T->seg_count);
-      const int a0_add = uni(T->a0_add), a1_add = uni(T->a1_add), b1_add = uni(T->b1_add);
+      // TcTile words: [0] seg_begin seg_count m_valid ncb | [1] ld_out stats_row total_kb a1_add | [2] b1_add a0_add n_cols nbp
+      const int seg_begin = uni(hdr0.x), seg_count = uni(hdr0.y);
+      const int a1_add = uni(hdrm.w), b1_add = uni(hdr1.x), a0_add = uni(hdr1.y);
+      if (slot + ngroups < nslots) {
+        const int4* hp = reinterpret_cast<const int4*>(p.tiles + (size_t)(slot + ngroups) * CG + rank);
+        hdr0 = __ldg(hp); hdrm = __ldg(hp + 1); hdr1 = __ldg(hp + 2);
+      }
+      int4 sA[4], sB[4], sC[4];  // TcSeg words: a0 a1 a2 b0 | b1 b2 nk n_mma | nb - - -
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        sA[i] = sB[i] = sC[i] = make_int4(0, 0, 0, 0);
+        if (lane + 32 * i < seg_count) {
+          const int4* sp4 = reinterpret_cast<const int4*>(p.segs + seg_begin + lane + 32 * i);
+          sA[i] = __ldg(sp4); sB[i] = __ldg(sp4 + 1); sC[i] = __ldg(sp4 + 2);
+        }
+      }
       for (int si = 0; si < seg_count; si++) {
-        const TcSeg* sp = p.segs + seg_begin + si;
-        const int sa0 = uni(sp->a0) + a0_add, sa1 = uni(sp->a1) + a1_add, sa2 = uni(sp->a2);
-        const int sb0 = uni(sp->b0), sb1 = uni(sp->b1) + b1_add, sb2 = uni(sp->b2);
-        const int snk = uni(sp->nk), sn = uni(sp->n_mma), snb = uni(sp->nb);
+        const int rs = si >> 5, src = si & 31;
+        const int4 wA = rs == 0 ? sA[0] : (rs == 1 ? sA[1] : (rs == 2 ? sA[2] : sA[3]));
+        const int4 wB = rs == 0 ? sB[0] : (rs == 1 ? sB[1] : (rs == 2 ? sB[2] : sB[3]));
+        const int4 wC = rs == 0 ? sC[0] : (rs == 1 ? sC[1] : (rs == 2 ? sC[2] : sC[3]));
+        const int sa0 = __shfl_sync(0xffffffffu, wA.x, src) + a0_add, sa1 = __shfl_sync(0xffffffffu, wA.y, src) + a1_add;
+        const int sa2 = __shfl_sync(0xffffffffu, wA.z, src), sb0 = __shfl_sync(0xffffffffu, wA.w, src);
+        const int sb1 = __shfl_sync(0xffffffffu, wB.x, src) + b1_add, sb2 = __shfl_sync(0xffffffffu, wB.y, src);
+        const int snk = __shfl_sync(0xffffffffu, wB.z, src), sn = __shfl_sync(0xffffffffu, wB.w, src);
+        const int snb = __shfl_sync(0xffffffffu, wC.x, src);
         // B boxes this CTA loads: K-major boxes of bn/CG rows, MN-major boxes of 32 columns
         const uint32_t b_box_bytes = MN ? 4096u : (uint32_t)(p.bn / CG) * 128u;
         const int nb = MN ? snb / CG : snb;
@@ -456,16 +488,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t desc_hi32 = (MN ? (512u >> 4) : (1024u >> 4)) | (1u << 14) | ((MN ? 1u : 2u) << 29);
       const uint32_t desc_lo_fixed = (MN ? (4096u >> 4) : (16u >> 4)) << 16;
       const uint32_t ks_step = MN ? (1024u >> 4) : (32u >> 4);  // descriptor address units per K step of 8
+      int4 hdr0 = make_int4(0, 0, 0, 0), hdr1 = make_int4(0, 0, 0, 0);
+      if (group < nslots) {
+        const int4* hp = reinterpret_cast<const int4*>(p.tiles + (size_t)group * CG);
+        hdr0 = __ldg(hp); hdr1 = __ldg(hp + 1);
+      }
       for (int slot = group; slot < nslots; slot += ngroups) {
-        const TcTile* T = p.tiles + (size_t)slot * CG;
-        const int seg_begin = uni(T->seg_begin), seg_count = uni(T->seg_count), total_kb = uni(T->total_kb);
+        const int seg_begin = uni(hdr0.x), seg_count = uni(hdr0.y), total_kb = uni(hdr1.z);
+        if (slot + ngroups < nslots) {
+          const int4* hp = reinterpret_cast<const int4*>(p.tiles + (size_t)(slot + ngroups) * CG);
+          hdr0 = __ldg(hp); hdr1 = __ldg(hp + 1);
+        }
+        int2 sN[4];  // (nk, n_mma) of segment lane + 32 i
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          sN[i] = make_int2(0, 0);
+          if (lane + 32 * i < seg_count)
+            sN[i] = __ldg(reinterpret_cast<const int2*>(&p.segs[seg_begin + lane + 32 * i].nk));
+        }
         uint32_t accum = 0;
         int kcount = 0;  // K blocks of this tile issued so far
         uint32_t buf = 0;
         for (int si = 0; si < seg_count; si++) {
-          const TcSeg* sp = p.segs + seg_begin + si;
-          const int snk = uni(sp->nk);
-          const uint32_t idesc = make_idesc_tf32(uni(sp->n_mma), MN, CG);
+          const int rs = si >> 5, src = si & 31;
+          const int2 wN = rs == 0 ? sN[0] : (rs == 1 ? sN[1] : (rs == 2 ? sN[2] : sN[3]));
+          const int snk = __shfl_sync(0xffffffffu, wN.x, src);
+          const uint32_t idesc = make_idesc_tf32(__shfl_sync(0xffffffffu, wN.y, src), MN, CG);
           for (int kb = 0; kb < snk; kb++, kcount++) {
             if (kcount % CH == 0) {  // new chunk: its TMEM buffer must have been drained
               buf = gchunk & 1u;
@@ -515,32 +563,34 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tempty_remote1 = CG == 2 ? mapa_shared(tempty_bar(1), 0) : tempty_bar(1);
     for (int slot = group; slot < nslots; slot += ngroups) {
       const TcTile* T = p.tiles + (size_t)slot * CG + rank;
-      const int seg_begin = T->seg_begin, seg_count = T->seg_count, total_kb = T->total_kb;
-      const int m_valid = T->m_valid, ld_out = T->ld_out, ncb = T->ncb;
+      // everything the tile needs from its descriptor goes to registers up front: header words, the MMA width
+      // breakpoints (lane i < nbp) and the column blocks (lane b < ncb); later lookups are ballots + shuffles
+      const int4 h0 = __ldg(reinterpret_cast<const int4*>(T));
+      const int4 h1 = __ldg(reinterpret_cast<const int4*>(T) + 1);
+      const int4 h2 = __ldg(reinterpret_cast<const int4*>(T) + 2);
+      const int m_valid = h0.z, ncb = h0.w, ld_out = h1.x, stats_row = h1.y, total_kb = h1.z, n_cols = h2.z, nbp = h2.w;
+      int my_bp_kb = 0x7fffffff, my_bp_n = 0;
+      if (lane < nbp) { my_bp_kb = __ldg(&T->bp_kb[lane]); my_bp_n = __ldg(&T->bp_n[lane]); }
+      int my_tcol = 0x7fffffff, my_width = 0, my_scol = 0;
+      int64_t my_off = 0;
+      if (lane < ncb) {
+        my_off = (int64_t)__ldg(reinterpret_cast<const long long*>(&T->cb[lane].out_off));
+        const int4 w = __ldg(reinterpret_cast<const int4*>(&T->cb[lane].tcol));
+        my_tcol = w.x; my_width = w.y; my_scol = w.z;
+      }
       // the two column halves split the tile's accumulator columns (multiples of 32 each)
-      const int hw = ((T->n_cols + 63) >> 6) << 5;
+      const int hw = ((n_cols + 63) >> 6) << 5;
       const int cbase = half * hw;
       float acc[TC_MAX_COLS / 2];
 #pragma unroll
       for (int i = 0; i < TC_MAX_COLS / 2; i++) acc[i] = 0.f;
       {
         const int nchunks = (total_kb + CH - 1) / CH;
-        int si = 0, left = 0;  // segment holding the chunk's first K block; K blocks of it still ahead
-        int n_first = 0;
-        if (seg_count > 0) { left = p.segs[seg_begin].nk; n_first = p.segs[seg_begin].n_mma; }
         for (int c = 0; c < nchunks; c++, gchunk++) {
           const uint32_t buf = gchunk & 1u;
-          const int n_c = n_first;  // segments are ordered by non-increasing n_mma
-          // advance the walker by CH K blocks
-          int adv = CH;
-          while (adv > 0 && si < seg_count) {
-            if (left > adv) { left -= adv; adv = 0; }
-            else {
-              adv -= left;
-              si++;
-              if (si < seg_count) { left = p.segs[seg_begin + si].nk; n_first = p.segs[seg_begin + si].n_mma; }
-            }
-          }
+          // columns the chunk accumulated = MMA width at its first K block (widths never increase inside a tile)
+          const uint32_t bpm = __ballot_sync(0xffffffffu, my_bp_kb <= c * CH);
+          const int n_c = __shfl_sync(0xffffffffu, my_bp_n, 31 - __clz((int)(bpm | 1u)));
           long long t0 = p.timing ? clock64() : 0;
           mbar_wait(tfull_bar(buf), (gchunk >> 1) & 1u);
           if (p.timing) { const long long t1 = clock64(); tm_wait_tfull += t1 - t0; t0 = t1; }
@@ -551,8 +601,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (g * 32 < hw && tc0 < n_c) {
               float v[32];
               tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC_MAX_COLS + tc0), v);
+              if (tc0 + 32 <= n_c) {
 #pragma unroll
-              for (int j = 0; j < 32; j++) acc[g * 32 + j] += (tc0 + j < n_c) ? v[j] : 0.f;
+                for (int j = 0; j < 32; j++) acc[g * 32 + j] += v[j];
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++) acc[g * 32 + j] += (tc0 + j < n_c) ? v[j] : 0.f;
+              }
             }
           }
           tc_fence_before();
@@ -573,104 +628,121 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       //      global stores / read-modify-writes are sector-complete instead of one row per lane.
       //      Column blocks map accumulator columns to output columns; they start at multiples of 16.
       const int r_lane = lane >> 2, c4 = (lane & 3) * 4;
+      const bool all_rows = m_valid == TC_BM;
 #pragma unroll
       for (int g = 0; g < 4; g++) {
         const int tc0 = cbase + g * 32;
-        if (g * 32 >= hw || tc0 >= T->n_cols) continue;  // warp-uniform
+        if (g * 32 >= hw || tc0 >= n_cols) continue;  // warp-uniform
 #pragma unroll
         for (int hh = 0; hh < 2; hh++) {
           const int c0 = tc0 + hh * 16;  // first accumulator column of this 16-column slab
-          // column block holding the slab (warp-uniform search)
-          int cb_i = -1;
-          for (int b = 0; b < ncb; b++)
-            if (T->cb[b].tcol <= c0 && (cb_i < 0 || T->cb[b].tcol > T->cb[cb_i].tcol)) cb_i = b;
-          if (cb_i < 0) continue;
-          const TcColBlock cb = T->cb[cb_i];
-          if (c0 >= cb.tcol + cb.width) continue;  // padding columns of the block
+          // column block holding the slab: blocks are listed by increasing tcol
+          const uint32_t cbm = __ballot_sync(0xffffffffu, my_tcol <= c0);
+          if (cbm == 0) continue;
+          const int cb_i = 31 - __clz((int)cbm);
+          const int cb_tcol = __shfl_sync(0xffffffffu, my_tcol, cb_i);
+          const int cb_width = __shfl_sync(0xffffffffu, my_width, cb_i);
+          const int64_t cb_off = __shfl_sync(0xffffffffu, my_off, cb_i);
+          if (c0 >= cb_tcol + cb_width) continue;  // padding columns of the block
 #pragma unroll
           for (int k = 0; k < 4; k++)
             *reinterpret_cast<float4*>(st + lane * TC_STAGE_LD + 4 * k) =
                 make_float4(acc[g * 32 + hh * 16 + 4 * k], acc[g * 32 + hh * 16 + 4 * k + 1],
                             acc[g * 32 + hh * 16 + 4 * k + 2], acc[g * 32 + hh * 16 + 4 * k + 3]);
           __syncwarp();
-          const int ocol = c0 + c4 - cb.tcol;             // output column of this lane's 4 values
-          const int nval = min(4, cb.width - ocol);       // valid values (<= 0: none)
+          const int ocol = c0 + c4 - cb_tcol;             // output column of this lane's 4 values
+          float* const obase = p.out + cb_off + (int64_t)(q * 32 + r_lane) * ld_out + ocol;
+          const int64_t ostep = (int64_t)8 * ld_out;     // rows advance by 8 per pass
           float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+          // warp-uniform fast path: whole slab valid, every lane's 4 values 16-byte aligned in the output
+          const bool fast = all_rows && (c0 + 16 <= cb_tcol + cb_width) && ((ld_out & 3) == 0) &&
+                            ((reinterpret_cast<uintptr_t>(p.out + cb_off + (c0 - cb_tcol)) & 15) == 0);
+          if (fast) {
+            float4 v[4];
 #pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const int r = i * 8 + r_lane;
-            const int grow = q * 32 + r;
-            float4 v = *reinterpret_cast<const float4*>(st + r * TC_STAGE_LD + c4);
-            if (grow < m_valid && nval > 0) {
-              float* optr = p.out + cb.out_off + (int64_t)grow * ld_out + ocol;
-              const bool vec = nval == 4 && ((reinterpret_cast<uintptr_t>(optr) & 15) == 0);
-              if (p.epi == EPI_ATOMIC) {
-                if (vec) {
-                  atomicAdd(reinterpret_cast<float4*>(optr), v);
-                } else {
-                  atomicAdd(optr, v.x);
-                  if (nval > 1) atomicAdd(optr + 1, v.y);
-                  if (nval > 2) atomicAdd(optr + 2, v.z);
-                  if (nval > 3) atomicAdd(optr + 3, v.w);
-                }
-              } else if (vec) {
-                if (p.epi == EPI_ACCUM) {
-                  const float4 o = *reinterpret_cast<const float4*>(optr);
-                  v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-                }
-                *reinterpret_cast<float4*>(optr) = v;
-              } else {
-                if (p.epi == EPI_ACCUM) {
-                  v.x += optr[0];
-                  if (nval > 1) v.y += optr[1];
-                  if (nval > 2) v.z += optr[2];
-                  if (nval > 3) v.w += optr[3];
-                }
-                optr[0] = v.x;
-                if (nval > 1) optr[1] = v.y;
-                if (nval > 2) optr[2] = v.z;
-                if (nval > 3) optr[3] = v.w;
+            for (int i = 0; i < 4; i++) v[i] = *reinterpret_cast<const float4*>(st + (i * 8 + r_lane) * TC_STAGE_LD + c4);
+            if (EPI == EPI_ACCUM) {
+              float4 o[4];
+#pragma unroll
+              for (int i = 0; i < 4; i++) o[i] = *reinterpret_cast<const float4*>(obase + i * ostep);
+#pragma unroll
+              for (int i = 0; i < 4; i++) { v[i].x += o[i].x; v[i].y += o[i].y; v[i].z += o[i].z; v[i].w += o[i].w; }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              if (EPI == EPI_ATOMIC) atomicAdd(reinterpret_cast<float4*>(obase + i * ostep), v[i]);
+              else *reinterpret_cast<float4*>(obase + i * ostep) = v[i];
+              if (EPI == EPI_STORE) {
+                s1[0] += v[i].x; s1[1] += v[i].y; s1[2] += v[i].z; s1[3] += v[i].w;
+                s2[0] += v[i].x * v[i].x; s2[1] += v[i].y * v[i].y; s2[2] += v[i].z * v[i].z; s2[3] += v[i].w * v[i].w;
               }
-              // statistics are taken on the GEMM result itself (EPI_STORE launches only)
-              s1[0] += v.x; s1[1] += v.y; s1[2] += v.z; s1[3] += v.w;
-              s2[0] += v.x * v.x; s2[1] += v.y * v.y; s2[2] += v.z * v.z; s2[3] += v.w * v.w;
+            }
+          } else {
+            const int nval = min(4, cb_width - ocol);  // valid values of this lane (<= 0: none)
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              const float4 v4 = *reinterpret_cast<const float4*>(st + (i * 8 + r_lane) * TC_STAGE_LD + c4);
+              const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+              if (q * 32 + i * 8 + r_lane < m_valid) {
+                float* optr = obase + i * ostep;
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                  if (t < nval) {
+                    float x = vv[t];
+                    if (EPI == EPI_ATOMIC) atomicAdd(optr + t, x);
+                    else {
+                      if (EPI == EPI_ACCUM) x += optr[t];
+                      optr[t] = x;
+                    }
+                    s1[t] += x;
+                    s2[t] += x * x;
+                  }
+                }
+              }
             }
           }
-          if (p.stats) {
+          if (EPI == EPI_STORE && p.stats) {
+            // the 8 lanes that share this lane's 4 columns (lane >> 2 = row lane) hold 8 partial sums each
+            // (s1[0..3], s2[0..3]); a halving butterfly leaves each of them with ONE fully reduced value
+            const bool u16 = (lane & 16) != 0, u8 = (lane & 8) != 0, u4 = (lane & 4) != 0;
+            float w4[4], w2[2], w1;
 #pragma unroll
-            for (int t = 0; t < 4; t++) {
-#pragma unroll
-              for (int o = 4; o <= 16; o <<= 1) {
-                s1[t] += __shfl_xor_sync(0xffffffffu, s1[t], o);
-                s2[t] += __shfl_xor_sync(0xffffffffu, s2[t], o);
-              }
+            for (int k = 0; k < 4; k++) {
+              const float keep = u16 ? s2[k] : s1[k], send = u16 ? s1[k] : s2[k];
+              w4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
             }
-            if (lane < 4) {
 #pragma unroll
-              for (int t = 0; t < 4; t++) {
-                s_part[(0 * 4 + q) * TC_MAX_COLS + c0 + c4 + t] = s1[t];
-                s_part[(1 * 4 + q) * TC_MAX_COLS + c0 + c4 + t] = s2[t];
-              }
+            for (int k = 0; k < 2; k++) {
+              const float keep = u8 ? w4[2 + k] : w4[k], send = u8 ? w4[k] : w4[2 + k];
+              w2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
             }
+            {
+              const float keep = u4 ? w2[1] : w2[0], send = u4 ? w2[0] : w2[1];
+              w1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            const int which = (u8 ? 2 : 0) + (u4 ? 1 : 0);  // column inside the lane group's 4; u16 selects s1 / s2
+            s_part[((u16 ? 1 : 0) * 4 + q) * TC_MAX_COLS + c0 + c4 + which] = w1;
           }
           __syncwarp();  // the staging rows are rewritten by the next slab
         }
       }
-      if (p.stats) {
+      if (EPI == EPI_STORE && p.stats) {
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const int t = threadIdx.x - 64;
-        float* srow = p.stats + (size_t)T->stats_row * 2 * p.stats_ld;
+        float* srow = p.stats + (size_t)stats_row * 2 * p.stats_ld;
         for (int b = 0; b < (m_valid > 0 ? ncb : 0); b++) {  // phantom tiles (m_valid == 0) own no statistics row
-          const int c = t - T->cb[b].tcol;
-          if (c >= 0 && c < T->cb[b].width) {
+          const int b_tcol = __shfl_sync(0xffffffffu, my_tcol, b), b_width = __shfl_sync(0xffffffffu, my_width, b);
+          const int b_scol = __shfl_sync(0xffffffffu, my_scol, b);
+          const int c = t - b_tcol;
+          if (c >= 0 && c < b_width) {
             float a1 = 0.f, a2 = 0.f;
 #pragma unroll
             for (int w = 0; w < 4; w++) {
               a1 += s_part[(0 * 4 + w) * TC_MAX_COLS + t];
               a2 += s_part[(1 * 4 + w) * TC_MAX_COLS + t];
             }
-            srow[T->cb[b].stats_col + c] = a1;
-            srow[p.stats_ld + T->cb[b].stats_col + c] = a2;
+            srow[b_scol + c] = a1;
+            srow[p.stats_ld + b_scol + c] = a2;
           }
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");  // s_part is reused by the next tile
@@ -741,6 +813,35 @@ constexpr int TC_DEFAULT_CHUNK_KB = 4;
 
 static thread_local const char* g_tc_timing_tag = nullptr;  // label of the next launch in HYP_TC_TIMING output
 
+// fills n_cols and the MMA-width breakpoints of every tile; checks the limits the kernel relies on
+inline int tc_finalize_tiles(std::vector<TcTile>& tiles, const std::vector<TcSeg>& segs) {
+  static_assert(sizeof(TcSeg) == 48 && sizeof(TcColBlock) == 32 && offsetof(TcTile, bp_kb) == 48 &&
+                    offsetof(TcTile, cb) == 48 + 8 * TC_MAX_BP && offsetof(TcSeg, nk) == 24,
+                "descriptor layouts are read as raw words by the kernel");
+  for (TcTile& t : tiles) {
+    if (t.seg_count > TC_MAX_SEGS) return fail(HYP_E_UNSUPPORTED, "tc gemm: more than 128 segments in one tile");
+    t.n_cols = 0;
+    t.nbp = 0;
+    int kb = 0, last = -1;
+    for (int i = 0; i < t.seg_count; i++) {
+      const TcSeg& sg = segs[t.seg_begin + i];
+      t.n_cols = std::max(t.n_cols, sg.n_mma);
+      if (sg.n_mma != last) {
+        if (last >= 0 && sg.n_mma > last) return fail(HYP_E_INVALID, "tc gemm: segment widths must not increase");
+        if (t.nbp == TC_MAX_BP) return fail(HYP_E_UNSUPPORTED, "tc gemm: too many distinct MMA widths in one tile");
+        t.bp_kb[t.nbp] = kb;
+        t.bp_n[t.nbp] = sg.n_mma;
+        t.nbp++;
+        last = sg.n_mma;
+      }
+      kb += sg.nk;
+    }
+    for (int b = 1; b < t.ncb; b++)
+      if (t.cb[b].tcol <= t.cb[b - 1].tcol) return fail(HYP_E_INVALID, "tc gemm: column blocks must be listed by increasing tcol");
+  }
+  return HYP_OK;
+}
+
 inline int tc_sm_count() {
   static int sms = 0;
   if (!sms) {
@@ -752,8 +853,18 @@ inline int tc_sm_count() {
 }
 
 // CG = 2: tiles 2i, 2i+1 form a pair sharing its segment list (ntiles even); tmB boxes hold bn/2 rows
+template <bool MN, int CG, int EPI>
+inline int launch_tc_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, int ntiles, cudaStream_t st);
+
 template <bool MN, int CG>
 inline int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, int ntiles, cudaStream_t st) {
+  if (p.epi == EPI_STORE) return launch_tc_epi<MN, CG, EPI_STORE>(tmA, tmB, p, ntiles, st);
+  if (p.epi == EPI_ACCUM) return launch_tc_epi<MN, CG, EPI_ACCUM>(tmA, tmB, p, ntiles, st);
+  return launch_tc_epi<MN, CG, EPI_ATOMIC>(tmA, tmB, p, ntiles, st);
+}
+
+template <bool MN, int CG, int EPI>
+inline int launch_tc_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, int ntiles, cudaStream_t st) {
   if (ntiles <= 0) return HYP_OK;
   if (ntiles % CG) return fail(HYP_E_INVALID, "tc gemm: tile count is not a multiple of the CTA group size");
   if (p.b_rows % (8 * CG)) return fail(HYP_E_INVALID, "tc gemm: B rows must be a multiple of 8 per CTA");
@@ -764,7 +875,7 @@ inline int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p,
   const size_t smem = tc_smem_bytes(p.b_rows / CG, p.stages);
   static bool attr_set = false;
   if (!attr_set) {
-    HYP_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    HYP_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MN, CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     attr_set = true;
   }
   const int groups = std::min(ntiles / CG, tc_sm_count() / CG);
@@ -787,7 +898,7 @@ inline int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p,
     HYP_CUDA(cudaMemsetAsync(tbuf, 0, (size_t)groups * CG * 8 * sizeof(unsigned long long), st));
     p.timing = tbuf;
   }
-  HYP_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<MN, CG>, tmA, tmB, p));
+  HYP_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<MN, CG, EPI>, tmA, tmB, p));
   HYP_LAUNCHED();
   if (timing_on) {
     std::vector<unsigned long long> h((size_t)groups * CG * 8);

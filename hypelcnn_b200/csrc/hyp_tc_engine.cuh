@@ -634,10 +634,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
       }
     }
   }
-  for (TcTile& t : pb.tiles) {
-    t.n_cols = 0;
-    for (int i = 0; i < t.seg_count; i++) t.n_cols = std::max(t.n_cols, pb.segs[t.seg_begin + i].n_mma);
-  }
+  if ((rc = tc_finalize_tiles(pb.tiles, pb.segs))) return rc;
   // upload
   if (pb.segs.size() > S.segs_cap) {
     if (S.segs_dev) cudaFree(S.segs_dev);
