@@ -255,6 +255,11 @@ static TcTile blank_tile() {
   memset(&t, 0, sizeof(t));
   return t;
 }
+static void schedule_tiles(std::vector<TcTile>& tiles, size_t begin, const std::vector<TcSeg>& segs, int cg, bool windowed);
+static void finish_launch(PlanBuf& pb, TcLaunch& l) {
+  schedule_tiles(pb.tiles, (size_t)l.tile0, pb.segs, l.cg, /*windowed=*/!l.mn);
+  l.ntiles = (int)pb.tiles.size() - l.tile0;
+}
 
 // K-major launches run as CTA pairs (cta_group::2): consecutive tiles (2i, 2i+1) must share their
 // segment list.  A run of tiles that differ only in their row block is closed with a phantom
@@ -268,6 +273,64 @@ static void close_pair_run(std::vector<TcTile>& tiles, size_t run_begin, int oob
   tiles.push_back(t);
 }
 
+
+// ---- static tile schedule ------------------------------------------------------------------------
+// The GEMM kernel is persistent: CTA group g walks tile slots g, g + G, g + 2G, ...  Tiles of one
+// launch differ in cost (taps per position, ring-dependent widths, positions per wgrad chunk), so
+// the launch's tile array is re-laid-out here: slot i * G + g holds the i-th unit of group g.
+//   windowed = true  (K-major level launches): units keep their locality order (batch-pair major: a
+//       wave of CTAs shares its A rows through L2); inside every window of 2G units the costs are
+//       sorted and dealt out in a snake (heaviest with lightest), so each group gets 2 units per window.
+//   windowed = false (wgrad): plain LPT, longest unit first onto the least loaded group; groups that
+//       end up with fewer units get empty tiles.
+static double tile_cost(const TcTile& t, const std::vector<TcSeg>& segs) {
+  double c = 1500.0;  // epilogue
+  for (int i = 0; i < t.seg_count; i++) c += (double)segs[t.seg_begin + i].nk * (256.0 + segs[t.seg_begin + i].n_mma);
+  return c;
+}
+static void schedule_tiles(std::vector<TcTile>& tiles, size_t begin, const std::vector<TcSeg>& segs, int cg, bool windowed) {
+  const int units = (int)((tiles.size() - begin) / cg);
+  const int G = tc_sm_count() / cg;
+  if (units <= G) return;
+  std::vector<std::pair<double, int>> cost(units);
+  bool uniform = true;
+  for (int u = 0; u < units; u++) {
+    cost[u] = {tile_cost(tiles[begin + (size_t)u * cg], segs), u};
+    uniform = uniform && cost[u].first == cost[0].first;
+  }
+  if (uniform) return;
+  std::vector<std::vector<int>> lists(G);
+  if (windowed) {
+    for (int w0 = 0; w0 < units; w0 += 2 * G) {
+      const int w1 = std::min(units, w0 + 2 * G);
+      std::stable_sort(cost.begin() + w0, cost.begin() + w1,
+                       [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first > b.first; });
+      for (int j = w0; j < w1; j++) {
+        const int k = j - w0;
+        lists[k < G ? k : 2 * G - 1 - k].push_back(cost[j].second);
+      }
+    }
+  } else {
+    std::stable_sort(cost.begin(), cost.end(),
+                     [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first > b.first; });
+    std::vector<double> load(G, 0.0);
+    for (const auto& cu : cost) {
+      int best = 0;
+      for (int g = 1; g < G; g++)
+        if (load[g] < load[best]) best = g;
+      load[best] += cu.first;
+      lists[best].push_back(cu.second);
+    }
+  }
+  size_t depth = 0;
+  for (const auto& l : lists) depth = std::max(depth, l.size());
+  std::vector<TcTile> out(depth * G * cg, blank_tile());
+  for (int g = 0; g < G; g++)
+    for (size_t i = 0; i < lists[g].size(); i++)
+      for (int r = 0; r < cg; r++) out[(i * G + g) * cg + r] = tiles[begin + (size_t)lists[g][i] * cg + r];
+  tiles.resize(begin);
+  tiles.insert(tiles.end(), out.begin(), out.end());
+}
 static int map4(CUtensorMap* mp, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2,
                 uint64_t plane, uint32_t b0, uint32_t b1, bool mn) {
   const uint64_t dims[4] = {d0, d1, d2, 2};
@@ -338,7 +401,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
           }
           close_pair_run(pb.tiles, run, nrt * 128);
         }
-      T.fwd.ntiles = (int)pb.tiles.size() - T.fwd.tile0;
+      finish_launch(pb, T.fwd);
       T.stats_rows = nrt;
       // ---------------- dgrad ----------------
       if (need_dgrad) {
@@ -367,7 +430,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
             }
             close_pair_run(pb.tiles, run, nrt * 128);
           }
-        T.dg.ntiles = (int)pb.tiles.size() - T.dg.tile0;
+        finish_launch(pb, T.dg);
       }
       // ---------------- wgrad ----------------
       {
@@ -396,7 +459,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
               pb.segs.push_back(s);
               pb.tiles.push_back(t);
             }
-        T.wg.ntiles = (int)pb.tiles.size() - T.wg.tile0;
+        finish_launch(pb, T.wg);
       }
     } else if (T.kind == 1) {
       const int Cin = tin.C, PP = tin.PP, R = T.R, fpad = T.fpad, f = T.f;
@@ -453,7 +516,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
           }
           close_pair_run(pb.tiles, run, nbt * 128);
         }
-      T.fwd.ntiles = (int)pb.tiles.size() - T.fwd.tile0;
+      finish_launch(pb, T.fwd);
       T.stats_rows = PP * nbt;
       // ---------------- dgrad ----------------
       if (need_dgrad) {
@@ -498,7 +561,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
             }
             close_pair_run(pb.tiles, run, nbt * 128);
           }
-        T.dg.ntiles = (int)pb.tiles.size() - T.dg.tile0;
+        finish_launch(pb, T.dg);
       }
       // ---------------- wgrad ----------------
       {
@@ -509,7 +572,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
         const int nkb = (int)cdiv(B, 32);
         int64_t pairs = 0;
         for (auto& tp : taps) pairs += (int64_t)(P - std::abs(tp.first)) * (P - std::abs(tp.second));
-        const int pc = (int)std::max<int64_t>(1, cdiv(pairs * mt * ngroups, 296));  // positions per CTA
+        const int pc = (int)std::max<int64_t>(1, cdiv(pairs * mt * ngroups, 4 * tc_sm_count()));  // positions per tile: ~4 tiles per CTA for the LPT schedule
         for (auto& tp : taps) {
           const int dy = tp.first, dx = tp.second, ring = std::max(std::abs(dy), std::abs(dx));
           std::vector<int> ps;  // output positions whose tap source is inside the patch
@@ -547,7 +610,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
               }
           }
         }
-        T.wg.ntiles = (int)pb.tiles.size() - T.wg.tile0;
+        finish_launch(pb, T.wg);
       }
     } else {
       const int Ct = tin.C, PP = tin.PP, Cout = L.Cout;
@@ -581,7 +644,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
           }
           close_pair_run(pb.tiles, run, nbt * 128);
         }
-      T.fwd.ntiles = (int)pb.tiles.size() - T.fwd.tile0;
+      finish_launch(pb, T.fwd);
       T.stats_rows = nbt;
       // ---------------- dgrad ----------------
       if (need_dgrad) {
@@ -609,7 +672,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
             }
             close_pair_run(pb.tiles, run, nbt * 128);
           }
-        T.dg.ntiles = (int)pb.tiles.size() - T.dg.tile0;
+        finish_launch(pb, T.dg);
       }
       // ---------------- wgrad ----------------
       {
@@ -630,7 +693,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
             pb.segs.push_back(s);
             pb.tiles.push_back(t);
           }
-        T.wg.ntiles = (int)pb.tiles.size() - T.wg.tile0;
+        finish_launch(pb, T.wg);
       }
     }
   }
