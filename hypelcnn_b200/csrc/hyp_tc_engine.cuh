@@ -76,6 +76,27 @@ static float* tc_plane0(const hyp_model& m, int t) {
 static float* tc_plane1(const hyp_model& m, int t) { return tc_plane0(m, t) + m.tc->tt[t].plane_elems; }
 static float* tc_grad(const hyp_model& m, int t) { return reinterpret_cast<float*>(m.ws + m.tc->tt[t].g_off); }
 
+// launch shape of the vectorised elementwise kernels: TX column groups of 4 channels per block row,
+// 256 / TX row lanes, `rblocks` row blocks of `rpb` rows
+struct EwGrid { int TX, gx, rblocks, rpb; };
+static inline EwGrid ew_grid2(int cols, int64_t rows) {
+  EwGrid g;
+  const int c4 = (int)cdiv(cols, 4);
+  g.TX = c4 > 16 ? 32 : (c4 > 8 ? 16 : 8);
+  g.gx = (int)cdiv(c4, g.TX);
+  const int TY = 256 / g.TX;
+  int64_t rb = std::max<int64_t>(1, std::min<int64_t>(cdiv(rows, 4 * TY), cdiv(tc_sm_count() * 8, g.gx)));
+  g.rpb = (int)cdiv(rows, rb);
+  g.rblocks = (int)cdiv(rows, g.rpb);
+  return g;
+}
+#define TC_EW_DISPATCH(G, KERNEL, ...)                                                             \
+  do {                                                                                             \
+    if ((G).TX == 32) KERNEL<32><<<dim3((G).gx, (G).rblocks), 256, 0, st>>>(__VA_ARGS__);          \
+    else if ((G).TX == 16) KERNEL<16><<<dim3((G).gx, (G).rblocks), 256, 0, st>>>(__VA_ARGS__);     \
+    else KERNEL<8><<<dim3((G).gx, (G).rblocks), 256, 0, st>>>(__VA_ARGS__);                        \
+  } while (0)
+
 // ---- static layout: workspace offsets, packed-weight offsets, pack jobs ------------------------
 static int tc_layout(hyp_model& m) {
   m.tc = new TcState();
@@ -203,11 +224,7 @@ static int tc_layout(hyp_model& m) {
     }
     gz_max = std::max(gz_max, rows_out * (size_t)T.Gp);
     part_max = std::max(part_max, (size_t)T.stats_rows * 2 * L.Cout);
-    {
-      const int64_t cblocks = cdiv(L.Cout, 32);
-      const int64_t rblocks = std::max<int64_t>(1, std::min<int64_t>(cdiv((int64_t)rows_out, 64), cdiv(148 * 8, cblocks)));
-      bpart_max = std::max(bpart_max, (size_t)(rblocks + 1) * 2 * L.Cout);
-    }
+    bpart_max = std::max(bpart_max, (size_t)(ew_grid2(L.Cout, (int64_t)rows_out).rblocks + 1) * 2 * L.Cout);
   }
   S.gz_plane_elems = align_up(gz_max, 64);
   S.gz_off = take(2 * S.gz_plane_elems * sizeof(float));
@@ -777,7 +794,7 @@ static int tc_forward(hyp_model& m, const float* x, int64_t B, bool training, bo
     float* rstd = reinterpret_cast<float*>(m.ws + T.rstd_off);
     if (training) {
       TC_PROF("tc_bn_finalize_kernel", 8.0 * T.stats_rows * L.Cout,
-              (tc_bn_finalize_kernel<<<(unsigned)cdiv(L.Cout, 32), dim3(32, 32), 0, st>>>(
+              (tc_bn_finalize8_kernel<<<(unsigned)cdiv(L.Cout, 8), 256, 0, st>>>(
                   part, T.stats_rows, L.Cout, L.Cout, (double)rows, m.d.bn_eps, m.d.bn_decay, m.state + L.mm_off,
                   m.state + L.mm_off + L.Cout, mean, rstd, update_moving ? 1 : 0)));
     } else {
@@ -859,24 +876,47 @@ static int tc_backward(hyp_model& m, const uint8_t* labels, int64_t B, float* lo
     p.s1 = s1; p.s2 = s2; p.gz_hi = gz0; p.gz_lo = gz1; p.ldgz = T.Gp;
     p.gcols = T.kind == 1 ? T.Gp : L.Cout;
     p.fpad = T.kind == 1 ? T.fpad : 0; p.f = T.f; p.R = T.R;
-    const int cblocks = (int)cdiv(L.Cout, 32);
-    int rblocks = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(rows, 64), cdiv(148 * 8, cblocks)));
-    const int rpb = (int)cdiv(rows, rblocks);
-    rblocks = (int)cdiv(rows, rpb);
-    TC_PROF("tc_bn_bwd_reduce_kernel", 8.0 * rows * L.Cout,
-            (tc_bn_bwd_reduce_kernel<<<dim3(cblocks, rblocks), 256, 0, st>>>(p, rpb)));
-    tc_bn_bwd_finalize_kernel<<<(unsigned)cdiv(L.Cout, 32), dim3(32, 32), 0, st>>>(bpart, rblocks, L.Cout, (double)rows, s1,
-                                                                                   s2, m.grads + L.beta_off);
+    const EwGrid gr = ew_grid2(L.Cout, rows);
+    TC_PROF("tc_bn_bwd_reduce_kernel", 8.0 * rows * L.Cout, TC_EW_DISPATCH(gr, tc_bn_bwd_reduce_v4_kernel, p, gr.rpb));
+    tc_bn_bwd_finalize8_kernel<<<(unsigned)cdiv(L.Cout, 8), 256, 0, st>>>(bpart, gr.rblocks, L.Cout, (double)rows, s1, s2,
+                                                                         m.grads + L.beta_off);
     HYP_LAUNCHED();
-    TC_PROF("tc_bn_bwd_apply_kernel", 4.0 * rows * (2.0 * L.Cout + 2.0 * p.gcols),
-            (tc_bn_bwd_apply_kernel<<<tc_grid(rows * p.gcols), 256, 0, st>>>(p)));
+    if (p.fpad == 0 || (p.f % 4 == 0 && p.fpad % 4 == 0)) {
+      const EwGrid ga = ew_grid2(p.gcols, rows);
+      TC_PROF("tc_bn_bwd_apply_kernel", 4.0 * rows * (2.0 * L.Cout + 2.0 * p.gcols),
+              TC_EW_DISPATCH(ga, tc_bn_bwd_apply_v4_kernel, p, ga.rpb));
+    } else {  // slot widths that break float4 alignment: scalar form
+      TC_PROF("tc_bn_bwd_apply_kernel", 4.0 * rows * (2.0 * L.Cout + 2.0 * p.gcols),
+              (tc_bn_bwd_apply_kernel<<<tc_grid(rows * p.gcols), 256, 0, st>>>(p)));
+    }
     for (const Resid& r : L.res) {
       const Tensor& src = m.tensors[r.src];
       if (!src.needs_grad) continue;
-      TC_PROF("tc_resid_bwd_kernel", 4.0 * rows * (L.Cout + 2.0 * src.C),
-              (tc_resid_bwd_kernel<<<tc_grid(rows * src.C), 256, 0, st>>>(p.gout, tout.Cp, tc_grad(m, r.src),
-                                                                          S.tt[r.src].Cp, src.C, r.lo, r.hi, rows,
-                                                                          ginit[r.src])));
+      const EwGrid gs = ew_grid2(src.C, rows);
+      const double bytes = 4.0 * rows * (L.Cout + (ginit[r.src] ? 2.0 : 1.0) * src.C);
+      if (r.identity) {
+        TC_PROF("tc_resid_bwd_kernel", bytes,
+                (gs.TX == 32 ? tc_resid_bwd_v4_kernel<32, 0><<<dim3(gs.gx, gs.rblocks), 256, 0, st>>>(
+                                   p.gout, tout.Cp, tc_grad(m, r.src), S.tt[r.src].Cp, src.C, nullptr, nullptr, rows,
+                                   ginit[r.src], gs.rpb)
+                 : gs.TX == 16 ? tc_resid_bwd_v4_kernel<16, 0><<<dim3(gs.gx, gs.rblocks), 256, 0, st>>>(
+                                     p.gout, tout.Cp, tc_grad(m, r.src), S.tt[r.src].Cp, src.C, nullptr, nullptr, rows,
+                                     ginit[r.src], gs.rpb)
+                               : tc_resid_bwd_v4_kernel<8, 0><<<dim3(gs.gx, gs.rblocks), 256, 0, st>>>(
+                                     p.gout, tout.Cp, tc_grad(m, r.src), S.tt[r.src].Cp, src.C, nullptr, nullptr, rows,
+                                     ginit[r.src], gs.rpb)));
+      } else {
+        TC_PROF("tc_resid_bwd_kernel", bytes,
+                (gs.TX == 32 ? tc_resid_bwd_v4_kernel<32, 1><<<dim3(gs.gx, gs.rblocks), 256, 0, st>>>(
+                                   p.gout, tout.Cp, tc_grad(m, r.src), S.tt[r.src].Cp, src.C, r.lo, r.hi, rows, ginit[r.src],
+                                   gs.rpb)
+                 : gs.TX == 16 ? tc_resid_bwd_v4_kernel<16, 1><<<dim3(gs.gx, gs.rblocks), 256, 0, st>>>(
+                                     p.gout, tout.Cp, tc_grad(m, r.src), S.tt[r.src].Cp, src.C, r.lo, r.hi, rows,
+                                     ginit[r.src], gs.rpb)
+                               : tc_resid_bwd_v4_kernel<8, 1><<<dim3(gs.gx, gs.rblocks), 256, 0, st>>>(
+                                     p.gout, tout.Cp, tc_grad(m, r.src), S.tt[r.src].Cp, src.C, r.lo, r.hi, rows,
+                                     ginit[r.src], gs.rpb)));
+      }
       ginit[r.src] = 1;
     }
     int rc = tc_run(m, T.wg, m.grads, nullptr, 0, EPI_ATOMIC, "tc_gemm_kernel/wgrad", layer_flops(L, B), st, L.scope.c_str());

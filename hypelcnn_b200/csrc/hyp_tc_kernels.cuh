@@ -289,6 +289,267 @@ __global__ void tc_resid_bwd_kernel(const float* __restrict__ gout, int ldg, flo
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Vectorised forms of the three backward passes above.  A block is TX column groups (4 channels,
+// one float4 each) x TY = 256 / TX row lanes; every thread walks its rows with 4 independent
+// loads in flight, so a warp reads TX * 16 contiguous bytes of several rows per step and there
+// is no per-element index division.  Rows are 16-byte aligned (ld % 4 == 0); the channel tail
+// (C % 4 != 0) is masked per element.
+struct Gy4 { float g[4], zh[4]; };
+__device__ __forceinline__ Gy4 tc_bn_gy4(const TcBnBwdArgs& p, int64_t m, int c0, const float4 gv, const float4 zv,
+                                         const float (&mean)[4], const float (&rstd)[4], const float (&beta)[4]) {
+  Gy4 r;
+  const float g_in[4] = {gv.x, gv.y, gv.z, gv.w}, z_in[4] = {zv.x, zv.y, zv.z, zv.w};
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const float zhat = (z_in[k] - mean[k]) * rstd[k];
+    const float y = zhat + beta[k];
+    float g = g_in[k];
+    if (p.keep < 1.f) g = (philox_uniform(p.seed, p.stream_id, (uint64_t)(m * p.C + c0 + k)) < p.keep) ? g / p.keep : 0.f;
+    if (p.act == ACT_LRELU) {
+      g = (y > 0.f) ? g : g * p.alpha;
+    } else if (p.act == ACT_SIGMOID) {
+      const float sg = 1.f / (1.f + __expf(-y));
+      g = g * sg * (1.f - sg);
+    }
+    r.g[k] = g;
+    r.zh[k] = zhat;
+  }
+  return r;
+}
+__device__ __forceinline__ void tc_load_ch4(const float* __restrict__ src, int c0, int C, float (&v)[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) v[k] = (c0 + k < C) ? src[c0 + k] : 0.f;
+}
+
+template <int TX>
+__global__ void __launch_bounds__(256) tc_bn_bwd_reduce_v4_kernel(const TcBnBwdArgs p, int rows_per_block) {
+  constexpr int TY = 256 / TX;
+  __shared__ float sh[2][TY][TX * 4 + 4];
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  const int c0 = (blockIdx.x * TX + tx) * 4;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = min((int64_t)p.rows, r0 + rows_per_block);
+  float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c0 < p.C) {
+    float mean[4], rstd[4], beta[4];
+    tc_load_ch4(p.mean, c0, p.C, mean);
+    tc_load_ch4(p.rstd, c0, p.C, rstd);
+    tc_load_ch4(p.beta, c0, p.C, beta);
+    for (int64_t r = r0 + ty; r < r1; r += 4 * TY) {
+      float4 gv[4], zv[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int64_t rr = r + u * TY;
+        if (rr < r1) {
+          gv[u] = *reinterpret_cast<const float4*>(p.gout + rr * p.ldg + c0);
+          zv[u] = *reinterpret_cast<const float4*>(p.z + rr * p.ldz + c0);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int64_t rr = r + u * TY;
+        if (rr < r1) {
+          const Gy4 y = tc_bn_gy4(p, rr, c0, gv[u], zv[u], mean, rstd, beta);
+#pragma unroll
+          for (int k = 0; k < 4; k++) { a1[k] += y.g[k]; a2[k] += y.g[k] * y.zh[k]; }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) { sh[0][ty][tx * 4 + k] = a1[k]; sh[1][ty][tx * 4 + k] = a2[k]; }
+  __syncthreads();
+  // TX * 4 columns x 2 sums, reduced over the TY row lanes by the first TX * 8 threads
+  for (int o = threadIdx.x; o < TX * 8; o += 256) {
+    const int which = o / (TX * 4), col = o % (TX * 4);
+    const int c = blockIdx.x * TX * 4 + col;
+    if (c < p.C) {
+      float a = 0.f;
+#pragma unroll
+      for (int i = 0; i < TY; i++) a += sh[which][i][col];
+      p.part[((size_t)blockIdx.y * 2 + which) * p.C + c] = a;
+    }
+  }
+}
+
+// gz = rstd * (g_y - mean(g_y) - zhat * mean(g_y * zhat)) -> (value, lo) planes.  Level layers (fpad > 0,
+// f % 4 == 0) write slot-ordered columns: gz column j = slot * fpad + n holds channel (R-1-slot) * f + n.
+template <int TX>
+__global__ void __launch_bounds__(256) tc_bn_bwd_apply_v4_kernel(const TcBnBwdArgs p, int rows_per_block) {
+  constexpr int TY = 256 / TX;
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  const int j0 = (blockIdx.x * TX + tx) * 4;  // first gz column of this thread
+  if (j0 >= p.gcols) return;
+  int c0 = j0;
+  bool valid = j0 < p.C;
+  if (p.fpad) {
+    const int slot = j0 / p.fpad, n = j0 - slot * p.fpad;
+    valid = n < p.f && slot < p.R;
+    c0 = (p.R - 1 - slot) * p.f + n;
+  }
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = min((int64_t)p.rows, r0 + rows_per_block);
+  if (!valid) {  // padding columns of the slot layout: zeros
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t r = r0 + ty; r < r1; r += TY) {
+      *reinterpret_cast<float4*>(p.gz_hi + r * p.ldgz + j0) = zero;
+      *reinterpret_cast<float4*>(p.gz_lo + r * p.ldgz + j0) = zero;
+    }
+    return;
+  }
+  float mean[4], rstd[4], beta[4], s1[4], s2[4];
+  tc_load_ch4(p.mean, c0, p.C, mean);
+  tc_load_ch4(p.rstd, c0, p.C, rstd);
+  tc_load_ch4(p.beta, c0, p.C, beta);
+  tc_load_ch4(p.s1, c0, p.C, s1);
+  tc_load_ch4(p.s2, c0, p.C, s2);
+  const bool c_aligned = (c0 & 3) == 0;  // level slots with f % 4 == 0 keep float4 alignment of the source row
+  for (int64_t r = r0 + ty; r < r1; r += 4 * TY) {
+    float4 gv[4], zv[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int64_t rr = r + u * TY;
+      if (rr < r1) {
+        if (c_aligned) {
+          gv[u] = *reinterpret_cast<const float4*>(p.gout + rr * p.ldg + c0);
+          zv[u] = *reinterpret_cast<const float4*>(p.z + rr * p.ldz + c0);
+        } else {
+          const float* gp = p.gout + rr * p.ldg + c0;
+          const float* zp = p.z + rr * p.ldz + c0;
+          gv[u] = make_float4(gp[0], gp[1], gp[2], gp[3]);
+          zv[u] = make_float4(zp[0], zp[1], zp[2], zp[3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int64_t rr = r + u * TY;
+      if (rr < r1) {
+        const Gy4 y = tc_bn_gy4(p, rr, c0, gv[u], zv[u], mean, rstd, beta);
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = (c0 + k < p.C) ? rstd[k] * (y.g[k] - s1[k] - y.zh[k] * s2[k]) : 0.f;
+        *reinterpret_cast<float4*>(p.gz_hi + rr * p.ldgz + j0) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(p.gz_lo + rr * p.ldgz + j0) =
+            make_float4(tf32_lo(v[0]), tf32_lo(v[1]), tf32_lo(v[2]), tf32_lo(v[3]));
+      }
+    }
+  }
+}
+
+// residual backward, 4 source channels per thread.  MODE 0: identity (gsrc += gout); MODE 1: generic
+// contiguous ranges [lo[c], hi[c]) of the consumer's channels.
+template <int TX, int MODE>
+__global__ void __launch_bounds__(256) tc_resid_bwd_v4_kernel(const float* __restrict__ gout, int ldg, float* __restrict__ gsrc,
+                                                              int lds, int Csrc, const int* __restrict__ lo,
+                                                              const int* __restrict__ hi, int64_t rows, int accumulate,
+                                                              int rows_per_block) {
+  constexpr int TY = 256 / TX;
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  const int c0 = (blockIdx.x * TX + tx) * 4;
+  if (c0 >= Csrc) return;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = min(rows, r0 + rows_per_block);
+  int jl[4] = {0, 0, 0, 0}, jh[4] = {0, 0, 0, 0};
+  if (MODE == 1) {
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (c0 + k < Csrc) { jl[k] = lo[c0 + k]; jh[k] = hi[c0 + k]; }
+  }
+  for (int64_t r = r0 + ty; r < r1; r += 2 * TY) {
+    float4 acc[2], old[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int64_t rr = r + u * TY;
+      if (rr < r1) {
+        if (MODE == 0) {
+          acc[u] = *reinterpret_cast<const float4*>(gout + rr * ldg + c0);
+        } else {
+          const float* gp = gout + rr * ldg;
+          float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            for (int j = jl[k]; j < jh[k]; j++) v[k] += gp[j];
+          acc[u] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        if (accumulate) old[u] = *reinterpret_cast<const float4*>(gsrc + rr * lds + c0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int64_t rr = r + u * TY;
+      if (rr < r1) {
+        float4 v = acc[u];
+        if (accumulate) { v.x += old[u].x; v.y += old[u].y; v.z += old[u].z; v.w += old[u].w; }
+        *reinterpret_cast<float4*>(gsrc + rr * lds + c0) = v;
+      }
+    }
+  }
+}
+
+// per-row-block partial sums [nrows][2][ld] -> mean / rstd / moving statistics.  8 channels per block
+// (one 32-byte sector per partial row), 32 row lanes.
+__global__ void __launch_bounds__(256) tc_bn_finalize8_kernel(const float* __restrict__ part, int nrows, int ld, int C,
+                                                              double count, float eps, float decay,
+                                                              float* __restrict__ moving_mean, float* __restrict__ moving_var,
+                                                              float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                              int update_moving) {
+  __shared__ double sh1[32][9], sh2[32][9];
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + tx;
+  double a1 = 0, a2 = 0;
+  if (c < C) {
+    for (int r = ty; r < nrows; r += 32) {
+      a1 += (double)part[((size_t)r * 2 + 0) * ld + c];
+      a2 += (double)part[((size_t)r * 2 + 1) * ld + c];
+    }
+  }
+  sh1[ty][tx] = a1;
+  sh2[ty][tx] = a2;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    for (int i = 1; i < 32; i++) { a1 += sh1[i][tx]; a2 += sh2[i][tx]; }
+    const double mean = a1 / count;
+    double var = a2 / count - mean * mean;
+    if (var < 0) var = 0;
+    const float meanf = (float)mean, varf = (float)var;
+    mean_out[c] = meanf;
+    const float x = varf + eps;
+    float r = rsqrtf(x);
+    r = r * (1.5f - 0.5f * x * r * r);
+    rstd_out[c] = r;
+    if (update_moving) {
+      const double unbiased = var * (count / fmax(count - 1.0, 1.0));
+      moving_mean[c] = moving_mean[c] * decay + meanf * (1.f - decay);
+      moving_var[c] = moving_var[c] * decay + (float)unbiased * (1.f - decay);
+    }
+  }
+}
+__global__ void __launch_bounds__(256) tc_bn_bwd_finalize8_kernel(const float* __restrict__ part, int nblocks, int C, double rows,
+                                                                  float* __restrict__ s1, float* __restrict__ s2,
+                                                                  float* __restrict__ gbeta) {
+  __shared__ double sh1[32][9], sh2[32][9];
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + tx;
+  double a1 = 0, a2 = 0;
+  if (c < C) {
+    for (int r = ty; r < nblocks; r += 32) {
+      a1 += (double)part[((size_t)r * 2 + 0) * C + c];
+      a2 += (double)part[((size_t)r * 2 + 1) * C + c];
+    }
+  }
+  sh1[ty][tx] = a1;
+  sh2[ty][tx] = a2;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    for (int i = 1; i < 32; i++) { a1 += sh1[i][tx]; a2 += sh2[i][tx]; }
+    s1[c] = (float)(a1 / rows);
+    s2[c] = (float)(a2 / rows);
+    gbeta[c] = (float)a1;
+  }
+}
+
 // softmax cross-entropy per row (one warp per row) on padded logits + gradient
 __global__ void tc_ce_loss_kernel(const float* __restrict__ logits, int ld, const uint8_t* __restrict__ labels,
                                   int64_t B, int classes, float* __restrict__ ce_out, float* __restrict__ glogits,
