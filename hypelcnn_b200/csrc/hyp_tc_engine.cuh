@@ -32,6 +32,7 @@ struct TcLaunch {
   int b_rows = 0, bn = 0;
   bool mn = false;
   int cg = 1;  // CTA group size: 2 = tiles come in pairs (2i, 2i+1) that share their B operand
+  bool windowed = false;  // schedule: keep the tile order's locality (snake inside windows) instead of global LPT
 };
 
 struct TcLayer {
@@ -274,7 +275,7 @@ static TcTile blank_tile() {
 }
 static void schedule_tiles(std::vector<TcTile>& tiles, size_t begin, const std::vector<TcSeg>& segs, int cg, bool windowed);
 static void finish_launch(PlanBuf& pb, TcLaunch& l) {
-  schedule_tiles(pb.tiles, (size_t)l.tile0, pb.segs, l.cg, /*windowed=*/!l.mn);
+  schedule_tiles(pb.tiles, (size_t)l.tile0, pb.segs, l.cg, l.windowed || !l.mn);
   l.ntiles = (int)pb.tiles.size() - l.tile0;
 }
 
@@ -457,11 +458,13 @@ static int tc_plan(hyp_model& m, int64_t B) {
         if ((rc = map4(&T.wg.tmB, gz0, Cout, rows_out, 1, T.Gp, (uint64_t)rows_out * T.Gp, S.gz_plane_elems, 32, 32, true))) return rc;
         T.wg.mn = true; T.wg.bn = 32; T.wg.b_rows = 0; T.wg.tile0 = (int)pb.tiles.size();
         const int kblocks = (int)cdiv(rows_out, 32);
-        int ksplit = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(296, mt * ntn), std::max(1, kblocks / 4)));
+        int ksplit = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(2 * tc_sm_count(), mt * ntn), std::max(1, kblocks / 4)));
         const int kb_per = (int)cdiv(kblocks, ksplit);
-        for (int im = 0; im < mt; im++)
-          for (int j = 0; j < ntn; j++)
-            for (int kb0 = 0; kb0 < kblocks; kb0 += kb_per) {
+        // K piece outermost: the (im, j) tiles of one row range run in the same wave and share their A / gz rows
+        // through L2, so every activation and gradient row crosses HBM once
+        for (int kb0 = 0; kb0 < kblocks; kb0 += kb_per)
+          for (int im = 0; im < mt; im++)
+            for (int j = 0; j < ntn; j++) {
               const int width = std::min(nw, Cout - j * nw);
               TcSeg s{};
               s.a0 = im * 128; s.a1 = kb0 * 32; s.b0 = j * nw; s.b1 = kb0 * 32;
@@ -589,44 +592,58 @@ static int tc_plan(hyp_model& m, int64_t B) {
         const int nkb = (int)cdiv(B, 32);
         int64_t pairs = 0;
         for (auto& tp : taps) pairs += (int64_t)(P - std::abs(tp.first)) * (P - std::abs(tp.second));
-        const int pc = (int)std::max<int64_t>(1, cdiv(pairs * mt * ngroups, 4 * tc_sm_count()));  // positions per tile: ~4 tiles per CTA for the LPT schedule
-        for (auto& tp : taps) {
-          const int dy = tp.first, dx = tp.second, ring = std::max(std::abs(dy), std::abs(dx));
-          std::vector<int> ps;  // output positions whose tap source is inside the patch
-          for (int p = 0; p < PP; p++) {
-            const int ph = p / P, pw = p % P;
-            if (ph + dy >= 0 && ph + dy < P && pw + dx >= 0 && pw + dx < P) ps.push_back(p);
-          }
-          for (int g = 0; g < ngroups; g++) {
-            const int s0 = g * spg, s1 = std::min(std::min(R, s0 + spg), R - ring);
-            if (s1 <= s0) continue;
-            const int ncols = (s1 - s0) * fpad;
-            for (int im = 0; im < mt; im++)
-              for (size_t c0 = 0; c0 < ps.size(); c0 += pc) {
-                TcTile t = blank_tile();
-                t.seg_begin = (int)pb.segs.size();
-                for (size_t ci = c0; ci < std::min(ps.size(), c0 + (size_t)pc); ci++) {
-                  TcSeg s{};
-                  s.a0 = im * 128; s.a2 = ps[ci] + dy * P + dx; s.b0 = s0 * fpad; s.b2 = ps[ci];
-                  s.nk = nkb; s.n_mma = r16(ncols); s.nb = (int)cdiv(s.n_mma, 32);
-                  T.wg.b_rows = std::max(T.wg.b_rows, s.nb * 32);
-                  t.total_kb += s.nk;
-                  pb.segs.push_back(s);
+        // Batch slices: every (tap, position) pair re-reads a[p + tap] and gz[p]; the whole level (activations +
+        // gradients, both planes) is several hundred MB, so the K range (batch rows) is cut into slices whose
+        // operands fit L2 and all tiles of a slice run in the same waves -> each row crosses HBM about once.
+        // The slices accumulate into the weight gradient with the epilogue's atomics (split-K).
+        const double level_bytes = (double)B * PP * (tin.Cp + T.Gp) * 2.0 * sizeof(float);
+        int nslice = 1;
+        while (nslice < nkb && level_bytes / nslice > 64e6) nslice *= 2;
+        const int slice_kb = (int)cdiv(nkb, nslice);
+        nslice = (int)cdiv(nkb, slice_kb);
+        const int pc = (int)std::max<int64_t>(1, cdiv(pairs * mt * ngroups, 2 * tc_sm_count()));  // positions per tile
+        for (int sl = 0; sl < nslice; sl++) {
+          const int kb0 = sl * slice_kb, kbn = std::min(slice_kb, nkb - kb0);
+          for (auto& tp : taps) {
+            const int dy = tp.first, dx = tp.second, ring = std::max(std::abs(dy), std::abs(dx));
+            std::vector<int> ps;  // output positions whose tap source is inside the patch
+            for (int p = 0; p < PP; p++) {
+              const int ph = p / P, pw = p % P;
+              if (ph + dy >= 0 && ph + dy < P && pw + dx >= 0 && pw + dx < P) ps.push_back(p);
+            }
+            for (int g = 0; g < ngroups; g++) {
+              const int s0 = g * spg, s1 = std::min(std::min(R, s0 + spg), R - ring);
+              if (s1 <= s0) continue;
+              const int ncols = (s1 - s0) * fpad;
+              for (int im = 0; im < mt; im++)
+                for (size_t c0 = 0; c0 < ps.size(); c0 += pc) {
+                  TcTile t = blank_tile();
+                  t.seg_begin = (int)pb.segs.size();
+                  for (size_t ci = c0; ci < std::min(ps.size(), c0 + (size_t)pc); ci++) {
+                    TcSeg s{};
+                    s.a0 = im * 128; s.a1 = kb0 * 32; s.a2 = ps[ci] + dy * P + dx;
+                    s.b0 = s0 * fpad; s.b1 = kb0 * 32; s.b2 = ps[ci];
+                    s.nk = kbn; s.n_mma = r16(ncols); s.nb = (int)cdiv(s.n_mma, 32);
+                    T.wg.b_rows = std::max(T.wg.b_rows, s.nb * 32);
+                    t.total_kb += s.nk;
+                    pb.segs.push_back(s);
+                  }
+                  t.seg_count = (int)pb.segs.size() - t.seg_begin;
+                  t.m_valid = std::min(128, Cin - im * 128);
+                  t.ld_out = f;
+                  t.ncb = s1 - s0;
+                  for (int s = s0; s < s1; s++) {
+                    const int q = R - 1 - s, k = 2 * q + 1;
+                    TcColBlock& cb = t.cb[s - s0];
+                    cb.tcol = (s - s0) * fpad; cb.width = f;
+                    cb.out_off = L.w_off[q] + (int64_t)((dy + q) * k + (dx + q)) * Cin * f + (int64_t)im * 128 * f;
+                  }
+                  pb.tiles.push_back(t);
                 }
-                t.seg_count = (int)pb.segs.size() - t.seg_begin;
-                t.m_valid = std::min(128, Cin - im * 128);
-                t.ld_out = f;
-                t.ncb = s1 - s0;
-                for (int s = s0; s < s1; s++) {
-                  const int q = R - 1 - s, k = 2 * q + 1;
-                  TcColBlock& cb = t.cb[s - s0];
-                  cb.tcol = (s - s0) * fpad; cb.width = f;
-                  cb.out_off = L.w_off[q] + (int64_t)((dy + q) * k + (dx + q)) * Cin * f + (int64_t)im * 128 * f;
-                }
-                pb.tiles.push_back(t);
-              }
+            }
           }
         }
+        T.wg.windowed = true;
         finish_launch(pb, T.wg);
       }
     } else {

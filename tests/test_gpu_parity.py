@@ -185,7 +185,11 @@ def test_forward_training_parity_per_layer(E, case, prec):
         elif l.kind == "level_end":
             a = eng.debug_tensor(l.dst, 0).cpu().numpy().reshape(ref["tensors"][l.dst].shape)
             assert_close(a, ref["tensors"][l.dst].numpy(), RTOL, 1e-4, f"level {l.dst}")
-    assert_close(logits.cpu().numpy(), ref["logits"].numpy(), RTOL, ATOL, "logits")
+    # logits: rtol 1e-4 (north star).  BN-normalised logits near 0 need an absolute floor: the fp32 round-off
+    # of 25 chained layers, measured as the distance of the fp32 CPU oracle from the fp64 one on this input
+    ref32 = R.forward(oracle_variables(eng, torch.float32), torch.tensor(x), c["classes"], alg, True)
+    floor32 = float((ref32["logits"].double() - ref["logits"]).abs().max())
+    assert_close(logits.cpu().numpy(), ref["logits"].numpy(), RTOL, max(ATOL, 3.0 * floor32), "logits")
     assert_close(recon.cpu().numpy(), ref["recon"].numpy(), RTOL, ATOL, "recon")
     # BN moving statistics (decay, Bessel-corrected variance)
     for name in eng.variables:
