@@ -167,10 +167,8 @@ def run_native(args):
     dev_x = [t.cuda() for t in host_x]
     dev_y = [t.cuda() for t in host_y]
 
-    def allreduce(grads):
-        dist.all_reduce(grads)  # one NCCL all-reduce over the flat gradient buffer
-        return 1.0 / world
-    ar = allreduce if world > 1 else None
+    from hypelcnn_b200 import parallel
+    ar = parallel.GradientAllReduce() if world > 1 else None  # one NCCL all-reduce over the flat gradient buffer
 
     def barrier():
         if world > 1:
@@ -245,8 +243,15 @@ def run_native(args):
             achieved = d["flops"] / (d["ms"] / 1e3) / 1e12
             peak = peaks["bf16_tflops_sustained"]
             tc = args.precision == "3xtf32"
+            traffic, traffic_src = None, None
+            tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+            if tc and args.workload == "c2_grss2013" and B == 4096 and os.path.exists(tp):
+                t = json.load(open(tp))  # dram__bytes_read.sum + dram__bytes_write.sum, averaged per GEMM launch (ncu)
+                traffic, traffic_src = t["gemm_dram_bytes_per_launch"], t["source"]
             roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                        "frac": achieved / peak, "traffic": None, "kernel": dom,
+                        "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)",
+                        "traffic_source": traffic_src, "algorithmic_flops_per_launch": d["flops"] / d["launches"],
+                        "kernel": dom,
                         "avg_launch_ms": d["ms"] / d["launches"], "share_of_step": d["ms"] / total_prof_ms,
                         "peak_source": f"{peaks['source']} bf16 dense sustained (kernel timed inside a long step)",
                         "note": ("achieved = useful (algorithmic) FLOPs; the kernel issues 3 kind::tf32 MMAs (half the "

@@ -598,7 +598,8 @@ static int tc_plan(hyp_model& m, int64_t B) {
         // The slices accumulate into the weight gradient with the epilogue's atomics (split-K).
         const double level_bytes = (double)B * PP * (tin.Cp + T.Gp) * 2.0 * sizeof(float);
         int nslice = 1;
-        while (nslice < nkb && level_bytes / nslice > 64e6) nslice *= 2;
+        static const double slice_bytes = getenv("HYP_WG_SLICE_MB") ? atof(getenv("HYP_WG_SLICE_MB")) * 1e6 : 128e6;
+        while (nslice < nkb && level_bytes / nslice > slice_bytes) nslice *= 2;
         const int slice_kb = (int)cdiv(nkb, nslice);
         nslice = (int)cdiv(nkb, slice_kb);
         const int pc = (int)std::max<int64_t>(1, cdiv(pairs * mt * ngroups, 2 * tc_sm_count()));  // positions per tile

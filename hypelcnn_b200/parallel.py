@@ -1,0 +1,87 @@
+"""Data-parallel plumbing: one process per GPU, patches sharded over ranks, ONE
+all-reduce over the flat gradient buffer per step and nothing else on the data path.
+
+The reference has no multi-device path (its device id is the literal "/gpu:0",
+classify/train_for_classification.py:51-55); this module is what a torchrun launch adds around
+``PatchEngine.train_step``.  Everything here is backend-agnostic torch.distributed (NCCL over
+NVLink on the GPU box, gloo in the CPU tests) — no arithmetic of the hot path lives here.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Process group from the torchrun environment (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*).
+    Returns (rank, local_rank, world).  world == 1 -> no group is created."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            kw["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend, **kw)
+    return rank, local, world
+
+
+def shard_range(n, rank, world):
+    """Contiguous partition of n units (patches of a batch, pixels of a scene) over ranks: the first
+    n % world ranks get one extra unit.  -> (begin, end)."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside world {world}")
+    base, extra = divmod(int(n), world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def shard_targets(targets, rank, world):
+    """Rank's slice of an [N, 3] (x, y, class) target list (full-scene inference: each rank writes its own
+    slice of the class map, no exchange)."""
+    b, e = shard_range(len(targets), rank, world)
+    return targets[b:e]
+
+
+class GradientAllReduce:
+    """The single collective of a train step: SUM all-reduce of the flat gradient buffer; the 1/world
+    factor is folded into the Adam kernel (``hyp_adam_step(grad_scale)``), so the returned scale is what
+    ``PatchEngine.train_step(allreduce=...)`` expects."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.calls = 0
+
+    def __call__(self, grads):
+        if self.world > 1:
+            dist.all_reduce(grads, op=dist.ReduceOp.SUM, group=self.group)
+        self.calls += 1
+        return 1.0 / self.world
+
+
+def broadcast_parameters(tensors, src=0, group=None):
+    """Same initial weights / BN state / Adam moments on every rank."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        for t in tensors:
+            dist.broadcast(t, src=src, group=group)
+
+
+def reduce_confusion(confusion, group=None):
+    """Sum the per-rank int32 confusion matrices (metrics are logged every N steps, off the step's critical
+    path — mirrors save_summaries_steps=100, classify/monitored_session_runner.py:147,177)."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(confusion, op=dist.ReduceOp.SUM, group=group)
+    return confusion
+
+
+def max_over_ranks(value, device=None, group=None):
+    """Timing helper: a device-measured duration as the maximum over ranks."""
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())

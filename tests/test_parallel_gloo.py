@@ -1,0 +1,73 @@
+"""world_size-2 gloo tests (CPU) of the data-parallel host logic in hypelcnn_b200/parallel.py: the
+sharding of patches over ranks and the one-all-reduce-per-step contract."""
+import os
+import socket
+
+import numpy
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from hypelcnn_b200 import parallel as P
+    r, local, w = P.init_from_env(backend="gloo")
+    assert (r, w) == (rank, world)
+    # ---- a linear least-squares "model": grad of the mean loss over the rank's shard of a global batch ----
+    rng = numpy.random.default_rng(7)
+    X = torch.tensor(rng.standard_normal((10, 4)))
+    y = torch.tensor(rng.standard_normal(10))
+    wgt = torch.tensor(rng.standard_normal(4))
+    P.broadcast_parameters([wgt])
+    b, e = P.shard_range(10, rank, world)
+    Xs, ys = X[b:e], y[b:e]
+    grad_local = 2.0 * Xs.T @ (Xs @ wgt - ys) / (e - b)  # mean over the local shard, like mean_B(loss)
+    ar = P.GradientAllReduce()
+    g = grad_local.clone()
+    scale = ar(g)
+    assert ar.calls == 1 and abs(scale - 1.0 / world) < 1e-15
+    # equal shard sizes -> averaged shard gradients == gradient of the global-batch mean
+    grad_global = 2.0 * X.T @ (X @ wgt - y) / 10
+    assert torch.allclose(g * scale, grad_global, atol=1e-12), (g * scale, grad_global)
+    # ---- metrics: confusion matrices add up ----
+    conf = torch.zeros((3, 3), dtype=torch.int32)
+    conf[rank, rank] = rank + 1
+    P.reduce_confusion(conf)
+    assert conf[0, 0].item() == 1 and conf[1, 1].item() == 2 and conf.sum().item() == 3
+    # ---- timing is the max over ranks ----
+    assert P.max_over_ranks(10.0 + rank) == 10.0 + world - 1
+    # ---- scene targets partition without overlap ----
+    targets = numpy.arange(23 * 3).reshape(23, 3)
+    mine = P.shard_targets(targets, rank, world)
+    numpy.save(os.path.join(out_dir, f"targets_{rank}.npy"), mine)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_and_sharding(tmp_path):
+    world, port = 2, _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    parts = [numpy.load(tmp_path / f"targets_{r}.npy") for r in range(world)]
+    assert [len(p) for p in parts] == [12, 11]
+    assert numpy.array_equal(numpy.concatenate(parts), numpy.arange(23 * 3).reshape(23, 3))
+
+
+def test_shard_range_properties():
+    from hypelcnn_b200 import parallel as P
+    for n in (0, 1, 7, 4096, 664845):
+        for world in (1, 2, 3, 8):
+            spans = [P.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1
