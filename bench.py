@@ -168,7 +168,7 @@ def run_native(args):
     dev_y = [t.cuda() for t in host_y]
 
     from hypelcnn_b200 import parallel
-    ar = parallel.GradientAllReduce() if world > 1 else None  # one NCCL all-reduce over the flat gradient buffer
+    ar = parallel.GradientAllReduce(overlap=not args.no_overlap) if world > 1 else None  # one NCCL all-reduce over the flat gradient buffer
 
     def barrier():
         if world > 1:
@@ -307,6 +307,8 @@ def main():
     ap.add_argument("--precision", default="3xtf32", choices=["fp32", "3xtf32"],
                     help="3xtf32: tcgen05 tensor-core engine (fp32-accurate split); fp32: FFMA engine")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: one blocking all-reduce after backward instead "
+                    "of reducing the FC/decoder gradients while the conv layers are still going backward")
     ap.add_argument("--prof-out", default=None, help="write the per-tag kernel timing table here (HYP_PROF_LAYERS=1 "
                     "adds the layer scope to GEMM tags)")
     args = ap.parse_args()

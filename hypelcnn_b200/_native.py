@@ -74,6 +74,7 @@ _PROTOS = {
     "hyp_model_forward": (_I, [_P, _P, _L, _I, _I, ctypes.c_uint64, _P, _P, _P]),
     "hyp_model_loss": (_I, [_P, _P, _P, _P, _P, _L, _P, _P]),
     "hyp_model_loss_backward": (_I, [_P, _P, _P, _L, _P, _P]),
+    "hyp_model_set_grad_notify": (_I, [_P, _L, _P]),
     "hyp_adam_step": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _L, _F, _P]),
     "hyp_argmax_confusion": (_I, [_P, _P, _L, _I, _P, _P, _P]),
     "hyp_scatter_class_map": (_I, [_P, _P, _L, _I, _I, _P, _P]),

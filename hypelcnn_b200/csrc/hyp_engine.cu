@@ -104,6 +104,9 @@ struct hyp_model {
   uint64_t last_seed = 0;
   const float* last_x = nullptr;
   hyp::tc::TcState* tc = nullptr;  // tensor-core engine state (HYP_PRECISION_3XTF32)
+  // gradient-ready notification (hyp_model_set_grad_notify)
+  cudaEvent_t notify_event = nullptr;
+  int64_t notify_offset = 0;
 };
 
 namespace hyp {
@@ -452,6 +455,13 @@ static double layer_flops(const Layer& L, int64_t B) {
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static inline int ew_grid(int64_t total) { return (int)std::min<int64_t>(cdiv(total, 256), 148 * 16); }
 
+// records the notify event once every layer whose parameters start at or above notify_offset is done
+static void grad_notify(const hyp_model& m, int li, cudaStream_t st) {
+  if (!m.notify_event) return;
+  const bool here = m.layers[li].w_off[0] >= m.notify_offset && (li == 0 || m.layers[li - 1].w_off[0] < m.notify_offset);
+  if (here) cudaEventRecord(m.notify_event, st);
+}
+
 static const float* act_ptr(const hyp_model& m, int t, const float* x) {
   return m.tensors[t].external ? x : reinterpret_cast<const float*>(m.ws + m.tensors[t].a_off);
 }
@@ -607,6 +617,7 @@ static int backward_impl(hyp_model& m, const float* x, const uint8_t* labels, in
       if (rc) return rc;
       ginit[L.in_t] = 1;
     }
+    grad_notify(m, li, st);
   }
   return HYP_OK;
 }
@@ -805,6 +816,14 @@ int hyp_model_loss_backward(hyp_model* m, const float* x, const uint8_t* labels,
     return fail(HYP_E_STATE, "hyp_model_loss_backward: needs the preceding hyp_model_forward(is_training=1) on the same x/B");
   if (m->tc) return hyp::tc::tc_backward(*m, labels, B, loss_out, static_cast<cudaStream_t>(stream));
   return backward_impl(*m, x, labels, B, loss_out, static_cast<cudaStream_t>(stream));
+}
+
+int hyp_model_set_grad_notify(hyp_model* m, int64_t param_offset, void* event) {
+  HYP_CHECK_ARG(m, "null model");
+  HYP_CHECK_ARG(!event || (param_offset >= 0 && param_offset <= m->n_params), "param_offset out of range");
+  m->notify_event = static_cast<cudaEvent_t>(event);
+  m->notify_offset = param_offset;
+  return HYP_OK;
 }
 
 int hyp_adam_step(float* params, const float* grads, float* mbuf, float* vbuf, int64_t n, float lr, float b1,

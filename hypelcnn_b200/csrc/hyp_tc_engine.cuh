@@ -945,6 +945,7 @@ static int tc_backward(hyp_model& m, const uint8_t* labels, int64_t B, float* lo
       if (rc) return rc;
       ginit[L.in_t] = 1;
     }
+    grad_notify(m, li, st);
   }
   return HYP_OK;
 }

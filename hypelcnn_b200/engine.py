@@ -51,6 +51,7 @@ class PatchEngine:
         self.global_step = 0
         self._max_batch = 0
         self.params = self.grads = self.state = self.adam_m = self.adam_v = self.workspace = None
+        self._notify_event = self._comm_stream = None
         self._create(int(max_batch))
 
     # ------------------------------------------------------------------ lifecycle
@@ -231,12 +232,38 @@ class PatchEngine:
         backward, [gradient all-reduce], Adam.  Returns the device loss tensor [3]."""
         seed = self.global_step if seed is None else seed
         self.forward_inplace(x, True, True, seed)
+        overlap = allreduce is not None and getattr(allreduce, "overlap", False)
+        if overlap:
+            # the FC / decoder gradients (the tail of the flat buffer, ~70 % of it) are final early in backward:
+            # their all-reduce runs on the communication stream while the conv layers are still going backward
+            if self._notify_event is None:
+                self._notify_event = torch.cuda.Event()
+                self._notify_event.record()  # materialises the cudaEvent_t
+                self._comm_stream = torch.cuda.Stream(device=self.device)
+            N.check(N.lib().hyp_model_set_grad_notify(self._handle, self.grad_split_offset,
+                                                      ctypes.c_void_p(self._notify_event.cuda_event)))
         loss = self.loss_backward(x, labels)
         scale = 1.0
-        if allreduce is not None:
+        if overlap:
+            main = torch.cuda.current_stream()
+            self._comm_stream.wait_event(self._notify_event)
+            with torch.cuda.stream(self._comm_stream):
+                allreduce(self.grads[self.grad_split_offset:])
+            scale = allreduce(self.grads[:self.grad_split_offset])
+            main.wait_stream(self._comm_stream)
+        elif allreduce is not None:
             scale = allreduce(self.grads)
         self.adam_step(grad_scale=scale)
         return loss
+
+    @property
+    def grad_split_offset(self):
+        """First parameter of the FC block: gradients from here to the end of the flat buffer are complete once
+        fc_0's backward has run (hyp_model_set_grad_notify)."""
+        for name, (kind, off, shape) in self.variables.items():
+            if kind == 0 and len(shape) == 2:
+                return off
+        return 0
 
     def debug_tensor(self, name, what=0):
         p, n = ctypes.c_void_p(), ctypes.c_int64()

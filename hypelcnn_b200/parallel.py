@@ -51,8 +51,9 @@ class GradientAllReduce:
     factor is folded into the Adam kernel (``hyp_adam_step(grad_scale)``), so the returned scale is what
     ``PatchEngine.train_step(allreduce=...)`` expects."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, overlap=False):
         self.group = group
+        self.overlap = overlap  # PatchEngine.train_step: reduce the FC/decoder tail while the conv layers go backward
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.calls = 0
 

@@ -139,6 +139,12 @@ int hyp_model_loss(hyp_model* m, const float* logits, const float* recon, const 
 int hyp_model_loss_backward(hyp_model* m, const float* x, const uint8_t* labels, int64_t B,
                             float* loss_out, void* stream);
 
+/* Overlap of the gradient all-reduce with the rest of backward (multi-GPU).  Parameters are laid
+ * out in layer order and backward walks the layers last to first, so the tail [param_offset, n_params) of the
+ * flat gradient buffer is final as soon as the first layer at or above param_offset has been processed:
+ * hyp_model_loss_backward then records `event` (a cudaEvent_t) on its stream.  event == NULL clears it. */
+int hyp_model_set_grad_notify(hyp_model* m, int64_t param_offset, void* event);
+
 /* TF1 AdamOptimizer (ApplyAdam): lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m += (g-m)(1-b1);
  * v += (g*g-v)(1-b2); p -= lr_t*m/(sqrt(v)+eps).  g = grads*grad_scale (1/world_size). */
 int hyp_adam_step(float* params, const float* grads, float* m, float* v, int64_t n,
