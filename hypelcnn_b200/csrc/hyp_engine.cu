@@ -42,8 +42,10 @@ struct Tensor {
   int rows_per_sample;
   size_t a_off = 0;   // byte offsets in workspace
   size_t g_off = 0;
-  bool external = false;  // the input x
+  bool external = false;  // a view of the input x: channels [x_c0, x_c0 + C), spatial crop of x_crop pixels per side
   bool needs_grad = true;
+  int P = 1;              // spatial edge (rows_per_sample = P * P)
+  int x_c0 = 0, x_crop = 0;
 };
 
 struct Layer {
@@ -67,6 +69,11 @@ struct Layer {
   int seg_begin, seg_count;
   std::vector<int> kseg_begin;  // first segment of kernel j
   uint32_t drop_stream;
+  bool bias_mode = false;       // slim conv2d / fully_connected without normalizer_fn: z + biases instead of BatchNorm
+  // an FC fed by the concatenation of two flattened tensors (DUALCNN fc1) is two layers that share one
+  // pre-activation buffer and one weight variable: share = 1 first part (GEMM only), 2 second part (accumulates
+  // into the first part's z, then bias / activation / dropout)
+  int share = 0;
 };
 
 namespace tc {
@@ -87,6 +94,7 @@ struct hyp_model {
   size_t gz_off = 0, ce_off = 0, mse_off = 0, stats_region_off = 0, stats_region_bytes = 0;
   size_t bstats_region_off = 0, bstats_region_bytes = 0;
   int logits_t = -1, recon_t = -1, last_eval_layer = -1;
+  float keep_prob = 1.f;  // dropout keep probability (HYPELCNN: 1 - drop_out_ratio; DUALCNN: drop_out_ratio itself)
   // library-owned device metadata
   Seg* segs_dev = nullptr;
   std::vector<Seg> segs_host;
@@ -138,6 +146,7 @@ struct Builder {
     t.name = name;
     t.C = C;
     t.rows_per_sample = rps;
+    t.P = (int)std::lround(std::sqrt((double)rps));
     t.external = external;
     t.needs_grad = !external;
     m.tensors.push_back(t);
@@ -218,6 +227,7 @@ static int build_hypelcnn(hyp_model& m) {
   Builder b(m);
   const int P = d.patch, PP = P * P;
   const bool res = d.use_residual != 0;
+  m.keep_prob = 1.f - d.drop_out_ratio;  // HYPELCNNModel.py:123
   int cur = b.add_tensor("x", d.channels, PP, true);
   const int x_t = cur;
   // spectral encoder / decoder (HYPELCNNModel.py:146-164, :54-64)
@@ -293,37 +303,115 @@ static int build_hypelcnn(hyp_model& m) {
   return HYP_OK;
 }
 
+// DUALCNNModel (nnmodel/DUALCNNModel.py:11-104): the HSI bands (window cropped by hs_lidar_diff) and the LiDAR
+// channel run through separate stacks of multi-kernel levels + 1x1 connectors, are flattened, concatenated and
+// classified by four FCs.  No BatchNorm: every conv / FC has a bias; LeakyReLU; dropout keep_prob = drop_out_ratio
+// (slim dropout's second positional argument, DUALCNNModel.py:49).
+static int build_dualcnn(hyp_model& m) {
+  const hyp_model_desc& d = m.d;
+  Builder b(m);
+  const int P0 = d.patch, diff = d.reserved;
+  if (d.channels < 2) return fail(HYP_E_INVALID, "DUALCNN needs at least one HSI band and the LiDAR channel");
+  const bool crop = P0 > 1;  // DUALCNNModel.py:24-26
+  const int Ph = crop ? P0 - 2 * diff : P0;
+  if (diff < 0 || Ph < 1) return fail(HYP_E_INVALID, "hs_lidar_diff leaves no HSI window");
+  if (d.filter_count < 32) return fail(HYP_E_INVALID, "filter_count must be >= 32 (level8 has filter_count / 32 filters)");
+  m.keep_prob = d.drop_out_ratio;
+  const int hs = b.add_tensor("x_hs", d.channels - 1, Ph * Ph, true);
+  m.tensors[hs].x_c0 = 0; m.tensors[hs].x_crop = crop ? diff : 0;
+  const int li_t = b.add_tensor("x_lidar", 1, P0 * P0, true);
+  m.tensors[li_t].x_c0 = d.channels - 1; m.tensors[li_t].x_crop = 0;
+  auto level_and_connector = [&](int cur, int P, int f, const std::string& lname, const std::string& cname) {
+    std::vector<int> ks;
+    std::vector<std::string> kn;
+    for (int k = 1; k <= P; k += 2) { ks.push_back(k); kn.push_back(lname + "_conv" + std::to_string(k) + "x" + std::to_string(k)); }
+    Layer& L = b.add_layer(lname, false, P, cur, lname, f, ks, kn, ACT_LRELU, false);
+    L.bias_mode = true;
+    const int lvl_t = L.out_t;
+    Layer& Cn = b.add_layer(cname, false, P, lvl_t, cname, m.tensors[lvl_t].C, {1}, {cname}, ACT_LRELU, false);
+    Cn.bias_mode = true;
+    return Cn.out_t;
+  };
+  int cur = hs;
+  const int F = d.filter_count;
+  const int hs_f[8] = {F / 4, F / 2, F, F / 2, F / 4, F / 8, F / 16, F / 32};
+  for (int i = 0; i < 8; i++)
+    cur = level_and_connector(cur, Ph, hs_f[i], "level" + std::to_string(i + 1), "connector_conv" + std::to_string(i + 1));
+  const int hs_net = cur;
+  cur = li_t;
+  const int li_f[3] = {2, 4, 8};
+  for (int i = 0; i < 3; i++)
+    cur = level_and_connector(cur, P0, li_f[i], "lidar_level" + std::to_string(i + 1),
+                              "lidar_connector_conv" + std::to_string(i + 1));
+  const int lidar_net = cur;
+  // fc1 over concat(flatten(hs_net), flatten(lidar_net)): two layers, one z, one weight variable
+  {
+    Layer& A = b.add_layer("fc1/hs", true, 1, hs_net, "fc1", d.classes * 9, {1}, {"fc1"}, ACT_LRELU, false);
+    A.bias_mode = true; A.share = 1;
+    const int out_t = A.out_t;
+    Layer& Bp = b.add_layer("fc1", true, 1, lidar_net, "fc1_lidar_tmp", d.classes * 9, {1}, {"fc1"}, ACT_LRELU, true);
+    Bp.bias_mode = true; Bp.share = 2;
+    m.tensor_by_name.erase("fc1_lidar_tmp");
+    m.tensors.pop_back();
+    m.layers.back().out_t = out_t;
+    cur = out_t;
+  }
+  const int mult[2] = {6, 3};
+  for (int i = 0; i < 2; i++) {
+    const std::string name = "fc" + std::to_string(i + 2);
+    Layer& L = b.add_layer(name, true, 1, cur, name, d.classes * mult[i], {1}, {name}, ACT_LRELU, true);
+    L.bias_mode = true;
+    cur = L.out_t;
+  }
+  {
+    Layer& L = b.add_layer("fc4", true, 1, cur, "fc4", d.classes, {1}, {"fc4"}, ACT_NONE, false);
+    L.bias_mode = true;
+    m.logits_t = L.out_t;
+    m.last_eval_layer = (int)m.layers.size() - 1;
+  }
+  return HYP_OK;
+}
+
 static int layout(hyp_model& m) {
   // ---- parameters: per layer W_0..W_{nk-1} (each 128-byte aligned), then beta[Cout] ----
   int64_t po = 0, so = 0;
-  for (Layer& L : m.layers) {
+  for (size_t li = 0; li < m.layers.size(); li++) {
+    Layer& L = m.layers[li];
     for (size_t j = 0; j < L.ksizes.size(); j++) {
       const int k = L.ksizes[j];
-      po = (int64_t)align_up((size_t)po, 32);
+      if (L.share != 2) po = (int64_t)align_up((size_t)po, 32);  // share 2: the rows continue the first part's variable
       L.w_off.push_back(po);
-      Variable v;
-      v.name = "nn_core/" + L.kscopes[j] + "/weights";
-      v.kind = 0;
-      v.offset = po;
-      if (L.is_fc) {
-        v.rank = 2;
-        v.shape[0] = L.Cin; v.shape[1] = L.f; v.shape[2] = v.shape[3] = 0;
-      } else {
-        v.rank = 4;
-        v.shape[0] = k; v.shape[1] = k; v.shape[2] = L.Cin; v.shape[3] = L.f;
+      if (L.share != 2) {
+        Variable v;
+        v.name = "nn_core/" + L.kscopes[j] + "/weights";
+        v.kind = 0;
+        v.offset = po;
+        if (L.is_fc) {
+          v.rank = 2;
+          v.shape[0] = L.Cin + (L.share == 1 ? m.layers[li + 1].Cin : 0);
+          v.shape[1] = L.f; v.shape[2] = v.shape[3] = 0;
+        } else {
+          v.rank = 4;
+          v.shape[0] = k; v.shape[1] = k; v.shape[2] = L.Cin; v.shape[3] = L.f;
+        }
+        m.vars.push_back(v);
       }
-      m.vars.push_back(v);
       po += (int64_t)k * k * L.Cin * L.f;
+    }
+    so = (int64_t)align_up((size_t)so, 32);
+    L.mm_off = so;
+    so += 2 * (int64_t)L.Cout;
+    if (L.share == 1) {  // bias / activation belong to the second part
+      L.beta_off = po;
+      continue;
     }
     po = (int64_t)align_up((size_t)po, 32);
     L.beta_off = po;
-    so = (int64_t)align_up((size_t)so, 32);
-    L.mm_off = so;
     for (size_t j = 0; j < L.ksizes.size(); j++) {
       const char* names[3] = {"beta", "moving_mean", "moving_variance"};
-      for (int q = 0; q < 3; q++) {
+      for (int q = 0; q < (L.bias_mode ? 1 : 3); q++) {
         Variable v;
-        v.name = "nn_core/" + L.kscopes[j] + "/BatchNorm/" + names[q];
+        v.name = "nn_core/" + L.kscopes[j] + (L.bias_mode ? "/biases" : std::string("/BatchNorm/") + names[q]);
         v.kind = 1 + q;
         v.offset = (q == 0 ? L.beta_off : (q == 1 ? L.mm_off : L.mm_off + L.Cout)) + (int64_t)j * L.f;
         v.rank = 1;
@@ -332,7 +420,6 @@ static int layout(hyp_model& m) {
       }
     }
     po += L.Cout;
-    so += 2 * (int64_t)L.Cout;
   }
   m.n_params = (int64_t)align_up((size_t)po, 32);
   m.n_state = (int64_t)align_up((size_t)so, 32);
@@ -666,11 +753,14 @@ int hyp_profile_get(int idx, char name[64], double* total_ms, int64_t* launches,
 
 int hyp_model_create(const hyp_model_desc* desc, hyp_model** out) {
   HYP_CHECK_ARG(desc && out, "null argument");
-  HYP_CHECK_ARG(desc->kind == HYP_MODEL_HYPELCNN, "unknown model kind");
+  HYP_CHECK_ARG(desc->kind == HYP_MODEL_HYPELCNN || desc->kind == HYP_MODEL_DUALCNN, "unknown model kind");
+  if (desc->kind == HYP_MODEL_DUALCNN && desc->precision_mode != HYP_PRECISION_3XTF32)
+    return fail(HYP_E_UNSUPPORTED, "hyp_model_create: DUALCNN is built for the tensor-core engine (HYP_PRECISION_3XTF32) only");
   HYP_CHECK_ARG(desc->patch >= 1 && desc->patch % 2 == 1 && desc->patch <= 15, "patch must be odd, 1..15");
   HYP_CHECK_ARG(desc->channels >= 1 && desc->classes >= 2 && desc->classes <= 255, "channels/classes out of range");
-  HYP_CHECK_ARG(desc->filter_count >= 8 && desc->spectral_levels >= 1 && desc->spatial_levels >= 1,
-                "filter_count/levels out of range");
+  HYP_CHECK_ARG(desc->filter_count >= 8, "filter_count out of range");
+  HYP_CHECK_ARG(desc->kind != HYP_MODEL_HYPELCNN || (desc->spectral_levels >= 1 && desc->spatial_levels >= 1),
+                "levels out of range");
   HYP_CHECK_ARG(desc->max_batch >= 1, "max_batch must be positive");
   HYP_CHECK_ARG(desc->drop_out_ratio >= 0.f && desc->drop_out_ratio < 1.f, "drop_out_ratio in [0,1)");
   if (desc->precision_mode != HYP_PRECISION_FP32 && desc->precision_mode != HYP_PRECISION_3XTF32)
@@ -680,7 +770,7 @@ int hyp_model_create(const hyp_model_desc* desc, hyp_model** out) {
     return fail(HYP_E_CUDA, "hyp_model_create: no CUDA device (this library has no CPU fallback)");
   std::unique_ptr<hyp_model> m(new hyp_model());
   m->d = *desc;
-  int rc = build_hypelcnn(*m);
+  int rc = desc->kind == HYP_MODEL_DUALCNN ? build_dualcnn(*m) : build_hypelcnn(*m);
   if (rc) return rc;
   rc = layout(*m);
   if (rc) return rc;
@@ -766,7 +856,8 @@ int hyp_model_forward(hyp_model* m, const float* x, int64_t B, int is_training, 
                                  (size_t)m->tc->tt[m->logits_t].Cp * sizeof(float), (size_t)m->d.classes * sizeof(float),
                                  (size_t)B, cudaMemcpyDeviceToDevice, st));
     if (recon) {
-      if (!is_training) return fail(HYP_E_INVALID, "hyp_model_forward: recon only exists in the training graph");
+      if (!is_training || m->recon_t < 0)
+        return fail(HYP_E_INVALID, "hyp_model_forward: recon only exists in HYPELCNN's training graph");
       const size_t D = (size_t)m->d.patch * m->d.patch * m->d.channels;
       HYP_CUDA(cudaMemcpy2DAsync(recon, D * sizeof(float), hyp::tc::tc_plane0(*m, m->recon_t),
                                  (size_t)m->tc->tt[m->recon_t].Cp * sizeof(float), D * sizeof(float), (size_t)B,
@@ -1100,7 +1191,7 @@ int hyp_model_dropout_mask(hyp_model* m, const char* layer_scope, uint64_t seed,
     if (L.scope == layer_scope && L.dropout) {
       const int64_t n = B * L.rows_per_sample * L.Cout;
       dropout_mask_kernel<<<(unsigned)cdiv(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-          seed, L.drop_stream, n, 1.f - m->d.drop_out_ratio, mask_out);
+          seed, L.drop_stream, n, m->keep_prob, mask_out);
       HYP_LAUNCHED();
       return HYP_OK;
     }

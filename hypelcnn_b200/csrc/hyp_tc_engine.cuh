@@ -38,6 +38,12 @@ struct TcLaunch {
 struct TcLayer {
   int kind = 0;  // 0 rowwise, 1 level, 2 flatten
   int R = 1, f = 0, fpad = 0, Gp = 0, Kp = 0, Cq = 0;
+  // level slots: kernel q = R-1 - slot / nt (largest kernel first), filters [jt * ft, jt * ft + width) with jt = slot % nt;
+  // nt > 1 only when a kernel has more than 256 filters (one accumulator holds at most 256 columns)
+  int nt = 1, ft = 0, NS = 1;
+  int slot_q(int s) const { return R - 1 - s / nt; }
+  int slot_ch0(int s) const { return slot_q(s) * f + (s % nt) * ft; }   // first channel in the level's output tensor
+  int slot_w(int s) const { return std::min(ft, f - (s % nt) * ft); }
   size_t z_off = 0, mean_off = 0, rstd_off = 0, s1_off = 0, s2_off = 0;
   int64_t wf_off = 0, wd_off = 0;  // packed forward / dgrad weights: element offsets inside a pack plane
   int wf_rows = 0, wf_ld = 0, wd_rows = 0, wd_ld = 0;
@@ -129,14 +135,15 @@ static int tc_layout(hyp_model& m) {
     return o;
   };
   size_t gz_max = 0, part_max = 0, bpart_max = 0, dbg_max = 0;
-  const int P = m.d.patch;
   for (size_t li = 0; li < m.layers.size(); li++) {
     Layer& L = m.layers[li];
     TcLayer& T = S.tl[li];
+    const int P = L.P;
     const TcTensor& tin = S.tt[L.in_t];
     const TcTensor& tout = S.tt[L.out_t];
     const size_t rows_out = Bm * tout.PP;
     T.z_off = take(rows_out * tout.Cp * sizeof(float));
+    if (L.share == 2) T.z_off = S.tl[li - 1].z_off;  // second part of a two-input FC accumulates into the first part's z
     T.mean_off = take(L.Cout * sizeof(float));
     T.rstd_off = take(L.Cout * sizeof(float));
     T.s1_off = take(L.Cout * sizeof(float));
@@ -171,12 +178,15 @@ static int tc_layout(hyp_model& m) {
       for (int q = 0; q < T.R; q++)
         if (L.ksizes[q] != 2 * q + 1) return fail(HYP_E_UNSUPPORTED, "tc engine: level kernels must be 1,3,5,...");
       T.f = L.f;
-      T.fpad = r16(L.f);
+      T.nt = (int)cdiv(L.f, 256);
+      T.ft = (int)cdiv(L.f, T.nt);
+      T.NS = T.R * T.nt;
+      T.fpad = r16(T.ft);
       T.Kp = r32(Cin);
-      T.Gp = r32(T.R * T.fpad);
+      T.Gp = r32(T.NS * T.fpad);
       T.Cq = r16(Cin);
       const int ntaps = P * P;
-      T.wf_rows = ntaps * T.R * T.fpad; T.wf_ld = T.Kp;
+      T.wf_rows = ntaps * T.NS * T.fpad; T.wf_ld = T.Kp;
       T.wd_rows = ntaps * T.Cq; T.wd_ld = T.Gp;
       T.wf_off = take_pack((int64_t)T.wf_rows * T.wf_ld);
       T.wd_off = take_pack((int64_t)T.wd_rows * T.wd_ld);
@@ -185,21 +195,23 @@ static int tc_layout(hyp_model& m) {
         for (int dx = -h; dx <= h; dx++) {
           const int tap = (dy + h) * P + (dx + h);
           const int ring = std::max(std::abs(dy), std::abs(dx));
-          for (int slot = 0; slot < T.R; slot++) {
-            const int q = T.R - 1 - slot;
+          for (int slot = 0; slot < T.NS; slot++) {
+            const int q = T.slot_q(slot);
             if (ring > q) continue;
             const int k = 2 * q + 1;
-            const int64_t src = L.w_off[q] + (int64_t)((dy + q) * k + (dx + q)) * Cin * L.f;
+            const int64_t src = L.w_off[q] + (int64_t)((dy + q) * k + (dx + q)) * Cin * L.f + (slot % T.nt) * T.ft;
             PackJob j{};
-            j.src_off = src; j.dst_off = T.wf_off + (int64_t)((tap * T.R + slot) * T.fpad) * T.Kp;
+            j.src_off = src; j.dst_off = T.wf_off + (int64_t)((tap * T.NS + slot) * T.fpad) * T.Kp;
             j.rows = T.fpad; j.cols = T.Kp; j.ld = T.Kp;
-            j.RD = T.fpad; j.RV = L.f; j.KD = T.Kp; j.KV = Cin; j.sr0 = 1; j.sk0 = L.f;
+            j.RD = T.fpad; j.RV = T.slot_w(slot); j.KD = T.Kp; j.KV = Cin; j.sr0 = 1; j.sk0 = L.f;
             S.jobs.push_back(j);
-            PackJob d{};
-            d.src_off = src; d.dst_off = T.wd_off + (int64_t)(tap * T.Cq) * T.Gp + slot * T.fpad;
-            d.rows = T.Cq; d.cols = T.fpad; d.ld = T.Gp;
-            d.RD = T.Cq; d.RV = Cin; d.KD = T.fpad; d.KV = L.f; d.sr0 = L.f; d.sk0 = 1;
-            S.jobs.push_back(d);
+            if (m.tensors[L.in_t].needs_grad) {
+              PackJob d{};
+              d.src_off = src; d.dst_off = T.wd_off + (int64_t)(tap * T.Cq) * T.Gp + slot * T.fpad;
+              d.rows = T.Cq; d.cols = T.fpad; d.ld = T.Gp;
+              d.RD = T.Cq; d.RV = Cin; d.KD = T.fpad; d.KV = T.slot_w(slot); d.sr0 = L.f; d.sk0 = 1;
+              S.jobs.push_back(d);
+            }
           }
         }
       T.stats_rows = (int)(tout.PP * cdiv((int64_t)Bm, 128));
@@ -258,6 +270,13 @@ static int tc_bind(hyp_model& m) {
     HYP_CUDA(cudaMemcpy(S.jobs_dev, S.jobs.data(), S.jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
   }
   HYP_CUDA(cudaMemset(m.ws + S.pack_off, 0, 2 * S.pack_plane_elems * sizeof(float)));
+  for (size_t li = 0; li < m.layers.size(); li++)
+    if (m.layers[li].bias_mode) {  // no normaliser: z + biases is the (mean 0, rstd 1, beta = biases) case of the BN kernels
+      const int C = m.layers[li].Cout;
+      HYP_CUDA(cudaMemset(m.ws + S.tl[li].mean_off, 0, C * sizeof(float)));
+      tc_fill_kernel<<<(unsigned)cdiv(C, 256), 256>>>(reinterpret_cast<float*>(m.ws + S.tl[li].rstd_off), C, 1.f);
+      HYP_LAUNCHED();
+    }
   S.planned_B = -1;
   return HYP_OK;
 }
@@ -367,22 +386,22 @@ static int tc_plan(hyp_model& m, int64_t B) {
   TcState& S = *m.tc;
   if (S.planned_B == B) return HYP_OK;
   PlanBuf pb;
-  const int P = m.d.patch, h = P / 2;
   const int nbt = (int)cdiv(B, 128);
   const int CG = TC_CG_KMAJOR;
   float* pack0 = reinterpret_cast<float*>(m.ws + S.pack_off);
   float* gz0 = reinterpret_cast<float*>(m.ws + S.gz_off);
   int rc;
-  // taps sorted by ring so that the MMA N of a tile's segments never increases
-  std::vector<std::pair<int, int>> taps;
-  for (int ring = 0; ring <= h; ring++)
-    for (int dy = -h; dy <= h; dy++)
-      for (int dx = -h; dx <= h; dx++)
-        if (std::max(std::abs(dy), std::abs(dx)) == ring) taps.push_back({dy, dx});
-
   for (size_t li = 0; li < m.layers.size(); li++) {
     Layer& L = m.layers[li];
     TcLayer& T = S.tl[li];
+    const int P = L.P, h = P / 2;
+    // taps sorted by ring so that the MMA N of a tile's segments never increases
+    std::vector<std::pair<int, int>> taps;
+    if (T.kind == 1)
+      for (int ring = 0; ring <= h; ring++)
+        for (int dy = -h; dy <= h; dy++)
+          for (int dx = -h; dx <= h; dx++)
+            if (std::max(std::abs(dy), std::abs(dx)) == ring) taps.push_back({dy, dx});
     const TcTensor& tin = S.tt[L.in_t];
     const TcTensor& tout = S.tt[L.out_t];
     const bool need_dgrad = m.tensors[L.in_t].needs_grad;
@@ -482,9 +501,9 @@ static int tc_plan(hyp_model& m, int64_t B) {
         finish_launch(pb, T.wg);
       }
     } else if (T.kind == 1) {
-      const int Cin = tin.C, PP = tin.PP, R = T.R, fpad = T.fpad, f = T.f;
-      const int spg = std::min(std::min(256 / fpad, TC_MAX_CB), R);  // slots per accumulator group
-      const int ngroups = (int)cdiv(R, spg);
+      const int Cin = tin.C, PP = tin.PP, R = T.R, NS = T.NS, nt = T.nt, fpad = T.fpad, f = T.f;
+      const int spg = std::min(std::min(256 / fpad, TC_MAX_CB), NS);  // slots per accumulator group
+      const int ngroups = (int)cdiv(NS, spg);
       // ---------------- forward ----------------
       if ((rc = map4(&T.fwd.tmA, a0, Cin, B, PP, tin.Cp, (uint64_t)B * tin.Cp, tin.plane_elems, 32, 128, false))) return rc;
       if ((rc = map4(&T.fwd.tmB, pack0 + T.wf_off, T.wf_ld, T.wf_rows, 1, T.wf_ld, (uint64_t)T.wf_rows * T.wf_ld,
@@ -498,16 +517,16 @@ static int tc_plan(hyp_model& m, int64_t B) {
       for (int p = 0; p < PP; p++) {
         const int ph = p / P, pw = p % P;
         for (int g = 0; g < ngroups; g++) {
-          const int s0 = g * spg, s1 = std::min(R, s0 + spg);
+          const int s0 = g * spg, s1 = std::min(NS, s0 + spg);
           const int seg0 = (int)pb.segs.size();
           for (auto& tp : taps) {
             const int dy = tp.first, dx = tp.second, ring = std::max(std::abs(dy), std::abs(dx));
             if (ph + dy < 0 || ph + dy >= P || pw + dx < 0 || pw + dx >= P) continue;
-            const int nbx = std::min(s1, R - ring) - s0;
+            const int nbx = std::min(s1, (R - ring) * nt) - s0;
             if (nbx <= 0) continue;
             const int tap = (dy + h) * P + (dx + h);
             TcSeg s{};
-            s.a2 = p + dy * P + dx; s.b1 = tap * R * fpad; s.nk = T.Kp / 32; s.n_mma = nbx * fpad; s.nb = nbx;
+            s.a2 = p + dy * P + dx; s.b1 = tap * NS * fpad; s.nk = T.Kp / 32; s.n_mma = nbx * fpad; s.nb = nbx;
             pb.segs.push_back(s);
           }
           const int nseg = (int)pb.segs.size() - seg0;
@@ -517,7 +536,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
       std::stable_sort(runs.begin(), runs.end(), [](const Run& a, const Run& b) { return a.tkb > b.tkb; });
       for (int bt2 = 0; bt2 < nbt; bt2 += CG)
         for (const Run& rn : runs) {
-          const int s0 = rn.g * spg, s1 = std::min(R, s0 + spg), p = rn.p;
+          const int s0 = rn.g * spg, s1 = std::min(NS, s0 + spg), p = rn.p;
           const size_t run = pb.tiles.size();
           for (int bt = bt2; bt < std::min(nbt, bt2 + CG); bt++) {
             TcTile t = blank_tile();
@@ -526,11 +545,10 @@ static int tc_plan(hyp_model& m, int64_t B) {
             t.ld_out = tout.Cp; t.stats_row = p * nbt + bt; t.a1_add = bt * 128; t.b1_add = s0 * fpad;
             t.ncb = s1 - s0;
             for (int s = s0; s < s1; s++) {
-              const int q = R - 1 - s;
               TcColBlock& cb = t.cb[s - s0];
-              cb.tcol = (s - s0) * fpad; cb.width = f;
-              cb.out_off = ((int64_t)p * B + (int64_t)bt * 128) * tout.Cp + q * f;
-              cb.stats_col = q * f;
+              cb.tcol = (s - s0) * fpad; cb.width = T.slot_w(s);
+              cb.out_off = ((int64_t)p * B + (int64_t)bt * 128) * tout.Cp + T.slot_ch0(s);
+              cb.stats_col = T.slot_ch0(s);
             }
             pb.tiles.push_back(t);
           }
@@ -559,7 +577,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
               const int tap = (dy + h) * P + (dx + h);
               TcSeg s{};
               s.a2 = p - (dy * P + dx); s.b1 = tap * T.Cq + j * nw;
-              s.nk = (int)cdiv((R - ring) * fpad, 32); s.n_mma = r16(std::min(nw, Cin - j * nw)); s.nb = 1;
+              s.nk = (int)cdiv((R - ring) * nt * fpad, 32); s.n_mma = r16(std::min(nw, Cin - j * nw)); s.nb = 1;
               tkb += s.nk;
               pb.segs.push_back(s);
             }
@@ -613,7 +631,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
               if (ph + dy >= 0 && ph + dy < P && pw + dx >= 0 && pw + dx < P) ps.push_back(p);
             }
             for (int g = 0; g < ngroups; g++) {
-              const int s0 = g * spg, s1 = std::min(std::min(R, s0 + spg), R - ring);
+              const int s0 = g * spg, s1 = std::min(std::min(NS, s0 + spg), (R - ring) * nt);
               if (s1 <= s0) continue;
               const int ncols = (s1 - s0) * fpad;
               for (int im = 0; im < mt; im++)
@@ -634,10 +652,11 @@ static int tc_plan(hyp_model& m, int64_t B) {
                   t.ld_out = f;
                   t.ncb = s1 - s0;
                   for (int s = s0; s < s1; s++) {
-                    const int q = R - 1 - s, k = 2 * q + 1;
+                    const int q = T.slot_q(s), k = 2 * q + 1;
                     TcColBlock& cb = t.cb[s - s0];
-                    cb.tcol = (s - s0) * fpad; cb.width = f;
-                    cb.out_off = L.w_off[q] + (int64_t)((dy + q) * k + (dx + q)) * Cin * f + (int64_t)im * 128 * f;
+                    cb.tcol = (s - s0) * fpad; cb.width = T.slot_w(s);
+                    cb.out_off = L.w_off[q] + (int64_t)((dy + q) * k + (dx + q)) * Cin * f + (int64_t)im * 128 * f +
+                                 (s % nt) * T.ft;
                   }
                   pb.tiles.push_back(t);
                 }
@@ -790,15 +809,20 @@ static int tc_forward(hyp_model& m, const float* x, int64_t B, bool training, bo
   const int nl = training ? (int)m.layers.size() : m.last_eval_layer + 1;
   float* pack0 = reinterpret_cast<float*>(m.ws + S.pack_off);
   {
-    const TcTensor& tx = S.tt[0];
-    TC_PROF("tc_prep_input_kernel", 12.0 * B * tx.PP * tx.C,
-            (tc_prep_input_kernel<<<tc_grid(B * tx.PP * tx.C), 256, 0, st>>>(x, (int)B, tx.PP, tx.C, tx.Cp, tc_plane0(m, 0),
-                                                                             tc_plane1(m, 0))));
+    for (size_t t = 0; t < m.tensors.size(); t++) {
+      if (!m.tensors[t].external) continue;
+      const Tensor& tn = m.tensors[t];
+      const TcTensor& tx = S.tt[t];
+      TC_PROF("tc_prep_input_kernel", 12.0 * B * tx.PP * tx.C,
+              (tc_prep_input_kernel<<<tc_grid(B * tx.PP * tx.C), 256, 0, st>>>(
+                  x, (int)B, m.d.patch, m.d.channels, tn.x_c0, tn.x_crop, tn.P, tx.C, tx.Cp, tc_plane0(m, (int)t),
+                  tc_plane1(m, (int)t))));
+    }
     TC_PROF("tc_pack_weights_kernel", 12.0 * S.pack_plane_elems,
             (tc_pack_weights_kernel<<<dim3(S.job_blocks, (unsigned)S.jobs.size()), 256, 0, st>>>(
                 S.jobs_dev, m.params, pack0, pack0 + S.pack_plane_elems)));
   }
-  const float keep_prob = 1.f - m.d.drop_out_ratio;
+  const float keep_prob = m.keep_prob;
   float* part = reinterpret_cast<float*>(m.ws + S.part_off);
   for (int li = 0; li < nl; li++) {
     Layer& L = m.layers[li];
@@ -806,11 +830,15 @@ static int tc_forward(hyp_model& m, const float* x, int64_t B, bool training, bo
     const TcTensor& tout = S.tt[L.out_t];
     const int64_t rows = B * tout.PP;
     float* Z = reinterpret_cast<float*>(m.ws + T.z_off);
-    rc = tc_run(m, T.fwd, Z, training ? part : nullptr, L.Cout, EPI_STORE, "tc_gemm_kernel/fwd", layer_flops(L, B), st, L.scope.c_str());
+    rc = tc_run(m, T.fwd, Z, (training && !L.bias_mode) ? part : nullptr, L.Cout, L.share == 2 ? EPI_ACCUM : EPI_STORE,
+                "tc_gemm_kernel/fwd", layer_flops(L, B), st, L.scope.c_str());
     if (rc) return rc;
+    if (L.share == 1) continue;  // the second part adds its product, then bias / activation run once
     float* mean = reinterpret_cast<float*>(m.ws + T.mean_off);
     float* rstd = reinterpret_cast<float*>(m.ws + T.rstd_off);
-    if (training) {
+    if (L.bias_mode) {
+      // no normaliser: mean = 0, rstd = 1 (set at bind), beta = the layer's biases
+    } else if (training) {
       TC_PROF("tc_bn_finalize_kernel", 8.0 * T.stats_rows * L.Cout,
               (tc_bn_finalize8_kernel<<<(unsigned)cdiv(L.Cout, 8), 256, 0, st>>>(
                   part, T.stats_rows, L.Cout, L.Cout, (double)rows, m.d.bn_eps, m.d.bn_decay, m.state + L.mm_off,
@@ -853,23 +881,26 @@ static int tc_backward(hyp_model& m, const uint8_t* labels, int64_t B, float* lo
   float* ce = reinterpret_cast<float*>(m.ws + S.ce_off);
   double* mse_acc = reinterpret_cast<double*>(m.ws + S.mse_off);
   const TcTensor& tlog = S.tt[m.logits_t];
-  const TcTensor& trec = S.tt[m.recon_t];
-  const TcTensor& tx = S.tt[0];
   TC_PROF("tc_ce_loss_kernel", 8.0 * B * d.classes,
           (tc_ce_loss_kernel<<<(unsigned)cdiv(B * 32, 256), 256, 0, st>>>(tc_plane0(m, m.logits_t), tlog.Cp, labels, B,
                                                                           d.classes, ce, tc_grad(m, m.logits_t), tlog.Cp,
                                                                           1.f / (float)B)));
   ginit[m.logits_t] = 1;
-  const int64_t D = (int64_t)tx.PP * tx.C;
-  TC_PROF("tc_mse_kernel", 12.0 * B * D,
-          (tc_mse_kernel<<<tc_grid(B * D), 256, 0, st>>>(tc_plane0(m, m.recon_t), trec.Cp, tc_plane0(m, 0), tx.Cp, (int)B,
-                                                         tx.PP, tx.C, mse_acc, tc_grad(m, m.recon_t), trec.Cp,
-                                                         1.f / (float)(B * D))));
-  ginit[m.recon_t] = 1;
-  loss_finalize_kernel<<<1, 256, 0, st>>>(ce, B, mse_acc, (double)(B * D), loss_out, nullptr);
+  int64_t D = 1;
+  if (m.recon_t >= 0) {  // reconstruction branch (HYPELCNN training graph)
+    const TcTensor& trec = S.tt[m.recon_t];
+    const TcTensor& tx = S.tt[0];
+    D = (int64_t)tx.PP * tx.C;
+    TC_PROF("tc_mse_kernel", 12.0 * B * D,
+            (tc_mse_kernel<<<tc_grid(B * D), 256, 0, st>>>(tc_plane0(m, m.recon_t), trec.Cp, tc_plane0(m, 0), tx.Cp, (int)B,
+                                                           tx.PP, tx.C, mse_acc, tc_grad(m, m.recon_t), trec.Cp,
+                                                           1.f / (float)(B * D))));
+    ginit[m.recon_t] = 1;
+  }
+  loss_finalize_kernel<<<1, 256, 0, st>>>(ce, B, m.recon_t >= 0 ? mse_acc : nullptr, (double)(B * D), loss_out, nullptr);
   HYP_LAUNCHED();
 
-  const float keep_prob = 1.f - d.drop_out_ratio;
+  const float keep_prob = m.keep_prob;
   float* gz0 = reinterpret_cast<float*>(m.ws + S.gz_off);
   float* gz1 = gz0 + S.gz_plane_elems;
   float* bpart = reinterpret_cast<float*>(m.ws + S.bpart_off);
@@ -879,6 +910,7 @@ static int tc_backward(hyp_model& m, const uint8_t* labels, int64_t B, float* lo
     const TcTensor& tout = S.tt[L.out_t];
     const int64_t rows = B * tout.PP;
     if (!ginit[L.out_t]) return fail(HYP_E_STATE, "backward: no gradient reached " + L.scope);
+    if (L.share != 1) {  // share 1: gz of the second part (processed just before) is still in the scratch planes
     TcBnBwdArgs p{};
     p.gout = tc_grad(m, L.out_t); p.ldg = tout.Cp;
     p.z = reinterpret_cast<float*>(m.ws + T.z_off); p.ldz = tout.Cp;
@@ -893,13 +925,13 @@ static int tc_backward(hyp_model& m, const uint8_t* labels, int64_t B, float* lo
     float* s2 = reinterpret_cast<float*>(m.ws + T.s2_off);
     p.s1 = s1; p.s2 = s2; p.gz_hi = gz0; p.gz_lo = gz1; p.ldgz = T.Gp;
     p.gcols = T.kind == 1 ? T.Gp : L.Cout;
-    p.fpad = T.kind == 1 ? T.fpad : 0; p.f = T.f; p.R = T.R;
+    p.fpad = T.kind == 1 ? T.fpad : 0; p.f = T.f; p.R = T.R; p.nt = T.nt; p.ft = T.ft;
     const EwGrid gr = ew_grid2(L.Cout, rows);
     TC_PROF("tc_bn_bwd_reduce_kernel", 8.0 * rows * L.Cout, TC_EW_DISPATCH(gr, tc_bn_bwd_reduce_v4_kernel, p, gr.rpb));
     tc_bn_bwd_finalize8_kernel<<<(unsigned)cdiv(L.Cout, 8), 256, 0, st>>>(bpart, gr.rblocks, L.Cout, (double)rows, s1, s2,
-                                                                         m.grads + L.beta_off);
+                                                                         m.grads + L.beta_off, L.bias_mode ? 1 : 0);
     HYP_LAUNCHED();
-    if (p.fpad == 0 || (p.f % 4 == 0 && p.fpad % 4 == 0)) {
+    if (p.fpad == 0 || (p.f % 4 == 0 && p.ft % 4 == 0 && p.fpad % 4 == 0)) {
       const EwGrid ga = ew_grid2(p.gcols, rows);
       TC_PROF("tc_bn_bwd_apply_kernel", 4.0 * rows * (2.0 * L.Cout + 2.0 * p.gcols),
               TC_EW_DISPATCH(ga, tc_bn_bwd_apply_v4_kernel, p, ga.rpb));
@@ -936,6 +968,7 @@ static int tc_backward(hyp_model& m, const uint8_t* labels, int64_t B, float* lo
                                      ginit[r.src], gs.rpb)));
       }
       ginit[r.src] = 1;
+    }
     }
     int rc = tc_run(m, T.wg, m.grads, nullptr, 0, EPI_ATOMIC, "tc_gemm_kernel/wgrad", layer_flops(L, B), st, L.scope.c_str());
     if (rc) return rc;

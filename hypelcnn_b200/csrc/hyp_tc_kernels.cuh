@@ -14,19 +14,26 @@ __device__ __forceinline__ float tf32_lo(float a) {
   return tf32_rna(a - __uint_as_float(__float_as_uint(a) & 0xffffe000u));
 }
 
-// x [B][PP][C] (NHWC patches as the importer hands them over) -> planes [PP][B][ld]
-__global__ void tc_prep_input_kernel(const float* __restrict__ x, int B, int PP, int C, int ld, float* __restrict__ hi,
-                                     float* __restrict__ lo) {
+// view of x [B][P0][P0][C0] (NHWC patches as the importer hands them over): channels [c0, c0 + C), window cropped
+// by `crop` pixels per side to P x P  -> planes [P*P][B][ld]
+__global__ void tc_prep_input_kernel(const float* __restrict__ x, int B, int P0, int C0, int c0, int crop, int P, int C,
+                                     int ld, float* __restrict__ hi, float* __restrict__ lo) {
+  const int PP = P * P;
   const int64_t total = (int64_t)B * PP * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t bp = i / C;
     const int c = (int)(i - bp * C);
     const int b = (int)(bp / PP), pos = (int)(bp - (int64_t)b * PP);
-    const float v = x[i];
+    const int ph = pos / P, pw = pos - ph * P;
+    const float v = x[(((int64_t)b * P0 + ph + crop) * P0 + pw + crop) * C0 + c0 + c];
     const int64_t o = ((int64_t)pos * B + b) * ld + c;
     hi[o] = v;
     lo[o] = tf32_lo(v);
   }
+}
+__global__ void tc_fill_kernel(float* __restrict__ p, int n, float v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
 }
 
 // position-major [PP][B][ld] -> dense [B][PP][C] (API outputs, tests)
@@ -177,7 +184,8 @@ struct TcBnBwdArgs {
   float *gz_hi, *gz_lo;  // [rows][ldgz]                   (apply)
   int ldgz;
   int gcols;          // columns of gz to write
-  int fpad, f, R;     // level layers: gz column j = slot*fpad + n holds channel (R-1-slot)*f + n; fpad == 0: identity
+  int fpad, f, R;     // level layers: gz column j = slot*fpad + n holds channel q*f + jt*ft + n with
+  int nt, ft;         //   q = R-1 - slot/nt, jt = slot % nt (n < min(ft, f - jt*ft)); fpad == 0: identity
 };
 
 __device__ __forceinline__ float tc_bn_gy(const TcBnBwdArgs& p, int64_t m, int c, float& zhat) {
@@ -256,8 +264,9 @@ __global__ void tc_bn_bwd_apply_kernel(const TcBnBwdArgs p) {
     bool valid = j < p.C;
     if (p.fpad) {
       const int slot = j / p.fpad, n = j - slot * p.fpad;
-      valid = n < p.f && slot < p.R;
-      c = (p.R - 1 - slot) * p.f + n;
+      const int jt = slot % p.nt;
+      valid = slot < p.R * p.nt && n < min(p.ft, p.f - jt * p.ft);
+      c = (p.R - 1 - slot / p.nt) * p.f + jt * p.ft + n;
     }
     float v = 0.f;
     if (valid) {
@@ -385,8 +394,9 @@ __global__ void __launch_bounds__(256) tc_bn_bwd_apply_v4_kernel(const TcBnBwdAr
   bool valid = j0 < p.C;
   if (p.fpad) {
     const int slot = j0 / p.fpad, n = j0 - slot * p.fpad;
-    valid = n < p.f && slot < p.R;
-    c0 = (p.R - 1 - slot) * p.f + n;
+    const int jt = slot % p.nt;
+    valid = slot < p.R * p.nt && n < min(p.ft, p.f - jt * p.ft);
+    c0 = (p.R - 1 - slot / p.nt) * p.f + jt * p.ft + n;
   }
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
   const int64_t r1 = min((int64_t)p.rows, r0 + rows_per_block);
@@ -528,7 +538,7 @@ __global__ void __launch_bounds__(256) tc_bn_finalize8_kernel(const float* __res
 }
 __global__ void __launch_bounds__(256) tc_bn_bwd_finalize8_kernel(const float* __restrict__ part, int nblocks, int C, double rows,
                                                                   float* __restrict__ s1, float* __restrict__ s2,
-                                                                  float* __restrict__ gbeta) {
+                                                                  float* __restrict__ gbeta, int bias_mode) {
   __shared__ double sh1[32][9], sh2[32][9];
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
   const int c = blockIdx.x * 8 + tx;
@@ -544,8 +554,9 @@ __global__ void __launch_bounds__(256) tc_bn_bwd_finalize8_kernel(const float* _
   __syncthreads();
   if (ty == 0 && c < C) {
     for (int i = 1; i < 32; i++) { a1 += sh1[i][tx]; a2 += sh2[i][tx]; }
-    s1[c] = (float)(a1 / rows);
-    s2[c] = (float)(a2 / rows);
+    // bias layers have no batch statistics to differentiate through: gz = g_y, d bias = sum g_y
+    s1[c] = bias_mode ? 0.f : (float)(a1 / rows);
+    s2[c] = bias_mode ? 0.f : (float)(a2 / rows);
     gbeta[c] = (float)a1;
   }
 }

@@ -40,13 +40,17 @@ class PatchEngine:
     (nnmodel/modelconfigs/alg_param_hypelcnn.json) — a missing key raises KeyError exactly
     like the reference's dict lookups."""
 
-    def __init__(self, patch, channels, classes, algorithm_params, max_batch, device=None, precision="3xtf32"):
+    def __init__(self, patch, channels, classes, algorithm_params, max_batch, device=None, precision="3xtf32",
+                 model="hypelcnn"):
         if not torch.cuda.is_available():
             raise N.NativeError(N.HYP_E_CUDA, "no CUDA device: hypelcnn_b200 has no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.patch, self.channels, self.classes = int(patch), int(channels), int(classes)
         self.alg = dict(algorithm_params)
         self.precision = precision
+        if model not in ("hypelcnn", "dualcnn"):
+            raise ValueError(f"unknown model kind {model!r}")
+        self.model = model
         self._handle = ctypes.c_void_p()
         self.global_step = 0
         self._max_batch = 0
@@ -57,6 +61,12 @@ class PatchEngine:
     # ------------------------------------------------------------------ lifecycle
     def _desc(self, max_batch):
         a = self.alg
+        if self.model == "dualcnn":  # nnmodel/modelconfigs/alg_param_dualcnn.json keys
+            return N.ModelDesc(kind=N.HYP_MODEL_DUALCNN, patch=self.patch, channels=self.channels, classes=self.classes,
+                               filter_count=int(a["filter_count"]), spectral_levels=0, spatial_levels=0, degradation=0,
+                               use_residual=0, precision_mode=_PRECISIONS[self.precision], max_batch=max_batch,
+                               reserved=int(a["hs_lidar_diff"]), lrelu_alpha=float(a["lrelu_alpha"]), bn_decay=0.0,
+                               bn_eps=0.0, drop_out_ratio=float(a["drop_out_ratio"]))
         return N.ModelDesc(kind=0, patch=self.patch, channels=self.channels, classes=self.classes,
                            filter_count=int(a["filter_count"]), spectral_levels=int(a["spectral_hierarchy_level"]),
                            spatial_levels=int(a["spatial_hierarchy_level"]), degradation=int(a["degradation_coeff"]),
@@ -144,6 +154,15 @@ class PatchEngine:
         self.adam_m.zero_()
         self.adam_v.zero_()
         self.global_step = 0
+        if self.model == "dualcnn":
+            # slim defaults (nnmodel/DUALCNNModel.py:13-18 sets only the activation): xavier-uniform weights
+            # (limit = sqrt(6 / (fan_in + fan_out)), receptive field included), zero biases [TF-lib]
+            for name, (kind, off, shape) in self.variables.items():
+                if kind == 0:
+                    rf = int(numpy.prod(shape[:-2]))
+                    limit = math.sqrt(6.0 / (rf * shape[-2] + rf * shape[-1]))
+                    self.variable(name).copy_(torch.from_numpy(rng.uniform(-limit, limit, shape).astype(numpy.float32)))
+            return
         for name, (kind, off, shape) in self.variables.items():
             if kind == 0:
                 fan_in = int(numpy.prod(shape[:-1]))
@@ -182,7 +201,7 @@ class PatchEngine:
         B = self._check_x(x)
         logits = torch.empty((B, self.classes), dtype=torch.float32, device=x.device)
         recon = torch.empty((B, self.patch * self.patch * self.channels), dtype=torch.float32,
-                            device=x.device) if is_training else None
+                            device=x.device) if (is_training and self.model == "hypelcnn") else None
         N.check(N.lib().hyp_model_forward(self._handle, _ptr(x), B, int(bool(is_training)), int(bool(update_moving)),
                                           ctypes.c_uint64(seed), _ptr(logits), _ptr(recon), _stream()))
         self._last_x = x  # keep alive until backward
@@ -275,7 +294,7 @@ class PatchEngine:
     def dropout_mask(self, layer_scope, seed, batch):
         width = None
         for nm, (k, o, s) in self.variables.items():
-            if nm == f"nn_core/{layer_scope}/BatchNorm/beta":
+            if nm in (f"nn_core/{layer_scope}/BatchNorm/beta", f"nn_core/{layer_scope}/biases"):
                 width = s[0]
         if width is None:
             raise KeyError(layer_scope)

@@ -78,7 +78,10 @@ int hyp_gather_patches(const void* casi, int casi_dtype, int Hc, int Wc, int C_h
  * (nnmodel/HYPELCNNModel.py:34-99), get_loss_func (:101-112) and optimize_nn
  * (common/common_nn_ops.py:208-240).
  * ------------------------------------------------------------------------------------- */
-enum { HYP_MODEL_HYPELCNN = 0 };
+enum {
+  HYP_MODEL_HYPELCNN = 0, /* nnmodel/HYPELCNNModel.py */
+  HYP_MODEL_DUALCNN = 1   /* nnmodel/DUALCNNModel.py:11-104 (tensor-core engine only) */
+};
 enum {
   HYP_PRECISION_FP32 = 0,    /* fp32 FFMA everywhere (parity mode) */
   HYP_PRECISION_3XTF32 = 1,  /* tcgen05 kind::tf32, hi/lo split, fp32-accurate */
@@ -97,11 +100,12 @@ typedef struct hyp_model_desc {
   int32_t use_residual;     /* "use_residual" */
   int32_t precision_mode;   /* HYP_PRECISION_* */
   int32_t max_batch;        /* largest B any call will pass */
-  int32_t reserved;
+  int32_t reserved;         /* DUALCNN: "hs_lidar_diff" (pixels cropped from each side of the HSI window); else 0 */
   float lrelu_alpha;        /* "lrelu_alpha" */
   float bn_decay;           /* "bn_decay" */
   float bn_eps;             /* slim default 0.001 */
-  float drop_out_ratio;     /* "drop_out_ratio"; keep_prob = 1 - ratio (HYPELCNNModel.py:123) */
+  float drop_out_ratio;     /* "drop_out_ratio"; HYPELCNN: keep_prob = 1 - ratio (HYPELCNNModel.py:123);
+                               DUALCNN: keep_prob = ratio (slim dropout's positional keep_prob, DUALCNNModel.py:49) */
 } hyp_model_desc;
 
 int hyp_model_create(const hyp_model_desc* desc, hyp_model** out);
