@@ -158,7 +158,11 @@ def run_native(args):
     P, C, classes = WORKLOADS[args.workload]
     B = args.batch
     alg = {**ALG, "batch_size": B}
-    eng = E.PatchEngine(P, C, classes, alg, max_batch=B, precision=args.precision)
+    if args.model == "dualcnn":  # BASELINE configs[0] (a parity / plumbing case, not the headline): alg_param_dualcnn.json
+        alg = {"batch_size": B, "drop_out_ratio": 0.70, "learning_rate": 0.0003, "learning_rate_decay_factor": 0.96,
+               "learning_rate_decay_step": 350, "lrelu_alpha": 0.18, "filter_count": 480, "optimizer": "AdamOptimizer",
+               "hs_lidar_diff": 1, "l2regularizer_scale": 0.00001}
+    eng = E.PatchEngine(P, C, classes, alg, max_batch=B, precision=args.precision, model=args.model)
     eng.init_variables(1234)  # same seed on every rank == broadcast initial weights
     rng = numpy.random.default_rng(1234 + rank)
     nb = args.input_batches
@@ -265,17 +269,19 @@ def run_native(args):
                         "avg_launch_ms": d["ms"] / d["launches"], "share_of_step": d["ms"] / total_prof_ms,
                         "peak_source": peaks["source"]}
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.model == "hypelcnn":
         rate, dt, threads = oracle_cpu_rate(args.workload, args.ref_batch, 3, 1)
         cpu = {"value": rate, "unit": "patches/s", "cores": threads, "kind": "port",
                "sample": f"3 train steps of {args.ref_batch} patches on the CPU oracle ({dt:.1f} s)"}
-    step_tflops = FWD_BWD_MFLOP[args.workload] * 1e6 * B * world / (ms / args.steps / 1e3) / 1e12
+    step_flops = FWD_BWD_MFLOP[args.workload] * 1e6 * B if args.model == "hypelcnn" else \
+        sum(r["flops"] for r in prof.values()) / args.steps  # useful FLOPs of the step's GEMM launches
+    step_tflops = step_flops * world / (ms / args.steps / 1e3) / 1e12
     line = {
         "metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": {"fp32": "f32", "3xtf32": "tf32x3", "bf16": "bf16"}[args.precision],
         "data": "synthetic",
-        "config": {"workload": args.workload, "per_gpu_batch": B, "global_batch": B * world, "patch": P, "channels": C,
+        "config": {"workload": args.workload + ("" if args.model == "hypelcnn" else "/" + args.model), "per_gpu_batch": B, "global_batch": B * world, "patch": P, "channels": C,
                    "classes": classes, "precision_mode": args.precision,
                    "parallelism": f"dp{world}: 1 NCCL all-reduce of {eng.params.numel()} fp32 grads/step" if world > 1 else "single GPU",
                    "l2": f"per-step working set {eng.workspace_bytes / 1e9:.1f} GB >> 126 MB L2; inputs rotate over "
@@ -306,6 +312,8 @@ def main():
     ap.add_argument("--input-batches", type=int, default=4)
     ap.add_argument("--precision", default="3xtf32", choices=["fp32", "3xtf32"],
                     help="3xtf32: tcgen05 tensor-core engine (fp32-accurate split); fp32: FFMA engine")
+    ap.add_argument("--model", default="hypelcnn", choices=["hypelcnn", "dualcnn"],
+                    help="hypelcnn = the headline metric; dualcnn = BASELINE configs[0] on the same engine (no CPU arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: one blocking all-reduce after backward instead "
                     "of reducing the FC/decoder gradients while the conv layers are still going backward")
