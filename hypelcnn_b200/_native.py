@@ -77,6 +77,8 @@ _PROTOS = {
     "hyp_model_loss_backward": (_I, [_P, _P, _P, _L, _P, _P]),
     "hyp_model_set_grad_notify": (_I, [_P, _L, _P]),
     "hyp_adam_step": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _L, _F, _P]),
+    "hyp_momentum_step": (_I, [_P, _P, _P, _L, _F, _F, _F, _P]),
+    "hyp_augment_patches": (_I, [_P, _P, _L, _I, _I, _I, _I, _F, ctypes.c_uint64, _P, _P, _P]),
     "hyp_argmax_confusion": (_I, [_P, _P, _L, _I, _P, _P, _P]),
     "hyp_scatter_class_map": (_I, [_P, _P, _L, _I, _I, _P, _P]),
     "hyp_model_debug_tensor": (_I, [_P, ctypes.c_char_p, _I, ctypes.POINTER(_P), ctypes.POINTER(_L)]),

@@ -215,9 +215,44 @@ class DeviceBatchIterator:
         return self.images.index_select(0, idx), self.labels.index_select(0, idx)
 
 
+class AugmentingIterator:
+    """add_augmentation_graph (:376-394) on the device: every training batch goes through hyp_augment_patches
+    (rotation, reflection, spectral offset — one random draw per sample, as the reference's per-sample tf.data maps).
+    The shadow map needs a trained GAN generator (gan/gan_utilities.py); it is applied when
+    ``augmentation_info.shadow_struct`` carries a callable ``shadow_op`` taking / returning a batch."""
+
+    def __init__(self, inner, augmentation_info, seed=1234):
+        self.inner, self.info, self.seed, self.calls = inner, augmentation_info, seed, 0
+        self.initializer = inner.initializer
+
+    def get_next(self):
+        images, labels = self.inner.get_next()
+        info = self.info
+        self.calls += 1
+        if info.perform_shadow_augmentation and info.shadow_struct is not None:
+            gen = torch.Generator(device="cpu")
+            gen.manual_seed(self.seed * 7919 + self.calls)
+            pick = (torch.rand(images.shape[0], generator=gen) < info.augmentation_random_threshold).to(images.device)
+            if bool(pick.any()):
+                images = torch.where(pick.view(-1, 1, 1, 1), info.shadow_struct.shadow_op(images), images)
+        if info.perform_rotation_augmentation or info.perform_reflection_augmentation or \
+                info.perform_spectral_augmentation:
+            spectral = float(info.perform_spectral_augmentation) if info.perform_spectral_augmentation else 0.0
+            images = E.augment_patches(images.contiguous(), info.perform_rotation_augmentation,
+                                       info.perform_reflection_augmentation, spectral, self.seed + self.calls)
+        return images, labels
+
+
 def training_nn_iterator(data_set, augmentation_info, batch_size, num_epochs, device, prefetch_size):
     images, labels = data_set
-    return DeviceBatchIterator(images, labels, batch_size, True, num_epochs)
+    it = DeviceBatchIterator(images, labels, batch_size, True, num_epochs)
+    if augmentation_info is not None and (augmentation_info.perform_rotation_augmentation or
+                                          augmentation_info.perform_reflection_augmentation or
+                                          augmentation_info.perform_spectral_augmentation or
+                                          (augmentation_info.perform_shadow_augmentation and
+                                           augmentation_info.shadow_struct is not None)):
+        return AugmentingIterator(it, augmentation_info)
+    return it
 
 
 def simple_nn_iterator(data_set, batch_size):

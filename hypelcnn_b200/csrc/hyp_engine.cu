@@ -930,6 +930,32 @@ int hyp_adam_step(float* params, const float* grads, float* mbuf, float* vbuf, i
   return HYP_OK;
 }
 
+int hyp_momentum_step(float* params, const float* grads, float* accum, int64_t n, float lr, float momentum,
+                      float grad_scale, void* stream) {
+  HYP_CHECK_ARG(params && grads && accum, "null argument");
+  HYP_CHECK_ARG(n >= 0, "n >= 0 required");
+  if (n == 0) return HYP_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PROF("momentum_kernel", 20.0 * n,
+       (momentum_kernel<<<ew_grid(n), 256, 0, st>>>(params, grads, accum, n, lr, momentum, grad_scale)));
+  return HYP_OK;
+}
+
+int hyp_augment_patches(const float* in, float* out, int64_t B, int patch, int channels, int do_rotation,
+                        int do_reflection, float spectral, uint64_t seed, uint8_t* choices_out, float* deltas_out,
+                        void* stream) {
+  HYP_CHECK_ARG(in && out && in != out, "in / out must be distinct non-null buffers");
+  HYP_CHECK_ARG(B >= 0 && patch >= 1 && channels >= 1 && spectral >= 0.f, "bad shape");
+  HYP_CHECK_ARG(B <= INT32_MAX, "too many patches for one call");
+  if (B == 0) return HYP_OK;
+  AugmentArgs a;
+  a.in = in; a.out = out; a.B = B; a.P = patch; a.C = channels; a.do_rot = do_rotation != 0; a.do_flip = do_reflection != 0;
+  a.spectral = spectral; a.seed = seed; a.choices = choices_out; a.deltas = deltas_out;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PROF("augment_kernel", 8.0 * B * patch * patch * channels, (augment_kernel<<<(unsigned)B, 256, 0, st>>>(a)));
+  return HYP_OK;
+}
+
 int hyp_argmax_confusion(const float* logits, const uint8_t* labels, int64_t B, int classes, uint8_t* pred,
                          int32_t* confusion, void* stream) {
   HYP_CHECK_ARG(logits && (pred || confusion), "null argument");

@@ -270,6 +270,63 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// tf MomentumOptimizer (use_nesterov = False): accum = momentum * accum + g;  p -= lr * accum
+__global__ void momentum_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ accum, int64_t n,
+                                float lr, float momentum, float gscale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float a = momentum * accum[i] + g[i] * gscale;
+    accum[i] = a;
+    p[i] = p[i] - lr * a;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Training-time augmentation of a batch of patches (common/common_nn_ops.py:397-440), one random draw per
+// SAMPLE as in the reference's tf.data map: rot90 by k in {0,1,2} (counter-clockwise, tf.image.rot90), random
+// left-right / up-down flips, and a per-channel spectral offset delta[c] ~ U(-s, 0) added to every pixel.
+// The geometric part is an index permutation, the spectral part one fp32 add.  choices [B][4] (uint8: k,
+// flip_lr, flip_ud, 0) and deltas [B][C] are written so that a caller (the parity tests) can replay the draw.
+struct AugmentArgs {
+  const float* in;
+  float* out;
+  int64_t B;
+  int P, C;
+  int do_rot, do_flip;
+  float spectral;  // s; 0 = off
+  uint64_t seed;
+  uint8_t* choices;  // nullable
+  float* deltas;     // nullable
+};
+__global__ void augment_kernel(const AugmentArgs a) {
+  const int64_t b = blockIdx.x;
+  const int P = a.P, C = a.C;
+  const int k = a.do_rot ? min(2, (int)(philox_uniform(a.seed, 0x41u, (uint64_t)b * 4 + 0) * 3.f)) : 0;
+  const int flr = a.do_flip ? (philox_uniform(a.seed, 0x41u, (uint64_t)b * 4 + 1) < 0.5f) : 0;
+  const int fud = a.do_flip ? (philox_uniform(a.seed, 0x41u, (uint64_t)b * 4 + 2) < 0.5f) : 0;
+  if (threadIdx.x == 0 && a.choices) {
+    a.choices[b * 4 + 0] = (uint8_t)k; a.choices[b * 4 + 1] = (uint8_t)flr; a.choices[b * 4 + 2] = (uint8_t)fud;
+    a.choices[b * 4 + 3] = 0;
+  }
+  const float* src = a.in + b * P * P * C;
+  float* dst = a.out + b * P * P * C;
+  for (int i = threadIdx.x; i < P * P * C; i += blockDim.x) {
+    const int pos = i / C, c = i - pos * C;
+    int r = pos / P, q = pos - r * P;             // output pixel (row, col)
+    if (fud) r = P - 1 - r;                       // undo tf.image.flip_up_down
+    if (flr) q = P - 1 - q;                       // undo tf.image.flip_left_right
+    int sr = r, sq = q;                           // undo rot90: R1[i,j] = in[j, P-1-i], R2[i,j] = in[P-1-i, P-1-j]
+    if (k == 1) { sr = q; sq = P - 1 - r; }
+    else if (k == 2) { sr = P - 1 - r; sq = P - 1 - q; }
+    float v = src[(sr * P + sq) * C + c];
+    if (a.spectral > 0.f) {
+      const float d = -a.spectral * philox_uniform(a.seed, 0x42u, (uint64_t)b * C + c);
+      if (a.deltas && pos == 0) a.deltas[b * C + c] = d;
+      v = v + d;
+    }
+    dst[i] = v;
+  }
+}
+
 // tf.argmax (first maximum) + confusion[label, pred] += 1
 __global__ void argmax_confusion_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ labels,
                                         int64_t B, int classes, uint8_t* __restrict__ pred,

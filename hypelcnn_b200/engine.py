@@ -238,9 +238,19 @@ class PatchEngine:
         return a["learning_rate"] * a["learning_rate_decay_factor"] ** (s // a["learning_rate_decay_step"])
 
     def adam_step(self, lr=None, grad_scale=1.0, b1=0.9, b2=0.999, eps=1e-8):
-        if self.alg.get("optimizer", "AdamOptimizer") != "AdamOptimizer":
-            raise N.NativeError(N.HYP_E_UNSUPPORTED, "only AdamOptimizer is built")
+        """The optimizer step of optimize_nn (common/common_nn_ops.py:223-232): "AdamOptimizer" or
+        ["MomentumOptimizer", momentum] as the JSON's "optimizer" value."""
+        opt = self.alg.get("optimizer", "AdamOptimizer")
         lr = self.learning_rate() if lr is None else lr
+        if isinstance(opt, (tuple, list)):
+            if opt[0] != "MomentumOptimizer":
+                raise N.NativeError(N.HYP_E_UNSUPPORTED, f"optimizer {opt[0]!r} is not one the reference selects")
+            N.check(N.lib().hyp_momentum_step(_ptr(self.params), _ptr(self.grads), _ptr(self.adam_m),
+                                              self.params.numel(), lr, float(opt[1]), grad_scale, _stream()))
+            self.global_step += 1
+            return
+        if opt != "AdamOptimizer":
+            raise N.NativeError(N.HYP_E_UNSUPPORTED, f"optimizer {opt!r} is not one the reference selects")
         N.check(N.lib().hyp_adam_step(_ptr(self.params), _ptr(self.grads), _ptr(self.adam_m), _ptr(self.adam_v),
                                       self.params.numel(), lr, b1, b2, eps, self.global_step + 1, grad_scale,
                                       _stream()))
@@ -310,6 +320,19 @@ def adam_step(params, grads, m, v, lr, t, grad_scale=1.0, b1=0.9, b2=0.999, eps=
         require_cuda(t_, name, torch.float32)
     N.check(N.lib().hyp_adam_step(_ptr(params), _ptr(grads), _ptr(m), _ptr(v), params.numel(), lr, b1, b2, eps, t,
                                   grad_scale, _stream()))
+
+
+def augment_patches(x, rotation=False, reflection=False, spectral=0.0, seed=0, return_draw=False):
+    """Device-side form of the reference's augmentation maps (common/common_nn_ops.py:397-440); one random draw per
+    sample.  -> augmented [B,P,P,C] (and (choices uint8 [B,4], deltas [B,C]) with return_draw)."""
+    require_cuda(x, "x", torch.float32)
+    B, P, _, C = x.shape
+    out = torch.empty_like(x)
+    choices = torch.zeros((B, 4), dtype=torch.uint8, device=x.device) if return_draw else None
+    deltas = torch.zeros((B, C), dtype=torch.float32, device=x.device) if return_draw else None
+    N.check(N.lib().hyp_augment_patches(_ptr(x), _ptr(out), B, P, C, int(bool(rotation)), int(bool(reflection)),
+                                        float(spectral), ctypes.c_uint64(seed), _ptr(choices), _ptr(deltas), _stream()))
+    return (out, choices, deltas) if return_draw else out
 
 
 def argmax_confusion(logits, labels=None, confusion=None):

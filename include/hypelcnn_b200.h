@@ -155,6 +155,20 @@ int hyp_adam_step(float* params, const float* grads, float* m, float* v, int64_t
                   float lr, float b1, float b2, float eps, int64_t t, float grad_scale,
                   void* stream);
 
+/* tf MomentumOptimizer (optimize_nn's second branch, common/common_nn_ops.py:223-227, use_nesterov = False):
+ * accum = momentum * accum + g;  p -= lr * accum.  g = grads*grad_scale. */
+int hyp_momentum_step(float* params, const float* grads, float* accum, int64_t n, float lr, float momentum,
+                      float grad_scale, void* stream);
+
+/* Training-time augmentation of a batch [B,P,P,C] (common/common_nn_ops.py:397-440, pinned to /cpu:0 and run per
+ * sample inside tf.data in the reference): rot90 by k in {0,1,2} (tf.image.rot90, counter-clockwise), random
+ * left-right / up-down flips, per-channel spectral offset U(-spectral, 0) — one draw per sample, Philox keyed by
+ * (seed, sample).  choices_out (nullable) uint8 [B,4] = (k, flip_lr, flip_ud, 0) and deltas_out (nullable) float
+ * [B,C] receive the draw.  in and out must not alias. */
+int hyp_augment_patches(const float* in, float* out, int64_t B, int patch, int channels, int do_rotation,
+                        int do_reflection, float spectral, uint64_t seed, uint8_t* choices_out, float* deltas_out,
+                        void* stream);
+
 /* tf.argmax (lowest index on ties) + tf.math.confusion_matrix accumulation
  * (common/common_nn_ops.py:246-262, :318).  labels/confusion nullable.
  * confusion: int32 [classes,classes], rows = labels, += semantics. */

@@ -137,3 +137,21 @@ def scatter_class_map(scene_shape, targets, predictions, fill=255):
     for t, p in zip(targets, predictions):
         img[t[1], t[0]] = p
     return img
+
+
+def augment_patches(x, choices, deltas=None):
+    """Replay of the reference's per-sample augmentation maps (common/common_nn_ops.py:397-440) for a given draw:
+    choices[b] = (k, flip_lr, flip_ud): tf.image.rot90(img, k) (counter-clockwise == numpy.rot90 on the H, W axes),
+    then tf.image.flip_left_right / flip_up_down, then img + delta[b] (broadcast over pixels, :428-431)."""
+    out = numpy.empty_like(x)
+    for b in range(x.shape[0]):
+        k, flr, fud = int(choices[b][0]), int(choices[b][1]), int(choices[b][2])
+        img = numpy.rot90(x[b], k, axes=(0, 1))
+        if flr:
+            img = img[:, ::-1, :]
+        if fud:
+            img = img[::-1, :, :]
+        if deltas is not None:
+            img = img + deltas[b][None, None, :]
+        out[b] = img
+    return out
