@@ -956,6 +956,27 @@ int hyp_augment_patches(const float* in, float* out, int64_t B, int patch, int c
   return HYP_OK;
 }
 
+int hyp_gan_generator_forward(const float* in, int ld_in, float* out, int ld_out, int64_t rows, int bands,
+                              int copy_extra, const float* weights, int encoder_only, int clip_invalid_values,
+                              int is_shadow_graph, void* stream) {
+  HYP_CHECK_ARG(in && out && weights, "null argument");
+  HYP_CHECK_ARG(bands >= 8 && bands <= GAN_MAX_C, "bands out of range (8..512)");
+  HYP_CHECK_ARG(rows >= 0 && copy_extra >= 0 && ld_in >= bands + copy_extra && ld_out >= bands + copy_extra, "bad shape");
+  if (rows == 0) return HYP_OK;
+  GanGenArgs a;
+  a.in = in; a.out = out; a.rows = rows; a.C = bands; a.ld_in = ld_in; a.ld_out = ld_out; a.copy_extra = copy_extra;
+  a.weights = weights; a.nlayers = encoder_only ? 4 : 7; a.clip = clip_invalid_values != 0; a.is_shadow = is_shadow_graph != 0;
+  const int K[7] = {bands, bands / 2, bands / 4, bands / 8, bands / 4, bands / 2, bands};
+  int nw = 0;
+  for (int l = 0; l < a.nlayers; l++) nw += K[l] + 1;
+  const size_t smem = (size_t)(((nw + 3) & ~3) + 4 * 3 * bands) * sizeof(float);
+  const unsigned grid = (unsigned)std::min<int64_t>(cdiv(rows, 4), 148 * 16);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PROF("gan_generator_fwd_kernel", 4.0 * rows * (ld_in + ld_out),
+       (gan_generator_fwd_kernel<<<grid, 128, smem, st>>>(a)));
+  return HYP_OK;
+}
+
 int hyp_argmax_confusion(const float* logits, const uint8_t* labels, int64_t B, int classes, uint8_t* pred,
                          int32_t* confusion, void* stream) {
   HYP_CHECK_ARG(logits && (pred || confusion), "null argument");

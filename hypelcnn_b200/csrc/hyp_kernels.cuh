@@ -327,6 +327,83 @@ __global__ void augment_kernel(const AugmentArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Shadow GAN generator, forward (gan/shadow_data_models.py:43-90): per spectrum x[C] seven 1-filter conv1d layers
+// (SAME, kernel sizes C, C/2, C/4, C/8, C/4, C/2, C; bias; leaky_relu 0.1) with the dense residual pattern
+// net_i = conv(net_{i-1}) + net_{i-1} + net_{i-2}; the last layer is tanh without residual; encoder-only stops
+// after net4.  One warp per spectrum: the three live activations sit in shared memory (C floats each), the <= 239
+// weights of the model in shared memory per block.  `rows` spectra of `C` bands at stride ld_in / ld_out; extra
+// channels (the LiDAR band of a patch pixel, create_gan_struct gan/gan_utilities.py:31-35) are copied through.
+// clip (create_inference_for_matrix_input, gan/wrappers/gan_common.py:282-304): keep the input unless the
+// generated mean is lower (is_shadow) / higher (deshadow) than the input mean.
+struct GanGenArgs {
+  const float* in;
+  float* out;
+  int64_t rows;
+  int C, ld_in, ld_out, copy_extra;  // copy_extra: channels after the C bands copied unchanged
+  const float* weights;              // net1 w[K1] b, net2 w[K2] b, ... in layer order
+  int nlayers;                       // 7 full generator, 4 encoder only
+  int clip, is_shadow;
+};
+constexpr int GAN_MAX_C = 512;
+__global__ void __launch_bounds__(128) gan_generator_fwd_kernel(const GanGenArgs a) {
+  extern __shared__ float sm[];
+  const int C = a.C;
+  int K[7];
+  K[0] = C; K[1] = C / 2; K[2] = C / 4; K[3] = C / 8; K[4] = C / 4; K[5] = C / 2; K[6] = C;
+  int nw = 0;
+  for (int l = 0; l < a.nlayers; l++) nw += K[l] + 1;
+  float* w = sm;                                 // [nw]
+  float* act = sm + ((nw + 3) & ~3);             // [warps][3][C]
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) w[i] = a.weights[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float* buf = act + warp * 3 * C;
+  for (int64_t r = (int64_t)blockIdx.x * nwarps + warp; r < a.rows; r += (int64_t)gridDim.x * nwarps) {
+    const float* xin = a.in + r * a.ld_in;
+    float* xout = a.out + r * a.ld_out;
+    float* p2 = buf;          // net_{i-2}
+    float* p1 = buf + C;      // net_{i-1}
+    float* cur = buf + 2 * C;
+    float in_sum = 0.f;
+    for (int c = lane; c < C; c += 32) { const float v = xin[c]; p1[c] = v; p2[c] = 0.f; in_sum += v; }
+    __syncwarp();
+    const float* wl = w;
+    for (int l = 0; l < a.nlayers; l++) {
+      const int k = K[l], left = (k - 1) / 2;  // SAME: total pad k-1, the extra one on the right (App. A.12)
+      const float bias = wl[k];
+      const bool last = l == 6;
+      for (int c = lane; c < C; c += 32) {
+        float s = bias;
+        const int t0 = max(0, left - c), t1 = min(k, C + left - c);
+        for (int t = t0; t < t1; t++) s += wl[t] * p1[c + t - left];
+        if (last) s = tanhf(s);
+        else {
+          s = fmaxf(s, 0.1f * s);
+          s += p1[c];
+          if (l > 0) s += p2[c];              // net1 = conv + net0 only
+        }
+        cur[c] = s;
+      }
+      __syncwarp();
+      float* t = p2; p2 = p1; p1 = cur; cur = t;
+      wl += k + 1;
+    }
+    // p1 = result
+    bool keep_generated = true;
+    if (a.clip) {
+      float gs = 0.f;
+      for (int c = lane; c < C; c += 32) gs += p1[c];
+      gs = warp_sum(gs);
+      in_sum = warp_sum(in_sum);
+      keep_generated = a.is_shadow ? (gs < in_sum) : (gs > in_sum);  // means over the same C bands
+    }
+    for (int c = lane; c < C; c += 32) xout[c] = keep_generated ? p1[c] : xin[c];
+    for (int c = lane; c < a.copy_extra; c += 32) xout[C + c] = xin[C + c];
+    __syncwarp();
+  }
+}
+
 // tf.argmax (first maximum) + confusion[label, pred] += 1
 __global__ void argmax_confusion_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ labels,
                                         int64_t B, int classes, uint8_t* __restrict__ pred,

@@ -1,0 +1,71 @@
+"""Shadow augmenter structs handed to the classifier's input pipeline (reference: gan/gan_utilities.py:7-43).
+Same names; the ops take and return device batches [B,P,P,C+1] (HSI bands + LiDAR) instead of one tf sample."""
+import numpy
+import torch
+
+from hypelcnn_b200.gan.wrappers.gan_common import create_inference_for_matrix_input
+
+
+class ShadowOpHolder:
+
+    def __init__(self, shadow_op, deshadow_op, shadow_op_creater, shadow_op_initializer) -> None:
+        super().__init__()
+        self.shadow_op_initializer = shadow_op_initializer
+        self.shadow_op_creater = shadow_op_creater
+        self.shadow_op = shadow_op
+        self.deshadow_op = deshadow_op
+
+
+def create_simple_shadow_struct(shadow_ratio):
+    """Division / multiplication by the per-band shadow ratio, LiDAR (last channel) by 1 (:18-28)."""
+    ratio = numpy.append(numpy.asarray(shadow_ratio, dtype=numpy.float32), numpy.float32(1))
+
+    def _ratio_on(inp):
+        return torch.as_tensor(ratio, device=inp.device)
+
+    def simple_shadow_func(inp):
+        return inp / _ratio_on(inp)
+
+    def simple_deshadow_func(inp):
+        return inp * _ratio_on(inp)
+
+    return ShadowOpHolder(shadow_op=simple_shadow_func, deshadow_op=simple_deshadow_func,
+                          shadow_op_creater=lambda: None, shadow_op_initializer=lambda restorer, session: None)
+
+
+class GeneratorInferenceWrapper:
+    """The InferenceWrapper slice create_gan_struct needs (gan/wrappers/wrapper.py:21-38): a forward (x -> y,
+    "shadow") and a backward generator with frozen weights, construct_inference_graph over a [B,H,W,C] matrix."""
+
+    def __init__(self, forward_generator, backward_generator):
+        self.forward_generator, self.backward_generator = forward_generator, backward_generator
+
+    def construct_inference_graph(self, input_tensor, is_shadow_graph, clip_invalid_values, copy_extra=0):
+        gen = self.forward_generator if is_shadow_graph else self.backward_generator
+        return create_inference_for_matrix_input(input_tensor, is_shadow_graph, clip_invalid_values, gen, copy_extra)
+
+    def create_generator_restorer(self):
+        return self  # restorer.restore(values) loads {"ModelX2Y/.../net1/weights": ...}-style dicts
+
+    def restore(self, forward_values=None, backward_values=None):
+        if forward_values is not None:
+            self.forward_generator.load(forward_values)
+        if backward_values is not None:
+            self.backward_generator.load(backward_values)
+
+
+def create_gan_struct(gan_inference_wrapper, model_base_dir=None, ckpt_relative_path=None):
+    """Reference: gan/gan_utilities.py:30-43.  The LiDAR channel is stripped, every pixel of the patch goes through
+    the (frozen) generator, the LiDAR channel is appended again — done inside one kernel launch."""
+
+    def _build_shadowed_inference_graph(input_data, is_shadow_graph):
+        return gan_inference_wrapper.construct_inference_graph(input_data, is_shadow_graph=is_shadow_graph,
+                                                               clip_invalid_values=False, copy_extra=1)
+
+    def _initializer(restorer, values):
+        restorer.restore(*values)
+
+    return ShadowOpHolder(shadow_op=lambda x: _build_shadowed_inference_graph(x, True),
+                          deshadow_op=lambda x: _build_shadowed_inference_graph(x, False),
+                          shadow_op_creater=gan_inference_wrapper.create_generator_restorer,
+                          shadow_op_initializer=_initializer)

@@ -169,6 +169,16 @@ int hyp_augment_patches(const float* in, float* out, int64_t B, int patch, int c
                         int do_reflection, float spectral, uint64_t seed, uint8_t* choices_out, float* deltas_out,
                         void* stream);
 
+/* Shadow GAN generator, forward only (gan/shadow_data_models.py:43-90; the frozen augmenter of
+ * gan/gan_utilities.py:18-43 and create_inference_for_matrix_input, gan/wrappers/gan_common.py:282-304).
+ * rows spectra of `bands` channels at row strides ld_in / ld_out; `copy_extra` channels after the bands (the LiDAR
+ * channel of a patch pixel) are copied through.  weights: net1 w[K1], b, net2 w[K2], b, ... (K = bands, /2, /4, /8,
+ * /4, /2, bands; 4 layers when encoder_only).  clip_invalid_values: keep the input spectrum unless the generated mean
+ * is lower (is_shadow_graph) / higher than the input mean. */
+int hyp_gan_generator_forward(const float* in, int ld_in, float* out, int ld_out, int64_t rows, int bands,
+                              int copy_extra, const float* weights, int encoder_only, int clip_invalid_values,
+                              int is_shadow_graph, void* stream);
+
 /* tf.argmax (lowest index on ties) + tf.math.confusion_matrix accumulation
  * (common/common_nn_ops.py:246-262, :318).  labels/confusion nullable.
  * confusion: int32 [classes,classes], rows = labels, += semantics. */

@@ -1,0 +1,62 @@
+"""CPU ORACLE (test infrastructure, NOT product code) — shadow GAN generator forward.
+
+Restates gan/shadow_data_models.py:43-90 in numpy (float64 or float32): seven slim convolution1d layers with one
+filter (SAME padding: total pad K-1, left = (K-1)//2; bias; leaky_relu 0.1), the dense residual
+pattern net_i = conv(net_{i-1}) + net_{i-1} + net_{i-2} (net1: + net0 only), tanh and no residual on net7;
+encoder-only stops after net4 (:75).  Parity with TensorFlow is unpinned (no TF here); the reference's DummySampler
+fixture (gan/gan_sampling_methods.py:191-201) gives the known answers used in tests/test_gpu_gan.py.
+Only tests/ imports this module."""
+import numpy
+
+
+def kernel_sizes(bands, encoder_only=False):
+    k = bands
+    s = [k, k // 2, k // 4, k // 8]
+    return s if encoder_only else s + [k // 4, k // 2, k]
+
+
+def conv1d_same(x, w, b):
+    """x [N,C], one filter w [K], SAME zero padding, stride 1."""
+    K, C = len(w), x.shape[1]
+    left = (K - 1) // 2
+    xp = numpy.zeros((x.shape[0], C + K - 1), dtype=x.dtype)
+    xp[:, left:left + C] = x
+    out = numpy.full(x.shape, b, dtype=x.dtype)
+    for t in range(K):
+        out += w[t] * xp[:, t:t + C]
+    return out
+
+
+def generator_forward(x, variables, encoder_only=False):
+    """x [N,C]; variables {"net1/weights": [K,1,1], "net1/biases": [1], ...} -> [N,C]."""
+    dt = x.dtype
+    nets = [x]
+    sizes = kernel_sizes(x.shape[1], encoder_only)
+    for i, k in enumerate(sizes):
+        w = numpy.asarray(variables[f"net{i + 1}/weights"], dtype=dt).reshape(-1)
+        b = dt.type(numpy.asarray(variables[f"net{i + 1}/biases"]).reshape(-1)[0])
+        assert len(w) == k
+        y = conv1d_same(nets[-1], w, b)
+        if i == 6:
+            y = numpy.tanh(y)
+        else:
+            y = numpy.maximum(y, dt.type(0.1) * y) + nets[-1]
+            if i > 0:
+                y = y + nets[-2]
+        nets.append(y)
+    return nets[-1]
+
+
+def inference_for_matrix_input(x, variables, is_shadow, clip, copy_extra=0):
+    """create_inference_for_matrix_input (gan/wrappers/gan_common.py:282-304) + LiDAR pass-through
+    (gan/gan_utilities.py:31-35) on [B,H,W,C(+extra)]."""
+    C = x.shape[3] - copy_extra
+    rows = x.reshape(-1, x.shape[3])
+    gen = generator_forward(rows[:, :C].copy(), variables)
+    if clip:
+        gm, im = gen.mean(axis=1), rows[:, :C].mean(axis=1)
+        keep = (gm < im) if is_shadow else (gm > im)
+        gen = numpy.where(keep[:, None], gen, rows[:, :C])
+    out = rows.copy()
+    out[:, :C] = gen
+    return out.reshape(x.shape)
