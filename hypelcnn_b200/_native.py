@@ -16,7 +16,7 @@ HYP_OK, HYP_E_INVALID, HYP_E_CUDA, HYP_E_STATE, HYP_E_UNSUPPORTED = 0, -1, -2, -
 HYP_DT_F32, HYP_DT_U16 = 0, 1
 HYP_GATHER_SAME_RES, HYP_GATHER_GRSS2018 = 0, 1
 HYP_PRECISION_FP32, HYP_PRECISION_3XTF32, HYP_PRECISION_BF16 = 0, 1, 2
-HYP_MODEL_HYPELCNN, HYP_MODEL_DUALCNN = 0, 1
+HYP_MODEL_HYPELCNN, HYP_MODEL_DUALCNN, HYP_MODEL_CONCNN = 0, 1, 2
 
 
 class NativeError(RuntimeError):

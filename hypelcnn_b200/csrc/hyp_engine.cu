@@ -74,6 +74,7 @@ struct Layer {
   // pre-activation buffer and one weight variable: share = 1 first part (GEMM only), 2 second part (accumulates
   // into the first part's z, then bias / activation / dropout)
   int share = 0;
+  bool lrn = false;  // tf.nn.local_response_normalization (TF defaults) after the activation (CONCNNModel.py:37,41)
 };
 
 namespace tc {
@@ -369,6 +370,47 @@ static int build_dualcnn(hyp_model& m) {
     m.logits_t = L.out_t;
     m.last_eval_layer = (int)m.layers.size() - 1;
   }
+  return HYP_OK;
+}
+
+// CONCNNModel (nnmodel/CONCNNModel.py:23-64): 1x1 / 3x3 / 5x5 convs concatenated -> LRN -> eight 1x1 convs (LRN after
+// the first, identity residuals net13 += net11, net22 += net13, dropout after conv31 / conv32) -> flatten -> FC.
+// slim defaults: ReLU (the caller passes lrelu_alpha = 0), biases, no BatchNorm; dropout keep_prob = drop_out_ratio.
+static int build_concnn(hyp_model& m) {
+  const hyp_model_desc& d = m.d;
+  Builder b(m);
+  const int P = d.patch, F = d.filter_count;
+  if (3 * F > 512) return fail(HYP_E_UNSUPPORTED, "CONCNN: filter_count above 170 (the LRN kernels keep 3 rows of 3*F channels per warp in shared memory)");
+  m.keep_prob = d.drop_out_ratio;
+  const int x = b.add_tensor("x", d.channels, P * P, true);
+  int cur;
+  {
+    Layer& L = b.add_layer("conv0", false, P, x, "net0_out", F, {1, 3, 5}, {"conv0_1x1", "conv0_3x3", "conv0_5x5"},
+                           ACT_LRELU, false);
+    L.bias_mode = true; L.lrn = true;
+    cur = L.out_t;
+  }
+  const int C1 = 3 * F;
+  bool res_failed = false;
+  auto conv = [&](const std::string& name, int in_t, bool lrn, bool dropout, int res_src) -> int {
+    Layer& L = b.add_layer(name, false, P, in_t, name, C1, {1}, {name}, ACT_LRELU, dropout);
+    L.bias_mode = true; L.lrn = lrn;
+    if (res_src >= 0 && b.add_resid(L, res_src)) res_failed = true;
+    return L.out_t;
+  };
+  const int net11 = conv("conv11", cur, true, false, -1);
+  const int net12 = conv("conv12", net11, false, false, -1);
+  const int net13 = conv("conv13", net12, false, false, net11);   // net13 = net13 + net11   (:45)
+  const int net21 = conv("conv21", net13, false, false, -1);
+  const int net22 = conv("conv22", net21, false, false, net13);   // net22 = net22 + net13   (:50)
+  const int net31 = conv("conv31", net22, false, true, -1);
+  const int net32 = conv("conv32", net31, false, true, -1);
+  const int net33 = conv("conv33", net32, false, false, -1);
+  if (res_failed) return fail(HYP_E_INVALID, "residual table");
+  Layer& L = b.add_layer("fc", true, 1, net33, "fc", d.classes, {1}, {"fc"}, ACT_NONE, false);
+  L.bias_mode = true;
+  m.logits_t = L.out_t;
+  m.last_eval_layer = (int)m.layers.size() - 1;
   return HYP_OK;
 }
 
@@ -753,9 +795,10 @@ int hyp_profile_get(int idx, char name[64], double* total_ms, int64_t* launches,
 
 int hyp_model_create(const hyp_model_desc* desc, hyp_model** out) {
   HYP_CHECK_ARG(desc && out, "null argument");
-  HYP_CHECK_ARG(desc->kind == HYP_MODEL_HYPELCNN || desc->kind == HYP_MODEL_DUALCNN, "unknown model kind");
-  if (desc->kind == HYP_MODEL_DUALCNN && desc->precision_mode != HYP_PRECISION_3XTF32)
-    return fail(HYP_E_UNSUPPORTED, "hyp_model_create: DUALCNN is built for the tensor-core engine (HYP_PRECISION_3XTF32) only");
+  HYP_CHECK_ARG(desc->kind == HYP_MODEL_HYPELCNN || desc->kind == HYP_MODEL_DUALCNN || desc->kind == HYP_MODEL_CONCNN,
+                "unknown model kind");
+  if (desc->kind != HYP_MODEL_HYPELCNN && desc->precision_mode != HYP_PRECISION_3XTF32)
+    return fail(HYP_E_UNSUPPORTED, "hyp_model_create: DUALCNN / CONCNN are built for the tensor-core engine (HYP_PRECISION_3XTF32) only");
   HYP_CHECK_ARG(desc->patch >= 1 && desc->patch % 2 == 1 && desc->patch <= 15, "patch must be odd, 1..15");
   HYP_CHECK_ARG(desc->channels >= 1 && desc->classes >= 2 && desc->classes <= 255, "channels/classes out of range");
   HYP_CHECK_ARG(desc->filter_count >= 8, "filter_count out of range");
@@ -770,7 +813,8 @@ int hyp_model_create(const hyp_model_desc* desc, hyp_model** out) {
     return fail(HYP_E_CUDA, "hyp_model_create: no CUDA device (this library has no CPU fallback)");
   std::unique_ptr<hyp_model> m(new hyp_model());
   m->d = *desc;
-  int rc = desc->kind == HYP_MODEL_DUALCNN ? build_dualcnn(*m) : build_hypelcnn(*m);
+  int rc = desc->kind == HYP_MODEL_DUALCNN ? build_dualcnn(*m)
+           : (desc->kind == HYP_MODEL_CONCNN ? build_concnn(*m) : build_hypelcnn(*m));
   if (rc) return rc;
   rc = layout(*m);
   if (rc) return rc;

@@ -45,6 +45,7 @@ struct TcLayer {
   int slot_ch0(int s) const { return slot_q(s) * f + (s % nt) * ft; }   // first channel in the level's output tensor
   int slot_w(int s) const { return std::min(ft, f - (s % nt) * ft); }
   size_t z_off = 0, mean_off = 0, rstd_off = 0, s1_off = 0, s2_off = 0;
+  size_t u_off = 0;  // LRN layers: the activation before local response normalisation (backward needs it)
   int64_t wf_off = 0, wd_off = 0;  // packed forward / dgrad weights: element offsets inside a pack plane
   int wf_rows = 0, wf_ld = 0, wd_rows = 0, wd_ld = 0;
   TcLaunch fwd, dg, wg;
@@ -144,6 +145,7 @@ static int tc_layout(hyp_model& m) {
     const size_t rows_out = Bm * tout.PP;
     T.z_off = take(rows_out * tout.Cp * sizeof(float));
     if (L.share == 2) T.z_off = S.tl[li - 1].z_off;  // second part of a two-input FC accumulates into the first part's z
+    if (L.lrn) T.u_off = take(rows_out * tout.Cp * sizeof(float));
     T.mean_off = take(L.Cout * sizeof(float));
     T.rstd_off = take(L.Cout * sizeof(float));
     T.s1_off = take(L.Cout * sizeof(float));
@@ -185,15 +187,17 @@ static int tc_layout(hyp_model& m) {
       T.Kp = r32(Cin);
       T.Gp = r32(T.NS * T.fpad);
       T.Cq = r16(Cin);
-      const int ntaps = P * P;
+      // taps reach max(|dy|, |dx|) <= h: the largest kernel's radius, at most P - 1 (a 5x5 kernel on a 3x3 patch still
+      // connects pixel 0 to pixel 2); tap index = (dy + h) * TW + (dx + h)
+      const int h = std::min(T.R - 1, P - 1), TW = 2 * h + 1;
+      const int ntaps = TW * TW;
       T.wf_rows = ntaps * T.NS * T.fpad; T.wf_ld = T.Kp;
       T.wd_rows = ntaps * T.Cq; T.wd_ld = T.Gp;
       T.wf_off = take_pack((int64_t)T.wf_rows * T.wf_ld);
       T.wd_off = take_pack((int64_t)T.wd_rows * T.wd_ld);
-      const int h = P / 2;
       for (int dy = -h; dy <= h; dy++)
         for (int dx = -h; dx <= h; dx++) {
-          const int tap = (dy + h) * P + (dx + h);
+          const int tap = (dy + h) * TW + (dx + h);
           const int ring = std::max(std::abs(dy), std::abs(dx));
           for (int slot = 0; slot < T.NS; slot++) {
             const int q = T.slot_q(slot);
@@ -220,7 +224,6 @@ static int tc_layout(hyp_model& m) {
       T.Kp = r32(Ct);
       T.Gp = tout.Cp;
       T.Cq = r16(Ct);
-      if (T.Cq > 256 || Ct > 128) return fail(HYP_E_UNSUPPORTED, "tc engine: flatten input wider than 128 channels");
       T.wf_rows = r16(L.Cout); T.wf_ld = tin.PP * T.Kp;
       T.wd_rows = tin.PP * T.Cq; T.wd_ld = r32(L.Cout);
       T.wf_off = take_pack((int64_t)T.wf_rows * T.wf_ld);
@@ -394,7 +397,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
   for (size_t li = 0; li < m.layers.size(); li++) {
     Layer& L = m.layers[li];
     TcLayer& T = S.tl[li];
-    const int P = L.P, h = P / 2;
+    const int P = L.P, h = std::min(T.R - 1, P - 1), TW = 2 * h + 1;  // tap radius / tap-table pitch (see tc_layout)
     // taps sorted by ring so that the MMA N of a tile's segments never increases
     std::vector<std::pair<int, int>> taps;
     if (T.kind == 1)
@@ -524,7 +527,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
             if (ph + dy < 0 || ph + dy >= P || pw + dx < 0 || pw + dx >= P) continue;
             const int nbx = std::min(s1, (R - ring) * nt) - s0;
             if (nbx <= 0) continue;
-            const int tap = (dy + h) * P + (dx + h);
+            const int tap = (dy + h) * TW + (dx + h);
             TcSeg s{};
             s.a2 = p + dy * P + dx; s.b1 = tap * NS * fpad; s.nk = T.Kp / 32; s.n_mma = nbx * fpad; s.nb = nbx;
             pb.segs.push_back(s);
@@ -574,7 +577,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
             for (auto& tp : taps) {
               const int dy = tp.first, dx = tp.second, ring = std::max(std::abs(dy), std::abs(dx));
               if (ph - dy < 0 || ph - dy >= P || pw - dx < 0 || pw - dx >= P) continue;
-              const int tap = (dy + h) * P + (dx + h);
+              const int tap = (dy + h) * TW + (dx + h);
               TcSeg s{};
               s.a2 = p - (dy * P + dx); s.b1 = tap * T.Cq + j * nw;
               s.nk = (int)cdiv((R - ring) * nt * fpad, 32); s.n_mma = r16(std::min(nw, Cin - j * nw)); s.nb = 1;
@@ -703,29 +706,33 @@ static int tc_plan(hyp_model& m, int64_t B) {
       // ---------------- dgrad ----------------
       if (need_dgrad) {
         if ((rc = map4(&T.dg.tmA, gz0, Cout, B, 1, T.Gp, (uint64_t)B * T.Gp, S.gz_plane_elems, 32, 128, false))) return rc;
+        int dtn, dw;  // column tiles over the flattened tensor's channels
+        n_tiling(Ct, dtn, dw);
         if ((rc = map4(&T.dg.tmB, pack0 + T.wd_off, T.wd_ld, T.wd_rows, 1, T.wd_ld, (uint64_t)T.wd_rows * T.wd_ld,
-                       S.pack_plane_elems, 32, T.Cq / CG, false))) return rc;
-        T.dg.mn = false; T.dg.cg = CG; T.dg.b_rows = T.Cq; T.dg.bn = T.Cq; T.dg.tile0 = (int)pb.tiles.size();
+                       S.pack_plane_elems, 32, dw / CG, false))) return rc;
+        T.dg.mn = false; T.dg.cg = CG; T.dg.b_rows = dw; T.dg.bn = dw; T.dg.tile0 = (int)pb.tiles.size();
         const int dseg0 = (int)pb.segs.size();
-        for (int pos = 0; pos < PP; pos++) {
-          TcSeg s{};
-          s.b1 = pos * T.Cq; s.nk = T.wd_ld / 32; s.n_mma = T.Cq; s.nb = 1;
-          pb.segs.push_back(s);
-        }
-        for (int bt2 = 0; bt2 < nbt; bt2 += CG)
-          for (int pos = 0; pos < PP; pos++) {
-            const size_t run = pb.tiles.size();
-            for (int bt = bt2; bt < std::min(nbt, bt2 + CG); bt++) {
-              TcTile t = blank_tile();
-              t.seg_begin = dseg0 + pos; t.seg_count = 1; t.total_kb = T.wd_ld / 32;
-              t.m_valid = (int)std::min<int64_t>(128, B - (int64_t)bt * 128);
-              t.ncb = 1; t.ld_out = tin.Cp; t.a1_add = bt * 128;
-              t.cb[0].out_off = ((int64_t)pos * B + (int64_t)bt * 128) * tin.Cp;
-              t.cb[0].width = Ct;
-              pb.tiles.push_back(t);
-            }
-            close_pair_run(pb.tiles, run, nbt * 128);
+        for (int pos = 0; pos < PP; pos++)
+          for (int jd = 0; jd < dtn; jd++) {
+            TcSeg s{};
+            s.b1 = pos * T.Cq + jd * dw; s.nk = T.wd_ld / 32; s.n_mma = r16(std::min(dw, Ct - jd * dw)); s.nb = 1;
+            pb.segs.push_back(s);
           }
+        for (int bt2 = 0; bt2 < nbt; bt2 += CG)
+          for (int pos = 0; pos < PP; pos++)
+            for (int jd = 0; jd < dtn; jd++) {
+              const size_t run = pb.tiles.size();
+              for (int bt = bt2; bt < std::min(nbt, bt2 + CG); bt++) {
+                TcTile t = blank_tile();
+                t.seg_begin = dseg0 + pos * dtn + jd; t.seg_count = 1; t.total_kb = T.wd_ld / 32;
+                t.m_valid = (int)std::min<int64_t>(128, B - (int64_t)bt * 128);
+                t.ncb = 1; t.ld_out = tin.Cp; t.a1_add = bt * 128;
+                t.cb[0].out_off = ((int64_t)pos * B + (int64_t)bt * 128) * tin.Cp + jd * dw;
+                t.cb[0].width = std::min(dw, Ct - jd * dw);
+                pb.tiles.push_back(t);
+              }
+              close_pair_run(pb.tiles, run, nbt * 128);
+            }
         finish_launch(pb, T.dg);
       }
       // ---------------- wgrad ----------------
@@ -734,19 +741,21 @@ static int tc_plan(hyp_model& m, int64_t B) {
         if ((rc = map4(&T.wg.tmB, gz0, Cout, B, 1, T.Gp, (uint64_t)B * T.Gp, S.gz_plane_elems, 32, 32, true))) return rc;
         T.wg.mn = true; T.wg.bn = 32; T.wg.b_rows = 0; T.wg.tile0 = (int)pb.tiles.size();
         for (int pos = 0; pos < PP; pos++)
-          for (int j = 0; j < ntn; j++) {
-            const int width = std::min(nw, Cout - j * nw);
-            TcSeg s{};
-            s.a2 = pos; s.b0 = j * nw; s.nk = (int)cdiv(B, 32); s.n_mma = r16(width); s.nb = (int)cdiv(s.n_mma, 32);
-            T.wg.b_rows = std::max(T.wg.b_rows, s.nb * 32);
-            TcTile t = blank_tile();
-            t.seg_begin = (int)pb.segs.size(); t.seg_count = 1; t.total_kb = s.nk;
-            t.m_valid = Ct; t.ncb = 1; t.ld_out = Cout;
-            t.cb[0].out_off = L.w_off[0] + (int64_t)pos * Ct * Cout + j * nw;
-            t.cb[0].width = width;
-            pb.segs.push_back(s);
-            pb.tiles.push_back(t);
-          }
+          for (int im = 0; im < (int)cdiv(Ct, 128); im++)
+            for (int j = 0; j < ntn; j++) {
+              const int width = std::min(nw, Cout - j * nw);
+              TcSeg s{};
+              s.a0 = im * 128; s.a2 = pos; s.b0 = j * nw; s.nk = (int)cdiv(B, 32); s.n_mma = r16(width);
+              s.nb = (int)cdiv(s.n_mma, 32);
+              T.wg.b_rows = std::max(T.wg.b_rows, s.nb * 32);
+              TcTile t = blank_tile();
+              t.seg_begin = (int)pb.segs.size(); t.seg_count = 1; t.total_kb = s.nk;
+              t.m_valid = std::min(128, Ct - im * 128); t.ncb = 1; t.ld_out = Cout;
+              t.cb[0].out_off = L.w_off[0] + ((int64_t)pos * Ct + im * 128) * Cout + j * nw;
+              t.cb[0].width = width;
+              pb.segs.push_back(s);
+              pb.tiles.push_back(t);
+            }
         finish_launch(pb, T.wg);
       }
     }
@@ -867,6 +876,11 @@ static int tc_forward(hyp_model& m, const float* x, int64_t B, bool training, bo
     } else {
       TC_PROF("tc_bn_apply_kernel", bytes, (tc_bn_apply_kernel<1><<<tc_grid(rows * L.Cout), 256, 0, st>>>(p)));
     }
+    if (L.lrn) {
+      TC_PROF("tc_lrn_fwd_kernel", 16.0 * rows * L.Cout,
+              (tc_lrn_fwd_kernel<<<tc_grid(rows * 32), 256, 8 * L.Cout * sizeof(float), st>>>(
+                  p.hi, p.lo, reinterpret_cast<float*>(m.ws + T.u_off), tout.Cp, L.Cout, rows)));
+    }
   }
   return HYP_OK;
 }
@@ -910,6 +924,11 @@ static int tc_backward(hyp_model& m, const uint8_t* labels, int64_t B, float* lo
     const TcTensor& tout = S.tt[L.out_t];
     const int64_t rows = B * tout.PP;
     if (!ginit[L.out_t]) return fail(HYP_E_STATE, "backward: no gradient reached " + L.scope);
+    if (L.lrn) {  // the gradient arrives w.r.t. the normalised tensor: rewrite it w.r.t. the LRN input, in place
+      TC_PROF("tc_lrn_bwd_kernel", 12.0 * rows * L.Cout,
+              (tc_lrn_bwd_kernel<<<tc_grid(rows * 32), 256, 8 * 3 * L.Cout * sizeof(float), st>>>(
+                  tc_grad(m, L.out_t), reinterpret_cast<const float*>(m.ws + T.u_off), tout.Cp, tout.Cp, L.Cout, rows)));
+    }
     if (L.share != 1) {  // share 1: gz of the second part (processed just before) is still in the scratch planes
     TcBnBwdArgs p{};
     p.gout = tc_grad(m, L.out_t); p.ldg = tout.Cp;

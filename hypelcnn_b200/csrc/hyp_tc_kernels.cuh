@@ -561,6 +561,66 @@ __global__ void __launch_bounds__(256) tc_bn_bwd_finalize8_kernel(const float* _
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// tf.nn.local_response_normalization with TF's defaults (CONCNNModel.py:37,41): depth_radius 5, bias 1, alpha 1,
+// beta 0.5:  y[c] = x[c] / sqrt(1 + sum_{|j-c|<=5} x[j]^2) over the channel axis.  One warp per row (pixel), the row
+// in shared memory.  Forward keeps the pre-LRN row in `u` (backward recomputes the sums from it) and rewrites the
+// activation planes in place.  Backward rewrites the gradient in place:
+//   dx[k] = g[k] / sqrt(s[k]) - x[k] * sum_{|i-k|<=5} g[i] x[i] s[i]^-1.5
+constexpr int LRN_RADIUS = 5;
+__global__ void __launch_bounds__(256) tc_lrn_fwd_kernel(float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ u,
+                                                         int ld, int C, int64_t rows) {
+  extern __shared__ float lrn_sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float* xs = lrn_sm + warp * C;
+  for (int64_t r = (int64_t)blockIdx.x * nwarps + warp; r < rows; r += (int64_t)gridDim.x * nwarps) {
+    for (int c = lane; c < C; c += 32) {
+      const float v = hi[r * ld + c];
+      xs[c] = v;
+      u[r * ld + c] = v;
+    }
+    __syncwarp();
+    for (int c = lane; c < C; c += 32) {
+      float s = 1.f;
+      const int j0 = max(0, c - LRN_RADIUS), j1 = min(C - 1, c + LRN_RADIUS);
+      for (int j = j0; j <= j1; j++) s += xs[j] * xs[j];
+      const float y = xs[c] / sqrtf(s);
+      hi[r * ld + c] = y;
+      lo[r * ld + c] = tf32_lo(y);
+    }
+    __syncwarp();
+  }
+}
+__global__ void __launch_bounds__(256) tc_lrn_bwd_kernel(float* __restrict__ g, const float* __restrict__ u, int ldg, int ldu, int C,
+                                                         int64_t rows) {
+  extern __shared__ float lrn_sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float* xs = lrn_sm + warp * 3 * C;
+  float* ts = xs + C;
+  float* gi = ts + C;
+  for (int64_t r = (int64_t)blockIdx.x * nwarps + warp; r < rows; r += (int64_t)gridDim.x * nwarps) {
+    for (int c = lane; c < C; c += 32) xs[c] = u[r * ldu + c];
+    __syncwarp();
+    for (int c = lane; c < C; c += 32) {
+      float s = 1.f;
+      const int j0 = max(0, c - LRN_RADIUS), j1 = min(C - 1, c + LRN_RADIUS);
+      for (int j = j0; j <= j1; j++) s += xs[j] * xs[j];
+      const float gv = g[r * ldg + c];
+      const float rs = 1.f / sqrtf(s);
+      gi[c] = gv * rs;
+      ts[c] = gv * xs[c] * rs / s;
+    }
+    __syncwarp();
+    for (int c = lane; c < C; c += 32) {
+      float t = 0.f;
+      const int j0 = max(0, c - LRN_RADIUS), j1 = min(C - 1, c + LRN_RADIUS);
+      for (int j = j0; j <= j1; j++) t += ts[j];
+      g[r * ldg + c] = gi[c] - xs[c] * t;
+    }
+    __syncwarp();
+  }
+}
+
 // softmax cross-entropy per row (one warp per row) on padded logits + gradient
 __global__ void tc_ce_loss_kernel(const float* __restrict__ logits, int ld, const uint8_t* __restrict__ labels,
                                   int64_t B, int classes, float* __restrict__ ce_out, float* __restrict__ glogits,

@@ -48,7 +48,7 @@ class PatchEngine:
         self.patch, self.channels, self.classes = int(patch), int(channels), int(classes)
         self.alg = dict(algorithm_params)
         self.precision = precision
-        if model not in ("hypelcnn", "dualcnn"):
+        if model not in ("hypelcnn", "dualcnn", "concnn"):
             raise ValueError(f"unknown model kind {model!r}")
         self.model = model
         self._handle = ctypes.c_void_p()
@@ -61,6 +61,12 @@ class PatchEngine:
     # ------------------------------------------------------------------ lifecycle
     def _desc(self, max_batch):
         a = self.alg
+        if self.model == "concnn":  # nnmodel/modelconfigs/alg_param_concnn.json keys; slim's default activation is ReLU
+            return N.ModelDesc(kind=N.HYP_MODEL_CONCNN, patch=self.patch, channels=self.channels, classes=self.classes,
+                               filter_count=int(a["filter_count"]), spectral_levels=0, spatial_levels=0, degradation=0,
+                               use_residual=1, precision_mode=_PRECISIONS[self.precision], max_batch=max_batch,
+                               reserved=0, lrelu_alpha=0.0, bn_decay=0.0, bn_eps=0.0,
+                               drop_out_ratio=float(a["drop_out_ratio"]))
         if self.model == "dualcnn":  # nnmodel/modelconfigs/alg_param_dualcnn.json keys
             return N.ModelDesc(kind=N.HYP_MODEL_DUALCNN, patch=self.patch, channels=self.channels, classes=self.classes,
                                filter_count=int(a["filter_count"]), spectral_levels=0, spatial_levels=0, degradation=0,
@@ -154,7 +160,7 @@ class PatchEngine:
         self.adam_m.zero_()
         self.adam_v.zero_()
         self.global_step = 0
-        if self.model == "dualcnn":
+        if self.model in ("dualcnn", "concnn"):
             # slim defaults (nnmodel/DUALCNNModel.py:13-18 sets only the activation): xavier-uniform weights
             # (limit = sqrt(6 / (fan_in + fan_out)), receptive field included), zero biases [TF-lib]
             for name, (kind, off, shape) in self.variables.items():
@@ -301,14 +307,17 @@ class PatchEngine:
         base = self._ws_ptr - self.workspace.data_ptr()
         return self.workspace[base + off: base + off + 4 * n.value].view(torch.float32).clone()
 
-    def dropout_mask(self, layer_scope, seed, batch):
+    def dropout_mask(self, layer_scope, seed, batch, rows_per_sample=1):
+        """0/1 keep mask of a dropout layer for `seed`.  FC layers: [batch, width]; conv layers (rows_per_sample =
+        P*P): [P*P, batch, width] in the engine's position-major row order."""
         width = None
         for nm, (k, o, s) in self.variables.items():
             if nm in (f"nn_core/{layer_scope}/BatchNorm/beta", f"nn_core/{layer_scope}/biases"):
                 width = s[0]
         if width is None:
             raise KeyError(layer_scope)
-        out = torch.empty((batch, width), dtype=torch.uint8, device=self.device)
+        out = torch.empty((batch, width) if rows_per_sample == 1 else (rows_per_sample, batch, width), dtype=torch.uint8,
+                          device=self.device)
         N.check(N.lib().hyp_model_dropout_mask(self._handle, layer_scope.encode(), ctypes.c_uint64(seed), batch,
                                                _ptr(out), _stream()))
         return out

@@ -80,7 +80,8 @@ int hyp_gather_patches(const void* casi, int casi_dtype, int Hc, int Wc, int C_h
  * ------------------------------------------------------------------------------------- */
 enum {
   HYP_MODEL_HYPELCNN = 0, /* nnmodel/HYPELCNNModel.py */
-  HYP_MODEL_DUALCNN = 1   /* nnmodel/DUALCNNModel.py:11-104 (tensor-core engine only) */
+  HYP_MODEL_DUALCNN = 1,  /* nnmodel/DUALCNNModel.py:11-104 (tensor-core engine only) */
+  HYP_MODEL_CONCNN = 2    /* nnmodel/CONCNNModel.py:23-64 (tensor-core engine only; pass lrelu_alpha = 0 for ReLU) */
 };
 enum {
   HYP_PRECISION_FP32 = 0,    /* fp32 FFMA everywhere (parity mode) */
