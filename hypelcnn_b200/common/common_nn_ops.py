@@ -417,6 +417,7 @@ def create_graph(training_data_set, testing_data_set, validation_data_set, class
     """Reference: :330-373.  Returns the same 6-tuple; cross_entropy / learning_rate are
     callables reading the TrainOp's latest values, train_step is the TrainOp."""
     deep_nn_template = partial(model.create_tensor_graph, class_count=class_range.stop)
+    model._class_count = class_range.stop  # what make_template("nn_core", ..., class_count=...) binds (:333)
     training_input_iter = training_nn_iterator(training_data_set, augmentation_info, batch_size, num_epochs,
                                                device_id, prefetch_size)
     train_step = TrainOp(model, training_input_iter, algorithm_params, model.get_loss_func)

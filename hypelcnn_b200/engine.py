@@ -191,6 +191,38 @@ class PatchEngine:
                 raise ValueError(f"{name}: shape {tuple(t.shape)} != {tuple(dst.shape)}")
             dst.copy_(t)
 
+    # ------------------------------------------------------------------ checkpoints
+    def save_checkpoint(self, path):
+        """Variables under their TF checkpoint names plus the optimizer slots and global_step, as safetensors — the
+        on-disk role of the reference's Saver(nn_core/*, global_step, training_optimizer/*)
+        (classify/monitored_session_runner.py:164-168).  TF's own ckpt format needs TensorFlow and is out of scope."""
+        from safetensors.torch import save_file
+        t = {}
+        for name, (kind, off, shape) in self.variables.items():
+            n = int(numpy.prod(shape))
+            t[name] = self.variable(name).detach().cpu().contiguous()
+            if kind in (0, 1):  # Adam slots are named <variable>/Adam and /Adam_1 in TF checkpoints [TF-lib]
+                t[name + "/Adam"] = self.adam_m[off:off + n].view(shape).detach().cpu().contiguous()
+                t[name + "/Adam_1"] = self.adam_v[off:off + n].view(shape).detach().cpu().contiguous()
+        t["global_step"] = torch.tensor([self.global_step], dtype=torch.int64)
+        save_file(t, path, metadata={"model": self.model, "patch": str(self.patch), "channels": str(self.channels),
+                                     "classes": str(self.classes)})
+
+    def load_checkpoint(self, path, exclude_prefixes=()):
+        """Restore what save_checkpoint wrote.  exclude_prefixes mirrors the inference restore, which skips
+        ``image_gen_net_*`` (classify/infer_for_classification.py:121-128)."""
+        from safetensors.torch import load_file
+        t = load_file(path)
+        for name, (kind, off, shape) in self.variables.items():
+            if any(name.startswith("nn_core/" + p) for p in exclude_prefixes):
+                continue
+            n = int(numpy.prod(shape))
+            self.variable(name).copy_(t[name])
+            if kind in (0, 1) and name + "/Adam" in t:
+                self.adam_m[off:off + n].view(shape).copy_(t[name + "/Adam"])
+                self.adam_v[off:off + n].view(shape).copy_(t[name + "/Adam_1"])
+        self.global_step = int(t["global_step"][0])
+
     def export_variables(self):
         return {name: self.variable(name).detach().cpu().numpy().copy() for name in self.variables}
 
