@@ -80,6 +80,12 @@ _PROTOS = {
     "hyp_momentum_step": (_I, [_P, _P, _P, _L, _F, _F, _F, _P]),
     "hyp_augment_patches": (_I, [_P, _P, _L, _I, _I, _I, _I, _F, ctypes.c_uint64, _P, _P, _P]),
     "hyp_gan_generator_forward": (_I, [_P, _I, _P, _I, _L, _I, _I, _P, _I, _I, _I, _P]),
+    "hyp_gan_generator_train_forward": (_I, [_P, _L, _I, _P, _P, _P]),
+    "hyp_gan_generator_backward": (_I, [_P, _P, _L, _I, _P, _P, _P, _P]),
+    "hyp_gan_discriminator_forward": (_I, [_P, _L, _I, _P, _P, _P, _P]),
+    "hyp_gan_discriminator_backward": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P]),
+    "hyp_gan_loss_grad": (_I, [_I, _P, _P, _F, _F, _L, _P, _I, _P, _P]),
+    "hyp_gan_l2_regularizer": (_I, [_P, _P, _L, _F, _P, _P]),
     "hyp_argmax_confusion": (_I, [_P, _P, _L, _I, _P, _P, _P]),
     "hyp_scatter_class_map": (_I, [_P, _P, _L, _I, _I, _P, _P]),
     "hyp_model_debug_tensor": (_I, [_P, ctypes.c_char_p, _I, ctypes.POINTER(_P), ctypes.POINTER(_L)]),

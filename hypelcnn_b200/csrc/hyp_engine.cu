@@ -1010,6 +1010,7 @@ int hyp_gan_generator_forward(const float* in, int ld_in, float* out, int ld_out
   GanGenArgs a;
   a.in = in; a.out = out; a.rows = rows; a.C = bands; a.ld_in = ld_in; a.ld_out = ld_out; a.copy_extra = copy_extra;
   a.weights = weights; a.nlayers = encoder_only ? 4 : 7; a.clip = clip_invalid_values != 0; a.is_shadow = is_shadow_graph != 0;
+  a.nets = nullptr;
   const int K[7] = {bands, bands / 2, bands / 4, bands / 8, bands / 4, bands / 2, bands};
   int nw = 0;
   for (int l = 0; l < a.nlayers; l++) nw += K[l] + 1;
@@ -1018,6 +1019,108 @@ int hyp_gan_generator_forward(const float* in, int ld_in, float* out, int ld_out
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   PROF("gan_generator_fwd_kernel", 4.0 * rows * (ld_in + ld_out),
        (gan_generator_fwd_kernel<<<grid, 128, smem, st>>>(a)));
+  return HYP_OK;
+}
+
+// ---- GAN training kernels (CycleGAN: gan/wrappers/cycle_gan_wrapper.py, gan/shadow_data_models.py) ----
+static int gan_gen_weight_count(int bands) {
+  const int K[7] = {bands, bands / 2, bands / 4, bands / 8, bands / 4, bands / 2, bands};
+  int nw = 0;
+  for (int l = 0; l < 7; l++) nw += K[l] + 1;
+  return nw;
+}
+int hyp_gan_generator_train_forward(const float* x, int64_t rows, int bands, const float* weights, float* nets,
+                                    void* stream) {
+  HYP_CHECK_ARG(x && weights && nets, "null argument");
+  HYP_CHECK_ARG(bands >= 8 && bands <= GAN_MAX_C && rows >= 0, "bad shape");
+  if (rows == 0) return HYP_OK;
+  GanGenArgs a;
+  a.in = x; a.rows = rows; a.C = bands; a.ld_in = bands; a.copy_extra = 0; a.weights = weights; a.nlayers = 7;
+  a.clip = 0; a.is_shadow = 0; a.nets = nets;
+  a.out = nets + 7 * (size_t)bands;  // row r's output lands in nets[r][7][:] (stride 8 * bands)
+  a.ld_out = 8 * bands;
+  const int nw = gan_gen_weight_count(bands);
+  const size_t smem = (size_t)(((nw + 3) & ~3) + 4 * 3 * bands) * sizeof(float);
+  const unsigned grid = (unsigned)std::min<int64_t>(cdiv(rows, 4), 148 * 16);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PROF("gan_generator_fwd_kernel", 4.0 * rows * 9 * bands, (gan_generator_fwd_kernel<<<grid, 128, smem, st>>>(a)));
+  return HYP_OK;
+}
+
+int hyp_gan_generator_backward(const float* nets, const float* gout, int64_t rows, int bands, const float* weights,
+                               float* gin, float* gweights, void* stream) {
+  HYP_CHECK_ARG(nets && gout && weights && gweights, "null argument");
+  HYP_CHECK_ARG(bands >= 8 && bands <= 256 && rows >= 0, "bands out of range (8..256)");
+  if (rows == 0) return HYP_OK;
+  GanGenBwdArgs a;
+  a.nets = nets; a.gout = gout; a.rows = rows; a.C = bands; a.weights = weights; a.gin = gin; a.gweights = gweights;
+  const int nw = gan_gen_weight_count(bands);
+  const size_t smem = (size_t)(2 * ((nw + 3) & ~3) + 4 * 17 * bands) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    HYP_CUDA(cudaFuncSetAttribute(gan_generator_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr = true;
+  }
+  HYP_CHECK_ARG(smem <= 96 * 1024, "bands too large for the backward kernel's shared memory");
+  const unsigned grid = (unsigned)std::min<int64_t>(cdiv(rows, 4), 148 * 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PROF("gan_generator_bwd_kernel", 4.0 * rows * 10 * bands, (gan_generator_bwd_kernel<<<grid, 128, smem, st>>>(a)));
+  return HYP_OK;
+}
+
+static int gan_disc_launch(bool backward, const GanDiscArgs& a, cudaStream_t st) {
+  const int C = a.C, H = C / 2;
+  const int nw = C * C + C + C * C + C + C * H + H, nwp = (nw + 3) & ~3;
+  static bool attr = false;
+  if (!attr) {
+    HYP_CUDA(cudaFuncSetAttribute(gan_discriminator_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    HYP_CUDA(cudaFuncSetAttribute(gan_discriminator_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr = true;
+  }
+  const unsigned grid = (unsigned)std::min<int64_t>(cdiv(a.rows, 8), 148 * 2);
+  if (!backward) {
+    const size_t smem = (size_t)(nwp + 8 * 3 * C) * sizeof(float);
+    PROF("gan_discriminator_fwd_kernel", 4.0 * a.rows * 3.5 * C, (gan_discriminator_fwd_kernel<<<grid, 256, smem, st>>>(a)));
+  } else {
+    const int wpad = ((2 * C * (C + 1) + C * (H + 1)) + 3) & ~3;
+    const size_t smem = (size_t)(wpad + (a.gweights ? nwp : 0) + 8 * 6 * C) * sizeof(float);
+    PROF("gan_discriminator_bwd_kernel", 4.0 * a.rows * 4.5 * C, (gan_discriminator_bwd_kernel<<<grid, 256, smem, st>>>(a)));
+  }
+  return HYP_OK;
+}
+int hyp_gan_discriminator_forward(const float* x, int64_t rows, int bands, const float* weights, float* hidden,
+                                  float* out, void* stream) {
+  HYP_CHECK_ARG(x && weights && hidden && out, "null argument");
+  HYP_CHECK_ARG(bands >= 8 && bands <= 96 && bands % 2 == 0 && rows >= 0, "bands out of range (even, 8..96: the weights live in shared memory)");
+  if (rows == 0) return HYP_OK;
+  GanDiscArgs a{};
+  a.x = x; a.rows = rows; a.C = bands; a.weights = weights; a.h = hidden; a.out = out;
+  return gan_disc_launch(false, a, static_cast<cudaStream_t>(stream));
+}
+int hyp_gan_discriminator_backward(const float* x, const float* hidden, const float* gout, int64_t rows, int bands,
+                                   const float* weights, float* gin, float* gweights, void* stream) {
+  HYP_CHECK_ARG(x && weights && hidden && gout && (gin || gweights), "null argument");
+  HYP_CHECK_ARG(bands >= 8 && bands <= 96 && bands % 2 == 0 && rows >= 0, "bands out of range (even, 8..96)");
+  if (rows == 0) return HYP_OK;
+  GanDiscArgs a{};
+  a.x = x; a.rows = rows; a.C = bands; a.weights = weights; a.h = const_cast<float*>(hidden); a.gout = gout; a.gin = gin;
+  a.gweights = gweights;
+  return gan_disc_launch(true, a, static_cast<cudaStream_t>(stream));
+}
+int hyp_gan_loss_grad(int mode, const float* a, const float* b, float target, float scale, int64_t numel, float* grad,
+                      int accumulate, double* loss_acc, void* stream) {
+  HYP_CHECK_ARG(a && (mode == 0 || (mode == 1 && b)) && numel >= 0, "bad argument");
+  if (numel == 0) return HYP_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PROF("gan_loss_grad_kernel", 8.0 * numel,
+       (gan_loss_grad_kernel<<<ew_grid(numel), 256, 0, st>>>(mode, a, b, target, scale, numel, grad, accumulate, loss_acc)));
+  return HYP_OK;
+}
+int hyp_gan_l2_regularizer(const float* weights, float* grads, int64_t n, float scale, double* loss_acc, void* stream) {
+  HYP_CHECK_ARG(weights && n >= 0, "bad argument");
+  if (n == 0) return HYP_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PROF("gan_l2_reg_kernel", 8.0 * n, (gan_l2_reg_kernel<<<ew_grid(n), 256, 0, st>>>(weights, grads, n, scale, loss_acc)));
   return HYP_OK;
 }
 

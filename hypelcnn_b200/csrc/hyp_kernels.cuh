@@ -344,6 +344,7 @@ struct GanGenArgs {
   const float* weights;              // net1 w[K1] b, net2 w[K2] b, ... in layer order
   int nlayers;                       // 7 full generator, 4 encoder only
   int clip, is_shadow;
+  float* nets;                       // nullable (training): [rows][nlayers + 1][C] = net0 (input) .. net_nlayers
 };
 constexpr int GAN_MAX_C = 512;
 __global__ void __launch_bounds__(128) gan_generator_fwd_kernel(const GanGenArgs a) {
@@ -367,6 +368,8 @@ __global__ void __launch_bounds__(128) gan_generator_fwd_kernel(const GanGenArgs
     float* cur = buf + 2 * C;
     float in_sum = 0.f;
     for (int c = lane; c < C; c += 32) { const float v = xin[c]; p1[c] = v; p2[c] = 0.f; in_sum += v; }
+    if (a.nets)
+      for (int c = lane; c < C; c += 32) a.nets[(r * (a.nlayers + 1)) * C + c] = p1[c];
     __syncwarp();
     const float* wl = w;
     for (int l = 0; l < a.nlayers; l++) {
@@ -384,6 +387,7 @@ __global__ void __launch_bounds__(128) gan_generator_fwd_kernel(const GanGenArgs
           if (l > 0) s += p2[c];              // net1 = conv + net0 only
         }
         cur[c] = s;
+        if (a.nets) a.nets[(r * (a.nlayers + 1) + l + 1) * C + c] = s;
       }
       __syncwarp();
       float* t = p2; p2 = p1; p1 = cur; cur = t;
@@ -401,6 +405,272 @@ __global__ void __launch_bounds__(128) gan_generator_fwd_kernel(const GanGenArgs
     for (int c = lane; c < C; c += 32) xout[c] = keep_generated ? p1[c] : xin[c];
     for (int c = lane; c < a.copy_extra; c += 32) xout[C + c] = xin[C + c];
     __syncwarp();
+  }
+}
+
+// Generator backward (full 7-layer generator): from the saved layer outputs nets [rows][8][C] and dL/dnet7 to dL/dnet0
+// and the weight / bias gradients.  One warp per spectrum; activations and the running gradients of net0..net7 in
+// shared memory; per-block weight-gradient accumulation in shared memory, one global atomicAdd per weight per block.
+//   pre_l = conv(net_{l-1}; w_l) + b_l;  act_l = lrelu_0.1(pre_l) (tanh for l = 7);
+//   net_l = act_l + net_{l-1} + net_{l-2}   (l = 1: + net_0 only; l = 7: no residual)
+struct GanGenBwdArgs {
+  const float* nets;
+  const float* gout;
+  int64_t rows;
+  int C;
+  const float* weights;
+  float* gin;       // nullable
+  float* gweights;  // += (same order as weights)
+};
+__global__ void __launch_bounds__(128) gan_generator_bwd_kernel(const GanGenBwdArgs a) {
+  extern __shared__ float sm[];
+  const int C = a.C;
+  int K[7];
+  K[0] = C; K[1] = C / 2; K[2] = C / 4; K[3] = C / 8; K[4] = C / 4; K[5] = C / 2; K[6] = C;
+  int woff[8];
+  woff[0] = 0;
+  for (int l = 0; l < 7; l++) woff[l + 1] = woff[l] + K[l] + 1;
+  const int nw = woff[7], nwp = (nw + 3) & ~3;
+  float* w = sm;                 // [nwp]
+  float* gw = sm + nwp;          // [nwp] block accumulator
+  float* per_warp = gw + nwp;    // [warps][(8 + 8 + 1) * C]
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) { w[i] = a.weights[i]; gw[i] = 0.f; }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float* nets = per_warp + warp * 17 * C;  // [8][C]
+  float* G = nets + 8 * C;                 // [8][C]
+  float* dpre = G + 8 * C;                 // [C]
+  for (int64_t r = (int64_t)blockIdx.x * nwarps + warp; r < a.rows; r += (int64_t)gridDim.x * nwarps) {
+    for (int i = lane; i < 8 * C; i += 32) { nets[i] = a.nets[r * 8 * C + i]; G[i] = 0.f; }
+    for (int c = lane; c < C; c += 32) G[7 * C + c] = a.gout[r * C + c];
+    __syncwarp();
+    for (int l = 7; l >= 1; l--) {
+      const int k = K[l - 1], left = (k - 1) / 2;
+      const float* wl = w + woff[l - 1];
+      const float* in = nets + (l - 1) * C;
+      float* Gl = G + l * C;
+      float* Gin = G + (l - 1) * C;
+      float bsum = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        float d;
+        if (l == 7) {
+          const float y = nets[7 * C + c];
+          d = Gl[c] * (1.f - y * y);
+        } else {
+          const float act = nets[l * C + c] - in[c] - (l > 1 ? nets[(l - 2) * C + c] : 0.f);
+          d = Gl[c] * (act > 0.f ? 1.f : 0.1f);
+        }
+        dpre[c] = d;
+        bsum += d;
+      }
+      __syncwarp();
+      if (l < 7) {  // residual paths
+        for (int c = lane; c < C; c += 32) {
+          Gin[c] += Gl[c];
+          if (l > 1) G[(l - 2) * C + c] += Gl[c];
+        }
+      }
+      bsum = warp_sum(bsum);
+      if (lane == 0) atomicAdd(&gw[woff[l - 1] + k], bsum);
+      // dW_l[t] = sum_c dpre[c] * in[c + t - left]
+      for (int t = lane; t < k; t += 32) {
+        float s = 0.f;
+        const int c0 = max(0, left - t), c1 = min(C, C + left - t);
+        for (int c = c0; c < c1; c++) s += dpre[c] * in[c + t - left];
+        atomicAdd(&gw[woff[l - 1] + t], s);
+      }
+      // dL/dnet_{l-1}[c'] += sum_t w[t] * dpre[c' - t + left]
+      for (int cp = lane; cp < C; cp += 32) {
+        float s = 0.f;
+        const int t0 = max(0, cp + left - (C - 1)), t1 = min(k, cp + left + 1);
+        for (int t = t0; t < t1; t++) s += wl[t] * dpre[cp - t + left];
+        Gin[cp] += s;
+      }
+      __syncwarp();
+    }
+    if (a.gin)
+      for (int c = lane; c < C; c += 32) a.gin[r * C + c] = G[c];
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) atomicAdd(&a.gweights[i], gw[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Shadow GAN discriminator (gan/shadow_data_models.py:93-123): flatten -> FC C->C -> FC C->C (leaky_relu 0.1) -> FC
+// C->C/2 linear.  Weights [W1 (C x C, input-major), b1, W2, b2, W3 (C x C/2), b3] in shared memory (C <= 64),
+// one warp per spectrum.  Forward keeps h1, h2 for the backward pass.
+struct GanDiscArgs {
+  const float* x;     // [rows][C]
+  int64_t rows;
+  int C;
+  const float* weights;
+  float* h;           // [rows][2][C]   (forward: out; backward: in)
+  float* out;         // forward: [rows][C/2]
+  const float* gout;  // backward: [rows][C/2]
+  float* gin;         // backward, nullable: [rows][C]
+  float* gweights;    // backward, nullable: += weight gradients
+};
+__device__ __forceinline__ int gan_disc_nweights(int C) { return C * C + C + C * C + C + C * (C / 2) + C / 2; }
+__global__ void __launch_bounds__(256) gan_discriminator_fwd_kernel(const GanDiscArgs a) {
+  extern __shared__ float sm[];
+  const int C = a.C, H = C / 2, nw = gan_disc_nweights(C);
+  float* w = sm;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) w[i] = a.weights[i];
+  __syncthreads();
+  const float *W1 = w, *b1 = W1 + C * C, *W2 = b1 + C, *b2 = W2 + C * C, *W3 = b2 + C, *b3 = W3 + C * H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float* v = sm + ((nw + 3) & ~3) + warp * 3 * C;  // x, h1, h2
+  for (int64_t r = (int64_t)blockIdx.x * nwarps + warp; r < a.rows; r += (int64_t)gridDim.x * nwarps) {
+    for (int c = lane; c < C; c += 32) v[c] = a.x[r * C + c];
+    __syncwarp();
+    for (int j = lane; j < C; j += 32) {
+      float s = b1[j];
+      for (int i = 0; i < C; i++) s += v[i] * W1[i * C + j];
+      s = fmaxf(s, 0.1f * s);
+      v[C + j] = s;
+      a.h[(r * 2 + 0) * C + j] = s;
+    }
+    __syncwarp();
+    for (int j = lane; j < C; j += 32) {
+      float s = b2[j];
+      for (int i = 0; i < C; i++) s += v[C + i] * W2[i * C + j];
+      s = fmaxf(s, 0.1f * s);
+      v[2 * C + j] = s;
+      a.h[(r * 2 + 1) * C + j] = s;
+    }
+    __syncwarp();
+    for (int j = lane; j < H; j += 32) {
+      float s = b3[j];
+      for (int i = 0; i < C; i++) s += v[2 * C + i] * W3[i * H + j];
+      a.out[r * H + j] = s;
+    }
+    __syncwarp();
+  }
+}
+__global__ void __launch_bounds__(256) gan_discriminator_bwd_kernel(const GanDiscArgs a) {
+  extern __shared__ float sm[];
+  const int C = a.C, H = C / 2, nw = gan_disc_nweights(C), nwp = (nw + 3) & ~3;
+  // weights with padded rows (the backward products walk a ROW per lane: stride C+1 / H+1 keeps lanes on distinct banks)
+  const int LW = C + 1, LH = H + 1;
+  const int wpad = ((2 * C * LW + C * LH) + 3) & ~3;
+  float* W1 = sm;
+  float* W2 = W1 + C * LW;
+  float* W3 = W2 + C * LW;
+  float* gw = sm + wpad;  // block accumulator in the dense layout of `weights` (only when gweights)
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x) {
+    W1[(i / C) * LW + i % C] = a.weights[i];
+    W2[(i / C) * LW + i % C] = a.weights[C * C + C + i];
+  }
+  for (int i = threadIdx.x; i < C * H; i += blockDim.x) W3[(i / H) * LH + i % H] = a.weights[2 * (C * C + C) + i];
+  if (a.gweights)
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) gw[i] = 0.f;
+  __syncthreads();
+  float *gW1 = gw, *gb1 = gW1 + C * C, *gW2 = gb1 + C, *gb2 = gW2 + C * C, *gW3 = gb2 + C, *gb3 = gW3 + C * H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float* v = sm + wpad + (a.gweights ? nwp : 0) + warp * 6 * C;  // x, h1, h2, d2 (dpre2), d1 (dpre1), dout
+  float *xs = v, *h1 = v + C, *h2 = v + 2 * C, *d2 = v + 3 * C, *d1 = v + 4 * C, *dout_s = v + 5 * C;
+  for (int64_t r = (int64_t)blockIdx.x * nwarps + warp; r < a.rows; r += (int64_t)gridDim.x * nwarps) {
+    for (int c = lane; c < C; c += 32) {
+      xs[c] = a.x[r * C + c];
+      h1[c] = a.h[(r * 2 + 0) * C + c];
+      h2[c] = a.h[(r * 2 + 1) * C + c];
+    }
+    for (int j = lane; j < H; j += 32) dout_s[j] = a.gout[r * H + j];
+    __syncwarp();
+    // layer 3 (linear): dh2[i] = sum_j W3[i][j] dout[j];  dpre2 = dh2 * lrelu'(h2)
+    for (int i = lane; i < C; i += 32) {
+      float s = 0.f;
+      for (int j = 0; j < H; j++) s += W3[i * LH + j] * dout_s[j];
+      d2[i] = s * (h2[i] > 0.f ? 1.f : 0.1f);
+    }
+    if (a.gweights) {
+      for (int j = lane; j < H; j += 32) {
+        atomicAdd(&gb3[j], dout_s[j]);
+        for (int i = 0; i < C; i++) atomicAdd(&gW3[i * H + j], h2[i] * dout_s[j]);
+      }
+    }
+    __syncwarp();
+    for (int i = lane; i < C; i += 32) {
+      float s = 0.f;
+      for (int j = 0; j < C; j++) s += W2[i * LW + j] * d2[j];
+      d1[i] = s * (h1[i] > 0.f ? 1.f : 0.1f);
+    }
+    if (a.gweights) {
+      for (int j = lane; j < C; j += 32) {
+        atomicAdd(&gb2[j], d2[j]);
+        for (int i = 0; i < C; i++) atomicAdd(&gW2[i * C + j], h1[i] * d2[j]);
+      }
+    }
+    __syncwarp();
+    if (a.gin) {
+      for (int i = lane; i < C; i += 32) {
+        float s = 0.f;
+        for (int j = 0; j < C; j++) s += W1[i * LW + j] * d1[j];
+        a.gin[r * C + i] = s;
+      }
+    }
+    if (a.gweights) {
+      for (int j = lane; j < C; j += 32) {
+        atomicAdd(&gb1[j], d1[j]);
+        for (int i = 0; i < C; i++) atomicAdd(&gW1[i * C + j], xs[i] * d1[j]);
+      }
+    }
+    __syncwarp();
+  }
+  if (a.gweights) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) atomicAdd(&a.gweights[i], gw[i]);
+  }
+}
+
+// GAN loss terms with their gradients.  mode 0 (tfgan least squares): sum 0.5 * scale * (a - target)^2, grad scale * (a -
+// target);  mode 1 (absolute_difference): sum scale * |a - b|, grad scale * sign(a - b).  The caller passes scale =
+// weight / numel (the losses are means).  grad (nullable) is overwritten or accumulated; loss_acc += the sum.
+__global__ void gan_loss_grad_kernel(int mode, const float* __restrict__ av, const float* __restrict__ bv, float target,
+                                     float scale, int64_t n, float* __restrict__ grad, int accumulate,
+                                     double* __restrict__ loss_acc) {
+  __shared__ float sh[32];
+  float s = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float g;
+    if (mode == 0) {
+      const float d = av[i] - target;
+      s += 0.5f * scale * d * d;
+      g = scale * d;
+    } else {
+      const float d = av[i] - bv[i];
+      s += scale * fabsf(d);
+      g = d > 0.f ? scale : (d < 0.f ? -scale : 0.f);
+    }
+    if (grad) grad[i] = accumulate ? grad[i] + g : g;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    if (threadIdx.x == 0 && loss_acc) atomicAdd(loss_acc, (double)s);
+  }
+}
+// slim l2_regularizer(scale): loss += scale * sum(w^2) / 2, grad += scale * w
+__global__ void gan_l2_reg_kernel(const float* __restrict__ w, float* __restrict__ g, int64_t n, float scale,
+                                  double* __restrict__ loss_acc) {
+  __shared__ float sh[32];
+  float s = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = w[i];
+    s += 0.5f * scale * v * v;
+    if (g) g[i] += scale * v;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    if (threadIdx.x == 0 && loss_acc) atomicAdd(loss_acc, (double)s);
   }
 }
 

@@ -180,6 +180,28 @@ int hyp_gan_generator_forward(const float* in, int ld_in, float* out, int ld_out
                               int copy_extra, const float* weights, int encoder_only, int clip_invalid_values,
                               int is_shadow_graph, void* stream);
 
+/* ---- CycleGAN training on [rows, bands] spectra (gan/wrappers/cycle_gan_wrapper.py:48-116,189-333 over the models
+ * of gan/shadow_data_models.py:43-123).  The host (hypelcnn_b200/gan/wrappers/cycle_gan_wrapper.py) chains these. ----
+ * generator training forward: nets [rows][8][bands] = net0 (the input) .. net7 (the output), kept for backward */
+int hyp_gan_generator_train_forward(const float* x, int64_t rows, int bands, const float* weights, float* nets,
+                                    void* stream);
+/* generator backward: gout = dL/dnet7 [rows,bands] -> gin = dL/dnet0 (nullable), gweights += dL/d(weights, biases) */
+int hyp_gan_generator_backward(const float* nets, const float* gout, int64_t rows, int bands, const float* weights,
+                               float* gin, float* gweights, void* stream);
+/* discriminator (FC C->C, C->C leaky_relu 0.1, C->C/2 linear; weights = W1 [C,C], b1, W2, b2, W3 [C,C/2], b3):
+ * forward keeps the hidden activations [rows][2][bands]; backward gives dL/dx (gin, nullable) and/or gweights += */
+int hyp_gan_discriminator_forward(const float* x, int64_t rows, int bands, const float* weights, float* hidden,
+                                  float* out, void* stream);
+int hyp_gan_discriminator_backward(const float* x, const float* hidden, const float* gout, int64_t rows, int bands,
+                                   const float* weights, float* gin, float* gweights, void* stream);
+/* loss terms + gradients.  mode 0 (tfgan least_squares_*): loss_acc += sum 0.5*scale*(a-target)^2, grad = scale*(a-target);
+ * mode 1 (absolute_difference): loss_acc += sum scale*|a-b|, grad = scale*sign(a-b).  scale = weight / numel (means).
+ * grad nullable; accumulate != 0 adds to it.  loss_acc: device double, nullable. */
+int hyp_gan_loss_grad(int mode, const float* a, const float* b, float target, float scale, int64_t numel, float* grad,
+                      int accumulate, double* loss_acc, void* stream);
+/* slim l2_regularizer(scale) on a weight range: loss_acc += scale * sum(w^2)/2, grads += scale * w (grads nullable) */
+int hyp_gan_l2_regularizer(const float* weights, float* grads, int64_t n, float scale, double* loss_acc, void* stream);
+
 /* tf.argmax (lowest index on ties) + tf.math.confusion_matrix accumulation
  * (common/common_nn_ops.py:246-262, :318).  labels/confusion nullable.
  * confusion: int32 [classes,classes], rows = labels, += semantics. */

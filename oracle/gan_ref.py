@@ -60,3 +60,64 @@ def inference_for_matrix_input(x, variables, is_shadow, clip, copy_extra=0):
     out = rows.copy()
     out[:, :C] = gen
     return out.reshape(x.shape)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# torch (autograd) restatement of the CycleGAN-with-identity objective for the gradient parity tests
+def t_generator(x, w):
+    """x [N,C] torch, w flat [net1 w, b, net2 w, b, ...] -> net7."""
+    import torch
+    import torch.nn.functional as F
+    C = x.shape[1]
+    nets, off = [x], 0
+    for i, k in enumerate(kernel_sizes(C)):
+        wk, b = w[off:off + k], w[off + k]
+        off += k + 1
+        left = (k - 1) // 2
+        xp = F.pad(nets[-1], (left, k - 1 - left))
+        y = F.conv1d(xp.unsqueeze(1), wk.view(1, 1, k)).squeeze(1) + b
+        if i == 6:
+            y = torch.tanh(y)
+        else:
+            y = torch.maximum(y, 0.1 * y) + nets[-1]
+            if i > 0:
+                y = y + nets[-2]
+        nets.append(y)
+    return nets[-1]
+
+
+def t_discriminator(x, w):
+    import torch
+    C = x.shape[1]
+    H = C // 2
+    o = 0
+    W1 = w[o:o + C * C].view(C, C); o += C * C
+    b1 = w[o:o + C]; o += C
+    W2 = w[o:o + C * C].view(C, C); o += C * C
+    b2 = w[o:o + C]; o += C
+    W3 = w[o:o + C * H].view(C, H); o += C * H
+    b3 = w[o:o + H]
+    h = x @ W1 + b1
+    h = torch.maximum(h, 0.1 * h)
+    h = h @ W2 + b2
+    h = torch.maximum(h, 0.1 * h)
+    return h @ W3 + b3
+
+
+def t_generator_loss(x, y, G, Fw, DY, DX, w_cyc, w_id):
+    """L_G of cyclegan_loss_with_identity summed over both partial models (aux counted twice)."""
+    gx, fy = t_generator(x, G), t_generator(y, Fw)
+    rx, ry = t_generator(gx, Fw), t_generator(fy, G)
+    gan = 0.5 * ((t_discriminator(gx, DY) - 1) ** 2).mean() + 0.5 * ((t_discriminator(fy, DX) - 1) ** 2).mean()
+    cyc = ((rx - x).abs().mean() + (ry - y).abs().mean()) / 2
+    ident = (gx - x).abs().mean() + (fy - y).abs().mean()
+    return gan + 2 * (w_cyc * cyc + w_id * ident), gan, 2 * w_cyc * cyc, 2 * w_id * ident
+
+
+def t_discriminator_loss(x, y, gx, fy, DY, DX, reg):
+    C = x.shape[1]
+    total = 0
+    for real, fake, w in ((y, gx, DY), (x, fy, DX)):
+        total = total + 0.5 * ((t_discriminator(real, w) - 1) ** 2).mean() + 0.5 * (t_discriminator(fake, w) ** 2).mean()
+        total = total + reg * 0.5 * ((w[:C * C] ** 2).sum() + (w[C * C + C:2 * C * C + C] ** 2).sum())
+    return total
