@@ -1,0 +1,51 @@
+"""CycleGAN (BASELINE configs[3]) train-iteration throughput on synthetic GULFPORT-shaped 64-band spectra (SURVEY S-C4):
+one iteration = global_step += 1, one generator step, one discriminator step.  Prints one JSON line per batch size.
+Launch with torchrun for N > 1 (data parallel: one all-reduce per optimizer step over the 478 / 20 800 gradients)."""
+import argparse
+import json
+import os
+import sys
+
+import numpy
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from hypelcnn_b200 import parallel  # noqa: E402
+from hypelcnn_b200.gan.wrappers.cycle_gan_wrapper import CycleGANWrapper  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batches", default="32,16384")
+ap.add_argument("--steps", type=int, default=20)
+ap.add_argument("--warmup", type=int, default=5)
+a = ap.parse_args()
+rank, local, world = parallel.init_from_env()
+torch.cuda.set_device(local)
+rng = numpy.random.default_rng(1234 + rank)
+for B in [int(b) for b in a.batches.split(",")]:
+    y = rng.uniform(0.02, 0.5, (B, 1, 1, 64)).astype(numpy.float32)
+    x = (y * numpy.linspace(1.5, 4, 64)).astype(numpy.float32)
+    xd, yd = torch.tensor(x).cuda(), torch.tensor(y).cuda()
+    w = CycleGANWrapper(10.0, 0.5, True)
+    model = w.define_model(xd, yd)
+    ops = w.define_train_ops(model, w.define_loss(model), 100000, generator_lr=2e-4, discriminator_lr=1e-4)
+    if world > 1:
+        ops.trainer.allreduce = parallel.GradientAllReduce()
+    for _ in range(a.warmup):
+        ops.train_iteration(xd, yd)
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        lg, ld = ops.train_iteration(xd, yd)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = parallel.max_over_ranks(e0.elapsed_time(e1), device="cuda")
+    if rank == 0:
+        print(json.dumps({"metric": "CycleGAN (x,y) pairs/s, 1 generator + 1 discriminator step per iteration",
+                          "value": world * B * a.steps / (ms / 1e3), "unit": "pairs/s", "n_gpus": world,
+                          "per_gpu_batch": B, "ms_per_iteration": ms / a.steps, "dtype": "f32",
+                          "generator_loss": lg.cpu().tolist(), "discriminator_loss": ld.cpu().tolist()}), flush=True)
+if world > 1:
+    torch.distributed.destroy_process_group()
