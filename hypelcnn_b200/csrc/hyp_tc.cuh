@@ -869,7 +869,10 @@ inline int launch_tc_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParam
   if (ntiles % CG) return fail(HYP_E_INVALID, "tc gemm: tile count is not a multiple of the CTA group size");
   if (p.b_rows % (8 * CG)) return fail(HYP_E_INVALID, "tc gemm: B rows must be a multiple of 8 per CTA");
   if (p.stages <= 0) p.stages = tc_pick_stages(p.b_rows / CG);
-  if (p.chunk_kb <= 0) p.chunk_kb = TC_DEFAULT_CHUNK_KB;
+  if (p.chunk_kb <= 0) {
+    static const int env_chunk = getenv("HYP_TC_CHUNK_KB") ? atoi(getenv("HYP_TC_CHUNK_KB")) : 0;  // experiments only
+    p.chunk_kb = env_chunk > 0 ? env_chunk : TC_DEFAULT_CHUNK_KB;
+  }
   if (p.stages < 2) return fail(HYP_E_INVALID, "tc gemm: B tile too large for two pipeline stages");
   p.ntiles = ntiles;
   const size_t smem = tc_smem_bytes(p.b_rows / CG, p.stages);
