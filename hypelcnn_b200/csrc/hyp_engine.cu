@@ -1109,7 +1109,7 @@ int hyp_gan_discriminator_backward(const float* x, const float* hidden, const fl
 }
 int hyp_gan_loss_grad(int mode, const float* a, const float* b, float target, float scale, int64_t numel, float* grad,
                       int accumulate, double* loss_acc, void* stream) {
-  HYP_CHECK_ARG(a && (mode == 0 || (mode == 1 && b)) && numel >= 0, "bad argument");
+  HYP_CHECK_ARG(a && (mode == 0 || mode == 2 || (mode == 1 && b)) && numel >= 0, "bad argument");
   if (numel == 0) return HYP_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   PROF("gan_loss_grad_kernel", 8.0 * numel,

@@ -638,10 +638,13 @@ __global__ void gan_loss_grad_kernel(int mode, const float* __restrict__ av, con
       const float d = av[i] - target;
       s += 0.5f * scale * d * d;
       g = scale * d;
-    } else {
+    } else if (mode == 1) {
       const float d = av[i] - bv[i];
       s += scale * fabsf(d);
       g = d > 0.f ? scale : (d < 0.f ? -scale : 0.f);
+    } else {  // mode 2 (tfgan wasserstein_*): sum scale * a, grad scale (scale carries the sign)
+      s += scale * av[i];
+      g = scale;
     }
     if (grad) grad[i] = accumulate ? grad[i] + g : g;
   }

@@ -195,7 +195,8 @@ int hyp_gan_discriminator_forward(const float* x, int64_t rows, int bands, const
 int hyp_gan_discriminator_backward(const float* x, const float* hidden, const float* gout, int64_t rows, int bands,
                                    const float* weights, float* gin, float* gweights, void* stream);
 /* loss terms + gradients.  mode 0 (tfgan least_squares_*): loss_acc += sum 0.5*scale*(a-target)^2, grad = scale*(a-target);
- * mode 1 (absolute_difference): loss_acc += sum scale*|a-b|, grad = scale*sign(a-b).  scale = weight / numel (means).
+ * mode 1 (absolute_difference): loss_acc += sum scale*|a-b|, grad = scale*sign(a-b);  mode 2 (tfgan wasserstein_*):
+ * loss_acc += sum scale*a, grad = scale (the sign rides on scale).  scale = weight / numel (means).
  * grad nullable; accumulate != 0 adds to it.  loss_acc: device double, nullable. */
 int hyp_gan_loss_grad(int mode, const float* a, const float* b, float target, float scale, int64_t numel, float* grad,
                       int accumulate, double* loss_acc, void* stream);

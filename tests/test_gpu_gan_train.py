@@ -120,3 +120,38 @@ def test_wrapper_trains_on_dummy_pairs():
     infer = CycleGANInferenceWrapper(trainer=ops.trainer)
     out = infer.construct_inference_graph(normal, True, False)  # x -> y: towards the shadowed level
     assert abs(out.mean().item() - 0.5) < abs(1.0 - 0.5)
+
+
+@pytest.mark.parametrize("swap", [False, True])
+def test_single_direction_gan_gradients_and_registry(swap):
+    """gan_x2y / gan_y2x (gan/wrappers/gan_wrapper.py): tfgan's default Wasserstein losses."""
+    from types import SimpleNamespace
+    from hypelcnn_b200.gan.wrapper_registry import get_wrapper
+    flags = SimpleNamespace(cycle_consistency_loss_weight=10.0, identity_loss_weight=0.5, use_identity_loss=True,
+                            discriminator_reg_scale=1e-3)
+    wrapper = get_wrapper("gan_y2x" if swap else "gan_x2y", flags)
+    x, y = _data(40, 64)
+    t = wrapper.define_model(x.view(40, 1, 1, 64), y.view(40, 1, 1, 64))
+    rng = numpy.random.default_rng(5)
+    t.gen_params.copy_(torch.tensor(rng.standard_normal(t.gen_params.numel()).astype(numpy.float32) * 0.05))
+    inp, real = (y, x) if swap else (x, y)
+    lg = t.generator_gradients(x, y).cpu()
+    G = t.G().double().cpu().requires_grad_(True)
+    D = t.DY().double().cpu().requires_grad_(True)
+    ref_g = -R.t_discriminator(R.t_generator(inp.double().cpu(), G), D.detach()).mean()
+    ref_g.backward()
+    assert abs(lg[0].item() - ref_g.item()) < 1e-5 * max(1.0, abs(ref_g.item()))
+    assert _rel(t.gen_grads[:t.ng], G.grad) < 2e-4
+    ld = t.discriminator_gradients(x, y, use_pool=False).cpu()
+    gen = R.t_generator(inp.double().cpu(), G.detach())
+    C = 64
+    ref_d = R.t_discriminator(gen, D).mean() - R.t_discriminator(real.double().cpu(), D).mean() + \
+        1e-3 * 0.5 * ((D[:C * C] ** 2).sum() + (D[C * C + C:2 * C * C + C] ** 2).sum())
+    ref_d.backward()
+    assert abs(ld[0].item() - ref_d.item()) < 1e-5 * max(1.0, abs(ref_d.item()))
+    assert _rel(t.dis_grads[:t.nd], D.grad) < 2e-4
+    ops = wrapper.define_train_ops(t, wrapper.define_loss(t), 100, generator_lr=2e-4, discriminator_lr=1e-4)
+    ops.train_iteration(x, y)
+    assert t.global_step == 1 and t.gen_steps == 1 and t.dis_steps == 1
+    with pytest.raises(NotImplementedError):
+        get_wrapper("dcl_gan", flags)
