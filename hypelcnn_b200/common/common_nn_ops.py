@@ -304,15 +304,46 @@ class HostBatchTrainer:
 
     def __init__(self, engine, allreduce=None):
         self.engine, self.allreduce = engine, allreduce
-        self._x = self._y = None
+        self._bufs = [None, None]   # two device batches: one being trained on, one being filled
+        self._cur = 0
+        self._pending = None        # (host_x data_ptr, buffer index, copy-done event) of a prefetched batch
+        self._copy_stream = None
 
-    def step(self, host_x, host_y):
-        if self._x is None or self._x.shape != host_x.shape:
-            self._x = torch.empty(host_x.shape, dtype=torch.float32, device=self.engine.device)
-            self._y = torch.empty(host_y.shape, dtype=torch.uint8, device=self.engine.device)
-        self._x.copy_(host_x, non_blocking=True)
-        self._y.copy_(host_y, non_blocking=True)
-        loss = self.engine.train_step(self._x, self._y, allreduce=self.allreduce)
+    def _buffers(self, i, host_x, host_y):
+        b = self._bufs[i]
+        if b is None or b[0].shape != host_x.shape:
+            b = (torch.empty(host_x.shape, dtype=torch.float32, device=self.engine.device),
+                 torch.empty(host_y.shape, dtype=torch.uint8, device=self.engine.device))
+            self._bufs[i] = b
+        return b
+
+    def step(self, host_x, host_y, prefetch=None):
+        """One train step on the host batch; returns the loss on the host.  prefetch = (next_host_x, next_host_y)
+        starts the NEXT step's host->device copy on a copy stream while this step computes — the device-side
+        counterpart of the reference's prefetch_to_device (common/common_nn_ops.py:200)."""
+        main = torch.cuda.current_stream()
+        if self._pending is not None and self._pending[0] == host_x.data_ptr():
+            _, self._cur, ev = self._pending          # this batch is already on its way
+            main.wait_event(ev)
+            x, y = self._bufs[self._cur]
+        else:
+            x, y = self._buffers(self._cur, host_x, host_y)
+            x.copy_(host_x, non_blocking=True)
+            y.copy_(host_y, non_blocking=True)
+        self._pending = None
+        if prefetch is not None:
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self.engine.device)
+            nxt = 1 - self._cur
+            nx, ny = self._buffers(nxt, prefetch[0], prefetch[1])
+            self._copy_stream.wait_stream(main)       # the buffer's previous step has been consumed
+            with torch.cuda.stream(self._copy_stream):
+                nx.copy_(prefetch[0], non_blocking=True)
+                ny.copy_(prefetch[1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+            self._pending = (prefetch[0].data_ptr(), nxt, ev)
+        loss = self.engine.train_step(x, y, allreduce=self.allreduce)
         return loss.cpu()  # synchronises: the step's result is on the host
 
 

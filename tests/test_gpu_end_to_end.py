@@ -106,3 +106,25 @@ def test_checkpoint_roundtrip(tmp_path):
     c.load_checkpoint(path, exclude_prefixes=("image_gen_net_",))
     assert torch.equal(c.variable("nn_core/image_gen_net_1/weights"), dec0)
     assert torch.equal(c.variable("nn_core/fc_final/weights"), a.variable("nn_core/fc_final/weights")) is False or True
+
+
+def test_host_batch_trainer_prefetch_is_equivalent():
+    """H2D of the next batch on a copy stream must not change any result."""
+    from hypelcnn_b200 import engine as E
+    from hypelcnn_b200.common.common_nn_ops import HostBatchTrainer
+    from tests.util import synthetic_batch
+    alg = {**HALG, "filter_count": 64, "batch_size": 32, "drop_out_ratio": 0.0}
+    batches = [synthetic_batch(32, 5, 21, 6, seed=s) for s in range(4)]
+    hx = [torch.tensor(x).pin_memory() for x, _ in batches]
+    hy = [torch.tensor(y).pin_memory() for _, y in batches]
+    losses = []
+    for prefetch in (False, True):
+        eng = E.PatchEngine(5, 21, 6, alg, max_batch=32)
+        eng.init_variables(2)
+        tr = HostBatchTrainer(eng)
+        out = []
+        for i in range(8):
+            nxt = (hx[(i + 1) % 4], hy[(i + 1) % 4]) if prefetch else None
+            out.append(tr.step(hx[i % 4], hy[i % 4], prefetch=nxt))
+        losses.append(torch.stack(out))
+    assert torch.allclose(losses[0], losses[1], rtol=2e-5, atol=1e-6), (losses[0] - losses[1]).abs().max()
