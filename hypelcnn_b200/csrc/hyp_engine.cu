@@ -1216,7 +1216,6 @@ int hyp_debug_tc_gemm(int mn_flags, const float* A, const float* B, int M, int N
   HYP_CHECK_ARG(A && B && D && M > 0 && N > 0 && K > 0, "bad argument");
   HYP_CHECK_ARG(N % 4 == 0, "N must be a multiple of 4 (output row alignment)");
   HYP_CHECK_ARG(ksplit >= 1 && (mn || ksplit == 1), "ksplit needs mn = 1");
-  HYP_CHECK_ARG(!(mn && cg == 2), "cta_group::2 is only built for K-major operands");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int lda_src = mn ? M : K, ldb_src = mn ? N : K;
   const int64_t a_rows = mn ? K : M, b_rows_src = mn ? K : N;
@@ -1266,7 +1265,7 @@ int hyp_debug_tc_gemm(int mn_flags, const float* A, const float* B, int M, int N
         s.a1 = kb0 * TC_KB;
         s.b0 = n0; s.b1 = kb0 * TC_KB;
         s.nb = (int)cdiv(s.n_mma, 32);
-        max_brows = std::max(max_brows, s.nb * 32);
+        max_brows = std::max(max_brows, cg * (int)cdiv(s.n_mma / cg, 32) * 32);
       }
       const int sidx = (int)segs.size();
       segs.push_back(s);
@@ -1288,7 +1287,7 @@ int hyp_debug_tc_gemm(int mn_flags, const float* A, const float* B, int M, int N
         tiles.push_back(t);
       }
     }
-  HYP_CHECK_ARG(cg == 1 || bn * (int)cdiv(max_brows, bn) == max_brows, "bad bn");
+  HYP_CHECK_ARG(mn || cg == 1 || bn * (int)cdiv(max_brows, bn) == max_brows, "bad bn");
   if ((rc = tc_finalize_tiles(tiles, segs))) return rc;
   TcSeg* dsegs = nullptr;
   TcTile* dtiles = nullptr;

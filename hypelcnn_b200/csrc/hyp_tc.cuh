@@ -443,9 +443,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int snb = __shfl_sync(0xffffffffu, wC.x, src);
         // B boxes this CTA loads: K-major boxes of bn/CG rows, MN-major boxes of 32 columns
         const uint32_t b_box_bytes = MN ? 4096u : (uint32_t)(p.bn / CG) * 128u;
-        const int nb = MN ? snb / CG : snb;
-        const int b_first = MN ? (int)rank * nb : 0;               // first 32-column box
+        // MN-major: this CTA's half of the N columns starts at column rank * n / CG and is loaded as 32-column boxes
+        // (the last one may run past the half: harmless extra columns)
+        const int nb = MN ? (sn / CG + 31) / 32 : snb;
+        const int b_col0 = MN ? (int)rank * (sn / CG) : 0;
         const int b_row0 = MN ? 0 : (int)rank * (sn / CG);          // first B row
+        (void)snb;
         const uint32_t tx_cta = 2u * TC_PLANE_A + 2u * (uint32_t)nb * b_box_bytes;
         for (int kb = 0; kb < snk; kb++) {
           { const long long t0 = p.timing ? clock64() : 0; mbar_wait(empty_bar(stage), phase ^ 1u); if (p.timing) tm_wait_empty += clock64() - t0; }
@@ -466,7 +469,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int i = 0; i < 4; i++)
                 tma_load_4d_u<CG>(pred, a_s + pl * TC_PLANE_A + i * 4096, &tmA, fb, sa0 + i * 32, sa1 + kb * TC_KB, sa2, pl);
               for (int j = 0; j < nb; j++)
-                tma_load_4d_u<CG>(pred, b_s + pl * b_plane + j * 4096, &tmB, fb, sb0 + (b_first + j) * 32, sb1 + kb * TC_KB,
+                tma_load_4d_u<CG>(pred, b_s + pl * b_plane + j * 4096, &tmB, fb, sb0 + b_col0 + j * 32, sb1 + kb * TC_KB,
                                   sb2, pl);
             }
           }

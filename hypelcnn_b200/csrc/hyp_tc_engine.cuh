@@ -301,6 +301,11 @@ static void finish_launch(PlanBuf& pb, TcLaunch& l) {
   l.ntiles = (int)pb.tiles.size() - l.tile0;
 }
 
+// wgrad (MN-major) launches run as CTA pairs over two adjacent 128-row tiles of the M side when their count is even
+// (the pair shares its gz columns); B rows reserved per stage: 32-column boxes covering n / cg columns, per CTA
+static inline int wg_cg(int mt) { return (mt % 2 == 0) ? 2 : 1; }
+static inline int wg_brows(int n_mma, int cg) { return cg * (int)cdiv(n_mma / cg, 32) * 32; }
+
 // K-major launches run as CTA pairs (cta_group::2): consecutive tiles (2i, 2i+1) must share their
 // segment list.  A run of tiles that differ only in their row block is closed with a phantom
 // tile (no valid rows; its A box is out of bounds and reads zeros) when its length is odd.
@@ -479,20 +484,22 @@ static int tc_plan(hyp_model& m, int64_t B) {
         if ((rc = map4(&T.wg.tmA, a0, Cin, rows_in, 1, tin.Cp, (uint64_t)rows_in * tin.Cp, tin.plane_elems, 32, 32, true))) return rc;
         if ((rc = map4(&T.wg.tmB, gz0, Cout, rows_out, 1, T.Gp, (uint64_t)rows_out * T.Gp, S.gz_plane_elems, 32, 32, true))) return rc;
         T.wg.mn = true; T.wg.bn = 32; T.wg.b_rows = 0; T.wg.tile0 = (int)pb.tiles.size();
+        T.wg.cg = wg_cg(mt);
         const int kblocks = (int)cdiv(rows_out, 32);
         int ksplit = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(2 * tc_sm_count(), mt * ntn), std::max(1, kblocks / 4)));
         const int kb_per = (int)cdiv(kblocks, ksplit);
         // K piece outermost: the (im, j) tiles of one row range run in the same wave and share their A / gz rows
         // through L2, so every activation and gradient row crosses HBM once
         for (int kb0 = 0; kb0 < kblocks; kb0 += kb_per)
-          for (int im = 0; im < mt; im++)
-            for (int j = 0; j < ntn; j++) {
+          for (int j = 0; j < ntn; j++)
+            for (int im = 0; im < mt; im++) {  // adjacent M tiles are consecutive: CTA pairs share (j, kb0)
               const int width = std::min(nw, Cout - j * nw);
               TcSeg s{};
-              s.a0 = im * 128; s.a1 = kb0 * 32; s.b0 = j * nw; s.b1 = kb0 * 32;
+              s.a1 = kb0 * 32; s.b0 = j * nw; s.b1 = kb0 * 32;
               s.nk = std::min(kb_per, kblocks - kb0); s.n_mma = r16(width); s.nb = (int)cdiv(s.n_mma, 32);
-              T.wg.b_rows = std::max(T.wg.b_rows, s.nb * 32);
+              T.wg.b_rows = std::max(T.wg.b_rows, wg_brows(s.n_mma, T.wg.cg));
               TcTile t = blank_tile();
+              t.a0_add = im * 128;
               t.seg_begin = (int)pb.segs.size(); t.seg_count = 1; t.total_kb = s.nk;
               t.m_valid = std::min(128, Cin - im * 128);
               t.ncb = 1; t.ld_out = Cout;
@@ -610,6 +617,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
         if ((rc = map4(&T.wg.tmB, gz0, T.Gp, B, PP, T.Gp, (uint64_t)B * T.Gp, S.gz_plane_elems, 32, 32, true))) return rc;
         T.wg.mn = true; T.wg.bn = 32; T.wg.b_rows = 0; T.wg.tile0 = (int)pb.tiles.size();
         const int mt = (int)cdiv(Cin, 128);
+        T.wg.cg = wg_cg(mt);
         const int nkb = (int)cdiv(B, 32);
         int64_t pairs = 0;
         for (auto& tp : taps) pairs += (int64_t)(P - std::abs(tp.first)) * (P - std::abs(tp.second));
@@ -637,16 +645,17 @@ static int tc_plan(hyp_model& m, int64_t B) {
               const int s0 = g * spg, s1 = std::min(std::min(NS, s0 + spg), (R - ring) * nt);
               if (s1 <= s0) continue;
               const int ncols = (s1 - s0) * fpad;
-              for (int im = 0; im < mt; im++)
-                for (size_t c0 = 0; c0 < ps.size(); c0 += pc) {
+              for (size_t c0 = 0; c0 < ps.size(); c0 += pc)
+                for (int im = 0; im < mt; im++) {  // adjacent M tiles are consecutive: CTA pairs share the gz columns
                   TcTile t = blank_tile();
                   t.seg_begin = (int)pb.segs.size();
+                  t.a0_add = im * 128;
                   for (size_t ci = c0; ci < std::min(ps.size(), c0 + (size_t)pc); ci++) {
                     TcSeg s{};
-                    s.a0 = im * 128; s.a1 = kb0 * 32; s.a2 = ps[ci] + dy * P + dx;
+                    s.a1 = kb0 * 32; s.a2 = ps[ci] + dy * P + dx;
                     s.b0 = s0 * fpad; s.b1 = kb0 * 32; s.b2 = ps[ci];
                     s.nk = kbn; s.n_mma = r16(ncols); s.nb = (int)cdiv(s.n_mma, 32);
-                    T.wg.b_rows = std::max(T.wg.b_rows, s.nb * 32);
+                    T.wg.b_rows = std::max(T.wg.b_rows, wg_brows(s.n_mma, T.wg.cg));
                     t.total_kb += s.nk;
                     pb.segs.push_back(s);
                   }
@@ -740,15 +749,17 @@ static int tc_plan(hyp_model& m, int64_t B) {
         if ((rc = map4(&T.wg.tmA, a0, Ct, B, PP, tin.Cp, (uint64_t)B * tin.Cp, tin.plane_elems, 32, 32, true))) return rc;
         if ((rc = map4(&T.wg.tmB, gz0, Cout, B, 1, T.Gp, (uint64_t)B * T.Gp, S.gz_plane_elems, 32, 32, true))) return rc;
         T.wg.mn = true; T.wg.bn = 32; T.wg.b_rows = 0; T.wg.tile0 = (int)pb.tiles.size();
+        T.wg.cg = wg_cg((int)cdiv(Ct, 128));
         for (int pos = 0; pos < PP; pos++)
-          for (int im = 0; im < (int)cdiv(Ct, 128); im++)
-            for (int j = 0; j < ntn; j++) {
+          for (int j = 0; j < ntn; j++)
+            for (int im = 0; im < (int)cdiv(Ct, 128); im++) {
               const int width = std::min(nw, Cout - j * nw);
               TcSeg s{};
-              s.a0 = im * 128; s.a2 = pos; s.b0 = j * nw; s.nk = (int)cdiv(B, 32); s.n_mma = r16(width);
+              s.a2 = pos; s.b0 = j * nw; s.nk = (int)cdiv(B, 32); s.n_mma = r16(width);
               s.nb = (int)cdiv(s.n_mma, 32);
-              T.wg.b_rows = std::max(T.wg.b_rows, s.nb * 32);
+              T.wg.b_rows = std::max(T.wg.b_rows, wg_brows(s.n_mma, T.wg.cg));
               TcTile t = blank_tile();
+              t.a0_add = im * 128;
               t.seg_begin = (int)pb.segs.size(); t.seg_count = 1; t.total_kb = s.nk;
               t.m_valid = std::min(128, Ct - im * 128); t.ncb = 1; t.ld_out = Cout;
               t.cb[0].out_off = L.w_off[0] + ((int64_t)pos * Ct + im * 128) * Cout + j * nw;
@@ -793,7 +804,8 @@ static int tc_run(hyp_model& m, const TcLaunch& l, float* out, float* stats, int
   if (timing_on && !per_layer && scope) full += std::string("/") + scope;
   g_tc_timing_tag = full.c_str();
   g_prof.begin(st, full.c_str(), flops, 0.0);
-  const int rc = l.mn ? launch_tc<true, 1>(l.tmA, l.tmB, p, l.ntiles, st)
+  const int rc = l.mn ? (l.cg == 2 ? launch_tc<true, 2>(l.tmA, l.tmB, p, l.ntiles, st)
+                                   : launch_tc<true, 1>(l.tmA, l.tmB, p, l.ntiles, st))
                       : (l.cg == 2 ? launch_tc<false, 2>(l.tmA, l.tmB, p, l.ntiles, st)
                                    : launch_tc<false, 1>(l.tmA, l.tmB, p, l.ntiles, st));
   g_prof.end(st);

@@ -224,7 +224,7 @@ int hyp_model_dropout_mask(hyp_model* m, const char* layer_scope, uint64_t seed,
                            uint8_t* mask_out, void* stream);
 /* probe of the tcgen05/TMA segment-GEMM building block used by the tensor-core precision
  * modes (3xTF32 split).  mn bit 0 = 0: A[M,K], B[N,K] -> D = A*B^T (K-major); 1: A[K,M], B[K,N]
- * -> D = A^T*B (MN-major).  mn bit 1: run as CTA pairs (tcgen05 cta_group::2, K-major only).
+ * -> D = A^T*B (MN-major).  mn bit 1: run as CTA pairs (tcgen05 cta_group::2).
  * stats (nullable): [ceil(M/128)][2][N] per-tile column sums / sums of squares. */
 int hyp_debug_tc_gemm(int mn, const float* A, const float* B, int M, int N, int K, float* D,
                       float* stats, int raw_hi, int bn, int ksplit, int chunk_kb, void* stream);

@@ -103,6 +103,19 @@ def test_mnmajor_3xtf32_matches_fp64(M, N, K, ksplit):
     assert err < max(3e-6, 4 * fp32), (err, fp32)
 
 
+@pytest.mark.parametrize("M,N,K,ksplit", [(256, 64, 64, 1), (480, 240, 1000, 1), (480, 480, 4096, 4), (145, 120, 777, 3),
+                                          (240, 128, 300, 2)])
+def test_mnmajor_cta_pair_matches_fp64(M, N, K, ksplit):
+    """wgrad layout as CTA pairs: two 128-row tiles of the M side share the B columns (each CTA loads half of them)."""
+    g = torch.Generator().manual_seed(M + N + K + 7)
+    A = torch.randn((K, M), generator=g)
+    B = torch.randn((K, N), generator=g)
+    ref = A.double().T @ B.double()
+    err = rel_err(tc_gemm(3, A, B, ksplit=ksplit), ref)
+    fp32 = rel_err(A.T @ B, ref)
+    assert err < max(3e-6, 4 * fp32), (err, fp32)
+
+
 def test_epilogue_column_statistics():
     g = torch.Generator().manual_seed(5)
     A = torch.randn((300, 96), generator=g)
