@@ -34,6 +34,8 @@ struct Resid {
   int* idx = nullptr;  // device [Cout]   out channel -> src channel
   int* lo = nullptr;   // device [Csrc]   src channel -> [lo, hi) out channels (idx is monotone)
   int* hi = nullptr;
+  int pattern = 0;     // 0 generic; 2: tf.repeat by 2 (idx[j] = j / 2); 3: strided gather (idx[j] = step * j)
+  int step = 0;
 };
 
 struct Tensor {
@@ -177,6 +179,13 @@ struct Builder {
       for (int c = 0; c < cs; c++)
         for (int j = lo[c]; j < hi[c]; j++)
           if (idx[j] != c) return -1;
+      bool rep2 = L.Cout == 2 * cs, strided = cs % L.Cout == 0 && cs > L.Cout;
+      for (int j = 0; j < L.Cout; j++) {
+        rep2 = rep2 && idx[j] == j / 2;
+        strided = strided && idx[j] == (cs / L.Cout) * j;
+      }
+      if (rep2 && cs % 4 == 0) r.pattern = 2;
+      else if (strided) { r.pattern = 3; r.step = cs / L.Cout; }
       r.idx = upload(idx);
       r.lo = upload(lo);
       r.hi = upload(hi);

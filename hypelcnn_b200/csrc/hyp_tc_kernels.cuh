@@ -449,12 +449,14 @@ __global__ void __launch_bounds__(256) tc_bn_bwd_apply_v4_kernel(const TcBnBwdAr
 }
 
 // residual backward, 4 source channels per thread.  MODE 0: identity (gsrc += gout); MODE 1: generic
-// contiguous ranges [lo[c], hi[c]) of the consumer's channels.
+// contiguous ranges [lo[c], hi[c]) of the consumer's channels; MODE 2: tf.repeat by 2 (source channel c feeds
+// consumer channels 2c, 2c+1: two float4 loads, pairwise sums); MODE 3: gather with stride `step` (consumer channel
+// j reads source channel step*j: only every step-th source channel gets a gradient).
 template <int TX, int MODE>
 __global__ void __launch_bounds__(256) tc_resid_bwd_v4_kernel(const float* __restrict__ gout, int ldg, float* __restrict__ gsrc,
                                                               int lds, int Csrc, const int* __restrict__ lo,
                                                               const int* __restrict__ hi, int64_t rows, int accumulate,
-                                                              int rows_per_block) {
+                                                              int rows_per_block, int step) {
   constexpr int TY = 256 / TX;
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const int c0 = (blockIdx.x * TX + tx) * 4;
@@ -475,6 +477,16 @@ __global__ void __launch_bounds__(256) tc_resid_bwd_v4_kernel(const float* __res
       if (rr < r1) {
         if (MODE == 0) {
           acc[u] = *reinterpret_cast<const float4*>(gout + rr * ldg + c0);
+        } else if (MODE == 2) {
+          const float4 p = *reinterpret_cast<const float4*>(gout + rr * ldg + 2 * c0);
+          const float4 q = *reinterpret_cast<const float4*>(gout + rr * ldg + 2 * c0 + 4);
+          acc[u] = make_float4(p.x + p.y, p.z + p.w, q.x + q.y, q.z + q.w);
+        } else if (MODE == 3) {
+          const float* gp = gout + rr * ldg;
+          float v[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) v[k] = ((c0 + k) % step == 0 && c0 + k < Csrc) ? gp[(c0 + k) / step] : 0.f;
+          acc[u] = make_float4(v[0], v[1], v[2], v[3]);
         } else {
           const float* gp = gout + rr * ldg;
           float v[4] = {0.f, 0.f, 0.f, 0.f};
