@@ -631,29 +631,35 @@ static int tc_plan(hyp_model& m, int64_t B) {
         while (nslice < nkb && level_bytes / nslice > slice_bytes) nslice *= 2;
         const int slice_kb = (int)cdiv(nkb, nslice);
         nslice = (int)cdiv(nkb, slice_kb);
-        const int pc = (int)std::max<int64_t>(1, cdiv(pairs * mt * ngroups, 2 * tc_sm_count()));  // positions per tile
+        // tile = (slice, chunk of output positions, tap, slot group, M tile).  Order: slice, then position chunk, then
+        // tap: the taps of one chunk reuse its gz rows back to back and the slice's activation rows stay L2-resident
+        // across chunks (every position is in every other's 7x7 neighbourhood).
+        const int cgw = T.wg.cg;
+        const int pc = (int)std::min<int64_t>(PP, std::max<int64_t>(1, cdiv((int64_t)PP * taps.size() * mt * ngroups / cgw,
+                                                                        4 * (tc_sm_count() / cgw))));
         for (int sl = 0; sl < nslice; sl++) {
           const int kb0 = sl * slice_kb, kbn = std::min(slice_kb, nkb - kb0);
-          for (auto& tp : taps) {
-            const int dy = tp.first, dx = tp.second, ring = std::max(std::abs(dy), std::abs(dx));
-            std::vector<int> ps;  // output positions whose tap source is inside the patch
-            for (int p = 0; p < PP; p++) {
-              const int ph = p / P, pw = p % P;
-              if (ph + dy >= 0 && ph + dy < P && pw + dx >= 0 && pw + dx < P) ps.push_back(p);
-            }
-            for (int g = 0; g < ngroups; g++) {
-              const int s0 = g * spg, s1 = std::min(std::min(NS, s0 + spg), (R - ring) * nt);
-              if (s1 <= s0) continue;
-              const int ncols = (s1 - s0) * fpad;
-              for (size_t c0 = 0; c0 < ps.size(); c0 += pc)
+          for (int pc0 = 0; pc0 < PP; pc0 += pc)
+            for (auto& tp : taps) {
+              const int dy = tp.first, dx = tp.second, ring = std::max(std::abs(dy), std::abs(dx));
+              std::vector<int> ps;  // output positions of the chunk whose tap source is inside the patch
+              for (int p = pc0; p < std::min(PP, pc0 + pc); p++) {
+                const int ph = p / P, pw = p % P;
+                if (ph + dy >= 0 && ph + dy < P && pw + dx >= 0 && pw + dx < P) ps.push_back(p);
+              }
+              if (ps.empty()) continue;
+              for (int g = 0; g < ngroups; g++) {
+                const int s0 = g * spg, s1 = std::min(std::min(NS, s0 + spg), (R - ring) * nt);
+                if (s1 <= s0) continue;
+                const int ncols = (s1 - s0) * fpad;
                 for (int im = 0; im < mt; im++) {  // adjacent M tiles are consecutive: CTA pairs share the gz columns
                   TcTile t = blank_tile();
                   t.seg_begin = (int)pb.segs.size();
                   t.a0_add = im * 128;
-                  for (size_t ci = c0; ci < std::min(ps.size(), c0 + (size_t)pc); ci++) {
+                  for (int pp : ps) {
                     TcSeg s{};
-                    s.a1 = kb0 * 32; s.a2 = ps[ci] + dy * P + dx;
-                    s.b0 = s0 * fpad; s.b1 = kb0 * 32; s.b2 = ps[ci];
+                    s.a1 = kb0 * 32; s.a2 = pp + dy * P + dx;
+                    s.b0 = s0 * fpad; s.b1 = kb0 * 32; s.b2 = pp;
                     s.nk = kbn; s.n_mma = r16(ncols); s.nb = (int)cdiv(s.n_mma, 32);
                     T.wg.b_rows = std::max(T.wg.b_rows, wg_brows(s.n_mma, T.wg.cg));
                     t.total_kb += s.nk;
@@ -672,8 +678,8 @@ static int tc_plan(hyp_model& m, int64_t B) {
                   }
                   pb.tiles.push_back(t);
                 }
+              }
             }
-          }
         }
         T.wg.windowed = true;
         finish_launch(pb, T.wg);

@@ -1,4 +1,4 @@
-for mb in 32 64 128 256 100000; do
+for mb in 48 96 128 256; do
   HYP_WG_SLICE_MB=$mb HYP_PROF_LAYERS=1 timeout 300 python bench.py --steps 4 --warmup 3 --no-cpu-baseline --prof-out gpurun_out/prof_$mb.json > gpurun_out/bench_$mb.log 2>&1
   python - <<PY
 import json
