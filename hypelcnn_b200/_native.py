@@ -86,6 +86,11 @@ _PROTOS = {
     "hyp_gan_discriminator_backward": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P]),
     "hyp_gan_loss_grad": (_I, [_I, _P, _P, _F, _F, _L, _P, _I, _P, _P]),
     "hyp_gan_l2_regularizer": (_I, [_P, _P, _L, _F, _P, _P]),
+    "hyp_gan_generator_backward_enc": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P]),
+    "hyp_gan_feature_discriminator_weight_count": (_L, [_I, _I, _I]),
+    "hyp_gan_feature_discriminator_forward": (_I, [_P, _L, _I, _I, _I, _P, _P, _P, _P]),
+    "hyp_gan_feature_discriminator_backward": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _I, _P, _P, _P, _P]),
+    "hyp_gan_patchnce": (_I, [_P, _P, _P, _P, _L, _I, _I, _F, _F, _I, _P, _P, _P, _P, _P, _P]),
     "hyp_argmax_confusion": (_I, [_P, _P, _L, _I, _P, _P, _P]),
     "hyp_scatter_class_map": (_I, [_P, _P, _L, _I, _I, _P, _P]),
     "hyp_model_debug_tensor": (_I, [_P, ctypes.c_char_p, _I, ctypes.POINTER(_P), ctypes.POINTER(_L)]),

@@ -1056,13 +1056,14 @@ int hyp_gan_generator_train_forward(const float* x, int64_t rows, int bands, con
   return HYP_OK;
 }
 
-int hyp_gan_generator_backward(const float* nets, const float* gout, int64_t rows, int bands, const float* weights,
-                               float* gin, float* gweights, void* stream) {
-  HYP_CHECK_ARG(nets && gout && weights && gweights, "null argument");
+static int gan_generator_backward_impl(const float* nets, const float* gout, const float* gout_enc, int64_t rows,
+                                       int bands, const float* weights, float* gin, float* gweights, void* stream) {
+  HYP_CHECK_ARG(nets && (gout || gout_enc) && weights && gweights, "null argument");
   HYP_CHECK_ARG(bands >= 8 && bands <= 256 && rows >= 0, "bands out of range (8..256)");
   if (rows == 0) return HYP_OK;
   GanGenBwdArgs a;
-  a.nets = nets; a.gout = gout; a.rows = rows; a.C = bands; a.weights = weights; a.gin = gin; a.gweights = gweights;
+  a.nets = nets; a.gout = gout; a.gout_enc = gout_enc; a.rows = rows; a.C = bands; a.weights = weights; a.gin = gin;
+  a.gweights = gweights;
   const int nw = gan_gen_weight_count(bands);
   const size_t smem = (size_t)(2 * ((nw + 3) & ~3) + 4 * 17 * bands) * sizeof(float);
   static bool attr = false;
@@ -1077,13 +1078,24 @@ int hyp_gan_generator_backward(const float* nets, const float* gout, int64_t row
   return HYP_OK;
 }
 
+int hyp_gan_generator_backward(const float* nets, const float* gout, int64_t rows, int bands, const float* weights,
+                               float* gin, float* gweights, void* stream) {
+  HYP_CHECK_ARG(gout, "null argument");
+  return gan_generator_backward_impl(nets, gout, nullptr, rows, bands, weights, gin, gweights, stream);
+}
+
+int hyp_gan_generator_backward_enc(const float* nets, const float* gout, const float* gout_enc, int64_t rows, int bands,
+                                   const float* weights, float* gin, float* gweights, void* stream) {
+  return gan_generator_backward_impl(nets, gout, gout_enc, rows, bands, weights, gin, gweights, stream);
+}
+
 static int gan_disc_launch(bool backward, const GanDiscArgs& a, cudaStream_t st) {
   const int C = a.C, H = C / 2;
   const int nw = C * C + C + C * C + C + C * H + H, nwp = (nw + 3) & ~3;
   static bool attr = false;
   if (!attr) {
-    HYP_CUDA(cudaFuncSetAttribute(gan_discriminator_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    HYP_CUDA(cudaFuncSetAttribute(gan_discriminator_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    HYP_CUDA(cudaFuncSetAttribute(gan_discriminator_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    HYP_CUDA(cudaFuncSetAttribute(gan_discriminator_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
   const unsigned grid = (unsigned)std::min<int64_t>(cdiv(a.rows, 8), 148 * 2);
@@ -1093,6 +1105,7 @@ static int gan_disc_launch(bool backward, const GanDiscArgs& a, cudaStream_t st)
   } else {
     const int wpad = ((2 * C * (C + 1) + C * (H + 1)) + 3) & ~3;
     const size_t smem = (size_t)(wpad + (a.gweights ? nwp : 0) + 8 * 6 * C) * sizeof(float);
+    HYP_CHECK_ARG(smem <= 227 * 1024, "bands too large for the discriminator backward kernel's shared memory");
     PROF("gan_discriminator_bwd_kernel", 4.0 * a.rows * 4.5 * C, (gan_discriminator_bwd_kernel<<<grid, 256, smem, st>>>(a)));
   }
   return HYP_OK;
@@ -1130,6 +1143,90 @@ int hyp_gan_l2_regularizer(const float* weights, float* grads, int64_t n, float 
   if (n == 0) return HYP_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   PROF("gan_l2_reg_kernel", 8.0 * n, (gan_l2_reg_kernel<<<ew_grid(n), 256, 0, st>>>(weights, grads, n, scale, loss_acc)));
+  return HYP_OK;
+}
+
+static int featdisc_launch(bool backward, GanFeatArgs a, int patch_count, cudaStream_t st) {
+  HYP_CHECK_ARG(a.x && a.weights && a.z && a.sumsq, "null argument");
+  HYP_CHECK_ARG(patch_count >= 1 && a.C >= patch_count, "bad patch_count");
+  a.ps = a.C / patch_count;
+  HYP_CHECK_ARG(a.ps >= 4 && a.ps <= 32 && a.E >= 1 && a.E <= NCE_MAX_E, "slice width (4..32) / embedding size (1..8)");
+  const int slices = (a.C + a.ps - 1) / a.ps;
+  HYP_CHECK_ARG(slices <= NCE_MAX_S, "too many slices");
+  if (a.rows == 0) return HYP_OK;
+  const int nrows_act = 2 * a.ps + a.ps / 4 + a.ps / 2 + a.E;
+  const size_t smem = (size_t)(((featdisc_slice_weights(a.ps, a.E) + 3) & ~3) + (backward ? 2 : 1) * nrows_act * FD_PITCH) *
+                      sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    HYP_CUDA(cudaFuncSetAttribute(gan_featdisc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    HYP_CUDA(cudaFuncSetAttribute(gan_featdisc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    attr = true;
+  }
+  dim3 grid((unsigned)cdiv(a.rows, FD_ROWS), (unsigned)slices);
+  if (backward)
+    PROF("gan_featdisc_bwd_kernel", 4.0 * a.rows * (2 * a.C + 2 * slices * a.E),
+         (gan_featdisc_bwd_kernel<<<grid, FD_ROWS, smem, st>>>(a)));
+  else
+    PROF("gan_featdisc_fwd_kernel", 4.0 * a.rows * (a.C + slices * a.E),
+         (gan_featdisc_fwd_kernel<<<grid, FD_ROWS, smem, st>>>(a)));
+  return HYP_OK;
+}
+
+int64_t hyp_gan_feature_discriminator_weight_count(int bands, int patch_count, int embedded_feature_size) {
+  if (patch_count < 1 || bands < patch_count) return -1;
+  const int ps = bands / patch_count;
+  return (int64_t)((bands + ps - 1) / ps) * featdisc_slice_weights(ps, embedded_feature_size);
+}
+
+int hyp_gan_feature_discriminator_forward(const float* x, int64_t rows, int bands, int patch_count,
+                                          int embedded_feature_size, const float* weights, float* z, float* sumsq,
+                                          void* stream) {
+  HYP_CHECK_ARG(rows >= 0 && bands >= 4 && bands <= GAN_MAX_C, "bad shape");
+  GanFeatArgs a{};
+  a.x = x; a.rows = rows; a.C = bands; a.E = embedded_feature_size; a.weights = weights; a.z = z; a.sumsq = sumsq;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (sumsq && patch_count >= 1 && bands >= patch_count) {
+    const int ps = bands / patch_count;
+    HYP_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float) * ((bands + ps - 1) / ps), st));
+  }
+  return featdisc_launch(false, a, patch_count, st);
+}
+
+int hyp_gan_feature_discriminator_backward(const float* x, const float* z, const float* sumsq, const float* gf,
+                                           const float* dot, int64_t rows, int bands, int patch_count,
+                                           int embedded_feature_size, const float* weights, float* gin, float* gweights,
+                                           void* stream) {
+  HYP_CHECK_ARG(rows >= 0 && bands >= 4 && bands <= GAN_MAX_C, "bad shape");
+  HYP_CHECK_ARG(gf && dot && (gin || gweights), "null argument");
+  GanFeatArgs a{};
+  a.x = x; a.rows = rows; a.C = bands; a.E = embedded_feature_size; a.weights = weights;
+  a.z = const_cast<float*>(z); a.sumsq = const_cast<float*>(sumsq); a.gf = gf; a.dot = dot; a.gin = gin;
+  a.gweights = gweights;
+  return featdisc_launch(true, a, patch_count, static_cast<cudaStream_t>(stream));
+}
+
+int hyp_gan_patchnce(const float* z_gen, const float* z_real, const float* sumsq_gen, const float* sumsq_real,
+                     int64_t rows, int slices, int embedded_feature_size, float tau, float scale, int fused_grad,
+                     float* g_gen, float* g_real, float* dot_gen, float* dot_real, double* loss_acc, void* stream) {
+  HYP_CHECK_ARG(z_gen && z_real && sumsq_gen && sumsq_real, "null argument");
+  HYP_CHECK_ARG(rows >= 0 && slices >= 1 && slices <= NCE_MAX_S && embedded_feature_size >= 1 &&
+                    embedded_feature_size <= NCE_MAX_E && tau > 0.f,
+                "bad shape");
+  HYP_CHECK_ARG((g_gen != nullptr) == (g_real != nullptr), "g_gen and g_real go together");
+  HYP_CHECK_ARG(!g_gen || (dot_gen && dot_real), "dot_gen / dot_real are required with the gradients");
+  if (rows == 0) return HYP_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (g_gen) {
+    HYP_CUDA(cudaMemsetAsync(dot_gen, 0, sizeof(float) * slices, st));
+    HYP_CUDA(cudaMemsetAsync(dot_real, 0, sizeof(float) * slices, st));
+  }
+  GanNceArgs a;
+  a.zg = z_gen; a.zr = z_real; a.ssg = sumsq_gen; a.ssr = sumsq_real; a.rows = rows; a.S = slices;
+  a.E = embedded_feature_size; a.inv_tau = 1.f / tau; a.scale = scale; a.fused_grad = fused_grad; a.gfg = g_gen;
+  a.gfr = g_real; a.dotg = dot_gen; a.dotr = dot_real; a.loss_acc = loss_acc;
+  const unsigned grid = (unsigned)std::min<int64_t>(cdiv(rows, 4), 148 * 16);
+  PROF("gan_patchnce_kernel", 16.0 * rows * slices * embedded_feature_size, (gan_patchnce_kernel<<<grid, 128, 0, st>>>(a)));
   return HYP_OK;
 }
 

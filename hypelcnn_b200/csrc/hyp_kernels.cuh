@@ -415,7 +415,8 @@ __global__ void __launch_bounds__(128) gan_generator_fwd_kernel(const GanGenArgs
 //   net_l = act_l + net_{l-1} + net_{l-2}   (l = 1: + net_0 only; l = 7: no residual)
 struct GanGenBwdArgs {
   const float* nets;
-  const float* gout;
+  const float* gout;      // dL/dnet7 [rows][C]; nullable: the decoder (net5..net7) is then skipped
+  const float* gout_enc;  // dL/dnet4 (the encoder output, create_only_encoder=True) [rows][C], nullable, added
   int64_t rows;
   int C;
   const float* weights;
@@ -442,9 +443,12 @@ __global__ void __launch_bounds__(128) gan_generator_bwd_kernel(const GanGenBwdA
   float* dpre = G + 8 * C;                 // [C]
   for (int64_t r = (int64_t)blockIdx.x * nwarps + warp; r < a.rows; r += (int64_t)gridDim.x * nwarps) {
     for (int i = lane; i < 8 * C; i += 32) { nets[i] = a.nets[r * 8 * C + i]; G[i] = 0.f; }
-    for (int c = lane; c < C; c += 32) G[7 * C + c] = a.gout[r * C + c];
+    if (a.gout)
+      for (int c = lane; c < C; c += 32) G[7 * C + c] = a.gout[r * C + c];
+    if (a.gout_enc)
+      for (int c = lane; c < C; c += 32) G[4 * C + c] = a.gout_enc[r * C + c];
     __syncwarp();
-    for (int l = 7; l >= 1; l--) {
+    for (int l = a.gout ? 7 : 4; l >= 1; l--) {
       const int k = K[l - 1], left = (k - 1) / 2;
       const float* wl = w + woff[l - 1];
       const float* in = nets + (l - 1) * C;
@@ -675,6 +679,243 @@ __global__ void gan_l2_reg_kernel(const float* __restrict__ w, float* __restrict
     s = warp_sum(s);
     if (threadIdx.x == 0 && loss_acc) atomicAdd(loss_acc, (double)s);
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// CUT / DCLGAN patch feature discriminator (gan/shadow_data_models.py:126-149): the C-band encoder embedding is cut
+// into slices of ps = C / patch_count bands (the last slice is ragged when ps does not divide C — 64 bands, 6 patches
+// give 7 slices, the last 4 wide); every slice has its own 4-layer MLP  in -> ps -> ps/4 -> ps/2 -> E, leaky_relu(0.1)
+// after every layer (the arg_scope default also applies to the last), and the [rows, E] output of a slice is divided
+// by its norm over the WHOLE batch (tf.math.l2_normalize with axis=None, epsilon 1e-12).
+// A CTA owns 128 rows of one slice: the slice's weights and the per-row activations ([dim][129] so that both the
+// row-per-thread MLP and the transposed loads / weight-gradient reductions are bank-conflict free) sit in shared memory.
+// forward writes the un-normalised z and adds sum z^2 to sumsq[slice]; the division happens in the consumers.
+struct GanFeatArgs {
+  const float* x;        // [rows][C]
+  int64_t rows;
+  int C, ps, E;
+  const float* weights;  // per slice: W1 [in][ps] b1 | W2 [ps][ps/4] b2 | W3 [ps/4][ps/2] b3 | W4 [ps/2][E] b4
+  float* z;              // [rows][slices][E]   forward: out, backward: in
+  float* sumsq;          // [slices]            forward: +=, backward: in
+  const float* gf;       // backward: dL/d(normalised embedding) [rows][slices][E]
+  const float* dot;      // backward: [slices] sum over the batch of gf * z
+  float* gin;            // backward, nullable: [rows][C]
+  float* gweights;       // backward, nullable: +=
+};
+constexpr int FD_ROWS = 128, FD_PITCH = 129;
+__host__ __device__ inline int featdisc_slice_weights(int ps, int E) {
+  return ps * ps + ps + ps * (ps / 4) + ps / 4 + (ps / 4) * (ps / 2) + ps / 2 + (ps / 2) * E + E;
+}
+// forward of one CTA's rows; returns with a0..a4 in act (a_l at row offset aoff[l]) and all threads synchronised
+__device__ __forceinline__ void featdisc_forward_block(const GanFeatArgs& a, const float* w, float* act, const int* dim,
+                                                      const int* aoff, int slice, int64_t r0) {
+  const int t = threadIdx.x, in_p = dim[0];
+  for (int idx = t; idx < FD_ROWS * in_p; idx += FD_ROWS) {
+    const int rr = idx / in_p, i = idx - rr * in_p;
+    const int64_t r = r0 + rr;
+    act[i * FD_PITCH + rr] = r < a.rows ? a.x[r * a.C + slice * a.ps + i] : 0.f;
+  }
+  __syncthreads();
+  const float* wl = w;
+  for (int l = 0; l < 4; l++) {
+    const int ni = dim[l], no = dim[l + 1];
+    const float* ain = act + aoff[l] * FD_PITCH;
+    float* aout = act + aoff[l + 1] * FD_PITCH;
+    const float* bias = wl + ni * no;
+    for (int j = 0; j < no; j++) {
+      float s = bias[j];
+      for (int i = 0; i < ni; i++) s += wl[i * no + j] * ain[i * FD_PITCH + t];
+      aout[j * FD_PITCH + t] = fmaxf(s, 0.1f * s);
+    }
+    wl += ni * no + no;
+  }
+  __syncthreads();
+}
+#define FEATDISC_SETUP()                                                                        \
+  const int slice = blockIdx.y, ps = a.ps, E = a.E;                                             \
+  const int dim[5] = {min(ps, a.C - slice * ps), ps, ps / 4, ps / 2, E};                        \
+  const int aoff[5] = {0, ps, 2 * ps, 2 * ps + ps / 4, 2 * ps + ps / 4 + ps / 2};               \
+  const int nrows_act = 2 * ps + ps / 4 + ps / 2 + E;                                           \
+  const int n_full = featdisc_slice_weights(ps, E), nw = n_full - (ps - dim[0]) * ps;           \
+  float* w = sm;                                                                                \
+  float* act = sm + ((n_full + 3) & ~3);                                                        \
+  for (int i = threadIdx.x; i < nw; i += FD_ROWS) w[i] = a.weights[(size_t)slice * n_full + i]; \
+  const int64_t r0 = (int64_t)blockIdx.x * FD_ROWS;                                             \
+  const int t = threadIdx.x;                                                                    \
+  const int64_t r = r0 + t;                                                                     \
+  const int slices = gridDim.y
+
+__global__ void __launch_bounds__(FD_ROWS) gan_featdisc_fwd_kernel(const GanFeatArgs a) {
+  extern __shared__ float sm[];
+  FEATDISC_SETUP();
+  (void)nrows_act;
+  featdisc_forward_block(a, w, act, dim, aoff, slice, r0);
+  float s2 = 0.f;
+  if (r < a.rows) {
+    for (int e = 0; e < E; e++) {
+      const float v = act[(aoff[4] + e) * FD_PITCH + t];
+      a.z[(r * slices + slice) * E + e] = v;
+      s2 += v * v;
+    }
+  }
+  s2 = warp_sum(s2);
+  if ((t & 31) == 0) atomicAdd(&a.sumsq[slice], s2);
+}
+
+__global__ void __launch_bounds__(FD_ROWS) gan_featdisc_bwd_kernel(const GanFeatArgs a) {
+  extern __shared__ float sm[];
+  FEATDISC_SETUP();
+  float* dact = act + nrows_act * FD_PITCH;  // gradients, same row offsets as act
+  featdisc_forward_block(a, w, act, dim, aoff, slice, r0);
+  {  // through z / max(|z|_batch, 1e-6): d z = gf / n - z (sum gf z) / n^3  (no second term when the clamp is active)
+    const float ss = a.sumsq[slice];
+    const bool clamped = ss < 1e-12f;
+    const float inv = rsqrtf(fmaxf(ss, 1e-12f));
+    const float k = clamped ? 0.f : a.dot[slice] * inv * inv * inv;
+    for (int e = 0; e < E; e++) {
+      float d = 0.f;
+      if (r < a.rows) {
+        const size_t o = (r * slices + slice) * E + e;
+        d = a.gf[o] * inv - a.z[o] * k;
+      }
+      dact[(aoff[4] + e) * FD_PITCH + t] = d;
+    }
+  }
+  int woff[5];
+  woff[0] = 0;
+  for (int l = 0; l < 4; l++) woff[l + 1] = woff[l] + dim[l] * dim[l + 1] + dim[l + 1];
+  float* gwg = a.gweights ? a.gweights + (size_t)slice * n_full : nullptr;
+  const int lane = t & 31;
+  for (int l = 4; l >= 1; l--) {
+    const int ni = dim[l - 1], no = dim[l];
+    const float* wl = w + woff[l - 1];
+    const float* al = act + aoff[l] * FD_PITCH;
+    const float* ain = act + aoff[l - 1] * FD_PITCH;
+    float* dl = dact + aoff[l] * FD_PITCH;
+    float* din = dact + aoff[l - 1] * FD_PITCH;
+    for (int j = 0; j < no; j++) dl[j * FD_PITCH + t] *= al[j * FD_PITCH + t] > 0.f ? 1.f : 0.1f;
+    if (l > 1 || a.gin) {
+      for (int i = 0; i < ni; i++) {
+        float s = 0.f;
+        for (int j = 0; j < no; j++) s += wl[i * no + j] * dl[j * FD_PITCH + t];
+        din[i * FD_PITCH + t] = s;
+      }
+    }
+    if (gwg) {
+      __syncthreads();
+      for (int idx = t; idx < ni * no + no; idx += FD_ROWS) {
+        float s = 0.f;
+        if (idx < ni * no) {
+          const int i = idx / no, j = idx - i * no;
+          for (int tt = 0; tt < FD_ROWS; tt++) {
+            const int q = (tt + lane) & (FD_ROWS - 1);
+            s += ain[i * FD_PITCH + q] * dl[j * FD_PITCH + q];
+          }
+        } else {
+          const int j = idx - ni * no;
+          for (int tt = 0; tt < FD_ROWS; tt++) s += dl[j * FD_PITCH + ((tt + lane) & (FD_ROWS - 1))];
+        }
+        atomicAdd(&gwg[woff[l - 1] + idx], s);
+      }
+    }
+  }
+  if (a.gin) {
+    __syncthreads();
+    const int in_p = dim[0];
+    for (int idx = t; idx < FD_ROWS * in_p; idx += FD_ROWS) {
+      const int rr = idx / in_p, i = idx - rr * in_p;
+      if (r0 + rr < a.rows) a.gin[(r0 + rr) * a.C + slice * ps + i] = dact[i * FD_PITCH + rr];
+    }
+  }
+}
+
+// PatchNCE (gan/wrappers/cut_wrapper.py:360-420): per sample logits[i][j] = <f_gen[i], f_real[j]> / tau over the
+// slices, labels = eye(slices) flattened, ONE softmax over all slices^2 logits, loss_b = -sum_i log_softmax[i][i],
+// mean over the batch.  fused_grad = 1 reproduces the gradient of TensorFlow's fused SoftmaxCrossEntropyWithLogits
+// kernel, softmax - labels, which is what the reference trains with although its labels sum to `slices` (the exact
+// derivative, slices * softmax - labels, is fused_grad = 0).  One warp per sample; f = z * rsqrt(max(sumsq, 1e-12)).
+struct GanNceArgs {
+  const float* zg;
+  const float* zr;   // [rows][S][E]
+  const float* ssg;
+  const float* ssr;  // [S]
+  int64_t rows;
+  int S, E;
+  float inv_tau, scale;
+  int fused_grad;
+  float* gfg;
+  float* gfr;        // nullable (both): dL/d f_gen, dL/d f_real  [rows][S][E]
+  float* dotg;
+  float* dotr;       // [S] += sum_b gf * z
+  double* loss_acc;  // += scale * sum_b loss_b
+};
+constexpr int NCE_MAX_S = 16, NCE_MAX_E = 8;
+__global__ void __launch_bounds__(128) gan_patchnce_kernel(const GanNceArgs a) {
+  __shared__ float fg_s[4][NCE_MAX_S * NCE_MAX_E], fr_s[4][NCE_MAX_S * NCE_MAX_E], gl_s[4][NCE_MAX_S * NCE_MAX_S];
+  __shared__ float dot_s[2][NCE_MAX_S];
+  __shared__ float loss_s;
+  const int S = a.S, E = a.E, SE = S * E, SS = S * S;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < 2 * NCE_MAX_S) dot_s[threadIdx.x / NCE_MAX_S][threadIdx.x % NCE_MAX_S] = 0.f;
+  if (threadIdx.x == 0) loss_s = 0.f;
+  __syncthreads();
+  float* fg = fg_s[warp];
+  float* fr = fr_s[warp];
+  float* gl = gl_s[warp];
+  float loss_w = 0.f;
+  for (int64_t r = (int64_t)blockIdx.x * 4 + warp; r < a.rows; r += (int64_t)gridDim.x * 4) {
+    for (int i = lane; i < SE; i += 32) {
+      const int s = i / E;
+      fg[i] = a.zg[r * SE + i] * rsqrtf(fmaxf(a.ssg[s], 1e-12f));
+      fr[i] = a.zr[r * SE + i] * rsqrtf(fmaxf(a.ssr[s], 1e-12f));
+    }
+    __syncwarp();
+    float mx = -INFINITY, diag = 0.f;
+    for (int idx = lane; idx < SS; idx += 32) {
+      const int i = idx / S, j = idx - i * S;
+      float l = 0.f;
+      for (int e = 0; e < E; e++) l += fg[i * E + e] * fr[j * E + e];
+      l *= a.inv_tau;
+      gl[idx] = l;
+      mx = fmaxf(mx, l);
+      if (i == j) diag += l;
+    }
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float se = 0.f;
+    for (int idx = lane; idx < SS; idx += 32) se += __expf(gl[idx] - mx);
+    se = warp_sum(se);
+    diag = warp_sum(diag);
+    const float logz = mx + __logf(se);
+    loss_w += (float)S * logz - diag;
+    if (a.gfg) {
+      const float ksm = a.fused_grad ? 1.f : (float)S;
+      for (int idx = lane; idx < SS; idx += 32) {
+        const int i = idx / S, j = idx - i * S;
+        gl[idx] = (ksm * __expf(gl[idx] - logz) - (i == j ? 1.f : 0.f)) * a.scale * a.inv_tau;
+      }
+      __syncwarp();
+      for (int idx = lane; idx < SE; idx += 32) {
+        const int s = idx / E, e = idx - s * E;
+        float gg = 0.f, gr = 0.f;
+        for (int q = 0; q < S; q++) {
+          gg += gl[s * S + q] * fr[q * E + e];   // d/d f_gen[s][e]
+          gr += gl[q * S + s] * fg[q * E + e];   // d/d f_real[s][e]
+        }
+        a.gfg[r * SE + idx] = gg;
+        a.gfr[r * SE + idx] = gr;
+        atomicAdd(&dot_s[0][s], gg * a.zg[r * SE + idx]);
+        atomicAdd(&dot_s[1][s], gr * a.zr[r * SE + idx]);
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) atomicAdd(&loss_s, loss_w);
+  __syncthreads();
+  if (a.gfg && threadIdx.x < 2 * NCE_MAX_S) {
+    const int k = threadIdx.x / NCE_MAX_S, s = threadIdx.x % NCE_MAX_S;
+    if (s < S) atomicAdd(k ? &a.dotr[s] : &a.dotg[s], dot_s[k][s]);
+  }
+  if (threadIdx.x == 0 && a.loss_acc) atomicAdd(a.loss_acc, (double)loss_s * (double)a.scale);
 }
 
 // tf.argmax (first maximum) + confusion[label, pred] += 1

@@ -1,10 +1,12 @@
-"""gan_type -> Wrapper registry (reference: gan/wrapper_registry.py:13-94).  Built here: cycle_gan, gan_x2y, gan_y2x.
-cut_x2y / cut_y2x / dcl_gan / dcl_cycle_gan (patch feature discriminator + PatchNCE) are not built yet and raise."""
+"""gan_type -> Wrapper registry (reference: gan/wrapper_registry.py:13-94): cycle_gan, gan_x2y, gan_y2x, cut_x2y,
+cut_y2x, dcl_gan, dcl_cycle_gan.  What the reference binds into its model functions with functools.partial
+(flags.patches, flags.embedded_feat_size, the two regularisation scales, :31-40) is passed to the wrappers here."""
 from hypelcnn_b200.gan.gan_sampling_methods import DummySampler
+from hypelcnn_b200.gan.wrappers.cut_wrapper import CUTInferenceWrapper, CUTWrapper
 from hypelcnn_b200.gan.wrappers.cycle_gan_wrapper import CycleGANInferenceWrapper, CycleGANWrapper
+from hypelcnn_b200.gan.wrappers.dcl_cycle_gan_wrapper import DCLCycleGANInferenceWrapper, DCLCycleGANWrapper
+from hypelcnn_b200.gan.wrappers.dcl_gan_wrapper import DCLGANInferenceWrapper, DCLGANWrapper
 from hypelcnn_b200.gan.wrappers.gan_wrapper import GANInferenceWrapper, GANWrapper
-
-_NOT_BUILT = ("cut_x2y", "cut_y2x", "dcl_gan", "dcl_cycle_gan")
 
 
 def get_sampling_map():
@@ -14,11 +16,20 @@ def get_sampling_map():
 def get_infer_wrapper_dict(bands=64):
     return {"cycle_gan": CycleGANInferenceWrapper(bands=bands),
             "gan_x2y": GANInferenceWrapper(fetch_shadows=False, bands=bands),
-            "gan_y2x": GANInferenceWrapper(fetch_shadows=True, bands=bands)}
+            "gan_y2x": GANInferenceWrapper(fetch_shadows=True, bands=bands),
+            "cut_x2y": CUTInferenceWrapper(fetch_shadows=False, bands=bands),
+            "cut_y2x": CUTInferenceWrapper(fetch_shadows=True, bands=bands),
+            "dcl_gan": DCLGANInferenceWrapper(bands=bands),
+            "dcl_cycle_gan": DCLCycleGANInferenceWrapper(bands=bands)}
 
 
 def get_wrapper_dict(flags):
     reg = getattr(flags, "discriminator_reg_scale", 1e-5)
+    contrastive = dict(nce_loss_weight=getattr(flags, "nce_loss_weight", 10.0),
+                       identity_loss_weight=flags.identity_loss_weight, use_identity_loss=flags.use_identity_loss,
+                       tau=getattr(flags, "tau", 0.07), batch_size=getattr(flags, "batch_size", None),
+                       patches=getattr(flags, "patches", 6), embedded_feat_size=getattr(flags, "embedded_feat_size", 2),
+                       discriminator_reg_scale=reg, gen_disc_reg_scale=getattr(flags, "gen_disc_reg_scale", 1e-4))
     return {"cycle_gan": CycleGANWrapper(cycle_consistency_loss_weight=flags.cycle_consistency_loss_weight,
                                          identity_loss_weight=flags.identity_loss_weight,
                                          use_identity_loss=flags.use_identity_loss, discriminator_reg_scale=reg),
@@ -27,10 +38,13 @@ def get_wrapper_dict(flags):
                                   discriminator_reg_scale=reg),
             "gan_y2x": GANWrapper(identity_loss_weight=flags.identity_loss_weight,
                                   use_identity_loss=flags.use_identity_loss, swap_inputs=True,
-                                  discriminator_reg_scale=reg)}
+                                  discriminator_reg_scale=reg),
+            "cut_x2y": CUTWrapper(swap_inputs=False, **contrastive),
+            "cut_y2x": CUTWrapper(swap_inputs=True, **contrastive),
+            "dcl_gan": DCLGANWrapper(**contrastive),
+            "dcl_cycle_gan": DCLCycleGANWrapper(
+                cycle_consistency_loss_weight=flags.cycle_consistency_loss_weight, **contrastive)}
 
 
 def get_wrapper(gan_type, flags):
-    if gan_type in _NOT_BUILT:
-        raise NotImplementedError(f"gan_type {gan_type!r}: the CUT / DCL wrappers are not built in this round")
     return get_wrapper_dict(flags)[gan_type]

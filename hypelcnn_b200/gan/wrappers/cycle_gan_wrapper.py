@@ -89,59 +89,9 @@ class TensorPool:
         return t
 
 
-class CycleGANTrainer:
-    """Variables, optimizer slots and the two train ops.  Generators: [G (x -> y) | F (y -> x)] in one flat buffer,
-    discriminators: [D_Y | D_X] in another, so each Adam step and (multi-GPU) each all-reduce is one call."""
+class GanKernels:
+    """The C-ABI calls every GAN trainer chains (needs self.C and self.loss_acc)."""
 
-    def __init__(self, bands, cycle_consistency_loss_weight=10.0, identity_loss_weight=0.5, use_identity_loss=True,
-                 discriminator_reg_scale=1e-5, device=None, seed=1234, pool_size=50):
-        if not torch.cuda.is_available():
-            raise N.NativeError(N.HYP_E_CUDA, "no CUDA device: hypelcnn_b200 has no CPU fallback")
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.C = int(bands)
-        self.w_cyc, self.w_id = float(cycle_consistency_loss_weight), float(identity_loss_weight) if use_identity_loss else 0.0
-        self.reg = float(discriminator_reg_scale)
-        self.gen_x2y, self.gen_y2x = GeneratorVariables(bands, False, self.device), GeneratorVariables(bands, False, self.device)
-        ng, nd = self.gen_x2y.flat.numel(), discriminator_weight_count(bands)
-        z = dict(dtype=torch.float32, device=self.device)
-        self.gen_params = torch.zeros(2 * ng, **z)   # zeros: shadow_data_models.py:47
-        self.gen_x2y.flat, self.gen_y2x.flat = self.gen_params[:ng], self.gen_params[ng:]
-        self.dis_params = torch.zeros(2 * nd, **z)
-        rng = numpy.random.default_rng(seed)
-        for d in range(2):  # variance_scaling(scale=2.0): fan_in, truncated normal (shadow_data_models.py:95)
-            for name, off, shape in discriminator_variable_table(bands):
-                if name.endswith("weights"):
-                    std = math.sqrt(2.0 / shape[0]) / E.TRUNC_STD_FIX
-                    w = rng.standard_normal(shape)
-                    bad = numpy.abs(w) > 2.0
-                    while bad.any():
-                        w[bad] = rng.standard_normal(int(bad.sum()))
-                        bad = numpy.abs(w) > 2.0
-                    self.dis_params[d * nd + off: d * nd + off + w.size].copy_(torch.from_numpy((w * std).astype(numpy.float32).ravel()))
-        self.ng, self.nd = ng, nd
-        self.gen_grads, self.dis_grads = torch.zeros_like(self.gen_params), torch.zeros_like(self.dis_params)
-        self.gen_m, self.gen_v = torch.zeros_like(self.gen_params), torch.zeros_like(self.gen_params)
-        self.dis_m, self.dis_v = torch.zeros_like(self.dis_params), torch.zeros_like(self.dis_params)
-        self.gen_steps = self.dis_steps = self.global_step = 0
-        self.pool_y, self.pool_x = TensorPool(pool_size, seed=seed), TensorPool(pool_size, seed=seed + 1)
-        self.loss_acc = torch.zeros(4, dtype=torch.float64, device=self.device)
-        self.allreduce = None  # set to a parallel.GradientAllReduce for data-parallel training
-        self.last = {}
-
-    # ---- views
-    def G(self):
-        return self.gen_params[:self.ng]
-
-    def F(self):
-        return self.gen_params[self.ng:]
-
-    def DY(self):
-        return self.dis_params[:self.nd]
-
-    def DX(self):
-        return self.dis_params[self.nd:]
-
-    # ---- kernels
     def _gen_fwd(self, x, w):
         nets = torch.empty((x.shape[0], 8, self.C), dtype=torch.float32, device=x.device)
         N.check(N.lib().hyp_gan_generator_train_forward(_p(x), x.shape[0], self.C, _p(w), _p(nets), _st()))
@@ -174,6 +124,67 @@ class CycleGANTrainer:
         if not t.is_cuda or t.dtype != torch.float32:
             raise TypeError("spectra must be CUDA float32 tensors (no CPU path)")
         return t.contiguous()
+
+
+def init_discriminator(params, bands, rng):
+    """variance_scaling(scale=2.0): fan_in, truncated normal (gan/shadow_data_models.py:95) into a flat buffer."""
+    for name, off, shape in discriminator_variable_table(bands):
+        if name.endswith("weights"):
+            params[off:off + shape[0] * shape[1]].copy_(torch.from_numpy(truncated_normal(rng, shape, math.sqrt(2.0 / shape[0]))))
+
+
+def truncated_normal(rng, shape, std):
+    w = rng.standard_normal(shape)
+    bad = numpy.abs(w) > 2.0
+    while bad.any():
+        w[bad] = rng.standard_normal(int(bad.sum()))
+        bad = numpy.abs(w) > 2.0
+    return (w * (std / E.TRUNC_STD_FIX)).astype(numpy.float32).ravel()
+
+
+class CycleGANTrainer(GanKernels):
+    """Variables, optimizer slots and the two train ops.  Generators: [G (x -> y) | F (y -> x)] in one flat buffer,
+    discriminators: [D_Y | D_X] in another, so each Adam step and (multi-GPU) each all-reduce is one call."""
+
+    def __init__(self, bands, cycle_consistency_loss_weight=10.0, identity_loss_weight=0.5, use_identity_loss=True,
+                 discriminator_reg_scale=1e-5, device=None, seed=1234, pool_size=50):
+        if not torch.cuda.is_available():
+            raise N.NativeError(N.HYP_E_CUDA, "no CUDA device: hypelcnn_b200 has no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.C = int(bands)
+        self.w_cyc, self.w_id = float(cycle_consistency_loss_weight), float(identity_loss_weight) if use_identity_loss else 0.0
+        self.reg = float(discriminator_reg_scale)
+        self.gen_x2y, self.gen_y2x = GeneratorVariables(bands, False, self.device), GeneratorVariables(bands, False, self.device)
+        ng, nd = self.gen_x2y.flat.numel(), discriminator_weight_count(bands)
+        z = dict(dtype=torch.float32, device=self.device)
+        self.gen_params = torch.zeros(2 * ng, **z)   # zeros: shadow_data_models.py:47
+        self.gen_x2y.flat, self.gen_y2x.flat = self.gen_params[:ng], self.gen_params[ng:]
+        self.dis_params = torch.zeros(2 * nd, **z)
+        rng = numpy.random.default_rng(seed)
+        for d in range(2):
+            init_discriminator(self.dis_params[d * nd:(d + 1) * nd], bands, rng)
+        self.ng, self.nd = ng, nd
+        self.gen_grads, self.dis_grads = torch.zeros_like(self.gen_params), torch.zeros_like(self.dis_params)
+        self.gen_m, self.gen_v = torch.zeros_like(self.gen_params), torch.zeros_like(self.gen_params)
+        self.dis_m, self.dis_v = torch.zeros_like(self.dis_params), torch.zeros_like(self.dis_params)
+        self.gen_steps = self.dis_steps = self.global_step = 0
+        self.pool_y, self.pool_x = TensorPool(pool_size, seed=seed), TensorPool(pool_size, seed=seed + 1)
+        self.loss_acc = torch.zeros(4, dtype=torch.float64, device=self.device)
+        self.allreduce = None  # set to a parallel.GradientAllReduce for data-parallel training
+        self.last = {}
+
+    # ---- views
+    def G(self):
+        return self.gen_params[:self.ng]
+
+    def F(self):
+        return self.gen_params[self.ng:]
+
+    def DY(self):
+        return self.dis_params[:self.nd]
+
+    def DX(self):
+        return self.dis_params[self.nd:]
 
     # ---- generator step (tfgan generator train op over both partial models)
     def generator_gradients(self, images_x, images_y):

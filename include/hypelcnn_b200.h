@@ -203,6 +203,32 @@ int hyp_gan_loss_grad(int mode, const float* a, const float* b, float target, fl
 /* slim l2_regularizer(scale) on a weight range: loss_acc += scale * sum(w^2)/2, grads += scale * w (grads nullable) */
 int hyp_gan_l2_regularizer(const float* weights, float* grads, int64_t n, float scale, double* loss_acc, void* stream);
 
+/* ---- CUT / DCLGAN / DCL-CycleGAN (gan/wrappers/cut_wrapper.py:256-420, dcl_gan_wrapper.py, dcl_cycle_gan_wrapper.py).
+ * generator backward that also takes the gradient of the ENCODER output net4 (generator_fn(create_only_encoder=True),
+ * gan/shadow_data_models.py:43-75): gout (dL/dnet7) nullable -> only net1..net4 are differentiated; gout_enc nullable */
+int hyp_gan_generator_backward_enc(const float* nets, const float* gout, const float* gout_enc, int64_t rows, int bands,
+                                   const float* weights, float* gin, float* gweights, void* stream);
+/* patch feature discriminator (gan/shadow_data_models.py:126-149): slices of bands / patch_count bands (last one
+ * ragged), per slice FC in->ps->ps/4->ps/2->E with leaky_relu(0.1) after each; weights per slice (padded to the full
+ * slice size): W1 [in,ps] b1 W2 b2 W3 b3 W4 [ps/2,E] b4.  forward: z [rows][slices][E] un-normalised, sumsq [slices] =
+ * sum over the batch of z^2 (tf.math.l2_normalize over the whole [rows,E] tensor is applied by the consumers).
+ * backward: gf = dL/d(normalised embedding), dot [slices] = sum gf*z (from hyp_gan_patchnce) -> gin [rows,bands]
+ * (nullable) and gweights += (nullable). */
+int64_t hyp_gan_feature_discriminator_weight_count(int bands, int patch_count, int embedded_feature_size);
+int hyp_gan_feature_discriminator_forward(const float* x, int64_t rows, int bands, int patch_count,
+                                          int embedded_feature_size, const float* weights, float* z, float* sumsq,
+                                          void* stream);
+int hyp_gan_feature_discriminator_backward(const float* x, const float* z, const float* sumsq, const float* gf,
+                                           const float* dot, int64_t rows, int bands, int patch_count,
+                                           int embedded_feature_size, const float* weights, float* gin, float* gweights,
+                                           void* stream);
+/* PatchNCE (cut_wrapper.py:360-420): logits = f_gen f_real^T / tau per sample, labels eye(slices) flattened, one
+ * softmax over slices^2; loss_acc += scale * sum_b loss_b (scale = weight / rows).  g_gen / g_real (nullable pair) =
+ * dL/d f; fused_grad 1 = TensorFlow's fused xent gradient (softmax - labels), 0 = exact (slices*softmax - labels). */
+int hyp_gan_patchnce(const float* z_gen, const float* z_real, const float* sumsq_gen, const float* sumsq_real,
+                     int64_t rows, int slices, int embedded_feature_size, float tau, float scale, int fused_grad,
+                     float* g_gen, float* g_real, float* dot_gen, float* dot_real, double* loss_acc, void* stream);
+
 /* tf.argmax (lowest index on ties) + tf.math.confusion_matrix accumulation
  * (common/common_nn_ops.py:246-262, :318).  labels/confusion nullable.
  * confusion: int32 [classes,classes], rows = labels, += semantics. */

@@ -64,13 +64,13 @@ def inference_for_matrix_input(x, variables, is_shadow, clip, copy_extra=0):
 
 # ---------------------------------------------------------------------------------------------------------------
 # torch (autograd) restatement of the CycleGAN-with-identity objective for the gradient parity tests
-def t_generator(x, w):
-    """x [N,C] torch, w flat [net1 w, b, net2 w, b, ...] -> net7."""
+def t_generator(x, w, encoder_only=False):
+    """x [N,C] torch, w flat [net1 w, b, net2 w, b, ...] -> net7 (net4 when encoder_only, shadow_data_models.py:75)."""
     import torch
     import torch.nn.functional as F
     C = x.shape[1]
     nets, off = [x], 0
-    for i, k in enumerate(kernel_sizes(C)):
+    for i, k in enumerate(kernel_sizes(C, encoder_only)):
         wk, b = w[off:off + k], w[off + k]
         off += k + 1
         left = (k - 1) // 2
@@ -121,3 +121,99 @@ def t_discriminator_loss(x, y, gx, fy, DY, DX, reg):
         total = total + 0.5 * ((t_discriminator(real, w) - 1) ** 2).mean() + 0.5 * (t_discriminator(fake, w) ** 2).mean()
         total = total + reg * 0.5 * ((w[:C * C] ** 2).sum() + (w[C * C + C:2 * C * C + C] ** 2).sum())
     return total
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CUT / DCLGAN (gan/shadow_data_models.py:126-149, gan/wrappers/cut_wrapper.py:90-208,256-420)
+def feature_discriminator_layout(bands, patch_count, E):
+    """[(slice start, in width, [(w offset, (n_in, n_out), b offset), ...])] inside the flat weight buffer; every slice
+    occupies the size of a full slice (ps wide) so that slice s starts at s * n_full."""
+    ps = bands // patch_count
+    dims = [ps, ps, ps // 4, ps // 2, E]
+    n_full = sum(dims[i] * dims[i + 1] + dims[i + 1] for i in range(4))
+    out = []
+    for s, start in enumerate(range(0, bands, ps)):
+        width = min(ps, bands - start)
+        d = [width] + dims[1:]
+        off, layers = s * n_full, []
+        for i in range(4):
+            layers.append((off, (d[i], d[i + 1]), off + d[i] * d[i + 1]))
+            off += d[i] * d[i + 1] + d[i + 1]
+        out.append((start, width, layers))
+    return out, n_full
+
+
+def t_feature_discriminator(x, w, patch_count, E):
+    """x [N,C] -> [N, slices, E]: per slice 4 FC + leaky_relu(0.1) and tf.math.l2_normalize over the WHOLE [N,E]
+    output of the slice (axis=None, epsilon 1e-12)."""
+    import torch
+    layout, _ = feature_discriminator_layout(x.shape[1], patch_count, E)
+    outs = []
+    for start, width, layers in layout:
+        h = x[:, start:start + width]
+        for wo, (ni, no), bo in layers:
+            h = h @ w[wo:wo + ni * no].view(ni, no) + w[bo:bo + no]
+            h = torch.maximum(h, 0.1 * h)
+        outs.append((h * torch.rsqrt(torch.clamp((h * h).sum(), min=1e-12))).unsqueeze(1))
+    return torch.cat(outs, dim=1)
+
+
+def t_feature_discriminator_reg(w, bands, patch_count, E, scale):
+    """slim l2_regularizer(scale) on every FC weight matrix of the feature discriminator (:128-129)."""
+    layout, _ = feature_discriminator_layout(bands, patch_count, E)
+    total = 0
+    for _, _, layers in layout:
+        for wo, (ni, no), _ in layers:
+            total = total + scale * 0.5 * (w[wo:wo + ni * no] ** 2).sum()
+    return total
+
+
+def _fused_xent():
+    import torch
+
+    class FusedXent(torch.autograd.Function):
+        """tf.nn.softmax_cross_entropy_with_logits as TensorFlow's fused kernel evaluates it [TF-lib]:
+        loss = -sum(labels * log_softmax(logits)), backprop = softmax(logits) - labels (exact only when the labels
+        sum to one; the reference's eye() labels sum to `slices`)."""
+
+        @staticmethod
+        def forward(ctx, logits, labels):
+            ls = torch.log_softmax(logits, dim=1)
+            ctx.save_for_backward(ls.exp() - labels)
+            return -(labels * ls).sum(dim=1)
+
+        @staticmethod
+        def backward(ctx, g):
+            (bp,) = ctx.saved_tensors
+            return g.unsqueeze(1) * bp, None
+
+    return FusedXent
+
+
+def t_patchnce(f_gen, f_real, tau, fused_grad=True):
+    """_calc_cross_feats + softmax CE + SUM_OVER_BATCH_SIZE (cut_wrapper.py:360-393)."""
+    import torch
+    B, S, _ = f_gen.shape
+    logits = (f_gen @ f_real.transpose(1, 2) / tau).reshape(B, S * S)
+    labels = torch.eye(S, dtype=f_gen.dtype).reshape(1, S * S).expand(B, S * S)
+    if fused_grad:
+        return _fused_xent().apply(logits, labels).mean()
+    return -(labels * torch.log_softmax(logits, dim=1)).sum(dim=1).mean()
+
+
+def t_cut_losses(inp, real, G, D, Fd, patch_count, E, tau, nce_w, id_w, dis_reg, feat_reg, fused_grad=True):
+    """cut_model + cut_loss with the LSGAN losses of CUTWrapper.define_loss (cut_wrapper.py:626-636).  Returns
+    (generator_loss, discriminator_loss, gen_discriminator_loss, parts)."""
+    C = inp.shape[1]
+    gen = t_generator(inp, G)
+    d_gen, d_real = t_discriminator(gen, D), t_discriminator(real, D)
+    fd = lambda t: t_feature_discriminator(t_generator(t, G, True), Fd, patch_count, E)
+    nce_x = t_patchnce(fd(gen), fd(inp), tau, fused_grad)
+    idt = t_generator(real, G)
+    nce_id = t_patchnce(fd(idt), fd(real), tau, fused_grad)
+    gan_g = 0.5 * ((d_gen - 1) ** 2).mean()
+    gen_loss = gan_g + nce_w * nce_x + id_w * nce_id
+    dis_loss = 0.5 * ((d_real - 1) ** 2).mean() + 0.5 * (d_gen ** 2).mean() + \
+        dis_reg * 0.5 * ((D[:C * C] ** 2).sum() + (D[C * C + C:2 * C * C + C] ** 2).sum())
+    feat_loss = nce_x + t_feature_discriminator_reg(Fd, C, patch_count, E, feat_reg)
+    return gen_loss, dis_loss, feat_loss, {"gan": gan_g, "nce_x": nce_x, "nce_identity": nce_id}

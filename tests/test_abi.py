@@ -73,3 +73,17 @@ def test_product_code_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(base, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, os.path.join(base, f)
+
+
+def test_feature_discriminator_layout_matches_the_oracle_and_slim_names(lib):
+    from hypelcnn_b200.gan.wrappers.cut_wrapper import feature_discriminator_variable_table
+    from oracle import gan_ref
+    for bands, patches, E in ((64, 6, 2), (144, 6, 2), (48, 4, 5), (32, 8, 1)):
+        layout, n_full = gan_ref.feature_discriminator_layout(bands, patches, E)
+        assert lib.hyp_gan_feature_discriminator_weight_count(bands, patches, E) == len(layout) * n_full
+        table = feature_discriminator_variable_table(bands, patches, E)
+        flat = [(wo, shape) for _, _, layers in layout for wo, shape, _ in layers]
+        assert [(off, shape) for name, off, shape in table if name.endswith("weights")] == flat
+    names = [n for n, _, _ in feature_discriminator_variable_table(64, 6, 2)]
+    assert names[0] == "fully_connected/weights" and names[2] == "fully_connected_1/weights"
+    assert names[-1] == "fully_connected_27/biases"       # 7 slices (64 bands, slices of 10: the last is 4 wide) x 4 layers

@@ -153,5 +153,5 @@ def test_single_direction_gan_gradients_and_registry(swap):
     ops = wrapper.define_train_ops(t, wrapper.define_loss(t), 100, generator_lr=2e-4, discriminator_lr=1e-4)
     ops.train_iteration(x, y)
     assert t.global_step == 1 and t.gen_steps == 1 and t.dis_steps == 1
-    with pytest.raises(NotImplementedError):
-        get_wrapper("dcl_gan", flags)
+    with pytest.raises(KeyError):
+        get_wrapper("no_such_gan", flags)

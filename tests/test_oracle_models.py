@@ -100,3 +100,18 @@ def test_cyclegan_objective_composition():
     id_once = (gx - x).abs().mean() + (fy - y).abs().mean()
     assert torch.allclose(cyc, 2 * 10.0 * cyc_once) and torch.allclose(ident, 2 * 0.5 * id_once)
     assert torch.allclose(total, gan + cyc + ident)
+
+
+def test_fused_xent_gradient_is_softmax_minus_labels():
+    """the [TF-lib] convention the oracle encodes: backprop = softmax - labels although the labels sum to S."""
+    torch.manual_seed(0)
+    fg = torch.randn(3, 4, 2, dtype=torch.float64, requires_grad=True)
+    fr = torch.randn(3, 4, 2, dtype=torch.float64)
+    RG.t_patchnce(fg, fr, 0.5, True).backward()
+    logits = (fg.detach() @ fr.transpose(1, 2) / 0.5).reshape(3, 16)
+    bp = (torch.softmax(logits, dim=1) - torch.eye(4, dtype=torch.float64).reshape(1, 16)).reshape(3, 4, 4) / 3
+    assert torch.allclose(fg.grad, bp @ fr / 0.5, atol=1e-12)
+    fg2 = fg.detach().clone().requires_grad_(True)
+    RG.t_patchnce(fg2, fr, 0.5, False).backward()          # exact derivative: S * softmax - labels
+    bp2 = (4 * torch.softmax(logits, dim=1) - torch.eye(4, dtype=torch.float64).reshape(1, 16)).reshape(3, 4, 4) / 3
+    assert torch.allclose(fg2.grad, bp2 @ fr / 0.5, atol=1e-12)
