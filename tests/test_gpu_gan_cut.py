@@ -189,3 +189,27 @@ def test_dcl_wrappers_are_two_cut_models_on_one_optimizer_clock(gan_type):
         Gx, Gy = tr.model_x2y.gen_params.double().cpu(), tr.model_y2x.gen_params.double().cpu()
         assert _rel(rx, R.t_generator(R.t_generator(x.double().cpu(), Gx), Gy)) < 1e-5
         assert _rel(ry, R.t_generator(R.t_generator(y.double().cpu(), Gy), Gx)) < 1e-5
+
+
+def test_dclgan_generators_feed_the_classifier_augmenter():
+    """BASELINE configs[4]'s data path: --augment_data_with_shadow=dcl_gan hands the DCLGAN generators to the
+    classifier's input pipeline through create_gan_struct (gan/gan_utilities.py:30-43)."""
+    from hypelcnn_b200.gan.gan_utilities import create_gan_struct
+    from hypelcnn_b200.gan.wrappers.dcl_gan_wrapper import DCLGANInferenceWrapper, DCLGANTrainer
+    bands, n, P = 64, 24, 3
+    tr = DCLGANTrainer(bands)
+    x, y = _data(64, bands)
+    from hypelcnn_b200.gan.wrappers.dcl_gan_wrapper import DCLGANTrainOps
+    ops = DCLGANTrainOps(tr, 100, 2e-3, 1e-4, 1e-4)
+    for _ in range(3):
+        ops.train_iteration(x, y)
+    struct = create_gan_struct(DCLGANInferenceWrapper(trainer=tr))
+    rng = numpy.random.default_rng(5)
+    patches = torch.tensor(rng.uniform(0.1, 0.6, (n, P, P, bands + 1)).astype(numpy.float32)).cuda()
+    for op, gen in ((struct.shadow_op, tr.model_x2y.generator), (struct.deshadow_op, tr.model_y2x.generator)):
+        out = op(patches)
+        ref = R.inference_for_matrix_input(patches.double().cpu().numpy(), {k: v.astype(numpy.float64) for k, v in
+                                                                            gen.export().items()}, True, False, 1)
+        assert out.shape == patches.shape and torch.equal(out[..., -1], patches[..., -1])
+        assert numpy.abs(out.cpu().numpy() - ref).max() < 1e-5
+        assert float((out[..., :-1] - patches[..., :-1]).abs().max()) > 0      # the trained generator does something
