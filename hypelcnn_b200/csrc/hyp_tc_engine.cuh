@@ -59,6 +59,8 @@ struct TcState {
   size_t ce_off = 0, mse_off = 0, dbg_off = 0, ws_bytes = 0;
   std::vector<PackJob> jobs;
   PackJob* jobs_dev = nullptr;
+  int* job_tiles_dev = nullptr;          // first 32x32 tile of every job (+ total)
+  std::vector<int> job_tile_first;
   int job_blocks = 1;
   TcSeg* segs_dev = nullptr;
   TcTile* tiles_dev = nullptr;
@@ -252,14 +254,17 @@ static int tc_layout(hyp_model& m) {
   S.mse_off = take(256);
   S.dbg_off = take(dbg_max * sizeof(float));
   S.ws_bytes = align_up(off, 256);
+  S.job_tile_first.assign(1, 0);
   for (const PackJob& j : S.jobs)
-    S.job_blocks = std::max<int>(S.job_blocks, (int)std::min<int64_t>(64, cdiv((int64_t)j.rows * j.cols, 1024)));
+    S.job_tile_first.push_back(S.job_tile_first.back() + (int)(cdiv(j.rows, 32) * cdiv(j.cols, 32)));
+  S.job_blocks = S.job_tile_first.back();
   return HYP_OK;
 }
 
 static void tc_destroy(hyp_model& m) {
   if (!m.tc) return;
   if (m.tc->jobs_dev) cudaFree(m.tc->jobs_dev);
+  if (m.tc->job_tiles_dev) cudaFree(m.tc->job_tiles_dev);
   if (m.tc->segs_dev) cudaFree(m.tc->segs_dev);
   if (m.tc->tiles_dev) cudaFree(m.tc->tiles_dev);
   delete m.tc;
@@ -271,6 +276,8 @@ static int tc_bind(hyp_model& m) {
   if (!S.jobs_dev) {
     HYP_CUDA(cudaMalloc(&S.jobs_dev, S.jobs.size() * sizeof(PackJob)));
     HYP_CUDA(cudaMemcpy(S.jobs_dev, S.jobs.data(), S.jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
+    HYP_CUDA(cudaMalloc(&S.job_tiles_dev, S.job_tile_first.size() * sizeof(int)));
+    HYP_CUDA(cudaMemcpy(S.job_tiles_dev, S.job_tile_first.data(), S.job_tile_first.size() * sizeof(int), cudaMemcpyHostToDevice));
   }
   HYP_CUDA(cudaMemset(m.ws + S.pack_off, 0, 2 * S.pack_plane_elems * sizeof(float)));
   for (size_t li = 0; li < m.layers.size(); li++)
@@ -846,8 +853,8 @@ static int tc_forward(hyp_model& m, const float* x, int64_t B, bool training, bo
                   tc_plane1(m, (int)t))));
     }
     TC_PROF("tc_pack_weights_kernel", 12.0 * S.pack_plane_elems,
-            (tc_pack_weights_kernel<<<dim3(S.job_blocks, (unsigned)S.jobs.size()), 256, 0, st>>>(
-                S.jobs_dev, m.params, pack0, pack0 + S.pack_plane_elems)));
+            (tc_pack_weights_kernel<<<(unsigned)S.job_blocks, 256, 0, st>>>(
+                S.jobs_dev, S.job_tiles_dev, (int)S.jobs.size(), m.params, pack0, pack0 + S.pack_plane_elems)));
   }
   const float keep_prob = m.keep_prob;
   float* part = reinterpret_cast<float*>(m.ws + S.part_off);
@@ -867,7 +874,7 @@ static int tc_forward(hyp_model& m, const float* x, int64_t B, bool training, bo
       // no normaliser: mean = 0, rstd = 1 (set at bind), beta = the layer's biases
     } else if (training) {
       TC_PROF("tc_bn_finalize_kernel", 8.0 * T.stats_rows * L.Cout,
-              (tc_bn_finalize8_kernel<<<(unsigned)cdiv(L.Cout, 8), 256, 0, st>>>(
+              (tc_bn_finalize8_kernel<<<(unsigned)cdiv(L.Cout, 8), 8 * FIN_LANES, 0, st>>>(
                   part, T.stats_rows, L.Cout, L.Cout, (double)rows, m.d.bn_eps, m.d.bn_decay, m.state + L.mm_off,
                   m.state + L.mm_off + L.Cout, mean, rstd, update_moving ? 1 : 0)));
     } else {
@@ -965,7 +972,7 @@ static int tc_backward(hyp_model& m, const uint8_t* labels, int64_t B, float* lo
     p.fpad = T.kind == 1 ? T.fpad : 0; p.f = T.f; p.R = T.R; p.nt = T.nt; p.ft = T.ft;
     const EwGrid gr = ew_grid2(L.Cout, rows);
     TC_PROF("tc_bn_bwd_reduce_kernel", 8.0 * rows * L.Cout, TC_EW_DISPATCH(gr, tc_bn_bwd_reduce_v4_kernel, p, gr.rpb));
-    tc_bn_bwd_finalize8_kernel<<<(unsigned)cdiv(L.Cout, 8), 256, 0, st>>>(bpart, gr.rblocks, L.Cout, (double)rows, s1, s2,
+    tc_bn_bwd_finalize8_kernel<<<(unsigned)cdiv(L.Cout, 8), 8 * FIN_LANES, 0, st>>>(bpart, gr.rblocks, L.Cout, (double)rows, s1, s2,
                                                                          m.grads + L.beta_off, L.bias_mode ? 1 : 0);
     HYP_LAUNCHED();
     if (p.fpad == 0 || (p.f % 4 == 0 && p.ft % 4 == 0 && p.fpad % 4 == 0)) {

@@ -16,19 +16,22 @@ __device__ __forceinline__ float tf32_lo(float a) {
 
 // view of x [B][P0][P0][C0] (NHWC patches as the importer hands them over): channels [c0, c0 + C), window cropped
 // by `crop` pixels per side to P x P  -> planes [P*P][B][ld]
-__global__ void tc_prep_input_kernel(const float* __restrict__ x, int B, int P0, int C0, int c0, int crop, int P, int C,
-                                     int ld, float* __restrict__ hi, float* __restrict__ lo) {
-  const int PP = P * P;
-  const int64_t total = (int64_t)B * PP * C;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t bp = i / C;
-    const int c = (int)(i - bp * C);
+__global__ void __launch_bounds__(256) tc_prep_input_kernel(const float* __restrict__ x, int B, int P0, int C0, int c0, int crop,
+                                                            int P, int C, int ld, float* __restrict__ hi, float* __restrict__ lo) {
+  // one warp per (sample, pixel) row of C contiguous channels: the index arithmetic is per row, not per element
+  const int PP = P * P, lane = threadIdx.x & 31;
+  const int64_t rows = (int64_t)B * PP;
+  const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t bp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); bp < rows; bp += wstride) {
     const int b = (int)(bp / PP), pos = (int)(bp - (int64_t)b * PP);
     const int ph = pos / P, pw = pos - ph * P;
-    const float v = x[(((int64_t)b * P0 + ph + crop) * P0 + pw + crop) * C0 + c0 + c];
-    const int64_t o = ((int64_t)pos * B + b) * ld + c;
-    hi[o] = v;
-    lo[o] = tf32_lo(v);
+    const float* src = x + (((int64_t)b * P0 + ph + crop) * P0 + pw + crop) * C0 + c0;
+    const int64_t o = ((int64_t)pos * B + b) * ld;
+    for (int c = lane; c < C; c += 32) {
+      const float v = __ldg(src + c);
+      hi[o + c] = v;
+      lo[o + c] = tf32_lo(v);
+    }
   }
 }
 __global__ void tc_fill_kernel(float* __restrict__ p, int n, float v) {
@@ -58,20 +61,45 @@ struct PackJob {
   int32_t sr1, sr0, sk1, sk0;
   int32_t pad;
 };
-__global__ void tc_pack_weights_kernel(const PackJob* __restrict__ jobs, const float* __restrict__ params,
-                                       float* __restrict__ hi, float* __restrict__ lo) {
-  const PackJob J = jobs[blockIdx.y];
-  const int64_t total = (int64_t)J.rows * J.cols;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / J.cols), k = (int)(i - (int64_t)r * J.cols);
+// One CTA packs one 32 x 32 (rows x cols) tile of one job; tile_first[j] = first tile of job j (prefix sums, njobs + 1
+// entries).  The source is read along whichever of (r0, k0) is contiguous in params (sr0 == 1: a transpose through
+// shared memory), the two planes are always written along k.
+__global__ void __launch_bounds__(256) tc_pack_weights_kernel(const PackJob* __restrict__ jobs, const int* __restrict__ tile_first,
+                                                              int njobs, const float* __restrict__ params,
+                                                              float* __restrict__ hi, float* __restrict__ lo) {
+  __shared__ float tile[32][33];
+  int jlo = 0, jhi = njobs - 1;  // last job with tile_first <= blockIdx.x
+  while (jlo < jhi) {
+    const int mid = (jlo + jhi + 1) >> 1;
+    if (__ldg(&tile_first[mid]) <= (int)blockIdx.x) jlo = mid; else jhi = mid - 1;
+  }
+  const PackJob J = jobs[jlo];
+  const int t = (int)blockIdx.x - __ldg(&tile_first[jlo]);
+  const int ctiles = (J.cols + 31) >> 5;
+  const int r_t = (t / ctiles) << 5, k_t = (t % ctiles) << 5;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const bool transpose = J.sr0 == 1;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int rr = transpose ? tx : ty + 8 * i, kk = transpose ? ty + 8 * i : tx;
+    const int r = r_t + rr, k = k_t + kk;
     const int r1 = r / J.RD, r0 = r - r1 * J.RD;
     const int k1 = k / J.KD, k0 = k - k1 * J.KD;
     float v = 0.f;
-    if (r0 < J.RV && k0 < J.KV)
+    if (r < J.rows && k < J.cols && r0 < J.RV && k0 < J.KV)
       v = params[J.src_off + (int64_t)r1 * J.sr1 + (int64_t)r0 * J.sr0 + (int64_t)k1 * J.sk1 + (int64_t)k0 * J.sk0];
-    const int64_t o = J.dst_off + (int64_t)r * J.ld + k;
-    hi[o] = v;
-    lo[o] = tf32_lo(v);
+    tile[rr][kk] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int rr = ty + 8 * i, r = r_t + rr, k = k_t + tx;
+    if (r < J.rows && k < J.cols) {
+      const float v = tile[rr][tx];
+      const int64_t o = J.dst_off + (int64_t)r * J.ld + k;
+      hi[o] = v;
+      lo[o] = tf32_lo(v);
+    }
   }
 }
 
@@ -511,27 +539,48 @@ __global__ void __launch_bounds__(256) tc_resid_bwd_v4_kernel(const float* __res
 }
 
 // per-row-block partial sums [nrows][2][ld] -> mean / rstd / moving statistics.  8 channels per block
-// (one 32-byte sector per partial row), 32 row lanes.
-__global__ void __launch_bounds__(256) tc_bn_finalize8_kernel(const float* __restrict__ part, int nrows, int ld, int C,
-                                                              double count, float eps, float decay,
-                                                              float* __restrict__ moving_mean, float* __restrict__ moving_var,
-                                                              float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                                              int update_moving) {
-  __shared__ double sh1[32][9], sh2[32][9];
+// (one 32-byte sector per partial row) x FIN_LANES row lanes: the kernel is pure load latency (a few thousand
+// partial rows, a few dozen channels), so the rows are spread over as many threads as a block holds and every
+// thread keeps four loads in flight; the cross-lane sum is a shuffle tree + one shared-memory round.
+constexpr int FIN_LANES = 128;
+__device__ __forceinline__ void tc_fin_reduce(const float* __restrict__ part, int nrows, size_t ld, int c, bool valid,
+                                              double& a1, double& a2, double (*sh)[8][2]) {
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
-  const int c = blockIdx.x * 8 + tx;
-  double a1 = 0, a2 = 0;
-  if (c < C) {
-    for (int r = ty; r < nrows; r += 32) {
+  a1 = a2 = 0;
+  if (valid) {
+    int r = ty;
+    for (; r + FIN_LANES < nrows; r += 2 * FIN_LANES) {
+      const float u0 = part[((size_t)r * 2 + 0) * ld + c], u1 = part[((size_t)r * 2 + 1) * ld + c];
+      const float v0 = part[((size_t)(r + FIN_LANES) * 2 + 0) * ld + c], v1 = part[((size_t)(r + FIN_LANES) * 2 + 1) * ld + c];
+      a1 += (double)u0 + (double)v0;
+      a2 += (double)u1 + (double)v1;
+    }
+    if (r < nrows) {
       a1 += (double)part[((size_t)r * 2 + 0) * ld + c];
       a2 += (double)part[((size_t)r * 2 + 1) * ld + c];
     }
   }
-  sh1[ty][tx] = a1;
-  sh2[ty][tx] = a2;
+  // lanes 8, 16 of a warp hold the same channel: fold the 4 row lanes of a warp, then the 32 warps
+  a1 += __shfl_xor_sync(0xffffffffu, a1, 8);  a2 += __shfl_xor_sync(0xffffffffu, a2, 8);
+  a1 += __shfl_xor_sync(0xffffffffu, a1, 16); a2 += __shfl_xor_sync(0xffffffffu, a2, 16);
+  const int warp = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) < 8) { sh[warp][tx][0] = a1; sh[warp][tx][1] = a2; }
   __syncthreads();
-  if (ty == 0 && c < C) {
-    for (int i = 1; i < 32; i++) { a1 += sh1[i][tx]; a2 += sh2[i][tx]; }
+  if (threadIdx.x < 8) {
+    a1 = a2 = 0;
+    for (int w = 0; w < FIN_LANES / 4; w++) { a1 += sh[w][tx][0]; a2 += sh[w][tx][1]; }
+  }
+}
+__global__ void __launch_bounds__(8 * FIN_LANES) tc_bn_finalize8_kernel(const float* __restrict__ part, int nrows, int ld, int C,
+                                                              double count, float eps, float decay,
+                                                              float* __restrict__ moving_mean, float* __restrict__ moving_var,
+                                                              float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                              int update_moving) {
+  __shared__ double sh[FIN_LANES / 4][8][2];
+  const int c = blockIdx.x * 8 + (threadIdx.x & 7);
+  double a1, a2;
+  tc_fin_reduce(part, nrows, (size_t)ld, c, c < C, a1, a2, sh);
+  if (threadIdx.x < 8 && c < C) {
     const double mean = a1 / count;
     double var = a2 / count - mean * mean;
     if (var < 0) var = 0;
@@ -548,24 +597,14 @@ __global__ void __launch_bounds__(256) tc_bn_finalize8_kernel(const float* __res
     }
   }
 }
-__global__ void __launch_bounds__(256) tc_bn_bwd_finalize8_kernel(const float* __restrict__ part, int nblocks, int C, double rows,
+__global__ void __launch_bounds__(8 * FIN_LANES) tc_bn_bwd_finalize8_kernel(const float* __restrict__ part, int nblocks, int C, double rows,
                                                                   float* __restrict__ s1, float* __restrict__ s2,
                                                                   float* __restrict__ gbeta, int bias_mode) {
-  __shared__ double sh1[32][9], sh2[32][9];
-  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
-  const int c = blockIdx.x * 8 + tx;
-  double a1 = 0, a2 = 0;
-  if (c < C) {
-    for (int r = ty; r < nblocks; r += 32) {
-      a1 += (double)part[((size_t)r * 2 + 0) * C + c];
-      a2 += (double)part[((size_t)r * 2 + 1) * C + c];
-    }
-  }
-  sh1[ty][tx] = a1;
-  sh2[ty][tx] = a2;
-  __syncthreads();
-  if (ty == 0 && c < C) {
-    for (int i = 1; i < 32; i++) { a1 += sh1[i][tx]; a2 += sh2[i][tx]; }
+  __shared__ double sh[FIN_LANES / 4][8][2];
+  const int c = blockIdx.x * 8 + (threadIdx.x & 7);
+  double a1, a2;
+  tc_fin_reduce(part, nblocks, (size_t)C, c, c < C, a1, a2, sh);
+  if (threadIdx.x < 8 && c < C) {
     // bias layers have no batch statistics to differentiate through: gz = g_y, d bias = sum g_y
     s1[c] = bias_mode ? 0.f : (float)(a1 / rows);
     s2[c] = bias_mode ? 0.f : (float)(a2 / rows);
@@ -659,19 +698,25 @@ __global__ void tc_ce_loss_kernel(const float* __restrict__ logits, int ld, cons
 }
 
 // sum (recon - x)^2: recon [B][ldr] with feature pos*C + c; x planes position-major [PP][B][ldx]
-__global__ void tc_mse_kernel(const float* __restrict__ recon, int ldr, const float* __restrict__ xin, int ldx, int B,
-                              int PP, int C, double* __restrict__ acc, float* __restrict__ grecon, int ldg,
-                              float gscale) {
+__global__ void __launch_bounds__(256) tc_mse_kernel(const float* __restrict__ recon, int ldr, const float* __restrict__ xin, int ldx,
+                                                     int B, int PP, int C, double* __restrict__ acc, float* __restrict__ grecon,
+                                                     int ldg, float gscale) {
   __shared__ float sh[32];
-  const int64_t D = (int64_t)PP * C, n = (int64_t)B * D;
+  // one warp per (sample, pixel): C contiguous features of recon against C contiguous channels of the x plane
+  const int lane = threadIdx.x & 31;
+  const int64_t rows = (int64_t)B * PP;
+  const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
   float s = 0.f;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int b = (int)(i / D);
-    const int fidx = (int)(i - (int64_t)b * D);
-    const int pos = fidx / C, c = fidx - pos * C;
-    const float d = recon[(int64_t)b * ldr + fidx] - xin[((int64_t)pos * B + b) * ldx + c];
-    s += d * d;
-    if (grecon) grecon[(int64_t)b * ldg + fidx] = 2.f * d * gscale;
+  for (int64_t bp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); bp < rows; bp += wstride) {
+    const int b = (int)(bp / PP), pos = (int)(bp - (int64_t)b * PP);
+    const float* r = recon + (int64_t)b * ldr + (int64_t)pos * C;
+    const float* xv = xin + ((int64_t)pos * B + b) * ldx;
+    float* g = grecon ? grecon + (int64_t)b * ldg + (int64_t)pos * C : nullptr;
+    for (int c = lane; c < C; c += 32) {
+      const float d = r[c] - xv[c];
+      s += d * d;
+      if (g) g[c] = 2.f * d * gscale;
+    }
   }
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
