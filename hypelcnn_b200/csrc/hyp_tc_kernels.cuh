@@ -162,37 +162,77 @@ struct TcApplyArgs {
 
 // out = dropout(act(bn(z))) + res0[:, idx0] + res1[:, idx1]; VEC channels per thread
 template <int VEC>
-__global__ void tc_bn_apply_kernel(const TcApplyArgs p) {
+struct TcApplyItem {
+  int64_t m;
+  int c0;
+  float v[VEC], r[VEC];
+};
+// issue every global load of one item (z and the residual sources) ...
+template <int VEC>
+__device__ __forceinline__ void tc_bn_apply_load(const TcApplyArgs& p, int64_t i, int cq, TcApplyItem<VEC>& it) {
+  it.m = i / cq;
+  it.c0 = (int)(i - it.m * cq) * VEC;
+  if (VEC == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p.z + it.m * p.ldz + it.c0);
+    it.v[0] = t.x; it.v[1 % VEC] = t.y; it.v[2 % VEC] = t.z; it.v[3 % VEC] = t.w;
+  } else {
+    it.v[0] = p.z[it.m * p.ldz + it.c0];
+  }
+#pragma unroll
+  for (int j = 0; j < VEC; j++) it.r[j] = 0.f;
+  if (p.res0) {
+    if (VEC == 4 && !p.idx0) {
+      const float4 t = *reinterpret_cast<const float4*>(p.res0 + it.m * p.ld0 + it.c0);
+      it.r[0] += t.x; it.r[1 % VEC] += t.y; it.r[2 % VEC] += t.z; it.r[3 % VEC] += t.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < VEC; j++) it.r[j] += p.res0[it.m * p.ld0 + (p.idx0 ? p.idx0[it.c0 + j] : it.c0 + j)];
+    }
+  }
+  if (p.res1) {
+    if (VEC == 4 && !p.idx1) {
+      const float4 t = *reinterpret_cast<const float4*>(p.res1 + it.m * p.ld1 + it.c0);
+      it.r[0] += t.x; it.r[1 % VEC] += t.y; it.r[2 % VEC] += t.z; it.r[3 % VEC] += t.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < VEC; j++) it.r[j] += p.res1[it.m * p.ld1 + (p.idx1 ? p.idx1[it.c0 + j] : it.c0 + j)];
+    }
+  }
+}
+// ... then normalise, activate, drop out, add the residuals and write the two planes
+template <int VEC>
+__device__ __forceinline__ void tc_bn_apply_finish(const TcApplyArgs& p, TcApplyItem<VEC>& it) {
+#pragma unroll
+  for (int j = 0; j < VEC; j++) {
+    const int c = it.c0 + j;
+    float y = (it.v[j] - p.mean[c]) * p.rstd[c] + p.beta[c];
+    y = act_fwd(y, p.act, p.alpha);
+    if (p.keep < 1.f) y = (philox_uniform(p.seed, p.stream_id, (uint64_t)(it.m * p.C + c)) < p.keep) ? y / p.keep : 0.f;
+    it.v[j] = y + it.r[j];
+  }
+  if (VEC == 4) {
+    *reinterpret_cast<float4*>(p.hi + it.m * p.ldo + it.c0) = make_float4(it.v[0], it.v[1 % VEC], it.v[2 % VEC], it.v[3 % VEC]);
+    *reinterpret_cast<float4*>(p.lo + it.m * p.ldo + it.c0) =
+        make_float4(tf32_lo(it.v[0]), tf32_lo(it.v[1 % VEC]), tf32_lo(it.v[2 % VEC]), tf32_lo(it.v[3 % VEC]));
+  } else {
+    p.hi[it.m * p.ldo + it.c0] = it.v[0];
+    p.lo[it.m * p.ldo + it.c0] = tf32_lo(it.v[0]);
+  }
+}
+// two items per thread and iteration, all loads issued before the first dependent instruction (four items measured
+// 35 % slower: the item array goes to local memory)
+template <int VEC>
+__global__ void __launch_bounds__(256) tc_bn_apply_kernel(const TcApplyArgs p) {
   const int cq = (p.C + VEC - 1) / VEC;
   const int64_t total = p.rows * cq;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t m = i / cq;
-    const int c0 = (int)(i - m * cq) * VEC;
-    float v[VEC];
-    if (VEC == 4) {
-      const float4 t = *reinterpret_cast<const float4*>(p.z + m * p.ldz + c0);
-      v[0] = t.x; v[1 % VEC] = t.y; v[2 % VEC] = t.z; v[3 % VEC] = t.w;
-    } else {
-      v[0] = p.z[m * p.ldz + c0];
-    }
-#pragma unroll
-    for (int j = 0; j < VEC; j++) {
-      const int c = c0 + j;
-      float y = (v[j] - p.mean[c]) * p.rstd[c] + p.beta[c];
-      y = act_fwd(y, p.act, p.alpha);
-      if (p.keep < 1.f) y = (philox_uniform(p.seed, p.stream_id, (uint64_t)(m * p.C + c)) < p.keep) ? y / p.keep : 0.f;
-      if (p.res0) y += p.res0[m * p.ld0 + (p.idx0 ? p.idx0[c] : c)];
-      if (p.res1) y += p.res1[m * p.ld1 + (p.idx1 ? p.idx1[c] : c)];
-      v[j] = y;
-    }
-    if (VEC == 4) {
-      *reinterpret_cast<float4*>(p.hi + m * p.ldo + c0) = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
-      *reinterpret_cast<float4*>(p.lo + m * p.ldo + c0) =
-          make_float4(tf32_lo(v[0]), tf32_lo(v[1 % VEC]), tf32_lo(v[2 % VEC]), tf32_lo(v[3 % VEC]));
-    } else {
-      p.hi[m * p.ldo + c0] = v[0];
-      p.lo[m * p.ldo + c0] = tf32_lo(v[0]);
-    }
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 2 * stride) {
+    TcApplyItem<VEC> a, b;
+    const bool two = i + stride < total;
+    tc_bn_apply_load<VEC>(p, i, cq, a);
+    if (two) tc_bn_apply_load<VEC>(p, i + stride, cq, b);
+    tc_bn_apply_finish<VEC>(p, a);
+    if (two) tc_bn_apply_finish<VEC>(p, b);
   }
 }
 
