@@ -53,6 +53,10 @@ def launches():
     out += ["", f"Total {tot / 1e3:.2f} ms over {len(step)} launches.",
             f"GEMM launches: {len(gem)}, {gt / 1e3:.2f} ms ({100 * gt / tot:.1f} % of the step), DRAM traffic {gb / 1e9:.2f} GB per step = {gb / len(gem) / 1e6:.1f} MB per launch (average)."]
     open(os.path.join(ROOT, "profiles", f"{tag}_launches_summary.md"), "w").write("\n".join(out) + "\n")
+    with open(os.path.join(ROOT, "profiles", f"{tag}_launches.csv"), "w") as f:   # the raw per-launch list of that step
+        f.write("launch,kernel,gpu_time_us,dram_read_bytes,dram_write_bytes\n")
+        for i, d in enumerate(step):
+            f.write(f"{i},\"{short(d['name'])}\",{d['gpu__time_duration.sum']:.2f},{d['dram__bytes_read.sum']:.0f},{d['dram__bytes_write.sum']:.0f}\n")
     json.dump({"gemm_launches_per_step": len(gem), "gemm_dram_bytes_per_step": gb, "gemm_dram_bytes_per_launch": gb / len(gem),
                "gemm_share_of_step_ncu": gt / tot, "source": f"profiles/{tag}_launches_summary.md"},
               open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json"), "w"), indent=1)
