@@ -1,11 +1,15 @@
-"""CPU ORACLE (test infrastructure, NOT product code) — shadow GAN generator forward.
+"""CPU ORACLE (test infrastructure, NOT product code) — shadow GAN models and objectives.
 
-Restates gan/shadow_data_models.py:43-90 in numpy (float64 or float32): seven slim convolution1d layers with one
-filter (SAME padding: total pad K-1, left = (K-1)//2; bias; leaky_relu 0.1), the dense residual
-pattern net_i = conv(net_{i-1}) + net_{i-1} + net_{i-2} (net1: + net0 only), tanh and no residual on net7;
-encoder-only stops after net4 (:75).  Parity with TensorFlow is unpinned (no TF here); the reference's DummySampler
-fixture (gan/gan_sampling_methods.py:191-201) gives the known answers used in tests/test_gpu_gan.py.
-Only tests/ imports this module."""
+numpy: the generator forward (gan/shadow_data_models.py:43-90; float64 or float32): seven slim convolution1d layers
+with one filter (SAME padding: total pad K-1, left = (K-1)//2; bias; leaky_relu 0.1), the dense
+residual pattern net_i = conv(net_{i-1}) + net_{i-1} + net_{i-2} (net1: + net0 only), tanh and no residual on net7;
+encoder-only stops after net4 (:75); create_inference_for_matrix_input (gan/wrappers/gan_common.py:282-304).
+torch (autograd, for the gradient parity tests): the generator, the discriminator (:93-123), the patch feature
+discriminator (:126-149), the CycleGAN-with-identity objective (gan/wrappers/cycle_gan_wrapper.py:189-333), PatchNCE
+and the CUT objective (gan/wrappers/cut_wrapper.py:90-208,256-420) including TensorFlow's fused softmax-xent gradient
+convention.  Parity with TensorFlow is UNPINNED (no TF in this image): the [TF-lib] semantics follow SURVEY App. A;
+the reference's DummySampler fixture (gan/gan_sampling_methods.py:191-201) gives the only known answers
+(tests/test_gpu_gan.py).  Only tests/ imports this module."""
 import numpy
 
 
