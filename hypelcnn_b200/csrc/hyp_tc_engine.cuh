@@ -833,6 +833,11 @@ static int tc_run(hyp_model& m, const TcLaunch& l, float* out, float* stats, int
     HYP_LAUNCHED();                               \
   } while (0)
 
+// rows per block for the one-column-per-thread kernels: about 8 resident blocks per SM over the whole grid
+static inline int tc_rows_per_block(int64_t rows, int cols) {
+  const int64_t xblocks = cdiv(cols, 128), want = std::max<int64_t>(1, 148 * 8 / xblocks);
+  return (int)std::max<int64_t>(8, cdiv(cdiv(rows, want), 8) * 8);
+}
 static inline int tc_grid(int64_t total) { return (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(total, 256), 148 * 16)); }
 
 static int tc_forward(hyp_model& m, const float* x, int64_t B, bool training, bool update_moving, uint64_t seed,
@@ -981,7 +986,8 @@ static int tc_backward(hyp_model& m, const uint8_t* labels, int64_t B, float* lo
               TC_EW_DISPATCH(ga, tc_bn_bwd_apply_v4_kernel, p, ga.rpb));
     } else {  // slot widths that break float4 alignment: scalar form
       TC_PROF("tc_bn_bwd_apply_kernel", 4.0 * rows * (2.0 * L.Cout + 2.0 * p.gcols),
-              (tc_bn_bwd_apply_kernel<<<tc_grid(rows * p.gcols), 256, 0, st>>>(p)));
+              (tc_bn_bwd_apply_kernel<<<dim3((unsigned)cdiv(p.gcols, 128), (unsigned)cdiv(rows, tc_rows_per_block(rows, p.gcols))), 256,
+                                        0, st>>>(p, tc_rows_per_block(rows, p.gcols))));
     }
     for (const Resid& r : L.res) {
       const Tensor& src = m.tensors[r.src];

@@ -323,27 +323,53 @@ __global__ void tc_bn_bwd_finalize_kernel(const float* __restrict__ part, int nb
 
 // gz = rstd * (g_y - mean(g_y) - zhat * mean(g_y * zhat)), written as (value, lo) planes in the
 // column order the dgrad / wgrad GEMMs want
-__global__ void tc_bn_bwd_apply_kernel(const TcBnBwdArgs p) {
-  const int64_t total = p.rows * p.gcols;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t m = i / p.gcols;
-    const int j = (int)(i - m * p.gcols);
-    int c = j;
-    bool valid = j < p.C;
-    if (p.fpad) {
-      const int slot = j / p.fpad, n = j - slot * p.fpad;
-      const int jt = slot % p.nt;
-      valid = slot < p.R * p.nt && n < min(p.ft, p.f - jt * p.ft);
-      c = (p.R - 1 - slot / p.nt) * p.f + jt * p.ft + n;
+// scalar form for slot widths that break float4 alignment: one gz column per thread (128 columns x 2 row lanes per
+// block), so the slot -> channel mapping and the per-channel constants are computed once and the row loop keeps four
+// independent loads of gout and z in flight; grid = (ceil(gcols / 128), row blocks)
+__global__ void __launch_bounds__(256) tc_bn_bwd_apply_kernel(const TcBnBwdArgs p, int rows_per_block) {
+  const int j = blockIdx.x * 128 + (threadIdx.x & 127), ty = threadIdx.x >> 7;
+  if (j >= p.gcols) return;
+  int c = j;
+  bool valid = j < p.C;
+  if (p.fpad) {
+    const int slot = j / p.fpad, n = j - slot * p.fpad;
+    const int jt = slot % p.nt;
+    valid = slot < p.R * p.nt && n < min(p.ft, p.f - jt * p.ft);
+    c = (p.R - 1 - slot / p.nt) * p.f + jt * p.ft + n;
+  }
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = min((int64_t)p.rows, r0 + rows_per_block);
+  if (!valid) {
+    for (int64_t r = r0 + ty; r < r1; r += 2) { p.gz_hi[r * p.ldgz + j] = 0.f; p.gz_lo[r * p.ldgz + j] = 0.f; }
+    return;
+  }
+  const float mean = p.mean[c], rstd = p.rstd[c], beta = p.beta[c], s1 = p.s1[c], s2 = p.s2[c];
+  for (int64_t r = r0 + ty; r < r1; r += 8) {
+    float g[4], z[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int64_t rr = r + 2 * u;
+      if (rr < r1) { g[u] = p.gout[rr * p.ldg + c]; z[u] = p.z[rr * p.ldz + c]; }
     }
-    float v = 0.f;
-    if (valid) {
-      float zhat;
-      const float g = tc_bn_gy(p, m, c, zhat);
-      v = p.rstd[c] * (g - p.s1[c] - zhat * p.s2[c]);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int64_t rr = r + 2 * u;
+      if (rr < r1) {
+        const float zhat = (z[u] - mean) * rstd;
+        const float y = zhat + beta;
+        float gy = g[u];
+        if (p.keep < 1.f) gy = (philox_uniform(p.seed, p.stream_id, (uint64_t)(rr * p.C + c)) < p.keep) ? gy / p.keep : 0.f;
+        if (p.act == ACT_LRELU) {
+          gy = (y > 0.f) ? gy : gy * p.alpha;
+        } else if (p.act == ACT_SIGMOID) {
+          const float sg = 1.f / (1.f + __expf(-y));
+          gy = gy * sg * (1.f - sg);
+        }
+        const float v = rstd * (gy - s1 - zhat * s2);
+        p.gz_hi[rr * p.ldgz + j] = v;
+        p.gz_lo[rr * p.ldgz + j] = tf32_lo(v);
+      }
     }
-    p.gz_hi[m * p.ldgz + j] = v;
-    p.gz_lo[m * p.ldgz + j] = tf32_lo(v);
   }
 }
 
