@@ -353,14 +353,39 @@ static void schedule_tiles(std::vector<TcTile>& tiles, size_t begin, const std::
   if (uniform) return;
   std::vector<std::vector<int>> lists(G);
   if (windowed) {
-    for (int w0 = 0; w0 < units; w0 += 2 * G) {
-      const int w1 = std::min(units, w0 + 2 * G);
+    // HYP_TC_SCHED=snake keeps the plain snake; default: inside every window the sorted units go, heaviest first, to
+    // the group with the smallest load accumulated over ALL windows so far (at most ceil(window / G) units per group
+    // and window), which also evens out the last, partially filled window
+    static const char* mode = getenv("HYP_TC_SCHED") ? getenv("HYP_TC_SCHED") : "lpt";
+    static const bool snake = !strcmp(mode, "snake");
+    static const int extra = !strcmp(mode, "lptx") ? 1 : 0;
+    static const int wmul = !strcmp(mode, "lpt4") ? 4 : (!strcmp(mode, "global") ? 1 << 20 : 2);
+    std::vector<double> load(G, 0.0);
+    for (int w0 = 0; w0 < units; w0 += wmul * G) {
+      const int w1 = (int)std::min<int64_t>(units, (int64_t)w0 + (int64_t)wmul * G);
       std::stable_sort(cost.begin() + w0, cost.begin() + w1,
                        [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first > b.first; });
+      const int cap = (int)cdiv(w1 - w0, G) + extra;
+      std::vector<int> taken(G, 0);
       for (int j = w0; j < w1; j++) {
         const int k = j - w0;
-        lists[k < G ? k : 2 * G - 1 - k].push_back(cost[j].second);
+        int g = k < G ? k : 2 * G - 1 - k;
+        if (!snake) {
+          g = -1;
+          for (int c = 0; c < G; c++)
+            if (taken[c] < cap && (g < 0 || load[c] < load[g])) g = c;
+        }
+        taken[g]++;
+        load[g] += cost[j].first;
+        lists[g].push_back(cost[j].second);
       }
+    }
+    if (wmul > 2)
+      for (auto& l : lists) std::sort(l.begin(), l.end());
+    if (getenv("HYP_TC_SCHED_DEBUG")) {
+      double mx = 0, sum = 0;
+      for (double l : load) { mx = std::max(mx, l); sum += l; }
+      fprintf(stderr, "[tc_sched] units=%d G=%d predicted max/avg load = %.3f\n", units, G, mx / (sum / G));
     }
   } else {
     std::stable_sort(cost.begin(), cost.end(),
@@ -372,6 +397,12 @@ static void schedule_tiles(std::vector<TcTile>& tiles, size_t begin, const std::
         if (load[g] < load[best]) best = g;
       load[best] += cu.first;
       lists[best].push_back(cu.second);
+    }
+    if (getenv("HYP_TC_SCHED_DEBUG")) {
+      double mx = 0, sum = 0;
+      for (double l : load) { mx = std::max(mx, l); sum += l; }
+      fprintf(stderr, "[tc_sched] LPT units=%d G=%d predicted max/avg load = %.3f (largest unit / avg load %.3f)\n", units, G,
+              mx / (sum / G), cost[0].first / (sum / G));
     }
   }
   size_t depth = 0;
@@ -494,6 +525,14 @@ static int tc_plan(hyp_model& m, int64_t B) {
         T.wg.cg = wg_cg(mt);
         const int kblocks = (int)cdiv(rows_out, 32);
         int ksplit = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(2 * tc_sm_count(), mt * ntn), std::max(1, kblocks / 4)));
+        {  // nudge the split so that the units fill the persistent grid evenly (units / groups just below an integer)
+          const double groups = (double)tc_sm_count() / T.wg.cg, units0 = (double)mt * ntn / T.wg.cg;
+          auto ratio = [&](int k) { const double per = units0 * k / groups; return std::ceil(per) / per; };
+          int bestk = ksplit;
+          for (int k = std::max(1, ksplit / 2); k <= std::min(2 * ksplit, std::max(1, kblocks / 4)); k++)
+            if (ratio(k) < ratio(bestk) - 1e-9) bestk = k;
+          if (ratio(ksplit) > 1.03) ksplit = bestk;
+        }
         const int kb_per = (int)cdiv(kblocks, ksplit);
         // K piece outermost: the (im, j) tiles of one row range run in the same wave and share their A / gz rows
         // through L2, so every activation and gradient row crosses HBM once
@@ -762,24 +801,38 @@ static int tc_plan(hyp_model& m, int64_t B) {
         if ((rc = map4(&T.wg.tmA, a0, Ct, B, PP, tin.Cp, (uint64_t)B * tin.Cp, tin.plane_elems, 32, 32, true))) return rc;
         if ((rc = map4(&T.wg.tmB, gz0, Cout, B, 1, T.Gp, (uint64_t)B * T.Gp, S.gz_plane_elems, 32, 32, true))) return rc;
         T.wg.mn = true; T.wg.bn = 32; T.wg.b_rows = 0; T.wg.tile0 = (int)pb.tiles.size();
-        T.wg.cg = wg_cg((int)cdiv(Ct, 128));
-        for (int pos = 0; pos < PP; pos++)
-          for (int j = 0; j < ntn; j++)
-            for (int im = 0; im < (int)cdiv(Ct, 128); im++) {
-              const int width = std::min(nw, Cout - j * nw);
-              TcSeg s{};
-              s.a2 = pos; s.b0 = j * nw; s.nk = (int)cdiv(B, 32); s.n_mma = r16(width);
-              s.nb = (int)cdiv(s.n_mma, 32);
-              T.wg.b_rows = std::max(T.wg.b_rows, wg_brows(s.n_mma, T.wg.cg));
-              TcTile t = blank_tile();
-              t.a0_add = im * 128;
-              t.seg_begin = (int)pb.segs.size(); t.seg_count = 1; t.total_kb = s.nk;
-              t.m_valid = std::min(128, Ct - im * 128); t.ncb = 1; t.ld_out = Cout;
-              t.cb[0].out_off = L.w_off[0] + ((int64_t)pos * Ct + im * 128) * Cout + j * nw;
-              t.cb[0].width = width;
-              pb.segs.push_back(s);
-              pb.tiles.push_back(t);
-            }
+        const int mt = (int)cdiv(Ct, 128);
+        T.wg.cg = wg_cg(mt);
+        // K (= batch) pieces: the split that fills the persistent grid most evenly (the epilogue is atomic, so pieces
+        // are free to land in any order); at least 8 K blocks per piece
+        const int kblocks = (int)cdiv(B, 32);
+        const double groups = (double)tc_sm_count() / T.wg.cg, units0 = (double)PP * ntn * mt / T.wg.cg;
+        int ksplit = 1;
+        double best = 1e30;
+        for (int k = 1; k <= std::max(1, std::min(8, kblocks / 8)); k++) {
+          const double per = units0 * k / groups, ratio = std::ceil(per) / per;
+          if (ratio < best - 1e-9) { best = ratio; ksplit = k; }
+        }
+        const int kb_per = (int)cdiv(kblocks, ksplit);
+        for (int kb0 = 0; kb0 < kblocks; kb0 += kb_per)
+          for (int pos = 0; pos < PP; pos++)
+            for (int j = 0; j < ntn; j++)
+              for (int im = 0; im < mt; im++) {
+                const int width = std::min(nw, Cout - j * nw);
+                TcSeg s{};
+                s.a1 = kb0 * 32; s.a2 = pos; s.b0 = j * nw; s.b1 = kb0 * 32;
+                s.nk = std::min(kb_per, kblocks - kb0); s.n_mma = r16(width);
+                s.nb = (int)cdiv(s.n_mma, 32);
+                T.wg.b_rows = std::max(T.wg.b_rows, wg_brows(s.n_mma, T.wg.cg));
+                TcTile t = blank_tile();
+                t.a0_add = im * 128;
+                t.seg_begin = (int)pb.segs.size(); t.seg_count = 1; t.total_kb = s.nk;
+                t.m_valid = std::min(128, Ct - im * 128); t.ncb = 1; t.ld_out = Cout;
+                t.cb[0].out_off = L.w_off[0] + ((int64_t)pos * Ct + im * 128) * Cout + j * nw;
+                t.cb[0].width = width;
+                pb.segs.push_back(s);
+                pb.tiles.push_back(t);
+              }
         finish_launch(pb, T.wg);
       }
     }
