@@ -32,7 +32,7 @@ struct TcLaunch {
   int b_rows = 0, bn = 0;
   bool mn = false;
   int cg = 1;  // CTA group size: 2 = tiles come in pairs (2i, 2i+1) that share their B operand
-  bool windowed = false;  // schedule: keep the tile order's locality (snake inside windows) instead of global LPT
+  bool windowed = false;  // schedule: keep the tile order's locality (load-aware dealing inside windows) instead of global LPT
 };
 
 struct TcLayer {
@@ -332,7 +332,7 @@ static void close_pair_run(std::vector<TcTile>& tiles, size_t run_begin, int oob
 // the launch's tile array is re-laid-out here: slot i * G + g holds the i-th unit of group g.
 //   windowed = true  (K-major level launches): units keep their locality order (batch-pair major: a
 //       wave of CTAs shares its A rows through L2); inside every window of 2G units the costs are
-//       sorted and dealt out in a snake (heaviest with lightest), so each group gets 2 units per window.
+//       sorted and dealt out heaviest first to the least loaded group (2 units per group and window).
 //   windowed = false (wgrad): plain LPT, longest unit first onto the least loaded group; groups that
 //       end up with fewer units get empty tiles.
 static double tile_cost(const TcTile& t, const std::vector<TcSeg>& segs) {
