@@ -353,19 +353,22 @@ static void schedule_tiles(std::vector<TcTile>& tiles, size_t begin, const std::
   if (uniform) return;
   std::vector<std::vector<int>> lists(G);
   if (windowed) {
-    // HYP_TC_SCHED=snake keeps the plain snake; default: inside every window the sorted units go, heaviest first, to
-    // the group with the smallest load accumulated over ALL windows so far (at most ceil(window / G) units per group
-    // and window), which also evens out the last, partially filled window
-    static const char* mode = getenv("HYP_TC_SCHED") ? getenv("HYP_TC_SCHED") : "lpt";
-    static const bool snake = !strcmp(mode, "snake");
-    static const int extra = !strcmp(mode, "lptx") ? 1 : 0;
-    static const int wmul = !strcmp(mode, "lpt4") ? 4 : (!strcmp(mode, "global") ? 1 << 20 : 2);
+    // Inside every window the sorted units go, heaviest first, to the group with the smallest load accumulated so
+    // far (at most ceil(window / G) units per group and window).  The windows are ASSIGNED last to first — the
+    // partially filled last window hands one unit to only some groups, and the full windows processed after it
+    // make up for that — but EXECUTED in their original order.  HYP_TC_SCHED=snake: the plain heaviest-with-
+    // lightest snake per window; =forward: assign first to last (measured 3 % / 0.5 % slower steps).
+    static const char* mode = getenv("HYP_TC_SCHED") ? getenv("HYP_TC_SCHED") : "reverse";
+    static const bool snake = !strcmp(mode, "snake"), forward = !strcmp(mode, "forward");
+    const int W = 2 * G, nwin = (int)cdiv(units, W);
     std::vector<double> load(G, 0.0);
-    for (int w0 = 0; w0 < units; w0 += wmul * G) {
-      const int w1 = (int)std::min<int64_t>(units, (int64_t)w0 + (int64_t)wmul * G);
+    std::vector<std::vector<std::vector<int>>> wl(nwin, std::vector<std::vector<int>>(G));
+    for (int wi = 0; wi < nwin; wi++) {
+      const int w = (snake || forward) ? wi : nwin - 1 - wi;
+      const int w0 = w * W, w1 = std::min(units, w0 + W);
       std::stable_sort(cost.begin() + w0, cost.begin() + w1,
                        [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first > b.first; });
-      const int cap = (int)cdiv(w1 - w0, G) + extra;
+      const int cap = (int)cdiv(w1 - w0, G);
       std::vector<int> taken(G, 0);
       for (int j = w0; j < w1; j++) {
         const int k = j - w0;
@@ -377,11 +380,11 @@ static void schedule_tiles(std::vector<TcTile>& tiles, size_t begin, const std::
         }
         taken[g]++;
         load[g] += cost[j].first;
-        lists[g].push_back(cost[j].second);
+        wl[w][g].push_back(cost[j].second);
       }
     }
-    if (wmul > 2)
-      for (auto& l : lists) std::sort(l.begin(), l.end());
+    for (int w = 0; w < nwin; w++)
+      for (int g = 0; g < G; g++) lists[g].insert(lists[g].end(), wl[w][g].begin(), wl[w][g].end());
     if (getenv("HYP_TC_SCHED_DEBUG")) {
       double mx = 0, sum = 0;
       for (double l : load) { mx = std::max(mx, l); sum += l; }
