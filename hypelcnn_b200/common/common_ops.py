@@ -1,38 +1,38 @@
-"""Mirror of the reference's common/common_ops.py:4-31 helpers (same names, same behaviour)."""
+"""Small host helpers with the names the reference's callers use (common/common_ops.py:4-31)."""
 import importlib
-import ntpath
+import os
 
 
 def get_class(kls):
-    """Resolve "pkg.Module.Class" (reference: common/common_ops.py:4-10).  The reference's
-    registry names ("nnmodel.X.X", "importer.X.X", "loader.X.X") resolve inside this package
-    first, then as top-level modules, so plug-ins on PYTHONPATH keep working."""
-    parts = kls.split(".")
-    module = ".".join(parts[:-1])
-    last = None
+    """Resolve a dotted "pkg.Module.Class" name.  The reference's registry strings ("nnmodel.X.X", "importer.X.X",
+    "loader.X.X") are looked up inside this package first and then as top-level modules, so third-party plug-ins on
+    PYTHONPATH keep working."""
+    module_name, _, attr = kls.rpartition(".")
+    failure = None
     for prefix in ("hypelcnn_b200.", ""):
         try:
-            m = importlib.import_module(prefix + module)
-            return getattr(m, parts[-1])
+            return getattr(importlib.import_module(prefix + module_name), attr)
         except (ImportError, AttributeError) as e:
-            last = e
-    raise ImportError(f"cannot resolve {kls}: {last}")
+            failure = e
+    raise ImportError(f"cannot resolve {kls}: {failure}")
 
 
 def is_integer_num(n):
-    if isinstance(n, int):
-        return True
-    if isinstance(n, float):
-        return n.is_integer()
-    return False
+    """True for ints and for floats with no fractional part (bools count as ints, like in the reference)."""
+    return isinstance(n, int) or (isinstance(n, float) and n.is_integer())
 
 
 def replace_abbrs(txt, abbrs_dict):
-    for word, abbr in abbrs_dict.items():
-        txt = txt.replace(word, abbr)
+    """Apply every word -> abbreviation substitution of the dict, in its order."""
+    for word in abbrs_dict:
+        txt = txt.replace(word, abbrs_dict[word])
     return txt
 
 
 def path_leaf(path):
-    head, tail = ntpath.split(path)
-    return tail or ntpath.basename(head)
+    """Last component of a path written with either separator (trailing separators and a drive prefix ignored)."""
+    unified = path.replace(chr(92), "/")
+    if len(unified) >= 2 and unified[1] == ":":
+        unified = unified[2:]
+    tail = unified.rsplit("/", 1)[-1]
+    return tail if tail else unified.rstrip("/").rsplit("/", 1)[-1]

@@ -7,30 +7,32 @@ from hypelcnn_b200.gan.wrappers.gan_common import create_inference_for_matrix_in
 
 
 class ShadowOpHolder:
+    """What the classifier's input pipeline receives from a shadow augmenter (reference: gan/gan_utilities.py:7-15,
+    same four fields): the two batch transforms, a factory for the object that restores the generator weights, and
+    the function that runs the restore."""
+
+    __slots__ = ("shadow_op", "deshadow_op", "shadow_op_creater", "shadow_op_initializer")
 
     def __init__(self, shadow_op, deshadow_op, shadow_op_creater, shadow_op_initializer) -> None:
-        super().__init__()
-        self.shadow_op_initializer = shadow_op_initializer
-        self.shadow_op_creater = shadow_op_creater
-        self.shadow_op = shadow_op
-        self.deshadow_op = deshadow_op
+        self.shadow_op, self.deshadow_op = shadow_op, deshadow_op
+        self.shadow_op_creater, self.shadow_op_initializer = shadow_op_creater, shadow_op_initializer
 
 
 def create_simple_shadow_struct(shadow_ratio):
-    """Division / multiplication by the per-band shadow ratio, LiDAR (last channel) by 1 (:18-28)."""
-    ratio = numpy.append(numpy.asarray(shadow_ratio, dtype=numpy.float32), numpy.float32(1))
+    """The ratio augmenter (:18-28): shadowing divides every band by its shadow ratio, de-shadowing multiplies; the
+    trailing LiDAR channel passes through (ratio 1).  The ratio vector is uploaded once per device."""
+    host_ratio = numpy.concatenate([numpy.asarray(shadow_ratio, dtype=numpy.float32), numpy.ones(1, numpy.float32)])
+    on_device = {}
 
-    def _ratio_on(inp):
-        return torch.as_tensor(ratio, device=inp.device)
+    def ratio_for(batch):
+        if batch.device not in on_device:
+            on_device[batch.device] = torch.as_tensor(host_ratio, device=batch.device)
+        return on_device[batch.device]
 
-    def simple_shadow_func(inp):
-        return inp / _ratio_on(inp)
-
-    def simple_deshadow_func(inp):
-        return inp * _ratio_on(inp)
-
-    return ShadowOpHolder(shadow_op=simple_shadow_func, deshadow_op=simple_deshadow_func,
-                          shadow_op_creater=lambda: None, shadow_op_initializer=lambda restorer, session: None)
+    return ShadowOpHolder(shadow_op=lambda batch: batch / ratio_for(batch),
+                          deshadow_op=lambda batch: batch * ratio_for(batch),
+                          shadow_op_creater=lambda: None,
+                          shadow_op_initializer=lambda restorer, session: None)
 
 
 class GeneratorInferenceWrapper:

@@ -32,18 +32,19 @@ class InMemoryImporter(DataImporter):
         return Target(data=data, labels=labels)
 
     def read_data_set(self, loader_name, path, train_data_ratio, test_data_ratio, neighborhood, normalize):
-        start_time = time.time()
+        t0 = time.perf_counter()
         loader = get_loader_from_name(loader_name, path)
-        data_set = loader.load_data(neighborhood, normalize)
-        sample_set = loader.load_samples(train_data_ratio, test_data_ratio)
-        training_data_with_labels = self._get_data_with_labels(sample_set.training_targets, loader, data_set)
-        validation_data_with_labels = self._get_data_with_labels(sample_set.validation_targets, loader, data_set)
-        test_data_with_labels = self._get_data_with_labels(sample_set.test_targets, loader, data_set)
+        scene = loader.load_data(neighborhood, normalize)
+        samples = loader.load_samples(train_data_ratio, test_data_ratio)
+        # one gather launch per split; the patches stay in HBM
+        split = {name: self._get_data_with_labels(getattr(samples, name + "_targets"), loader, scene)
+                 for name in ("training", "test", "validation")}
         torch.cuda.synchronize()
-        print(f"Loaded dataset({time.time() - start_time:.3f} sec)")
-        return training_data_with_labels, test_data_with_labels, validation_data_with_labels, \
-            data_set.shadow_creator_dict, loader.get_class_count(), data_set.get_scene_shape(), \
-            loader.get_samples_color_list()
+        counts = ", ".join(f"{name} {t.labels.shape[0]}" for name, t in split.items())
+        print(f"Gathered {counts} patches in {time.perf_counter() - t0:.3f} s")
+        # the 7-tuple the reference's callers unpack (importer/InMemoryImporter.py:51-52)
+        return (split["training"], split["test"], split["validation"], scene.shadow_creator_dict,
+                loader.get_class_count(), scene.get_scene_shape(), loader.get_samples_color_list())
 
     @staticmethod
     def _one_hot(labels, class_range):
