@@ -1314,6 +1314,24 @@ int hyp_gather_patches(const void* casi, int casi_dtype, int Hc, int Wc, int C_h
 // Splits both operands into TF32 (hi, lo) planes, builds tensor maps and tile tables exactly
 // as the engine does, and runs tc_gemm_kernel.  ksplit > 1 (mn = 1 only) splits K over CTAs
 // that accumulate with atomics (D must be zeroed by the caller).
+// host-only: the static tile schedule on a plain cost vector (tests/test_schedule.py)
+int hyp_debug_schedule(const double* costs, int units, int groups, int windowed, int32_t* group_of_unit,
+                       int32_t* rank_in_group) {
+  HYP_CHECK_ARG(costs && group_of_unit && rank_in_group && units >= 0 && groups >= 1, "bad argument");
+  std::vector<std::pair<double, int>> cost((size_t)units);
+  for (int u = 0; u < units; u++) cost[u] = {costs[u], u};
+  const std::vector<std::vector<int>> lists = tc::assign_units(cost, groups, windowed != 0);
+  for (int u = 0; u < units; u++) group_of_unit[u] = rank_in_group[u] = -1;
+  for (int g = 0; g < groups; g++)
+    for (size_t i = 0; i < lists[g].size(); i++) {
+      const int u = lists[g][i];
+      HYP_CHECK_ARG(u >= 0 && u < units && group_of_unit[u] < 0, "schedule lost or duplicated a unit");
+      group_of_unit[u] = g;
+      rank_in_group[u] = (int32_t)i;
+    }
+  return HYP_OK;
+}
+
 int hyp_debug_tc_gemm(int mn_flags, const float* A, const float* B, int M, int N, int K, float* D, float* stats,
                       int raw_hi, int bn, int ksplit, int chunk_kb, void* stream) {
   using namespace hyp::tc;

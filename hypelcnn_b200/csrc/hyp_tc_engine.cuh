@@ -340,17 +340,9 @@ static double tile_cost(const TcTile& t, const std::vector<TcSeg>& segs) {
   for (int i = 0; i < t.seg_count; i++) c += (double)segs[t.seg_begin + i].nk * (256.0 + segs[t.seg_begin + i].n_mma);
   return c;
 }
-static void schedule_tiles(std::vector<TcTile>& tiles, size_t begin, const std::vector<TcSeg>& segs, int cg, bool windowed) {
-  const int units = (int)((tiles.size() - begin) / cg);
-  const int G = tc_sm_count() / cg;
-  if (units <= G) return;
-  std::vector<std::pair<double, int>> cost(units);
-  bool uniform = true;
-  for (int u = 0; u < units; u++) {
-    cost[u] = {tile_cost(tiles[begin + (size_t)u * cg], segs), u};
-    uniform = uniform && cost[u].first == cost[0].first;
-  }
-  if (uniform) return;
+// the assignment itself, on plain (cost, unit) pairs: lists[g] = the units of group g in execution order
+static std::vector<std::vector<int>> assign_units(std::vector<std::pair<double, int>> cost, int G, bool windowed) {
+  const int units = (int)cost.size();
   std::vector<std::vector<int>> lists(G);
   if (windowed) {
     // Inside every window the sorted units go, heaviest first, to the group with the smallest load accumulated so
@@ -408,6 +400,20 @@ static void schedule_tiles(std::vector<TcTile>& tiles, size_t begin, const std::
               mx / (sum / G), cost[0].first / (sum / G));
     }
   }
+  return lists;
+}
+static void schedule_tiles(std::vector<TcTile>& tiles, size_t begin, const std::vector<TcSeg>& segs, int cg, bool windowed) {
+  const int units = (int)((tiles.size() - begin) / cg);
+  const int G = tc_sm_count() / cg;
+  if (units <= G) return;
+  std::vector<std::pair<double, int>> cost(units);
+  bool uniform = true;
+  for (int u = 0; u < units; u++) {
+    cost[u] = {tile_cost(tiles[begin + (size_t)u * cg], segs), u};
+    uniform = uniform && cost[u].first == cost[0].first;
+  }
+  if (uniform) return;
+  const std::vector<std::vector<int>> lists = assign_units(cost, G, windowed);
   size_t depth = 0;
   for (const auto& l : lists) depth = std::max(depth, l.size());
   std::vector<TcTile> out(depth * G * cg, blank_tile());

@@ -248,6 +248,13 @@ int hyp_model_debug_tensor(hyp_model* m, const char* name, int what, float** ptr
 /* the 0/1 keep mask hyp_model_forward applies on dropout layer `layer_scope` for `seed` */
 int hyp_model_dropout_mask(hyp_model* m, const char* layer_scope, uint64_t seed, int64_t B,
                            uint8_t* mask_out, void* stream);
+/* Debug / test hook, host only (no device needed): the static tile schedule of the persistent GEMM kernel
+ * (hyp_tc_engine.cuh schedule_tiles) applied to a plain cost vector.  group_of_unit[u] = CTA group that runs unit u,
+ * rank_in_group[u] = its position in that group's execution order.  windowed != 0: locality windows of 2*groups units
+ * with load-aware dealing (K-major and level-wgrad launches); 0: plain longest-processing-time-first. */
+int hyp_debug_schedule(const double* costs, int units, int groups, int windowed, int32_t* group_of_unit,
+                       int32_t* rank_in_group);
+
 /* probe of the tcgen05/TMA segment-GEMM building block used by the tensor-core precision
  * modes (3xTF32 split).  mn bit 0 = 0: A[M,K], B[N,K] -> D = A*B^T (K-major); 1: A[K,M], B[K,N]
  * -> D = A^T*B (MN-major).  mn bit 1: run as CTA pairs (tcgen05 cta_group::2).
