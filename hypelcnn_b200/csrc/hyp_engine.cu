@@ -1314,6 +1314,38 @@ int hyp_gather_patches(const void* casi, int casi_dtype, int Hc, int Wc, int C_h
 // Splits both operands into TF32 (hi, lo) planes, builds tensor maps and tile tables exactly
 // as the engine does, and runs tc_gemm_kernel.  ksplit > 1 (mn = 1 only) splits K over CTAs
 // that accumulate with atomics (D must be zeroed by the caller).
+// host-only: CRC-32C (Castagnoli, reflected 0x82F63B78), slicing-by-8 — the checksum of the TFRecord framing
+// (importer/TFRecordImporter.py, utilities/tfrecord_writer.py read / write TFRecord files through TensorFlow)
+int hyp_crc32c(const void* data, uint64_t len, uint32_t* crc_inout) {
+  HYP_CHECK_ARG(crc_inout && (data || len == 0), "null argument");
+  static uint32_t table[8][256];
+  static bool ready = false;
+  if (!ready) {
+    for (uint32_t n = 0; n < 256; n++) {
+      uint32_t c = n;
+      for (int k = 0; k < 8; k++) c = (c & 1u) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      table[0][n] = c;
+    }
+    for (uint32_t n = 0; n < 256; n++)
+      for (int t = 1; t < 8; t++) table[t][n] = (table[t - 1][n] >> 8) ^ table[0][table[t - 1][n] & 0xffu];
+    ready = true;
+  }
+  const uint8_t* p = static_cast<const uint8_t*>(data);
+  uint32_t c = ~*crc_inout;
+  while (len >= 8) {
+    uint64_t w;
+    memcpy(&w, p, 8);
+    w ^= c;  // little-endian hosts (x86-64, aarch64)
+    c = table[7][w & 0xff] ^ table[6][(w >> 8) & 0xff] ^ table[5][(w >> 16) & 0xff] ^ table[4][(w >> 24) & 0xff] ^
+        table[3][(w >> 32) & 0xff] ^ table[2][(w >> 40) & 0xff] ^ table[1][(w >> 48) & 0xff] ^ table[0][w >> 56];
+    p += 8;
+    len -= 8;
+  }
+  while (len--) c = (c >> 8) ^ table[0][(c ^ *p++) & 0xffu];
+  *crc_inout = ~c;
+  return HYP_OK;
+}
+
 // host-only: the static tile schedule on a plain cost vector (tests/test_schedule.py)
 int hyp_debug_schedule(const double* costs, int units, int groups, int windowed, int32_t* group_of_unit,
                        int32_t* rank_in_group) {

@@ -248,6 +248,11 @@ int hyp_model_debug_tensor(hyp_model* m, const char* name, int what, float** ptr
 /* the 0/1 keep mask hyp_model_forward applies on dropout layer `layer_scope` for `seed` */
 int hyp_model_dropout_mask(hyp_model* m, const char* layer_scope, uint64_t seed, int64_t B,
                            uint8_t* mask_out, void* stream);
+/* Host only: CRC-32C (Castagnoli) update, *crc_inout = crc32c(previous *crc_inout, data[0..len)); start from 0.
+ * The checksum of the TFRecord framing TensorFlow writes for importer/TFRecordImporter.py:16-72 and
+ * utilities/tfrecord_writer.py:45-81 (masked: ((crc >> 15) | (crc << 17)) + 0xa282ead8). */
+int hyp_crc32c(const void* data, uint64_t len, uint32_t* crc_inout);
+
 /* Debug / test hook, host only (no device needed): the static tile schedule of the persistent GEMM kernel
  * (hyp_tc_engine.cuh schedule_tiles) applied to a plain cost vector.  group_of_unit[u] = CTA group that runs unit u,
  * rank_in_group[u] = its position in that group's execution order.  windowed != 0: locality windows of 2*groups units
