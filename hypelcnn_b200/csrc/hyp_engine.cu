@@ -1364,6 +1364,27 @@ int hyp_debug_schedule(const double* costs, int units, int groups, int windowed,
   return HYP_OK;
 }
 
+// host-only: the pair-tile plan of a level forward launch as flat tables (tests/test_level_pairs.py)
+int hyp_debug_plan_level_pairs(int P, int R, int fpad, int32_t* tiles, int tiles_cap, int32_t* segs, int segs_cap,
+                               int32_t* counts) {
+  HYP_CHECK_ARG(tiles && segs && counts && P >= 1 && R >= 1 && fpad >= 16 && fpad % 16 == 0 && R * fpad <= 128,
+                "bad argument (R * fpad <= 128)");
+  std::vector<tc::PairTile> t;
+  std::vector<tc::PairSeg> sg;
+  tc::plan_level_pairs(P, R, fpad, t, sg);
+  counts[0] = (int32_t)t.size();
+  counts[1] = (int32_t)sg.size();
+  HYP_CHECK_ARG((int)t.size() <= tiles_cap && (int)sg.size() <= segs_cap, "output tables too small");
+  for (size_t i = 0; i < t.size(); i++) {
+    tiles[4 * i] = t[i].p1; tiles[4 * i + 1] = t[i].p2; tiles[4 * i + 2] = t[i].seg_begin; tiles[4 * i + 3] = t[i].seg_count;
+  }
+  for (size_t i = 0; i < sg.size(); i++) {
+    segs[6 * i] = sg[i].q; segs[6 * i + 1] = sg[i].n1; segs[6 * i + 2] = sg[i].n2; segs[6 * i + 3] = sg[i].brow1;
+    segs[6 * i + 4] = sg[i].brow2; segs[6 * i + 5] = sg[i].dcol;
+  }
+  return HYP_OK;
+}
+
 int hyp_debug_tc_gemm(int mn_flags, const float* A, const float* B, int M, int N, int K, float* D, float* stats,
                       int raw_hi, int bn, int ksplit, int chunk_kb, void* stream) {
   using namespace hyp::tc;

@@ -423,6 +423,55 @@ static void schedule_tiles(std::vector<TcTile>& tiles, size_t begin, const std::
   tiles.resize(begin);
   tiles.insert(tiles.end(), out.begin(), out.end());
 }
+// ---- groundwork for the next round ("level forward"): pair tiles --------------------------------
+// One tile = two horizontally adjacent output positions p1, p2 = p1 + 1 (a position left over at the end of an odd
+// row runs alone).  TMEM columns [0, W) hold p1 with the slot order MIRRORED (smallest kernel first), [W, 2W) hold p2
+// in the normal order (largest kernel first), W = R * fpad <= 128.  A tap of ring r feeds the (R - r) largest
+// kernels, i.e. the LAST n1 = (R - r1) * fpad columns of p1's half and the FIRST n2 = (R - r2) * fpad of p2's: an
+// input position q that both outputs use is ONE MMA of N = n1 + n2 into the contiguous range [W - n1, W + n2), its B
+// operand = the last n1 rows of tap (q - p1) in a mirrored copy of the packed weights followed by the first n2 rows
+// of tap (q - p2) in the normal copy.  Pure planning code (no device state): tests/test_level_pairs.py replays the
+// plan in numpy against a direct SAME convolution.  Not wired into tc_plan yet — the kernel still needs a per-segment
+// accumulator column offset and B assembled from two box sets.
+struct PairSeg { int q, n1, n2, brow1, brow2, dcol; };   // brow1: row in the mirrored copy, brow2: row in the normal copy
+struct PairTile { int p1, p2, seg_begin, seg_count; };   // p2 = -1: single position
+static void plan_level_pairs(int P, int R, int fpad, std::vector<PairTile>& tiles, std::vector<PairSeg>& segs) {
+  const int h = std::min(R - 1, P - 1), TW = 2 * h + 1, W = R * fpad;
+  auto ring_of = [&](int p, int q, int& tap) {   // ring of the tap that connects input q to output p, -1 if none
+    const int dy = q / P - p / P, dx = q % P - p % P;
+    if (std::abs(dy) > h || std::abs(dx) > h) return -1;
+    tap = (dy + h) * TW + (dx + h);
+    return std::max(std::abs(dy), std::abs(dx));
+  };
+  for (int y = 0; y < P; y++)
+    for (int x = 0; x < P; x += 2) {
+      PairTile t;
+      t.p1 = y * P + x;
+      t.p2 = x + 1 < P ? t.p1 + 1 : -1;
+      t.seg_begin = (int)segs.size();
+      // widest ranges first: (r1, r2) ascending by max ring keeps the epilogue's per-chunk column range shrinking
+      std::vector<std::pair<int, PairSeg>> found;
+      for (int q = 0; q < P * P; q++) {
+        int tap1 = 0, tap2 = 0;
+        const int r1 = ring_of(t.p1, q, tap1), r2 = t.p2 >= 0 ? ring_of(t.p2, q, tap2) : -1;
+        if (r1 < 0 && r2 < 0) continue;
+        PairSeg s;
+        s.q = q;
+        s.n1 = r1 >= 0 ? (R - r1) * fpad : 0;
+        s.n2 = r2 >= 0 ? (R - r2) * fpad : 0;
+        s.brow1 = tap1 * W + (W - s.n1);
+        s.brow2 = tap2 * W;
+        s.dcol = W - s.n1;
+        found.push_back({std::max(r1, r2), s});
+      }
+      std::stable_sort(found.begin(), found.end(),
+                       [](const std::pair<int, PairSeg>& a, const std::pair<int, PairSeg>& b) { return a.first < b.first; });
+      for (auto& f : found) segs.push_back(f.second);
+      t.seg_count = (int)segs.size() - t.seg_begin;
+      tiles.push_back(t);
+    }
+}
+
 static int map4(CUtensorMap* mp, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2,
                 uint64_t plane, uint32_t b0, uint32_t b1, bool mn) {
   const uint64_t dims[4] = {d0, d1, d2, 2};

@@ -253,6 +253,13 @@ int hyp_model_dropout_mask(hyp_model* m, const char* layer_scope, uint64_t seed,
  * utilities/tfrecord_writer.py:45-81 (masked: ((crc >> 15) | (crc << 17)) + 0xa282ead8). */
 int hyp_crc32c(const void* data, uint64_t len, uint32_t* crc_inout);
 
+/* Debug / test hook, host only: the pair-tile plan of a level forward launch (hyp_tc_engine.cuh plan_level_pairs;
+ * groundwork, not used by hyp_model_forward yet).  tiles: rows of (p1, p2 or -1, seg_begin, seg_count); segs: rows of
+ * (input position q, n1, n2, row in the mirrored weight copy, row in the normal copy, accumulator column); counts =
+ * (number of tiles, number of segments). */
+int hyp_debug_plan_level_pairs(int P, int R, int fpad, int32_t* tiles, int tiles_cap, int32_t* segs, int segs_cap,
+                               int32_t* counts);
+
 /* Debug / test hook, host only (no device needed): the static tile schedule of the persistent GEMM kernel
  * (hyp_tc_engine.cuh schedule_tiles) applied to a plain cost vector.  group_of_unit[u] = CTA group that runs unit u,
  * rank_in_group[u] = its position in that group's execution order.  windowed != 0: locality windows of 2*groups units
