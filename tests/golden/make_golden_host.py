@@ -44,6 +44,25 @@ def main():
            "dummy_sampler": {"element_count": 5, "fill_value": 0.5, "coefficient": 2, "shape": list(normal.shape),
                              "dtype": str(normal.dtype), "normal": float(normal.flat[0]), "shadow": float(shadow.flat[0]),
                              "constant": bool((normal == normal.flat[0]).all() and (shadow == shadow.flat[0]).all())}}
+    # the plug-in boundary itself: abstract method names and argument lists of the reference's four ABC modules
+    import inspect
+    import importer.DataImporter as DI
+    import loader.DataLoader as DL
+    import nnmodel.NNModel as NM
+    import gan.wrappers.wrapper as GW
+    interfaces = {}
+    for module, names in ((DI, ["DataImporter"]), (DL, ["DataLoader", "SampleSet", "LoadingMode"]), (NM, ["NNModel"]),
+                          (GW, ["Wrapper", "InferenceWrapper"])):
+        for name in names:
+            cls = getattr(module, name)
+            entry = {"abstract": sorted(getattr(cls, "__abstractmethods__", [])), "methods": {}}
+            for mname, fn in inspect.getmembers(cls, predicate=inspect.isfunction):
+                if not mname.startswith("__") or mname == "__init__":
+                    entry["methods"][mname] = list(inspect.signature(fn).parameters)
+            if name == "LoadingMode":
+                entry["members"] = {m.name: m.value for m in cls}
+            interfaces[module.__name__ + "." + name] = entry
+    out["interfaces"] = interfaces
     with open(os.path.join(HERE, "host_helpers.json"), "w") as f:
         json.dump(out, f, indent=1)
     print("wrote host_helpers.json")

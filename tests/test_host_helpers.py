@@ -33,3 +33,19 @@ def test_dummy_sampler_matches_the_reference():
     normal, shadow = DummySampler(g["element_count"], g["fill_value"], g["coefficient"]).get_sample_pairs(Shape(), None, None)
     assert list(normal.shape) == g["shape"] and str(normal.dtype) == g["dtype"] and g["constant"]
     assert numpy.all(normal == g["normal"]) and numpy.all(shadow == g["shadow"])
+
+
+def test_plugin_interfaces_have_the_reference_signatures():
+    """Every abstract method of the reference's DataImporter / DataLoader / NNModel / Wrapper / InferenceWrapper exists
+    here under the same name with the same argument list (the drop-in boundary)."""
+    import importlib
+    import inspect
+    assert len(GOLD["interfaces"]) == 7
+    for qualified, entry in GOLD["interfaces"].items():
+        module_name, _, cls_name = qualified.rpartition(".")
+        cls = getattr(importlib.import_module("hypelcnn_b200." + module_name), cls_name)
+        assert sorted(getattr(cls, "__abstractmethods__", [])) == entry["abstract"], qualified
+        for mname, params in entry["methods"].items():
+            assert list(inspect.signature(getattr(cls, mname)).parameters) == params, (qualified, mname)
+        if "members" in entry:
+            assert {m.name: m.value for m in cls} == entry["members"]
