@@ -488,9 +488,8 @@ def get_loader_from_name(loader_name, path):
     return get_class("loader." + loader_name + "." + loader_name)(path)
 
 
-def create_target_image_via_samples(sample_set, scene_shape):
-    image = numpy.full([scene_shape[0], scene_shape[1]], INVALID_TARGET_VALUE, dtype=numpy.uint8)
-    targets = numpy.vstack([sample_set.training_targets, sample_set.test_targets, sample_set.validation_targets])
-    for point in targets.astype(int):
-        image[point[1], point[0]] = point[2]
-    return image
+# host-side sample-list / shadow-statistics helpers of the reference's module, implemented in sample_ops.py
+from hypelcnn_b200.common.sample_ops import (calculate_shadow_ratio, create_colored_image,  # noqa: E402,F401
+                                             create_target_image_via_samples, read_targets_from_image,
+                                             shuffle_test_data_using_ratio, shuffle_training_data_using_ratio,
+                                             shuffle_training_data_using_size)
