@@ -105,3 +105,67 @@ def test_concnn_oracle_follows_the_reference_graph(case):
     got = replay(case, v, x, lambda y, name: y if name is None else RC._relu(y), RC.lrn)
     ref = RC.forward(v, x, classes, alg, False)["logits"]
     assert got.shape == ref.shape and torch.allclose(got, ref, rtol=1e-10, atol=1e-10)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# HYPELCNN: the same replay for the headline model (tests/golden/hypelcnn_graph_trace.json, make_golden.py)
+HYP = json.load(open(os.path.join(GOLD, "hypelcnn_graph_trace.json")))
+
+
+def replay_hypelcnn(case, v, x, alg):
+    from oracle import hypelcnn_ref as R
+    t = {case["input_id"]: x}
+
+    def normalise_activate(z, e):
+        assert e["normalizer"] == "batch_norm"
+        params = e.get("norm_params", {"decay": alg["bn_decay"], "is_training": case["is_training"]})   # FCs: arg_scope's
+        assert params["decay"] == alg["bn_decay"] and params["is_training"] == case["is_training"]
+        scope = f"nn_core/{e['scope']}/BatchNorm/"
+        y = R.batch_norm(z, v[scope + "beta"], v[scope + "moving_mean"], v[scope + "moving_variance"],
+                         params["is_training"], alg["bn_decay"])[0]
+        if e["activation"] == "<lambda>":
+            return R.leaky_relu(y, alg["lrelu_alpha"])
+        return torch.sigmoid(y) if e["activation"] == "sigmoid" else y
+
+    for e in case["trace"]:
+        op = e["op"]
+        if op == "conv2d":
+            t[e["out"]] = normalise_activate(R.conv2d_same_nhwc(t[e["in"]], v[f"nn_core/{e['scope']}/weights"]), e)
+        elif op == "fully_connected":
+            t[e["out"]] = normalise_activate(t[e["in"]] @ v[f"nn_core/{e['scope']}/weights"], e)
+        elif op == "gather":
+            t[e["out"]] = t[e["in"]].index_select(e["axis"], torch.tensor(e["indices"]))
+        elif op == "repeat":
+            t[e["out"]] = t[e["in"]].repeat_interleave(e["repeats"], dim=e["axis"])
+        elif op == "add":
+            t[e["out"]] = t[e["a"]] + t[e["b"]]
+        elif op == "concat":
+            t[e["out"]] = torch.cat([t[i] for i in e["ins"]], dim=e["axis"])
+        elif op == "flatten":
+            t[e["out"]] = t[e["in"]].reshape(t[e["in"]].shape[0], -1)
+        elif op == "dropout":
+            t[e["out"]] = t[e["in"]]                             # compared against the oracle with dropout off
+        else:
+            raise AssertionError(f"unknown op {op}")
+    recon = None if case["image_output"] is None else t[case["image_output"]]
+    return t[case["y_conv"]], recon
+
+
+@pytest.mark.parametrize("key", sorted(HYP))
+def test_hypelcnn_oracle_follows_the_reference_graph(key):
+    from oracle import hypelcnn_ref as R
+    case = HYP[key]
+    P, C, classes = case["patch"], case["channels"], case["classes"]
+    alg = {**case["alg"], "drop_out_ratio": 0.0}
+    v = R.init_variables(P, C, classes, alg, seed=7, dtype=torch.float64)
+    for name in v:                                               # non-trivial BN state on both sides
+        if name.endswith("moving_mean") or name.endswith("beta"):
+            v[name] = v[name] + 0.05 * torch.randn(v[name].shape, dtype=torch.float64, generator=torch.Generator().manual_seed(1))
+    x = torch.rand(4, P, P, C, dtype=torch.float64, generator=torch.Generator().manual_seed(2))
+    logits, recon = replay_hypelcnn(case, v, x, alg)
+    ref = R.forward(v, x, classes, alg, case["is_training"], update_moving=False)
+    assert torch.allclose(logits, ref["logits"], rtol=1e-9, atol=1e-9)
+    if recon is not None:
+        assert torch.allclose(recon.reshape(ref["recon"].shape), ref["recon"], rtol=1e-9, atol=1e-9)
+    else:
+        assert ref.get("recon") is None
