@@ -1,7 +1,8 @@
 """gan_type -> Wrapper registry (reference: gan/wrapper_registry.py:13-94): cycle_gan, gan_x2y, gan_y2x, cut_x2y,
 cut_y2x, dcl_gan, dcl_cycle_gan.  What the reference binds into its model functions with functools.partial
 (flags.patches, flags.embedded_feat_size, the two regularisation scales, :31-40) is passed to the wrappers here."""
-from hypelcnn_b200.gan.gan_sampling_methods import DummySampler
+from hypelcnn_b200.gan.gan_sampling_methods import (DummySampler, NeighborhoodBasedSampler, RandomBasedSampler,
+                                                    TargetBasedSampler)
 from hypelcnn_b200.gan.wrappers.cut_wrapper import CUTInferenceWrapper, CUTWrapper
 from hypelcnn_b200.gan.wrappers.cycle_gan_wrapper import CycleGANInferenceWrapper, CycleGANWrapper
 from hypelcnn_b200.gan.wrappers.dcl_cycle_gan_wrapper import DCLCycleGANInferenceWrapper, DCLCycleGANWrapper
@@ -10,7 +11,11 @@ from hypelcnn_b200.gan.wrappers.gan_wrapper import GANInferenceWrapper, GANWrapp
 
 
 def get_sampling_map():
-    return {"dummy": DummySampler(element_count=2000, fill_value=0.5, coefficient=2)}
+    """--pairing_method -> sampler, with the reference's constants (gan/wrapper_registry.py:13-18)."""
+    return {"target": TargetBasedSampler(margin=5),
+            "random": RandomBasedSampler(multiply_shadowed_data=True),
+            "neighbour": NeighborhoodBasedSampler(neighborhood_size=20, margin=2),
+            "dummy": DummySampler(element_count=2000, fill_value=0.5, coefficient=2)}
 
 
 def get_infer_wrapper_dict(bands=64):
