@@ -488,6 +488,41 @@ def get_loader_from_name(loader_name, path):
     return get_class("loader." + loader_name + "." + loader_name)(path)
 
 
+def shadow_ratio_of_data_set(data_set, padded_shadow_map, neighborhood):
+    """calculate_shadow_ratio (:473-483) over the cube the reference holds — symmetric-padded by ``neighborhood`` and
+    min-max normalised — computed from the unpadded, un-normalised cube resident on the device: a padded pixel is a
+    copy of scene pixel (rows[i], cols[j]), so the two masked means are weighted sums over the scene (weights = how
+    often the padding repeats a row / column), and (mean_lit - min) / (mean_shadow - min) is the ratio of the
+    normalised means (the per-band max cancels).  One [H*W] x [H*W, C] product in fp64 per mask."""
+    casi = data_set.casi
+    height, width, bands = casi.shape
+    padded_shadow_map = numpy.asarray(padded_shadow_map)
+    if padded_shadow_map.shape != (height + 2 * neighborhood, width + 2 * neighborhood):
+        raise ValueError(f"shadow map {padded_shadow_map.shape} does not match the padded scene "
+                         f"{(height + 2 * neighborhood, width + 2 * neighborhood)}")
+    in_shadow = torch.as_tensor(padded_shadow_map != 0, device=casi.device).to(torch.float64)
+    rows = torch.as_tensor(numpy.pad(numpy.arange(height), neighborhood, mode="symmetric"), device=casi.device)
+    cols = torch.as_tensor(numpy.pad(numpy.arange(width), neighborhood, mode="symmetric"), device=casi.device)
+    flat = (rows[:, None] * width + cols[None, :]).reshape(-1)
+    cube = casi.reshape(height * width, bands).to(torch.float64)
+    means = []
+    for mask in (1.0 - in_shadow, in_shadow):
+        weights = torch.zeros(height * width, dtype=torch.float64, device=casi.device).index_add_(0, flat, mask.reshape(-1))
+        means.append((weights @ cube) / weights.sum())
+    cmin = getattr(data_set, "_cmin", None)
+    offset = 0.0 if cmin is None else cmin.to(torch.float64)
+    return ((means[0] - offset) / (means[1] - offset)).to(torch.float32).cpu().numpy()
+
+
+def load_shadow_map_common(data_set, neighborhood, shadow_file_name):
+    """Reference :567-571.  ``shadow_file_name`` is a ``.npy`` file or an [H,W] array of 0 / 1 (GeoTIFF reading is not
+    part of this engine); the map is symmetric-padded by ``neighborhood`` like the scene the reference keeps."""
+    shadow_map = numpy.load(shadow_file_name) if isinstance(shadow_file_name, (str, bytes)) else numpy.asarray(shadow_file_name)
+    shadow_map = numpy.pad(shadow_map, neighborhood, mode="symmetric")
+    shadow_ratio = None if data_set is None else shadow_ratio_of_data_set(data_set, shadow_map, neighborhood)
+    return shadow_map, shadow_ratio
+
+
 # host-side sample-list / shadow-statistics helpers of the reference's module, implemented in sample_ops.py
 from hypelcnn_b200.common.sample_ops import (calculate_shadow_ratio, create_colored_image,  # noqa: E402,F401
                                              create_target_image_via_samples, read_targets_from_image,

@@ -1,0 +1,224 @@
+"""GAN training run (reference: gan/gan_train_for_shadow.py): pair the scene's normal / shadowed spectra, feed them
+batch by batch to the train ops of the chosen wrapper, validate the generators every ``validation_steps`` iterations.
+
+Same function names and argument meaning as the reference where a function exists there (``load_op``,
+``perform_shadow_augmentation_random``, ``get_log_suffix``, ``gan_train``, ``run_session``).  What differs is where the
+work happens: the paired matrices are gathered once into HBM (gan_sampling_methods), ``load_op`` returns an iterator
+whose batches are index selections of those resident matrices (the reference re-feeds them through a tf.data pipeline
+pinned to the CPU, :147-169), the regularisation-support augmentation is applied to the whole batch at once with one
+uniform draw per sample, and ``gan_train`` is a plain loop instead of a MonitoredTrainingSession.
+Hyper-parameter search (optuna, :215-231) and parameter-server flags are not part of this engine.
+"""
+import json
+import os
+from collections.abc import Sequence
+from types import SimpleNamespace
+
+import numpy
+import torch
+
+from hypelcnn_b200.common.common_ops import replace_abbrs
+from hypelcnn_b200.gan.wrapper_registry import get_infer_wrapper, get_sampling_map, get_wrapper_dict
+from hypelcnn_b200.gan.wrappers.gan_common import read_hsi_data
+
+
+def default_flags(**overrides):
+    """The reference's command-line defaults (gan/gan_train_for_shadow.py:28-77, common/cmd_parser.py:15-53) as the
+    flags object ``run_session`` / ``get_wrapper_dict`` read."""
+    flags = dict(gan_type="cycle_gan", use_identity_loss=True, identity_loss_weight=0.5,
+                 regularization_support_rate=0.0, cycle_consistency_loss_weight=10.0, nce_loss_weight=10.0, tau=0.07,
+                 patches=6, embedded_feat_size=2, validation_steps=1000, validation_sample_count=300,
+                 generator_lr=0.0002, discriminator_lr=0.0001, gen_discriminator_lr=0.0001,
+                 discriminator_reg_scale=0.00001, gen_disc_reg_scale=0.0001, pairing_method="random",
+                 batch_size=20, step=50000, epoch=None, base_log_path=os.getcwd(), output_path=os.getcwd(),
+                 path="/data/2013_DFTC/2013_DFTC", loader_name="GRSS2013DataLoader", neighborhood=0, test_ratio=0.05,
+                 train_ratio=0.10)
+    unknown = set(overrides) - set(flags)
+    if unknown:
+        raise KeyError(f"unknown flags: {sorted(unknown)}")
+    flags.update(overrides)
+    return SimpleNamespace(**flags)
+
+
+def perform_shadow_augmentation_random(normal_images, shadow_images, shadow_ratio, reg_support_rate, generator=None):
+    """Reference :172-184, for a batch ``[B,1,1,C]`` (or ``[B,C]``): per sample, with probability governed by
+    ``u < reg_support_rate``, u ~ U(0.01, 0.99), the normal spectrum is replaced by ``shadow * shadow_ratio``, and —
+    with a second, independent draw — the shadowed spectrum by ``normal_rand / shadow_ratio`` (the already
+    replaced normal spectrum, as in the reference).  Rates <= 0.01 never fire: the inputs are returned as they are."""
+    if reg_support_rate <= 0.01:
+        return normal_images, shadow_images
+    batch = normal_images.shape[0]
+    ratio = torch.as_tensor(shadow_ratio, dtype=normal_images.dtype, device=normal_images.device)
+    draws = torch.empty(2, batch, device=normal_images.device).uniform_(0.01, 0.99, generator=generator)
+    pick = (draws < reg_support_rate).reshape(2, batch, *([1] * (normal_images.dim() - 1)))
+    normal_images_rand = torch.where(pick[0], shadow_images * ratio, normal_images)
+    shadow_images_rand = torch.where(pick[1], normal_images_rand / ratio, shadow_images)
+    return normal_images_rand, shadow_images_rand
+
+
+class PairIterator:
+    """What the reference's ``load_op`` builds as tf.data (:147-169): ``shuffle_and_repeat(count=epoch)`` over the
+    paired rows, the random augmentation, ``batch(batch_size, drop_remainder=True)``.  As there, batching happens after
+    the repeat, so a batch may straddle two passes and the stream ends after ``epoch * N // batch_size`` batches
+    (``StopIteration`` = tf's OutOfRangeError, which ends the training loop).  Each pass is a full permutation drawn on
+    the device (tf shuffles within a 10 000-element window; for the reference's pair counts that is the whole set).
+    The matrices stay where they are (HBM); a batch is one index_select per side."""
+
+    def __init__(self, normal_data, shadow_data, batch_size, epoch, shadow_ratio, reg_support_rate, seed=1234):
+        self.normal_data = torch.as_tensor(normal_data)
+        self.shadow_data = torch.as_tensor(shadow_data).to(self.normal_data.device)
+        if self.normal_data.shape[0] != self.shadow_data.shape[0]:
+            raise ValueError("normal and shadow matrices must pair row by row")
+        self.batch_size, self.epoch = int(batch_size), int(epoch)
+        self.shadow_ratio, self.reg_support_rate = shadow_ratio, reg_support_rate
+        self._generator = torch.Generator(device=self.normal_data.device)
+        self._generator.manual_seed(seed)
+        self._pending = torch.empty(0, dtype=torch.int64, device=self.normal_data.device)
+        self._passes_started = 0
+        self.batches_served = 0
+
+    @property
+    def initializer(self):
+        return None     # nothing to feed: the data is resident (the reference's InitializerHook feeds placeholders)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        return self.get_next()
+
+    def get_next(self):
+        rows = self.normal_data.shape[0]
+        while self._pending.numel() < self.batch_size:
+            if self._passes_started >= self.epoch or rows == 0:
+                raise StopIteration
+            self._passes_started += 1
+            order = torch.randperm(rows, generator=self._generator, device=self.normal_data.device)
+            self._pending = torch.cat([self._pending, order])
+        take, self._pending = self._pending[:self.batch_size], self._pending[self.batch_size:]
+        self.batches_served += 1
+        return perform_shadow_augmentation_random(self.normal_data.index_select(0, take),
+                                                  self.shadow_data.index_select(0, take),
+                                                  self.shadow_ratio, self.reg_support_rate, self._generator)
+
+
+def load_op(batch_size, iteration_count, loader, data_set, shadow_map, shadow_ratio, reg_support_rate, pairing_method,
+            device=None):
+    """Reference :147-169.  Pairs via the registry's sampler, HSI bands only; ``epoch = iteration_count * batch_size
+    // pairs`` passes over them."""
+    normal_data_as_matrix, shadow_data_as_matrix = read_hsi_data(loader, data_set, shadow_map, pairing_method,
+                                                                 get_sampling_map())
+    normal = torch.as_tensor(normal_data_as_matrix)
+    if device is None:
+        device = normal.device if normal.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    normal = normal.to(device).contiguous()
+    shadow = torch.as_tensor(shadow_data_as_matrix).to(device).contiguous()
+    epoch = (iteration_count * batch_size) // normal.shape[0]
+    return PairIterator(normal, shadow, batch_size, epoch, shadow_ratio, reg_support_rate)
+
+
+def get_log_suffix(flags):
+    """Reference :187-200 (including its formatting of the boolean ``use_identity_loss`` as ``1.00`` -> ``idnty100``)."""
+    abbreviations = {"dataloader": "ldr"}
+    patch_size = (flags.neighborhood * 2) + 1
+    suffix = f"{flags.loader_name.lower():s}_{flags.gan_type.lower():s}_" \
+             f"{patch_size:d}x{patch_size:d}_" \
+             f"regsup{flags.regularization_support_rate:.2f}_" \
+             f"batch{flags.batch_size:d}".replace(".", "")
+    if flags.use_identity_loss is True:
+        suffix = suffix + f"_idnty{flags.use_identity_loss:.2f}".replace(".", "")
+    return replace_abbrs(suffix, abbreviations)
+
+
+class RunContext:
+    """What hooks see after every iteration: the global step just completed and the last losses."""
+
+    def __init__(self):
+        self.global_step, self.results = 0, None
+
+
+def gan_train(train_ops, input_iterator, logdir, get_hooks_fn, hooks=None, num_steps=None, save_checkpoint_steps=None,
+              saver=None):
+    """Reference :80-144.  One iteration = ``global_step_inc_op`` + the wrapper's sequential train ops on the next
+    batch (gan/wrappers: generator step, discriminator step[, feature-discriminator step]), then every hook's
+    ``after_run``.  Stops after ``num_steps`` iterations (StopAtStepHook) or when the input is exhausted.
+    ``saver(global_step)`` is called every ``save_checkpoint_steps`` iterations.  Returns the last global step."""
+    step_ops = get_hooks_fn(train_ops)
+    hooks = [h for h in (hooks or []) if h is not None]
+    for hook in hooks:
+        hook.after_create_session(None, None)
+    context, gstep, done = RunContext(), None, 0
+    while num_steps is None or done < num_steps:
+        try:
+            images_x, images_y = input_iterator.get_next()
+        except StopIteration:
+            break
+        gstep = train_ops.global_step_inc_op()
+        context.results = [op(images_x, images_y) for op in step_ops]
+        context.global_step = gstep
+        done += 1
+        for hook in hooks:
+            hook.after_run(context, None)
+        if saver is not None and save_checkpoint_steps and gstep % save_checkpoint_steps == 0:
+            saver(gstep)
+    return gstep
+
+
+def _generator_exports(inference_wrapper):
+    gens = {}
+    for scope, attr in (("ModelX2Y", "forward_generator"), ("ModelY2X", "backward_generator"), ("Model", "generator")):
+        variables = getattr(inference_wrapper, attr, None)
+        if variables is not None:
+            gens.update({f"{scope}/Generator/{name}": value for name, value in variables.export().items()})
+    return gens
+
+
+def run_session(params, base_log_path, loader=None):
+    """Reference :234-305.  ``params``: the flags as a dict (``vars(default_flags(...))``).  The loader is resolved
+    by name like the reference does unless one is handed in.  Returns ``[best upper divergence, best mean
+    divergence]`` (the maximum over the two validation directions where the wrapper validates both)."""
+    from hypelcnn_b200.common.common_nn_ops import get_loader_from_name
+    flags = SimpleNamespace(**params)
+    print("Args:", json.dumps(vars(flags), indent=3, default=str))
+    log_dir = f"{base_log_path}_{get_log_suffix(flags)}"
+    os.makedirs(log_dir, exist_ok=True)
+
+    validation_iteration_count = flags.validation_steps
+    validation_sample_count = flags.validation_sample_count
+    neighborhood = 0
+
+    if loader is None:
+        loader = get_loader_from_name(flags.loader_name, flags.path)
+    data_set = loader.load_data(neighborhood, True)
+    shadow_map, shadow_ratio = loader.load_shadow_map(neighborhood, data_set)
+
+    input_iterator = load_op(flags.batch_size, flags.step, loader, data_set, shadow_map, shadow_ratio,
+                             flags.regularization_support_rate, flags.pairing_method)
+    wrapper = get_wrapper_dict(flags)[flags.gan_type]
+    the_gan_model = wrapper.define_model(input_iterator.normal_data[:flags.batch_size],
+                                         input_iterator.shadow_data[:flags.batch_size])
+    the_gan_loss = wrapper.define_loss(the_gan_model)
+    inference_wrapper = get_infer_wrapper(flags.gan_type, trainer=wrapper.trainer)
+    peer_validation_hook = inference_wrapper.create_inference_hook(
+        data_set, loader, log_dir, neighborhood, shadow_map, shadow_ratio,
+        validation_iteration_count, validation_sample_count)
+    train_ops = wrapper.define_train_ops(the_gan_model, the_gan_loss, max_number_of_steps=flags.step,
+                                         generator_lr=flags.generator_lr, discriminator_lr=flags.discriminator_lr,
+                                         gen_discriminator_lr=flags.gen_discriminator_lr)
+
+    from hypelcnn_b200.classify.summaries import ClassificationSummaryWriter
+    writer = ClassificationSummaryWriter(log_dir)
+    writer.add_text("flags", json.dumps(vars(flags), indent=3, default=str), 0)      # TextSummaryAtStartHook
+    writer.close()
+
+    def saver(global_step):
+        numpy.savez(os.path.join(log_dir, f"model.ckpt-{global_step}.npz"), global_step=global_step,
+                    **_generator_exports(inference_wrapper))
+
+    gan_train(train_ops, input_iterator, log_dir, get_hooks_fn=wrapper.get_train_hooks_fn(),
+              hooks=[peer_validation_hook], num_steps=flags.step, save_checkpoint_steps=validation_iteration_count,
+              saver=saver)
+    best_upper_div = peer_validation_hook.get_best_upper_div()
+    best_mean_div = peer_validation_hook.get_best_mean_div()
+    return [max(best_upper_div) if isinstance(best_upper_div, Sequence) else best_upper_div,
+            max(best_mean_div) if isinstance(best_mean_div, Sequence) else best_mean_div]

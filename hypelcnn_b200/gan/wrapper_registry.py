@@ -18,14 +18,26 @@ def get_sampling_map():
             "dummy": DummySampler(element_count=2000, fill_value=0.5, coefficient=2)}
 
 
+_INFER_WRAPPERS = {"cycle_gan": (CycleGANInferenceWrapper, {}),
+                   "gan_x2y": (GANInferenceWrapper, {"fetch_shadows": False}),
+                   "gan_y2x": (GANInferenceWrapper, {"fetch_shadows": True}),
+                   "cut_x2y": (CUTInferenceWrapper, {"fetch_shadows": False}),
+                   "cut_y2x": (CUTInferenceWrapper, {"fetch_shadows": True}),
+                   "dcl_gan": (DCLGANInferenceWrapper, {}),
+                   "dcl_cycle_gan": (DCLCycleGANInferenceWrapper, {})}
+
+
+def get_infer_wrapper(gan_type, bands=None, trainer=None):
+    """One inference wrapper: over fresh (zero) generator variables of ``bands`` bands to be restored from a
+    checkpoint, or bound to a live ``trainer``'s generators — what sharing the "Generator" variable scope between the
+    train and the validation graph does in the reference (gan/gan_train_for_shadow.py:268-275)."""
+    cls, kwargs = _INFER_WRAPPERS[gan_type]
+    return cls(trainer=trainer, bands=bands, **kwargs)
+
+
 def get_infer_wrapper_dict(bands=64):
-    return {"cycle_gan": CycleGANInferenceWrapper(bands=bands),
-            "gan_x2y": GANInferenceWrapper(fetch_shadows=False, bands=bands),
-            "gan_y2x": GANInferenceWrapper(fetch_shadows=True, bands=bands),
-            "cut_x2y": CUTInferenceWrapper(fetch_shadows=False, bands=bands),
-            "cut_y2x": CUTInferenceWrapper(fetch_shadows=True, bands=bands),
-            "dcl_gan": DCLGANInferenceWrapper(bands=bands),
-            "dcl_cycle_gan": DCLCycleGANInferenceWrapper(bands=bands)}
+    """Reference: gan/wrapper_registry.py:21-32."""
+    return {gan_type: get_infer_wrapper(gan_type, bands=bands) for gan_type in _INFER_WRAPPERS}
 
 
 def get_wrapper_dict(flags):

@@ -24,7 +24,7 @@ import torch
 from hypelcnn_b200 import _native as N
 from hypelcnn_b200 import engine as E
 from hypelcnn_b200.gan.shadow_data_models import GeneratorVariables
-from hypelcnn_b200.gan.wrappers.gan_common import create_inference_for_matrix_input
+from hypelcnn_b200.gan.wrappers.gan_common import create_base_validation_hook, create_inference_for_matrix_input
 from hypelcnn_b200.gan.wrappers.wrapper import InferenceWrapper, Wrapper
 
 model_forward_generator_name = "ModelX2Y"
@@ -345,4 +345,10 @@ class CycleGANInferenceWrapper(InferenceWrapper):
 
     def create_inference_hook(self, data_set, loader, log_dir, neighborhood, shadow_map, shadow_ratio,
                               validation_iteration_count, validation_sample_count):
-        return None  # validation plots / best-ratio bookkeeping are reporting, out of scope
+        """cycle_gan_wrapper.py:149-166: peer validation of both generators (no clipping of invalid values)."""
+        return create_base_validation_hook(
+            data_set=data_set, loader=loader, log_dir=log_dir, neighborhood=neighborhood, shadow_map=shadow_map,
+            shadow_ratio=shadow_ratio, validation_iteration_count=validation_iteration_count,
+            validation_sample_count=validation_sample_count,
+            model_forward=lambda x: self.construct_inference_graph(x, True, False),
+            model_backward=lambda x: self.construct_inference_graph(x, False, False))

@@ -1,4 +1,11 @@
-"""Inference helpers of gan/wrappers/gan_common.py on the device."""
+"""gan/wrappers/gan_common.py of the reference on the device: the per-pixel generator inference over a matrix, and the
+validation side of GAN training (best-ratio bookkeeping, band-ratio statistics, validation hooks, sample loading)."""
+import json
+import os
+import random
+from json import JSONDecodeError
+
+import numpy
 import torch
 
 from hypelcnn_b200.gan.shadow_data_models import _generator_rows
@@ -25,3 +32,302 @@ def create_inference_for_matrix_input(input_tensor, is_shadow_graph, clip_invali
     out = torch.empty_like(rows)
     _generator_rows(rows, out, C, copy_extra, generator_variables, clip_invalid_values, is_shadow_graph)
     return out.reshape(x.shape)
+
+
+# --------------------------------------------------------------------------------------------------------------- #
+# Validation during GAN training (reference: gan/wrappers/gan_common.py:32-219, 307-429).  The reference evaluates a
+# second TF sub-graph through session.run inside SessionRunHooks; here a hook holds the validation spectra in HBM,
+# calls the inference callable (one generator launch) and reduces the band ratios with a handful of tensor ops.
+# --------------------------------------------------------------------------------------------------------------- #
+input_x_tensor_name = "x"
+input_y_tensor_name = "y"
+
+
+class BestRatioHolder:
+    """Reference :47-104: the ``max_size`` lowest divergences seen so far as (iteration, divergence), ascending.  A new
+    point goes after every held point it is strictly greater than *counted over the whole list* (the reference's loop
+    does not stop at the first larger element; on a sorted list that is the sorted position, ties go in front)."""
+
+    def __init__(self, max_size) -> None:
+        super().__init__()
+        self.data_holder = []
+        self.max_size = max_size
+
+    def add_point(self, iteration, diver_val):
+        iteration, diver_val = int(iteration), float(diver_val)     # JSON-serialisable
+        insert_idx = sum(1 for (_, curr_diver) in self.data_holder if diver_val > curr_diver)
+        self.data_holder.insert(insert_idx, (iteration, diver_val))
+        if len(self.data_holder) > self.max_size:
+            self.data_holder.pop()
+
+    def get_best_diver(self):
+        return self.data_holder[0][1] if self.data_holder else None
+
+    def get_point_with_itr(self, iteration):
+        for (curr_iter, curr_diver) in self.data_holder:
+            if curr_iter == iteration:
+                return curr_iter, curr_diver
+        return None, None
+
+    def load(self, file_address):
+        try:
+            with open(file_address, "rb") as read_file:
+                self.data_holder = json.load(read_file)
+            print(f"Best ratio file {file_address} is loaded.", self.data_holder)
+        except IOError:
+            print(f"File {file_address} file not found. No best ratio is loaded.")
+        except JSONDecodeError:
+            print(f"File {file_address} file can not be decoded. No best ratio is loaded.")
+
+    def save(self, file_address):
+        with open(file_address, "w") as write_file:
+            write_file.write(json.dumps(self.data_holder))
+
+    @staticmethod
+    def create_common_iterations(ratio_holder_1, ratio_holder_2):
+        result = BestRatioHolder(ratio_holder_1.max_size)
+        for (curr_iter, _) in ratio_holder_1.data_holder:
+            (found_itr, found_kl) = ratio_holder_2.get_point_with_itr(curr_iter)
+            if found_itr is not None:
+                result.add_point(found_itr, found_kl)
+        return result
+
+    def __str__(self) -> str:
+        return str(self.data_holder)
+
+
+def _iteration_of(run_context):
+    """Hooks are called as ``after_run(run_context, run_values)`` like tf SessionRunHooks; the training loop of
+    gan_train_for_shadow.gan_train passes an object with ``global_step`` (an int is accepted too)."""
+    return int(getattr(run_context, "global_step", run_context))
+
+
+class BaseValidationHook:
+    """Reference :107-138."""
+
+    def __init__(self, iteration_freq, log_dir, shadow_ratio):
+        self._iteration_frequency = iteration_freq
+        self._shadow_ratio = shadow_ratio
+        self._log_dir = log_dir
+        self.best_mean_div_holder = BestRatioHolder(10)
+        self.best_upper_div_holder = BestRatioHolder(10)
+        self.validation_itr_mark = False
+
+    def after_create_session(self, session=None, coord=None):
+        pass
+
+    def _is_validation_itr(self, current_iteration):
+        """Every iteration when the frequency is 0; otherwise at 1 + k * frequency, k >= 1 (never at iteration 1)."""
+        result = True
+        if self._iteration_frequency != 0:
+            result = current_iteration % self._iteration_frequency == 1 and current_iteration != 1
+        return result
+
+    def get_best_mean_div(self):
+        return self.best_mean_div_holder.get_best_diver()
+
+    def get_best_upper_div(self):
+        return self.best_upper_div_holder.get_best_diver()
+
+
+class PeerValidationHook:
+    """Reference :141-166: the shadowed and the de-shadowed validation side by side; after a validation iteration it
+    prints the iterations that are among the best of both."""
+
+    def __init__(self, *validation_base_hooks):
+        self._validation_base_hooks = validation_base_hooks
+
+    def after_create_session(self, session=None, coord=None):
+        for validation_base_hook in self._validation_base_hooks:
+            validation_base_hook.after_create_session(session, coord)
+
+    def after_run(self, run_context, run_values=None):
+        ratio_holder_list = []
+        for validation_base_hook in self._validation_base_hooks:
+            validation_base_hook.after_run(run_context, run_values)
+            ratio_holder_list.append(validation_base_hook.best_mean_div_holder)
+        if self._validation_base_hooks[0].validation_itr_mark:
+            print("Best common options:",
+                  BestRatioHolder.create_common_iterations(ratio_holder_list[0], ratio_holder_list[1]))
+
+    def get_best_mean_div(self):
+        return [val_base_hook.get_best_mean_div() for val_base_hook in self._validation_base_hooks
+                if val_base_hook.get_best_mean_div() is not None]
+
+    def get_best_upper_div(self):
+        return [val_base_hook.get_best_upper_div() for val_base_hook in self._validation_base_hooks
+                if val_base_hook.get_best_upper_div() is not None]
+
+
+def _kl_divergence(p, q):
+    return torch.sum(torch.where(p != 0., p * torch.log(p / q), torch.zeros_like(p)))
+
+
+def _js_divergence(p, q):
+    m = 0.5 * (p + q)
+    return 0.5 * _kl_divergence(p, m) + 0.5 * _kl_divergence(q, m)
+
+
+def create_stats_tensor(generate_y_tensor, images_x_input_tensor, shadow_ratio):
+    """Reference :314-330, evaluated eagerly on whatever device the spectra live on (fp32 like the TF graph).
+    generated / input * shadow_ratio per band -> samples with a non-finite ratio dropped -> band-wise mean and
+    population std -> |JS(|mean - 1|, 0)| and the same for mean + std.
+    Returns (div_mean, div_upper, ratio [kept, bands], mean [bands], std [bands])."""
+    generated = torch.as_tensor(generate_y_tensor, dtype=torch.float32)
+    inputs = torch.as_tensor(images_x_input_tensor, dtype=torch.float32).to(generated.device)
+    ratio = torch.as_tensor(numpy.asarray(shadow_ratio, dtype=numpy.float32) if not isinstance(shadow_ratio, torch.Tensor)
+                            else shadow_ratio, dtype=torch.float32).to(generated.device)
+    ratio_tensor = (generated / inputs * ratio).squeeze(2).squeeze(1)
+    finite_map = torch.isfinite(ratio_tensor).all(dim=1)
+    ratio_inf_eliminated = ratio_tensor[finite_map]
+    mean = ratio_inf_eliminated.mean(dim=0)
+    std = ratio_inf_eliminated.std(dim=0, unbiased=False)
+    div_mean = torch.abs(_js_divergence(torch.abs(mean - 1), torch.zeros_like(mean)))
+    div_upper = torch.abs(_js_divergence(torch.abs(mean + std - 1), torch.zeros_like(mean)))
+    return div_mean, div_upper, ratio_inf_eliminated, mean, std
+
+
+def calculate_stats_from_samples(infer_model, data_sample_list, shadow_ratio, log_dir, current_iteration, plt_name,
+                                 bands):
+    """Reference :333-361 (the offline variant used by gan_infer_for_shadow): same statistics, returns the mean
+    divergence.  ``infer_model`` is the callable of InferenceWrapper.make_inference_graph; the reference's
+    (sess, input placeholder, output tensor) triple collapses into it."""
+    samples = torch.as_tensor(data_sample_list, dtype=torch.float32)
+    generated = infer_model(samples)
+    div_mean, _, final_ratio, mean, std = create_stats_tensor(generated, samples.to(generated.device), shadow_ratio)
+    final_ratio, mean, std = final_ratio.cpu().numpy(), mean.cpu().numpy(), std.cpu().numpy()
+    print_overall_info(mean, std)
+    plot_overall_info(bands, numpy.percentile(final_ratio, 50, axis=0), numpy.percentile(final_ratio, 10, axis=0),
+                      numpy.percentile(final_ratio, 90, axis=0), current_iteration, plt_name, log_dir)
+    return float(div_mean)
+
+
+def load_samples_for_testing(data_set, sample_count, neighborhood, shadow_map, fetch_shadows):
+    """Reference :364-385: ``sample_count`` random shadowed (or shadow-free) pixels, HSI bands only.  The draws use
+    Python's ``random.randint`` in the reference's order, so ``random.seed`` reproduces the reference's picks; the
+    patches come from one batched gather when the data set offers it.  Note the reference crops the map by
+    ``neighborhood`` but uses the cropped indices as scene coordinates unchanged — kept."""
+    band_size = data_set.get_casi_band_count()
+    if neighborhood > 0:
+        shadow_map = shadow_map[neighborhood:-neighborhood, neighborhood:-neighborhood]
+    indices = numpy.where(shadow_map > 0) if fetch_shadows else numpy.where(shadow_map == 0)
+    picks = [random.randint(0, indices[0].size - 1) for _ in range(sample_count)]
+    targets = numpy.stack([indices[1][picks], indices[0][picks]], axis=1).astype(numpy.int32).reshape(-1, 2)
+    batched = getattr(data_set, "get_data_points", None)
+    if batched is not None:
+        points = batched(targets)
+        return [points[i, :, :, 0:band_size] for i in range(sample_count)]
+    return [data_set.get_data_point(int(x), int(y))[:, :, 0:band_size] for x, y in targets]
+
+
+def read_hsi_data(loader, data_set, shadow_map, pairing_method, sampling_method_map):
+    """Reference :388-395: run the chosen sampler and keep the HSI bands (drops the LiDAR channel)."""
+    if pairing_method not in sampling_method_map:
+        raise ValueError(f"Wrong sampling parameter value ({pairing_method}).")
+    normal_data_as_matrix, shadow_data_as_matrix = \
+        sampling_method_map[pairing_method].get_sample_pairs(data_set, loader, shadow_map)
+    normal_data_as_matrix = normal_data_as_matrix[:, :, :, 0:data_set.get_casi_band_count()]
+    shadow_data_as_matrix = shadow_data_as_matrix[:, :, :, 0:data_set.get_casi_band_count()]
+    return normal_data_as_matrix, shadow_data_as_matrix
+
+
+def plot_overall_info(bands, mean, lower_bound, upper_bound, iteration, plt_name, log_dir):
+    """Reference :398-419 draws the band-ratio curve with its 10-90 % envelope into ``{plt_name}_{iteration}.pdf``.
+    The curve data always goes to ``{plt_name}_{iteration}.csv`` (band, median, p10, p90); the PDF is drawn as well when
+    matplotlib is importable (it is not part of this image)."""
+    table = numpy.stack([numpy.asarray(bands, dtype=numpy.float64), mean, lower_bound, upper_bound], axis=1)
+    numpy.savetxt(os.path.join(log_dir, f"{plt_name}_{iteration}.csv"), table, delimiter=",",
+                  header="band,ratio_p50,ratio_p10,ratio_p90", comments="")
+    try:
+        from matplotlib import pyplot as plt
+    except ImportError:
+        return
+    plt.rcParams['font.size'] = 14
+    plt.scatter(bands, mean, label="mean ratio", s=10)
+    plt.plot(bands, mean)
+    plt.fill_between(bands, lower_bound, upper_bound, alpha=0.2)
+    plt.xlabel("Spectral band(nm)")
+    plt.ylabel("Ratio between generated and original samples")
+    plt.ylim([-1, 4])
+    plt.yticks(list(range(-1, 5)))
+    plt.grid()
+    plt.savefig(os.path.join(log_dir, f"{plt_name}_{iteration}.pdf"), dpi=300, bbox_inches='tight')
+    plt.clf()
+
+
+def print_overall_info(mean, std):
+    """Reference :422-429: ``mean±std`` per band, a line break after every band whose index is 1 mod 5."""
+    print("Mean&std Generated vs Original Ratio: ")
+    band_size = mean.shape[0]
+    for band_index in range(0, band_size):
+        prefix = "[ " if band_index == 0 else ""
+        postfix = " ]" if band_index == band_size - 1 and band_index != 0 else ""
+        print(f"{prefix}{mean[band_index]:2.4f}±{std[band_index]:2.2f}{postfix}",
+              end="\n" if band_index % 5 == 1 else " ")
+
+
+class ValidationHook(BaseValidationHook):
+    """Reference :169-219.  ``infer_model`` is a callable [N,1,1,bands] -> [N,1,1,bands] (the inference wrapper's
+    generator over a matrix); ``input_tensor`` — a placeholder in the reference — is accepted and unused.  The
+    validation spectra are picked once (load_samples_for_testing) and kept on the device of the data set."""
+
+    def __init__(self, iteration_freq, sample_count, log_dir, loader, data_set, neighborhood, shadow_map, shadow_ratio,
+                 input_tensor, infer_model, name_suffix, fetch_shadows):
+        super().__init__(iteration_freq, log_dir, shadow_ratio)
+        self._writer = None
+        self._infer_model = infer_model
+        self._name_suffix = name_suffix
+        self._plt_name = f"band_ratio_{name_suffix}"
+        self._best_mean_div_addr = os.path.join(self._log_dir, f"best_ratio_{name_suffix}.json")
+        self.best_mean_div_holder.load(self._best_mean_div_addr)
+        self._bands = loader.get_band_measurements()
+        samples = load_samples_for_testing(data_set, sample_count, neighborhood, shadow_map, fetch_shadows=fetch_shadows)
+        if samples and isinstance(samples[0], torch.Tensor):
+            self._data_sample_list = torch.stack(samples).contiguous()
+        else:
+            self._data_sample_list = torch.as_tensor(numpy.asarray(samples, dtype=numpy.float32))
+
+    def after_create_session(self, session=None, coord=None):
+        from hypelcnn_b200.classify.summaries import ClassificationSummaryWriter
+        self._writer = ClassificationSummaryWriter(self._log_dir)
+
+    def after_run(self, run_context, run_values=None):
+        current_iter = _iteration_of(run_context)
+        self.validation_itr_mark = self._is_validation_itr(current_iter)
+        if self.validation_itr_mark:
+            generated = self._infer_model(self._data_sample_list)
+            div_mean, div_upper, ratio, mean, std = create_stats_tensor(
+                generated, self._data_sample_list.to(generated.device), self._shadow_ratio)
+            div_mean, div_upper = float(div_mean), float(div_upper)
+            self.best_mean_div_holder.add_point(current_iter, div_mean)
+            self.best_mean_div_holder.save(self._best_mean_div_addr)
+            self.best_upper_div_holder.add_point(current_iter, div_upper)
+            if self._writer is not None:
+                self._writer.add_scalar(f"divergence_{self._name_suffix}", div_mean, current_iter)
+            self.print_stats(current_iter, div_mean, div_upper, mean.cpu().numpy(), ratio.cpu().numpy(),
+                             std.cpu().numpy())
+
+    def print_stats(self, current_iteration, div_mean, div_upper, mean, ratio, std):
+        print(f"Validation metrics for {self._name_suffix} #{current_iteration}")
+        print_overall_info(mean, std)
+        plot_overall_info(self._bands, numpy.percentile(ratio, 50, axis=0), numpy.percentile(ratio, 10, axis=0),
+                          numpy.percentile(ratio, 90, axis=0), current_iteration, self._plt_name, self._log_dir)
+        print(f"Divergence for {self._name_suffix}; mean:{div_mean}, upper:{div_upper}")
+        print(f"Best {self._name_suffix} options:{self.best_mean_div_holder}")
+
+
+def create_base_validation_hook(data_set, loader, log_dir, neighborhood, shadow_map, shadow_ratio,
+                                validation_iteration_count, validation_sample_count, model_forward, model_backward,
+                                x_input_tensor=None, y_input_tensor=None):
+    """Reference: gan/wrappers/cycle_gan_wrapper.py:22-45 — normal spectra through the forward generator judged
+    against shadow_ratio ("shadowed"), shadowed spectra through the backward generator against 1 / shadow_ratio
+    ("deshadowed"), as peers."""
+    shadowed = ValidationHook(iteration_freq=validation_iteration_count, sample_count=validation_sample_count,
+                              log_dir=log_dir, loader=loader, data_set=data_set, neighborhood=neighborhood,
+                              shadow_map=shadow_map, shadow_ratio=shadow_ratio, input_tensor=x_input_tensor,
+                              infer_model=model_forward, fetch_shadows=False, name_suffix="shadowed")
+    de_shadowed = ValidationHook(iteration_freq=validation_iteration_count, sample_count=validation_sample_count,
+                                 log_dir=log_dir, loader=loader, data_set=data_set, neighborhood=neighborhood,
+                                 shadow_map=shadow_map, shadow_ratio=1. / shadow_ratio, input_tensor=y_input_tensor,
+                                 infer_model=model_backward, fetch_shadows=True, name_suffix="deshadowed")
+    return PeerValidationHook(shadowed, de_shadowed)

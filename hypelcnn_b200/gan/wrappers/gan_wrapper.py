@@ -10,7 +10,8 @@ import torch
 from hypelcnn_b200 import _native as N
 from hypelcnn_b200 import engine as E
 from hypelcnn_b200.gan.wrappers.cycle_gan_wrapper import CycleGANTrainer, GANTrainOps, _p, _st
-from hypelcnn_b200.gan.wrappers.gan_common import create_inference_for_matrix_input
+from hypelcnn_b200.gan.wrappers.gan_common import (ValidationHook, adj_shadow_ratio,
+                                                   create_inference_for_matrix_input)
 from hypelcnn_b200.gan.wrappers.wrapper import InferenceWrapper, Wrapper
 
 
@@ -115,4 +116,11 @@ class GANInferenceWrapper(InferenceWrapper):
 
     def create_inference_hook(self, data_set, loader, log_dir, neighborhood, shadow_map, shadow_ratio,
                               validation_iteration_count, validation_sample_count):
-        return None  # validation plots are reporting, out of scope
+        """gan_wrapper.py:94-106: one hook; a y2x wrapper validates on shadowed pixels against 1 / shadow_ratio."""
+        return ValidationHook(iteration_freq=validation_iteration_count, sample_count=validation_sample_count,
+                              log_dir=log_dir, loader=loader, data_set=data_set, neighborhood=neighborhood,
+                              shadow_map=shadow_map, shadow_ratio=adj_shadow_ratio(shadow_ratio, self._fetch_shadows),
+                              input_tensor=None,
+                              infer_model=lambda x: self.construct_inference_graph(x, None, clip_invalid_values=False),
+                              fetch_shadows=self._fetch_shadows,
+                              name_suffix="deshadowed" if self._fetch_shadows else "shadowed")

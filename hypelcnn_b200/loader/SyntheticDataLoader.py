@@ -26,6 +26,7 @@ class SyntheticDataLoader(DataLoader):
     CASI_DTYPE = numpy.uint16
     HALF_RES_HSI = False
     SAMPLES = (2832, 12197)  # training / validation counts of GRSS2013 (dataset facts)
+    SHADOWED = False         # True: the pixels under the synthetic shadow map are darkened by SHADOW_RATIO per band
 
     def __init__(self, base_dir):
         self.base_dir = base_dir
@@ -42,6 +43,7 @@ class SyntheticDataLoader(DataLoader):
                 elif k == "samples":
                     self.samples = (int(v), int(v))
         self.rng = numpy.random.default_rng(1234)
+        self._shadow_map = None
 
     def load_data(self, neighborhood, normalize):
         hc, wc = (self.h // 2, self.w // 2) if self.HALF_RES_HSI else (self.h, self.w)
@@ -50,6 +52,9 @@ class SyntheticDataLoader(DataLoader):
         else:
             casi = self.rng.random((hc, wc, self.BANDS), dtype=numpy.float32)
         lidar = (self.rng.random((self.h, self.w, 1), dtype=numpy.float32) * 50).astype(numpy.float32)
+        if self.SHADOWED and not self.HALF_RES_HSI:
+            in_shadow = self.synthetic_shadow_map() == 1
+            casi[in_shadow] = (casi[in_shadow] / self.shadow_band_ratio()).astype(casi.dtype)
         cls = GRSS2018DataSet if self.HALF_RES_HSI else BasicDataSet
         return cls(shadow_creator_dict=None, casi=casi, lidar=lidar, neighborhood=neighborhood, normalize=normalize)
 
@@ -64,8 +69,37 @@ class SyntheticDataLoader(DataLoader):
         test, train = train[:n_test], train[n_test:]
         return SampleSet(training_targets=train, test_targets=test, validation_targets=validation)
 
+    def synthetic_shadow_map(self):
+        """[H,W] uint8 blobs (about a fifth of the scene) from a generator of its own, so asking for the shadow map
+        does not shift the scene / sample draws."""
+        if self._shadow_map is None:
+            rng = numpy.random.default_rng(4321)
+            shadow = numpy.zeros([self.h, self.w], numpy.uint8)
+            for _ in range(max(3, self.h * self.w // 250)):
+                r, c = rng.integers(0, self.h), rng.integers(0, self.w)
+                shadow[r:r + rng.integers(3, 14), c:c + rng.integers(3, 14)] = 1
+            self._shadow_map = shadow
+        return self._shadow_map
+
+    def shadow_band_ratio(self):
+        """lit / shadowed level per band used when SHADOWED (SURVEY S-C4: linspace(1.5, 4, bands))."""
+        return numpy.linspace(1.5, 4.0, self.BANDS).astype(numpy.float32)
+
     def load_shadow_map(self, neighborhood, data_set):
-        return None, None
+        """-> (shadow map padded by neighborhood, per-band lit / shadow ratio measured on the data set) like the
+        reference loaders (load_shadow_map_common, common/common_nn_ops.py:567-571); the map is synthetic."""
+        from hypelcnn_b200.common.common_nn_ops import load_shadow_map_common
+        if self.HALF_RES_HSI:
+            return numpy.pad(self.synthetic_shadow_map(), neighborhood, mode="symmetric"), None
+        return load_shadow_map_common(data_set, neighborhood, self.synthetic_shadow_map())
+
+    def read_targets(self, target_image_path):
+        """Labelled pixels of a target image as [N,3] = (x, y, class) (reference loaders: read_targets); synthetic:
+        drawn from a generator seeded by the name, independent of the scene draws."""
+        rng = numpy.random.default_rng(sum(target_image_path.encode()) + 99)
+        n = self.samples[0]
+        return numpy.stack([rng.integers(0, self.w, n), rng.integers(0, self.h, n),
+                            rng.integers(0, self.CLASSES, n)], axis=1).astype(numpy.int64)
 
     def get_class_count(self):
         return range(0, self.CLASSES)

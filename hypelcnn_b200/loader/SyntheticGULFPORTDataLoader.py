@@ -8,3 +8,4 @@ class SyntheticGULFPORTDataLoader(SyntheticDataLoader):
     H, W, BANDS, CLASSES = 325, 220, 64, 11
     CASI_DTYPE = numpy.float32
     SAMPLES = (2000, 2000)
+    SHADOWED = True      # the GAN configurations (BASELINE configs 4 / 5) need shadowed and lit spectra

@@ -211,6 +211,55 @@ def common_goldens(C):
     return arrays, meta
 
 
+def shadow_ratio_goldens():
+    """load_shadow_map_common (common/common_nn_ops.py:567-571) minus the tif read: the reference's BasicDataSet pads and
+    normalises the cube, the shadow map is padded the same way, calculate_shadow_ratio (:473-483) gives the ratio."""
+    from common.common_nn_ops import BasicDataSet, calculate_shadow_ratio
+    rng = numpy.random.default_rng(77)
+    arrays = {}
+    for name, (h, w, c, n) in {"r0": (12, 9, 5, 0), "r2": (14, 11, 6, 2)}.items():
+        casi = rng.integers(100, 16384, (h, w, c)).astype(numpy.float32)
+        smap = blob_map(rng, h, w, 4, numpy.uint8)
+        casi[smap == 1] /= rng.uniform(1.5, 4.0, c).astype(numpy.float32)
+        ds = BasicDataSet(None, casi.copy(), None, n, True)
+        padded = numpy.pad(smap, n, mode="symmetric")
+        ratio = calculate_shadow_ratio(ds.casi, padded, numpy.logical_not(padded).astype(int))
+        arrays[f"sr_{name}_casi"], arrays[f"sr_{name}_map"], arrays[f"sr_{name}_ratio"] = casi, smap, ratio
+        arrays[f"sr_{name}_n"] = numpy.array(n)
+    return arrays
+
+
+def train_app_goldens():
+    """gan/gan_train_for_shadow.py cannot be imported even against the stubs (tfgan namedtuples are subclassed at import
+    time), so the two pure functions needed — add_parse_cmds_for_app (:28-77) and get_log_suffix (:187-200) — are
+    compiled from the reference file's own AST and executed here; the other flag groups come from common/cmd_parser.py,
+    which imports as it is."""
+    import argparse
+    import ast
+    from types import SimpleNamespace
+    from common import cmd_parser
+    from common.common_ops import replace_abbrs
+    path = os.path.join(G.REF, "gan", "gan_train_for_shadow.py")
+    tree = ast.parse(open(path).read())
+    picked = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("add_parse_cmds_for_app", "get_log_suffix")]
+    space = {"type_ensure_strtobool": cmd_parser.type_ensure_strtobool, "replace_abbrs": replace_abbrs}
+    exec(compile(ast.Module(body=picked, type_ignores=[]), path, "exec"), space)
+    parser = argparse.ArgumentParser()
+    cmd_parser.add_parse_cmds_for_loaders(parser)
+    cmd_parser.add_parse_cmds_for_loggers(parser)
+    cmd_parser.add_parse_cmds_for_trainers(parser)
+    space["add_parse_cmds_for_app"](parser)
+    flags, _ = parser.parse_known_args([])
+    defaults = {k: v for k, v in vars(flags).items() if k not in ("base_log_path", "output_path")}
+    suffixes = []
+    for over in [{}, {"use_identity_loss": False}, {"loader_name": "GULFPORTALTDataLoader", "gan_type": "DCL_GAN",
+                                                    "neighborhood": 2, "regularization_support_rate": 0.25,
+                                                    "batch_size": 128}]:
+        f = SimpleNamespace(**{**vars(flags), **over})
+        suffixes.append({"overrides": over, "suffix": space["get_log_suffix"](f)})
+    return {"train_flag_defaults": defaults, "log_suffixes": suffixes}
+
+
 def main():
     G.install_stubs()
     for sub in ["tensorflow.python.ops.math_ops", "tensorflow.python.summary", "tensorflow.python.summary.summary",
@@ -221,10 +270,12 @@ def main():
     import gan.wrappers.gan_common as C
     C.plt.rcParams = {}  # the plotting stub only has to accept the font settings
     a1, m1 = sampler_goldens(S)
+    a3 = shadow_ratio_goldens()
+    m3 = train_app_goldens()
     a2, m2 = common_goldens(C)
-    numpy.savez_compressed(os.path.join(HERE, "gan_host_golden.npz"), **a1, **a2)
+    numpy.savez_compressed(os.path.join(HERE, "gan_host_golden.npz"), **a1, **a2, **a3)
     with open(os.path.join(HERE, "gan_host_golden.json"), "w") as f:
-        json.dump({**m1, **m2}, f, indent=1)
+        json.dump({**m1, **m2, **m3}, f, indent=1)
     print("wrote", len(a1) + len(a2), "arrays")
 
 

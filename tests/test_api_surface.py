@@ -17,7 +17,6 @@ NOT_MIRRORED = {
     "get_data_point_func": "hyp_gather_patches", "get_data_point_func_hsi": "hyp_gather_patches",
     # channel-resampling index arithmetic: lives in the layer plan (hyp_engine.cu), pinned by tests/golden/scale_in_to_out.json
     "scale_in_to_out": "hyp_engine.cu residual tables",
-    "load_shadow_map_common": "needs tifffile (GeoTIFF I/O is out of scope); calculate_shadow_ratio is mirrored",
     "objective": "optuna hyper-parameter search (out of scope)", "set_all_gpu_config": "TensorFlow memory-growth switch",
 }
 NOT_MIRRORED_CLASSES = {"TextSummaryAtStartHook": "hypelcnn_b200.classify.summaries.ClassificationSummaryWriter.add_text"}
