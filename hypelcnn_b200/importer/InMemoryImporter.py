@@ -67,6 +67,7 @@ class InMemoryImporter(DataImporter):
     def init_tensors(self, session, tensor, nn_params):
         """Reference :80-83: (re)initialise the iterator with nn_params.data_with_labels."""
         it = nn_params.input_iterator
+        it = getattr(it, "inner", it)       # an AugmentingIterator wraps the batch iterator that holds the data
         d = nn_params.data_with_labels
         if d is not None:
             it.images = d.data

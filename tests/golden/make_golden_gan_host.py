@@ -257,7 +257,50 @@ def train_app_goldens():
                                                     "batch_size": 128}]:
         f = SimpleNamespace(**{**vars(flags), **over})
         suffixes.append({"overrides": over, "suffix": space["get_log_suffix"](f)})
-    return {"train_flag_defaults": defaults, "log_suffixes": suffixes}
+    out = {"train_flag_defaults": defaults, "log_suffixes": suffixes}
+
+    # classify/train_for_classification.py: add_parse_cmds_for_app (:123-157), get_log_suffix (:160-180) the same way
+    from common.common_ops import path_leaf
+    path = os.path.join(G.REF, "classify", "train_for_classification.py")
+    tree = ast.parse(open(path).read())
+    picked = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("add_parse_cmds_for_app", "get_log_suffix")]
+    space = {"type_ensure_strtobool": cmd_parser.type_ensure_strtobool, "replace_abbrs": replace_abbrs,
+             "path_leaf": path_leaf, "os": os}
+    exec(compile(ast.Module(body=picked, type_ignores=[]), path, "exec"), space)
+    parser = argparse.ArgumentParser()
+    for add in (cmd_parser.add_parse_cmds_for_loaders, cmd_parser.add_parse_cmds_for_loggers,
+                cmd_parser.add_parse_cmds_for_trainers, cmd_parser.add_parse_cmds_for_models,
+                cmd_parser.add_parse_cmds_for_importers, space["add_parse_cmds_for_app"]):
+        add(parser)
+    flags, _ = parser.parse_known_args([])
+    out["classify_flag_defaults"] = {k: v for k, v in vars(flags).items() if k not in ("base_log_path", "output_path")}
+    suffixes = []
+    for over in [{"algorithm_param_path": "/some/dir/alg_param_hypelcnn.json"},
+                 {"algorithm_param_path": "alg_param_dualcnn.json", "model_name": "DUALCNNModel", "neighborhood": 3,
+                  "train_ratio": 200.0, "augment_data_with_shadow": "cycle_gan", "augmentation_random_threshold": 0.25},
+                 {"algorithm_param_path": "C:\\x\\alg_param_concnn.json", "model_name": "CONCNNModel",
+                  "loader_name": "GULFPORTALTDataLoader", "neighborhood": 1, "train_ratio": 0.5,
+                  "augment_data_with_spectral": 0.0125, "augment_data_with_shadow": "simple"}]:
+        f = SimpleNamespace(**{**vars(flags), **over})
+        suffixes.append({"overrides": over, "suffix": space["get_log_suffix"](f)})
+    out["classify_log_suffixes"] = suffixes
+
+    # classify/infer_for_classification.py: create_all_scene_data (:24-35), create_sample_data (:38-47)
+    from collections import namedtuple
+    info = namedtuple("GeneratorDataInfo", ["data", "targets", "loader", "dataset"])
+    path = os.path.join(G.REF, "classify", "infer_for_classification.py")
+    tree = ast.parse(open(path).read())
+    picked = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("create_all_scene_data", "create_sample_data")]
+    space = {"numpy": numpy, "GeneratorDataInfo": info}
+    exec(compile(ast.Module(body=picked, type_ignores=[]), path, "exec"), space)
+    scene = space["create_all_scene_data"]([3, 5], info(None, None, "the loader", "the data set"))
+    parts = [info(None, numpy.array(t, dtype=numpy.int64), f"loader{i}", f"set{i}")
+             for i, t in enumerate([[[1, 2, 3]], [[4, 5, 6], [7, 8, 9]], [[10, 11, 12]]])]
+    sample = space["create_sample_data"](*parts)
+    out["infer_targets"] = {"all_3x5": scene.targets.tolist(), "all_loader": scene.loader, "all_dataset": scene.dataset,
+                            "sample": sample.targets.tolist(), "sample_dtype": str(sample.targets.dtype),
+                            "sample_loader": sample.loader, "sample_dataset": sample.dataset}
+    return out
 
 
 def main():

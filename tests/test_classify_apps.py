@@ -1,0 +1,167 @@
+"""Host logic of the classification apps (hypelcnn_b200/classify/{monitored_session_runner,train_for_classification,
+infer_for_classification}.py) on the CPU: flag defaults, log suffixes and inference target lists against values
+produced by executing the reference's own functions (tests/golden/make_golden_gan_host.py); the monitored loop's stop
+rule, hook cadence, NaN stop, summaries and checkpoint rotation with a recording train step."""
+import json
+import os
+from types import SimpleNamespace
+
+import numpy
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+META = json.load(open(os.path.join(HERE, "golden", "gan_host_golden.json")))
+
+
+def test_flag_defaults_and_log_suffix_equal_the_reference():
+    from hypelcnn_b200.classify.train_for_classification import default_flags, get_log_suffix
+    ours = vars(default_flags())
+    assert {k: ours[k] for k in META["classify_flag_defaults"]} == META["classify_flag_defaults"]
+    for case in META["classify_log_suffixes"]:
+        assert get_log_suffix(default_flags(**case["overrides"])) == case["suffix"]
+    with pytest.raises(KeyError):
+        default_flags(nope=1)
+
+
+def test_inference_target_lists_equal_the_reference():
+    from hypelcnn_b200.classify.infer_for_classification import create_all_scene_data, create_sample_data
+    from hypelcnn_b200.importer.GeneratorImporter import GeneratorDataInfo
+    g = META["infer_targets"]
+    scene = create_all_scene_data([3, 5], GeneratorDataInfo(None, None, "the loader", "the data set"))
+    assert scene.targets.tolist() == g["all_3x5"] and scene.data is None
+    assert (scene.loader, scene.dataset) == (g["all_loader"], g["all_dataset"])
+    parts = [GeneratorDataInfo(None, numpy.array(t, dtype=numpy.int64), f"loader{i}", f"set{i}")
+             for i, t in enumerate([[[1, 2, 3]], [[4, 5, 6], [7, 8, 9]], [[10, 11, 12]]])]
+    sample = create_sample_data(*parts)
+    assert sample.targets.tolist() == g["sample"] and str(sample.targets.dtype) == g["sample_dtype"]
+    assert (sample.loader, sample.dataset) == (g["sample_loader"], g["sample_dataset"])
+    big = create_all_scene_data([349, 1905], parts[0]).targets                     # GRSS2013 scene: vectorised
+    assert big.shape == (664845, 3) and big[1905].tolist() == [0, 1, 0] and big[-1].tolist() == [1904, 348, 0]
+
+
+class _Engine:
+    def __init__(self):
+        self.saved, self.loaded, self.global_step = [], [], 0
+
+    def save_checkpoint(self, path):
+        open(path, "w").write(str(self.global_step))
+        self.saved.append(os.path.basename(path))
+
+    def load_checkpoint(self, path):
+        self.global_step = int(open(path).read())
+        self.loaded.append(os.path.basename(path))
+
+    def export_variables(self):
+        return {"nn_core/fc_final/weights": numpy.linspace(-1, 1, 11)}
+
+
+class _TrainStep:
+    def __init__(self, engine, nan_at=None, exhaust_at=None):
+        self.engine, self.nan_at, self.exhaust_at, self.last_loss = engine, nan_at, exhaust_at, None
+
+    @property
+    def global_step(self):
+        return self.engine.global_step
+
+    def run(self):
+        if self.exhaust_at is not None and self.engine.global_step >= self.exhaust_at:
+            raise StopIteration
+        self.engine.global_step += 1
+        value = float("nan") if self.engine.global_step == self.nan_at else 1.0 / self.engine.global_step
+        self.last_loss = torch.tensor([value, value, 0.0])
+        return self.last_loss
+
+
+class _Metrics:
+    def __init__(self):
+        self.confusion = numpy.eye(3, dtype=numpy.int32)
+        self.accuracy, self.mean_per_class_accuracy, self.kappa = 0.5, 0.4, 0.3
+
+
+class _Importer:
+    def __init__(self, log):
+        self.log = log
+
+    def init_tensors(self, session, tensor, nn_params):
+        self.log.append(("init", tensor))
+
+
+def _params(rows):
+    return SimpleNamespace(metrics=_Metrics(), data_with_labels=SimpleNamespace(data=torch.zeros(rows, 1)))
+
+
+def _run(tmp_path, monkeypatch, required_steps, engine=None, **step_args):
+    from hypelcnn_b200.classify import monitored_session_runner as M
+    log = []
+
+    def accuracy(sess, nn_params, class_range):
+        log.append(("accuracy", nn_params.name, engine.global_step))
+        return 0.75 if nn_params.name == "validation" else 0.5, None, None, 0.25, 0.6
+
+    monkeypatch.setattr(M, "calculate_accuracy", accuracy)
+    engine = engine or _Engine()
+    train_step = _TrainStep(engine, **step_args)
+    testing, validation, training = _params(4), _params(4), _params(4)
+    testing.name, validation.name, training.name = "testing", "validation", "training"
+    cross_entropy = lambda: train_step.last_loss                                       # noqa: E731
+    summaries = M.add_classification_summaries(cross_entropy, lambda: 3e-4, True, testing, validation)
+    result = M.run_monitored_session(cross_entropy, str(tmp_path), range(0, 3), 100, 150, train_step, required_steps,
+                                     None, training, "train-tensor", testing, "test-tensor", validation,
+                                     "validation-tensor", _Importer(log), '{"a": 1}', '{"b": 2}', summaries=summaries,
+                                     engine_of=lambda: engine)
+    return result, log, engine
+
+
+def test_monitored_loop_cadence_checkpoints_and_summaries(tmp_path, monkeypatch, capsys):
+    from tensorboard.backend.event_processing.event_file_loader import EventFileLoader
+    result, log, engine = _run(tmp_path, monkeypatch, required_steps=321)
+    assert engine.global_step == 320                                                   # StopAtStepHook(last_step=320)
+    assert log[0] == ("init", "train-tensor")
+    validation_at = [e[2] for e in log if e[:2] == ("accuracy", "validation")]
+    testing_at = [e[2] for e in log if e[:2] == ("accuracy", "testing")]
+    assert validation_at == [151, 301, 320]           # 1 + k * validation_steps, and required_steps - 1
+    assert testing_at == [1, 101, 201, 301, 320]      # 1 + k * 100, and once more at the end
+    assert engine.saved == ["model.ckpt-100.safetensors", "model.ckpt-200.safetensors", "model.ckpt-300.safetensors",
+                            "model.ckpt-320.safetensors"]
+    assert (result.validation_accuracy, result.test_accuracy) == (0.75, 0.5) and result.loss == pytest.approx(1 / 320)
+    out = capsys.readouterr().out
+    assert "Validation metrics #151 : Overall accuracy=0.75, Class based average accuracy=0.6, Kappa=0.25" in out
+    assert "Training step=320, Testing accuracy=0.5, loss=0.00313" in out
+    events = [e for f in sorted(os.listdir(tmp_path)) if "tfevents" in f
+              for e in EventFileLoader(str(tmp_path / f)).Load() if e.HasField("summary")]
+    tags = {(e.step, v.tag) for e in events for v in e.summary.value}
+    assert (0, "flags") in tags and (0, "algorithm_params") in tags
+    for step in (100, 200, 300, 151, 301, 320):
+        assert (step, "training_cross_entropy") in tags and (step, "validation_kappa") in tags
+    assert (100, "nn_core/fc_final/weights") in tags                                   # log_all_model_variables
+
+    # a second run in the same directory resumes from the newest checkpoint and only does the missing steps
+    result, log, engine2 = _run(tmp_path, monkeypatch, required_steps=331)
+    assert engine2.loaded == ["model.ckpt-320.safetensors"] and engine2.global_step == 330
+    assert engine2.saved == ["model.ckpt-330.safetensors"]
+
+
+def test_monitored_loop_stops_on_nan_and_on_exhausted_input(tmp_path, monkeypatch, capsys):
+    result, log, engine = _run(tmp_path / "nan", monkeypatch, required_steps=1000, nan_at=7)
+    assert engine.global_step == 7 and "Model diverged with loss = NaN." in capsys.readouterr().out
+    assert engine.saved == ["model.ckpt-7.safetensors"] and numpy.isnan(result.loss)
+    result, log, engine = _run(tmp_path / "short", monkeypatch, required_steps=1000, exhaust_at=12)
+    assert engine.global_step == 12 and engine.saved == ["model.ckpt-12.safetensors"]
+
+
+def test_checkpoint_rotation_keeps_twenty(tmp_path):
+    from hypelcnn_b200.classify.monitored_session_runner import CheckpointSaver
+    engine = _Engine()
+    saver = CheckpointSaver(str(tmp_path), lambda: engine, 10)
+    for step in range(1, 301):
+        engine.global_step = step
+        saver.after_run(step)
+    kept = [s for s, _ in saver.existing()]
+    assert kept == list(range(110, 301, 10)) and len(kept) == 20
+    assert saver.restore_latest() == 300 and engine.loaded == ["model.ckpt-300.safetensors"]
+    from hypelcnn_b200.classify.infer_for_classification import latest_checkpoint
+    assert latest_checkpoint(str(tmp_path)).endswith("model.ckpt-300.safetensors")
+    assert latest_checkpoint("/some/file.safetensors") == "/some/file.safetensors"
+    with pytest.raises(IOError):
+        latest_checkpoint(str(tmp_path / ".."  / "empty" if (tmp_path / ".." / "empty").mkdir() is None else ""))
