@@ -56,16 +56,40 @@ class GeneratorInferenceWrapper:
             self.backward_generator.load(backward_values)
 
 
+def read_generator_checkpoint(path):
+    """A generator checkpoint written by gan_train_for_shadow.run_session (``model.ckpt-<step>.npz``, variables named
+    ``ModelX2Y/Generator/net1/weights`` ... like the reference's TF checkpoints) -> (forward values, backward values)
+    keyed below the Generator scope.  A single-generator checkpoint (``Model/Generator/...``) fills the forward slot."""
+    import os
+    if not os.path.exists(path) and os.path.exists(path + ".npz"):
+        path = path + ".npz"
+    if not os.path.exists(path):
+        raise IOError(f"generator checkpoint {path} not found")
+    stored = numpy.load(path)
+    scopes = {"ModelX2Y/Generator/": {}, "ModelY2X/Generator/": {}, "Model/Generator/": {}}
+    for name in stored.files:
+        for scope, values in scopes.items():
+            if name.startswith(scope):
+                values[name[len(scope):]] = stored[name]
+    forward = scopes["ModelX2Y/Generator/"] or scopes["Model/Generator/"]
+    return (forward or None), (scopes["ModelY2X/Generator/"] or None)
+
+
 def create_gan_struct(gan_inference_wrapper, model_base_dir=None, ckpt_relative_path=None):
     """Reference: gan/gan_utilities.py:30-43.  The LiDAR channel is stripped, every pixel of the patch goes through
-    the (frozen) generator, the LiDAR channel is appended again — done inside one kernel launch."""
+    the (frozen) generator, the LiDAR channel is appended again — done inside one kernel launch.
+    ``shadow_op_initializer(restorer, session)`` restores the generators from ``model_base_dir + ckpt_relative_path``
+    like the reference; without a path, ``session`` may carry the (forward, backward) value dicts directly."""
 
     def _build_shadowed_inference_graph(input_data, is_shadow_graph):
         return gan_inference_wrapper.construct_inference_graph(input_data, is_shadow_graph=is_shadow_graph,
                                                                clip_invalid_values=False, copy_extra=1)
 
-    def _initializer(restorer, values):
-        restorer.restore(*values)
+    def _initializer(restorer, session):
+        if model_base_dir is not None and ckpt_relative_path is not None:
+            restorer.restore(*read_generator_checkpoint(model_base_dir + ckpt_relative_path))
+        elif session is not None:
+            restorer.restore(*session)
 
     return ShadowOpHolder(shadow_op=lambda x: _build_shadowed_inference_graph(x, True),
                           deshadow_op=lambda x: _build_shadowed_inference_graph(x, False),

@@ -278,3 +278,47 @@ def test_run_session_glue_with_stand_in_wrappers(tmp_path, monkeypatch, capsys):
     assert len(result) == 2 and all(numpy.isfinite(result)) and result[1] < 0.5    # mean divergence small: ratio learnt
     assert "Best common options:" in capsys.readouterr().out
     assert any("tfevents" in f for f in files) and "band_ratio_deshadowed_21.csv" in files
+
+
+def test_gan_struct_restores_generators_from_a_run_session_checkpoint(tmp_path):
+    """create_gan_struct's shadow_op_initializer (gan/gan_utilities.py:36-37): model_base_dir + ckpt_relative_path names
+    a checkpoint of the training run; variables are split by generator scope and handed to the restorer."""
+    from hypelcnn_b200.gan.gan_utilities import create_gan_struct, read_generator_checkpoint
+
+    class Wrapper:
+        restored = None
+
+        def construct_inference_graph(self, input_tensor, is_shadow_graph, clip_invalid_values, copy_extra=0):
+            return ("shadow" if is_shadow_graph else "deshadow", copy_extra, clip_invalid_values)
+
+        def create_generator_restorer(self):
+            return self
+
+        def restore(self, forward_values=None, backward_values=None):
+            self.restored = (forward_values, backward_values)
+
+    os.makedirs(tmp_path / "shadow_gen_model" / "dcl_gan")
+    numpy.savez(tmp_path / "shadow_gen_model" / "dcl_gan" / "model.ckpt-3000.npz", global_step=3000,
+                **{"ModelX2Y/Generator/net1/weights": numpy.full((4, 1, 1), 1.0), "ModelX2Y/Generator/net1/biases": numpy.zeros(1),
+                   "ModelY2X/Generator/net1/weights": numpy.full((4, 1, 1), 2.0)})
+    wrapper = Wrapper()
+    struct = create_gan_struct(wrapper, str(tmp_path) + os.sep, "shadow_gen_model/dcl_gan/model.ckpt-3000")
+    assert struct.shadow_op("x") == ("shadow", 1, False) and struct.deshadow_op("x") == ("deshadow", 1, False)
+    restorer = struct.shadow_op_creater()
+    struct.shadow_op_initializer(restorer, None)                    # what InitHook.after_create_session calls
+    forward, backward = wrapper.restored
+    assert sorted(forward) == ["net1/biases", "net1/weights"] and float(forward["net1/weights"].mean()) == 1.0
+    assert list(backward) == ["net1/weights"] and float(backward["net1/weights"].mean()) == 2.0
+    numpy.savez(tmp_path / "single.npz", **{"Model/Generator/net7/weights": numpy.ones((2, 1, 1))})
+    forward, backward = read_generator_checkpoint(str(tmp_path / "single"))
+    assert list(forward) == ["net7/weights"] and backward is None
+    with pytest.raises(IOError):
+        create_gan_struct(wrapper, str(tmp_path) + os.sep, "nope/model.ckpt-1").shadow_op_initializer(wrapper, None)
+    # without a path the values may be handed over directly (an in-process trainer), or nothing happens
+    create_gan_struct(wrapper).shadow_op_initializer(wrapper, ({"a": 1}, None))
+    assert wrapper.restored == ({"a": 1}, None)
+    create_gan_struct(wrapper).shadow_op_initializer(wrapper, None)
+    from hypelcnn_b200.loader.SyntheticGULFPORTALTDataLoader import SyntheticGULFPORTALTDataLoader
+    loader = SyntheticGULFPORTALTDataLoader(f"synthetic:H=8,W=9,models={tmp_path}")
+    assert loader.get_model_base_dir() == str(tmp_path) + os.sep and (loader.h, loader.w) == (8, 9)
+    assert sorted(loader.GAN_CHECKPOINTS) == ["cycle_gan", "dcl_cycle_gan", "dcl_gan"]
