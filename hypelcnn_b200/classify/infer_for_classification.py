@@ -6,7 +6,8 @@ The per-pixel Python generator of the reference (GeneratorImporter -> tf.data.fr
 launch per batch followed by the model's eval forward, argmax and a scatter into the class image, all on the device
 (common_nn_ops.perform_prediction).  The weights come from a checkpoint written by the training loop
 (``model.ckpt-<step>.safetensors``); like the reference's Saver the ``image_gen_net_*`` decoder is not restored.
-The class images are returned (and written as ``.npy``; GeoTIFF output needs tifffile, which this image lacks).
+The class images are returned and written as ``result_raw.tif`` / ``result_colorized.tif`` like the reference's
+(utilities/tiff_io.py; no GeoTIFF georeferencing tags — the reference writes none either).
 """
 import json
 import os
@@ -19,6 +20,7 @@ from hypelcnn_b200.common.common_nn_ops import (ModelInputParams, NNParams, crea
                                                 create_target_image_via_samples, get_loader_from_name,
                                                 get_model_from_name, perform_prediction, simple_nn_iterator)
 from hypelcnn_b200.importer.GeneratorImporter import GeneratorDataInfo, GeneratorImporter
+from hypelcnn_b200.utilities.tiff_io import imwrite
 
 
 def create_all_scene_data(scene_shape, data_with_labels_to_copy):
@@ -111,7 +113,7 @@ def run(flags, model=None):
         raise ValueError(f"Domain flags does not support value:{flags.domain}")
     colored = create_colored_image(scene_as_image, color_list)
     if flags.output_path is not None:
-        numpy.save(os.path.join(flags.output_path, "result_raw.npy"), scene_as_image)
-        numpy.save(os.path.join(flags.output_path, "result_colorized.npy"), colored)
+        imwrite(os.path.join(flags.output_path, "result_raw.tif"), scene_as_image)
+        imwrite(os.path.join(flags.output_path, "result_colorized.tif"), colored)
     print(f"Done evaluation({time.time() - start_time:.3f} sec)")
     return scene_as_image, colored

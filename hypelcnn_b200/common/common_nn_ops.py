@@ -77,11 +77,15 @@ class BasicDataSet(DataSet):
                     lmax = torch.tensor([lidar_max], dtype=torch.float32, device=self.device)
                 self._lmm = torch.cat([lmin, lmax]).contiguous()
                 self.lidar_min, self.lidar_max = float(lmin.item()), float(lmax.item())
-            cmin, cmax = E.scene_minmax(self.casi)
-            if casi_min is not None:
-                cmin = torch.as_tensor(numpy.asarray(casi_min), dtype=torch.float32).to(self.device)
+            cmin, cmax = E.scene_minmax(self.casi)          # per-band min and max of the SHIFTED data (:73-77)
+            bands = self.casi.shape[2]
+            if casi_min is not None:                        # given offsets (scalar or per band), e.g. AVON's 0
+                given = torch.as_tensor(numpy.asarray(casi_min), dtype=torch.float32).to(self.device).expand(bands)
+                if casi_max is None:                        # the divisor is the maximum of the data shifted by THEM
+                    cmax = (cmin + cmax) - given
+                cmin = given
             if casi_max is not None:
-                cmax = torch.as_tensor(numpy.asarray(casi_max), dtype=torch.float32).to(self.device)
+                cmax = torch.as_tensor(numpy.asarray(casi_max), dtype=torch.float32).to(self.device).expand(bands)
             self._cmin, self._cmax = cmin.contiguous(), cmax.contiguous()
             self.casi_min, self.casi_max = cmin.cpu().numpy(), cmax.cpu().numpy()
 
@@ -515,9 +519,16 @@ def shadow_ratio_of_data_set(data_set, padded_shadow_map, neighborhood):
 
 
 def load_shadow_map_common(data_set, neighborhood, shadow_file_name):
-    """Reference :567-571.  ``shadow_file_name`` is a ``.npy`` file or an [H,W] array of 0 / 1 (GeoTIFF reading is not
-    part of this engine); the map is symmetric-padded by ``neighborhood`` like the scene the reference keeps."""
-    shadow_map = numpy.load(shadow_file_name) if isinstance(shadow_file_name, (str, bytes)) else numpy.asarray(shadow_file_name)
+    """Reference :567-571.  ``shadow_file_name`` is a TIFF (or ``.npy``) file, or the [H,W] array of 0 / 1 itself; the
+    map is symmetric-padded by ``neighborhood`` like the scene the reference keeps."""
+    if isinstance(shadow_file_name, str):
+        if shadow_file_name.endswith(".npy"):
+            shadow_map = numpy.load(shadow_file_name)
+        else:
+            from hypelcnn_b200.utilities.tiff_io import imread
+            shadow_map = imread(shadow_file_name)
+    else:
+        shadow_map = numpy.asarray(shadow_file_name)
     shadow_map = numpy.pad(shadow_map, neighborhood, mode="symmetric")
     shadow_ratio = None if data_set is None else shadow_ratio_of_data_set(data_set, shadow_map, neighborhood)
     return shadow_map, shadow_ratio

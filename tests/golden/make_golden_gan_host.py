@@ -303,6 +303,83 @@ def train_app_goldens():
     return out
 
 
+def loader_goldens():
+    """The reference's scene loaders run over small synthetic scene directories (written with this repo's TIFF
+    writer, read back through ``tifffile.imread`` := this repo's reader): constant tables, read_targets, the union and
+    sizes of load_samples' splits (the stratified shuffles themselves are unseeded in the reference)."""
+    import importlib.machinery
+    import tempfile
+    from collections import namedtuple
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from hypelcnn_b200.utilities.tiff_io import imread, imwrite
+
+    class Finder:           # every tensorflow* / tf_slim* / tensorflow_gan* submodule resolves to a stub
+        def find_spec(self, name, path, target=None):
+            if name.split(".")[0] in ("tensorflow", "tensorflow_gan", "tf_slim", "tensorflow_probability", "imageio"):
+                return importlib.machinery.ModuleSpec(name, self)
+
+        def create_module(self, spec):
+            return sys.modules.get(spec.name) or G._Stub(spec.name)
+
+        def exec_module(self, module):
+            pass
+
+    sys.meta_path.append(Finder())
+    import tensorflow_gan as tfgan
+    tfgan.CycleGANModel = namedtuple("CycleGANModel", ["model_x2y", "model_y2x", "reconstructed_x", "reconstructed_y"])
+    rng = numpy.random.default_rng(2013)
+    base = tempfile.mkdtemp()
+    arrays, meta = {}, {}
+
+    def labels(h, w, classes, density=0.4, first=1):
+        image = rng.integers(first, first + classes, (h, w)).astype(numpy.uint8)
+        image[rng.random((h, w)) > density] = 0
+        return image
+
+    files = {"2013_DFTC/2013_IEEE_GRSS_DF_Contest_Samples_TR.tif": labels(20, 30, 15, first=0),
+             "2013_DFTC/2013_IEEE_GRSS_DF_Contest_Samples_VA.tif": labels(20, 30, 15, first=0),
+             "2018_DFTC/2018_IEEE_GRSS_DFC_GT_TR.tif": labels(24, 40, 20),
+             "GULFPORT/muulf_gt.tif": labels(25, 22, 11),
+             "GULFPORT/muulf_gt_shadow_corrected.tif": labels(25, 22, 11),
+             "GULFPORT/muulf_shadow_map.tif": blob_map(rng, 25, 22, 6)}
+    for name, image in files.items():
+        os.makedirs(os.path.dirname(os.path.join(base, name)), exist_ok=True)
+        imwrite(os.path.join(base, name), image)
+        arrays["file_" + name.replace("/", "__")] = image
+    tables = {}
+    for name in ["GRSS2013DataLoader", "GRSS2018DataLoader", "GULFPORTDataLoader", "GULFPORTALTDataLoader", "AVONDataLoader"]:
+        module = __import__("loader." + name, fromlist=[name])
+        if hasattr(module, "imread"):
+            module.imread = imread
+        loader = getattr(module, name)(base)
+        bands = loader.get_band_measurements()
+        tables[name] = {"colors": loader.get_samples_color_list().tolist(),
+                        "classes": [loader.get_class_count().start, loader.get_class_count().stop],
+                        "bands": [float(bands[0]), float(bands[-1]), int(bands.shape[0])],
+                        "base_suffix": loader.get_model_base_dir()[len(base):]}
+        if name == "GRSS2013DataLoader":
+            arrays["targets_2013_tr"] = loader.read_targets("2013_IEEE_GRSS_DF_Contest_Samples_TR.tif")
+            s = loader.load_samples(0.1, 0.25)
+            tables[name]["split_sizes"] = [len(s.training_targets), len(s.test_targets), len(s.validation_targets)]
+            arrays["targets_2013_va"] = s.validation_targets
+        if name == "GRSS2018DataLoader":
+            s = loader.load_samples(0.5, 0.2)
+            tables[name]["split_sizes"] = [len(s.training_targets), len(s.test_targets), len(s.validation_targets)]
+            arrays["targets_2018_all"] = numpy.vstack([s.training_targets, s.test_targets, s.validation_targets])
+        if name == "GULFPORTDataLoader":
+            arrays["targets_gulfport"] = loader.read_targets("muulf_gt.tif")
+            s = loader.load_samples(3, 0.0)        # 3 samples per class, no test list
+            tables[name]["split_sizes"] = [len(s.training_targets), len(s.test_targets), len(s.validation_targets)]
+        if name == "GULFPORTALTDataLoader":
+            sys.modules["common.common_nn_ops"].imread = imread
+            s = loader.load_samples(0.5, 0.3)
+            tables[name]["split_sizes"] = [len(s.training_targets), len(s.test_targets), len(s.validation_targets)]
+            tables[name]["test_shape"] = list(s.test_targets.shape)
+            arrays["targets_alt_train_val"] = numpy.vstack([s.training_targets, s.validation_targets]).astype(int)
+    meta["loaders"] = tables
+    return arrays, meta
+
+
 def main():
     G.install_stubs()
     for sub in ["tensorflow.python.ops.math_ops", "tensorflow.python.summary", "tensorflow.python.summary.summary",
@@ -315,10 +392,11 @@ def main():
     a1, m1 = sampler_goldens(S)
     a3 = shadow_ratio_goldens()
     m3 = train_app_goldens()
+    a4, m4 = loader_goldens()
     a2, m2 = common_goldens(C)
-    numpy.savez_compressed(os.path.join(HERE, "gan_host_golden.npz"), **a1, **a2, **a3)
+    numpy.savez_compressed(os.path.join(HERE, "gan_host_golden.npz"), **a1, **a2, **a3, **a4)
     with open(os.path.join(HERE, "gan_host_golden.json"), "w") as f:
-        json.dump({**m1, **m2, **m3}, f, indent=1)
+        json.dump({**m1, **m2, **m3, **m4}, f, indent=1)
     print("wrote", len(a1) + len(a2), "arrays")
 
 

@@ -49,7 +49,7 @@ def test_train_then_infer_whole_scene(tmp_path, capsys):
     infer_flags.domain = "all"
     class_image, colored = I.run(infer_flags)
     assert class_image.shape == (20, 24) and class_image.dtype == numpy.uint8 and class_image.max() < 15
-    assert colored.shape == (20, 24, 3) and os.path.exists(tmp_path / "result_raw.npy")
+    assert colored.shape == (20, 24, 3) and os.path.exists(tmp_path / "result_raw.tif")
     data_set = SyntheticGRSS2013DataLoader(SPEC).load_data(3, True)         # the same seeded scene
     targets = numpy.array([[x, y] for y in range(20) for x in range(24)], dtype=numpy.int32)
     want = numpy.concatenate([
