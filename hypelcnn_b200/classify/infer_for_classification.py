@@ -117,3 +117,23 @@ def run(flags, model=None):
         imwrite(os.path.join(flags.output_path, "result_colorized.tif"), colored)
     print(f"Done evaluation({time.time() - start_time:.3f} sec)")
     return scene_as_image, colored
+
+
+def build_parser():
+    import argparse
+    from hypelcnn_b200.common import cmd_parser as C
+    parser = argparse.ArgumentParser()
+    for add in (C.add_parse_cmds_for_loaders, C.add_parse_cmds_for_loggers, C.add_parse_cmds_for_trainers,
+                C.add_parse_cmds_for_models, C.add_parse_cmds_for_importers):
+        add(parser)
+    C.add_flags(parser, (("domain", str, "all", "all (whole scene), sample (labelled samples) or gt (ground truth)"),))
+    return parser
+
+
+def main(argv=None):
+    flags, _ = build_parser().parse_known_args(argv)
+    return run(flags)
+
+
+if __name__ == "__main__":
+    main()

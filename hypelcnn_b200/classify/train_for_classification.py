@@ -2,6 +2,7 @@
 training loop -> TrainingResult.  ``perform_an_episode`` and ``get_log_suffix`` keep the reference's names and
 arguments; ``default_flags`` carries the reference's command-line defaults (hyper-parameter search via optuna is not
 part of this engine)."""
+import argparse
 import json
 import os
 import time
@@ -13,18 +14,41 @@ from hypelcnn_b200.classify.monitored_session_runner import (add_classification_
                                                              set_run_seed)
 from hypelcnn_b200.common.common_nn_ops import (AugmentationInfo, TrainingResult, create_graph, get_importer_from_name,
                                                 get_model_from_name)
+from hypelcnn_b200.common.cmd_parser import (add_flags, add_parse_cmds_for_importers, add_parse_cmds_for_loaders,
+                                             add_parse_cmds_for_loggers, add_parse_cmds_for_models,
+                                             add_parse_cmds_for_trainers, type_ensure_strtobool)
 from hypelcnn_b200.common.common_ops import path_leaf, replace_abbrs
 
 
+APP_FLAGS = (("perform_validation", type_ensure_strtobool, False, "Validate during / after training."),
+             ("augment_data_with_rotation", type_ensure_strtobool, False, "Augment with 90-degree rotations."),
+             ("augment_data_with_spectral", float, None, "Augment with a random spectral offset of this size."),
+             ("augment_data_with_shadow", str, None, "Shadow augmenter: cycle_gan, dcl_gan, dcl_cycle_gan or simple."),
+             ("augment_data_with_reflection", type_ensure_strtobool, False, "Augment with reflections."),
+             ("augmentation_random_threshold", float, 0.5, "Probability of the shadow augmentation per sample."),
+             ("device", str, "gpu", "gpu (this engine has no CPU path)"),
+             ("save_checkpoint_steps", int, 2000, "Checkpoint frequency"),
+             ("validation_steps", int, 40000, "Validation frequency"),
+             ("all_data_shuffle_ratio", float, None, "Unused (kept for the reference's command lines)."),
+             ("log_model_params", type_ensure_strtobool, False, "Log variable histograms to TensorBoard."))
+
+
+def add_parse_cmds_for_app(parser):
+    """Reference :123-157."""
+    add_flags(parser, APP_FLAGS)
+
+
+def build_parser():
+    parser = argparse.ArgumentParser()
+    for add in (add_parse_cmds_for_loaders, add_parse_cmds_for_loggers, add_parse_cmds_for_trainers,
+                add_parse_cmds_for_models, add_parse_cmds_for_importers, add_parse_cmds_for_app):
+        add(parser)
+    return parser
+
+
 def default_flags(**overrides):
-    """Reference defaults: common/cmd_parser.py:15-67 and classify/train_for_classification.py:123-157."""
-    flags = dict(path="/data/2013_DFTC/2013_DFTC", loader_name="GRSS2013DataLoader", neighborhood=0, test_ratio=0.05,
-                 train_ratio=0.10, base_log_path=os.getcwd(), output_path=os.getcwd(), batch_size=20, step=50000,
-                 epoch=None, algorithm_param_path=None, model_name="HYPELCNNModel", importer_name="InMemoryImporter",
-                 perform_validation=False, augment_data_with_rotation=False, augment_data_with_spectral=None,
-                 augment_data_with_shadow=None, augment_data_with_reflection=False, augmentation_random_threshold=0.5,
-                 device="gpu", save_checkpoint_steps=2000, validation_steps=40000, all_data_shuffle_ratio=None,
-                 log_model_params=False)
+    """The parser's defaults as a flags object (reference: common/cmd_parser.py:15-67 and :123-157 here)."""
+    flags = vars(build_parser().parse_known_args([])[0])
     unknown = set(overrides) - set(flags)
     if unknown:
         raise KeyError(f"unknown flags: {sorted(unknown)}")
@@ -121,3 +145,13 @@ def run(flags):
     algorithm_params["batch_size"] = flags.batch_size
     return perform_an_episode(flags, algorithm_params, nn_model,
                               os.path.join(flags.base_log_path, get_log_suffix(flags)))
+
+
+def main(argv=None):
+    flags, _ = build_parser().parse_known_args(argv)
+    print("Running on training mode")
+    return run(flags)
+
+
+if __name__ == "__main__":
+    main()

@@ -9,6 +9,7 @@ pinned to the CPU, :147-169), the regularisation-support augmentation is applied
 uniform draw per sample, and ``gan_train`` is a plain loop instead of a MonitoredTrainingSession.
 Hyper-parameter search (optuna, :215-231) and parameter-server flags are not part of this engine.
 """
+import argparse
 import json
 import os
 from collections.abc import Sequence
@@ -17,27 +18,62 @@ from types import SimpleNamespace
 import numpy
 import torch
 
+from hypelcnn_b200.common.cmd_parser import (add_flags, add_parse_cmds_for_json_loader, add_parse_cmds_for_loaders,
+                                             add_parse_cmds_for_loggers, add_parse_cmds_for_trainers,
+                                             type_ensure_strtobool)
 from hypelcnn_b200.common.common_ops import replace_abbrs
 from hypelcnn_b200.gan.wrapper_registry import get_infer_wrapper, get_sampling_map, get_wrapper_dict
 from hypelcnn_b200.gan.wrappers.gan_common import read_hsi_data
 
 
+APP_FLAGS = (("gan_type", str, "cycle_gan", "cycle_gan, gan_x2y, gan_y2x, cut_x2y, cut_y2x, dcl_gan, dcl_cycle_gan"),
+             ("use_identity_loss", type_ensure_strtobool, True, "Add the identity loss to the generator objective."),
+             ("identity_loss_weight", float, 0.5, "Weight of the identity loss."),
+             ("regularization_support_rate", float, 0.0, "Rate of ratio-made pairs mixed into the batches."),
+             ("cycle_consistency_loss_weight", float, 10.0, "Weight of the cycle-consistency loss."),
+             ("nce_loss_weight", float, 10.0, "Weight of the PatchNCE loss."),
+             ("tau", float, 0.07, "PatchNCE temperature."),
+             ("patches", int, 6, "Band slices of the feature discriminator."),
+             ("embedded_feat_size", int, 2, "Embedding size of the feature discriminator."),
+             ("validation_steps", int, 1000, "Validation / checkpoint frequency."),
+             ("validation_sample_count", int, 300, "Validation samples."),
+             ("generator_lr", float, 0.0002, "Generator learning rate."),
+             ("discriminator_lr", float, 0.0001, "Discriminator learning rate."),
+             ("gen_discriminator_lr", float, 0.0001, "Feature-discriminator learning rate."),
+             ("discriminator_reg_scale", float, 0.00001, "L2 scale of the discriminator."),
+             ("gen_disc_reg_scale", float, 0.0001, "L2 scale of the feature discriminator."),
+             ("pairing_method", str, "random", "target, random, neighbour or dummy."))
+
+
+def add_parse_cmds_for_app(parser):
+    """Reference :28-77 (without the parameter-server flags master / ps_tasks / task)."""
+    add_flags(parser, APP_FLAGS)
+
+
+def build_parser():
+    parser = argparse.ArgumentParser()
+    for add in (add_parse_cmds_for_loaders, add_parse_cmds_for_loggers, add_parse_cmds_for_trainers,
+                add_parse_cmds_for_json_loader, add_parse_cmds_for_app):
+        add(parser)
+    return parser
+
+
 def default_flags(**overrides):
-    """The reference's command-line defaults (gan/gan_train_for_shadow.py:28-77, common/cmd_parser.py:15-53) as the
-    flags object ``run_session`` / ``get_wrapper_dict`` read."""
-    flags = dict(gan_type="cycle_gan", use_identity_loss=True, identity_loss_weight=0.5,
-                 regularization_support_rate=0.0, cycle_consistency_loss_weight=10.0, nce_loss_weight=10.0, tau=0.07,
-                 patches=6, embedded_feat_size=2, validation_steps=1000, validation_sample_count=300,
-                 generator_lr=0.0002, discriminator_lr=0.0001, gen_discriminator_lr=0.0001,
-                 discriminator_reg_scale=0.00001, gen_disc_reg_scale=0.0001, pairing_method="random",
-                 batch_size=20, step=50000, epoch=None, base_log_path=os.getcwd(), output_path=os.getcwd(),
-                 path="/data/2013_DFTC/2013_DFTC", loader_name="GRSS2013DataLoader", neighborhood=0, test_ratio=0.05,
-                 train_ratio=0.10)
+    """The parser's defaults as the flags object ``run_session`` / ``get_wrapper_dict`` read."""
+    flags = vars(build_parser().parse_known_args([])[0])
     unknown = set(overrides) - set(flags)
     if unknown:
         raise KeyError(f"unknown flags: {sorted(unknown)}")
     flags.update(overrides)
     return SimpleNamespace(**flags)
+
+
+def update_flags_from_json(flags, flag_config_file):
+    """Reference :308-314: a JSON file overrides the command line."""
+    print("Updating flags from json file,", flag_config_file)
+    merged = dict(vars(flags))
+    merged.update(json.load(open(flag_config_file, "r")))
+    return SimpleNamespace(**merged)
 
 
 def perform_shadow_augmentation_random(normal_images, shadow_images, shadow_ratio, reg_support_rate, generator=None):
@@ -222,3 +258,15 @@ def run_session(params, base_log_path, loader=None):
     best_mean_div = peer_validation_hook.get_best_mean_div()
     return [max(best_upper_div) if isinstance(best_upper_div, Sequence) else best_upper_div,
             max(best_mean_div) if isinstance(best_mean_div, Sequence) else best_mean_div]
+
+
+def main(argv=None):
+    flags, _ = build_parser().parse_known_args(argv)
+    if flags.flag_config_file:
+        flags = update_flags_from_json(flags, flags.flag_config_file)
+    print("Running on training mode")
+    print("Output divergence values:", run_session(params=dict(vars(flags)), base_log_path=flags.base_log_path))
+
+
+if __name__ == "__main__":
+    main()

@@ -322,3 +322,105 @@ def test_gan_struct_restores_generators_from_a_run_session_checkpoint(tmp_path):
     loader = SyntheticGULFPORTALTDataLoader(f"synthetic:H=8,W=9,models={tmp_path}")
     assert loader.get_model_base_dir() == str(tmp_path) + os.sep and (loader.h, loader.w) == (8, 9)
     assert sorted(loader.GAN_CHECKPOINTS) == ["cycle_gan", "dcl_cycle_gan", "dcl_gan"]
+
+
+def test_command_lines_parse_like_the_reference():
+    """The flag tables of common/cmd_parser.py and the apps: defaults equal the reference's parsers (golden), values
+    parse with the reference's types, unknown arguments are tolerated (parse_known_args)."""
+    from hypelcnn_b200.classify import infer_for_classification as I
+    from hypelcnn_b200.classify import train_for_classification as T
+    from hypelcnn_b200.common.cmd_parser import type_ensure_strtobool
+    from hypelcnn_b200.gan import gan_train_for_shadow as G
+    gan_flags, extra = G.build_parser().parse_known_args(
+        ["--gan_type", "dcl_gan", "--use_identity_loss", "false", "--step", "300", "--tau", "0.1", "--unknown", "x"])
+    assert (gan_flags.gan_type, gan_flags.use_identity_loss, gan_flags.step, gan_flags.tau) == ("dcl_gan", False, 300, 0.1)
+    assert extra == ["--unknown", "x"] and gan_flags.pairing_method == "random"
+    flags, _ = T.build_parser().parse_known_args(["--perform_validation", "True", "--augment_data_with_spectral", "0.01",
+                                                  "--augment_data_with_shadow", "dcl_gan", "--neighborhood", "3"])
+    assert flags.perform_validation is True and flags.augment_data_with_spectral == 0.01
+    assert flags.augment_data_with_shadow == "dcl_gan" and flags.neighborhood == 3 and flags.epoch is None
+    assert I.build_parser().parse_known_args([])[0].domain == "all"
+    for text, value in [("y", True), ("YES", True), ("t", True), ("on", True), ("1", True), (True, True),
+                        ("n", False), ("No", False), ("f", False), ("off", False), ("0", False), (False, False)]:
+        assert type_ensure_strtobool(text) is value
+    with pytest.raises(ValueError):
+        type_ensure_strtobool("maybe")
+
+
+def test_update_flags_from_json(tmp_path):
+    from hypelcnn_b200.gan.gan_train_for_shadow import default_flags, update_flags_from_json
+    (tmp_path / "flags.json").write_text(json.dumps({"batch_size": 128, "gan_type": "cut_x2y"}))
+    flags = update_flags_from_json(default_flags(step=7), str(tmp_path / "flags.json"))
+    assert (flags.batch_size, flags.gan_type, flags.step) == (128, "cut_x2y", 7)
+
+
+def test_scene_conversion_with_a_stand_in_generator(tmp_path):
+    """gan_infer_image_for_shadow.convert_scene: which pixels go through the generator, chunking, de-normalisation
+    and dtype — against a direct numpy computation (the generator stand-in halves every band)."""
+    from hypelcnn_b200.gan.gan_infer_image_for_shadow import conversion_plan, convert_scene
+    assert conversion_plan("shadow") == (True, 0, "shadow") and conversion_plan("deshadow") == (False, 1, "deshadow")
+    assert conversion_plan("") == (True, -1, "none") and conversion_plan("anything") == (True, -1, "none")
+    rng = numpy.random.default_rng(4)
+    H, W, C = 9, 11, 5
+    raw = rng.integers(100, 4000, (H, W, C)).astype(numpy.uint16)
+    lidar = rng.random((H, W, 1)).astype(numpy.float32)
+    casi_min = raw.min(axis=(0, 1))
+    casi_max = (raw - casi_min).max(axis=(0, 1))
+    normalised = ((raw - casi_min) / casi_max.astype(numpy.float32)).astype(numpy.float32)
+    shadow_map = (rng.random((H, W)) < 0.3).astype(numpy.uint8)
+
+    class DataSet:
+        def __init__(self):
+            self.casi_min, self.casi_max, self.calls = casi_min, casi_max, 0
+
+        def get_scene_shape(self):
+            return [H, W]
+
+        def get_casi_band_count(self):
+            return C
+
+        def get_unnormalized_casi_dtype(self):
+            return numpy.dtype(numpy.uint16)
+
+        def get_data_points(self, targets):
+            self.calls += 1
+            t = numpy.asarray(targets)
+            patch = numpy.concatenate([normalised[t[:, 1], t[:, 0]], lidar[t[:, 1], t[:, 0]]], axis=1)
+            return torch.from_numpy(patch).reshape(-1, 1, 1, C + 1)
+
+    halve = lambda x: x * 0.5                                                            # noqa: E731
+    for sign, convert_all in [(0, False), (1, False), (-1, False), (-1, True)]:
+        data_set = DataSet()
+        got = convert_scene(data_set, shadow_map, halve, sign, convert_all, chunk=40)
+        selected = numpy.ones((H, W), bool) if convert_all else shadow_map == sign
+        want_norm = numpy.where(selected[:, :, None], normalised * numpy.float32(0.5), normalised)
+        want = (want_norm * casi_max.astype(numpy.float32) + casi_min.astype(numpy.float32)).astype(numpy.uint16)
+        assert got.dtype == numpy.uint16 and got.shape == (H, W, C) and numpy.array_equal(got, want)
+        assert data_set.calls == -(-H * W // 40)                                           # one gather per chunk
+    untouched = convert_scene(DataSet(), shadow_map, halve, -1, False)
+    assert numpy.abs(untouched.astype(int) - raw.astype(int)).max() <= 1                   # round trip of the normalisation
+
+
+def test_generators_restore_into_either_wrapper_kind(tmp_path):
+    from hypelcnn_b200.gan.gan_infer_for_shadow import restore_generators
+    numpy.savez(tmp_path / "model.ckpt-7.npz", **{"ModelX2Y/Generator/net1/weights": numpy.ones(3),
+                                                   "ModelY2X/Generator/net1/weights": numpy.zeros(3)})
+
+    class Pair:
+        backward_generator = object()
+
+        def create_generator_restorer(self):
+            return self
+
+        def restore(self, forward_values=None, backward_values=None):
+            self.got = (sorted(forward_values), sorted(backward_values))
+
+    class Single:
+        def create_generator_restorer(self):
+            return self
+
+        def restore(self, values):
+            self.got = sorted(values)
+
+    assert restore_generators(Pair(), str(tmp_path / "model.ckpt-7")).got == (["net1/weights"], ["net1/weights"])
+    assert restore_generators(Single(), str(tmp_path / "model.ckpt-7.npz")).got == ["net1/weights"]
