@@ -1304,8 +1304,13 @@ int hyp_gather_patches(const void* casi, int casi_dtype, int Hc, int Wc, int C_h
   a.nb = neighborhood; a.mode = mode; a.xy = targets_xy; a.N = N; a.out = out; a.out_ld = out_ld;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const double S2 = (double)(2 * neighborhood + 1) * (2 * neighborhood + 1);
-  PROF("gather_kernel", (double)N * S2 * (4.0 * out_ld + (casi_dtype == HYP_DT_U16 ? 2.0 : 4.0) * C_hsi + (lidar ? 4.0 : 0.0)),
-       (gather_kernel<<<(unsigned)N, 256, 0, st>>>(a)));
+  const char* v2 = getenv("HYP_GATHER_V2");   // opt-in until measured against v1 (scripts/bench_gather.py)
+  const double gather_bytes = (double)N * S2 * (4.0 * out_ld + (casi_dtype == HYP_DT_U16 ? 2.0 : 4.0) * C_hsi + (lidar ? 4.0 : 0.0));
+  if (v2 && v2[0] == '1') {
+    PROF("gather_kernel_v2", gather_bytes, (gather_kernel_v2<<<(unsigned)N, 256, 0, st>>>(a)));
+  } else {
+    PROF("gather_kernel", gather_bytes, (gather_kernel<<<(unsigned)N, 256, 0, st>>>(a)));
+  }
   return HYP_OK;
 }
 

@@ -1055,4 +1055,67 @@ __global__ void gather_kernel(const GatherArgs p) {
   }
 }
 
+// Same arithmetic as gather_kernel (bit-identical results), without the two integer divisions per element: the
+// (row, column, channel) position of a thread's element advances incrementally by the block's stride of 256 elements,
+// and four elements are in flight per thread.  Selected with HYP_GATHER_V2=1 until it has been measured against v1
+// on a B200 (scripts/bench_gather.py).
+__global__ void __launch_bounds__(256) gather_kernel_v2(const GatherArgs p) {
+  const int64_t n = blockIdx.x;
+  const int S = 2 * p.nb + 1;
+  const int x = p.xy[2 * n], y = p.xy[2 * n + 1];
+  int bx = x, by = y;
+  const bool half_res = p.mode == HYP_GATHER_GRSS2018;
+  if (half_res) {
+    bx = x / 2 + p.nb - p.nb / 2;
+    by = y / 2 + p.nb - p.nb / 2;
+  }
+  const int per_pixel = p.out_ld;
+  const int total = S * S * per_pixel;
+  float* op = p.out + (size_t)n * total;
+  const float lmin = p.lminmax ? p.lminmax[0] : 0.f, lmax = p.lminmax ? p.lminmax[1] : 1.f;
+  const int dpix = 256 / per_pixel, dc = 256 - dpix * per_pixel;   // 256 elements = dpix pixels + dc channels
+  int pix = threadIdx.x / per_pixel;
+  int c = threadIdx.x - pix * per_pixel;
+  int py = pix / S, px = pix - py * S;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < total; i += 256) {
+    float v = 0.f;
+    if (c < p.C) {
+      const int oy = half_res ? py / 2 : py;
+      const int ox = half_res ? px / 2 : px;
+      const int ry = reflect_sym(by + oy - p.nb, p.Hc), rx = reflect_sym(bx + ox - p.nb, p.Wc);
+      const size_t off = ((size_t)ry * p.Wc + rx) * p.C + c;
+      if (p.casi_u16) {
+        const unsigned short raw = __ldg(reinterpret_cast<const unsigned short*>(p.casi) + off);
+        if (p.cmin) {
+          const unsigned short sh = (unsigned short)(raw - (unsigned short)__ldg(p.cmin + c));
+          v = __fdiv_rn((float)sh, __ldg(p.cmax + c));
+        } else {
+          v = (float)raw;
+        }
+      } else {
+        const float raw = __ldg(reinterpret_cast<const float*>(p.casi) + off);
+        v = p.cmin ? __fdiv_rn(__fsub_rn(raw, __ldg(p.cmin + c)), __ldg(p.cmax + c)) : raw;
+      }
+    } else if (c == p.C && p.lidar) {
+      const int ry = reflect_sym(y + py - p.nb, p.Hl), rx = reflect_sym(x + px - p.nb, p.Wl);
+      const float raw = __ldg(p.lidar + (size_t)ry * p.Wl + rx);
+      v = p.lminmax ? __fdiv_rn(__fsub_rn(raw, lmin), lmax) : raw;
+    }
+    op[i] = v;
+    c += dc;
+    int advance = dpix;
+    if (c >= per_pixel) {
+      c -= per_pixel;
+      ++advance;
+    }
+    px += advance;
+    if (px >= S) {
+      const int rows = px / S;
+      py += rows;
+      px -= rows * S;
+    }
+  }
+}
+
 }  // namespace hyp
