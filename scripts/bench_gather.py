@@ -20,6 +20,7 @@ from hypelcnn_b200 import engine as E  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--grss2018", action="store_true")
 ap.add_argument("--reps", type=int, default=20)
+ap.add_argument("--only", choices=["v1", "v2"], default=None, help="run one kernel version only (for ncu captures)")
 ap.add_argument("--scene-batch", type=int, default=65536, help="targets per launch of the whole-scene sweep")
 args = ap.parse_args()
 
@@ -60,7 +61,7 @@ def timed(targets, out, reps):
 results = {}
 out = torch.empty((min(args.scene_batch, scene_targets.shape[0]), S, S, C + 1), dtype=torch.float32, device="cuda")
 reference_out = None
-for version in ("0", "1"):
+for version in {"v1": ("0",), "v2": ("1",), None: ("0", "1")}[args.only]:
     os.environ["HYP_GATHER_V2"] = version
     got = E.gather_patches(casi, lidar, nb, random_targets, cmin, cmax, lmm, mode).clone()
     if reference_out is None:
@@ -78,4 +79,4 @@ for version in ("0", "1"):
 os.environ["HYP_GATHER_V2"] = "0"
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
 print(json.dumps({"workload": "grss2018_gather" if args.grss2018 else "grss2013_gather", "bytes_per_patch": bytes_per_patch,
-                  "hbm_peak_GB_per_s": peaks.get("hbm_gbs"), "v2_bit_identical": True, "results": results}, indent=1))
+                  "hbm_peak_GB_per_s": peaks.get("hbm_gbs"), "v2_bit_identical": args.only is None, "results": results}, indent=1))

@@ -8,9 +8,9 @@ timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/pyt
 timeout 300 python scripts/bench_gather.py > gpurun_out/gather_2013.json 2> gpurun_out/gather_2013.err; tail -30 gpurun_out/gather_2013.json
 timeout 300 python scripts/bench_gather.py --grss2018 > gpurun_out/gather_2018.json 2> gpurun_out/gather_2018.err; tail -30 gpurun_out/gather_2018.json
 # 3. ncu of both gather kernels (one launch each): dram bytes, achieved bandwidth, stall reasons
-for v in 0 1; do
-  HYP_GATHER_V2=$v timeout 300 ncu --set full --clock-control none --import-source on -k regex:gather_kernel -c 2 \
-    -o gpurun_out/gather_v$v -f python scripts/bench_gather.py --reps 1 > gpurun_out/ncu_gather_v$v.log 2>&1
+for v in v1 v2; do
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:gather_kernel -c 2 \
+    -o gpurun_out/gather_$v -f python scripts/bench_gather.py --reps 1 --only $v > gpurun_out/ncu_gather_$v.log 2>&1
 done
 # 4. headline bench, both arms
 timeout 600 python bench.py > gpurun_out/bench.log 2>&1; tail -1 gpurun_out/bench.log
