@@ -15,3 +15,5 @@ done
 # 4. headline bench, both arms
 timeout 600 python bench.py > gpurun_out/bench.log 2>&1; tail -1 gpurun_out/bench.log
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2>&1; tail -1 gpurun_out/bench_ref.log | cut -c1-300
+timeout 600 python scripts/bench_inference.py > gpurun_out/inference.json 2> gpurun_out/inference.err; tail -1 gpurun_out/inference.json
+# 5. whole-scene inference throughput (above)
