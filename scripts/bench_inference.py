@@ -62,4 +62,4 @@ pixels = scene_shape[0] * scene_shape[1]
 assert int((class_map == 255).sum()) == 0
 print(json.dumps({"metric": "whole-scene classification, pixels/s (HYPELCNN eval, GRSS2013 shape)", "pixels": pixels,
                   "batch": args.batch, "device_ms": device_ms, "wall_ms": wall_ms, "pixels_per_s": pixels / device_ms * 1e3,
-                  "useful_TFLOP_per_s": pixels * 157.16e6 / device_ms / 1e9}))
+                  "useful_TFLOP_per_s": pixels * 151.28e6 / device_ms / 1e9}))   # eval graph: 157.16 - 5.88 MFLOP of decoder
