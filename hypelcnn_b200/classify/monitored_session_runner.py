@@ -241,15 +241,19 @@ def run_monitored_session(cross_entropy, log_dir, class_range,
                           testing_nn_params, testing_tensor,
                           validation_nn_params, validation_tensor,
                           importer, flags_as_json_str, alg_params_as_json_str,
-                          summaries=None, engine_of=None):
+                          summaries=None, engine_of=None, is_chief=True):
     """Reference :127-188.  ``summaries`` is what add_classification_summaries returned (the reference finds it
-    through the graph's "summary_op" collection); ``engine_of`` overrides how the checkpoint saver reaches the engine."""
+    through the graph's "summary_op" collection); ``engine_of`` overrides how the checkpoint saver reaches the engine;
+    ``is_chief`` (MonitoredTrainingSession's flag, always True in the reference): only the chief writes checkpoints and
+    summaries — every rank of a data-parallel run restores the same checkpoint and runs the same hooks."""
     augmentation_restorer = None
     if augmentation_info is not None and augmentation_info.perform_shadow_augmentation:
         if augmentation_info.shadow_struct is not None and \
                 augmentation_info.shadow_struct.shadow_op_initializer is not None:
             augmentation_restorer = augmentation_info.shadow_struct.shadow_op_creater()
 
+    if not is_chief:
+        summaries = None
     validation_hook = ValidationHook(validation_nn_params, validation_tensor, class_range, required_steps,
                                      validation_steps, log_dir, importer)
     validation_hook.summaries = summaries
@@ -258,10 +262,12 @@ def run_monitored_session(cross_entropy, log_dir, class_range,
     hooks = [initializer_hook, validation_hook, test_hook]
 
     os.makedirs(log_dir, exist_ok=True)
-    writer = ClassificationSummaryWriter(log_dir)
-    writer.add_text("flags", flags_as_json_str, 0)                       # TextSummaryAtStartHook x 2 (:144-145)
-    writer.add_text("algorithm_params", alg_params_as_json_str, 0)
-    saver = CheckpointSaver(log_dir, engine_of or (lambda: _engine_of(train_step)), save_checkpoint_steps)
+    writer = ClassificationSummaryWriter(log_dir) if is_chief else None
+    if writer is not None:
+        writer.add_text("flags", flags_as_json_str, 0)                   # TextSummaryAtStartHook x 2 (:144-145)
+        writer.add_text("algorithm_params", alg_params_as_json_str, 0)
+    saver = CheckpointSaver(log_dir, engine_of or (lambda: _engine_of(train_step)),
+                            save_checkpoint_steps if is_chief else None)
     if summaries is not None and summaries.model_variables is None:
         summaries.model_variables = lambda: saver.engine_of().export_variables()
 
@@ -288,8 +294,9 @@ def run_monitored_session(cross_entropy, log_dir, class_range,
     for hook in hooks:
         if hasattr(hook, "end"):
             hook.end(None)
-    if context.global_step > 0:
+    if context.global_step > 0 and is_chief:
         saver.save(context.global_step)
-    writer.close()
+    if writer is not None:
+        writer.close()
     return TrainingResult(validation_accuracy=validation_hook.validation_accuracy,
                           test_accuracy=test_hook.testing_accuracy, loss=test_hook.loss)

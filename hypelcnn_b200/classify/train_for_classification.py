@@ -10,6 +10,7 @@ from types import SimpleNamespace
 
 from numpy import mean, std
 
+from hypelcnn_b200 import parallel
 from hypelcnn_b200.classify.monitored_session_runner import (add_classification_summaries, run_monitored_session,
                                                              set_run_seed)
 from hypelcnn_b200.common.common_nn_ops import (AugmentationInfo, TrainingResult, create_graph, get_importer_from_name,
@@ -93,6 +94,10 @@ def perform_an_episode(flags, algorithm_params, model, base_log_path):
     train, test, validation, shadow_dict, class_range, scene_shape, color_list = importer.read_data_set(
         flags.loader_name, flags.path, flags.train_ratio, flags.test_ratio, flags.neighborhood, True)
     augmentation_info = _augmentation_info(flags, shadow_dict)
+    # under torchrun: one process per GPU, the training split strided over the ranks, one gradient all-reduce per step
+    # (hypelcnn_b200/parallel.py); every rank evaluates the whole validation / test lists, rank 0 writes the files
+    rank, _, world = parallel.init_from_env()
+    train = parallel.shard_training_data(train, rank, world)
 
     batch_size = algorithm_params["batch_size"]
     required_steps = flags.step if flags.epoch is None else (train.data.shape[0] * flags.epoch) // batch_size
@@ -106,6 +111,8 @@ def perform_an_episode(flags, algorithm_params, model, base_log_path):
         1000, "/gpu:0", flags.epoch, augmentation_info=augmentation_info, algorithm_params=algorithm_params,
         model=model, create_separate_validation_branch=importer.requires_separate_validation_branch)
     training_nn.data_with_labels, testing_nn.data_with_labels, validation_nn.data_with_labels = train, test, validation
+    if world > 1:
+        train_step.allreduce = parallel.GradientAllReduce(overlap=True)
     if not flags.perform_validation:
         validation_nn = None
 
@@ -116,7 +123,7 @@ def perform_an_episode(flags, algorithm_params, model, base_log_path):
                                    flags.validation_steps, train_step, required_steps, augmentation_info,
                                    training_nn, training_tensor, testing_nn, testing_tensor, validation_nn,
                                    validation_tensor, importer, json.dumps(vars(flags), indent=3),
-                                   json.dumps(algorithm_params, indent=3), summaries=summaries)
+                                   json.dumps(algorithm_params, indent=3), summaries=summaries, is_chief=rank == 0)
     print(f"Done training for {time.time() - started:.3f} sec")
     return _report(result, flags.perform_validation)
 

@@ -46,6 +46,20 @@ def shard_targets(targets, rank, world):
     return targets[b:e]
 
 
+def shard_training_data(data_with_labels, rank, world):
+    """Rank's share of an importer's training split, strided (rank, rank + world, ...) so that every rank sees every
+    class whatever the order of the list.  Works on the importers' holders: (data, labels) arrays in HBM
+    (InMemoryImporter / TFRecordImporter) or a lazy target list (GeneratorImporter)."""
+    if world <= 1:
+        return data_with_labels
+    if not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside world {world}")
+    if hasattr(data_with_labels, "labels"):
+        return data_with_labels._replace(data=data_with_labels.data[rank::world],
+                                         labels=data_with_labels.labels[rank::world])
+    return data_with_labels._replace(targets=data_with_labels.targets[rank::world])
+
+
 class GradientAllReduce:
     """The single collective of a train step: SUM all-reduce of the flat gradient buffer; the 1/world
     factor is folded into the Adam kernel (``hyp_adam_step(grad_scale)``), so the returned scale is what

@@ -165,3 +165,34 @@ def test_checkpoint_rotation_keeps_twenty(tmp_path):
     assert latest_checkpoint("/some/file.safetensors") == "/some/file.safetensors"
     with pytest.raises(IOError):
         latest_checkpoint(str(tmp_path / ".."  / "empty" if (tmp_path / ".." / "empty").mkdir() is None else ""))
+
+
+def test_non_chief_ranks_write_nothing(tmp_path, monkeypatch):
+    from hypelcnn_b200.classify import monitored_session_runner as M
+    monkeypatch.setattr(M, "calculate_accuracy", lambda sess, nn_params, class_range: (0.5, None, None, 0.1, 0.2))
+    engine = _Engine()
+    train_step = _TrainStep(engine)
+    testing, validation, training = _params(4), _params(4), _params(4)
+    cross_entropy = lambda: train_step.last_loss                                       # noqa: E731
+    summaries = M.add_classification_summaries(cross_entropy, lambda: 3e-4, False, testing, validation)
+    result = M.run_monitored_session(cross_entropy, str(tmp_path), range(0, 3), 10, 20, train_step, 41, None, training,
+                                     "t", testing, "t", validation, "t", _Importer([]), "{}", "{}", summaries=summaries,
+                                     engine_of=lambda: engine, is_chief=False)
+    assert engine.global_step == 40 and engine.saved == [] and result.validation_accuracy == 0.5
+    assert not [f for f in os.listdir(tmp_path) if f.startswith("model.ckpt")]
+
+
+def test_training_split_is_strided_over_ranks():
+    from collections import namedtuple
+    from hypelcnn_b200.parallel import shard_training_data
+    Target = namedtuple("Target", ["data", "labels"])
+    Lazy = namedtuple("Lazy", ["data", "targets", "loader", "dataset"])
+    full = Target(data=torch.arange(10).reshape(10, 1), labels=torch.arange(10) % 3)
+    parts = [shard_training_data(full, r, 3) for r in range(3)]
+    assert [p.data.reshape(-1).tolist() for p in parts] == [[0, 3, 6, 9], [1, 4, 7], [2, 5, 8]]
+    assert all(torch.equal(p.labels, p.data.reshape(-1) % 3) for p in parts)
+    assert shard_training_data(full, 0, 1) is full
+    lazy = shard_training_data(Lazy(None, numpy.arange(14).reshape(7, 2), "L", "D"), 1, 2)
+    assert lazy.targets.tolist() == [[2, 3], [6, 7], [10, 11]] and (lazy.loader, lazy.dataset) == ("L", "D")
+    with pytest.raises(ValueError):
+        shard_training_data(full, 3, 3)
