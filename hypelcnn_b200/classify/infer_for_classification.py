@@ -16,6 +16,7 @@ import time
 import numpy
 import torch
 
+from hypelcnn_b200 import parallel
 from hypelcnn_b200.common.common_nn_ops import (ModelInputParams, NNParams, create_colored_image,
                                                 create_target_image_via_samples, get_loader_from_name,
                                                 get_model_from_name, perform_prediction, simple_nn_iterator)
@@ -73,6 +74,12 @@ def prediction_process(flags, model=None):
         validation_data_with_labels = create_sample_data(training_data_with_labels, test_data_with_labels,
                                                          validation_data_with_labels)
 
+    # under torchrun every rank classifies a contiguous slice of the pixel list; the slices meet in merge_class_map
+    rank, _, world = parallel.init_from_env()
+    if world > 1:
+        validation_data_with_labels = validation_data_with_labels._replace(
+            targets=parallel.shard_targets(validation_data_with_labels.targets, rank, world))
+
     if flags.algorithm_param_path is None:
         raise IOError("Algorithm parameter file is not given")
     algorithm_params = json.load(open(flags.algorithm_param_path, "r"))
@@ -99,6 +106,7 @@ def prediction_process(flags, model=None):
     scene_as_image = torch.full(tuple(scene_shape), 255, dtype=torch.uint8, device=data_set.device)
     data_importer.init_tensors(None, validation_tensor, validation_nn_params)
     perform_prediction(None, validation_nn_params, scene_as_image)
+    parallel.merge_class_map(scene_as_image)
     return scene_as_image.cpu().numpy(), color_list
 
 

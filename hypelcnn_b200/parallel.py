@@ -93,6 +93,15 @@ def reduce_confusion(confusion, group=None):
     return confusion
 
 
+def merge_class_map(class_map, fill_value=255, group=None):
+    """Whole-scene inference over ranks: every rank classified its own slice of the pixel list into a class image
+    pre-filled with ``fill_value`` (255 > any class id); the element-wise minimum over ranks is the complete image.
+    The only exchange of the inference path, once, after the last batch."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(class_map, op=dist.ReduceOp.MIN, group=group)
+    return class_map
+
+
 def max_over_ranks(value, device=None, group=None):
     """Timing helper: a device-measured duration as the maximum over ranks."""
     if not (dist.is_initialized() and dist.get_world_size(group) > 1):

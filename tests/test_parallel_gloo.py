@@ -50,6 +50,16 @@ def _worker(rank, world, port, out_dir):
     targets = numpy.arange(23 * 3).reshape(23, 3)
     mine = P.shard_targets(targets, rank, world)
     numpy.save(os.path.join(out_dir, f"targets_{rank}.npy"), mine)
+    # ---- whole-scene inference: each rank fills its slice of the class image, the slices meet in one MIN all-reduce ----
+    class_map = torch.full((23,), 255, dtype=torch.uint8)
+    class_map[torch.from_numpy(mine[:, 0] // 3)] = torch.from_numpy((mine[:, 2] % 7).astype(numpy.uint8))
+    P.merge_class_map(class_map)
+    assert class_map.tolist() == [int(v % 7) for v in targets[:, 2]]
+    # ---- the training split is strided over ranks ----
+    from collections import namedtuple
+    Target = namedtuple("Target", ["data", "labels"])
+    share = P.shard_training_data(Target(torch.arange(9), torch.arange(9) % 2), rank, world)
+    assert share.data.tolist() == list(range(rank, 9, world))
     dist.barrier()
     dist.destroy_process_group()
 
