@@ -21,6 +21,7 @@ import torch
 from hypelcnn_b200.common.cmd_parser import (add_flags, add_parse_cmds_for_json_loader, add_parse_cmds_for_loaders,
                                              add_parse_cmds_for_loggers, add_parse_cmds_for_trainers,
                                              type_ensure_strtobool)
+from hypelcnn_b200 import parallel
 from hypelcnn_b200.common.common_ops import replace_abbrs
 from hypelcnn_b200.gan.wrapper_registry import get_infer_wrapper, get_sampling_map, get_wrapper_dict
 from hypelcnn_b200.gan.wrappers.gan_common import read_hsi_data
@@ -138,6 +139,23 @@ class PairIterator:
                                                   self.shadow_ratio, self.reg_support_rate, self._generator)
 
 
+def shard_pair_iterator(iterator, rank, world):
+    """Data-parallel GAN training: rank's strided share of the paired rows, every rank the same number of rows (the
+    remainder is dropped) so that all ranks run the same number of iterations and meet in every all-reduce; each
+    rank shuffles with its own seed."""
+    if world <= 1:
+        return iterator
+    rows = (iterator.normal_data.shape[0] // world) * world
+    share = slice(rank, rows, world)
+    return PairIterator(iterator.normal_data[share], iterator.shadow_data[share], iterator.batch_size, iterator.epoch,
+                        iterator.shadow_ratio, iterator.reg_support_rate, seed=1234 + rank)
+
+
+def _trainers_of(wrapper):
+    trainer = wrapper.trainer
+    return [trainer.model_x2y, trainer.model_y2x] if hasattr(trainer, "model_x2y") else [trainer]
+
+
 def load_op(batch_size, iteration_count, loader, data_set, shadow_map, shadow_ratio, reg_support_rate, pairing_method,
             device=None):
     """Reference :147-169.  Pairs via the registry's sampler, HSI bands only; ``epoch = iteration_count * batch_size
@@ -230,6 +248,9 @@ def run_session(params, base_log_path, loader=None):
 
     input_iterator = load_op(flags.batch_size, flags.step, loader, data_set, shadow_map, shadow_ratio,
                              flags.regularization_support_rate, flags.pairing_method)
+    # under torchrun: the pairs are strided over the ranks, every train op all-reduces its gradient buffer once
+    rank, _, world = parallel.init_from_env()
+    input_iterator = shard_pair_iterator(input_iterator, rank, world)
     wrapper = get_wrapper_dict(flags)[flags.gan_type]
     the_gan_model = wrapper.define_model(input_iterator.normal_data[:flags.batch_size],
                                          input_iterator.shadow_data[:flags.batch_size])
@@ -242,22 +263,30 @@ def run_session(params, base_log_path, loader=None):
                                          generator_lr=flags.generator_lr, discriminator_lr=flags.discriminator_lr,
                                          gen_discriminator_lr=flags.gen_discriminator_lr)
 
-    from hypelcnn_b200.classify.summaries import ClassificationSummaryWriter
-    writer = ClassificationSummaryWriter(log_dir)
-    writer.add_text("flags", json.dumps(vars(flags), indent=3, default=str), 0)      # TextSummaryAtStartHook
-    writer.close()
+    if world > 1:
+        for trainer in _trainers_of(wrapper):
+            trainer.allreduce = parallel.GradientAllReduce()
+    is_chief = rank == 0                        # validation, summaries and checkpoints are the chief's
+    if is_chief:
+        from hypelcnn_b200.classify.summaries import ClassificationSummaryWriter
+        writer = ClassificationSummaryWriter(log_dir)
+        writer.add_text("flags", json.dumps(vars(flags), indent=3, default=str), 0)  # TextSummaryAtStartHook
+        writer.close()
 
     def saver(global_step):
         numpy.savez(os.path.join(log_dir, f"model.ckpt-{global_step}.npz"), global_step=global_step,
                     **_generator_exports(inference_wrapper))
 
     gan_train(train_ops, input_iterator, log_dir, get_hooks_fn=wrapper.get_train_hooks_fn(),
-              hooks=[peer_validation_hook], num_steps=flags.step, save_checkpoint_steps=validation_iteration_count,
-              saver=saver)
+              hooks=[peer_validation_hook] if is_chief else [], num_steps=flags.step,
+              save_checkpoint_steps=validation_iteration_count, saver=saver if is_chief else None)
     best_upper_div = peer_validation_hook.get_best_upper_div()
     best_mean_div = peer_validation_hook.get_best_mean_div()
-    return [max(best_upper_div) if isinstance(best_upper_div, Sequence) else best_upper_div,
-            max(best_mean_div) if isinstance(best_mean_div, Sequence) else best_mean_div]
+
+    def worst(value):       # both validation directions: the larger divergence; none validated (e.g. a non-chief rank): None
+        return (max(value) if value else None) if isinstance(value, Sequence) else value
+
+    return [worst(best_upper_div), worst(best_mean_div)]
 
 
 def main(argv=None):

@@ -424,3 +424,14 @@ def test_generators_restore_into_either_wrapper_kind(tmp_path):
 
     assert restore_generators(Pair(), str(tmp_path / "model.ckpt-7")).got == (["net1/weights"], ["net1/weights"])
     assert restore_generators(Single(), str(tmp_path / "model.ckpt-7.npz")).got == ["net1/weights"]
+
+
+def test_pair_rows_are_strided_over_ranks_with_equal_counts():
+    from hypelcnn_b200.gan.gan_train_for_shadow import PairIterator, shard_pair_iterator
+    normal = torch.arange(11, dtype=torch.float32).reshape(11, 1, 1, 1)
+    whole = PairIterator(normal, normal * 0.5, 2, 4, 1.0, 0.0)
+    assert shard_pair_iterator(whole, 0, 1) is whole
+    shares = [shard_pair_iterator(whole, r, 3) for r in range(3)]
+    assert [s.normal_data.reshape(-1).tolist() for s in shares] == [[0, 3, 6], [1, 4, 7], [2, 5, 8]]   # 11 // 3 rows each
+    assert all(torch.equal(s.shadow_data, s.normal_data * 0.5) and (s.batch_size, s.epoch) == (2, 4) for s in shares)
+    assert len({len(list(s)) for s in shares}) == 1                      # same number of iterations on every rank
