@@ -168,3 +168,50 @@ def test_avon_overlays(tmp_path):
     assert len(s.training_targets) + len(s.test_targets) + len(s.validation_targets) == total
     shadowed = int(marks[(1, "sh")].sum() + marks[(2, "sh")].sum())
     assert len(s.validation_targets) >= shadowed              # every shadowed target validates
+
+
+def test_multi_data_set_mixes_renditions_per_point():
+    """GULFPORTALT's MIXED mode: every requested point comes from one randomly chosen rendition, the batched form
+    issues one fetch per rendition; shape queries go to the first data set."""
+    import torch
+    from hypelcnn_b200.loader.GULFPORTALTDataLoader import MultiDataSet
+
+    class Rendition:
+        neighborhood, shadow_creator_dict, lidar, casi, device = 1, {"simple": 1}, "lidar", "casi", torch.device("cpu")
+
+        def __init__(self, value):
+            self.value, self.batched = value, 0
+
+        def get_data_shape(self):
+            return [3, 3, 5]
+
+        def get_casi_band_count(self):
+            return 4
+
+        def get_scene_shape(self):
+            return [10, 12]
+
+        def get_unnormalized_casi_dtype(self):
+            return numpy.dtype(numpy.uint16)
+
+        def get_data_point(self, point_x, point_y):
+            return torch.full((3, 3, 5), float(self.value))
+
+        def get_data_points(self, targets_xy):
+            self.batched += 1
+            out = torch.full((targets_xy.shape[0], 3, 3, 5), float(self.value))
+            out[:, 0, 0, 0] = targets_xy[:, 0].float()              # which point landed where
+            return out
+
+    original, shadowed = Rendition(1), Rendition(2)
+    mixed = MultiDataSet(original, shadowed, shadowed, shadowed)
+    assert mixed.get_data_shape() == [3, 3, 5] and mixed.get_casi_band_count() == 4 and mixed.get_scene_shape() == [10, 12]
+    assert (mixed.casi, mixed.lidar, mixed.neighborhood, mixed.shadow_creator_dict) == ("casi", "lidar", 1, {"simple": 1})
+    targets = numpy.stack([numpy.arange(400), numpy.zeros(400, int)], axis=1)
+    got = mixed.get_data_points(targets)
+    assert got.shape == (400, 3, 3, 5) and torch.equal(got[:, 0, 0, 0], torch.arange(400).float())   # order kept
+    share_shadowed = float((got[:, 1, 1, 1] == 2).float().mean())
+    assert 0.65 < share_shadowed < 0.85 and set(got[:, 1, 1, 1].tolist()) == {1.0, 2.0}             # 1 : 3 mix
+    assert original.batched == 1 and shadowed.batched == 3
+    singles = {float(mixed.get_data_point(0, 0)[0, 0, 0]) for _ in range(40)}
+    assert singles == {1.0, 2.0}
