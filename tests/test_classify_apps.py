@@ -196,3 +196,66 @@ def test_training_split_is_strided_over_ranks():
     assert lazy.targets.tolist() == [[2, 3], [6, 7], [10, 11]] and (lazy.loader, lazy.dataset) == ("L", "D")
     with pytest.raises(ValueError):
         shard_training_data(full, 3, 3)
+
+
+def test_perform_an_episode_plumbing(monkeypatch, capsys):
+    """perform_an_episode with the device pieces replaced: what reaches the importer, create_graph and the monitored
+    loop (steps from --epoch, augmentation switches, validation on / off), and the reported result."""
+    from collections import namedtuple
+    from hypelcnn_b200.classify import train_for_classification as T
+    from hypelcnn_b200.common.common_nn_ops import TrainingResult
+    Target = namedtuple("Target", ["data", "labels"])
+    seen = {}
+
+    class Importer:
+        def read_data_set(self, *args):
+            seen["read"] = args
+            mk = lambda n: Target(torch.zeros(n, 3, 3, 5), torch.zeros(n, dtype=torch.uint8))     # noqa: E731
+            return mk(100), mk(10), mk(50), {"simple": "SIMPLE"}, range(0, 4), [8, 9], numpy.zeros((4, 3), numpy.uint8)
+
+        def convert_data_to_tensor(self, test, train, validation, class_range):
+            seen["convert"] = (test.data.shape[0], train.data.shape[0], validation.data.shape[0])
+            return SimpleNamespace(dataset="TEST"), SimpleNamespace(dataset="TRAIN"), SimpleNamespace(dataset="VAL")
+
+        def requires_separate_validation_branch(self):
+            return True
+
+    def create_graph(train_ds, test_ds, val_ds, class_range, batch_size, prefetch, device_id, epochs, **kw):
+        seen["graph"] = (train_ds, test_ds, val_ds, class_range, batch_size, prefetch, device_id, epochs, kw)
+        return "CE", "LR", SimpleNamespace(), SimpleNamespace(), SimpleNamespace(), SimpleNamespace(allreduce=None)
+
+    def run_monitored_session(*args, **kw):
+        seen["run"] = (args, kw)
+        return TrainingResult(validation_accuracy=0.75, test_accuracy=0.5, loss=1.25)
+
+    monkeypatch.setattr(T, "get_importer_from_name", lambda name: Importer())
+    monkeypatch.setattr(T, "create_graph", create_graph)
+    monkeypatch.setattr(T, "run_monitored_session", run_monitored_session)
+    monkeypatch.setattr(T, "add_classification_summaries", lambda *a: ("SUMMARIES",) + a)
+    flags = T.default_flags(loader_name="L", path="P", neighborhood=1, epoch=3, augment_data_with_shadow="simple",
+                            augment_data_with_rotation=True, perform_validation=True, validation_steps=7,
+                            save_checkpoint_steps=9, train_ratio=0.2, test_ratio=0.1)
+    result = T.perform_an_episode(flags, {"batch_size": 16}, "MODEL", "/logs/x")
+    assert seen["read"] == ("L", "P", 0.2, 0.1, 1, True) and seen["convert"] == (10, 100, 50)
+    train_ds, test_ds, val_ds, class_range, batch, prefetch, device, epochs, kw = seen["graph"]
+    assert (train_ds, test_ds, val_ds, class_range, batch, prefetch, device, epochs) == ("TRAIN", "TEST", "VAL", range(0, 4), 16, 1000, "/gpu:0", 3)
+    info = kw["augmentation_info"]
+    assert (info.shadow_struct, info.perform_shadow_augmentation, info.perform_rotation_augmentation,
+            info.perform_reflection_augmentation, info.perform_spectral_augmentation,
+            info.augmentation_random_threshold) == ("SIMPLE", True, True, False, None, 0.5)
+    assert kw["model"] == "MODEL" and kw["algorithm_params"] == {"batch_size": 16}
+    args, kwargs = seen["run"]
+    assert args[:7] == ("CE", "/logs/x", range(0, 4), 9, 7, args[5], 100 * 3 // 16)         # steps from --epoch
+    assert args[12] is not None and kwargs["is_chief"] is True and kwargs["summaries"][0] == "SUMMARIES"
+    assert args[8].data_with_labels.data.shape[0] == 100 and args[10].data_with_labels.data.shape[0] == 10
+    assert (result.validation_accuracy, result.test_accuracy, result.loss) == (0.75, 0.5, 1.25)
+    out = capsys.readouterr().out
+    assert "Steps: 18," in out and "Validation accuracy=0.75, Testing accuracy=0.5, loss=1.25" in out
+    assert "Mean testing accuracy result: (0.5) +- (0), Loss result: (1.25) +- (0)" in out
+    # validation off: the loop gets no validation branch, the result carries none
+    flags.perform_validation, flags.epoch = False, None
+    result = T.perform_an_episode(flags, {"batch_size": 16}, "MODEL", "/logs/x")
+    assert seen["run"][0][12] is None and seen["run"][0][6] == flags.step and result.validation_accuracy is None
+    flags.device = "cpu"
+    with pytest.raises(RuntimeError):
+        T.perform_an_episode(flags, {"batch_size": 16}, "MODEL", "/logs/x")
