@@ -259,3 +259,73 @@ def test_perform_an_episode_plumbing(monkeypatch, capsys):
     flags.device = "cpu"
     with pytest.raises(RuntimeError):
         T.perform_an_episode(flags, {"batch_size": 16}, "MODEL", "/logs/x")
+
+
+def test_inference_app_plumbing(tmp_path, monkeypatch):
+    """infer_for_classification.run with stand-ins for the device pieces: domain handling, checkpoint choice, the
+    decoder excluded from the restore, the class image written as TIFF."""
+    from hypelcnn_b200.classify import infer_for_classification as I
+    from hypelcnn_b200.importer.GeneratorImporter import GeneratorDataInfo
+    from hypelcnn_b200.utilities.tiff_io import imread
+    seen = {}
+
+    class DataSet:
+        device = "cpu"
+
+        def get_data_points(self, targets):
+            return torch.zeros(len(targets), 3, 3, 5)
+
+    data_set = DataSet()
+
+    class Importer:
+        def read_data_set(self, *args):
+            seen["read"] = args
+            mk = lambda t: GeneratorDataInfo(None, numpy.array(t), "LOADER", data_set)            # noqa: E731
+            return (mk([[1, 1, 0]]), mk([[2, 2, 1]]), mk([[3, 3, 2], [0, 1, 2]]), None, range(0, 3), [4, 5],
+                    numpy.array([[255, 0, 0], [0, 255, 0], [0, 0, 255]], numpy.uint8))
+
+        def convert_data_to_tensor(self, test, train, validation, class_range):
+            seen["targets"] = numpy.asarray(validation.targets)
+            return SimpleNamespace(dataset="T"), SimpleNamespace(dataset="TR"), SimpleNamespace(dataset="V")
+
+        def init_tensors(self, session, tensor, nn_params):
+            seen["init"] = tensor.dataset
+
+    class Engine:
+        def load_checkpoint(self, path, exclude_prefixes=()):
+            seen["restore"] = (os.path.basename(path), exclude_prefixes)
+
+    class Model:
+        engine = None
+
+        def engine_for(self, x, alg):
+            seen["engine_for"] = (tuple(x.shape), alg["batch_size"], self._class_count)
+            self.engine = Engine()
+
+    def perform_prediction(session, nn_params, class_map):
+        targets = numpy.asarray(nn_params.data_with_labels.targets)
+        class_map[torch.as_tensor(targets[:, 1]), torch.as_tensor(targets[:, 0])] = 1
+        return class_map
+
+    monkeypatch.setattr(I, "GeneratorImporter", Importer)
+    monkeypatch.setattr(I, "simple_nn_iterator", lambda dataset, batch: ("ITER", dataset, batch))
+    monkeypatch.setattr(I, "perform_prediction", perform_prediction)
+    (tmp_path / "alg.json").write_text(json.dumps({"filter_count": 8}))
+    for step in (5, 20, 100):
+        (tmp_path / f"model.ckpt-{step}.safetensors").write_text("x")
+    flags = SimpleNamespace(loader_name="L", path="P", neighborhood=1, algorithm_param_path=str(tmp_path / "alg.json"),
+                            batch_size=64, model_name="unused", base_log_path=str(tmp_path), output_path=str(tmp_path),
+                            domain="all")
+    image, colored = I.run(flags, model=Model())
+    assert seen["read"] == ("L", "P", 0.1, 0, 1, True) and seen["targets"].shape == (20, 3) and seen["init"] == "V"
+    assert seen["engine_for"] == ((1, 3, 3, 5), 64, 3) and seen["restore"] == ("model.ckpt-100.safetensors", ("image_gen_net_",))
+    assert image.shape == (4, 5) and (image == 1).all() and colored.shape == (4, 5, 3) and (colored == [0, 255, 0]).all()
+    assert numpy.array_equal(imread(str(tmp_path / "result_raw.tif")), image)
+    assert numpy.array_equal(imread(str(tmp_path / "result_colorized.tif")), colored)
+    flags.domain = "sample"
+    image, _ = I.run(flags, model=Model())
+    assert seen["targets"].tolist() == [[1, 1, 0], [2, 2, 1], [3, 3, 2], [0, 1, 2]]     # (train, test, validation) order
+    assert (image == 1).sum() == 4 and (image == 255).sum() == 16
+    flags.algorithm_param_path = None
+    with pytest.raises(IOError):
+        I.run(flags, model=Model())
