@@ -73,3 +73,30 @@ def test_directory_of_csv_files(tmp_path, capsys):
     S.print_statistics_info(S.extract_statistics_info(loaded))
     assert "#Metrics statistics:" in capsys.readouterr().out
     assert S.extract_statistics_info([]).oa_array is None
+
+
+def test_confusion_matrices_round_trip_through_event_files(tmp_path, capsys, monkeypatch):
+    """Training loop -> TensorBoard event file -> read_summary_file -> statistics: what classify/summaries.py writes under
+    ``validation_confusion`` comes back as the same integer matrices, filtered by step, saved as CSV."""
+    from types import SimpleNamespace
+    from hypelcnn_b200.classify.summaries import ClassificationSummaryWriter
+    from hypelcnn_b200.utilities import read_summary_file as R
+    log_dir = tmp_path / "experiment" / "run_1"
+    os.makedirs(log_dir)
+    runs = _matrices()[2][:3]
+    writer = ClassificationSummaryWriter(str(log_dir))
+    for step, m in zip((100, 200, 300), runs):
+        metrics = SimpleNamespace(confusion=m.astype(numpy.int32), accuracy=0.5, mean_per_class_accuracy=0.4, kappa=0.3)
+        writer.add_classification_summaries(step, 1.0, 3e-4, metrics, metrics)
+    writer.close()
+    out_dir = tmp_path / "csv"
+    os.makedirs(out_dir)
+    got = R.collect(str(log_dir), output_dir=str(out_dir))
+    assert len(got) == 3 and all(numpy.array_equal(a, b) for a, b in zip(got, runs))
+    assert sorted(os.listdir(out_dir)) == ["experiment_run_1_s100.csv", "experiment_run_1_s200.csv", "experiment_run_1_s300.csv"]
+    assert numpy.array_equal(numpy.loadtxt(out_dir / "experiment_run_1_s200.csv", dtype=int, delimiter=","), runs[1])
+    only = R.collect(str(log_dir), filtered_steps=[300], output_dir=str(out_dir))
+    assert len(only) == 1 and numpy.array_equal(only[0], runs[2])
+    monkeypatch.chdir(tmp_path)
+    R.main([str(log_dir), "100", "200"])
+    assert "OA:" in capsys.readouterr().out
