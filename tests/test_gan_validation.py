@@ -191,3 +191,33 @@ def test_shadow_ratio_from_the_resident_scene_equals_the_reference():
     assert load_shadow_map_common(None, 1, smap)[1] is None
     with pytest.raises(ValueError):
         load_shadow_map_common(data_set, n + 1, smap[1:])
+
+
+def test_shadow_tooling():
+    """measure_targets_shadow_ratio.ratio_statistics and remove_test_targets_from_shadow.clear_targets against direct
+    numpy (the reference scripts' arithmetic: divide, keep finite rows, mean / std; clear the shadowed targets)."""
+    from hypelcnn_b200.utilities.measure_targets_shadow_ratio import ratio_statistics
+    from hypelcnn_b200.utilities.remove_test_targets_from_shadow import clear_targets
+    rng = numpy.random.default_rng(8)
+    normal = rng.uniform(0.2, 1.0, (300, 1, 1, 6)).astype(numpy.float32)
+    shadow = (normal / numpy.linspace(1.5, 4, 6).astype(numpy.float32) * rng.uniform(0.8, 1.2, normal.shape)).astype(numpy.float32)
+    normal[5, 0, 0, 2] = 0.0                                            # inf -> the pair is dropped
+    normal[9, 0, 0, 0], shadow[9, 0, 0, 0] = 0.0, 0.0                   # nan -> dropped
+    mean, std = ratio_statistics(normal, shadow)
+    with numpy.errstate(all="ignore"):
+        ratio = numpy.squeeze(shadow) / numpy.squeeze(normal)
+    ratio = ratio[numpy.isfinite(ratio).all(axis=1)]
+    assert ratio.shape[0] == 298 and numpy.allclose(mean, ratio.mean(axis=0), rtol=1e-5) and numpy.allclose(std, ratio.std(axis=0), rtol=1e-4)
+    shadow_map = (rng.random((12, 15)) < 0.4).astype(numpy.uint8)
+    targets = numpy.stack([rng.integers(0, 15, 40), rng.integers(0, 12, 40), rng.integers(0, 5, 40)], axis=1)
+    cleared, lit = clear_targets(shadow_map, targets)
+    want = shadow_map.copy()
+    count = 0
+    for x, y, _ in targets:                                             # the reference's loop
+        if want[y, x] == 1:
+            want[y, x] = 0
+        else:
+            count += 1
+    assert numpy.array_equal(cleared, want) and shadow_map.sum() > cleared.sum()
+    # the loop counts a target twice-listed under shadow as "not shadowed" the second time; the array form does not
+    assert lit <= count
