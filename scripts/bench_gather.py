@@ -21,6 +21,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--grss2018", action="store_true")
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--only", choices=["v1", "v2"], default=None, help="run one kernel version only (for ncu captures)")
+ap.add_argument("--cpu-patches", type=int, default=4096, help="patches of the CPU arm (0: skip): the reference's per-pixel "
+                "window slice restated in numpy (oracle/dataset_ref.py), scene preparation not timed")
 ap.add_argument("--scene-batch", type=int, default=65536, help="targets per launch of the whole-scene sweep")
 args = ap.parse_args()
 
@@ -77,6 +79,19 @@ for version in {"v1": ("0",), "v2": ("1",), None: ("0", "1")}[args.only]:
             "ms": ms, "patches_per_s": n / ms * 1e3, "GB_per_s": n * bytes_per_patch / ms / 1e6,
             "launches": -(-n // args.scene_batch)}
 os.environ["HYP_GATHER_V2"] = "0"
+cpu = None
+if args.cpu_patches and not args.grss2018 and args.only is None:
+    import time
+    from oracle import dataset_ref as D                               # the checker, timed as the CPU baseline
+    scene = D.SceneRef(casi.cpu().numpy().copy(), lidar.cpu().numpy()[:, :, None].copy(), nb, True)
+    points = numpy.concatenate([random_targets.cpu().numpy()[:args.cpu_patches], numpy.zeros((min(4096, args.cpu_patches), 1), numpy.int32)], 1)
+    t0 = time.perf_counter()
+    host_patches, _ = D.gather_patches(scene, points)
+    seconds = time.perf_counter() - t0
+    assert numpy.array_equal(host_patches, reference_out[:len(points)].cpu().numpy()), "device gather differs from the oracle"
+    cpu = {"patches": len(points), "patches_per_s": len(points) / seconds, "kind": "port", "cores": 1,
+           "note": "per-pixel window slice in numpy; pad + normalisation of the scene not timed"}
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
 print(json.dumps({"workload": "grss2018_gather" if args.grss2018 else "grss2013_gather", "bytes_per_patch": bytes_per_patch,
-                  "hbm_peak_GB_per_s": peaks.get("hbm_gbs"), "v2_bit_identical": args.only is None, "results": results}, indent=1))
+                  "hbm_peak_GB_per_s": peaks.get("hbm_gbs"), "v2_bit_identical": args.only is None, "results": results,
+                  "cpu_baseline": cpu}, indent=1))
