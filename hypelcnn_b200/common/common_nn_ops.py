@@ -236,9 +236,10 @@ class AugmentingIterator:
         if info.perform_shadow_augmentation and info.shadow_struct is not None:
             gen = torch.Generator(device="cpu")
             gen.manual_seed(self.seed * 7919 + self.calls)
-            pick = (torch.rand(images.shape[0], generator=gen) < info.augmentation_random_threshold).to(images.device)
-            if bool(pick.any()):
-                images = torch.where(pick.view(-1, 1, 1, 1), info.shadow_struct.shadow_op(images), images)
+            pick = torch.rand(images.shape[0], generator=gen) < info.augmentation_random_threshold
+            if bool(pick.any()):            # decided on the host draw: no device synchronisation in the input pipeline
+                images = torch.where(pick.to(images.device, non_blocking=True).view(-1, 1, 1, 1),
+                                     info.shadow_struct.shadow_op(images), images)
         if info.perform_rotation_augmentation or info.perform_reflection_augmentation or \
                 info.perform_spectral_augmentation:
             spectral = float(info.perform_spectral_augmentation) if info.perform_spectral_augmentation else 0.0
