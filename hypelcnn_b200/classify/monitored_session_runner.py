@@ -4,7 +4,8 @@ Same function / class names and argument lists; ``run_monitored_session`` is a p
 instead of a tf MonitoredTrainingSession.  What the session machinery did implicitly is spelled out here:
 
 * StopAtStepHook(last_step = required_steps - 1): the loop ends once global_step reaches ``required_steps - 1``;
-* NanTensorHook(fail_on_nan_loss=False): a NaN loss ends the loop with a message instead of raising;
+* NanTensorHook(fail_on_nan_loss=False): a NaN loss ends the loop with a message instead of raising (noticed one step
+  late, so that the check never stalls the launch queue);
 * the summary saver (``save_summaries_steps = 100``) and ValidationHook write the tags of
   ``add_classification_summaries`` through classify/summaries.py;
 * the checkpoint saver: ``model.ckpt-<step>.safetensors`` (TF variable names, Adam slots, global_step) every
@@ -227,11 +228,42 @@ def _engine_of(train_step):
     return model.engine
 
 
-def _is_nan(loss):
-    if loss is None:
-        return False
-    loss = loss[0] if getattr(loss, "dim", lambda: 0)() > 0 else loss
-    return bool(torch.isnan(torch.as_tensor(loss)).item())
+class _LossWatch:
+    """NaN watch that never drains the launch queue: the loss of step n is copied into pinned host memory right behind
+    step n (asynchronously, two alternating slots) and an event marks the copy; it is looked at after step n + 1 has
+    been launched, waiting at most for that event — i.e. for step n, not for the work queued behind it."""
+
+    def __init__(self):
+        self._slots, self._events, self._turn, self._pending = None, None, 0, None
+
+    def submit(self, loss):
+        """Register this step's loss; returns True if the PREVIOUS step's loss was NaN."""
+        previous_was_nan = self.check()
+        if loss is None:
+            return previous_was_nan
+        loss = loss.reshape(-1)[:1] if hasattr(loss, "reshape") else torch.as_tensor([float(loss)])
+        if loss.is_cuda:
+            if self._slots is None:
+                self._slots = [torch.empty(1, dtype=loss.dtype, pin_memory=True) for _ in range(2)]
+                self._events = [torch.cuda.Event() for _ in range(2)]
+            slot = self._turn
+            self._turn ^= 1
+            self._slots[slot].copy_(loss, non_blocking=True)
+            self._events[slot].record()
+            self._pending = slot
+        else:
+            self._pending = loss.clone()
+        return previous_was_nan
+
+    def check(self):
+        """Is the registered (not yet examined) loss NaN?"""
+        pending, self._pending = self._pending, None
+        if pending is None:
+            return False
+        if isinstance(pending, int):
+            self._events[pending].synchronize()
+            return bool(torch.isnan(self._slots[pending]).item())
+        return bool(torch.isnan(pending).item())
 
 
 def run_monitored_session(cross_entropy, log_dir, class_range,
@@ -277,13 +309,17 @@ def run_monitored_session(cross_entropy, log_dir, class_range,
     restored = saver.restore_latest()
     context.global_step = train_step.global_step if restored is not None else 0
     last_step = required_steps - 1                                       # StopAtStepHook(last_step=...)
+    loss_watch = _LossWatch()
     while context.global_step < last_step and not context.stop_requested:
         try:
             train_step.run()
         except StopIteration:                                            # --epoch given: the input ran out
             break
         context.global_step = train_step.global_step
-        if _is_nan(cross_entropy()):                                     # NanTensorHook(fail_on_nan_loss=False)
+        # NanTensorHook(fail_on_nan_loss=False).  The loss of step n is looked at after step n + 1 has been launched, so
+        # reading it does not drain the device queue every step (at the reference's batch of 48 a step is ~170 short
+        # launches and the host has to run ahead); a divergence is noticed one step late.
+        if loss_watch.submit(cross_entropy()):
             print("Model diverged with loss = NaN.")
             context.request_stop()
         for hook in hooks:
@@ -291,6 +327,8 @@ def run_monitored_session(cross_entropy, log_dir, class_range,
         if summaries is not None and context.global_step % TEST_ITERATION_COUNT == 0:
             summaries.write(writer, context.global_step)
         saver.after_run(context.global_step)
+    if not context.stop_requested and loss_watch.check():
+        print("Model diverged with loss = NaN.")
     for hook in hooks:
         if hasattr(hook, "end"):
             hook.end(None)

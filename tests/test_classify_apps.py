@@ -144,8 +144,8 @@ def test_monitored_loop_cadence_checkpoints_and_summaries(tmp_path, monkeypatch,
 
 def test_monitored_loop_stops_on_nan_and_on_exhausted_input(tmp_path, monkeypatch, capsys):
     result, log, engine = _run(tmp_path / "nan", monkeypatch, required_steps=1000, nan_at=7)
-    assert engine.global_step == 7 and "Model diverged with loss = NaN." in capsys.readouterr().out
-    assert engine.saved == ["model.ckpt-7.safetensors"] and numpy.isnan(result.loss)
+    assert engine.global_step == 8 and "Model diverged with loss = NaN." in capsys.readouterr().out   # seen one step late
+    assert engine.saved == ["model.ckpt-8.safetensors"] and result.loss == pytest.approx(1 / 8)
     result, log, engine = _run(tmp_path / "short", monkeypatch, required_steps=1000, exhaust_at=12)
     assert engine.global_step == 12 and engine.saved == ["model.ckpt-12.safetensors"]
 
@@ -329,3 +329,12 @@ def test_inference_app_plumbing(tmp_path, monkeypatch):
     flags.algorithm_param_path = None
     with pytest.raises(IOError):
         I.run(flags, model=Model())
+
+
+def test_loss_watch_reports_one_step_late():
+    from hypelcnn_b200.classify.monitored_session_runner import _LossWatch
+    watch = _LossWatch()
+    seen = [watch.submit(torch.tensor([v, 0.0, 0.0])) for v in (1.0, float("nan"), 2.0, 3.0)]
+    assert seen == [False, False, True, False] and watch.check() is False
+    assert watch.submit(torch.tensor(float("nan"))) is False and watch.check() is True and watch.check() is False
+    assert watch.submit(None) is False and watch.submit(float("nan")) is False and watch.submit(None) is True
