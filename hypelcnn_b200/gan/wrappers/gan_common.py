@@ -331,3 +331,48 @@ def create_base_validation_hook(data_set, loader, log_dir, neighborhood, shadow_
                                  shadow_map=shadow_map, shadow_ratio=1. / shadow_ratio, input_tensor=y_input_tensor,
                                  infer_model=model_backward, fetch_shadows=True, name_suffix="deshadowed")
     return PeerValidationHook(shadowed, de_shadowed)
+
+
+# --------------------------------------------------------------------------------------------------------------- #
+# The remaining names of the reference module, for callers written against it.
+# --------------------------------------------------------------------------------------------------------------- #
+def _get_lr(base_lr, max_number_of_steps, global_step=0):
+    """Reference :222-244: ``base_lr`` for the first half of the run, then linear to zero at ``max_number_of_steps``
+    (tf polynomial_decay, power 1).  The global step is an argument here (a graph variable in the reference)."""
+    lr_constant_steps = max_number_of_steps // 2
+    if global_step < lr_constant_steps:
+        return base_lr
+    decay_steps = max_number_of_steps - lr_constant_steps
+    return base_lr * (1.0 - min(global_step - lr_constant_steps, decay_steps) / decay_steps)
+
+
+def define_standard_train_ops(gan_model, gan_loss, max_number_of_steps, generator_lr, discriminator_lr):
+    """Reference :247-279: Adam(beta1 0.5) generator / discriminator train ops with the schedule above.  ``gan_model``
+    is what a wrapper's define_model returned (it carries the trainer)."""
+    from hypelcnn_b200.gan.wrappers.cycle_gan_wrapper import GANTrainOps
+    return GANTrainOps(getattr(gan_model, "trainer", gan_model), max_number_of_steps, generator_lr, discriminator_lr)
+
+
+def create_input_tensor(data_set, is_shadow_graph):
+    """Reference :307-312 creates the placeholder ``x`` / ``y`` of shape [None, P, P, bands]; eager code feeds tensors
+    directly, so only the description of that input is returned."""
+    shape = data_set.get_data_shape()
+    return {"name": input_x_tensor_name if is_shadow_graph else input_y_tensor_name,
+            "shape": [None, shape[0], shape[1], data_set.get_casi_band_count()], "dtype": "float32"}
+
+
+class InitializerHook:
+    """Reference :32-44 feeds the pair matrices into the tf.data placeholders when the session starts.  The pair
+    iterator of gan_train_for_shadow.load_op already owns its (device-resident) data: nothing to do, kept so that hook
+    lists written for the reference still construct."""
+
+    def __init__(self, input_itr, normal_placeholder=None, shadow_placeholder=None, normal_data=None, shadow_data=None):
+        self.input_itr = input_itr
+        self.normal_data, self.shadow_data = normal_data, shadow_data
+        self.normal_placeholder, self.shadow_placeholder = normal_placeholder, shadow_placeholder
+
+    def after_create_session(self, session=None, coord=None):
+        pass
+
+    def after_run(self, run_context, run_values=None):
+        pass

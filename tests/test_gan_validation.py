@@ -221,3 +221,23 @@ def test_shadow_tooling():
     assert numpy.array_equal(cleared, want) and shadow_map.sum() > cleared.sum()
     # the loop counts a target twice-listed under shadow as "not shadowed" the second time; the array form does not
     assert lit <= count
+
+
+def test_remaining_gan_common_names():
+    from hypelcnn_b200.gan.wrappers import gan_common as C
+    from hypelcnn_b200.gan.wrappers.cycle_gan_wrapper import get_lr
+    for step in (0, 1, 499, 500, 501, 750, 999, 1000, 1500):
+        assert C._get_lr(2e-4, 1000, step) == get_lr(2e-4, 1000, step)
+    assert C._get_lr(1.0, 7, 3) == 1.0 and C._get_lr(1.0, 7, 5) == pytest.approx(0.5) and C._get_lr(1.0, 7, 7) == 0.0
+    ds = ProbeDataSet([4, 4], patch=3)
+    assert C.create_input_tensor(ds, True) == {"name": "x", "shape": [None, 3, 3, 2], "dtype": "float32"}
+    assert C.create_input_tensor(ds, False)["name"] == "y"
+    hook = C.InitializerHook("ITER", None, None, "N", "S")
+    hook.after_create_session(None, None)
+    assert (hook.input_itr, hook.normal_data, hook.shadow_data) == ("ITER", "N", "S")
+    reference_names = ["InitializerHook", "BestRatioHolder", "BaseValidationHook", "PeerValidationHook", "ValidationHook",
+                       "adj_shadow_ratio", "_get_lr", "define_standard_train_ops", "create_inference_for_matrix_input",
+                       "create_input_tensor", "create_stats_tensor", "calculate_stats_from_samples",
+                       "load_samples_for_testing", "read_hsi_data", "plot_overall_info", "print_overall_info",
+                       "model_generator_name", "model_base_name", "input_x_tensor_name", "input_y_tensor_name"]
+    assert [n for n in reference_names if not hasattr(C, n)] == []
