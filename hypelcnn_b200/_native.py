@@ -95,6 +95,7 @@ _PROTOS = {
     "hyp_scatter_class_map": (_I, [_P, _P, _L, _I, _I, _P, _P]),
     "hyp_model_debug_tensor": (_I, [_P, ctypes.c_char_p, _I, ctypes.POINTER(_P), ctypes.POINTER(_L)]),
     "hyp_crc32c": (_I, [_P, ctypes.c_uint64, _P]),
+    "hyp_tiff_lzw_decode": (_I, [_P, ctypes.c_uint64, _P, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]),
     "hyp_debug_plan_level_pairs": (_I, [_I, _I, _I, _P, _I, _P, _I, _P]),
     "hyp_debug_schedule": (_I, [_P, _I, _I, _I, _P, _P]),
     "hyp_debug_tc_gemm": (_I, [_I, _P, _P, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P]),

@@ -123,11 +123,28 @@ def _lzw_decode_chunked(data, expected):
     return bytes(out)
 
 
+def _lzw_decode_native(data, expected):
+    """The same decoder inside libhypelcnn_b200.so (hyp_tiff_lzw_decode, host code): two orders of magnitude faster on
+    the hundreds of megabytes of a compressed scene.  None when the library has not been built."""
+    try:
+        import ctypes
+        from hypelcnn_b200 import _native
+        lib = _native.lib()
+    except Exception:
+        return None
+    out = ctypes.create_string_buffer(expected)
+    written = ctypes.c_uint64(0)
+    if lib.hyp_tiff_lzw_decode(data, len(data), out, expected, ctypes.byref(written)) != 0:
+        raise TiffError("corrupt LZW stream")
+    return out.raw[:written.value]
+
+
 def _decompress(data, compression, expected):
     if compression == 1:
         return data
     if compression == 5:
-        return _lzw_decode_chunked(data, expected)
+        decoded = _lzw_decode_native(data, expected)
+        return decoded if decoded is not None else _lzw_decode_chunked(data, expected)
     if compression in (8, 32946):
         return zlib.decompress(data)
     if compression == 32773:

@@ -252,6 +252,10 @@ int hyp_model_dropout_mask(hyp_model* m, const char* layer_scope, uint64_t seed,
  * The checksum of the TFRecord framing TensorFlow writes for importer/TFRecordImporter.py:16-72 and
  * utilities/tfrecord_writer.py:45-81 (masked: ((crc >> 15) | (crc << 17)) + 0xa282ead8). */
 int hyp_crc32c(const void* data, uint64_t len, uint32_t* crc_inout);
+/* Host only: decode one TIFF LZW strip / tile (compression 5) into out[0..out_capacity); *out_len = bytes written.
+ * Replaces tifffile's decoder behind the reference's scene reads (loader/GRSS2013DataLoader.py, GRSS2018DataLoader.py:53-67,
+ * GULFPORTDataLoader.py:22-43: `from tifffile import imread`). */
+int hyp_tiff_lzw_decode(const void* data, uint64_t len, void* out, uint64_t out_capacity, uint64_t* out_len);
 
 /* Debug / test hook, host only: the pair-tile plan of a level forward launch (hyp_tc_engine.cuh plan_level_pairs;
  * groundwork, not used by hyp_model_forward yet).  tiles: rows of (p1, p2 or -1, seg_begin, seg_count); segs: rows of

@@ -185,3 +185,31 @@ def test_unsupported_files_are_refused():
     data = bytearray(_assemble(a))
     with pytest.raises(TiffError):
         imread(bytes(data[:2]) + struct.pack("<H", 99) + bytes(data[4:]))    # wrong magic
+
+
+def test_native_and_python_lzw_decoders_agree(tmp_path):
+    """hyp_tiff_lzw_decode (libhypelcnn_b200.so, host code) against the pure-Python decoder on libtiff-written strips:
+    smooth data (long strings, table resets), noise (short strings), and a strip cut short by its capacity."""
+    from PIL import Image
+    from hypelcnn_b200.utilities import tiff_io as T
+    path = str(tmp_path / "l.tif")
+    smooth = (numpy.add.outer(numpy.arange(400), numpy.arange(700)) // 5).astype(numpy.uint16)
+    noise = _cube((300, 300), numpy.uint8)
+    flat = numpy.zeros((500, 500), numpy.uint8)
+    for image in (smooth, noise, flat):
+        Image.fromarray(image).save(path, compression="tiff_lzw")
+        raw = open(path, "rb").read()
+        page = T._read_ifds(memoryview(raw))[0]
+        for offset, count in zip(page.all(T.STRIP_OFFSETS), page.all(T.STRIP_BYTE_COUNTS)):
+            strip = raw[offset:offset + count]
+            rows = min(page.first(T.ROWS_PER_STRIP), image.shape[0])
+            expected = rows * image.shape[1] * image.dtype.itemsize
+            python_bytes = T._lzw_decode_chunked(strip, expected)
+            native_bytes = T._lzw_decode_native(strip, expected)
+            assert native_bytes is not None and native_bytes[:len(python_bytes)] == python_bytes[:len(native_bytes)]
+            assert len(native_bytes) == min(expected, len(python_bytes)) or len(native_bytes) == expected
+            short = T._lzw_decode_native(strip, 1000)
+            assert short == python_bytes[:1000]
+        assert numpy.array_equal(imread(path), image)
+    with pytest.raises(TiffError):
+        T._lzw_decode_native(bytes([0xff] * 64), 100)                       # codes beyond the table
