@@ -9,7 +9,8 @@ compression none / LZW / Deflate / PackBits, predictors none / horizontal / floa
 stacked.  Result layout follows tifffile: ``[H,W]`` for one sample per pixel, ``[H,W,S]`` for chunky, ``[S,H,W]`` for
 planar data, ``[pages, ...]`` for a stack.  GeoTIFF tags are ignored (the reference ignores them too).
 Writer: uncompressed little-endian strips, chunky by default (``planarconfig="contig"`` as the reference passes) or
-``"separate"``; BigTIFF when the file would pass 4 GiB.
+``"separate"``; BigTIFF when the file would pass 4 GiB.  LZW strips are decoded by ``hyp_tiff_lzw_decode`` in the native
+library when it is built (host code; a pure-Python decoder of the same algorithm otherwise).
 Pinned in tests/test_tiff_io.py against Pillow and OpenCV (libtiff) in both directions for every layout they support.
 """
 import struct
