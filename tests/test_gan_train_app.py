@@ -435,3 +435,88 @@ def test_pair_rows_are_strided_over_ranks_with_equal_counts():
     assert [s.normal_data.reshape(-1).tolist() for s in shares] == [[0, 3, 6], [1, 4, 7], [2, 5, 8]]   # 11 // 3 rows each
     assert all(torch.equal(s.shadow_data, s.normal_data * 0.5) and (s.batch_size, s.epoch) == (2, 4) for s in shares)
     assert len({len(list(s)) for s in shares}) == 1                      # same number of iterations on every rank
+
+
+def test_gan_inference_apps_glue(tmp_path, monkeypatch, capsys):
+    """gan_infer_for_shadow.run and gan_infer_image_for_shadow.run with stand-ins for the loader and the device
+    wrapper: checkpoint restore, hook with frequency 0, output file naming, which pixels get converted."""
+    from hypelcnn_b200.gan import gan_infer_for_shadow as V
+    from hypelcnn_b200.gan import gan_infer_image_for_shadow as M
+    from hypelcnn_b200.gan.wrappers.cycle_gan_wrapper import CycleGANInferenceWrapper
+    from hypelcnn_b200.utilities.tiff_io import imread
+    rng = numpy.random.default_rng(2)
+    H, W, C = 10, 12, 4
+    raw = rng.integers(200, 3000, (H, W, C)).astype(numpy.uint16)
+    casi_min = raw.min(axis=(0, 1))
+    casi_max = (raw - casi_min).max(axis=(0, 1))
+    normalised = ((raw - casi_min) / casi_max.astype(numpy.float32)).astype(numpy.float32)
+    shadow_map = (rng.random((H, W)) < 0.3).astype(numpy.uint8)
+
+    class DataSet:
+        def __init__(self):
+            self.casi_min, self.casi_max = casi_min, casi_max
+
+        def get_data_shape(self):
+            return [1, 1, C + 1]
+
+        def get_scene_shape(self):
+            return [H, W]
+
+        def get_casi_band_count(self):
+            return C
+
+        def get_unnormalized_casi_dtype(self):
+            return numpy.dtype(numpy.uint16)
+
+        def get_data_points(self, targets):
+            t = numpy.asarray(targets)
+            patch = numpy.concatenate([normalised[t[:, 1], t[:, 0]], numpy.zeros((len(t), 1), numpy.float32)], axis=1)
+            return torch.from_numpy(patch).reshape(-1, 1, 1, C + 1)
+
+    class Loader:
+        def load_data(self, neighborhood, normalize):
+            return DataSet()
+
+        def load_shadow_map(self, neighborhood, data_set):
+            return shadow_map, numpy.full(C, 2.0, numpy.float32)
+
+        def get_band_measurements(self):
+            return numpy.arange(C)
+
+    class Variables:
+        scale = None
+
+        def load(self, values):
+            self.scale = float(values["net1/weights"].reshape(-1)[0])
+
+    class Wrapper(CycleGANInferenceWrapper):
+        def __init__(self):
+            self.forward_generator, self.backward_generator = Variables(), Variables()
+
+        def construct_inference_graph(self, input_tensor, is_shadow_graph, clip_invalid_values, copy_extra=0):
+            gen = self.forward_generator if is_shadow_graph else self.backward_generator
+            return input_tensor * gen.scale
+
+    numpy.savez(tmp_path / "model.ckpt-3000.npz", **{"ModelX2Y/Generator/net1/weights": numpy.full((2, 1, 1), 0.5),
+                                                      "ModelY2X/Generator/net1/weights": numpy.full((2, 1, 1), 2.0)})
+    for module in (V, M):
+        monkeypatch.setattr(module, "get_loader_from_name", lambda name, path: Loader())
+        monkeypatch.setattr(module, "get_infer_wrapper", lambda gan_type, bands=None: Wrapper())
+    flags = SimpleNamespace(loader_name="L", path="P", neighborhood=0, gan_type="cycle_gan", number_of_samples=30,
+                            base_log_path=str(tmp_path / "model.ckpt-3000"), output_path=str(tmp_path),
+                            make_them_shadow="shadow", convert_all=False)
+    best = V.run(flags)
+    out = capsys.readouterr().out
+    assert len(best) == 2 and "Validation metrics for shadowed #0" in out and "Validation metrics for deshadowed #0" in out
+    assert best[0] == pytest.approx(0.0, abs=1e-6)       # forward generator halves, ratio 2: generated / input * ratio = 1
+    path, image = M.run(flags)
+    assert os.path.basename(path) == "shadow_image_shadow_3000.tif" and numpy.array_equal(imread(path), image)
+    lit = shadow_map == 0
+    assert numpy.abs(image[~lit].astype(int) - raw[~lit].astype(int)).max() <= 1           # shadowed pixels untouched
+    want = ((normalised * numpy.float32(0.5)) * casi_max.astype(numpy.float32) + casi_min.astype(numpy.float32)).astype(numpy.uint16)
+    assert numpy.array_equal(image[lit], want[lit])
+    flags.make_them_shadow, flags.convert_all = "deshadow", True
+    path, image = M.run(flags)
+    assert os.path.basename(path) == "shadow_image_deshadow_3000_all.tif"
+    want = ((normalised * numpy.float32(2.0)) * casi_max.astype(numpy.float32) + casi_min.astype(numpy.float32)).astype(numpy.uint16)
+    assert numpy.array_equal(image, want)
