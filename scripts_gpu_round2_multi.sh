@@ -17,7 +17,7 @@ timeout 300 $RUN -m hypelcnn_b200.classify.train_for_classification --loader_nam
 # whole-scene inference: contiguous pixel slices per rank, one MIN all-reduce of the class image
 timeout 300 $RUN -m hypelcnn_b200.classify.infer_for_classification --loader_name SyntheticGRSS2013DataLoader \
   --path synthetic:H=40,W=60,samples=800 --neighborhood 3 --batch_size 256 --algorithm_param_path /tmp/r2/alg.json \
-  --base_log_path /tmp/r2/classify/syntheticgrss2013ldr_hypelcnnmdl_trn100_palg_7x7 --output_path /tmp/r2 \
+  --base_log_path /tmp/r2/classify/syntheticgrss2013ldr_hypelcnnmdl_trn100_alg_7x7 --output_path /tmp/r2 \
   > gpurun_out/dp_infer.log 2>&1; tail -2 gpurun_out/dp_infer.log
 # GAN: pair rows strided with equal counts, one all-reduce per train op, chief-only validation
 timeout 300 $RUN -m hypelcnn_b200.gan.gan_train_for_shadow --loader_name SyntheticGULFPORTALTDataLoader \
