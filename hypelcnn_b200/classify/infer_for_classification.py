@@ -120,7 +120,7 @@ def run(flags, model=None):
     else:
         raise ValueError(f"Domain flags does not support value:{flags.domain}")
     colored = create_colored_image(scene_as_image, color_list)
-    if flags.output_path is not None:
+    if flags.output_path is not None and parallel.init_from_env()[0] == 0:       # rank 0 writes the merged images
         imwrite(os.path.join(flags.output_path, "result_raw.tif"), scene_as_image)
         imwrite(os.path.join(flags.output_path, "result_colorized.tif"), colored)
     print(f"Done evaluation({time.time() - start_time:.3f} sec)")
