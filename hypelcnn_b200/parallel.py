@@ -54,10 +54,14 @@ def shard_training_data(data_with_labels, rank, world):
         return data_with_labels
     if not 0 <= rank < world:
         raise ValueError(f"rank {rank} outside world {world}")
+    # equal counts on every rank (the remainder is dropped): all ranks then run the same number of steps per epoch and
+    # meet in every all-reduce
     if hasattr(data_with_labels, "labels"):
-        return data_with_labels._replace(data=data_with_labels.data[rank::world],
-                                         labels=data_with_labels.labels[rank::world])
-    return data_with_labels._replace(targets=data_with_labels.targets[rank::world])
+        rows = (data_with_labels.labels.shape[0] // world) * world
+        return data_with_labels._replace(data=data_with_labels.data[rank:rows:world],
+                                         labels=data_with_labels.labels[rank:rows:world])
+    rows = (len(data_with_labels.targets) // world) * world
+    return data_with_labels._replace(targets=data_with_labels.targets[rank:rows:world])
 
 
 class GradientAllReduce:
