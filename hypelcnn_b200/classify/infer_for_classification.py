@@ -65,6 +65,10 @@ def prediction_process(flags, model=None):
     validation, ...) and ``create_sample_data(training, test, validation)`` receives them in that order although its
     parameters are named (test, training, validation) — only the stacking order of the targets depends on it."""
     data_importer = GeneratorImporter()
+    # under torchrun every rank classifies a contiguous slice of the pixel list; the slices meet in merge_class_map.
+    # The sample lists are random splits: same seed on every rank first, or the slices would not tile one list.
+    rank, _, world = parallel.init_from_env()
+    parallel.sync_split_seed()
     training_data_with_labels, test_data_with_labels, validation_data_with_labels, shadow_dict, class_range, \
         scene_shape, color_list = data_importer.read_data_set(flags.loader_name, flags.path, 0.1, 0,
                                                                flags.neighborhood, True)
@@ -74,8 +78,6 @@ def prediction_process(flags, model=None):
         validation_data_with_labels = create_sample_data(training_data_with_labels, test_data_with_labels,
                                                          validation_data_with_labels)
 
-    # under torchrun every rank classifies a contiguous slice of the pixel list; the slices meet in merge_class_map
-    rank, _, world = parallel.init_from_env()
     if world > 1:
         validation_data_with_labels = validation_data_with_labels._replace(
             targets=parallel.shard_targets(validation_data_with_labels.targets, rank, world))

@@ -266,6 +266,15 @@ class _LossWatch:
         return bool(torch.isnan(pending).item())
 
 
+def _loss_over_ranks(loss):
+    import torch.distributed as dist
+    if loss is None or not (dist.is_initialized() and dist.get_world_size() > 1):
+        return loss
+    total = torch.as_tensor(loss, dtype=torch.float32).detach().reshape(-1)[:1].clone()
+    dist.all_reduce(total, op=dist.ReduceOp.SUM)
+    return total
+
+
 def run_monitored_session(cross_entropy, log_dir, class_range,
                           save_checkpoint_steps, validation_steps,
                           train_step, required_steps,
@@ -319,7 +328,10 @@ def run_monitored_session(cross_entropy, log_dir, class_range,
         # NanTensorHook(fail_on_nan_loss=False).  The loss of step n is looked at after step n + 1 has been launched, so
         # reading it does not drain the device queue every step (at the reference's batch of 48 a step is ~170 short
         # launches and the host has to run ahead); a divergence is noticed one step late.
-        if loss_watch.submit(cross_entropy()):
+        # Data parallel: the watched value is the SUM over ranks of the local losses (NaN on one rank -> NaN everywhere,
+        # one 4-byte all-reduce queued behind the step, no host wait), so every rank takes the stop decision at the same
+        # global step and nobody is left alone in the next gradient all-reduce.
+        if loss_watch.submit(_loss_over_ranks(cross_entropy())):
             print("Model diverged with loss = NaN.")
             context.request_stop()
         for hook in hooks:

@@ -91,12 +91,14 @@ def perform_an_episode(flags, algorithm_params, model, base_log_path):
     if flags.device == "cpu":
         raise RuntimeError("--device=cpu: this engine has no CPU path (the kernels are sm_100a only)")
     importer = get_importer_from_name(flags.importer_name)
+    # under torchrun: one process per GPU, the training split strided over the ranks, one gradient all-reduce per step
+    # (hypelcnn_b200/parallel.py); every rank evaluates the whole validation / test lists, rank 0 writes the files.
+    # The loaders' random splits must come out identical on every rank before they are strided: one broadcast seed.
+    rank, _, world = parallel.init_from_env()
+    parallel.sync_split_seed()
     train, test, validation, shadow_dict, class_range, scene_shape, color_list = importer.read_data_set(
         flags.loader_name, flags.path, flags.train_ratio, flags.test_ratio, flags.neighborhood, True)
     augmentation_info = _augmentation_info(flags, shadow_dict)
-    # under torchrun: one process per GPU, the training split strided over the ranks, one gradient all-reduce per step
-    # (hypelcnn_b200/parallel.py); every rank evaluates the whole validation / test lists, rank 0 writes the files
-    rank, _, world = parallel.init_from_env()
     train = parallel.shard_training_data(train, rank, world)
 
     batch_size = algorithm_params["batch_size"]

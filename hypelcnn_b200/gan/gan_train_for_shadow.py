@@ -215,7 +215,75 @@ def gan_train(train_ops, input_iterator, logdir, get_hooks_fn, hooks=None, num_s
             hook.after_run(context, None)
         if saver is not None and save_checkpoint_steps and gstep % save_checkpoint_steps == 0:
             saver(gstep)
+    # CheckpointSaverHook.end: MonitoredTrainingSession writes the final state whatever the step count
+    if saver is not None and gstep is not None and not (save_checkpoint_steps and gstep % save_checkpoint_steps == 0):
+        saver(gstep)
     return gstep
+
+
+_STATE_TENSORS = ("gen_params", "dis_params", "feat_params", "gen_m", "gen_v", "dis_m", "dis_v")
+_STATE_COUNTERS = ("gen_steps", "dis_steps", "global_step")
+
+
+def _named_trainers(trainer):
+    if hasattr(trainer, "model_x2y"):
+        return [("ModelX2Y/", trainer.model_x2y), ("ModelY2X/", trainer.model_y2x)]
+    return [("", trainer)]
+
+
+def trainer_state(trainer):
+    """Everything a restarted run needs beyond the generator weights (MonitoredTrainingSession(checkpoint_dir=log_dir)
+    saves every global variable, reference :123-141): all flat parameter buffers — discriminators and feature
+    discriminators included —, the Adam moments, the optimizers' step counts and the global step."""
+    out = {}
+    for scope, t in _named_trainers(trainer):
+        for name in _STATE_TENSORS:
+            if hasattr(t, name):
+                out[f"{scope}train_state/{name}"] = getattr(t, name).detach().cpu().numpy()
+        for key, (m, v) in getattr(t, "slots", {}).items():
+            out[f"{scope}train_state/{key}_m"] = m.detach().cpu().numpy()
+            out[f"{scope}train_state/{key}_v"] = v.detach().cpu().numpy()
+        for name in _STATE_COUNTERS:
+            if hasattr(t, name):
+                out[f"{scope}train_state/{name}"] = numpy.int64(getattr(t, name))
+        for key, value in getattr(t, "clock", {}).items():
+            out[f"{scope}train_state/clock_{key}"] = numpy.int64(value)
+    return out
+
+
+def restore_trainer_state(trainer, values):
+    """Inverse of trainer_state; buffers are overwritten in place (the generator objects hold views of them)."""
+    for scope, t in _named_trainers(trainer):
+        def get(name):
+            return values.get(f"{scope}train_state/{name}")
+        for name in _STATE_TENSORS:
+            if hasattr(t, name) and get(name) is not None:
+                getattr(t, name).copy_(torch.as_tensor(numpy.asarray(get(name))))
+        for key, (m, v) in getattr(t, "slots", {}).items():
+            if get(f"{key}_m") is not None:
+                m.copy_(torch.as_tensor(numpy.asarray(get(f"{key}_m"))))
+                v.copy_(torch.as_tensor(numpy.asarray(get(f"{key}_v"))))
+        for name in _STATE_COUNTERS:
+            if hasattr(t, name) and get(name) is not None:
+                setattr(t, name, int(get(name)))
+        for key in list(getattr(t, "clock", {})):
+            if get(f"clock_{key}") is not None:
+                t.clock[key] = int(get(f"clock_{key}"))
+
+
+def latest_checkpoint(log_dir):
+    """(step, path) of the newest model.ckpt-N.npz in log_dir, or (None, None)."""
+    best = (None, None)
+    if os.path.isdir(log_dir):
+        for name in os.listdir(log_dir):
+            if name.startswith("model.ckpt-") and name.endswith(".npz"):
+                try:
+                    step = int(name[len("model.ckpt-"):-len(".npz")])
+                except ValueError:
+                    continue
+                if best[0] is None or step > best[0]:
+                    best = (step, os.path.join(log_dir, name))
+    return best
 
 
 def _generator_exports(inference_wrapper):
@@ -246,10 +314,12 @@ def run_session(params, base_log_path, loader=None):
     data_set = loader.load_data(neighborhood, True)
     shadow_map, shadow_ratio = loader.load_shadow_map(neighborhood, data_set)
 
+    # under torchrun: the pairs are strided over the ranks, every train op all-reduces its gradient buffer once; the
+    # samplers draw from the global generators, so every rank seeds them alike before the pair list is built
+    rank, _, world = parallel.init_from_env()
+    parallel.sync_split_seed()
     input_iterator = load_op(flags.batch_size, flags.step, loader, data_set, shadow_map, shadow_ratio,
                              flags.regularization_support_rate, flags.pairing_method)
-    # under torchrun: the pairs are strided over the ranks, every train op all-reduces its gradient buffer once
-    rank, _, world = parallel.init_from_env()
     input_iterator = shard_pair_iterator(input_iterator, rank, world)
     wrapper = get_wrapper_dict(flags)[flags.gan_type]
     the_gan_model = wrapper.define_model(input_iterator.normal_data[:flags.batch_size],
@@ -275,7 +345,14 @@ def run_session(params, base_log_path, loader=None):
 
     def saver(global_step):
         numpy.savez(os.path.join(log_dir, f"model.ckpt-{global_step}.npz"), global_step=global_step,
-                    **_generator_exports(inference_wrapper))
+                    **_generator_exports(inference_wrapper), **trainer_state(wrapper.trainer))
+
+    # a log dir that already holds a checkpoint continues from it (every rank restores the same file)
+    restored_step, restored_path = latest_checkpoint(log_dir)
+    if restored_path is not None:
+        with numpy.load(restored_path) as values:
+            restore_trainer_state(wrapper.trainer, values)
+        print(f"Restored {restored_path} (global step {restored_step})")
 
     gan_train(train_ops, input_iterator, log_dir, get_hooks_fn=wrapper.get_train_hooks_fn(),
               hooks=[peer_validation_hook] if is_chief else [], num_steps=flags.step,

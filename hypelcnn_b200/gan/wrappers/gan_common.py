@@ -1,5 +1,6 @@
 """gan/wrappers/gan_common.py of the reference on the device: the per-pixel generator inference over a matrix, and the
 validation side of GAN training (best-ratio bookkeeping, band-ratio statistics, validation hooks, sample loading)."""
+import bisect
 import json
 import os
 import random
@@ -44,53 +45,54 @@ input_y_tensor_name = "y"
 
 
 class BestRatioHolder:
-    """Reference :47-104: the ``max_size`` lowest divergences seen so far as (iteration, divergence), ascending.  A new
-    point goes after every held point it is strictly greater than *counted over the whole list* (the reference's loop
-    does not stop at the first larger element; on a sorted list that is the sorted position, ties go in front)."""
+    """The ``max_size`` lowest divergences seen so far, kept as an ascending list of (iteration, divergence) in
+    ``data_holder`` (the attribute callers and the JSON file use; reference gan_common.py:47-104).  A new value lands in
+    front of the held values that are >= it — ``bisect_left`` over the divergences — and the largest drops off the end
+    once the list is over ``max_size``."""
 
     def __init__(self, max_size) -> None:
-        super().__init__()
-        self.data_holder = []
         self.max_size = max_size
+        self.data_holder = []
 
     def add_point(self, iteration, diver_val):
-        iteration, diver_val = int(iteration), float(diver_val)     # JSON-serialisable
-        insert_idx = sum(1 for (_, curr_diver) in self.data_holder if diver_val > curr_diver)
-        self.data_holder.insert(insert_idx, (iteration, diver_val))
-        if len(self.data_holder) > self.max_size:
-            self.data_holder.pop()
+        point = (int(iteration), float(diver_val))                 # plain Python numbers: the list goes to JSON
+        at = bisect.bisect_left([held[1] for held in self.data_holder], point[1])
+        self.data_holder[at:at] = [point]
+        del self.data_holder[self.max_size:]
 
     def get_best_diver(self):
         return self.data_holder[0][1] if self.data_holder else None
 
     def get_point_with_itr(self, iteration):
-        for (curr_iter, curr_diver) in self.data_holder:
-            if curr_iter == iteration:
-                return curr_iter, curr_diver
-        return None, None
+        return next(((it, div) for it, div in self.data_holder if it == iteration), (None, None))
 
     def load(self, file_address):
+        """A missing or undecodable file is reported and leaves the holder as it is."""
         try:
-            with open(file_address, "rb") as read_file:
-                self.data_holder = json.load(read_file)
-            print(f"Best ratio file {file_address} is loaded.", self.data_holder)
+            with open(file_address, "rb") as stream:
+                self.data_holder = json.load(stream)
         except IOError:
             print(f"File {file_address} file not found. No best ratio is loaded.")
         except JSONDecodeError:
             print(f"File {file_address} file can not be decoded. No best ratio is loaded.")
+        else:
+            print(f"Best ratio file {file_address} is loaded.", self.data_holder)
 
     def save(self, file_address):
-        with open(file_address, "w") as write_file:
-            write_file.write(json.dumps(self.data_holder))
+        with open(file_address, "w") as stream:
+            json.dump(self.data_holder, stream)
 
     @staticmethod
     def create_common_iterations(ratio_holder_1, ratio_holder_2):
-        result = BestRatioHolder(ratio_holder_1.max_size)
-        for (curr_iter, _) in ratio_holder_1.data_holder:
-            (found_itr, found_kl) = ratio_holder_2.get_point_with_itr(curr_iter)
-            if found_itr is not None:
-                result.add_point(found_itr, found_kl)
-        return result
+        """Iterations held by both, with the second holder's divergences."""
+        common = BestRatioHolder(ratio_holder_1.max_size)
+        second = {}
+        for it, div in ratio_holder_2.data_holder:
+            second.setdefault(it, div)
+        for it, _ in ratio_holder_1.data_holder:
+            if it in second:
+                common.add_point(it, second[it])
+        return common
 
     def __str__(self) -> str:
         return str(self.data_holder)
@@ -103,25 +105,20 @@ def _iteration_of(run_context):
 
 
 class BaseValidationHook:
-    """Reference :107-138."""
+    """State shared by the validation hooks (reference :107-138): two best-10 lists and the validation cadence."""
 
     def __init__(self, iteration_freq, log_dir, shadow_ratio):
-        self._iteration_frequency = iteration_freq
-        self._shadow_ratio = shadow_ratio
-        self._log_dir = log_dir
-        self.best_mean_div_holder = BestRatioHolder(10)
-        self.best_upper_div_holder = BestRatioHolder(10)
+        self._iteration_frequency, self._log_dir, self._shadow_ratio = iteration_freq, log_dir, shadow_ratio
+        self.best_mean_div_holder, self.best_upper_div_holder = BestRatioHolder(10), BestRatioHolder(10)
         self.validation_itr_mark = False
 
     def after_create_session(self, session=None, coord=None):
         pass
 
     def _is_validation_itr(self, current_iteration):
-        """Every iteration when the frequency is 0; otherwise at 1 + k * frequency, k >= 1 (never at iteration 1)."""
-        result = True
-        if self._iteration_frequency != 0:
-            result = current_iteration % self._iteration_frequency == 1 and current_iteration != 1
-        return result
+        """Frequency 0: every iteration.  Otherwise iterations 1 + k * frequency with k >= 1 (never iteration 1)."""
+        freq = self._iteration_frequency
+        return freq == 0 or (current_iteration != 1 and current_iteration % freq == 1)
 
     def get_best_mean_div(self):
         return self.best_mean_div_holder.get_best_diver()
@@ -131,32 +128,33 @@ class BaseValidationHook:
 
 
 class PeerValidationHook:
-    """Reference :141-166: the shadowed and the de-shadowed validation side by side; after a validation iteration it
-    prints the iterations that are among the best of both."""
+    """Several validation hooks run side by side (reference :141-166: the shadowed and the de-shadowed direction); on
+    a validation iteration the iterations that are among the best of the first two are reported."""
 
     def __init__(self, *validation_base_hooks):
         self._validation_base_hooks = validation_base_hooks
 
     def after_create_session(self, session=None, coord=None):
-        for validation_base_hook in self._validation_base_hooks:
-            validation_base_hook.after_create_session(session, coord)
+        for hook in self._validation_base_hooks:
+            hook.after_create_session(session, coord)
 
     def after_run(self, run_context, run_values=None):
-        ratio_holder_list = []
-        for validation_base_hook in self._validation_base_hooks:
-            validation_base_hook.after_run(run_context, run_values)
-            ratio_holder_list.append(validation_base_hook.best_mean_div_holder)
-        if self._validation_base_hooks[0].validation_itr_mark:
+        for hook in self._validation_base_hooks:
+            hook.after_run(run_context, run_values)
+        first, second = self._validation_base_hooks[0], self._validation_base_hooks[1]
+        if first.validation_itr_mark:
             print("Best common options:",
-                  BestRatioHolder.create_common_iterations(ratio_holder_list[0], ratio_holder_list[1]))
+                  BestRatioHolder.create_common_iterations(first.best_mean_div_holder, second.best_mean_div_holder))
+
+    def _bests(self, getter):
+        values = [getter(hook) for hook in self._validation_base_hooks]
+        return [v for v in values if v is not None]
 
     def get_best_mean_div(self):
-        return [val_base_hook.get_best_mean_div() for val_base_hook in self._validation_base_hooks
-                if val_base_hook.get_best_mean_div() is not None]
+        return self._bests(lambda hook: hook.get_best_mean_div())
 
     def get_best_upper_div(self):
-        return [val_base_hook.get_best_upper_div() for val_base_hook in self._validation_base_hooks
-                if val_base_hook.get_best_upper_div() is not None]
+        return self._bests(lambda hook: hook.get_best_upper_div())
 
 
 def _kl_divergence(p, q):
@@ -221,49 +219,33 @@ def load_samples_for_testing(data_set, sample_count, neighborhood, shadow_map, f
 
 
 def read_hsi_data(loader, data_set, shadow_map, pairing_method, sampling_method_map):
-    """Reference :388-395: run the chosen sampler and keep the HSI bands (drops the LiDAR channel)."""
-    if pairing_method not in sampling_method_map:
+    """The chosen sampler's (normal, shadowed) pair matrices without the trailing LiDAR channel (reference :388-395)."""
+    sampler = sampling_method_map.get(pairing_method)
+    if sampler is None:
         raise ValueError(f"Wrong sampling parameter value ({pairing_method}).")
-    normal_data_as_matrix, shadow_data_as_matrix = \
-        sampling_method_map[pairing_method].get_sample_pairs(data_set, loader, shadow_map)
-    normal_data_as_matrix = normal_data_as_matrix[:, :, :, 0:data_set.get_casi_band_count()]
-    shadow_data_as_matrix = shadow_data_as_matrix[:, :, :, 0:data_set.get_casi_band_count()]
-    return normal_data_as_matrix, shadow_data_as_matrix
+    bands = data_set.get_casi_band_count()
+    return tuple(matrix[..., :bands] for matrix in sampler.get_sample_pairs(data_set, loader, shadow_map))
 
 
 def plot_overall_info(bands, mean, lower_bound, upper_bound, iteration, plt_name, log_dir):
-    """Reference :398-419 draws the band-ratio curve with its 10-90 % envelope into ``{plt_name}_{iteration}.pdf``.
-    The curve data always goes to ``{plt_name}_{iteration}.csv`` (band, median, p10, p90); the PDF is drawn as well when
-    matplotlib is importable (it is not part of this image)."""
-    table = numpy.stack([numpy.asarray(bands, dtype=numpy.float64), mean, lower_bound, upper_bound], axis=1)
+    """The reference (:398-419) draws the band-ratio curve and its 10-90 % envelope with matplotlib, which is not part of
+    this image; the curve goes to ``{plt_name}_{iteration}.csv`` (band, median, p10, p90) for any plotting tool."""
+    table = numpy.column_stack([numpy.asarray(bands, dtype=numpy.float64), mean, lower_bound, upper_bound])
     numpy.savetxt(os.path.join(log_dir, f"{plt_name}_{iteration}.csv"), table, delimiter=",",
                   header="band,ratio_p50,ratio_p10,ratio_p90", comments="")
-    try:
-        from matplotlib import pyplot as plt
-    except ImportError:
-        return
-    plt.rcParams['font.size'] = 14
-    plt.scatter(bands, mean, label="mean ratio", s=10)
-    plt.plot(bands, mean)
-    plt.fill_between(bands, lower_bound, upper_bound, alpha=0.2)
-    plt.xlabel("Spectral band(nm)")
-    plt.ylabel("Ratio between generated and original samples")
-    plt.ylim([-1, 4])
-    plt.yticks(list(range(-1, 5)))
-    plt.grid()
-    plt.savefig(os.path.join(log_dir, f"{plt_name}_{iteration}.pdf"), dpi=300, bbox_inches='tight')
-    plt.clf()
 
 
 def print_overall_info(mean, std):
-    """Reference :422-429: ``mean±std`` per band, a line break after every band whose index is 1 mod 5."""
+    """``mean±std`` per band in the reference's text layout (:422-429): brackets around the list, a line break after
+    the bands whose index is 1 mod 5, a space after the others."""
+    cells = [f"{m:2.4f}\u00B1{s:2.2f}" for m, s in zip(mean, std)]
+    if cells:
+        cells[0] = "[ " + cells[0]
+        if len(cells) > 1:
+            cells[-1] += " ]"
+    text = "".join(cell + ("\n" if i % 5 == 1 else " ") for i, cell in enumerate(cells))
     print("Mean&std Generated vs Original Ratio: ")
-    band_size = mean.shape[0]
-    for band_index in range(0, band_size):
-        prefix = "[ " if band_index == 0 else ""
-        postfix = " ]" if band_index == band_size - 1 and band_index != 0 else ""
-        print(f"{prefix}{mean[band_index]:2.4f}±{std[band_index]:2.2f}{postfix}",
-              end="\n" if band_index % 5 == 1 else " ")
+    print(text, end="")
 
 
 class ValidationHook(BaseValidationHook):

@@ -13,7 +13,8 @@ from hypelcnn_b200.common.common_nn_ops import get_loader_from_name
 from hypelcnn_b200.importer.DataImporter import DataImporter
 from hypelcnn_b200.utilities.tfrecord_io import decode_example, iter_records
 
-TFRecordDataInfo = namedtuple("TFRecordDataInfo", ["data", "path"])
+# shard = (rank, world) of a data-parallel run (hypelcnn_b200/parallel.shard_training_data): rows rank::world of the file
+TFRecordDataInfo = namedtuple("TFRecordDataInfo", ["data", "path", "shard"], defaults=[None])
 TFRecordDataTensor = namedtuple("TFRecordDataTensor", ["dataset", "path_placeholder"])
 TFRecordSpecialData = namedtuple("TFRecordSpecialData", ["shape"])
 
@@ -64,14 +65,22 @@ class TFRecordImporter(DataImporter):
                 TFRecordDataInfo(data=TFRecordSpecialData(validation_shape), path=base + "validation.tfrecord"),
                 None, loader.get_class_count(), None, loader.get_samples_color_list())
 
-    @staticmethod
-    def _device_split(info, class_count, device):
-        images, labels = load_split(info.path, info.data.shape[1:4], class_count, pin=True)
-        images = images.to(device, non_blocking=True)
-        one_hot = torch.zeros((labels.shape[0], class_count), dtype=torch.uint8, device=device)
-        if labels.shape[0]:
-            one_hot.scatter_(1, labels.to(device).unsqueeze(1), 1)
-        return images, one_hot
+    def _device_split(self, info, class_count, device):
+        """The split file of ``info`` in HBM as (images, one-hot labels); parsed once per (file, shard)."""
+        cache = self.__dict__.setdefault("_splits", {})
+        key = (info.path, info.shard, class_count)
+        if key not in cache:
+            images, labels = load_split(info.path, info.data.shape[1:4], class_count, pin=True)
+            if info.shard is not None:
+                rank, world = info.shard
+                rows = (labels.shape[0] // world) * world
+                images, labels = images[rank:rows:world].contiguous(), labels[rank:rows:world].contiguous()
+            images = images.to(device, non_blocking=True)
+            one_hot = torch.zeros((labels.shape[0], class_count), dtype=torch.uint8, device=device)
+            if labels.shape[0]:
+                one_hot.scatter_(1, labels.to(device).unsqueeze(1), 1)
+            cache[key] = (images, one_hot)
+        return cache[key]
 
     def convert_data_to_tensor(self, test_data_with_labels, training_data_with_labels, validation_data_with_labels,
                                class_range):
@@ -80,13 +89,25 @@ class TFRecordImporter(DataImporter):
         device = torch.device("cuda", torch.cuda.current_device())
         testing = self._device_split(test_data_with_labels, class_range.stop, device)
         training = self._device_split(training_data_with_labels, class_range.stop, device)
-        # like the reference (:66-68) the third tensor is the TESTING set again; the validation file is not read here
+        # like the reference (:66-68) the third tensor is built over the TESTING file; which file a branch really reads
+        # is decided by init_tensors from the branch's own data_with_labels.path (the reference's path placeholder)
         return (TFRecordDataTensor(dataset=testing, path_placeholder=test_data_with_labels.path),
                 TFRecordDataTensor(dataset=training, path_placeholder=training_data_with_labels.path),
                 TFRecordDataTensor(dataset=testing, path_placeholder=test_data_with_labels.path))
 
     def init_tensors(self, session, tensor, nn_params):
-        nn_params.input_iterator.reset()
+        """Reference :70-72 feeds ``nn_params.data_with_labels.path`` into the path placeholder and re-initialises the
+        iterator: the validation branch — built over the testing tensor — thereby reads validation.tfrecord.  Here the
+        branch's iterator is pointed at the (cached) HBM copy of that file, then rewound."""
+        iterator = nn_params.input_iterator
+        info = getattr(nn_params, "data_with_labels", None)
+        if info is not None and getattr(info, "path", None) is not None:
+            batches = iterator
+            while hasattr(batches, "inner"):                     # AugmentingIterator and friends wrap the batcher
+                batches = batches.inner
+            class_count = batches.labels.shape[1]
+            batches.images, batches.labels = self._device_split(info, class_count, batches.images.device)
+        iterator.reset() if hasattr(iterator, "reset") else iterator.initializer()
 
     def requires_separate_validation_branch(self):
         return False

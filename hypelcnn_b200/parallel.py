@@ -29,6 +29,35 @@ def init_from_env(backend=None):
     return rank, local, world
 
 
+def sync_split_seed(group=None):
+    """Same train / validation / test split on every rank.  The loaders draw their splits from numpy's and Python's
+    global generators (sklearn's StratifiedShuffleSplit without a random_state, numpy.random.shuffle), which every
+    process seeds differently: strided shards of DIFFERENT permutations overlap, and one rank's validation pixels turn
+    up in another rank's training shard.  Rank 0 draws one seed, broadcasts it, and every rank seeds both generators
+    with it; call this right before ``read_data_set``.  Returns the seed (None for a single process)."""
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        return None
+    import random
+
+    import numpy
+    box = [int.from_bytes(os.urandom(4), "little") if dist.get_rank(group) == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    numpy.random.seed(box[0])
+    random.seed(box[0])
+    return box[0]
+
+
+def collective_any(flag, device=None, group=None):
+    """True on every rank as soon as ``flag`` is true on one of them (MAX all-reduce of one byte).  Stop decisions of
+    a training loop (NaN watch, stop requests) go through this so that all ranks leave the loop at the same step and
+    nobody is left waiting in a gradient all-reduce."""
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        return bool(flag)
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return bool(t.item())
+
+
 def shard_range(n, rank, world):
     """Contiguous partition of n units (patches of a batch, pixels of a scene) over ranks: the first
     n % world ranks get one extra unit.  -> (begin, end)."""
@@ -56,6 +85,10 @@ def shard_training_data(data_with_labels, rank, world):
         raise ValueError(f"rank {rank} outside world {world}")
     # equal counts on every rank (the remainder is dropped): all ranks then run the same number of steps per epoch and
     # meet in every all-reduce
+    if hasattr(data_with_labels, "path"):          # TFRecordImporter: the file is strided when it is parsed into HBM
+        shape = list(data_with_labels.data.shape)
+        shape[0] = int(shape[0]) // world
+        return data_with_labels._replace(data=type(data_with_labels.data)(shape), shard=(rank, world))
     if hasattr(data_with_labels, "labels"):
         rows = (data_with_labels.labels.shape[0] // world) * world
         return data_with_labels._replace(data=data_with_labels.data[rank:rows:world],

@@ -137,7 +137,7 @@ def test_training_loop_order_and_stops():
     assert last == 5
     assert log[0] == ("session",)
     assert log[1:6] == [("inc", 1), ("gen", 1, (2, 1, 1, 4)), ("dis", 1, (2, 1, 1, 4)), ("hook", 1, [1.0, 2.0]), ("inc", 2)]
-    assert [e[1] for e in log if e[0] == "save"] == [2, 4]
+    assert [e[1] for e in log if e[0] == "save"] == [2, 4, 5]            # every 2 steps + the final state (CheckpointSaverHook.end)
     assert [e[1] for e in log if e[0] == "hook"] == [1, 2, 3, 4, 5]
     # exhausted input ends the run before num_steps (tf OutOfRangeError in the reference)
     log2 = []
@@ -269,9 +269,10 @@ def test_run_session_glue_with_stand_in_wrappers(tmp_path, monkeypatch, capsys):
     batches = (200 * 16 // pairs) * pairs // 16
     assert 0 < batches <= 200
     checkpoints = sorted(int(f[len("model.ckpt-"):-4]) for f in files if f.startswith("model.ckpt-"))
-    assert checkpoints == list(range(20, batches + 1, 20))
+    assert checkpoints == sorted(set(range(20, batches + 1, 20)) | {batches})       # every 20 steps + the final state
     ckpt = numpy.load(os.path.join(log_dir, f"model.ckpt-{checkpoints[-1]}.npz"))
-    assert set(ckpt.files) == {"global_step", "ModelX2Y/Generator/net1/weights", "ModelY2X/Generator/net1/weights"}
+    assert set(ckpt.files) == {"global_step", "ModelX2Y/Generator/net1/weights", "ModelY2X/Generator/net1/weights",
+                               "train_state/global_step"}
     assert numpy.allclose(ckpt["ModelX2Y/Generator/net1/weights"], 1 / true_ratio, rtol=0.25)
     shadowed = json.load(open(os.path.join(log_dir, "best_ratio_shadowed.json")))
     assert sorted(p[0] for p in shadowed)[:2] == [21, 41] and len(shadowed) == min(10, (batches - 1) // 20)

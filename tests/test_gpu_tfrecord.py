@@ -40,3 +40,18 @@ def test_tfrecord_importer_round_trip_and_training(tmp_path):
     for _ in range(3):
         train_step.run()
     assert train_step.global_step == 3 and numpy.isfinite(float(ce()[0]))
+    # the validation branch is built over the TESTING tensor; init_tensors points it at validation.tfrecord
+    # (reference importer/TFRecordImporter.py:70-72 feeds nn_params.data_with_labels.path into the path placeholder)
+    validation_nn.data_with_labels, testing_nn.data_with_labels = va_info, te_info
+    imp.init_tensors(None, validation_tensor, validation_nn)
+    assert torch.equal(validation_nn.input_iterator.images, val.data)
+    assert torch.equal(validation_nn.input_iterator.labels.argmax(dim=1).to(torch.uint8), val.labels)
+    imp.init_tensors(None, testing_tensor, testing_nn)
+    assert torch.equal(testing_nn.input_iterator.images, test.data)
+    # data parallel: the training file is strided over the ranks when it is parsed
+    from hypelcnn_b200 import parallel
+    shard = parallel.shard_training_data(tr_info, 1, 2)
+    rows = (train.data.shape[0] // 2) * 2
+    assert int(shard.data.shape[0]) == rows // 2 and shard.shard == (1, 2)
+    images_1, _ = imp._device_split(shard, classes.stop, images.device)
+    assert torch.equal(images_1, train.data[1:rows:2])

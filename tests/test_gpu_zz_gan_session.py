@@ -59,8 +59,11 @@ def test_run_session(tmp_path, gan_type, pairing, capsys):
     suffixes = ["shadowed"] if gan_type == "cut_x2y" else ["shadowed", "deshadowed"]
     for suffix in suffixes:
         best = json.load(open(os.path.join(log_dir, f"best_ratio_{suffix}.json")))
-        assert {11, 21} <= {p[0] for p in best} and all(numpy.isfinite(p[1]) for p in best)
-        assert all(p[0] % 10 == 1 for p in best)
+        # 11 validations (iterations 11, 21, .., 111) into a best-10 list: WHICH one is evicted depends on how the
+        # divergence moves during training, so only what every run guarantees is asserted
+        kept = [p[0] for p in best]
+        assert len(kept) == 10 and len(set(kept)) == 10 and set(kept) <= set(range(11, 120, 10))
+        assert all(numpy.isfinite(p[1]) for p in best) and [p[1] for p in best] == sorted(p[1] for p in best)
         assert f"band_ratio_{suffix}_11.csv" in files
     assert any("tfevents" in f for f in files)
     ckpt = numpy.load(os.path.join(log_dir, "model.ckpt-20.npz"))
@@ -69,3 +72,18 @@ def test_run_session(tmp_path, gan_type, pairing, capsys):
     if gan_type == "cycle_gan":
         assert any(numpy.abs(ckpt[n]).sum() > 0 for n in names)              # the zero-initialised generator moved
     assert "Validation metrics for shadowed #11" in capsys.readouterr().out
+    # the final state is always written, and a second run over the same log dir continues from it: generators,
+    # discriminators, Adam moments and the step clocks (MonitoredTrainingSession(checkpoint_dir=log_dir))
+    final = numpy.load(os.path.join(log_dir, "model.ckpt-120.npz"))
+    state_keys = [n for n in final.files if "train_state/" in n]
+    assert any(n.endswith("dis_params") for n in state_keys) and any(n.endswith("_m") for n in state_keys)
+    if gan_type != "dcl_gan":
+        flags.step = 7
+        run_session(vars(flags), base, loader=_loader())
+        assert "Restored" in capsys.readouterr().out
+        again = numpy.load(os.path.join(log_dir, "model.ckpt-127.npz"))
+        assert int(again["global_step"]) == 127
+        moved = [n for n in state_keys if n.endswith("dis_params") and not numpy.array_equal(final[n], again[n])]
+        assert moved                                                         # training went on from the restored weights
+        steps = [n for n in state_keys if n.endswith("gen_steps") or n.endswith("clock_gen")]
+        assert steps and all(int(again[n]) == int(final[n]) + 7 for n in steps)

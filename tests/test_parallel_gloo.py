@@ -60,6 +60,22 @@ def _worker(rank, world, port, out_dir):
     Target = namedtuple("Target", ["data", "labels"])
     share = P.shard_training_data(Target(torch.arange(9), torch.arange(9) % 2), rank, world)
     assert share.data.tolist() == list(range(rank, 8, world))            # 9 rows over 2 ranks: 4 each, the last dropped
+    # ---- the loaders' random splits are drawn from one broadcast seed: every rank holds the SAME train / validation
+    #      split, so rank-strided training shards never contain another rank's validation pixels ----
+    numpy.random.seed(1000 + rank)                                        # what separately started processes look like
+    seed = P.sync_split_seed()
+    assert isinstance(seed, int)
+    from hypelcnn_b200.common.sample_ops import shuffle_training_data_using_ratio, shuffle_training_data_using_size
+    samples = numpy.stack([numpy.arange(400), numpy.arange(400)[::-1], numpy.arange(400) % 5], axis=1)
+    train_a, val_a = shuffle_training_data_using_ratio(samples, 0.25)
+    train_b, val_b = shuffle_training_data_using_size(range(5), samples, 20, None)
+    Targets = namedtuple("Targets", ["targets"])
+    for tag, train, val in (("ratio", train_a, val_a), ("size", train_b, val_b)):
+        mine = P.shard_training_data(Targets(train), rank, world).targets
+        numpy.save(os.path.join(out_dir, f"split_{tag}_train_{rank}.npy"), mine)
+        numpy.save(os.path.join(out_dir, f"split_{tag}_val_{rank}.npy"), val)
+    # ---- stop decisions are collective ----
+    assert P.collective_any(rank == 1) is True and P.collective_any(False) is False
     dist.barrier()
     dist.destroy_process_group()
 
@@ -70,6 +86,14 @@ def test_two_rank_gradient_allreduce_and_sharding(tmp_path):
     parts = [numpy.load(tmp_path / f"targets_{r}.npy") for r in range(world)]
     assert [len(p) for p in parts] == [12, 11]
     assert numpy.array_equal(numpy.concatenate(parts), numpy.arange(23 * 3).reshape(23, 3))
+    for tag in ("ratio", "size"):
+        vals = [numpy.load(tmp_path / f"split_{tag}_val_{r}.npy") for r in range(world)]
+        trains = [numpy.load(tmp_path / f"split_{tag}_train_{r}.npy") for r in range(world)]
+        assert numpy.array_equal(vals[0], vals[1])                                   # one validation set
+        val_ids = set(vals[0][:, 0].tolist())
+        ids = [set(t[:, 0].tolist()) for t in trains]
+        assert not (ids[0] & ids[1]) and not ((ids[0] | ids[1]) & val_ids)           # disjoint shards, none in validation
+        assert len(ids[0]) == len(ids[1]) > 0
 
 
 def test_shard_range_properties():
