@@ -40,13 +40,33 @@ def sources():
 
 
 def build_native(force=False, verbose=False):
-    """Compile csrc/*.cu for sm_100a into lib/libhypelcnn_b200.so (nvcc cross-compiles without a GPU)."""
+    """Compile csrc/*.cu for sm_100a (one object per translation unit, in parallel; nvcc cross-compiles without a
+    GPU) and link lib/libhypelcnn_b200.so."""
+    from concurrent.futures import ThreadPoolExecutor
     srcs = sources()
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
         return LIB_PATH
     os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH, os.path.join(CSRC, "hyp_engine.cu")]
+    obj_dir = os.path.join(os.path.dirname(LIB_PATH), "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    headers = [s for s in srcs if not s.endswith(".cu")]
+    units = [s for s in srcs if s.endswith(".cu")]
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_unit(unit):
+        obj = os.path.join(obj_dir, os.path.basename(unit)[:-3] + ".o")
+        fresh = os.path.exists(obj) and all(os.path.getmtime(obj) >= os.path.getmtime(s) for s in [unit] + headers)
+        if force or not fresh:
+            cmd = [nvcc] + compile_flags + ["-c", "-o", obj, unit]
+            if verbose:
+                print(" ".join(cmd))
+            subprocess.run(cmd, check=True)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(units)) as pool:
+        objects = list(pool.map(compile_unit, units))
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + objects
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)

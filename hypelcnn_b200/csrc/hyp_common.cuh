@@ -83,6 +83,14 @@ struct Profiler {
 };
 extern thread_local Profiler g_prof;
 
+#define PROF(name, bytes, launch)             \
+  do {                                        \
+    ::hyp::g_prof.begin(st, name, 0.0, (double)(bytes)); \
+    launch;                                   \
+    ::hyp::g_prof.end(st);                           \
+    HYP_LAUNCHED();                           \
+  } while (0)
+
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -582,14 +582,6 @@ static double layer_flops(const Layer& L, int64_t B) {
   for (int k : L.ksizes) f += conv_flops(B, L.P, k, L.Cin, L.f);
   return f;
 }
-#define PROF(name, bytes, launch)             \
-  do {                                        \
-    g_prof.begin(st, name, 0.0, (double)(bytes)); \
-    launch;                                   \
-    g_prof.end(st);                           \
-    HYP_LAUNCHED();                           \
-  } while (0)
-
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static inline int ew_grid(int64_t total) { return (int)std::min<int64_t>(cdiv(total, 256), 148 * 16); }
 
@@ -1252,167 +1244,11 @@ int hyp_scatter_class_map(const uint8_t* pred, const int32_t* targets_xy, int64_
   return HYP_OK;
 }
 
-int hyp_scene_minmax(const void* cube, int dtype, int H, int W, int C, float* min_out, float* max_out, void* stream) {
-  HYP_CHECK_ARG(cube && min_out && max_out && H > 0 && W > 0 && C > 0, "bad argument");
-  HYP_CHECK_ARG(dtype == HYP_DT_F32 || dtype == HYP_DT_U16, "dtype must be f32 or u16");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  unsigned int* bits = nullptr;
-  HYP_CUDA(cudaMallocAsync(&bits, 2 * (size_t)C * sizeof(unsigned int), st));
-  HYP_CUDA(cudaMemsetAsync(bits, 0xff, (size_t)C * sizeof(unsigned int), st));
-  HYP_CUDA(cudaMemsetAsync(bits + C, 0x00, (size_t)C * sizeof(unsigned int), st));
-  const int64_t pixels = (int64_t)H * W;
-  const int ppb = (int)std::max<int64_t>(16, cdiv(pixels, 148 * 8));
-  const unsigned grid = (unsigned)cdiv(pixels, ppb);
-  const int threads = C >= 128 ? 128 : (C >= 64 ? 64 : 32);
-  if (dtype == HYP_DT_U16)
-    scene_min_kernel<unsigned short><<<grid, threads, 0, st>>>((const unsigned short*)cube, pixels, C, ppb, bits);
-  else
-    scene_min_kernel<float><<<grid, threads, 0, st>>>((const float*)cube, pixels, C, ppb, bits);
-  HYP_LAUNCHED();
-  decode_ordered_kernel<<<(unsigned)cdiv(C, 128), 128, 0, st>>>(bits, C, min_out);
-  HYP_LAUNCHED();
-  if (dtype == HYP_DT_U16)
-    scene_max_kernel<unsigned short><<<grid, threads, 0, st>>>((const unsigned short*)cube, pixels, C, ppb, min_out,
-                                                               bits + C);
-  else
-    scene_max_kernel<float><<<grid, threads, 0, st>>>((const float*)cube, pixels, C, ppb, min_out, bits + C);
-  HYP_LAUNCHED();
-  decode_ordered_kernel<<<(unsigned)cdiv(C, 128), 128, 0, st>>>(bits + C, C, max_out);
-  HYP_LAUNCHED();
-  HYP_CUDA(cudaFreeAsync(bits, st));
-  return HYP_OK;
-}
-
-int hyp_gather_patches(const void* casi, int casi_dtype, int Hc, int Wc, int C_hsi, const float* casi_min,
-                       const float* casi_max, const float* lidar, int Hl, int Wl, const float* lidar_minmax,
-                       int neighborhood, int mode, const int32_t* targets_xy, int64_t N, float* out, int out_ld,
-                       void* stream) {
-  HYP_CHECK_ARG(casi && targets_xy && out, "null argument");
-  HYP_CHECK_ARG(casi_dtype == HYP_DT_F32 || casi_dtype == HYP_DT_U16, "casi dtype must be f32 or u16");
-  HYP_CHECK_ARG(Hc > 0 && Wc > 0 && C_hsi > 0 && neighborhood >= 0 && N >= 0, "bad shape");
-  HYP_CHECK_ARG((casi_min == nullptr) == (casi_max == nullptr), "casi_min and casi_max go together");
-  HYP_CHECK_ARG(mode == HYP_GATHER_SAME_RES || mode == HYP_GATHER_GRSS2018, "unknown gather mode");
-  HYP_CHECK_ARG(!lidar || (Hl > 0 && Wl > 0), "bad lidar shape");
-  HYP_CHECK_ARG(mode != HYP_GATHER_GRSS2018 || lidar, "GRSS2018 mode needs the LiDAR raster");
-  HYP_CHECK_ARG(out_ld >= C_hsi + (lidar ? 1 : 0), "out_ld too small");
-  HYP_CHECK_ARG(neighborhood <= Hc && neighborhood <= Wc, "neighborhood larger than the scene");
-  HYP_CHECK_ARG(N <= INT32_MAX, "too many targets for one call");
-  if (N == 0) return HYP_OK;
-  GatherArgs a;
-  a.casi = casi; a.casi_u16 = casi_dtype == HYP_DT_U16; a.Hc = Hc; a.Wc = Wc; a.C = C_hsi;
-  a.cmin = casi_min; a.cmax = casi_max; a.lidar = lidar; a.Hl = Hl; a.Wl = Wl; a.lminmax = lidar_minmax;
-  a.nb = neighborhood; a.mode = mode; a.xy = targets_xy; a.N = N; a.out = out; a.out_ld = out_ld;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const double S2 = (double)(2 * neighborhood + 1) * (2 * neighborhood + 1);
-  const char* v2 = getenv("HYP_GATHER_V2");   // opt-in until measured against v1 (scripts/bench_gather.py)
-  const double gather_bytes = (double)N * S2 * (4.0 * out_ld + (casi_dtype == HYP_DT_U16 ? 2.0 : 4.0) * C_hsi + (lidar ? 4.0 : 0.0));
-  if (v2 && v2[0] == '1') {
-    PROF("gather_kernel_v2", gather_bytes, (gather_kernel_v2<<<(unsigned)N, 256, 0, st>>>(a)));
-  } else {
-    PROF("gather_kernel", gather_bytes, (gather_kernel<<<(unsigned)N, 256, 0, st>>>(a)));
-  }
-  return HYP_OK;
-}
-
 // ---- tensor-core building block probe (tests/test_gpu_tc.py) --------------------------------
 // mn = 0: A [M,K], B [N,K] row-major, D = A * B^T.   mn = 1: A [K,M], B [K,N], D = A^T * B.
 // Splits both operands into TF32 (hi, lo) planes, builds tensor maps and tile tables exactly
 // as the engine does, and runs tc_gemm_kernel.  ksplit > 1 (mn = 1 only) splits K over CTAs
 // that accumulate with atomics (D must be zeroed by the caller).
-// host-only: TIFF LZW (MSB-first codes of 9..12 bits, ClearCode 256, EndOfInformation 257, the code width grows one
-// code early) — the strips of compressed scene files (hypelcnn_b200/utilities/tiff_io.py; the reference reads them
-// through tifffile).  Table entries are (prefix code, last byte, length); a string is written back to front.
-int hyp_tiff_lzw_decode(const void* data, uint64_t len, void* out, uint64_t out_capacity, uint64_t* out_len) {
-  HYP_CHECK_ARG(out_len && (data || len == 0) && (out || out_capacity == 0), "null argument");
-  const uint8_t* src = static_cast<const uint8_t*>(data);
-  uint8_t* dst = static_cast<uint8_t*>(out);
-  static thread_local uint16_t prefix[4096];
-  static thread_local uint8_t last[4096], first[4096];
-  static thread_local uint32_t length[4096];
-  for (int i = 0; i < 256; i++) {
-    prefix[i] = 0xffff;
-    last[i] = first[i] = (uint8_t)i;
-    length[i] = 1;
-  }
-  uint64_t pos = 0, written = 0;
-  uint32_t buffer = 0;
-  int buffered = 0, width = 9, next = 258, previous = -1;
-  bool corrupt = false;
-  while (written < out_capacity) {
-    while (buffered < width && pos < len) {
-      buffer = (buffer << 8) | src[pos++];
-      buffered += 8;
-    }
-    if (buffered < width) break;
-    const int code = (int)((buffer >> (buffered - width)) & ((1u << width) - 1u));
-    buffered -= width;
-    if (code == 256) {  // ClearCode
-      width = 9;
-      next = 258;
-      previous = -1;
-      continue;
-    }
-    if (code == 257) break;  // EndOfInformation
-    if (previous < 0) {
-      if (code >= 256) { corrupt = true; break; }
-    } else {
-      if (code > next || next >= 4096) { corrupt = true; break; }
-      // new string = previous string + first byte of this code's string (of the previous one when the code is new)
-      prefix[next] = (uint16_t)previous;
-      first[next] = first[previous];
-      last[next] = (code < next) ? first[code] : first[previous];
-      length[next] = length[previous] + 1;
-      next++;
-    }
-    const uint32_t n = length[code];
-    const uint64_t room = out_capacity - written;
-    const uint32_t keep = n <= room ? n : (uint32_t)room;  // a string may run past the strip's last byte
-    int walk = code;
-    for (uint32_t k = n; k-- > 0;) {
-      if (k < keep) dst[written + k] = last[walk];
-      if (prefix[walk] != 0xffff) walk = prefix[walk];
-    }
-    written += keep;
-    previous = code;
-    if (next + 1 >= (1 << width) && width < 12) width++;
-  }
-  *out_len = written;
-  HYP_CHECK_ARG(!corrupt, "corrupt LZW stream");
-  return HYP_OK;
-}
-
-// host-only: CRC-32C (Castagnoli, reflected 0x82F63B78), slicing-by-8 — the checksum of the TFRecord framing
-// (importer/TFRecordImporter.py, utilities/tfrecord_writer.py read / write TFRecord files through TensorFlow)
-int hyp_crc32c(const void* data, uint64_t len, uint32_t* crc_inout) {
-  HYP_CHECK_ARG(crc_inout && (data || len == 0), "null argument");
-  static uint32_t table[8][256];
-  static bool ready = false;
-  if (!ready) {
-    for (uint32_t n = 0; n < 256; n++) {
-      uint32_t c = n;
-      for (int k = 0; k < 8; k++) c = (c & 1u) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
-      table[0][n] = c;
-    }
-    for (uint32_t n = 0; n < 256; n++)
-      for (int t = 1; t < 8; t++) table[t][n] = (table[t - 1][n] >> 8) ^ table[0][table[t - 1][n] & 0xffu];
-    ready = true;
-  }
-  const uint8_t* p = static_cast<const uint8_t*>(data);
-  uint32_t c = ~*crc_inout;
-  while (len >= 8) {
-    uint64_t w;
-    memcpy(&w, p, 8);
-    w ^= c;  // little-endian hosts (x86-64, aarch64)
-    c = table[7][w & 0xff] ^ table[6][(w >> 8) & 0xff] ^ table[5][(w >> 16) & 0xff] ^ table[4][(w >> 24) & 0xff] ^
-        table[3][(w >> 32) & 0xff] ^ table[2][(w >> 40) & 0xff] ^ table[1][(w >> 48) & 0xff] ^ table[0][w >> 56];
-    p += 8;
-    len -= 8;
-  }
-  while (len--) c = (c >> 8) ^ table[0][(c ^ *p++) & 0xffu];
-  *crc_inout = ~c;
-  return HYP_OK;
-}
-
 // host-only: the static tile schedule on a plain cost vector (tests/test_schedule.py)
 int hyp_debug_schedule(const double* costs, int units, int groups, int windowed, int32_t* group_of_unit,
                        int32_t* rank_in_group) {

@@ -949,173 +949,4 @@ __global__ void dropout_mask_kernel(uint64_t seed, uint32_t stream_id, int64_t n
   if (i < n) out[i] = philox_uniform(seed, stream_id, (uint64_t)i) < keep ? 1 : 0;
 }
 
-// ------------------------------------------------------------------------------------------
-// scene min / max(value - min): two passes over the cube, channel-coalesced
-template <typename T>
-__global__ void scene_min_kernel(const T* __restrict__ cube, int64_t pixels, int C, int pixels_per_block,
-                                 unsigned int* __restrict__ min_bits) {
-  // float order-preserving encoding so atomicMin on uint works for non-negative and negative values
-  const int64_t p0 = (int64_t)blockIdx.x * pixels_per_block;
-  const int64_t p1 = min(pixels, p0 + pixels_per_block);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float mn = INFINITY;
-    for (int64_t px = p0; px < p1; px++) mn = fminf(mn, (float)cube[px * C + c]);
-    unsigned int b = __float_as_uint(mn);
-    b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-    atomicMin(&min_bits[c], b);
-  }
-}
-template <typename T>
-__global__ void scene_max_kernel(const T* __restrict__ cube, int64_t pixels, int C, int pixels_per_block,
-                                 const float* __restrict__ mn, unsigned int* __restrict__ max_bits) {
-  const int64_t p0 = (int64_t)blockIdx.x * pixels_per_block;
-  const int64_t p1 = min(pixels, p0 + pixels_per_block);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float mx = -INFINITY;
-    const float lo = mn[c];
-    for (int64_t px = p0; px < p1; px++) mx = fmaxf(mx, (float)cube[px * C + c] - lo);
-    unsigned int b = __float_as_uint(mx);
-    b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-    atomicMax(&max_bits[c], b);
-  }
-}
-__global__ void decode_ordered_kernel(const unsigned int* __restrict__ bits, int C, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  unsigned int b = bits[c];
-  b = (b & 0x80000000u) ? (b & 0x7fffffffu) : ~b;
-  out[c] = __uint_as_float(b);
-}
-
-// ------------------------------------------------------------------------------------------
-// patch gather.  numpy "symmetric" padding == reflect with the edge repeated.
-__device__ __forceinline__ int reflect_sym(int i, int n) {
-  if (i < 0) i = -i - 1;
-  if (i >= n) i = 2 * n - 1 - i;
-  return i;
-}
-
-struct GatherArgs {
-  const void* casi;
-  int casi_u16;
-  int Hc, Wc, C;
-  const float* cmin;
-  const float* cmax;
-  const float* lidar;
-  int Hl, Wl;
-  const float* lminmax;
-  int nb, mode;
-  const int32_t* xy;
-  int64_t N;
-  float* out;
-  int out_ld;
-};
-
-// one block per patch; threads sweep (pixel, channel) with channel fastest -> coalesced
-__global__ void gather_kernel(const GatherArgs p) {
-  const int64_t n = blockIdx.x;
-  const int S = 2 * p.nb + 1;
-  const int x = p.xy[2 * n], y = p.xy[2 * n + 1];
-  int bx = x, by = y;
-  if (p.mode == HYP_GATHER_GRSS2018) {  // loader/GRSS2018DataLoader.py:23-29 (int() truncation)
-    bx = x / 2 + p.nb - p.nb / 2;
-    by = y / 2 + p.nb - p.nb / 2;
-  }
-  const int per_pixel = p.out_ld;
-  const int total = S * S * per_pixel;
-  float* op = p.out + (size_t)n * total;
-  const float lmin = p.lminmax ? p.lminmax[0] : 0.f, lmax = p.lminmax ? p.lminmax[1] : 1.f;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int pix = i / per_pixel, c = i - pix * per_pixel;
-    const int py = pix / S, px = pix - py * S;
-    float v = 0.f;
-    if (c < p.C) {
-      const int oy = (p.mode == HYP_GATHER_GRSS2018) ? py / 2 : py;
-      const int ox = (p.mode == HYP_GATHER_GRSS2018) ? px / 2 : px;
-      const int ry = reflect_sym(by + oy - p.nb, p.Hc), rx = reflect_sym(bx + ox - p.nb, p.Wc);
-      const size_t off = ((size_t)ry * p.Wc + rx) * p.C + c;
-      if (p.casi_u16) {
-        const unsigned short raw = reinterpret_cast<const unsigned short*>(p.casi)[off];
-        if (p.cmin) {
-          const unsigned short sh = (unsigned short)(raw - (unsigned short)p.cmin[c]);
-          v = __fdiv_rn((float)sh, p.cmax[c]);
-        } else {
-          v = (float)raw;
-        }
-      } else {
-        const float raw = reinterpret_cast<const float*>(p.casi)[off];
-        v = p.cmin ? __fdiv_rn(__fsub_rn(raw, p.cmin[c]), p.cmax[c]) : raw;
-      }
-    } else if (c == p.C && p.lidar) {
-      const int ry = reflect_sym(y + py - p.nb, p.Hl), rx = reflect_sym(x + px - p.nb, p.Wl);
-      const float raw = p.lidar[(size_t)ry * p.Wl + rx];
-      v = p.lminmax ? __fdiv_rn(__fsub_rn(raw, lmin), lmax) : raw;
-    }
-    op[i] = v;
-  }
-}
-
-// Same arithmetic as gather_kernel (bit-identical results), without the two integer divisions per element: the
-// (row, column, channel) position of a thread's element advances incrementally by the block's stride of 256 elements,
-// and four elements are in flight per thread.  Selected with HYP_GATHER_V2=1 until it has been measured against v1
-// on a B200 (scripts/bench_gather.py).
-__global__ void __launch_bounds__(256) gather_kernel_v2(const GatherArgs p) {
-  const int64_t n = blockIdx.x;
-  const int S = 2 * p.nb + 1;
-  const int x = p.xy[2 * n], y = p.xy[2 * n + 1];
-  int bx = x, by = y;
-  const bool half_res = p.mode == HYP_GATHER_GRSS2018;
-  if (half_res) {
-    bx = x / 2 + p.nb - p.nb / 2;
-    by = y / 2 + p.nb - p.nb / 2;
-  }
-  const int per_pixel = p.out_ld;
-  const int total = S * S * per_pixel;
-  float* op = p.out + (size_t)n * total;
-  const float lmin = p.lminmax ? p.lminmax[0] : 0.f, lmax = p.lminmax ? p.lminmax[1] : 1.f;
-  const int dpix = 256 / per_pixel, dc = 256 - dpix * per_pixel;   // 256 elements = dpix pixels + dc channels
-  int pix = threadIdx.x / per_pixel;
-  int c = threadIdx.x - pix * per_pixel;
-  int py = pix / S, px = pix - py * S;
-#pragma unroll 4
-  for (int i = threadIdx.x; i < total; i += 256) {
-    float v = 0.f;
-    if (c < p.C) {
-      const int oy = half_res ? py / 2 : py;
-      const int ox = half_res ? px / 2 : px;
-      const int ry = reflect_sym(by + oy - p.nb, p.Hc), rx = reflect_sym(bx + ox - p.nb, p.Wc);
-      const size_t off = ((size_t)ry * p.Wc + rx) * p.C + c;
-      if (p.casi_u16) {
-        const unsigned short raw = __ldg(reinterpret_cast<const unsigned short*>(p.casi) + off);
-        if (p.cmin) {
-          const unsigned short sh = (unsigned short)(raw - (unsigned short)__ldg(p.cmin + c));
-          v = __fdiv_rn((float)sh, __ldg(p.cmax + c));
-        } else {
-          v = (float)raw;
-        }
-      } else {
-        const float raw = __ldg(reinterpret_cast<const float*>(p.casi) + off);
-        v = p.cmin ? __fdiv_rn(__fsub_rn(raw, __ldg(p.cmin + c)), __ldg(p.cmax + c)) : raw;
-      }
-    } else if (c == p.C && p.lidar) {
-      const int ry = reflect_sym(y + py - p.nb, p.Hl), rx = reflect_sym(x + px - p.nb, p.Wl);
-      const float raw = __ldg(p.lidar + (size_t)ry * p.Wl + rx);
-      v = p.lminmax ? __fdiv_rn(__fsub_rn(raw, lmin), lmax) : raw;
-    }
-    op[i] = v;
-    c += dc;
-    int advance = dpix;
-    if (c >= per_pixel) {
-      c -= per_pixel;
-      ++advance;
-    }
-    px += advance;
-    if (px >= S) {
-      const int rows = px / S;
-      py += rows;
-      px -= rows * S;
-    }
-  }
-}
-
 }  // namespace hyp

@@ -90,3 +90,27 @@ def test_doubled_batch_equals_the_half_batch_step():
         worst = max(worst, rel)
         assert rel < 2e-3, (name, rel)
     assert worst > 0.0   # different tilings did run (bit-identical gradients would mean the same code path)
+
+
+def test_large_batch_gradients_match_the_oracle():
+    """Every variable gradient of a 1024-patch C2 step against autograd of the CPU oracle (fp64, with the fp32 oracle as
+    the yardstick of what fp32 arithmetic can deliver): the multi-tile plans of the bench size — 8 batch tiles per
+    position, K-split wgrads, CTA pairs — checked against something other than the engine itself."""
+    from tests.test_gpu_parity import CASES, engine_lrelu_gates
+    from tests.util import assert_grad_close
+    Bg = 1024
+    E, eng = _engine(Bg)
+    x, y = synthetic_batch(Bg, P, C, CLASSES, seed=21)
+    xd, yd = torch.as_tensor(x).cuda(), torch.as_tensor(y).cuda()
+    eng.forward(xd, True, True, seed=0)
+    case = dict(CASES["c2"], B=Bg)
+    gates = engine_lrelu_gates(eng, case, ALG0)
+    yt = torch.tensor(y.astype(numpy.int64))
+    loss_ref, g_ref, _ = R.loss_and_grads(oracle_variables(eng), torch.tensor(x, dtype=torch.float64), yt, CLASSES, ALG0,
+                                          lrelu_gates=gates)
+    _, g_ref32, _ = R.loss_and_grads(oracle_variables(eng, torch.float32), torch.tensor(x), yt, CLASSES, ALG0,
+                                     lrelu_gates=gates)
+    loss = eng.loss_backward(xd, yd).cpu().numpy()
+    assert abs(loss[0] - loss_ref.item()) <= RTOL * abs(loss_ref.item()) + ATOL
+    for name in reversed([n for n in eng.variables if "moving_" not in n]):
+        assert_grad_close(eng.gradient(name).cpu().numpy(), g_ref[name].numpy(), g_ref32[name].numpy(), f"grad {name}")

@@ -79,6 +79,60 @@ def test_gather_vs_oracle_grss2018_shape(E):
     assert got.shape == (200, 11, 11, 49) and numpy.array_equal(got, ref)
 
 
+def test_gather_division_is_ieee_exact_for_every_uint16_value(E):
+    """The vector gather divides (raw - min) by max with a reciprocal + one corrected FMA step instead of an IEEE
+    division; for integer operands below 2^16 that is exact.  Checked exhaustively: for eight divisors (among them the
+    extremes 1 and 65535) every dividend 0..max, against numpy's correctly rounded float32 division."""
+    rng = numpy.random.default_rng(11)
+    maxima = [1, 3, 1000, 4095, 12345, 16383, 40000, 65535]
+    offsets = [0, 7, 64535, 0, 50000, 1, 25535, 0]
+    casi = numpy.empty((256, 256, 8), numpy.uint16)
+    for c, (m, o) in enumerate(zip(maxima, offsets)):
+        values = numpy.arange(65536, dtype=numpy.int64) % (m + 1) + o
+        casi[:, :, c] = rng.permutation(values).reshape(256, 256).astype(numpy.uint16)
+    ys, xs = numpy.divmod(numpy.arange(65536), 256)
+    pts = numpy.stack([xs, ys], 1)
+    got = _gather_case(E, casi, None, 0, pts, 0).reshape(256, 256, 8)
+    lo = casi.reshape(-1, 8).min(axis=0)
+    want = (casi - lo).astype(numpy.float32) / (casi.reshape(-1, 8).max(axis=0) - lo).astype(numpy.float32)
+    assert numpy.array_equal(got, want)
+
+
+def test_gather_vector_kernel_equals_the_scalar_kernel(E, monkeypatch):
+    """Same targets through gather_rows_kernel (128-bit loads, shared-memory patch image, 128-bit streaming stores) and
+    through the element-wise gather_kernel: bit-identical, for every 16-byte phase a patch can start at, with a padded
+    output row (out_ld > C + 1: padding channels are zero), at the scene border, in both gather modes."""
+    rng = numpy.random.default_rng(5)
+    for mode, (Hc, Wc, C, n, dtype) in ((0, (33, 47, 144, 3, numpy.uint16)), (0, (20, 31, 64, 1, numpy.uint16)),
+                                        (1, (26, 30, 48, 5, numpy.float32)), (0, (12, 9, 8, 4, numpy.float32))):
+        casi = (rng.integers(0, 16384, (Hc, Wc, C)).astype(dtype) if dtype == numpy.uint16
+                else rng.random((Hc, Wc, C)).astype(numpy.float32))
+        Hl, Wl = (2 * Hc, 2 * Wc) if mode == 1 else (Hc, Wc)
+        lidar = (rng.random((Hl, Wl)) * 40).astype(numpy.float32)
+        pts = numpy.stack([rng.integers(0, Wl, 203), rng.integers(0, Hl, 203)], 1).astype(numpy.int32)
+        pts[:4] = [[0, 0], [Wl - 1, Hl - 1], [0, Hl - 1], [Wl - 1, 0]]
+        casi_d, lidar_d, pts_d = dev(casi), dev(lidar), dev(pts)
+        cmin, cmax = E.scene_minmax(casi_d)
+        lmin, lmax = E.scene_minmax(lidar_d.view(Hl, Wl, 1))
+        lmm = torch.cat([lmin, lmax])
+        S = 2 * n + 1
+        for ld in (C + 1, C + 4):
+            outs = []
+            for scalar in ("1", "0"):
+                monkeypatch.setenv("HYP_GATHER_SCALAR", scalar)
+                out = torch.full((203, S, S, ld), -7.0, dtype=torch.float32, device="cuda")
+                E.gather_patches(casi_d, lidar_d, n, pts_d, cmin, cmax, lmm, mode, out)
+                outs.append(out.cpu().numpy())
+            assert numpy.array_equal(outs[0], outs[1]), (mode, C, ld)
+            assert (outs[1][..., C + 1:] == 0).all()
+        raw = [None, None]
+        for i, scalar in enumerate(("1", "0")):                          # un-normalised, no LiDAR
+            monkeypatch.setenv("HYP_GATHER_SCALAR", scalar)
+            if mode == 0:
+                raw[i] = E.gather_patches(casi_d, None, n, pts_d).cpu().numpy()
+        assert mode == 1 or numpy.array_equal(raw[0], raw[1])
+
+
 def test_gather_rejects_bad_arguments(E):
     from hypelcnn_b200 import NativeError
     casi = dev(numpy.zeros((4, 4, 3), numpy.float32))
@@ -116,6 +170,11 @@ CASES = {
     "c5": dict(P=3, C=65, classes=11, alg=ALG, B=32),
     "c2": dict(P=7, C=145, classes=15, alg=ALG, B=16),
     "nonres": dict(P=5, C=20, classes=6, alg={**ALG, "filter_count": 64, "use_residual": False}, B=20),
+    # BASELINE configs[2] (GRSS2018 shape): 11x11 patches -> kernel sizes 1..11 (6 slots per level, K up to 43 560 in the
+    # level GEMMs), fc_0 10 890 x 3 630, four FC stages.  49 = the reference loader's 48 HSI + 1 LiDAR channel
+    # (loader/GRSS2018DataLoader.py:20-21,53-54), 51 = BASELINE's 48 + 3 LiDAR variant.
+    "c3": dict(P=11, C=49, classes=20, alg=ALG, B=16),
+    "c3_51": dict(P=11, C=51, classes=20, alg=ALG, B=16),
 }
 
 
@@ -157,7 +216,7 @@ def engine_lrelu_gates(eng, c, alg):
     return gates
 
 
-@pytest.mark.parametrize("case", ["tiny", "c5", "nonres", "c2"])
+@pytest.mark.parametrize("case", ["tiny", "c5", "nonres", "c2", "c3", "c3_51"])
 def test_variable_table_matches_reference_names(E, case, prec):
     eng, alg, c, x, y = _make(E, case, precision=prec)
     specs = R.variable_specs(c["P"], c["C"], c["classes"], alg)
@@ -167,9 +226,13 @@ def test_variable_table_matches_reference_names(E, case, prec):
     assert eng.trainable_count == sum(int(numpy.prod(s)) for _, s, k in specs if k in ("weights", "beta"))
     if case == "c2":
         assert eng.trainable_count == 8160297
+    if case == "c3":
+        assert eng.trainable_count == 54407798
+    if case == "c3_51":
+        assert eng.trainable_count == 54538960
 
 
-@pytest.mark.parametrize("case", ["tiny", "c5", "nonres", "c2"])
+@pytest.mark.parametrize("case", ["tiny", "c5", "nonres", "c2", "c3", "c3_51"])
 def test_forward_training_parity_per_layer(E, case, prec):
     eng, alg, c, x, y = _make(E, case, precision=prec)
     v = oracle_variables(eng)
@@ -226,7 +289,7 @@ def test_forward_eval_parity(E, case, prec):
         eng.forward(dev(x[:1]), True)
 
 
-@pytest.mark.parametrize("case", ["tiny", "c5", "nonres", "c2"])
+@pytest.mark.parametrize("case", ["tiny", "c5", "nonres", "c2", "c3"])
 def test_loss_and_gradient_parity(E, case, prec):
     eng, alg, c, x, y = _make(E, case, precision=prec)
     v = oracle_variables(eng)
