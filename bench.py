@@ -28,11 +28,17 @@ ALG = {"batch_size": 4096, "drop_out_ratio": 0.70, "filter_count": 480, "learnin
        "spectral_hierarchy_level": 3, "spatial_hierarchy_level": 3, "degradation_coeff": 3, "use_residual": True}
 WORKLOADS = {  # name -> (patch, channels, classes)
     "c2_grss2013": (7, 145, 15),
-    "c3_grss2018": (11, 49, 20),
+    "c3_grss2018": (11, 49, 20),          # the reference loader's shape: 48 HSI + 1 LiDAR (GRSS2018DataLoader.py:20-21,53-54)
+    "c3_grss2018_51": (11, 51, 20),       # BASELINE.json configs[2] as written: 48 HSI + 3 LiDAR
     "c5_gulfport": (3, 65, 11),
 }
+SCENES = {"c2_grss2013": (349, 1905, 144), "c3_grss2018": (601, 2384, 48), "c5_gulfport": (325, 220, 64)}
+GATHER_WORKLOADS = {  # name -> (H, W, bands, neighborhood, gather mode): S-gather of SURVEY §8d
+    "gather_c2": (349, 1905, 144, 3, 0),
+    "gather_c3": (601, 2384, 48, 5, 1),
+}
 METRIC = "HSI+LiDAR patches/sec fwd+bwd (HYPELCNN, GRSS2013 shape)"
-FWD_BWD_MFLOP = {"c2_grss2013": 469.8, "c3_grss2018": 3550.3, "c5_gulfport": 37.0}  # SURVEY §8d, per patch
+FWD_BWD_MFLOP = {"c2_grss2013": 469.8, "c3_grss2018": 3550.3, "c3_grss2018_51": 3551.1, "c5_gulfport": 37.0}  # SURVEY §8d, per patch
 
 
 def measured_peaks():
@@ -230,9 +236,44 @@ def run_native(args):
         t = torch.tensor([ems], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ems = t.item()
-    e2e = {"value": world * B * args.steps / (ems / 1e3), "unit": "patches/s",
-           "h2d_bytes_per_step": host_x[0].numel() * 4 + host_y[0].numel(), "d2h_bytes_per_step": 12,
-           "ms_per_step": ems / args.steps, "api": "common_nn_ops.HostBatchTrainer.step (optimize_nn equivalent; next batch's H2D prefetched on a copy stream)"}
+    e2e_patches = {"value": world * B * args.steps / (ems / 1e3), "unit": "patches/s",
+                   "h2d_bytes_per_step": host_x[0].numel() * 4 + host_y[0].numel(), "d2h_bytes_per_step": 12,
+                   "ms_per_step": ems / args.steps,
+                   "api": "common_nn_ops.HostBatchTrainer.step: the host hands in B pre-cut fp32 patches per step (next "
+                          "batch's H2D prefetched on a copy stream)"}
+    e2e = e2e_patches
+    if args.workload in SCENES and args.model == "hypelcnn" and args.e2e_input == "targets":
+        # the scene is resident in HBM (what InMemoryImporter amounts to on a 180 GB device); per step the host hands in
+        # the TARGET LIST (x, y, class) of the batch: H2D 12 B per patch, patch gather on the device, train step, D2H loss
+        H, W, bands = SCENES[args.workload]
+        mode = N.HYP_GATHER_GRSS2018 if args.workload == "c3_grss2018" else N.HYP_GATHER_SAME_RES
+        srng = numpy.random.default_rng(4321)
+        casi = torch.from_numpy(srng.integers(0, 16384, (H, W, bands)).astype(numpy.uint16)).cuda()
+        Hl, Wl = (2 * H, 2 * W) if mode == N.HYP_GATHER_GRSS2018 else (H, W)
+        lidar = torch.from_numpy((srng.random((Hl, Wl)) * 50).astype(numpy.float32)).cuda()
+        host_t = [torch.from_numpy(numpy.stack([rng.integers(0, Wl, B), rng.integers(0, Hl, B), rng.integers(0, classes, B)],
+                                               1).astype(numpy.int32)).pin_memory() for _ in range(nb)]
+        strainer = ops.SceneBatchTrainer(eng, casi, lidar, P // 2, mode, allreduce=ar)
+        for i in range(2):
+            strainer.step(host_t[i % nb])
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            host_loss = strainer.step(host_t[i % nb])
+        e1.record()
+        barrier()
+        tms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([tms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tms = t.item()
+        e2e = {"value": world * B * args.steps / (tms / 1e3), "unit": "patches/s",
+               "h2d_bytes_per_step": host_t[0].numel() * 4, "d2h_bytes_per_step": 12, "ms_per_step": tms / args.steps,
+               "api": "common_nn_ops.SceneBatchTrainer.step: scene resident in HBM, the host hands in the step's int32 "
+                      "(x, y, class) target list; gather + optimize_nn step + loss read-back inside the timed region",
+               "with_host_patches": e2e_patches}
+        del casi, lidar
 
     if rank != 0:
         if world > 1:
@@ -309,13 +350,134 @@ def run_native(args):
         dist.destroy_process_group()
 
 
+def run_gather(args):
+    """--workload gather_c2 / gather_c3: the patch gather alone (the kernel that replaces InMemoryImporter's per-pixel
+    window slice).  A step = one hyp_gather_patches call over `--batch` random targets of the resident scene."""
+    import torch
+    import torch.distributed as dist
+    from hypelcnn_b200 import _native as N
+    from hypelcnn_b200 import engine as E
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    H, W, bands, nbh, mode = GATHER_WORKLOADS[args.workload]
+    B = args.batch
+    S = 2 * nbh + 1
+    rng = numpy.random.default_rng(1234 + rank)
+    casi = torch.from_numpy(rng.integers(0, 16384, (H, W, bands)).astype(numpy.uint16)).cuda()
+    Hl, Wl = (2 * H, 2 * W) if mode == 1 else (H, W)
+    lidar = torch.from_numpy((rng.random((Hl, Wl)) * 50).astype(numpy.float32)).cuda()
+    cmin, cmax = E.scene_minmax(casi)
+    lmin, lmax = E.scene_minmax(lidar.view(Hl, Wl, 1))
+    lmm = torch.cat([lmin, lmax]).contiguous()
+    nb = 8                                                  # rotating output buffers: 8 x B patches >> 126 MB L2 at B >= 4096
+    host_t = [torch.from_numpy(numpy.stack([rng.integers(0, Wl, B), rng.integers(0, Hl, B)], 1).astype(numpy.int32)).pin_memory()
+              for _ in range(nb)]
+    dev_t = [t.cuda() for t in host_t]
+    outs = [torch.empty((B, S, S, bands + 1), dtype=torch.float32, device="cuda") for _ in range(nb)]
+    bytes_per_patch = S * S * (4 * (bands + 1) + 2 * bands + 4)     # fp32 written + uint16 HSI read + fp32 LiDAR read
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather(i, targets):
+        E.gather_patches(casi, lidar, nbh, targets, cmin, cmax, lmm, mode, outs[i % nb])
+
+    for i in range(args.warmup):
+        gather(i, dev_t[i % nb])
+    barrier()
+    N.lib().hyp_launch_count(1)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        gather(i, dev_t[i % nb])
+    ev1.record()
+    barrier()
+    clocks = sampler.result()
+    launches = int(N.lib().hyp_launch_count(0))
+    ms = ev0.elapsed_time(ev1)
+    # per-launch durations (CUDA events around each launch) for the roofline object
+    N.check(N.lib().hyp_profile_enable(1 if rank == 0 else 0))
+    for i in range(args.steps):
+        gather(i, dev_t[i % nb])
+    barrier()
+    prof = profile_table(N) if rank == 0 else {}
+    N.lib().hyp_profile_enable(0)
+    # end to end: pinned host target list -> H2D -> gather -> 4-byte completion token back on the host
+    dev_in = torch.empty((B, 2), dtype=torch.int32, device="cuda")
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        dev_in.copy_(host_t[i % nb], non_blocking=True)
+        gather(i, dev_in)
+        token = outs[i % nb].view(-1)[-1:].cpu()
+    e1.record()
+    barrier()
+    ems = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms, ems], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ems = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = measured_peaks()
+    kname = max(prof, key=lambda k: prof[k]["ms"])
+    d = prof[kname]
+    achieved = d["bytes"] / (d["ms"] / 1e3) / 1e9
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline and mode == 0:
+        from oracle import dataset_ref as D                        # the checker, timed as the CPU baseline
+        scene = D.SceneRef(casi.cpu().numpy().copy(), lidar.cpu().numpy()[:, :, None].copy(), nbh, True)
+        n_cpu = min(B, 8192)
+        pts = numpy.concatenate([host_t[0].numpy()[:n_cpu], numpy.zeros((n_cpu, 1), numpy.int32)], 1)
+        t0 = time.perf_counter()
+        ref, _ = D.gather_patches(scene, pts)
+        dt = time.perf_counter() - t0
+        gather(0, dev_t[0])
+        assert numpy.array_equal(outs[0][:n_cpu].cpu().numpy(), ref), "device gather differs from the oracle"
+        cpu = {"value": n_cpu / dt, "unit": "patches/s", "cores": 1, "kind": "port",
+               "sample": f"{n_cpu} window slices in numpy (oracle/dataset_ref.py, the reference's per-pixel get_data_point "
+                         f"loop); pad + normalisation of the scene not timed ({dt:.2f} s)"}
+    line = {
+        "metric": "HSI+LiDAR patches/sec gathered from the resident scene", "value": world * B * args.steps / (ms / 1e3),
+        "unit": "patches/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16->f32", "data": "synthetic",
+        "config": {"workload": args.workload, "scene": [H, W, bands], "neighborhood": nbh, "targets_per_step": B,
+                   "l2": f"outputs rotate over {nb} buffers of {B * bytes_per_patch / 1e6:.0f} MB; the scene "
+                         f"({casi.numel() * 2 / 1e6:.0f} MB) is larger than L2"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "kernel": kname,
+                     "algorithmic_bytes_per_launch": d["bytes"] / d["launches"], "avg_launch_ms": d["ms"] / d["launches"],
+                     "bytes_per_patch": bytes_per_patch, "peak_source": f"{peaks['source']} copy bandwidth"},
+        "cpu_baseline": cpu,
+        "e2e": {"value": world * B * args.steps / (ems / 1e3), "unit": "patches/s", "h2d_bytes_per_step": B * 8,
+                "d2h_bytes_per_step": 4, "ms_per_step": ems / args.steps,
+                "api": "engine.gather_patches on a pinned host target list; the patches stay in HBM for the model, a "
+                       "4-byte token of the result is read back"},
+        "clocks": clocks, "gpu_launches": launches,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="c2_grss2013", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2_grss2013", choices=sorted(WORKLOADS) + sorted(GATHER_WORKLOADS))
     ap.add_argument("--batch", type=int, default=4096, help="patches per GPU per step")
     ap.add_argument("--ref-batch", type=int, default=256, help="patches per step of the CPU arm (bounded sample)")
     ap.add_argument("--input-batches", type=int, default=4)
@@ -323,6 +485,9 @@ def main():
                     help="3xtf32: tcgen05 tensor-core engine (fp32-accurate split); fp32: FFMA engine")
     ap.add_argument("--model", default="hypelcnn", choices=["hypelcnn", "dualcnn"],
                     help="hypelcnn = the headline metric; dualcnn = BASELINE configs[0] on the same engine (no CPU arm)")
+    ap.add_argument("--e2e-input", default="targets", choices=["targets", "patches"],
+                    help="what the host hands in per e2e step: the (x, y, class) target list against the HBM-resident "
+                         "scene (default) or pre-cut fp32 patches (reported as e2e.with_host_patches either way)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: one blocking all-reduce after backward instead "
                     "of reducing the FC/decoder gradients while the conv layers are still going backward")
@@ -331,7 +496,12 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3
-    if args.impl == "reference":
+    if args.workload in GATHER_WORKLOADS:
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the gather's CPU arm is the cpu_baseline of the native line"}))
+            return
+        run_gather(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_native(args)

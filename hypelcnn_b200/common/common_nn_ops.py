@@ -352,6 +352,38 @@ class HostBatchTrainer:
         return loss.cpu()  # synchronises: the step's result is on the host
 
 
+class SceneBatchTrainer:
+    """The same end-to-end step when the scene lives in HBM (what InMemoryImporter amounts to here): the host hands in
+    the step's TARGET LIST — int32 [B, 3] = (x, y, class), the rows of the reference's sample sets
+    (loader/DataLoader.py:5-47) — instead of B pre-cut patches.  H2D copy of the list (12 B per patch instead of
+    P*P*C*4), patch gather from the resident scene (hyp_gather_patches), one optimize_nn step, D2H read of the loss."""
+
+    def __init__(self, engine, casi, lidar, neighborhood, mode=0, allreduce=None):
+        self.engine, self.allreduce = engine, allreduce
+        self.casi, self.lidar, self.neighborhood, self.mode = casi, lidar, neighborhood, mode
+        self.cmin, self.cmax = E.scene_minmax(casi)
+        self.lmm = None
+        if lidar is not None:
+            lmin, lmax = E.scene_minmax(lidar.reshape(lidar.shape[0], lidar.shape[1], 1))
+            self.lmm = torch.cat([lmin, lmax]).contiguous()
+        self._targets = self._patches = None
+
+    def step(self, host_targets):
+        n = host_targets.shape[0]
+        if self._targets is None or self._targets.shape[0] != n:
+            S = 2 * self.neighborhood + 1
+            channels = self.casi.shape[2] + (0 if self.lidar is None else 1)
+            self._targets = torch.empty((n, 3), dtype=torch.int32, device=self.engine.device)
+            self._patches = torch.empty((n, S, S, channels), dtype=torch.float32, device=self.engine.device)
+        self._targets.copy_(host_targets, non_blocking=True)
+        xy = self._targets[:, :2].contiguous()
+        labels = self._targets[:, 2].to(torch.uint8)
+        E.gather_patches(self.casi, self.lidar, self.neighborhood, xy, self.cmin, self.cmax, self.lmm, self.mode,
+                         self._patches)
+        loss = self.engine.train_step(self._patches, labels, allreduce=self.allreduce)
+        return loss.cpu()  # synchronises: the step's result is on the host
+
+
 class MetricOpsHolder:
     """create_metric_tensors (:243-277): streaming accuracy / mean-per-class accuracy / kappa and
     an int32 confusion accumulator, all derived from the device-side confusion matrix."""

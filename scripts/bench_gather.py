@@ -1,7 +1,8 @@
 """Patch-gather throughput on the S-gather inputs of SURVEY §8d: GRSS2013-shaped scene (349 x 1905 x 144 uint16 + LiDAR),
 neighborhood 3, (i) 4 096 random targets, (ii) every pixel of the scene in batches; GRSS2018-shaped variant with
 --grss2018.  Reports patches/s and GB/s = algorithmic bytes (28 420 B written + the same read per C2 patch) / CUDA-event
-time, for gather_kernel and — bit-compared against it — gather_kernel_v2 (HYP_GATHER_V2=1).  One B200:
+time, for the element-wise gather_kernel ("v1", HYP_GATHER_SCALAR=1) and — bit-compared against it — the vector
+gather_rows_kernel ("v2", the default).  One B200:
     python scripts/bench_gather.py [--grss2018] [--reps 20]
 Under ncu: ncu --set full -k regex:gather_kernel -c 4 python scripts/bench_gather.py --reps 1"""
 import argparse
@@ -64,12 +65,12 @@ results = {}
 out = torch.empty((min(args.scene_batch, scene_targets.shape[0]), S, S, C + 1), dtype=torch.float32, device="cuda")
 reference_out = None
 for version in {"v1": ("0",), "v2": ("1",), None: ("0", "1")}[args.only]:
-    os.environ["HYP_GATHER_V2"] = version
+    os.environ["HYP_GATHER_SCALAR"] = "1" if version == "0" else "0"
     got = E.gather_patches(casi, lidar, nb, random_targets, cmin, cmax, lmm, mode).clone()
     if reference_out is None:
         reference_out = got
     else:
-        assert torch.equal(got, reference_out), "gather_kernel_v2 differs from gather_kernel"
+        assert torch.equal(got, reference_out), "gather_rows_kernel differs from gather_kernel"
     timed(random_targets, out, 3)                                     # warm-up
     for name, targets, reps in (("random_4096", random_targets, args.reps),
                                 ("whole_scene", scene_targets, max(1, args.reps // 10))):
@@ -78,7 +79,7 @@ for version in {"v1": ("0",), "v2": ("1",), None: ("0", "1")}[args.only]:
         results[f"{'v2' if version == '1' else 'v1'}_{name}"] = {
             "ms": ms, "patches_per_s": n / ms * 1e3, "GB_per_s": n * bytes_per_patch / ms / 1e6,
             "launches": -(-n // args.scene_batch)}
-os.environ["HYP_GATHER_V2"] = "0"
+os.environ["HYP_GATHER_SCALAR"] = "0"
 cpu = None
 if args.cpu_patches and not args.grss2018 and args.only is None:
     import time
