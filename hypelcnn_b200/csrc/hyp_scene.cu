@@ -119,17 +119,22 @@ __global__ void gather_kernel(const GatherArgs p) {
 // C % 4 == 0 for fp32 -- every scene of the reference: 144, 48, 64 bands).
 //
 //   * a block owns one patch at a time (persistent, grid-stride over the target list);
-//   * phase 1: thread (row slot, chunk) loads ONE 16-byte chunk (8 uint16 / 4 fp32 bands) of a window pixel with a
-//     128-bit read-only load, normalises it and puts the fp32 values into the patch image in shared memory.  A thread
-//     keeps the same chunk for the whole kernel, so its bands' min / max / reciprocal live in registers;
+//   * phase 1: thread (chunk, row slot) loads ONE 16-byte chunk (8 uint16 / 4 fp32 bands) of a window pixel with a
+//     128-bit read-only load -- four pixels in flight per thread --, normalises it and puts the fp32 values into the
+//     patch image in shared memory.  A thread keeps the same chunk for the whole kernel, so its bands' constants live
+//     in registers; neighbouring lanes hold neighbouring PIXELS of the same chunk, i.e. shared-memory addresses one
+//     output row (C + 1 floats, odd for every scene of the reference) apart: conflict-free scalar stores;
 //   * phase 2: the patch image leaves as one flat stream of 16-byte streaming stores.  A patch of (2n+1)^2 * (C+1)
 //     floats starts at any 4-byte phase of a 16-byte line, so the image sits in shared memory at the same phase
 //     (`shift`) and only the first / last vector of a patch is written element-wise.
 //
-// Arithmetic is bit-identical to gather_kernel / the numpy reference: uint16 bands are (raw - min) as an exact integer,
-// then an IEEE-correct division by max.  For integer max in [1, 65535] (what scene_minmax returns for uint16 cubes) the
-// division is q = a * r, q' = fma(fma(-q, b, a), r, q) with r = RN(1 / b): Markstein's correction, exact for these
-// operands (a, b integers below 2^16, no all-ones significand); any other max takes __fdiv_rn.
+// Arithmetic is bit-identical to gather_kernel / the numpy reference for every valid scene: uint16 bands are
+// (raw - min), an exact integer (computed in fp32 through the 2^23 exponent trick: both operands are integers below
+// 2^16; casi_min must not exceed the band's minimum, which hyp_scene_minmax guarantees), then an IEEE-correct division
+// by max.  For integer max in [1, 65535] (what hyp_scene_minmax returns for uint16 cubes) the division is
+// q = a * r, q' = fma(fma(-q, b, a), r, q) with r = RN(1 / b): Markstein's correction, exact for these operands
+// (integers below 2^16, no all-ones significand; tests/test_gpu_parity.py checks every dividend for eight divisors);
+// a chunk with any other max takes __fdiv_rn.
 template <typename T>
 struct ChunkOf;
 template <>
@@ -138,33 +143,101 @@ template <>
 struct ChunkOf<float> { static constexpr int N = 4; };
 
 constexpr int GATHER_THREADS = 256;
+constexpr int GATHER_UNROLL = 2;  // window pixels in flight per thread
 
 template <typename T>
-__global__ void __launch_bounds__(GATHER_THREADS) gather_rows_kernel(const GatherArgs p) {
+__device__ __forceinline__ void gather_convert(const uint4 raw, const float (&bias)[ChunkOf<T>::N],
+                                               const float (&cmx)[ChunkOf<T>::N], const float (&rcp)[ChunkOf<T>::N],
+                                               bool normalize, bool fast, float (&v)[ChunkOf<T>::N]) {
+  constexpr int EPC = ChunkOf<T>::N;
+  if (sizeof(T) == 2) {
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int j = 0; j < EPC; j++) {
+      // 0x4B000000 | r16 is the float 2^23 + r16: one byte permute builds it, one subtraction removes 2^23 + min
+      const uint32_t bits = __byte_perm(w[j >> 1], 0x4B000000u, (j & 1) ? 0x7632 : 0x7610);
+      const float a = __uint_as_float(bits) - bias[j];
+      const float q = a * rcp[j];
+      v[j] = normalize ? __fmaf_rn(__fmaf_rn(-q, cmx[j], a), rcp[j], q) : a;
+    }
+    if (!fast && normalize) {  // a divisor outside the proven range: rare, per thread
+#pragma unroll
+      for (int j = 0; j < EPC; j++) {
+        const uint32_t bits = __byte_perm(w[j >> 1], 0x4B000000u, (j & 1) ? 0x7632 : 0x7610);
+        v[j] = __fdiv_rn(__uint_as_float(bits) - bias[j], cmx[j]);
+      }
+    }
+  } else {
+    const float f[4] = {__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), __uint_as_float(raw.w)};
+#pragma unroll
+    for (int j = 0; j < EPC; j++) v[j] = normalize ? __fdiv_rn(__fsub_rn(f[j & 3], bias[j]), cmx[j]) : f[j & 3];
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void gather_phase1(const GatherArgs& p, const T* __restrict__ casi, float* __restrict__ img, int bx,
+                                              int by, int chunk, int slot, int rows_per_iter,
+                                              const float (&bias)[ChunkOf<T>::N], const float (&cmx)[ChunkOf<T>::N],
+                                              const float (&rcp)[ChunkOf<T>::N], bool fast) {
+  constexpr int EPC = ChunkOf<T>::N;
+  const int S = 2 * p.nb + 1, npix = S * S, ld = p.out_ld;
+  const bool half_res = p.mode == HYP_GATHER_GRSS2018, normalize = p.cmin != nullptr;
+  const int dy = rows_per_iter / S, dx = rows_per_iter - dy * S;  // one step of rows_per_iter pixels in (row, column)
+  int py = slot / S, px = slot - py * S;
+  for (int pix = slot; pix < npix; pix += GATHER_UNROLL * rows_per_iter) {
+    uint4 raw[GATHER_UNROLL];
+    int at[GATHER_UNROLL];
+#pragma unroll
+    for (int u = 0; u < GATHER_UNROLL; u++) {
+      at[u] = pix + u * rows_per_iter;
+      if (at[u] < npix) {
+        const int ry = reflect_sym(by + (half_res ? py / 2 : py) - p.nb, p.Hc);
+        const int rx = reflect_sym(bx + (half_res ? px / 2 : px) - p.nb, p.Wc);
+        raw[u] = __ldg(reinterpret_cast<const uint4*>(casi + ((size_t)ry * p.Wc + rx) * p.C) + chunk);
+      }
+      py += dy;
+      px += dx;
+      if (px >= S) { px -= S; py++; }
+    }
+#pragma unroll
+    for (int u = 0; u < GATHER_UNROLL; u++) {
+      if (at[u] < npix) {
+        float v[EPC];
+        gather_convert<T>(raw[u], bias, cmx, rcp, normalize, fast, v);
+        float* const dst = img + at[u] * ld + chunk * EPC;
+#pragma unroll
+        for (int j = 0; j < EPC; j++) dst[j] = v[j];
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(GATHER_THREADS, 4) gather_rows_kernel(const GatherArgs p) {
   constexpr int EPC = ChunkOf<T>::N;
   extern __shared__ float4 gather_smem4[];
   float* const sm = reinterpret_cast<float*>(gather_smem4);
   const int S = 2 * p.nb + 1, ld = p.out_ld, total = S * S * ld, npix = S * S;
   const int nchunks = p.C / EPC;
   const int rows_per_iter = GATHER_THREADS / nchunks;
-  const int chunk = (int)threadIdx.x % nchunks, slot = (int)threadIdx.x / nchunks;
+  // neighbouring lanes: neighbouring window pixels of one chunk
+  const int chunk = (int)threadIdx.x / rows_per_iter, slot = (int)threadIdx.x - chunk * rows_per_iter;
+  const bool active = chunk < nchunks;
   const bool half_res = p.mode == HYP_GATHER_GRSS2018;
   const bool normalize = p.cmin != nullptr;
   const int n_out_c = p.C + (p.lidar ? 1 : 0);
-  // this thread's bands
-  float cmn[EPC], cmx[EPC], rcp[EPC];
-  unsigned short cmn16[EPC];
-  bool fast = true;
+  // this thread's bands: bias = what is subtracted from the raw value (+ 2^23 for the uint16 exponent trick)
+  float bias[EPC], cmx[EPC], rcp[EPC];
+  bool fast = sizeof(T) == 2;
 #pragma unroll
   for (int j = 0; j < EPC; j++) {
-    const int c = chunk * EPC + j;
-    cmn[j] = normalize ? __ldg(p.cmin + c) : 0.f;
+    const int c = (active ? chunk : 0) * EPC + j;
+    const float mn = normalize ? __ldg(p.cmin + c) : 0.f;
     cmx[j] = normalize ? __ldg(p.cmax + c) : 1.f;
-    cmn16[j] = (unsigned short)cmn[j];
+    bias[j] = sizeof(T) == 2 ? 8388608.f + (float)(unsigned short)mn : mn;
     rcp[j] = __frcp_rn(cmx[j]);
-    fast = fast && cmx[j] >= 1.f && cmx[j] <= 65535.f && cmx[j] == floorf(cmx[j]);
+    fast = fast && cmx[j] >= 1.f && cmx[j] <= 65535.f && cmx[j] == floorf(cmx[j]);  // see the header comment
   }
-  const int rot = (chunk / (32 / EPC)) & (EPC - 1);
   const float lmin = p.lminmax ? __ldg(p.lminmax) : 0.f, lmax = p.lminmax ? __ldg(p.lminmax + 1) : 1.f;
   const T* const casi = reinterpret_cast<const T*>(p.casi);
 
@@ -179,59 +252,12 @@ __global__ void __launch_bounds__(GATHER_THREADS) gather_rows_kernel(const Gathe
     const int shift = (int)((reinterpret_cast<uintptr_t>(gout) >> 2) & 3);
     float* const img = sm + shift;
     // ---- phase 1: window pixels -> fp32 patch image in shared memory
-    if (slot < rows_per_iter) {
-      for (int pix = slot; pix < npix; pix += rows_per_iter) {
-        const int py = pix / S, px = pix - py * S;
-        const int ry = reflect_sym(by + (half_res ? py / 2 : py) - p.nb, p.Hc);
-        const int rx = reflect_sym(bx + (half_res ? px / 2 : px) - p.nb, p.Wc);
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(casi + ((size_t)ry * p.Wc + rx) * p.C) + chunk);
-        float v[EPC];
-        if (sizeof(T) == 2) {
-          const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-          for (int j = 0; j < EPC; j++) {
-            const unsigned short r16 = (unsigned short)((j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xffffu));
-            if (normalize) {
-              const float a = (float)(unsigned short)(r16 - cmn16[j]);
-              if (fast) {
-                const float q = a * rcp[j];
-                v[j] = __fmaf_rn(__fmaf_rn(-q, cmx[j], a), rcp[j], q);
-              } else {
-                v[j] = __fdiv_rn(a, cmx[j]);
-              }
-            } else {
-              v[j] = (float)r16;
-            }
-          }
-        } else {
-          const float f[4] = {__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z),
-                              __uint_as_float(raw.w)};
-#pragma unroll
-          for (int j = 0; j < EPC; j++)
-            v[j] = normalize ? __fdiv_rn(__fsub_rn(f[j & 3], cmn[j]), cmx[j]) : f[j & 3];
-        }
-        float* const dst = img + pix * ld + chunk * EPC;
-        // Lanes of a warp hold neighbouring chunks: for a fixed element j their addresses are EPC floats apart, i.e. only
-        // 32 / EPC distinct banks.  Every lane therefore stores its elements in an order rotated by `rot` (a barrel
-        // rotation of the register array: log2(EPC) select stages), which spreads one store instruction over all banks.
-        float w[EPC];
-#pragma unroll
-        for (int j = 0; j < EPC; j++) w[j] = v[j];
-#pragma unroll
-        for (int bit = 1; bit < EPC; bit <<= 1) {
-          const bool on = (rot & bit) != 0;
-          float t[EPC];
-#pragma unroll
-          for (int j = 0; j < EPC; j++) t[j] = on ? w[(j + bit) & (EPC - 1)] : w[j];
-#pragma unroll
-          for (int j = 0; j < EPC; j++) w[j] = t[j];
-        }
-#pragma unroll
-        for (int j = 0; j < EPC; j++) dst[(j + rot) & (EPC - 1)] = w[j];
-      }
+    if (active) {
+      gather_phase1<T>(p, casi, img, bx, by, chunk, slot, rows_per_iter, bias, cmx, rcp, fast);
     }
-    // LiDAR channel and zero padding channels: one thread per window pixel
-    for (int pix = threadIdx.x; pix < npix; pix += GATHER_THREADS) {
+    // LiDAR channel and zero padding channels: one thread per window pixel (the last warps first: they are the ones
+    // with idle lanes in phase 1 when 256 is not a multiple of the chunk count)
+    for (int pix = GATHER_THREADS - 1 - (int)threadIdx.x; pix < npix; pix += GATHER_THREADS) {
       if (p.lidar) {
         const int py = pix / S, px = pix - py * S;
         const int ry = reflect_sym(y + py - p.nb, p.Hl), rx = reflect_sym(x + px - p.nb, p.Wl);
@@ -339,6 +365,7 @@ int hyp_gather_patches(const void* casi, int casi_dtype, int Hc, int Wc, int C_h
   // persistent grid: as many blocks as stay resident (registers / shared memory decide), each walks the target list
   auto launch = [&](auto kernel) -> int {
     HYP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    HYP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 1;
     HYP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, GATHER_THREADS, smem));
     const unsigned grid = (unsigned)std::min<int64_t>(N, (int64_t)sms * std::max(1, per_sm));
