@@ -1293,39 +1293,53 @@ int hyp_debug_tc_gemm(int mn_flags, const float* A, const float* B, int M, int N
   using namespace hyp::tc;
   const int mn = mn_flags & 1;
   const int cg = (mn_flags & 2) ? 2 : 1;
+  const int op = (mn_flags >> 2) & 3;   // OP_TF32X3 / OP_F16X3 / OP_BF16
   HYP_CHECK_ARG(A && B && D && M > 0 && N > 0 && K > 0, "bad argument");
+  HYP_CHECK_ARG(op <= OP_BF16, "unknown operand format");
   HYP_CHECK_ARG(N % 4 == 0, "N must be a multiple of 4 (output row alignment)");
   HYP_CHECK_ARG(ksplit >= 1 && (mn || ksplit == 1), "ksplit needs mn = 1");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int kbe = op_kbe(op), npl = op_planes(op), esz = op_esize(op);
   const int lda_src = mn ? M : K, ldb_src = mn ? N : K;
   const int64_t a_rows = mn ? K : M, b_rows_src = mn ? K : N;
-  const int ldA = (int)align_up(lda_src, 4), ldB = (int)align_up(ldb_src, 4);
-  float *Ap = nullptr, *Bp = nullptr;
-  HYP_CUDA(cudaMalloc(&Ap, 2 * (size_t)a_rows * ldA * sizeof(float)));
-  HYP_CUDA(cudaMalloc(&Bp, 2 * (size_t)b_rows_src * ldB * sizeof(float)));
-  split_planes_kernel<<<256, 256, 0, st>>>(A, a_rows, lda_src, lda_src, Ap, Ap + a_rows * ldA, ldA, raw_hi);
-  HYP_LAUNCHED();
-  split_planes_kernel<<<256, 256, 0, st>>>(B, b_rows_src, ldb_src, ldb_src, Bp, Bp + b_rows_src * ldB, ldB, raw_hi);
-  HYP_LAUNCHED();
+  const int ldA = (int)align_up(lda_src, 16 / esz), ldB = (int)align_up(ldb_src, 16 / esz);
+  // the 16-bit formats multiply scaled operands (A by 4, B by 64: powers of two, exact) and undo it in the epilogue --
+  // the same mechanism the engine uses to keep fp16 remainders in the normal range
+  const float sa_ = op == OP_F16X3 ? 4.f : 1.f, sb_ = op == OP_F16X3 ? 64.f : 1.f;
+  void *Ap = nullptr, *Bp = nullptr;
+  HYP_CUDA(cudaMalloc(&Ap, (size_t)npl * a_rows * ldA * esz));
+  HYP_CUDA(cudaMalloc(&Bp, (size_t)npl * b_rows_src * ldB * esz));
+  if (op == OP_TF32X3) {
+    float *Af = static_cast<float*>(Ap), *Bf = static_cast<float*>(Bp);
+    split_planes_kernel<<<256, 256, 0, st>>>(A, a_rows, lda_src, lda_src, Af, Af + a_rows * ldA, ldA, raw_hi);
+    HYP_LAUNCHED();
+    split_planes_kernel<<<256, 256, 0, st>>>(B, b_rows_src, ldb_src, ldb_src, Bf, Bf + b_rows_src * ldB, ldB, raw_hi);
+    HYP_LAUNCHED();
+  } else {
+    split_planes16_kernel<<<256, 256, 0, st>>>(A, a_rows, lda_src, lda_src, static_cast<uint16_t*>(Ap), (size_t)a_rows * ldA, ldA, op, sa_);
+    HYP_LAUNCHED();
+    split_planes16_kernel<<<256, 256, 0, st>>>(B, b_rows_src, ldb_src, ldb_src, static_cast<uint16_t*>(Bp), (size_t)b_rows_src * ldB, ldB, op, sb_);
+    HYP_LAUNCHED();
+  }
   const int ntile_n = 256;
   if (bn <= 0) bn = (int)std::min<int64_t>(256, align_up(N, 16));
   HYP_CHECK_ARG(bn % (8 * cg) == 0 && bn <= 256, "bn must be a multiple of 8 per CTA, <= 256");
   CUtensorMap tmA, tmB;
   int rc;
   {
-    const uint64_t da[4] = {(uint64_t)lda_src, (uint64_t)a_rows, 1, 2};
+    const uint64_t da[4] = {(uint64_t)lda_src, (uint64_t)a_rows, 1, (uint64_t)npl};
     const uint64_t sa[3] = {(uint64_t)ldA, (uint64_t)a_rows * ldA, (uint64_t)a_rows * ldA};
-    const uint32_t ba[4] = {32, mn ? 32u : 128u, 1, 1};
-    if ((rc = make_map(&tmA, Ap, da, sa, ba, mn != 0))) return rc;
-    const uint64_t db[4] = {(uint64_t)ldb_src, (uint64_t)b_rows_src, 1, 2};
+    const uint32_t ba[4] = {(uint32_t)kbe, mn ? (uint32_t)kbe : 128u, 1, 1};
+    if ((rc = make_map(&tmA, Ap, da, sa, ba, mn != 0, op))) return rc;
+    const uint64_t db[4] = {(uint64_t)ldb_src, (uint64_t)b_rows_src, 1, (uint64_t)npl};
     const uint64_t sb[3] = {(uint64_t)ldB, (uint64_t)b_rows_src * ldB, (uint64_t)b_rows_src * ldB};
-    const uint32_t bb[4] = {32, mn ? 32u : (uint32_t)(bn / cg), 1, 1};
-    if ((rc = make_map(&tmB, Bp, db, sb, bb, mn != 0))) return rc;
+    const uint32_t bb[4] = {(uint32_t)kbe, mn ? (uint32_t)kbe : (uint32_t)(bn / cg), 1, 1};
+    if ((rc = make_map(&tmB, Bp, db, sb, bb, mn != 0, op))) return rc;
   }
   std::vector<TcSeg> segs;
   std::vector<TcTile> tiles;
   const int mt = (int)cdiv(M, 128), nt = (int)cdiv(N, ntile_n);
-  const int kblocks = (int)cdiv(K, TC_KB);
+  const int kblocks = (int)cdiv(K, kbe);
   const int kb_per = (int)cdiv(kblocks, ksplit);
   int max_brows = 0;
   // one segment per (N tile, K split); the M tiles that share it are consecutive (CTA pairs)
@@ -1342,10 +1356,10 @@ int hyp_debug_tc_gemm(int mn_flags, const float* A, const float* B, int M, int N
         s.nb = (int)cdiv(s.n_mma, bn);
         max_brows = std::max(max_brows, s.nb * bn);
       } else {
-        s.a1 = kb0 * TC_KB;
-        s.b0 = n0; s.b1 = kb0 * TC_KB;
-        s.nb = (int)cdiv(s.n_mma, 32);
-        max_brows = std::max(max_brows, cg * (int)cdiv(s.n_mma / cg, 32) * 32);
+        s.a1 = kb0 * kbe;
+        s.b0 = n0; s.b1 = kb0 * kbe;
+        s.nb = (int)cdiv(s.n_mma, kbe);
+        max_brows = std::max(max_brows, cg * (int)cdiv(s.n_mma / cg, kbe) * kbe);
       }
       const int sidx = (int)segs.size();
       segs.push_back(s);
@@ -1377,9 +1391,11 @@ int hyp_debug_tc_gemm(int mn_flags, const float* A, const float* B, int M, int N
   HYP_CUDA(cudaMemcpyAsync(dtiles, tiles.data(), tiles.size() * sizeof(TcTile), cudaMemcpyHostToDevice, st));
   TcParams p{};
   p.segs = dsegs; p.tiles = dtiles; p.out = D; p.stats = stats; p.stats_ld = N;
+  p.op = op; p.out_scale = 1.f / (sa_ * sb_);
   p.epi = ksplit > 1 ? EPI_ATOMIC : EPI_STORE;
   p.b_rows = max_brows; p.bn = bn; p.chunk_kb = chunk_kb; p.stages = 0;
-  rc = mn ? launch_tc<true, 1>(tmA, tmB, p, (int)tiles.size(), st)
+  rc = mn ? (cg == 2 ? launch_tc<true, 2>(tmA, tmB, p, (int)tiles.size(), st)
+                     : launch_tc<true, 1>(tmA, tmB, p, (int)tiles.size(), st))
           : (cg == 2 ? launch_tc<false, 2>(tmA, tmB, p, (int)tiles.size(), st)
                      : launch_tc<false, 1>(tmA, tmB, p, (int)tiles.size(), st));
   cudaError_t e = cudaStreamSynchronize(st);

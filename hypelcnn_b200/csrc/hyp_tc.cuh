@@ -18,6 +18,8 @@
 // partial sums).
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cstddef>
@@ -79,10 +81,23 @@ struct alignas(16) TcTile {
 
 enum { EPI_STORE = 0, EPI_ACCUM = 1, EPI_ATOMIC = 2 };
 
+// operand formats: how the two GEMM operands are stored and multiplied
+//   OP_TF32X3 : two fp32 planes (value, TF32 remainder), 3 kind::tf32 MMAs per K step of 8      (fp32-accurate)
+//   OP_F16X3  : two fp16 planes (hi, lo = fp16(v - hi)), 3 kind::f16 MMAs per K step of 16      (fp32-accurate, 2x rate)
+//   OP_BF16   : one bf16 plane, 1 kind::f16 MMA per K step of 16                                 (fast mode)
+// A K block is always one 128-byte row per operand row: 32 fp32 or 64 16-bit elements.
+enum { OP_TF32X3 = 0, OP_F16X3 = 1, OP_BF16 = 2 };
+__host__ __device__ inline int op_planes(int op) { return op == OP_BF16 ? 1 : 2; }
+__host__ __device__ inline int op_kbe(int op) { return op == OP_TF32X3 ? 32 : 64; }       // K elements per 128-byte block
+__host__ __device__ inline int op_esize(int op) { return op == OP_TF32X3 ? 4 : 2; }
+
 struct TcParams {
   const TcSeg* segs;
   const TcTile* tiles;
   float* out;
+  int32_t op;             // OP_*
+  float out_scale;        // every output value is multiplied by out_scale * (*out_scale_ptr) (operand scaling of the
+  const float* out_scale_ptr;  // 16-bit formats; nullable)
   float* stats;       // nullable: [stats rows][2][stats_ld] per-tile column sum / sum of squares
   int32_t stats_ld;
   int32_t epi;
@@ -95,12 +110,12 @@ struct TcParams {
 };
 
 // b_rows = B rows held by ONE CTA per stage and plane
-inline size_t tc_smem_bytes(int b_rows, int stages) {
-  return 1024 + (size_t)stages * (2 * TC_PLANE_A + 2 * (size_t)b_rows * 128) + TC_SMEM_FIXED;
+inline size_t tc_smem_bytes(int b_rows, int stages, int planes = 2) {
+  return 1024 + (size_t)stages * planes * (TC_PLANE_A + (size_t)b_rows * 128) + TC_SMEM_FIXED;
 }
-inline int tc_pick_stages(int b_rows) {
+inline int tc_pick_stages(int b_rows, int planes = 2) {
   const size_t fixed = 1024 + TC_SMEM_FIXED;
-  const size_t st = 2 * TC_PLANE_A + 2 * (size_t)b_rows * 128;
+  const size_t st = (size_t)planes * (TC_PLANE_A + (size_t)b_rows * 128);
   int s = (int)((TC_SMEM_LIMIT - fixed) / st);
   return s > 8 ? 8 : s;
 }
@@ -156,12 +171,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)layout << 61;
   return d;
 }
-// instruction descriptor: D fp32, A/B tf32, M = 128 per CTA of the group
-__device__ __forceinline__ uint32_t make_idesc_tf32(int n, bool mn_major, int cg = 1) {
+// instruction descriptor: D fp32, A/B format fmt (kind::tf32: 2 = tf32; kind::f16: 0 = f16, 1 = bf16), M = 128 per CTA
+// of the group
+__device__ __forceinline__ uint32_t make_idesc(int n, bool mn_major, int cg, uint32_t fmt) {
   uint32_t d = 0;
   d |= 1u << 4;
-  d |= 2u << 7;
-  d |= 2u << 10;
+  d |= fmt << 7;
+  d |= fmt << 10;
   if (mn_major) d |= (1u << 15) | (1u << 16);
   d |= (uint32_t)(n >> 3) << 17;
   d |= (uint32_t)((TC_BM * cg) >> 4) << 24;
@@ -302,6 +318,31 @@ __device__ __forceinline__ void mma_tf32_u(uint32_t pred, uint32_t tmem_d, uint3
   }
 }
 template <int CG>
+__device__ __forceinline__ void mma_f16_u(uint32_t pred, uint32_t tmem_d, uint32_t a_lo32, uint32_t b_lo32, uint32_t desc_hi32,
+                                          uint32_t idesc, uint32_t accum) {
+  if (CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "setp.ne.b32 q, %6, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo32), "r"(b_lo32), "r"(desc_hi32), "r"(idesc), "r"(accum), "r"(pred)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "setp.ne.b32 q, %6, 0;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo32), "r"(b_lo32), "r"(desc_hi32), "r"(idesc), "r"(accum), "r"(pred)
+        : "memory");
+  }
+}
+template <int CG>
 __device__ __forceinline__ void tc_commit_u(uint32_t pred, uint32_t bar) {
   if (CG == 1) {
     asm volatile(
@@ -351,7 +392,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t base = (raw + 1023u) & ~1023u;  // swizzle atoms are 1024-byte aligned
   uint8_t* gen = smem_raw + (base - raw);
   const uint32_t b_plane = (uint32_t)(p.b_rows / CG) * 128u;  // B rows held by THIS CTA
-  const uint32_t stage_bytes = 2u * TC_PLANE_A + 2u * b_plane;
+  const uint32_t npl = (uint32_t)op_planes(p.op);
+  const int kbe = op_kbe(p.op);                 // K elements per 128-byte block
+  const int mnb = kbe;                          // MN-major boxes: mnb columns x kbe rows (32 x 32 fp32, 64 x 64 16-bit)
+  const uint32_t mn_box_bytes = (uint32_t)kbe * 128u;
+  const uint32_t stage_bytes = npl * (TC_PLANE_A + b_plane);
   const uint32_t bar_base = base + (uint32_t)p.stages * stage_bytes;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (size_t)p.stages * stage_bytes + 192);
   float* s_part = reinterpret_cast<float*>(gen + (size_t)p.stages * stage_bytes + 256);  // [2][4][TC_MAX_COLS]
@@ -442,34 +487,33 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int snk = __shfl_sync(0xffffffffu, wB.z, src), sn = __shfl_sync(0xffffffffu, wB.w, src);
         const int snb = __shfl_sync(0xffffffffu, wC.x, src);
         // B boxes this CTA loads: K-major boxes of bn/CG rows, MN-major boxes of 32 columns
-        const uint32_t b_box_bytes = MN ? 4096u : (uint32_t)(p.bn / CG) * 128u;
-        // MN-major: this CTA's half of the N columns starts at column rank * n / CG and is loaded as 32-column boxes
+        const uint32_t b_box_bytes = MN ? mn_box_bytes : (uint32_t)(p.bn / CG) * 128u;
+        // MN-major: this CTA's half of the N columns starts at column rank * n / CG and is loaded as mnb-column boxes
         // (the last one may run past the half: harmless extra columns)
-        const int nb = MN ? (sn / CG + 31) / 32 : snb;
+        const int nb = MN ? (sn / CG + mnb - 1) / mnb : snb;
         const int b_col0 = MN ? (int)rank * (sn / CG) : 0;
         const int b_row0 = MN ? 0 : (int)rank * (sn / CG);          // first B row
         (void)snb;
-        const uint32_t tx_cta = 2u * TC_PLANE_A + 2u * (uint32_t)nb * b_box_bytes;
+        const uint32_t tx_cta = npl * (TC_PLANE_A + (uint32_t)nb * b_box_bytes);
+        const int a_boxes = TC_BM / mnb;  // MN-major A: boxes of mnb columns
         for (int kb = 0; kb < snk; kb++) {
           { const long long t0 = p.timing ? clock64() : 0; mbar_wait(empty_bar(stage), phase ^ 1u); if (p.timing) tm_wait_empty += clock64() - t0; }
           const uint32_t fb_local = full_bar(stage);
           const uint32_t fb = CG == 2 ? mapa_shared(fb_local, 0) : fb_local;
           if (leader) mbar_expect_tx_u(pred, fb_local, tx_cta * CG);
           const uint32_t a_s = base + (uint32_t)stage * stage_bytes;
-          const uint32_t b_s = a_s + 2u * TC_PLANE_A;
-#pragma unroll
-          for (int pl = 0; pl < 2; pl++) {
+          const uint32_t b_s = a_s + npl * TC_PLANE_A;
+          for (int pl = 0; pl < (int)npl; pl++) {
             if (!MN) {
-              tma_load_4d_u<CG>(pred, a_s + pl * TC_PLANE_A, &tmA, fb, sa0 + kb * TC_KB, sa1, sa2, pl);
+              tma_load_4d_u<CG>(pred, a_s + pl * TC_PLANE_A, &tmA, fb, sa0 + kb * kbe, sa1, sa2, pl);
               for (int j = 0; j < nb; j++)
-                tma_load_4d_u<CG>(pred, b_s + pl * b_plane + j * b_box_bytes, &tmB, fb, sb0 + kb * TC_KB,
+                tma_load_4d_u<CG>(pred, b_s + pl * b_plane + j * b_box_bytes, &tmB, fb, sb0 + kb * kbe,
                                   sb1 + b_row0 + j * (p.bn / CG), sb2, pl);
             } else {
-#pragma unroll
-              for (int i = 0; i < 4; i++)
-                tma_load_4d_u<CG>(pred, a_s + pl * TC_PLANE_A + i * 4096, &tmA, fb, sa0 + i * 32, sa1 + kb * TC_KB, sa2, pl);
+              for (int i = 0; i < a_boxes; i++)
+                tma_load_4d_u<CG>(pred, a_s + pl * TC_PLANE_A + i * mn_box_bytes, &tmA, fb, sa0 + i * mnb, sa1 + kb * kbe, sa2, pl);
               for (int j = 0; j < nb; j++)
-                tma_load_4d_u<CG>(pred, b_s + pl * b_plane + j * 4096, &tmB, fb, sb0 + b_col0 + j * 32, sb1 + kb * TC_KB,
+                tma_load_4d_u<CG>(pred, b_s + pl * b_plane + j * mn_box_bytes, &tmB, fb, sb0 + b_col0 + j * mnb, sb1 + kb * kbe,
                                   sb2, pl);
             }
           }
@@ -488,9 +532,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       long long tm_wait_full = 0, tm_wait_tempty = 0;
       // smem matrix descriptors: only the 14-bit start address field changes between operands
       //   K-major : LBO 16 B, SBO 1024 B, SWIZZLE_128B;  MN-major: LBO 4096 B, SBO 512 B, SWIZZLE_128B_BASE32B
-      const uint32_t desc_hi32 = (MN ? (512u >> 4) : (1024u >> 4)) | (1u << 14) | ((MN ? 1u : 2u) << 29);
-      const uint32_t desc_lo_fixed = (MN ? (4096u >> 4) : (16u >> 4)) << 16;
-      const uint32_t ks_step = MN ? (1024u >> 4) : (32u >> 4);  // descriptor address units per K step of 8
+      //             16-bit MN-major: LBO = one box (8192 B), SBO 1024 B (8 K rows of 128 B), plain SWIZZLE_128B
+      const bool op16 = p.op != OP_TF32X3;
+      const uint32_t mn_sbo = op16 ? 1024u : 512u, mn_layout = op16 ? 2u : 1u;
+      const uint32_t desc_hi32 = (MN ? (mn_sbo >> 4) : (1024u >> 4)) | (1u << 14) | ((MN ? mn_layout : 2u) << 29);
+      const uint32_t desc_lo_fixed = (MN ? (mn_box_bytes >> 4) : (16u >> 4)) << 16;
+      // descriptor address units per K step (8 fp32 / 16 16-bit elements = 32 bytes of a K-major row, or that many
+      // 128-byte K rows of an MN-major box)
+      const uint32_t ks_step = MN ? ((op16 ? 2048u : 1024u) >> 4) : (32u >> 4);
+      const uint32_t ab_fmt = p.op == OP_TF32X3 ? 2u : (p.op == OP_F16X3 ? 0u : 1u);
       int4 hdr0 = make_int4(0, 0, 0, 0), hdr1 = make_int4(0, 0, 0, 0);
       if (group < nslots) {
         const int4* hp = reinterpret_cast<const int4*>(p.tiles + (size_t)group * CG);
@@ -516,7 +566,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int rs = si >> 5, src = si & 31;
           const int2 wN = rs == 0 ? sN[0] : (rs == 1 ? sN[1] : (rs == 2 ? sN[2] : sN[3]));
           const int snk = __shfl_sync(0xffffffffu, wN.x, src);
-          const uint32_t idesc = make_idesc_tf32(__shfl_sync(0xffffffffu, wN.y, src), MN, CG);
+          const uint32_t idesc = make_idesc(__shfl_sync(0xffffffffu, wN.y, src), MN, CG, ab_fmt);
           for (int kb = 0; kb < snk; kb++, kcount++) {
             if (kcount % CH == 0) {  // new chunk: its TMEM buffer must have been drained
               buf = gchunk & 1u;
@@ -530,15 +580,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t a_s = base + (uint32_t)stage * stage_bytes;
             const uint32_t a_hi = desc_lo_fixed | ((a_s & 0x3FFFFu) >> 4);
             const uint32_t a_lo = a_hi + (TC_PLANE_A >> 4);
-            const uint32_t b_hi = a_hi + (2u * TC_PLANE_A >> 4);
+            const uint32_t b_hi = a_hi + (npl * TC_PLANE_A >> 4);
             const uint32_t b_lo = b_hi + (b_plane >> 4);
+            if (p.op == OP_TF32X3) {
 #pragma unroll
-            for (int ks = 0; ks < TC_KB / 8; ks++) {
-              const uint32_t o = (uint32_t)ks * ks_step;
-              mma_tf32_u<CG>(pred, tmem_d, a_lo + o, b_hi + o, desc_hi32, idesc, accum);
-              mma_tf32_u<CG>(pred, tmem_d, a_hi + o, b_lo + o, desc_hi32, idesc, 1);
-              mma_tf32_u<CG>(pred, tmem_d, a_hi + o, b_hi + o, desc_hi32, idesc, 1);
-              accum = 1;
+              for (int ks = 0; ks < 4; ks++) {
+                const uint32_t o = (uint32_t)ks * ks_step;
+                mma_tf32_u<CG>(pred, tmem_d, a_lo + o, b_hi + o, desc_hi32, idesc, accum);
+                mma_tf32_u<CG>(pred, tmem_d, a_hi + o, b_lo + o, desc_hi32, idesc, 1);
+                mma_tf32_u<CG>(pred, tmem_d, a_hi + o, b_hi + o, desc_hi32, idesc, 1);
+                accum = 1;
+              }
+            } else if (p.op == OP_F16X3) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ks++) {
+                const uint32_t o = (uint32_t)ks * ks_step;
+                mma_f16_u<CG>(pred, tmem_d, a_lo + o, b_hi + o, desc_hi32, idesc, accum);
+                mma_f16_u<CG>(pred, tmem_d, a_hi + o, b_lo + o, desc_hi32, idesc, 1);
+                mma_f16_u<CG>(pred, tmem_d, a_hi + o, b_hi + o, desc_hi32, idesc, 1);
+                accum = 1;
+              }
+            } else {
+#pragma unroll
+              for (int ks = 0; ks < 4; ks++) {
+                mma_f16_u<CG>(pred, tmem_d, a_hi + (uint32_t)ks * ks_step, b_hi + (uint32_t)ks * ks_step, desc_hi32, idesc, accum);
+                accum = 1;
+              }
             }
             tc_commit_u<CG>(pred, empty_bar(stage));  // frees the stage (in both CTAs) once these MMAs have read it
             if (kcount % CH == CH - 1 || kcount == total_kb - 1) {
@@ -562,6 +629,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* st = s_stage + (warp - 2) * TC_STAGE_FLOATS;
     uint32_t gchunk = 0;
     long long tm_wait_tfull = 0, tm_store = 0, tm_drain = 0, tm_tiles = 0;
+    const float oscale = p.out_scale * (p.out_scale_ptr ? __ldg(p.out_scale_ptr) : 1.f);
     const uint32_t tempty_remote0 = CG == 2 ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
     const uint32_t tempty_remote1 = CG == 2 ? mapa_shared(tempty_bar(1), 0) : tempty_bar(1);
     for (int slot = group; slot < nslots; slot += ngroups) {
@@ -650,8 +718,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < 4; k++)
             *reinterpret_cast<float4*>(st + lane * TC_STAGE_LD + 4 * k) =
-                make_float4(acc[g * 32 + hh * 16 + 4 * k], acc[g * 32 + hh * 16 + 4 * k + 1],
-                            acc[g * 32 + hh * 16 + 4 * k + 2], acc[g * 32 + hh * 16 + 4 * k + 3]);
+                make_float4(acc[g * 32 + hh * 16 + 4 * k] * oscale, acc[g * 32 + hh * 16 + 4 * k + 1] * oscale,
+                            acc[g * 32 + hh * 16 + 4 * k + 2] * oscale, acc[g * 32 + hh * 16 + 4 * k + 3] * oscale);
           __syncwarp();
           const int ocol = c0 + c4 - cb_tcol;             // output column of this lane's 4 values
           float* const obase = p.out + cb_off + (int64_t)(q * 32 + r_lane) * ld_out + ocol;
@@ -791,21 +859,23 @@ inline EncodeTiledFn encode_tiled_fn() {
 
 // fp32 tensor of rank 4 (dim 0 innermost, contiguous).  strides_elems: element strides of dims 1..3.
 // mn_major: boxes feed MN-major tf32 operands -> SWIZZLE_128B_ATOM_32B, else SWIZZLE_128B.
-inline int make_map(CUtensorMap* map, const float* base, const uint64_t dims[4], const uint64_t strides_elems[3],
-                    const uint32_t box[4], bool mn_major = false) {
+// op = OP_*: fp32 elements (MN-major boxes feed tf32 operands -> SWIZZLE_128B_ATOM_32B) or 16-bit elements (plain
+// SWIZZLE_128B for both majors)
+inline int make_map(CUtensorMap* map, const void* base, const uint64_t dims[4], const uint64_t strides_elems[3],
+                    const uint32_t box[4], bool mn_major = false, int op = OP_TF32X3) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return fail(HYP_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t gd[4], gs[3];
   cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
   for (int i = 0; i < 4; i++) { gd[i] = dims[i]; bx[i] = box[i]; }
   for (int i = 0; i < 3; i++) {
-    gs[i] = strides_elems[i] * sizeof(float);
+    gs[i] = strides_elems[i] * (uint64_t)op_esize(op);
     if (gs[i] % 16) return fail(HYP_E_INVALID, "tensor map stride is not a multiple of 16 bytes");
   }
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(HYP_E_INVALID, "tensor map base is not 16-byte aligned");
-  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gd, gs, bx, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+  const CUresult r = fn(map, op == OP_TF32X3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                        const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        (mn_major && op == OP_TF32X3) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(HYP_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
@@ -871,14 +941,15 @@ inline int launch_tc_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParam
   if (ntiles <= 0) return HYP_OK;
   if (ntiles % CG) return fail(HYP_E_INVALID, "tc gemm: tile count is not a multiple of the CTA group size");
   if (p.b_rows % (8 * CG)) return fail(HYP_E_INVALID, "tc gemm: B rows must be a multiple of 8 per CTA");
-  if (p.stages <= 0) p.stages = tc_pick_stages(p.b_rows / CG);
+  if (p.stages <= 0) p.stages = tc_pick_stages(p.b_rows / CG, op_planes(p.op));
+  if (p.out_scale == 0.f) p.out_scale = 1.f;
   if (p.chunk_kb <= 0) {
     static const int env_chunk = getenv("HYP_TC_CHUNK_KB") ? atoi(getenv("HYP_TC_CHUNK_KB")) : 0;  // experiments only
     p.chunk_kb = env_chunk > 0 ? env_chunk : TC_DEFAULT_CHUNK_KB;
   }
   if (p.stages < 2) return fail(HYP_E_INVALID, "tc gemm: B tile too large for two pipeline stages");
   p.ntiles = ntiles;
-  const size_t smem = tc_smem_bytes(p.b_rows / CG, p.stages);
+  const size_t smem = tc_smem_bytes(p.b_rows / CG, p.stages, op_planes(p.op));
   static bool attr_set = false;
   if (!attr_set) {
     HYP_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MN, CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
@@ -941,6 +1012,46 @@ __device__ __forceinline__ float tf32_rna(float x) {
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = tf32_rna(x);
   lo = tf32_rna(x - hi);
+}
+// 16-bit operand formats.  OP_F16X3: hi = fp16(x), lo = fp16(x - hi) — 22 significand bits as long as lo stays a
+// normal fp16 number (|x| >= 2^-3); below that the absolute error is bounded by half the subnormal spacing, 2^-25, so
+// tensors are scaled to O(1)..O(2^10) magnitudes before the split (see hyp_tc_engine.cuh).  OP_BF16: one bf16 plane.
+__device__ __forceinline__ void split_f16(float x, uint16_t& hi, uint16_t& lo) {
+  const __half h = __float2half_rn(x);
+  hi = __half_as_ushort(h);
+  lo = __half_as_ushort(__float2half_rn(x - __half2float(h)));
+}
+__device__ __forceinline__ uint16_t to_bf16(float x) { return __bfloat16_as_ushort(__float2bfloat16_rn(x)); }
+// the planes of 4 consecutive elements, 8 bytes per plane; `planes` points at element 0 of plane 0
+__device__ __forceinline__ void store_op16x4(uint16_t* planes, size_t plane_stride, int op, float v0, float v1, float v2, float v3) {
+  if (op == OP_F16X3) {
+    uint16_t h[4], l[4];
+    split_f16(v0, h[0], l[0]); split_f16(v1, h[1], l[1]); split_f16(v2, h[2], l[2]); split_f16(v3, h[3], l[3]);
+    *reinterpret_cast<uint2*>(planes) = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
+    *reinterpret_cast<uint2*>(planes + plane_stride) = make_uint2(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16));
+  } else {
+    *reinterpret_cast<uint2*>(planes) = make_uint2(to_bf16(v0) | ((uint32_t)to_bf16(v1) << 16),
+                                                   to_bf16(v2) | ((uint32_t)to_bf16(v3) << 16));
+  }
+}
+__device__ __forceinline__ void store_op16(uint16_t* planes, size_t plane_stride, int op, float v) {
+  if (op == OP_F16X3) {
+    uint16_t h, l;
+    split_f16(v, h, l);
+    planes[0] = h;
+    planes[plane_stride] = l;
+  } else {
+    planes[0] = to_bf16(v);
+  }
+}
+__global__ void split_planes16_kernel(const float* __restrict__ src, int64_t rows, int cols, int ld_src, uint16_t* planes,
+                                      size_t plane_stride, int ld_dst, int op, float scale) {
+  const int64_t total = rows * ld_dst;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / ld_dst;
+    const int c = (int)(i - r * ld_dst);
+    store_op16(planes + i, plane_stride, op, c < cols ? src[r * ld_src + c] * scale : 0.f);
+  }
 }
 __global__ void split_planes_kernel(const float* __restrict__ src, int64_t rows, int cols, int ld_src, float* hi,
                                     float* lo, int ld_dst, int raw_hi) {

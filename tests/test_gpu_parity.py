@@ -259,9 +259,12 @@ def test_forward_training_parity_per_layer(E, case, prec):
     assert_close(logits.cpu().numpy(), ref["logits"].numpy(), RTOL, max(ATOL, 3.0 * floor32), "logits")
     assert_close(recon.cpu().numpy(), ref["recon"].numpy(), RTOL, ATOL, "recon")
     # BN moving statistics (decay, Bessel-corrected variance)
+    # (moving_mean is (1 - decay) x the batch mean of z: its absolute error follows the scale of the layer's z, whose
+    # pre-BN check above allows 2e-5 of max|z|; 5e-6 of the tensor's largest entry keeps the same relation)
     for name in eng.variables:
         if "moving_" in name:
-            assert_close(eng.variable(name).cpu().numpy(), ref["new_variables"][name].numpy(), RTOL, 1e-6, name)
+            want = ref["new_variables"][name].numpy()
+            assert_close(eng.variable(name).cpu().numpy(), want, RTOL, max(1e-6, 5e-6 * float(numpy.abs(want).max())), name)
     # integer argmax class map bit-exact
     pred = E.argmax_confusion(logits)
     assert numpy.array_equal(pred.cpu().numpy(), D.argmax_lowest(ref["logits"].numpy()).astype(numpy.uint8))
