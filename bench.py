@@ -295,10 +295,12 @@ def run_native(args):
         if d["flops"] > 0:
             achieved = d["flops"] / (d["ms"] / 1e3) / 1e12
             peak = peaks["bf16_tflops_sustained"]
-            tc = args.precision == "3xtf32"
+            tc = args.precision in ("3xtf32", "3xf16", "bf16")
+            # tensor-pipe work per useful MAC relative to one bf16 MMA: 3 tf32 MMAs at half rate / 3 f16 MMAs / 1
+            pipe_factor = {"3xtf32": 6, "3xf16": 3, "bf16": 1}.get(args.precision)
             traffic, traffic_src = None, None
             tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
-            if tc and args.workload == "c2_grss2013" and B == 4096 and os.path.exists(tp):
+            if args.precision == "3xtf32" and args.workload == "c2_grss2013" and B == 4096 and os.path.exists(tp):
                 t = json.load(open(tp))  # dram__bytes_read.sum + dram__bytes_write.sum, averaged per GEMM launch (ncu)
                 traffic, traffic_src = t["gemm_dram_bytes_per_launch"], t["source"]
             roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -307,10 +309,14 @@ def run_native(args):
                         "kernel": dom,
                         "avg_launch_ms": d["ms"] / d["launches"], "share_of_step": d["ms"] / total_prof_ms,
                         "peak_source": f"{peaks['source']} bf16 dense sustained (kernel timed inside a long step)",
-                        "note": ("achieved = useful (algorithmic) FLOPs; the kernel issues 3 kind::tf32 MMAs (half the "
-                                 "bf16 rate) per useful MAC, so tensor_pipe_frac = 6 x frac is the pipe utilisation"
+                        "note": ({"3xtf32": "achieved = useful (algorithmic) FLOPs; the kernel issues 3 kind::tf32 MMAs (half "
+                                            "the bf16 rate) per useful MAC, so tensor_pipe_frac = 6 x frac is the pipe "
+                                            "utilisation",
+                                  "3xf16": "achieved = useful (algorithmic) FLOPs; the kernel issues 3 kind::f16 MMAs per "
+                                           "useful MAC (fp16 hi/lo operand planes), so tensor_pipe_frac = 3 x frac",
+                                  "bf16": "one bf16 MMA per useful MAC: the fast mode, not a parity mode"}[args.precision]
                                  if tc else "this kernel computes in fp32 FFMA, not on the tensor pipe"),
-                        "tensor_pipe_frac": 6 * achieved / peak if tc else None}
+                        "tensor_pipe_frac": pipe_factor * achieved / peak if tc else None}
         else:
             achieved = d["bytes"] / (d["ms"] / 1e3) / 1e9
             roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -323,13 +329,35 @@ def run_native(args):
         rate, dt, threads = oracle_cpu_rate(args.workload, args.ref_batch, 40, 2)
         cpu = {"value": rate, "unit": "patches/s", "cores": threads, "kind": "port",
                "sample": f"40 train steps of {args.ref_batch} patches on the CPU oracle ({dt:.1f} s)"}
+    parity = None
+    if world == 1 and args.model == "hypelcnn" and args.workload == "c2_grss2013" and not args.no_cpu_baseline:
+        # what this precision mode costs in accuracy: 512 fresh patches through a fresh engine of the same mode against
+        # the fp64 CPU oracle on the same variables (training-mode forward, dropout off)
+        from oracle import dataset_ref as D
+        from oracle import hypelcnn_ref as R
+        alg0 = {**alg, "drop_out_ratio": 0.0, "batch_size": 512}
+        probe = E.PatchEngine(P, C, classes, alg0, max_batch=512, precision=args.precision)
+        probe.init_variables(1234)
+        px = numpy.random.default_rng(99).random((512, P, P, C), dtype=numpy.float32)
+        plog, _ = probe.forward(torch.from_numpy(px).cuda(), True, True, 0)
+        with torch.no_grad():
+            v64 = {k: torch.tensor(a, dtype=torch.float64) for k, a in probe.export_variables().items()}
+            ref = R.forward(v64, torch.tensor(px, dtype=torch.float64), classes, alg0, True)["logits"]
+        got = plog.cpu().double()
+        rel = ((got - ref).abs() / ref.abs().clamp_min(1e-2)).max().item()
+        pred = E.argmax_confusion(plog).cpu().numpy()
+        want = D.argmax_lowest(ref.numpy()).astype(numpy.uint8)
+        parity = {"sample": "512 patches, training-mode forward vs the fp64 CPU oracle",
+                  "max_abs_logit_error": (got - ref).abs().max().item(), "max_rel_logit_error_floor_1e-2": rel,
+                  "logit_scale": ref.abs().max().item(), "argmax_mismatches": int((pred != want).sum()), "rows": 512}
+        del probe
     step_flops = FWD_BWD_MFLOP[args.workload] * 1e6 * B if args.model == "hypelcnn" else \
         sum(r["flops"] for r in prof.values()) / args.steps  # useful FLOPs of the step's GEMM launches
     step_tflops = step_flops * world / (ms / args.steps / 1e3) / 1e12
     line = {
         "metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": {"fp32": "f32", "3xtf32": "tf32x3", "bf16": "bf16"}[args.precision],
+        "vs_baseline": None, "dtype": {"fp32": "f32", "3xtf32": "tf32x3", "3xf16": "f16x3", "bf16": "bf16"}[args.precision],
         "data": "synthetic",
         "config": {"workload": args.workload + ("" if args.model == "hypelcnn" else "/" + args.model), "per_gpu_batch": B, "global_batch": B * world, "patch": P, "channels": C,
                    "classes": classes, "precision_mode": args.precision,
@@ -338,7 +366,7 @@ def run_native(args):
                          f"{nb} resident batches ({nb * host_x[0].numel() * 4 / 1e6:.0f} MB)"},
         "step_tflops_useful": step_tflops, "step_frac_of_bf16_peak": step_tflops / (peaks["bf16_tflops_sustained"] * world),
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": launches,
-        "final_loss": final_loss,
+        "final_loss": final_loss, "parity_vs_fp64_oracle": parity,
         "kernel_breakdown_ms_per_step": {k: round(v["ms"] / args.steps, 4) for k, v in
                                          sorted(by_kernel.items(), key=lambda kv: -kv[1]["ms"])},
     }
@@ -481,8 +509,10 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="patches per GPU per step")
     ap.add_argument("--ref-batch", type=int, default=256, help="patches per step of the CPU arm (bounded sample)")
     ap.add_argument("--input-batches", type=int, default=4)
-    ap.add_argument("--precision", default="3xtf32", choices=["fp32", "3xtf32"],
-                    help="3xtf32: tcgen05 tensor-core engine (fp32-accurate split); fp32: FFMA engine")
+    ap.add_argument("--precision", default="3xtf32", choices=["fp32", "3xtf32", "3xf16", "bf16"],
+                    help="3xtf32 / 3xf16: tcgen05 tensor-core engine with an fp32-accurate operand split (TF32 planes, "
+                         "3 kind::tf32 MMAs per K step of 8 / fp16 hi-lo planes, 3 kind::f16 MMAs per K step of 16); "
+                         "bf16: the labelled fast mode (one bf16 plane, not a parity mode); fp32: FFMA engine")
     ap.add_argument("--model", default="hypelcnn", choices=["hypelcnn", "dualcnn"],
                     help="hypelcnn = the headline metric; dualcnn = BASELINE configs[0] on the same engine (no CPU arm)")
     ap.add_argument("--e2e-input", default="targets", choices=["targets", "patches"],

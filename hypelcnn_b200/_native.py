@@ -15,7 +15,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 HYP_OK, HYP_E_INVALID, HYP_E_CUDA, HYP_E_STATE, HYP_E_UNSUPPORTED = 0, -1, -2, -3, -4
 HYP_DT_F32, HYP_DT_U16 = 0, 1
 HYP_GATHER_SAME_RES, HYP_GATHER_GRSS2018 = 0, 1
-HYP_PRECISION_FP32, HYP_PRECISION_3XTF32, HYP_PRECISION_BF16 = 0, 1, 2
+HYP_PRECISION_FP32, HYP_PRECISION_3XTF32, HYP_PRECISION_BF16, HYP_PRECISION_3XF16 = 0, 1, 2, 3
 HYP_MODEL_HYPELCNN, HYP_MODEL_DUALCNN, HYP_MODEL_CONCNN = 0, 1, 2
 
 
@@ -116,7 +116,6 @@ _PROTOS = {
     "hyp_model_debug_tensor": (_I, [_P, ctypes.c_char_p, _I, ctypes.POINTER(_P), ctypes.POINTER(_L)]),
     "hyp_crc32c": (_I, [_P, ctypes.c_uint64, _P]),
     "hyp_tiff_lzw_decode": (_I, [_P, ctypes.c_uint64, _P, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]),
-    "hyp_debug_plan_level_pairs": (_I, [_I, _I, _I, _P, _I, _P, _I, _P]),
     "hyp_debug_schedule": (_I, [_P, _I, _I, _I, _P, _P]),
     "hyp_debug_tc_gemm": (_I, [_I, _P, _P, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P]),
     "hyp_model_dropout_mask": (_I, [_P, ctypes.c_char_p, ctypes.c_uint64, _L, _P, _P]),

@@ -798,8 +798,10 @@ int hyp_model_create(const hyp_model_desc* desc, hyp_model** out) {
   HYP_CHECK_ARG(desc && out, "null argument");
   HYP_CHECK_ARG(desc->kind == HYP_MODEL_HYPELCNN || desc->kind == HYP_MODEL_DUALCNN || desc->kind == HYP_MODEL_CONCNN,
                 "unknown model kind");
-  if (desc->kind != HYP_MODEL_HYPELCNN && desc->precision_mode != HYP_PRECISION_3XTF32)
-    return fail(HYP_E_UNSUPPORTED, "hyp_model_create: DUALCNN / CONCNN are built for the tensor-core engine (HYP_PRECISION_3XTF32) only");
+  const bool tensor_core = desc->precision_mode == HYP_PRECISION_3XTF32 || desc->precision_mode == HYP_PRECISION_3XF16 ||
+                           desc->precision_mode == HYP_PRECISION_BF16;
+  if (desc->kind != HYP_MODEL_HYPELCNN && !tensor_core)
+    return fail(HYP_E_UNSUPPORTED, "hyp_model_create: DUALCNN / CONCNN are built for the tensor-core engine only");
   HYP_CHECK_ARG(desc->patch >= 1 && desc->patch % 2 == 1 && desc->patch <= 15, "patch must be odd, 1..15");
   HYP_CHECK_ARG(desc->channels >= 1 && desc->classes >= 2 && desc->classes <= 255, "channels/classes out of range");
   HYP_CHECK_ARG(desc->filter_count >= 8, "filter_count out of range");
@@ -807,8 +809,8 @@ int hyp_model_create(const hyp_model_desc* desc, hyp_model** out) {
                 "levels out of range");
   HYP_CHECK_ARG(desc->max_batch >= 1, "max_batch must be positive");
   HYP_CHECK_ARG(desc->drop_out_ratio >= 0.f && desc->drop_out_ratio < 1.f, "drop_out_ratio in [0,1)");
-  if (desc->precision_mode != HYP_PRECISION_FP32 && desc->precision_mode != HYP_PRECISION_3XTF32)
-    return fail(HYP_E_UNSUPPORTED, "hyp_model_create: precision mode not built yet");
+  if (desc->precision_mode != HYP_PRECISION_FP32 && !tensor_core)
+    return fail(HYP_E_UNSUPPORTED, "hyp_model_create: unknown precision mode");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(HYP_E_CUDA, "hyp_model_create: no CUDA device (this library has no CPU fallback)");
@@ -819,7 +821,7 @@ int hyp_model_create(const hyp_model_desc* desc, hyp_model** out) {
   if (rc) return rc;
   rc = layout(*m);
   if (rc) return rc;
-  if (desc->precision_mode == HYP_PRECISION_3XTF32) {
+  if (tensor_core) {
     rc = hyp::tc::tc_layout(*m);
     if (rc) { hyp::tc::tc_destroy(*m); return rc; }
     m->ws_bytes = m->tc->ws_bytes;
@@ -1264,27 +1266,6 @@ int hyp_debug_schedule(const double* costs, int units, int groups, int windowed,
       group_of_unit[u] = g;
       rank_in_group[u] = (int32_t)i;
     }
-  return HYP_OK;
-}
-
-// host-only: the pair-tile plan of a level forward launch as flat tables (tests/test_level_pairs.py)
-int hyp_debug_plan_level_pairs(int P, int R, int fpad, int32_t* tiles, int tiles_cap, int32_t* segs, int segs_cap,
-                               int32_t* counts) {
-  HYP_CHECK_ARG(tiles && segs && counts && P >= 1 && R >= 1 && fpad >= 16 && fpad % 16 == 0 && R * fpad <= 128,
-                "bad argument (R * fpad <= 128)");
-  std::vector<tc::PairTile> t;
-  std::vector<tc::PairSeg> sg;
-  tc::plan_level_pairs(P, R, fpad, t, sg);
-  counts[0] = (int32_t)t.size();
-  counts[1] = (int32_t)sg.size();
-  HYP_CHECK_ARG((int)t.size() <= tiles_cap && (int)sg.size() <= segs_cap, "output tables too small");
-  for (size_t i = 0; i < t.size(); i++) {
-    tiles[4 * i] = t[i].p1; tiles[4 * i + 1] = t[i].p2; tiles[4 * i + 2] = t[i].seg_begin; tiles[4 * i + 3] = t[i].seg_count;
-  }
-  for (size_t i = 0; i < sg.size(); i++) {
-    segs[6 * i] = sg[i].q; segs[6 * i + 1] = sg[i].n1; segs[6 * i + 2] = sg[i].n2; segs[6 * i + 3] = sg[i].brow1;
-    segs[6 * i + 4] = sg[i].brow2; segs[6 * i + 5] = sg[i].dcol;
-  }
   return HYP_OK;
 }
 

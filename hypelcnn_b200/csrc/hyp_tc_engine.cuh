@@ -50,6 +50,7 @@ struct TcLayer {
   int wf_rows = 0, wf_ld = 0, wd_rows = 0, wd_ld = 0;
   TcLaunch fwd, dg, wg;
   int stats_rows = 0;
+  size_t gzs_off = 0;  // OP_F16X3: [0] bits of the |gz| bound, [1] the power-of-two gz scale, [2] its inverse (4 floats)
 };
 
 struct TcState {
@@ -67,6 +68,14 @@ struct TcState {
   size_t segs_cap = 0, tiles_cap = 0;
   int planned_B = -1;
   bool pack_cleared = false;
+  // operand format of every GEMM of the model (hyp_tc.cuh OP_*), K elements per 128-byte block, and the power of two
+  // the packed weights are multiplied by before a 16-bit split (undone in the forward / dgrad epilogues)
+  int op = OP_TF32X3, kbe = 32;
+  float w_scale = 1.f;
+  size_t gzs_off = 0, gzs_bytes = 0;
+  int rk(int v) const { return (int)align_up((size_t)v, (size_t)kbe); }                  // K padding
+  int rc(int v) const { return (int)align_up((size_t)v, (size_t)(op == OP_TF32X3 ? 4 : 8)); }  // row pitch: 16-byte rows
+  size_t op_bytes(size_t elems) const { return (size_t)op_planes(op) * op_esize(op) * elems; }   // operand-only buffers
 };
 
 inline int r16(int v) { return (int)align_up((size_t)v, 16); }
@@ -85,6 +94,11 @@ static float* tc_plane0(const hyp_model& m, int t) {
 }
 static float* tc_plane1(const hyp_model& m, int t) { return tc_plane0(m, t) + m.tc->tt[t].plane_elems; }
 static float* tc_grad(const hyp_model& m, int t) { return reinterpret_cast<float*>(m.ws + m.tc->tt[t].g_off); }
+// first GEMM operand plane of an activation tensor: the value plane itself (3xTF32) or the 16-bit planes that live in
+// the second region
+static void* tc_operand(const hyp_model& m, int t) {
+  return m.tc->op == OP_TF32X3 ? static_cast<void*>(tc_plane0(m, t)) : static_cast<void*>(tc_plane1(m, t));
+}
 
 // launch shape of the vectorised elementwise kernels: TX column groups of 4 channels per block row,
 // 256 / TX row lanes, `rblocks` row blocks of `rpb` rows
@@ -111,6 +125,10 @@ static inline EwGrid ew_grid2(int cols, int64_t rows) {
 static int tc_layout(hyp_model& m) {
   m.tc = new TcState();
   TcState& S = *m.tc;
+  S.op = m.d.precision_mode == HYP_PRECISION_3XF16 ? OP_F16X3 : (m.d.precision_mode == HYP_PRECISION_BF16 ? OP_BF16 : OP_TF32X3);
+  S.kbe = op_kbe(S.op);
+  // weights are O(1e-2): x 2^8 puts their fp16 remainders into the normal range (|w| must stay below 255)
+  S.w_scale = S.op == OP_F16X3 ? 256.f : 1.f;
   const size_t Bm = (size_t)m.d.max_batch;
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -124,7 +142,7 @@ static int tc_layout(hyp_model& m) {
     TcTensor& T = S.tt[t];
     T.PP = m.tensors[t].rows_per_sample;
     T.C = m.tensors[t].C;
-    T.Cp = r4(T.C);
+    T.Cp = S.rc(T.C);
     T.plane_elems = align_up(Bm * T.PP * T.Cp, 64);
     T.a_off = take(2 * T.plane_elems * sizeof(float));
     if (m.tensors[t].needs_grad) T.g_off = take(T.plane_elems * sizeof(float));
@@ -159,10 +177,10 @@ static int tc_layout(hyp_model& m) {
     T.kind = flatten ? 2 : (level ? 1 : 0);
     if (T.kind == 0) {
       const int Cin = tin.C;
-      T.Kp = r32(Cin);
+      T.Kp = S.rk(Cin);
       T.Gp = tout.Cp;
       T.wf_rows = r16(L.Cout); T.wf_ld = T.Kp;
-      T.wd_rows = r16(Cin); T.wd_ld = r32(L.Cout);
+      T.wd_rows = r16(Cin); T.wd_ld = S.rk(L.Cout);
       T.wf_off = take_pack((int64_t)T.wf_rows * T.wf_ld);
       T.wd_off = take_pack((int64_t)T.wd_rows * T.wd_ld);
       PackJob j{};
@@ -186,8 +204,8 @@ static int tc_layout(hyp_model& m) {
       T.ft = (int)cdiv(L.f, T.nt);
       T.NS = T.R * T.nt;
       T.fpad = r16(T.ft);
-      T.Kp = r32(Cin);
-      T.Gp = r32(T.NS * T.fpad);
+      T.Kp = S.rk(Cin);
+      T.Gp = S.rk(T.NS * T.fpad);
       T.Cq = r16(Cin);
       // taps reach max(|dy|, |dx|) <= h: the largest kernel's radius, at most P - 1 (a 5x5 kernel on a 3x3 patch still
       // connects pixel 0 to pixel 2); tap index = (dy + h) * TW + (dx + h)
@@ -223,11 +241,11 @@ static int tc_layout(hyp_model& m) {
       T.stats_rows = (int)(tout.PP * cdiv((int64_t)Bm, 128));
     } else {
       const int Ct = tin.C;
-      T.Kp = r32(Ct);
+      T.Kp = S.rk(Ct);
       T.Gp = tout.Cp;
       T.Cq = r16(Ct);
       T.wf_rows = r16(L.Cout); T.wf_ld = tin.PP * T.Kp;
-      T.wd_rows = tin.PP * T.Cq; T.wd_ld = r32(L.Cout);
+      T.wd_rows = tin.PP * T.Cq; T.wd_ld = S.rk(L.Cout);
       T.wf_off = take_pack((int64_t)T.wf_rows * T.wf_ld);
       T.wd_off = take_pack((int64_t)T.wd_rows * T.wd_ld);
       PackJob j{};
@@ -242,14 +260,17 @@ static int tc_layout(hyp_model& m) {
     }
     gz_max = std::max(gz_max, rows_out * (size_t)T.Gp);
     part_max = std::max(part_max, (size_t)T.stats_rows * 2 * L.Cout);
-    bpart_max = std::max(bpart_max, (size_t)(ew_grid2(L.Cout, (int64_t)rows_out).rblocks + 1) * 2 * L.Cout);
+    bpart_max = std::max(bpart_max, (size_t)(ew_grid2(L.Cout, (int64_t)rows_out).rblocks + 1) * 4 * L.Cout);
   }
   S.gz_plane_elems = align_up(gz_max, 64);
-  S.gz_off = take(2 * S.gz_plane_elems * sizeof(float));
+  S.gz_off = take(S.op_bytes(S.gz_plane_elems));
+  S.gzs_bytes = m.layers.size() * 4 * sizeof(float);  // one contiguous array: cleared with one memset per backward
+  S.gzs_off = take(S.gzs_bytes);
+  for (size_t li = 0; li < m.layers.size(); li++) S.tl[li].gzs_off = S.gzs_off + li * 4 * sizeof(float);
   S.part_off = take(part_max * sizeof(float));
   S.bpart_off = take(bpart_max * sizeof(float));
   S.pack_plane_elems = align_up((size_t)pk, 64);
-  S.pack_off = take(2 * S.pack_plane_elems * sizeof(float));
+  S.pack_off = take(S.op_bytes(S.pack_plane_elems));
   S.ce_off = take(Bm * sizeof(float));
   S.mse_off = take(256);
   S.dbg_off = take(dbg_max * sizeof(float));
@@ -279,7 +300,7 @@ static int tc_bind(hyp_model& m) {
     HYP_CUDA(cudaMalloc(&S.job_tiles_dev, S.job_tile_first.size() * sizeof(int)));
     HYP_CUDA(cudaMemcpy(S.job_tiles_dev, S.job_tile_first.data(), S.job_tile_first.size() * sizeof(int), cudaMemcpyHostToDevice));
   }
-  HYP_CUDA(cudaMemset(m.ws + S.pack_off, 0, 2 * S.pack_plane_elems * sizeof(float)));
+  HYP_CUDA(cudaMemset(m.ws + S.pack_off, 0, S.op_bytes(S.pack_plane_elems)));
   for (size_t li = 0; li < m.layers.size(); li++)
     if (m.layers[li].bias_mode) {  // no normaliser: z + biases is the (mean 0, rstd 1, beta = biases) case of the BN kernels
       const int C = m.layers[li].Cout;
@@ -309,9 +330,9 @@ static void finish_launch(PlanBuf& pb, TcLaunch& l) {
 }
 
 // wgrad (MN-major) launches run as CTA pairs over two adjacent 128-row tiles of the M side when their count is even
-// (the pair shares its gz columns); B rows reserved per stage: 32-column boxes covering n / cg columns, per CTA
+// (the pair shares its gz columns); B rows reserved per stage: boxes of kb columns covering n / cg columns, per CTA
 static inline int wg_cg(int mt) { return (mt % 2 == 0) ? 2 : 1; }
-static inline int wg_brows(int n_mma, int cg) { return cg * (int)cdiv(n_mma / cg, 32) * 32; }
+static inline int wg_brows(int n_mma, int cg, int kb) { return cg * (int)cdiv(n_mma / cg, kb) * kb; }
 
 // K-major launches run as CTA pairs (cta_group::2): consecutive tiles (2i, 2i+1) must share their
 // segment list.  A run of tiles that differ only in their row block is closed with a phantom
@@ -423,61 +444,13 @@ static void schedule_tiles(std::vector<TcTile>& tiles, size_t begin, const std::
   tiles.resize(begin);
   tiles.insert(tiles.end(), out.begin(), out.end());
 }
-// ---- groundwork for the next round ("level forward"): pair tiles --------------------------------
-// One tile = two horizontally adjacent output positions p1, p2 = p1 + 1 (a position left over at the end of an odd
-// row runs alone).  TMEM columns [0, W) hold p1 with the slot order MIRRORED (smallest kernel first), [W, 2W) hold p2
-// in the normal order (largest kernel first), W = R * fpad <= 128.  A tap of ring r feeds the (R - r) largest
-// kernels, i.e. the LAST n1 = (R - r1) * fpad columns of p1's half and the FIRST n2 = (R - r2) * fpad of p2's: an
-// input position q that both outputs use is ONE MMA of N = n1 + n2 into the contiguous range [W - n1, W + n2), its B
-// operand = the last n1 rows of tap (q - p1) in a mirrored copy of the packed weights followed by the first n2 rows
-// of tap (q - p2) in the normal copy.  Pure planning code (no device state): tests/test_level_pairs.py replays the
-// plan in numpy against a direct SAME convolution.  Not wired into tc_plan yet — the kernel still needs a per-segment
-// accumulator column offset and B assembled from two box sets.
-struct PairSeg { int q, n1, n2, brow1, brow2, dcol; };   // brow1: row in the mirrored copy, brow2: row in the normal copy
-struct PairTile { int p1, p2, seg_begin, seg_count; };   // p2 = -1: single position
-static void plan_level_pairs(int P, int R, int fpad, std::vector<PairTile>& tiles, std::vector<PairSeg>& segs) {
-  const int h = std::min(R - 1, P - 1), TW = 2 * h + 1, W = R * fpad;
-  auto ring_of = [&](int p, int q, int& tap) {   // ring of the tap that connects input q to output p, -1 if none
-    const int dy = q / P - p / P, dx = q % P - p % P;
-    if (std::abs(dy) > h || std::abs(dx) > h) return -1;
-    tap = (dy + h) * TW + (dx + h);
-    return std::max(std::abs(dy), std::abs(dx));
-  };
-  for (int y = 0; y < P; y++)
-    for (int x = 0; x < P; x += 2) {
-      PairTile t;
-      t.p1 = y * P + x;
-      t.p2 = x + 1 < P ? t.p1 + 1 : -1;
-      t.seg_begin = (int)segs.size();
-      // widest ranges first: (r1, r2) ascending by max ring keeps the epilogue's per-chunk column range shrinking
-      std::vector<std::pair<int, PairSeg>> found;
-      for (int q = 0; q < P * P; q++) {
-        int tap1 = 0, tap2 = 0;
-        const int r1 = ring_of(t.p1, q, tap1), r2 = t.p2 >= 0 ? ring_of(t.p2, q, tap2) : -1;
-        if (r1 < 0 && r2 < 0) continue;
-        PairSeg s;
-        s.q = q;
-        s.n1 = r1 >= 0 ? (R - r1) * fpad : 0;
-        s.n2 = r2 >= 0 ? (R - r2) * fpad : 0;
-        s.brow1 = tap1 * W + (W - s.n1);
-        s.brow2 = tap2 * W;
-        s.dcol = W - s.n1;
-        found.push_back({std::max(r1, r2), s});
-      }
-      std::stable_sort(found.begin(), found.end(),
-                       [](const std::pair<int, PairSeg>& a, const std::pair<int, PairSeg>& b) { return a.first < b.first; });
-      for (auto& f : found) segs.push_back(f.second);
-      t.seg_count = (int)segs.size() - t.seg_begin;
-      tiles.push_back(t);
-    }
-}
-
-static int map4(CUtensorMap* mp, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2,
+static thread_local int g_map_op = OP_TF32X3;  // operand format of the plan being built (tc_plan is single-threaded per model)
+static int map4(CUtensorMap* mp, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2,
                 uint64_t plane, uint32_t b0, uint32_t b1, bool mn) {
-  const uint64_t dims[4] = {d0, d1, d2, 2};
+  const uint64_t dims[4] = {d0, d1, d2, (uint64_t)op_planes(g_map_op)};
   const uint64_t strides[3] = {s1, s2, plane};
   const uint32_t box[4] = {b0, b1, 1, 1};
-  return make_map(mp, base, dims, strides, box, mn);
+  return make_map(mp, base, dims, strides, box, mn, g_map_op);
 }
 
 // split `total` output columns into the fewest tiles of <= 256, each a multiple of 16 wide
@@ -492,8 +465,11 @@ static int tc_plan(hyp_model& m, int64_t B) {
   PlanBuf pb;
   const int nbt = (int)cdiv(B, 128);
   const int CG = TC_CG_KMAJOR;
-  float* pack0 = reinterpret_cast<float*>(m.ws + S.pack_off);
-  float* gz0 = reinterpret_cast<float*>(m.ws + S.gz_off);
+  const int KB = S.kbe, esz = op_esize(S.op);  // K elements per 128-byte block, bytes per operand element
+  g_map_op = S.op;
+  // packed weights / gz hold operand planes only; element offsets -> pointers
+  auto pk = [&](int64_t off) -> const void* { return m.ws + S.pack_off + (size_t)off * esz; };
+  const void* gz0 = m.ws + S.gz_off;
   int rc;
   for (size_t li = 0; li < m.layers.size(); li++) {
     Layer& L = m.layers[li];
@@ -509,21 +485,21 @@ static int tc_plan(hyp_model& m, int64_t B) {
     const TcTensor& tin = S.tt[L.in_t];
     const TcTensor& tout = S.tt[L.out_t];
     const bool need_dgrad = m.tensors[L.in_t].needs_grad;
-    const float* a0 = tc_plane0(m, L.in_t);
+    const void* a0 = tc_operand(m, L.in_t);
     const int64_t rows_in = B * tin.PP, rows_out = B * tout.PP;
     if (T.kind == 0) {
       const int Cin = tin.C, Cout = L.Cout;
       // ---------------- forward ----------------
       int ntn, nw;
       n_tiling(Cout, ntn, nw);
-      if ((rc = map4(&T.fwd.tmA, a0, Cin, rows_in, 1, tin.Cp, (uint64_t)rows_in * tin.Cp, tin.plane_elems, 32, 128, false))) return rc;
-      if ((rc = map4(&T.fwd.tmB, pack0 + T.wf_off, T.wf_ld, T.wf_rows, 1, T.wf_ld, (uint64_t)T.wf_rows * T.wf_ld,
-                     S.pack_plane_elems, 32, nw / CG, false))) return rc;
+      if ((rc = map4(&T.fwd.tmA, a0, Cin, rows_in, 1, tin.Cp, (uint64_t)rows_in * tin.Cp, tin.plane_elems, KB, 128, false))) return rc;
+      if ((rc = map4(&T.fwd.tmB, pk(T.wf_off), T.wf_ld, T.wf_rows, 1, T.wf_ld, (uint64_t)T.wf_rows * T.wf_ld,
+                     S.pack_plane_elems, KB, nw / CG, false))) return rc;
       T.fwd.mn = false; T.fwd.cg = CG; T.fwd.b_rows = nw; T.fwd.bn = nw; T.fwd.tile0 = (int)pb.tiles.size();
       const int seg0 = (int)pb.segs.size();
       for (int j = 0; j < ntn; j++) {
         TcSeg s{};
-        s.b1 = j * nw; s.nk = T.Kp / 32; s.n_mma = r16(std::min(nw, Cout - j * nw)); s.nb = 1;
+        s.b1 = j * nw; s.nk = T.Kp / KB; s.n_mma = r16(std::min(nw, Cout - j * nw)); s.nb = 1;
         pb.segs.push_back(s);
       }
       const int nrt = (int)cdiv(rows_out, 128);
@@ -532,7 +508,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
           const size_t run = pb.tiles.size();
           for (int rt = rt2; rt < std::min(nrt, rt2 + CG); rt++) {
             TcTile t = blank_tile();
-            t.seg_begin = seg0 + j; t.seg_count = 1; t.total_kb = T.Kp / 32;
+            t.seg_begin = seg0 + j; t.seg_count = 1; t.total_kb = T.Kp / KB;
             t.m_valid = (int)std::min<int64_t>(128, rows_out - (int64_t)rt * 128);
             t.ncb = 1; t.ld_out = tout.Cp; t.stats_row = rt; t.a1_add = rt * 128;
             t.cb[0].out_off = (int64_t)rt * 128 * tout.Cp + j * nw;
@@ -547,14 +523,14 @@ static int tc_plan(hyp_model& m, int64_t B) {
       // ---------------- dgrad ----------------
       if (need_dgrad) {
         n_tiling(Cin, ntn, nw);
-        if ((rc = map4(&T.dg.tmA, gz0, Cout, rows_out, 1, T.Gp, (uint64_t)rows_out * T.Gp, S.gz_plane_elems, 32, 128, false))) return rc;
-        if ((rc = map4(&T.dg.tmB, pack0 + T.wd_off, T.wd_ld, T.wd_rows, 1, T.wd_ld, (uint64_t)T.wd_rows * T.wd_ld,
-                       S.pack_plane_elems, 32, nw / CG, false))) return rc;
+        if ((rc = map4(&T.dg.tmA, gz0, Cout, rows_out, 1, T.Gp, (uint64_t)rows_out * T.Gp, S.gz_plane_elems, KB, 128, false))) return rc;
+        if ((rc = map4(&T.dg.tmB, pk(T.wd_off), T.wd_ld, T.wd_rows, 1, T.wd_ld, (uint64_t)T.wd_rows * T.wd_ld,
+                       S.pack_plane_elems, KB, nw / CG, false))) return rc;
         T.dg.mn = false; T.dg.cg = CG; T.dg.b_rows = nw; T.dg.bn = nw; T.dg.tile0 = (int)pb.tiles.size();
         const int dseg0 = (int)pb.segs.size();
         for (int j = 0; j < ntn; j++) {
           TcSeg s{};
-          s.b1 = j * nw; s.nk = T.wd_ld / 32; s.n_mma = r16(std::min(nw, Cin - j * nw)); s.nb = 1;
+          s.b1 = j * nw; s.nk = T.wd_ld / KB; s.n_mma = r16(std::min(nw, Cin - j * nw)); s.nb = 1;
           pb.segs.push_back(s);
         }
         for (int rt2 = 0; rt2 < nrt; rt2 += CG)
@@ -562,7 +538,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
             const size_t run = pb.tiles.size();
             for (int rt = rt2; rt < std::min(nrt, rt2 + CG); rt++) {
               TcTile t = blank_tile();
-              t.seg_begin = dseg0 + j; t.seg_count = 1; t.total_kb = T.wd_ld / 32;
+              t.seg_begin = dseg0 + j; t.seg_count = 1; t.total_kb = T.wd_ld / KB;
               t.m_valid = (int)std::min<int64_t>(128, rows_out - (int64_t)rt * 128);
               t.ncb = 1; t.ld_out = tin.Cp; t.a1_add = rt * 128;
               t.cb[0].out_off = (int64_t)rt * 128 * tin.Cp + j * nw;
@@ -577,11 +553,11 @@ static int tc_plan(hyp_model& m, int64_t B) {
       {
         n_tiling(Cout, ntn, nw);
         const int mt = (int)cdiv(Cin, 128);
-        if ((rc = map4(&T.wg.tmA, a0, Cin, rows_in, 1, tin.Cp, (uint64_t)rows_in * tin.Cp, tin.plane_elems, 32, 32, true))) return rc;
-        if ((rc = map4(&T.wg.tmB, gz0, Cout, rows_out, 1, T.Gp, (uint64_t)rows_out * T.Gp, S.gz_plane_elems, 32, 32, true))) return rc;
+        if ((rc = map4(&T.wg.tmA, a0, Cin, rows_in, 1, tin.Cp, (uint64_t)rows_in * tin.Cp, tin.plane_elems, KB, KB, true))) return rc;
+        if ((rc = map4(&T.wg.tmB, gz0, Cout, rows_out, 1, T.Gp, (uint64_t)rows_out * T.Gp, S.gz_plane_elems, KB, KB, true))) return rc;
         T.wg.mn = true; T.wg.bn = 32; T.wg.b_rows = 0; T.wg.tile0 = (int)pb.tiles.size();
         T.wg.cg = wg_cg(mt);
-        const int kblocks = (int)cdiv(rows_out, 32);
+        const int kblocks = (int)cdiv(rows_out, KB);
         int ksplit = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(2 * tc_sm_count(), mt * ntn), std::max(1, kblocks / 4)));
         {  // nudge the split so that the units fill the persistent grid evenly (units / groups just below an integer)
           const double groups = (double)tc_sm_count() / T.wg.cg, units0 = (double)mt * ntn / T.wg.cg;
@@ -599,9 +575,9 @@ static int tc_plan(hyp_model& m, int64_t B) {
             for (int im = 0; im < mt; im++) {  // adjacent M tiles are consecutive: CTA pairs share (j, kb0)
               const int width = std::min(nw, Cout - j * nw);
               TcSeg s{};
-              s.a1 = kb0 * 32; s.b0 = j * nw; s.b1 = kb0 * 32;
-              s.nk = std::min(kb_per, kblocks - kb0); s.n_mma = r16(width); s.nb = (int)cdiv(s.n_mma, 32);
-              T.wg.b_rows = std::max(T.wg.b_rows, wg_brows(s.n_mma, T.wg.cg));
+              s.a1 = kb0 * KB; s.b0 = j * nw; s.b1 = kb0 * KB;
+              s.nk = std::min(kb_per, kblocks - kb0); s.n_mma = r16(width); s.nb = (int)cdiv(s.n_mma, KB);
+              T.wg.b_rows = std::max(T.wg.b_rows, wg_brows(s.n_mma, T.wg.cg, KB));
               TcTile t = blank_tile();
               t.a0_add = im * 128;
               t.seg_begin = (int)pb.segs.size(); t.seg_count = 1; t.total_kb = s.nk;
@@ -619,9 +595,9 @@ static int tc_plan(hyp_model& m, int64_t B) {
       const int spg = std::min(std::min(256 / fpad, TC_MAX_CB), NS);  // slots per accumulator group
       const int ngroups = (int)cdiv(NS, spg);
       // ---------------- forward ----------------
-      if ((rc = map4(&T.fwd.tmA, a0, Cin, B, PP, tin.Cp, (uint64_t)B * tin.Cp, tin.plane_elems, 32, 128, false))) return rc;
-      if ((rc = map4(&T.fwd.tmB, pack0 + T.wf_off, T.wf_ld, T.wf_rows, 1, T.wf_ld, (uint64_t)T.wf_rows * T.wf_ld,
-                     S.pack_plane_elems, 32, fpad / CG, false))) return rc;
+      if ((rc = map4(&T.fwd.tmA, a0, Cin, B, PP, tin.Cp, (uint64_t)B * tin.Cp, tin.plane_elems, KB, 128, false))) return rc;
+      if ((rc = map4(&T.fwd.tmB, pk(T.wf_off), T.wf_ld, T.wf_rows, 1, T.wf_ld, (uint64_t)T.wf_rows * T.wf_ld,
+                     S.pack_plane_elems, KB, fpad / CG, false))) return rc;
       T.fwd.mn = false; T.fwd.cg = CG; T.fwd.b_rows = spg * fpad; T.fwd.bn = fpad; T.fwd.tile0 = (int)pb.tiles.size();
       // one segment list per (position, slot group); tiles are emitted batch-pair major so that a wave of
       // CTAs works on few batch rows x all positions (the A rows stay in L2 across the taps that reuse
@@ -640,11 +616,11 @@ static int tc_plan(hyp_model& m, int64_t B) {
             if (nbx <= 0) continue;
             const int tap = (dy + h) * TW + (dx + h);
             TcSeg s{};
-            s.a2 = p + dy * P + dx; s.b1 = tap * NS * fpad; s.nk = T.Kp / 32; s.n_mma = nbx * fpad; s.nb = nbx;
+            s.a2 = p + dy * P + dx; s.b1 = tap * NS * fpad; s.nk = T.Kp / KB; s.n_mma = nbx * fpad; s.nb = nbx;
             pb.segs.push_back(s);
           }
           const int nseg = (int)pb.segs.size() - seg0;
-          runs.push_back({seg0, nseg, nseg * (T.Kp / 32), p, g});
+          runs.push_back({seg0, nseg, nseg * (T.Kp / KB), p, g});
         }
       }
       std::stable_sort(runs.begin(), runs.end(), [](const Run& a, const Run& b) { return a.tkb > b.tkb; });
@@ -674,9 +650,9 @@ static int tc_plan(hyp_model& m, int64_t B) {
       if (need_dgrad) {
         int ntn, nw;
         n_tiling(Cin, ntn, nw);
-        if ((rc = map4(&T.dg.tmA, gz0, T.Gp, B, PP, T.Gp, (uint64_t)B * T.Gp, S.gz_plane_elems, 32, 128, false))) return rc;
-        if ((rc = map4(&T.dg.tmB, pack0 + T.wd_off, T.wd_ld, T.wd_rows, 1, T.wd_ld, (uint64_t)T.wd_rows * T.wd_ld,
-                       S.pack_plane_elems, 32, nw / CG, false))) return rc;
+        if ((rc = map4(&T.dg.tmA, gz0, T.Gp, B, PP, T.Gp, (uint64_t)B * T.Gp, S.gz_plane_elems, KB, 128, false))) return rc;
+        if ((rc = map4(&T.dg.tmB, pk(T.wd_off), T.wd_ld, T.wd_rows, 1, T.wd_ld, (uint64_t)T.wd_rows * T.wd_ld,
+                       S.pack_plane_elems, KB, nw / CG, false))) return rc;
         T.dg.mn = false; T.dg.cg = CG; T.dg.b_rows = nw; T.dg.bn = nw; T.dg.tile0 = (int)pb.tiles.size();
         struct DRun { int seg0, nseg, tkb, p, j; };
         std::vector<DRun> druns;
@@ -691,7 +667,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
               const int tap = (dy + h) * TW + (dx + h);
               TcSeg s{};
               s.a2 = p - (dy * P + dx); s.b1 = tap * T.Cq + j * nw;
-              s.nk = (int)cdiv((R - ring) * nt * fpad, 32); s.n_mma = r16(std::min(nw, Cin - j * nw)); s.nb = 1;
+              s.nk = (int)cdiv((R - ring) * nt * fpad, KB); s.n_mma = r16(std::min(nw, Cin - j * nw)); s.nb = 1;
               tkb += s.nk;
               pb.segs.push_back(s);
             }
@@ -717,19 +693,19 @@ static int tc_plan(hyp_model& m, int64_t B) {
       }
       // ---------------- wgrad ----------------
       {
-        if ((rc = map4(&T.wg.tmA, a0, Cin, B, PP, tin.Cp, (uint64_t)B * tin.Cp, tin.plane_elems, 32, 32, true))) return rc;
-        if ((rc = map4(&T.wg.tmB, gz0, T.Gp, B, PP, T.Gp, (uint64_t)B * T.Gp, S.gz_plane_elems, 32, 32, true))) return rc;
+        if ((rc = map4(&T.wg.tmA, a0, Cin, B, PP, tin.Cp, (uint64_t)B * tin.Cp, tin.plane_elems, KB, KB, true))) return rc;
+        if ((rc = map4(&T.wg.tmB, gz0, T.Gp, B, PP, T.Gp, (uint64_t)B * T.Gp, S.gz_plane_elems, KB, KB, true))) return rc;
         T.wg.mn = true; T.wg.bn = 32; T.wg.b_rows = 0; T.wg.tile0 = (int)pb.tiles.size();
         const int mt = (int)cdiv(Cin, 128);
         T.wg.cg = wg_cg(mt);
-        const int nkb = (int)cdiv(B, 32);
+        const int nkb = (int)cdiv(B, KB);
         int64_t pairs = 0;
         for (auto& tp : taps) pairs += (int64_t)(P - std::abs(tp.first)) * (P - std::abs(tp.second));
         // Batch slices: every (tap, position) pair re-reads a[p + tap] and gz[p]; the whole level (activations +
         // gradients, both planes) is several hundred MB, so the K range (batch rows) is cut into slices whose
         // operands fit L2 and all tiles of a slice run in the same waves -> each row crosses HBM about once.
         // The slices accumulate into the weight gradient with the epilogue's atomics (split-K).
-        const double level_bytes = (double)B * PP * (tin.Cp + T.Gp) * 2.0 * sizeof(float);
+        const double level_bytes = (double)B * PP * (tin.Cp + T.Gp) * (double)(op_planes(S.op) * esz);
         int nslice = 1;
         static const double slice_bytes = getenv("HYP_WG_SLICE_MB") ? atof(getenv("HYP_WG_SLICE_MB")) * 1e6 : 128e6;
         while (nslice < nkb && level_bytes / nslice > slice_bytes) nslice *= 2;
@@ -762,10 +738,10 @@ static int tc_plan(hyp_model& m, int64_t B) {
                   t.a0_add = im * 128;
                   for (int pp : ps) {
                     TcSeg s{};
-                    s.a1 = kb0 * 32; s.a2 = pp + dy * P + dx;
-                    s.b0 = s0 * fpad; s.b1 = kb0 * 32; s.b2 = pp;
-                    s.nk = kbn; s.n_mma = r16(ncols); s.nb = (int)cdiv(s.n_mma, 32);
-                    T.wg.b_rows = std::max(T.wg.b_rows, wg_brows(s.n_mma, T.wg.cg));
+                    s.a1 = kb0 * KB; s.a2 = pp + dy * P + dx;
+                    s.b0 = s0 * fpad; s.b1 = kb0 * KB; s.b2 = pp;
+                    s.nk = kbn; s.n_mma = r16(ncols); s.nb = (int)cdiv(s.n_mma, KB);
+                    T.wg.b_rows = std::max(T.wg.b_rows, wg_brows(s.n_mma, T.wg.cg, KB));
                     t.total_kb += s.nk;
                     pb.segs.push_back(s);
                   }
@@ -793,15 +769,15 @@ static int tc_plan(hyp_model& m, int64_t B) {
       int ntn, nw;
       n_tiling(Cout, ntn, nw);
       // ---------------- forward ----------------
-      if ((rc = map4(&T.fwd.tmA, a0, Ct, B, PP, tin.Cp, (uint64_t)B * tin.Cp, tin.plane_elems, 32, 128, false))) return rc;
-      if ((rc = map4(&T.fwd.tmB, pack0 + T.wf_off, T.wf_ld, T.wf_rows, 1, T.wf_ld, (uint64_t)T.wf_rows * T.wf_ld,
-                     S.pack_plane_elems, 32, nw / CG, false))) return rc;
+      if ((rc = map4(&T.fwd.tmA, a0, Ct, B, PP, tin.Cp, (uint64_t)B * tin.Cp, tin.plane_elems, KB, 128, false))) return rc;
+      if ((rc = map4(&T.fwd.tmB, pk(T.wf_off), T.wf_ld, T.wf_rows, 1, T.wf_ld, (uint64_t)T.wf_rows * T.wf_ld,
+                     S.pack_plane_elems, KB, nw / CG, false))) return rc;
       T.fwd.mn = false; T.fwd.cg = CG; T.fwd.b_rows = nw; T.fwd.bn = nw; T.fwd.tile0 = (int)pb.tiles.size();
       const int fseg0 = (int)pb.segs.size();
       for (int j = 0; j < ntn; j++)
         for (int pos = 0; pos < PP; pos++) {
           TcSeg s{};
-          s.a2 = pos; s.b0 = pos * T.Kp; s.b1 = j * nw; s.nk = T.Kp / 32;
+          s.a2 = pos; s.b0 = pos * T.Kp; s.b1 = j * nw; s.nk = T.Kp / KB;
           s.n_mma = r16(std::min(nw, Cout - j * nw)); s.nb = 1;
           pb.segs.push_back(s);
         }
@@ -810,7 +786,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
           const size_t run = pb.tiles.size();
           for (int bt = bt2; bt < std::min(nbt, bt2 + CG); bt++) {
             TcTile t = blank_tile();
-            t.seg_begin = fseg0 + j * PP; t.seg_count = PP; t.total_kb = PP * (T.Kp / 32);
+            t.seg_begin = fseg0 + j * PP; t.seg_count = PP; t.total_kb = PP * (T.Kp / KB);
             t.m_valid = (int)std::min<int64_t>(128, B - (int64_t)bt * 128);
             t.ncb = 1; t.ld_out = tout.Cp; t.stats_row = bt; t.a1_add = bt * 128;
             t.cb[0].out_off = (int64_t)bt * 128 * tout.Cp + j * nw;
@@ -824,17 +800,17 @@ static int tc_plan(hyp_model& m, int64_t B) {
       T.stats_rows = nbt;
       // ---------------- dgrad ----------------
       if (need_dgrad) {
-        if ((rc = map4(&T.dg.tmA, gz0, Cout, B, 1, T.Gp, (uint64_t)B * T.Gp, S.gz_plane_elems, 32, 128, false))) return rc;
+        if ((rc = map4(&T.dg.tmA, gz0, Cout, B, 1, T.Gp, (uint64_t)B * T.Gp, S.gz_plane_elems, KB, 128, false))) return rc;
         int dtn, dw;  // column tiles over the flattened tensor's channels
         n_tiling(Ct, dtn, dw);
-        if ((rc = map4(&T.dg.tmB, pack0 + T.wd_off, T.wd_ld, T.wd_rows, 1, T.wd_ld, (uint64_t)T.wd_rows * T.wd_ld,
-                       S.pack_plane_elems, 32, dw / CG, false))) return rc;
+        if ((rc = map4(&T.dg.tmB, pk(T.wd_off), T.wd_ld, T.wd_rows, 1, T.wd_ld, (uint64_t)T.wd_rows * T.wd_ld,
+                       S.pack_plane_elems, KB, dw / CG, false))) return rc;
         T.dg.mn = false; T.dg.cg = CG; T.dg.b_rows = dw; T.dg.bn = dw; T.dg.tile0 = (int)pb.tiles.size();
         const int dseg0 = (int)pb.segs.size();
         for (int pos = 0; pos < PP; pos++)
           for (int jd = 0; jd < dtn; jd++) {
             TcSeg s{};
-            s.b1 = pos * T.Cq + jd * dw; s.nk = T.wd_ld / 32; s.n_mma = r16(std::min(dw, Ct - jd * dw)); s.nb = 1;
+            s.b1 = pos * T.Cq + jd * dw; s.nk = T.wd_ld / KB; s.n_mma = r16(std::min(dw, Ct - jd * dw)); s.nb = 1;
             pb.segs.push_back(s);
           }
         for (int bt2 = 0; bt2 < nbt; bt2 += CG)
@@ -843,7 +819,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
               const size_t run = pb.tiles.size();
               for (int bt = bt2; bt < std::min(nbt, bt2 + CG); bt++) {
                 TcTile t = blank_tile();
-                t.seg_begin = dseg0 + pos * dtn + jd; t.seg_count = 1; t.total_kb = T.wd_ld / 32;
+                t.seg_begin = dseg0 + pos * dtn + jd; t.seg_count = 1; t.total_kb = T.wd_ld / KB;
                 t.m_valid = (int)std::min<int64_t>(128, B - (int64_t)bt * 128);
                 t.ncb = 1; t.ld_out = tin.Cp; t.a1_add = bt * 128;
                 t.cb[0].out_off = ((int64_t)pos * B + (int64_t)bt * 128) * tin.Cp + jd * dw;
@@ -856,14 +832,14 @@ static int tc_plan(hyp_model& m, int64_t B) {
       }
       // ---------------- wgrad ----------------
       {
-        if ((rc = map4(&T.wg.tmA, a0, Ct, B, PP, tin.Cp, (uint64_t)B * tin.Cp, tin.plane_elems, 32, 32, true))) return rc;
-        if ((rc = map4(&T.wg.tmB, gz0, Cout, B, 1, T.Gp, (uint64_t)B * T.Gp, S.gz_plane_elems, 32, 32, true))) return rc;
+        if ((rc = map4(&T.wg.tmA, a0, Ct, B, PP, tin.Cp, (uint64_t)B * tin.Cp, tin.plane_elems, KB, KB, true))) return rc;
+        if ((rc = map4(&T.wg.tmB, gz0, Cout, B, 1, T.Gp, (uint64_t)B * T.Gp, S.gz_plane_elems, KB, KB, true))) return rc;
         T.wg.mn = true; T.wg.bn = 32; T.wg.b_rows = 0; T.wg.tile0 = (int)pb.tiles.size();
         const int mt = (int)cdiv(Ct, 128);
         T.wg.cg = wg_cg(mt);
         // K (= batch) pieces: the split that fills the persistent grid most evenly (the epilogue is atomic, so pieces
         // are free to land in any order); at least 8 K blocks per piece
-        const int kblocks = (int)cdiv(B, 32);
+        const int kblocks = (int)cdiv(B, KB);
         const double groups = (double)tc_sm_count() / T.wg.cg, units0 = (double)PP * ntn * mt / T.wg.cg;
         int ksplit = 1;
         double best = 1e30;
@@ -878,10 +854,10 @@ static int tc_plan(hyp_model& m, int64_t B) {
               for (int im = 0; im < mt; im++) {
                 const int width = std::min(nw, Cout - j * nw);
                 TcSeg s{};
-                s.a1 = kb0 * 32; s.a2 = pos; s.b0 = j * nw; s.b1 = kb0 * 32;
+                s.a1 = kb0 * KB; s.a2 = pos; s.b0 = j * nw; s.b1 = kb0 * KB;
                 s.nk = std::min(kb_per, kblocks - kb0); s.n_mma = r16(width);
-                s.nb = (int)cdiv(s.n_mma, 32);
-                T.wg.b_rows = std::max(T.wg.b_rows, wg_brows(s.n_mma, T.wg.cg));
+                s.nb = (int)cdiv(s.n_mma, KB);
+                T.wg.b_rows = std::max(T.wg.b_rows, wg_brows(s.n_mma, T.wg.cg, KB));
                 TcTile t = blank_tile();
                 t.a0_add = im * 128;
                 t.seg_begin = (int)pb.segs.size(); t.seg_count = 1; t.total_kb = s.nk;
@@ -914,12 +890,16 @@ static int tc_plan(hyp_model& m, int64_t B) {
   return HYP_OK;
 }
 
+// out_scale / out_scale_ptr: what the epilogue multiplies the accumulators by (undoes the operand scales of the 16-bit
+// formats: 1 / w_scale in forward, 1 / (w_scale * gz scale) in dgrad, 1 / gz scale in wgrad)
 static int tc_run(hyp_model& m, const TcLaunch& l, float* out, float* stats, int stats_ld, int epi, const char* tag,
-                  double flops, cudaStream_t st, const char* scope = nullptr) {
+                  double flops, cudaStream_t st, const char* scope = nullptr, float out_scale = 1.f,
+                  const float* out_scale_ptr = nullptr) {
   if (l.ntiles == 0) return HYP_OK;
   TcState& S = *m.tc;
   TcParams p{};
   p.segs = S.segs_dev; p.tiles = S.tiles_dev + l.tile0; p.out = out; p.stats = stats; p.stats_ld = stats_ld;
+  p.op = S.op; p.out_scale = out_scale; p.out_scale_ptr = out_scale_ptr;
   p.epi = epi; p.b_rows = l.b_rows; p.bn = l.bn; p.chunk_kb = 0; p.stages = 0;
   static const bool per_layer = getenv("HYP_PROF_LAYERS") != nullptr;
   std::string full = tag;
@@ -966,11 +946,12 @@ static int tc_forward(hyp_model& m, const float* x, int64_t B, bool training, bo
       TC_PROF("tc_prep_input_kernel", 12.0 * B * tx.PP * tx.C,
               (tc_prep_input_kernel<<<tc_grid(B * tx.PP * tx.C), 256, 0, st>>>(
                   x, (int)B, m.d.patch, m.d.channels, tn.x_c0, tn.x_crop, tn.P, tx.C, tx.Cp, tc_plane0(m, (int)t),
-                  tc_plane1(m, (int)t))));
+                  tc_plane1(m, (int)t), S.op, tx.plane_elems)));
     }
     TC_PROF("tc_pack_weights_kernel", 12.0 * S.pack_plane_elems,
             (tc_pack_weights_kernel<<<(unsigned)S.job_blocks, 256, 0, st>>>(
-                S.jobs_dev, S.job_tiles_dev, (int)S.jobs.size(), m.params, pack0, pack0 + S.pack_plane_elems)));
+                S.jobs_dev, S.job_tiles_dev, (int)S.jobs.size(), m.params, pack0, pack0 + S.pack_plane_elems, S.op,
+                S.pack_plane_elems, S.w_scale)));
   }
   const float keep_prob = m.keep_prob;
   float* part = reinterpret_cast<float*>(m.ws + S.part_off);
@@ -981,7 +962,7 @@ static int tc_forward(hyp_model& m, const float* x, int64_t B, bool training, bo
     const int64_t rows = B * tout.PP;
     float* Z = reinterpret_cast<float*>(m.ws + T.z_off);
     rc = tc_run(m, T.fwd, Z, (training && !L.bias_mode) ? part : nullptr, L.Cout, L.share == 2 ? EPI_ACCUM : EPI_STORE,
-                "tc_gemm_kernel/fwd", layer_flops(L, B), st, L.scope.c_str());
+                "tc_gemm_kernel/fwd", layer_flops(L, B), st, L.scope.c_str(), 1.f / S.w_scale);
     if (rc) return rc;
     if (L.share == 1) continue;  // the second part adds its product, then bias / activation run once
     float* mean = reinterpret_cast<float*>(m.ws + T.mean_off);
@@ -1002,6 +983,7 @@ static int tc_forward(hyp_model& m, const float* x, int64_t B, bool training, bo
     TcApplyArgs p{};
     p.z = Z; p.ldz = tout.Cp; p.mean = mean; p.rstd = rstd; p.beta = m.params + L.beta_off;
     p.hi = tc_plane0(m, L.out_t); p.lo = tc_plane1(m, L.out_t); p.ldo = tout.Cp;
+    p.op = S.op; p.op_plane = tout.plane_elems;
     p.rows = rows; p.C = L.Cout; p.act = L.act; p.alpha = m.d.lrelu_alpha;
     p.keep = (L.dropout && training) ? keep_prob : 1.f;
     p.seed = seed; p.stream_id = L.drop_stream;
@@ -1020,7 +1002,7 @@ static int tc_forward(hyp_model& m, const float* x, int64_t B, bool training, bo
     if (L.lrn) {
       TC_PROF("tc_lrn_fwd_kernel", 16.0 * rows * L.Cout,
               (tc_lrn_fwd_kernel<<<tc_grid(rows * 32), 256, 8 * L.Cout * sizeof(float), st>>>(
-                  p.hi, p.lo, reinterpret_cast<float*>(m.ws + T.u_off), tout.Cp, L.Cout, rows)));
+                  p.hi, p.lo, reinterpret_cast<float*>(m.ws + T.u_off), tout.Cp, L.Cout, rows, S.op, tout.plane_elems)));
     }
   }
   return HYP_OK;
@@ -1033,6 +1015,7 @@ static int tc_backward(hyp_model& m, const uint8_t* labels, int64_t B, float* lo
   std::vector<char> ginit(m.tensors.size(), 0);
   HYP_CUDA(cudaMemsetAsync(m.grads, 0, (size_t)m.n_params * sizeof(float), st));
   HYP_CUDA(cudaMemsetAsync(m.ws + S.mse_off, 0, 256, st));
+  if (S.op == OP_F16X3) HYP_CUDA(cudaMemsetAsync(m.ws + S.gzs_off, 0, S.gzs_bytes, st));  // |gz| bounds: atomic maxima
   float* ce = reinterpret_cast<float*>(m.ws + S.ce_off);
   double* mse_acc = reinterpret_cast<double*>(m.ws + S.mse_off);
   const TcTensor& tlog = S.tt[m.logits_t];
@@ -1056,8 +1039,8 @@ static int tc_backward(hyp_model& m, const uint8_t* labels, int64_t B, float* lo
   HYP_LAUNCHED();
 
   const float keep_prob = m.keep_prob;
-  float* gz0 = reinterpret_cast<float*>(m.ws + S.gz_off);
-  float* gz1 = gz0 + S.gz_plane_elems;
+  float* gz0 = reinterpret_cast<float*>(m.ws + S.gz_off);  // 16-bit formats: the start of the operand planes
+  float* gz1 = gz0 + S.gz_plane_elems;                     // (3xTF32 only)
   float* bpart = reinterpret_cast<float*>(m.ws + S.bpart_off);
   for (int li = nl - 1; li >= 0; li--) {
     Layer& L = m.layers[li];
@@ -1084,12 +1067,16 @@ static int tc_backward(hyp_model& m, const uint8_t* labels, int64_t B, float* lo
     float* s1 = reinterpret_cast<float*>(m.ws + T.s1_off);
     float* s2 = reinterpret_cast<float*>(m.ws + T.s2_off);
     p.s1 = s1; p.s2 = s2; p.gz_hi = gz0; p.gz_lo = gz1; p.ldgz = T.Gp;
+    p.op = S.op; p.gz_plane = S.gz_plane_elems;
+    float* gzs = reinterpret_cast<float*>(m.ws + T.gzs_off);
+    if (S.op == OP_F16X3) { p.gmax_bits = reinterpret_cast<unsigned int*>(gzs); p.gz_scale_out = gzs + 1; }
     p.gcols = T.kind == 1 ? T.Gp : L.Cout;
     p.fpad = T.kind == 1 ? T.fpad : 0; p.f = T.f; p.R = T.R; p.nt = T.nt; p.ft = T.ft;
     const EwGrid gr = ew_grid2(L.Cout, rows);
     TC_PROF("tc_bn_bwd_reduce_kernel", 8.0 * rows * L.Cout, TC_EW_DISPATCH(gr, tc_bn_bwd_reduce_v4_kernel, p, gr.rpb));
     tc_bn_bwd_finalize8_kernel<<<(unsigned)cdiv(L.Cout, 8), 8 * FIN_LANES, 0, st>>>(bpart, gr.rblocks, L.Cout, (double)rows, s1, s2,
-                                                                         m.grads + L.beta_off, L.bias_mode ? 1 : 0);
+                                                                         m.grads + L.beta_off, L.bias_mode ? 1 : 0, p.rstd,
+                                                                         S.op == OP_F16X3 ? reinterpret_cast<unsigned int*>(gzs) : nullptr);
     HYP_LAUNCHED();
     if (p.fpad == 0 || (p.f % 4 == 0 && p.ft % 4 == 0 && p.fpad % 4 == 0)) {
       const EwGrid ga = ew_grid2(p.gcols, rows);
@@ -1122,11 +1109,14 @@ static int tc_backward(hyp_model& m, const uint8_t* labels, int64_t B, float* lo
       ginit[r.src] = 1;
     }
     }
-    int rc = tc_run(m, T.wg, m.grads, nullptr, 0, EPI_ATOMIC, "tc_gemm_kernel/wgrad", layer_flops(L, B), st, L.scope.c_str());
+    // (a two-input FC's first part reuses the gz planes of the second part, processed just before: same scale slot)
+    const float* gz_inv = S.op == OP_F16X3 ? reinterpret_cast<const float*>(m.ws + S.tl[L.share == 1 ? li + 1 : li].gzs_off) + 2 : nullptr;
+    int rc = tc_run(m, T.wg, m.grads, nullptr, 0, EPI_ATOMIC, "tc_gemm_kernel/wgrad", layer_flops(L, B), st, L.scope.c_str(),
+                    1.f, gz_inv);
     if (rc) return rc;
     if (m.tensors[L.in_t].needs_grad) {
       rc = tc_run(m, T.dg, tc_grad(m, L.in_t), nullptr, 0, ginit[L.in_t] ? EPI_ACCUM : EPI_STORE, "tc_gemm_kernel/dgrad",
-                  layer_flops(L, B), st, L.scope.c_str());
+                  layer_flops(L, B), st, L.scope.c_str(), 1.f / S.w_scale, gz_inv);
       if (rc) return rc;
       ginit[L.in_t] = 1;
     }

@@ -1,8 +1,12 @@
 // HBM-bound kernels of the tensor-core path.  Activations live position-major:
 //   tensor[pos][b][ld]   (pos = h*P + w of the patch, b = sample, ld = channels padded to 4)
 // so every spatial tap of a k x k conv is a plain row-offset into the same matrix, and they
-// come as two fp32 planes: plane 0 = the value, plane 1 = TF32 rounding of what the tensor
-// core drops from plane 0 (its 13 low mantissa bits) — see hyp_tc.cuh.
+// come as an fp32 value plane followed by the GEMM operand planes of the model's operand format (hyp_tc.cuh OP_*):
+//   OP_TF32X3 : the value plane doubles as the TF32 "hi" operand (the tensor core ignores its 13 low mantissa
+//               bits); the second plane holds the TF32 rounding of what it drops
+//   OP_F16X3  : two fp16 planes (hi, lo) of plane_elems elements each, in the bytes of the second fp32 plane
+//   OP_BF16   : one bf16 plane there
+// `lo` below is always the start of that second region, `op_plane` the element stride between 16-bit planes.
 #pragma once
 #include "hyp_kernels.cuh"
 #include "hyp_tc.cuh"
@@ -14,10 +18,24 @@ __device__ __forceinline__ float tf32_lo(float a) {
   return tf32_rna(a - __uint_as_float(__float_as_uint(a) & 0xffffe000u));
 }
 
+// operand planes of one element / of 4 consecutive elements at index `idx` of a tensor whose second region starts at lo
+__device__ __forceinline__ void tc_store_operand(float* lo, size_t op_plane, int op, int64_t idx, float v) {
+  if (op == OP_TF32X3) lo[idx] = tf32_lo(v);
+  else store_op16(reinterpret_cast<uint16_t*>(lo) + idx, op_plane, op, v);
+}
+__device__ __forceinline__ void tc_store_operand4(float* lo, size_t op_plane, int op, int64_t idx, float v0, float v1, float v2,
+                                                  float v3) {
+  if (op == OP_TF32X3)
+    *reinterpret_cast<float4*>(lo + idx) = make_float4(tf32_lo(v0), tf32_lo(v1), tf32_lo(v2), tf32_lo(v3));
+  else
+    store_op16x4(reinterpret_cast<uint16_t*>(lo) + idx, op_plane, op, v0, v1, v2, v3);
+}
+
 // view of x [B][P0][P0][C0] (NHWC patches as the importer hands them over): channels [c0, c0 + C), window cropped
 // by `crop` pixels per side to P x P  -> planes [P*P][B][ld]
 __global__ void __launch_bounds__(256) tc_prep_input_kernel(const float* __restrict__ x, int B, int P0, int C0, int c0, int crop,
-                                                            int P, int C, int ld, float* __restrict__ hi, float* __restrict__ lo) {
+                                                            int P, int C, int ld, float* __restrict__ hi, float* __restrict__ lo,
+                                                            int op, size_t op_plane) {
   // one warp per (sample, pixel) row of C contiguous channels: the index arithmetic is per row, not per element
   const int PP = P * P, lane = threadIdx.x & 31;
   const int64_t rows = (int64_t)B * PP;
@@ -30,7 +48,7 @@ __global__ void __launch_bounds__(256) tc_prep_input_kernel(const float* __restr
     for (int c = lane; c < C; c += 32) {
       const float v = __ldg(src + c);
       hi[o + c] = v;
-      lo[o + c] = tf32_lo(v);
+      tc_store_operand(lo, op_plane, op, o + c, v);
     }
   }
 }
@@ -66,7 +84,8 @@ struct PackJob {
 // shared memory), the two planes are always written along k.
 __global__ void __launch_bounds__(256) tc_pack_weights_kernel(const PackJob* __restrict__ jobs, const int* __restrict__ tile_first,
                                                               int njobs, const float* __restrict__ params,
-                                                              float* __restrict__ hi, float* __restrict__ lo) {
+                                                              float* __restrict__ hi, float* __restrict__ lo, int op,
+                                                              size_t op_plane, float w_scale) {
   __shared__ float tile[32][33];
   int jlo = 0, jhi = njobs - 1;  // last job with tile_first <= blockIdx.x
   while (jlo < jhi) {
@@ -97,46 +116,12 @@ __global__ void __launch_bounds__(256) tc_pack_weights_kernel(const PackJob* __r
     if (r < J.rows && k < J.cols) {
       const float v = tile[rr][tx];
       const int64_t o = J.dst_off + (int64_t)r * J.ld + k;
-      hi[o] = v;
-      lo[o] = tf32_lo(v);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// BatchNorm statistics from the GEMM epilogue's per-tile partial sums part[nrows][2][ld]
-// block = (32 channels, 32 row lanes)
-__global__ void tc_bn_finalize_kernel(const float* __restrict__ part, int nrows, int ld, int C, double count, float eps,
-                                      float decay, float* __restrict__ moving_mean, float* __restrict__ moving_var,
-                                      float* __restrict__ mean_out, float* __restrict__ rstd_out, int update_moving) {
-  __shared__ double sh1[32][33], sh2[32][33];
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const int c = blockIdx.x * 32 + tx;
-  double a1 = 0, a2 = 0;
-  if (c < C) {
-    for (int r = ty; r < nrows; r += 32) {
-      a1 += (double)part[((size_t)r * 2 + 0) * ld + c];
-      a2 += (double)part[((size_t)r * 2 + 1) * ld + c];
-    }
-  }
-  sh1[ty][tx] = a1;
-  sh2[ty][tx] = a2;
-  __syncthreads();
-  if (ty == 0 && c < C) {
-    for (int i = 1; i < 32; i++) { a1 += sh1[i][tx]; a2 += sh2[i][tx]; }
-    const double mean = a1 / count;
-    double var = a2 / count - mean * mean;
-    if (var < 0) var = 0;
-    const float meanf = (float)mean, varf = (float)var;
-    mean_out[c] = meanf;
-    const float x = varf + eps;
-    float r = rsqrtf(x);
-    r = r * (1.5f - 0.5f * x * r * r);
-    rstd_out[c] = r;
-    if (update_moving) {
-      const double unbiased = var * (count / fmax(count - 1.0, 1.0));
-      moving_mean[c] = moving_mean[c] * decay + meanf * (1.f - decay);
-      moving_var[c] = moving_var[c] * decay + (float)unbiased * (1.f - decay);
+      if (op == OP_TF32X3) {
+        hi[o] = v;
+        lo[o] = tf32_lo(v);
+      } else {  // 16-bit packs hold the operand planes only (hi = start of the pack), scaled into the fp16 sweet spot
+        store_op16(reinterpret_cast<uint16_t*>(hi) + o, op_plane, op, v * w_scale);
+      }
     }
   }
 }
@@ -145,8 +130,10 @@ struct TcApplyArgs {
   const float* z;  // [rows][ldz] pre-BN
   int ldz;
   const float *mean, *rstd, *beta;
-  float *hi, *lo;  // output planes [rows][ldo]
+  float *hi, *lo;  // output: value plane, operand region [rows][ldo]
   int ldo;
+  int op;          // OP_*
+  size_t op_plane;
   int64_t rows;
   int C, act;
   float alpha, keep;
@@ -212,11 +199,10 @@ __device__ __forceinline__ void tc_bn_apply_finish(const TcApplyArgs& p, TcApply
   }
   if (VEC == 4) {
     *reinterpret_cast<float4*>(p.hi + it.m * p.ldo + it.c0) = make_float4(it.v[0], it.v[1 % VEC], it.v[2 % VEC], it.v[3 % VEC]);
-    *reinterpret_cast<float4*>(p.lo + it.m * p.ldo + it.c0) =
-        make_float4(tf32_lo(it.v[0]), tf32_lo(it.v[1 % VEC]), tf32_lo(it.v[2 % VEC]), tf32_lo(it.v[3 % VEC]));
+    tc_store_operand4(p.lo, p.op_plane, p.op, it.m * p.ldo + it.c0, it.v[0], it.v[1 % VEC], it.v[2 % VEC], it.v[3 % VEC]);
   } else {
     p.hi[it.m * p.ldo + it.c0] = it.v[0];
-    p.lo[it.m * p.ldo + it.c0] = tf32_lo(it.v[0]);
+    tc_store_operand(p.lo, p.op_plane, p.op, it.m * p.ldo + it.c0, it.v[0]);
   }
 }
 // two items per thread and iteration, all loads issued before the first dependent instruction (four items measured
@@ -249,8 +235,12 @@ struct TcBnBwdArgs {
   uint32_t stream_id;
   float* part;        // [row blocks][2][C]   (reduce)
   const float *s1, *s2;  // [C] means of g_y and g_y*zhat   (apply)
-  float *gz_hi, *gz_lo;  // [rows][ldgz]                   (apply)
+  float *gz_hi, *gz_lo;  // [rows][ldgz]                   (apply)  OP_TF32X3: two fp32 planes
   int ldgz;
+  int op;                // 16-bit formats: gz_hi = start of the operand planes, gz_plane = their element stride
+  size_t gz_plane;
+  const unsigned int* gmax_bits;  // OP_F16X3: bits of an upper bound of |gz| over the layer (bn_bwd_finalize)
+  float* gz_scale_out;   // OP_F16X3: [2] = (power-of-two scale applied to gz before the fp16 split, its inverse)
   int gcols;          // columns of gz to write
   int fpad, f, R;     // level layers: gz column j = slot*fpad + n holds channel q*f + jt*ft + n with
   int nt, ft;         //   q = R-1 - slot/nt, jt = slot % nt (n < min(ft, f - jt*ft)); fpad == 0: identity
@@ -270,64 +260,49 @@ __device__ __forceinline__ float tc_bn_gy(const TcBnBwdArgs& p, int64_t m, int c
   return g;
 }
 
-// block = 32 columns x 8 row lanes; grid = (ceil(C/32), row blocks); deterministic partials
-__global__ void tc_bn_bwd_reduce_kernel(const TcBnBwdArgs p, int rows_per_block) {
-  __shared__ float sh1[8][33], sh2[8][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + tx;
-  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
-  const int64_t r1 = min((int64_t)p.rows, r0 + rows_per_block);
-  float a1 = 0.f, a2 = 0.f;
-  if (c < p.C) {
-    for (int64_t r = r0 + ty; r < r1; r += 8) {
-      float zhat;
-      const float g = tc_bn_gy(p, r, c, zhat);
-      a1 += g;
-      a2 += g * zhat;
-    }
+// OP_F16X3: gz is multiplied by a power of two before the fp16 split so that its largest possible magnitude lands just
+// below 2^15 (fp16 tops out at 65504; remainders of values >= 2^-3 stay normal fp16 numbers).  The bound comes from the
+// backward statistics pass (tc_bn_bwd_finalize8_kernel); the inverse goes to the dgrad / wgrad epilogues.
+__device__ __forceinline__ float tc_gz_scale(const TcBnBwdArgs& p) {
+  if (p.op != OP_F16X3 || !p.gmax_bits) return 1.f;
+  const float bound = __uint_as_float(__ldg(p.gmax_bits));  // non-negative floats order like their bit patterns
+  if (!(bound > 0.f) || !(bound < 3e38f)) return 1.f;
+  int e;
+  frexpf(bound, &e);  // bound < 2^e
+  return ldexpf(1.f, max(-100, min(100, 15 - e)));
+}
+__device__ __forceinline__ void tc_store_gz4(const TcBnBwdArgs& p, int64_t idx, float scale, float v0, float v1, float v2, float v3) {
+  if (p.op == OP_TF32X3) {
+    *reinterpret_cast<float4*>(p.gz_hi + idx) = make_float4(v0, v1, v2, v3);
+    *reinterpret_cast<float4*>(p.gz_lo + idx) = make_float4(tf32_lo(v0), tf32_lo(v1), tf32_lo(v2), tf32_lo(v3));
+  } else {
+    store_op16x4(reinterpret_cast<uint16_t*>(p.gz_hi) + idx, p.gz_plane, p.op, v0 * scale, v1 * scale, v2 * scale, v3 * scale);
   }
-  sh1[ty][tx] = a1;
-  sh2[ty][tx] = a2;
-  __syncthreads();
-  if (ty == 0 && c < p.C) {
-#pragma unroll
-    for (int i = 1; i < 8; i++) { a1 += sh1[i][tx]; a2 += sh2[i][tx]; }
-    p.part[((size_t)blockIdx.y * 2 + 0) * p.C + c] = a1;
-    p.part[((size_t)blockIdx.y * 2 + 1) * p.C + c] = a2;
+}
+__device__ __forceinline__ void tc_store_gz(const TcBnBwdArgs& p, int64_t idx, float scale, float v) {
+  if (p.op == OP_TF32X3) {
+    p.gz_hi[idx] = v;
+    p.gz_lo[idx] = tf32_lo(v);
+  } else {
+    store_op16(reinterpret_cast<uint16_t*>(p.gz_hi) + idx, p.gz_plane, p.op, v * scale);
+  }
+}
+__device__ __forceinline__ void tc_publish_gz_scale(const TcBnBwdArgs& p, float scale) {
+  if (p.gz_scale_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    p.gz_scale_out[0] = scale;
+    p.gz_scale_out[1] = 1.f / scale;
   }
 }
 
-// block (32, 32): partials -> s1, s2 (means), gbeta (sum)
-__global__ void tc_bn_bwd_finalize_kernel(const float* __restrict__ part, int nblocks, int C, double rows,
-                                          float* __restrict__ s1, float* __restrict__ s2, float* __restrict__ gbeta) {
-  __shared__ double sh1[32][33], sh2[32][33];
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const int c = blockIdx.x * 32 + tx;
-  double a1 = 0, a2 = 0;
-  if (c < C) {
-    for (int r = ty; r < nblocks; r += 32) {
-      a1 += (double)part[((size_t)r * 2 + 0) * C + c];
-      a2 += (double)part[((size_t)r * 2 + 1) * C + c];
-    }
-  }
-  sh1[ty][tx] = a1;
-  sh2[ty][tx] = a2;
-  __syncthreads();
-  if (ty == 0 && c < C) {
-    for (int i = 1; i < 32; i++) { a1 += sh1[i][tx]; a2 += sh2[i][tx]; }
-    s1[c] = (float)(a1 / rows);
-    s2[c] = (float)(a2 / rows);
-    gbeta[c] = (float)a1;
-  }
-}
-
-// gz = rstd * (g_y - mean(g_y) - zhat * mean(g_y * zhat)), written as (value, lo) planes in the
+// gz = rstd * (g_y - mean(g_y) - zhat * mean(g_y * zhat)), written as operand planes in the
 // column order the dgrad / wgrad GEMMs want
 // scalar form for slot widths that break float4 alignment: one gz column per thread (128 columns x 2 row lanes per
 // block), so the slot -> channel mapping and the per-channel constants are computed once and the row loop keeps four
 // independent loads of gout and z in flight; grid = (ceil(gcols / 128), row blocks)
 __global__ void __launch_bounds__(256) tc_bn_bwd_apply_kernel(const TcBnBwdArgs p, int rows_per_block) {
   const int j = blockIdx.x * 128 + (threadIdx.x & 127), ty = threadIdx.x >> 7;
+  const float gscale = tc_gz_scale(p);
+  tc_publish_gz_scale(p, gscale);
   if (j >= p.gcols) return;
   int c = j;
   bool valid = j < p.C;
@@ -340,7 +315,7 @@ __global__ void __launch_bounds__(256) tc_bn_bwd_apply_kernel(const TcBnBwdArgs 
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
   const int64_t r1 = min((int64_t)p.rows, r0 + rows_per_block);
   if (!valid) {
-    for (int64_t r = r0 + ty; r < r1; r += 2) { p.gz_hi[r * p.ldgz + j] = 0.f; p.gz_lo[r * p.ldgz + j] = 0.f; }
+    for (int64_t r = r0 + ty; r < r1; r += 2) tc_store_gz(p, r * p.ldgz + j, 1.f, 0.f);
     return;
   }
   const float mean = p.mean[c], rstd = p.rstd[c], beta = p.beta[c], s1 = p.s1[c], s2 = p.s2[c];
@@ -365,35 +340,14 @@ __global__ void __launch_bounds__(256) tc_bn_bwd_apply_kernel(const TcBnBwdArgs 
           const float sg = 1.f / (1.f + __expf(-y));
           gy = gy * sg * (1.f - sg);
         }
-        const float v = rstd * (gy - s1 - zhat * s2);
-        p.gz_hi[rr * p.ldgz + j] = v;
-        p.gz_lo[rr * p.ldgz + j] = tf32_lo(v);
+        tc_store_gz(p, rr * p.ldgz + j, gscale, rstd * (gy - s1 - zhat * s2));
       }
     }
   }
 }
 
-// residual backward: gsrc[m, c'] (+)= sum_{j in [lo[c'], hi[c'])} gout[m, j]   (lo == NULL: identity)
-__global__ void tc_resid_bwd_kernel(const float* __restrict__ gout, int ldg, float* __restrict__ gsrc, int lds, int Csrc,
-                                    const int* __restrict__ lo, const int* __restrict__ hi, int64_t rows,
-                                    int accumulate) {
-  const int64_t total = rows * Csrc;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t m = i / Csrc;
-    const int c = (int)(i - m * Csrc);
-    float v = 0.f;
-    if (lo) {
-      for (int j = lo[c]; j < hi[c]; j++) v += gout[m * ldg + j];
-    } else {
-      v = gout[m * ldg + c];
-    }
-    float* d = gsrc + m * lds + c;
-    *d = accumulate ? *d + v : v;
-  }
-}
-
 // ------------------------------------------------------------------------------------------
-// Vectorised forms of the three backward passes above.  A block is TX column groups (4 channels,
+// Vectorised backward passes (statistics, gz, residual pushes).  A block is TX column groups (4 channels,
 // one float4 each) x TY = 256 / TX row lanes; every thread walks its rows with 4 independent
 // loads in flight, so a warp reads TX * 16 contiguous bytes of several rows per step and there
 // is no per-element index division.  Rows are 16-byte aligned (ld % 4 == 0); the channel tail
@@ -428,12 +382,13 @@ __device__ __forceinline__ void tc_load_ch4(const float* __restrict__ src, int c
 template <int TX>
 __global__ void __launch_bounds__(256) tc_bn_bwd_reduce_v4_kernel(const TcBnBwdArgs p, int rows_per_block) {
   constexpr int TY = 256 / TX;
-  __shared__ float sh[2][TY][TX * 4 + 4];
+  __shared__ float sh[4][TY][TX * 4 + 4];
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const int c0 = (blockIdx.x * TX + tx) * 4;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
   const int64_t r1 = min((int64_t)p.rows, r0 + rows_per_block);
   float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
+  float mg[4] = {0.f, 0.f, 0.f, 0.f}, mz[4] = {0.f, 0.f, 0.f, 0.f};  // max |g_y|, max |zhat| (bound of |gz|, OP_F16X3)
   if (c0 < p.C) {
     float mean[4], rstd[4], beta[4];
     tc_load_ch4(p.mean, c0, p.C, mean);
@@ -455,23 +410,36 @@ __global__ void __launch_bounds__(256) tc_bn_bwd_reduce_v4_kernel(const TcBnBwdA
         if (rr < r1) {
           const Gy4 y = tc_bn_gy4(p, rr, c0, gv[u], zv[u], mean, rstd, beta);
 #pragma unroll
-          for (int k = 0; k < 4; k++) { a1[k] += y.g[k]; a2[k] += y.g[k] * y.zh[k]; }
+          for (int k = 0; k < 4; k++) {
+            a1[k] += y.g[k];
+            a2[k] += y.g[k] * y.zh[k];
+            mg[k] = fmaxf(mg[k], fabsf(y.g[k]));
+            mz[k] = fmaxf(mz[k], fabsf(y.zh[k]));
+          }
         }
       }
     }
   }
 #pragma unroll
-  for (int k = 0; k < 4; k++) { sh[0][ty][tx * 4 + k] = a1[k]; sh[1][ty][tx * 4 + k] = a2[k]; }
+  for (int k = 0; k < 4; k++) {
+    sh[0][ty][tx * 4 + k] = a1[k]; sh[1][ty][tx * 4 + k] = a2[k];
+    sh[2][ty][tx * 4 + k] = mg[k]; sh[3][ty][tx * 4 + k] = mz[k];
+  }
   __syncthreads();
-  // TX * 4 columns x 2 sums, reduced over the TY row lanes by the first TX * 8 threads
-  for (int o = threadIdx.x; o < TX * 8; o += 256) {
+  // TX * 4 columns x (2 sums + 2 maxima), reduced over the TY row lanes by the first TX * 16 threads
+  for (int o = threadIdx.x; o < TX * 16; o += 256) {
     const int which = o / (TX * 4), col = o % (TX * 4);
     const int c = blockIdx.x * TX * 4 + col;
     if (c < p.C) {
       float a = 0.f;
+      if (which < 2) {
 #pragma unroll
-      for (int i = 0; i < TY; i++) a += sh[which][i][col];
-      p.part[((size_t)blockIdx.y * 2 + which) * p.C + c] = a;
+        for (int i = 0; i < TY; i++) a += sh[which][i][col];
+      } else {
+#pragma unroll
+        for (int i = 0; i < TY; i++) a = fmaxf(a, sh[which][i][col]);
+      }
+      p.part[((size_t)blockIdx.y * 4 + which) * p.C + c] = a;
     }
   }
 }
@@ -483,6 +451,8 @@ __global__ void __launch_bounds__(256) tc_bn_bwd_apply_v4_kernel(const TcBnBwdAr
   constexpr int TY = 256 / TX;
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const int j0 = (blockIdx.x * TX + tx) * 4;  // first gz column of this thread
+  const float gscale = tc_gz_scale(p);
+  tc_publish_gz_scale(p, gscale);
   if (j0 >= p.gcols) return;
   int c0 = j0;
   bool valid = j0 < p.C;
@@ -495,11 +465,7 @@ __global__ void __launch_bounds__(256) tc_bn_bwd_apply_v4_kernel(const TcBnBwdAr
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
   const int64_t r1 = min((int64_t)p.rows, r0 + rows_per_block);
   if (!valid) {  // padding columns of the slot layout: zeros
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t r = r0 + ty; r < r1; r += TY) {
-      *reinterpret_cast<float4*>(p.gz_hi + r * p.ldgz + j0) = zero;
-      *reinterpret_cast<float4*>(p.gz_lo + r * p.ldgz + j0) = zero;
-    }
+    for (int64_t r = r0 + ty; r < r1; r += TY) tc_store_gz4(p, r * p.ldgz + j0, 1.f, 0.f, 0.f, 0.f, 0.f);
     return;
   }
   float mean[4], rstd[4], beta[4], s1[4], s2[4];
@@ -534,9 +500,7 @@ __global__ void __launch_bounds__(256) tc_bn_bwd_apply_v4_kernel(const TcBnBwdAr
         float v[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) v[k] = (c0 + k < p.C) ? rstd[k] * (y.g[k] - s1[k] - y.zh[k] * s2[k]) : 0.f;
-        *reinterpret_cast<float4*>(p.gz_hi + rr * p.ldgz + j0) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(p.gz_lo + rr * p.ldgz + j0) =
-            make_float4(tf32_lo(v[0]), tf32_lo(v[1]), tf32_lo(v[2]), tf32_lo(v[3]));
+        tc_store_gz4(p, rr * p.ldgz + j0, gscale, v[0], v[1], v[2], v[3]);
       }
     }
   }
@@ -609,6 +573,8 @@ __global__ void __launch_bounds__(256) tc_resid_bwd_v4_kernel(const float* __res
 // partial rows, a few dozen channels), so the rows are spread over as many threads as a block holds and every
 // thread keeps four loads in flight; the cross-lane sum is a shuffle tree + one shared-memory round.
 constexpr int FIN_LANES = 128;
+// E = entries (rows of ld floats) per partial record; the sums are entries 0 and 1
+template <int E = 2>
 __device__ __forceinline__ void tc_fin_reduce(const float* __restrict__ part, int nrows, size_t ld, int c, bool valid,
                                               double& a1, double& a2, double (*sh)[8][2]) {
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
@@ -616,14 +582,14 @@ __device__ __forceinline__ void tc_fin_reduce(const float* __restrict__ part, in
   if (valid) {
     int r = ty;
     for (; r + FIN_LANES < nrows; r += 2 * FIN_LANES) {
-      const float u0 = part[((size_t)r * 2 + 0) * ld + c], u1 = part[((size_t)r * 2 + 1) * ld + c];
-      const float v0 = part[((size_t)(r + FIN_LANES) * 2 + 0) * ld + c], v1 = part[((size_t)(r + FIN_LANES) * 2 + 1) * ld + c];
+      const float u0 = part[((size_t)r * E + 0) * ld + c], u1 = part[((size_t)r * E + 1) * ld + c];
+      const float v0 = part[((size_t)(r + FIN_LANES) * E + 0) * ld + c], v1 = part[((size_t)(r + FIN_LANES) * E + 1) * ld + c];
       a1 += (double)u0 + (double)v0;
       a2 += (double)u1 + (double)v1;
     }
     if (r < nrows) {
-      a1 += (double)part[((size_t)r * 2 + 0) * ld + c];
-      a2 += (double)part[((size_t)r * 2 + 1) * ld + c];
+      a1 += (double)part[((size_t)r * E + 0) * ld + c];
+      a2 += (double)part[((size_t)r * E + 1) * ld + c];
     }
   }
   // lanes 8, 16 of a warp hold the same channel: fold the 4 row lanes of a warp, then the 32 warps
@@ -663,18 +629,42 @@ __global__ void __launch_bounds__(8 * FIN_LANES) tc_bn_finalize8_kernel(const fl
     }
   }
 }
+// partial records of the backward statistics pass: [nblocks][4][C] = (sum g_y, sum g_y zhat, max |g_y|, max |zhat|).
+// gmax_bits (nullable, zeroed by the caller): atomic maximum over channels of rstd * (max|g_y| + |s1| + max|zhat| |s2|),
+// an upper bound of |gz| that sets the layer's fp16 scale (OP_F16X3).
 __global__ void __launch_bounds__(8 * FIN_LANES) tc_bn_bwd_finalize8_kernel(const float* __restrict__ part, int nblocks, int C, double rows,
                                                                   float* __restrict__ s1, float* __restrict__ s2,
-                                                                  float* __restrict__ gbeta, int bias_mode) {
+                                                                  float* __restrict__ gbeta, int bias_mode,
+                                                                  const float* __restrict__ rstd, unsigned int* gmax_bits) {
   __shared__ double sh[FIN_LANES / 4][8][2];
+  __shared__ float shm[FIN_LANES / 4][8][2];
   const int c = blockIdx.x * 8 + (threadIdx.x & 7);
   double a1, a2;
-  tc_fin_reduce(part, nblocks, (size_t)C, c, c < C, a1, a2, sh);
+  tc_fin_reduce<4>(part, nblocks, (size_t)C, c, c < C, a1, a2, sh);
+  float mg = 0.f, mz = 0.f;
+  if (gmax_bits) {  // block-uniform
+    if (c < C)
+      for (int r = threadIdx.x >> 3; r < nblocks; r += FIN_LANES) {
+        mg = fmaxf(mg, part[((size_t)r * 4 + 2) * C + c]);
+        mz = fmaxf(mz, part[((size_t)r * 4 + 3) * C + c]);
+      }
+    mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, 8));  mz = fmaxf(mz, __shfl_xor_sync(0xffffffffu, mz, 8));
+    mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, 16)); mz = fmaxf(mz, __shfl_xor_sync(0xffffffffu, mz, 16));
+    if ((threadIdx.x & 31) < 8) { shm[threadIdx.x >> 5][threadIdx.x & 7][0] = mg; shm[threadIdx.x >> 5][threadIdx.x & 7][1] = mz; }
+    __syncthreads();
+    if (threadIdx.x < 8)
+      for (int w = 0; w < FIN_LANES / 4; w++) { mg = fmaxf(mg, shm[w][threadIdx.x][0]); mz = fmaxf(mz, shm[w][threadIdx.x][1]); }
+  }
   if (threadIdx.x < 8 && c < C) {
     // bias layers have no batch statistics to differentiate through: gz = g_y, d bias = sum g_y
-    s1[c] = bias_mode ? 0.f : (float)(a1 / rows);
-    s2[c] = bias_mode ? 0.f : (float)(a2 / rows);
+    const float m1 = bias_mode ? 0.f : (float)(a1 / rows), m2 = bias_mode ? 0.f : (float)(a2 / rows);
+    s1[c] = m1;
+    s2[c] = m2;
     gbeta[c] = (float)a1;
+    if (gmax_bits) {
+      const float bound = fabsf(rstd[c]) * (mg + fabsf(m1) + mz * fabsf(m2));
+      if (bound == bound) atomicMax(gmax_bits, __float_as_uint(fminf(bound, 3e38f)));
+    }
   }
 }
 
@@ -686,7 +676,7 @@ __global__ void __launch_bounds__(8 * FIN_LANES) tc_bn_bwd_finalize8_kernel(cons
 //   dx[k] = g[k] / sqrt(s[k]) - x[k] * sum_{|i-k|<=5} g[i] x[i] s[i]^-1.5
 constexpr int LRN_RADIUS = 5;
 __global__ void __launch_bounds__(256) tc_lrn_fwd_kernel(float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ u,
-                                                         int ld, int C, int64_t rows) {
+                                                         int ld, int C, int64_t rows, int op, size_t op_plane) {
   extern __shared__ float lrn_sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   float* xs = lrn_sm + warp * C;
@@ -703,7 +693,7 @@ __global__ void __launch_bounds__(256) tc_lrn_fwd_kernel(float* __restrict__ hi,
       for (int j = j0; j <= j1; j++) s += xs[j] * xs[j];
       const float y = xs[c] / sqrtf(s);
       hi[r * ld + c] = y;
-      lo[r * ld + c] = tf32_lo(y);
+      tc_store_operand(lo, op_plane, op, r * ld + c, y);
     }
     __syncwarp();
   }

@@ -14,7 +14,8 @@ from hypelcnn_b200 import _native as N
 
 TRUNC_STD_FIX = 0.87962566103423978  # variance_scaling truncated-normal correction [TF-lib]
 # "3xtf32": tcgen05 tensor-core engine (fp32-accurate TF32 split, the default); "fp32": FFMA engine
-_PRECISIONS = {"fp32": N.HYP_PRECISION_FP32, "3xtf32": N.HYP_PRECISION_3XTF32, "bf16": N.HYP_PRECISION_BF16}
+_PRECISIONS = {"fp32": N.HYP_PRECISION_FP32, "3xtf32": N.HYP_PRECISION_3XTF32, "bf16": N.HYP_PRECISION_BF16,
+               "3xf16": N.HYP_PRECISION_3XF16}
 
 
 def _ptr(t):

@@ -86,7 +86,9 @@ enum {
 enum {
   HYP_PRECISION_FP32 = 0,    /* fp32 FFMA everywhere (parity mode) */
   HYP_PRECISION_3XTF32 = 1,  /* tcgen05 kind::tf32, hi/lo split, fp32-accurate */
-  HYP_PRECISION_BF16 = 2     /* tcgen05 kind::f16 bf16 inputs, fp32 accumulate */
+  HYP_PRECISION_BF16 = 2,    /* tcgen05 kind::f16, one bf16 plane per operand, fp32 accumulate: the fast mode */
+  HYP_PRECISION_3XF16 = 3    /* tcgen05 kind::f16, fp16 hi/lo split (3 MMAs per K step of 16), fp32-accurate at twice
+                                the 3xTF32 rate; operands are power-of-two scaled into the fp16 range */
 };
 
 typedef struct hyp_model_desc {
@@ -257,13 +259,6 @@ int hyp_crc32c(const void* data, uint64_t len, uint32_t* crc_inout);
  * GULFPORTDataLoader.py:22-43: `from tifffile import imread`). */
 int hyp_tiff_lzw_decode(const void* data, uint64_t len, void* out, uint64_t out_capacity, uint64_t* out_len);
 
-/* Debug / test hook, host only: the pair-tile plan of a level forward launch (hyp_tc_engine.cuh plan_level_pairs;
- * groundwork, not used by hyp_model_forward yet).  tiles: rows of (p1, p2 or -1, seg_begin, seg_count); segs: rows of
- * (input position q, n1, n2, row in the mirrored weight copy, row in the normal copy, accumulator column); counts =
- * (number of tiles, number of segments). */
-int hyp_debug_plan_level_pairs(int P, int R, int fpad, int32_t* tiles, int tiles_cap, int32_t* segs, int segs_cap,
-                               int32_t* counts);
-
 /* Debug / test hook, host only (no device needed): the static tile schedule of the persistent GEMM kernel
  * (hyp_tc_engine.cuh schedule_tiles) applied to a plain cost vector.  group_of_unit[u] = CTA group that runs unit u,
  * rank_in_group[u] = its position in that group's execution order.  windowed != 0: locality windows of 2*groups units
@@ -272,8 +267,9 @@ int hyp_debug_schedule(const double* costs, int units, int groups, int windowed,
                        int32_t* rank_in_group);
 
 /* probe of the tcgen05/TMA segment-GEMM building block used by the tensor-core precision
- * modes (3xTF32 split).  mn bit 0 = 0: A[M,K], B[N,K] -> D = A*B^T (K-major); 1: A[K,M], B[K,N]
- * -> D = A^T*B (MN-major).  mn bit 1: run as CTA pairs (tcgen05 cta_group::2).
+ * modes.  mn bit 0 = 0: A[M,K], B[N,K] -> D = A*B^T (K-major); 1: A[K,M], B[K,N]
+ * -> D = A^T*B (MN-major).  mn bit 1: run as CTA pairs (tcgen05 cta_group::2).  mn bits 2..3: operand format
+ * (0: two fp32 planes, 3 kind::tf32 MMAs; 1: two fp16 planes, 3 kind::f16 MMAs; 2: one bf16 plane).
  * stats (nullable): [ceil(M/128)][2][N] per-tile column sums / sums of squares. */
 int hyp_debug_tc_gemm(int mn, const float* A, const float* B, int M, int N, int K, float* D,
                       float* stats, int raw_hi, int bn, int ksplit, int chunk_kb, void* stream);

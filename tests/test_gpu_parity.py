@@ -178,7 +178,8 @@ CASES = {
 }
 
 
-PRECISIONS = ["fp32", "3xtf32"]  # FFMA engine and the tcgen05 3xTF32 engine: same tests, same tolerances
+# FFMA engine, the tcgen05 3xTF32 engine and the tcgen05 3xF16 engine (fp16 hi/lo planes): same tests, same tolerances
+PRECISIONS = ["fp32", "3xtf32", "3xf16"]
 
 
 @pytest.fixture(params=PRECISIONS)
@@ -398,3 +399,25 @@ def test_weights_shared_across_calls_and_capacity_growth(E, prec):
     assert all(numpy.array_equal(before[k], after[k]) for k in before)
     lb, _ = eng.forward(dev(x2[: c["B"]]), False)
     assert torch.equal(la[: c["B"]], lb)  # eval mode is per-sample
+
+
+@pytest.mark.parametrize("case", ["c5", "c2"])
+def test_bf16_fast_mode_deviation(E, case):
+    """HYP_PRECISION_BF16 (one bf16 plane per operand) is the labelled fast mode, not a parity mode: its distance from
+    the fp64 oracle is measured and bounded loosely here and reported by bench.py --precision bf16."""
+    eng, alg, c, x, y = _make(E, case, precision="bf16")
+    ref = R.forward(oracle_variables(eng), torch.tensor(x, dtype=torch.float64), c["classes"], alg, True)
+    logits, recon = eng.forward(dev(x), True, True, seed=0)
+    err = float((logits.cpu().double() - ref["logits"]).abs().max())
+    scale = float(ref["logits"].abs().max())
+    pred = E.argmax_confusion(logits).cpu().numpy()
+    mismatches = int((pred != D.argmax_lowest(ref["logits"].numpy()).astype(numpy.uint8)).sum())
+    print(f"bf16 {case}: max |logit error| {err:.3e} (logit scale {scale:.2f}), argmax mismatches {mismatches}/{len(pred)}")
+    assert err < 0.15 * scale and mismatches <= len(pred) // 4
+    loss = eng.loss_backward(dev(x), dev(y)).cpu().numpy()
+    loss_ref, g_ref, _ = R.loss_and_grads(oracle_variables(eng), torch.tensor(x, dtype=torch.float64),
+                                          torch.tensor(y.astype(numpy.int64)), c["classes"], alg)
+    assert abs(loss[0] - loss_ref.item()) < 0.05 * abs(loss_ref.item())
+    name = "nn_core/fc_final/weights"
+    g = eng.gradient(name).cpu().double()
+    assert float((g - g_ref[name]).abs().max()) < 0.2 * float(g_ref[name].abs().max())

@@ -139,3 +139,65 @@ def test_tensor_core_input_truncation_probe():
     err_rna = rel_err(tc_gemm(0, A, B, raw_hi=0), ref)
     print(f"raw-hi rel err {err_raw:.3e}; rna-hi rel err {err_rna:.3e}")
     assert err_rna < 4e-6
+
+
+# ---- 16-bit operand formats: mn flag bits 2..3 select the format (1: fp16 hi/lo planes x 3 MMAs, 2: one bf16 plane) ----
+OP_F16X3, OP_BF16 = 1 << 2, 2 << 2
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (128, 256, 128), (300, 120, 145), (256, 240, 480), (1000, 480, 240),
+                                   (77, 16, 8), (130, 980, 2940)])
+@pytest.mark.parametrize("pair", [0, 2])
+def test_kmajor_f16x3_matches_fp64(M, N, K, pair):
+    """fp16 (hi, lo) planes, hi*hi + lo*hi + hi*lo on kind::f16 at twice the TF32 rate: the same 3e-6 bound."""
+    g = torch.Generator().manual_seed(M * 7 + N + pair)
+    A = torch.randn((M, K), generator=g)
+    B = torch.randn((N, K), generator=g)
+    ref = A.double() @ B.double().T
+    err = rel_err(tc_gemm(pair | OP_F16X3, A, B), ref)
+    fp32 = rel_err(A @ B.T, ref)
+    assert err < max(3e-6, 4 * fp32), (err, fp32)
+
+
+@pytest.mark.parametrize("M,N,K,ksplit", [(128, 64, 64, 1), (120, 240, 1000, 1), (480, 480, 4096, 4), (145, 120, 777, 3),
+                                          (60, 16, 200, 1), (256, 64, 128, 1), (240, 128, 300, 2)])
+@pytest.mark.parametrize("pair", [1, 3])
+def test_mnmajor_f16x3_matches_fp64(M, N, K, ksplit, pair):
+    """wgrad layout with 16-bit operands: 64 x 64 SWIZZLE_128B boxes, MN-major descriptors (LBO = one box, SBO 1024)."""
+    if pair == 3 and (M + 127) // 128 % 2:
+        pytest.skip("CTA pairs need an even number of 128-row tiles")
+    g = torch.Generator().manual_seed(M + N + K + pair)
+    A = torch.randn((K, M), generator=g)
+    B = torch.randn((K, N), generator=g)
+    ref = A.double().T @ B.double()
+    err = rel_err(tc_gemm(pair | OP_F16X3, A, B, ksplit=ksplit), ref)
+    fp32 = rel_err(A.T @ B, ref)
+    assert err < max(3e-6, 4 * fp32), (err, fp32)
+
+
+@pytest.mark.parametrize("mn", [0, 2, 1, 3])
+def test_bf16_single_plane(mn):
+    """The fast mode: one bf16 plane, one MMA per K step.  Error is bf16 input rounding (2^-9 per operand)."""
+    g = torch.Generator().manual_seed(40 + mn)
+    M, N, K = 256, 240, 512
+    if mn & 1:
+        A, B = torch.randn((K, M), generator=g), torch.randn((K, N), generator=g)
+        ref = A.double().T @ B.double()
+        bf = (A.bfloat16().double().T @ B.bfloat16().double())
+    else:
+        A, B = torch.randn((M, K), generator=g), torch.randn((N, K), generator=g)
+        ref = A.double() @ B.double().T
+        bf = A.bfloat16().double() @ B.bfloat16().double().T
+    got = tc_gemm(mn | OP_BF16, A, B)
+    assert rel_err(got, bf) < 3e-6          # exact products of the rounded operands, fp32 accumulation
+    assert rel_err(got, ref) < 2e-2
+
+
+def test_f16x3_small_magnitudes_keep_relative_accuracy():
+    """Operands around 1e-3 (weights) and 1e-4: the probe scales A by 4 and B by 64 before the split, as the engine does
+    with its per-tensor power-of-two scales; the error stays relative to the result's own scale."""
+    g = torch.Generator().manual_seed(3)
+    A = torch.randn((256, 480), generator=g) * 1e-2
+    B = torch.randn((240, 480), generator=g) * 3e-2
+    ref = A.double() @ B.double().T
+    assert rel_err(tc_gemm(OP_F16X3, A, B), ref) < 2e-5
