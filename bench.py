@@ -509,7 +509,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="patches per GPU per step")
     ap.add_argument("--ref-batch", type=int, default=256, help="patches per step of the CPU arm (bounded sample)")
     ap.add_argument("--input-batches", type=int, default=4)
-    ap.add_argument("--precision", default="3xtf32", choices=["fp32", "3xtf32", "3xf16", "bf16"],
+    ap.add_argument("--precision", default="3xf16", choices=["fp32", "3xtf32", "3xf16", "bf16"],
                     help="3xtf32 / 3xf16: tcgen05 tensor-core engine with an fp32-accurate operand split (TF32 planes, "
                          "3 kind::tf32 MMAs per K step of 8 / fp16 hi-lo planes, 3 kind::f16 MMAs per K step of 16); "
                          "bf16: the labelled fast mode (one bf16 plane, not a parity mode); fp32: FFMA engine")

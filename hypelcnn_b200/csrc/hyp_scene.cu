@@ -119,12 +119,13 @@ __global__ void gather_kernel(const GatherArgs p) {
 // C % 4 == 0 for fp32 -- every scene of the reference: 144, 48, 64 bands).
 //
 //   * a block owns one patch at a time (persistent, grid-stride over the target list);
-//   * phase 1: thread (chunk, row slot) loads ONE 16-byte chunk (8 uint16 / 4 fp32 bands) of a window pixel with a
-//     128-bit read-only load -- four pixels in flight per thread --, normalises it and puts the fp32 values into the
-//     patch image in shared memory.  A thread keeps the same chunk for the whole kernel, so its bands' constants live
+//   * loads: thread (chunk, row slot) loads ONE 16-byte chunk (8 uint16 / 4 fp32 bands) of up to four window pixels with
+//     128-bit read-only loads; the loads of the block's NEXT patch are issued before the current one is streamed out
+//     (software pipeline: the registers carry them across the store phase);
+//   * convert: the thread normalises its chunks and puts the fp32 values into the patch image in shared memory.  A thread keeps the same chunk for the whole kernel, so its bands' constants live
 //     in registers; neighbouring lanes hold neighbouring PIXELS of the same chunk, i.e. shared-memory addresses one
 //     output row (C + 1 floats, odd for every scene of the reference) apart: conflict-free scalar stores;
-//   * phase 2: the patch image leaves as one flat stream of 16-byte streaming stores.  A patch of (2n+1)^2 * (C+1)
+//   * store: the patch image leaves as one flat stream of 16-byte streaming stores.  A patch of (2n+1)^2 * (C+1)
 //     floats starts at any 4-byte phase of a 16-byte line, so the image sits in shared memory at the same phase
 //     (`shift`) and only the first / last vector of a patch is written element-wise.
 //
@@ -143,7 +144,6 @@ template <>
 struct ChunkOf<float> { static constexpr int N = 4; };
 
 constexpr int GATHER_THREADS = 256;
-constexpr int GATHER_UNROLL = 2;  // window pixels in flight per thread
 
 template <typename T>
 __device__ __forceinline__ void gather_convert(const uint4 raw, const float (&bias)[ChunkOf<T>::N],
@@ -174,41 +174,46 @@ __device__ __forceinline__ void gather_convert(const uint4 raw, const float (&bi
   }
 }
 
+// The loads of one patch that a thread keeps in flight: GATHER_PF window pixels of its chunk + one LiDAR sample.
+constexpr int GATHER_PF = 4;
+struct GatherLoads {
+  uint4 raw[GATHER_PF];
+  float lidar;
+};
+
+// issue this thread's loads for the patch at target (x, y); window pixels beyond GATHER_PF * rows_per_iter (large
+// windows of wide scenes) are fetched later, inside the convert step
 template <typename T>
-__device__ __forceinline__ void gather_phase1(const GatherArgs& p, const T* __restrict__ casi, float* __restrict__ img, int bx,
-                                              int by, int chunk, int slot, int rows_per_iter,
-                                              const float (&bias)[ChunkOf<T>::N], const float (&cmx)[ChunkOf<T>::N],
-                                              const float (&rcp)[ChunkOf<T>::N], bool fast) {
-  constexpr int EPC = ChunkOf<T>::N;
-  const int S = 2 * p.nb + 1, npix = S * S, ld = p.out_ld;
-  const bool half_res = p.mode == HYP_GATHER_GRSS2018, normalize = p.cmin != nullptr;
-  const int dy = rows_per_iter / S, dx = rows_per_iter - dy * S;  // one step of rows_per_iter pixels in (row, column)
-  int py = slot / S, px = slot - py * S;
-  for (int pix = slot; pix < npix; pix += GATHER_UNROLL * rows_per_iter) {
-    uint4 raw[GATHER_UNROLL];
-    int at[GATHER_UNROLL];
+__device__ __forceinline__ void gather_issue(const GatherArgs& p, const T* __restrict__ casi, int x, int y, int chunk, int slot,
+                                             int rows_per_iter, bool active, GatherLoads& L) {
+  const int S = 2 * p.nb + 1, npix = S * S;
+  const bool half_res = p.mode == HYP_GATHER_GRSS2018;
+  int bx = x, by = y;
+  if (half_res) {  // loader/GRSS2018DataLoader.py:23-29 (int() truncation)
+    bx = x / 2 + p.nb - p.nb / 2;
+    by = y / 2 + p.nb - p.nb / 2;
+  }
+  if (active) {
+    const int dy = rows_per_iter / S, dx = rows_per_iter - dy * S;  // one step of rows_per_iter pixels in (row, column)
+    int py = slot / S, px = slot - py * S;
 #pragma unroll
-    for (int u = 0; u < GATHER_UNROLL; u++) {
-      at[u] = pix + u * rows_per_iter;
-      if (at[u] < npix) {
+    for (int u = 0; u < GATHER_PF; u++) {
+      if (slot + u * rows_per_iter < npix) {
         const int ry = reflect_sym(by + (half_res ? py / 2 : py) - p.nb, p.Hc);
         const int rx = reflect_sym(bx + (half_res ? px / 2 : px) - p.nb, p.Wc);
-        raw[u] = __ldg(reinterpret_cast<const uint4*>(casi + ((size_t)ry * p.Wc + rx) * p.C) + chunk);
+        L.raw[u] = __ldg(reinterpret_cast<const uint4*>(casi + ((size_t)ry * p.Wc + rx) * p.C) + chunk);
       }
       py += dy;
       px += dx;
       if (px >= S) { px -= S; py++; }
     }
-#pragma unroll
-    for (int u = 0; u < GATHER_UNROLL; u++) {
-      if (at[u] < npix) {
-        float v[EPC];
-        gather_convert<T>(raw[u], bias, cmx, rcp, normalize, fast, v);
-        float* const dst = img + at[u] * ld + chunk * EPC;
-#pragma unroll
-        for (int j = 0; j < EPC; j++) dst[j] = v[j];
-      }
-    }
+  }
+  // LiDAR: one thread per window pixel, the last threads first (they idle in the chunk loads when 256 is not a multiple
+  // of the chunk count)
+  const int lpix = GATHER_THREADS - 1 - (int)threadIdx.x;
+  if (p.lidar && lpix < npix) {
+    const int py = lpix / S, px = lpix - py * S;
+    L.lidar = __ldg(p.lidar + (size_t)reflect_sym(y + py - p.nb, p.Hl) * p.Wl + reflect_sym(x + px - p.nb, p.Wl));
   }
 }
 
@@ -241,33 +246,71 @@ __global__ void __launch_bounds__(GATHER_THREADS, 4) gather_rows_kernel(const Ga
   const float lmin = p.lminmax ? __ldg(p.lminmax) : 0.f, lmax = p.lminmax ? __ldg(p.lminmax + 1) : 1.f;
   const T* const casi = reinterpret_cast<const T*>(p.casi);
 
-  for (int64_t n = blockIdx.x; n < p.N; n += gridDim.x) {
-    const int x = __ldg(p.xy + 2 * n), y = __ldg(p.xy + 2 * n + 1);
-    int bx = x, by = y;
-    if (half_res) {  // loader/GRSS2018DataLoader.py:23-29 (int() truncation)
-      bx = x / 2 + p.nb - p.nb / 2;
-      by = y / 2 + p.nb - p.nb / 2;
-    }
+  // software pipeline over the block's patches: the loads of patch n + grid are issued before patch n is streamed out,
+  // so their latency is covered by the store phase and the two barriers
+  int64_t n = blockIdx.x;
+  GatherLoads L;
+  int x = 0, y = 0;
+  if (n < p.N) {
+    x = __ldg(p.xy + 2 * n); y = __ldg(p.xy + 2 * n + 1);
+    gather_issue<T>(p, casi, x, y, chunk, slot, rows_per_iter, active, L);
+  }
+  for (; n < p.N; n += gridDim.x) {
     float* const gout = p.out + (size_t)n * total;
     const int shift = (int)((reinterpret_cast<uintptr_t>(gout) >> 2) & 3);
     float* const img = sm + shift;
-    // ---- phase 1: window pixels -> fp32 patch image in shared memory
+    // ---- convert: the loads in flight -> fp32 patch image in shared memory
     if (active) {
-      gather_phase1<T>(p, casi, img, bx, by, chunk, slot, rows_per_iter, bias, cmx, rcp, fast);
-    }
-    // LiDAR channel and zero padding channels: one thread per window pixel (the last warps first: they are the ones
-    // with idle lanes in phase 1 when 256 is not a multiple of the chunk count)
-    for (int pix = GATHER_THREADS - 1 - (int)threadIdx.x; pix < npix; pix += GATHER_THREADS) {
-      if (p.lidar) {
-        const int py = pix / S, px = pix - py * S;
-        const int ry = reflect_sym(y + py - p.nb, p.Hl), rx = reflect_sym(x + px - p.nb, p.Wl);
-        const float raw = __ldg(p.lidar + (size_t)ry * p.Wl + rx);
-        img[pix * ld + p.C] = p.lminmax ? __fdiv_rn(__fsub_rn(raw, lmin), lmax) : raw;
+#pragma unroll
+      for (int u = 0; u < GATHER_PF; u++) {
+        const int at = slot + u * rows_per_iter;
+        if (at < npix) {
+          float v[EPC];
+          gather_convert<T>(L.raw[u], bias, cmx, rcp, normalize, fast, v);
+          float* const dst = img + at * ld + chunk * EPC;
+#pragma unroll
+          for (int j = 0; j < EPC; j++) dst[j] = v[j];
+        }
       }
-      for (int c = n_out_c; c < ld; c++) img[pix * ld + c] = 0.f;
+      if (GATHER_PF * rows_per_iter < npix) {  // window pixels beyond the prefetch depth
+        int bx = x, by = y;
+        if (half_res) { bx = x / 2 + p.nb - p.nb / 2; by = y / 2 + p.nb - p.nb / 2; }
+        for (int at = slot + GATHER_PF * rows_per_iter; at < npix; at += rows_per_iter) {
+          const int py = at / S, px = at - py * S;
+          const int ry = reflect_sym(by + (half_res ? py / 2 : py) - p.nb, p.Hc);
+          const int rx = reflect_sym(bx + (half_res ? px / 2 : px) - p.nb, p.Wc);
+          const uint4 raw = __ldg(reinterpret_cast<const uint4*>(casi + ((size_t)ry * p.Wc + rx) * p.C) + chunk);
+          float v[EPC];
+          gather_convert<T>(raw, bias, cmx, rcp, normalize, fast, v);
+          float* const dst = img + at * ld + chunk * EPC;
+#pragma unroll
+          for (int j = 0; j < EPC; j++) dst[j] = v[j];
+        }
+      }
+    }
+    {  // LiDAR channel and zero padding channels
+      const int lpix = GATHER_THREADS - 1 - (int)threadIdx.x;
+      if (lpix < npix) {
+        if (p.lidar) img[lpix * ld + p.C] = p.lminmax ? __fdiv_rn(__fsub_rn(L.lidar, lmin), lmax) : L.lidar;
+        for (int c = n_out_c; c < ld; c++) img[lpix * ld + c] = 0.f;
+      }
+      for (int pix = lpix + GATHER_THREADS; pix < npix; pix += GATHER_THREADS) {  // windows of more than 256 pixels
+        if (p.lidar) {
+          const int py = pix / S, px = pix - py * S;
+          const float raw = __ldg(p.lidar + (size_t)reflect_sym(y + py - p.nb, p.Hl) * p.Wl + reflect_sym(x + px - p.nb, p.Wl));
+          img[pix * ld + p.C] = p.lminmax ? __fdiv_rn(__fsub_rn(raw, lmin), lmax) : raw;
+        }
+        for (int c = n_out_c; c < ld; c++) img[pix * ld + c] = 0.f;
+      }
     }
     __syncthreads();
-    // ---- phase 2: flat stream out, 16 bytes per store
+    // ---- next patch's loads go out now
+    const int64_t nn = n + gridDim.x;
+    if (nn < p.N) {
+      x = __ldg(p.xy + 2 * nn); y = __ldg(p.xy + 2 * nn + 1);
+      gather_issue<T>(p, casi, x, y, chunk, slot, rows_per_iter, active, L);
+    }
+    // ---- stream the image out, 16 bytes per store
     float4* const gvec = reinterpret_cast<float4*>(gout - shift);
     const int nvec = (shift + total + 3) >> 2;
     for (int v = threadIdx.x; v < nvec; v += GATHER_THREADS) {

@@ -13,7 +13,8 @@ import torch
 from hypelcnn_b200 import _native as N
 
 TRUNC_STD_FIX = 0.87962566103423978  # variance_scaling truncated-normal correction [TF-lib]
-# "3xtf32": tcgen05 tensor-core engine (fp32-accurate TF32 split, the default); "fp32": FFMA engine
+# tcgen05 tensor-core engine: "3xf16" (fp16 hi/lo operand planes, fp32-accurate, the default for HYPELCNN), "3xtf32"
+# (TF32 planes, fp32-accurate, half the rate), "bf16" (one bf16 plane: the labelled fast mode); "fp32": FFMA engine
 _PRECISIONS = {"fp32": N.HYP_PRECISION_FP32, "3xtf32": N.HYP_PRECISION_3XTF32, "bf16": N.HYP_PRECISION_BF16,
                "3xf16": N.HYP_PRECISION_3XF16}
 
@@ -41,14 +42,16 @@ class PatchEngine:
     (nnmodel/modelconfigs/alg_param_hypelcnn.json) — a missing key raises KeyError exactly
     like the reference's dict lookups."""
 
-    def __init__(self, patch, channels, classes, algorithm_params, max_batch, device=None, precision="3xtf32",
+    def __init__(self, patch, channels, classes, algorithm_params, max_batch, device=None, precision=None,
                  model="hypelcnn"):
         if not torch.cuda.is_available():
             raise N.NativeError(N.HYP_E_CUDA, "no CUDA device: hypelcnn_b200 has no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.patch, self.channels, self.classes = int(patch), int(channels), int(classes)
         self.alg = dict(algorithm_params)
-        self.precision = precision
+        # default operand format: fp16 hi/lo planes for HYPELCNN (BatchNorm after every layer keeps activations in the
+        # fp16 range); TF32 planes for DUALCNN / CONCNN, whose un-normalised activations have no such bound
+        self.precision = precision if precision is not None else ("3xf16" if model == "hypelcnn" else "3xtf32")
         if model not in ("hypelcnn", "dualcnn", "concnn"):
             raise ValueError(f"unknown model kind {model!r}")
         self.model = model

@@ -15,7 +15,7 @@ from hypelcnn_b200.nnmodel.NNModel import NNModel
 
 
 class HYPELCNNModel(NNModel):
-    precision = "3xtf32"  # tcgen05 tensor-core engine; "fp32" selects the FFMA engine
+    precision = "3xf16"  # tcgen05 tensor-core engine, fp16 hi/lo operand planes (fp32-accurate); "3xtf32": TF32 planes; "fp32": FFMA engine
 
     def __init__(self):
         self.engine = None

@@ -14,10 +14,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--batch", type=int, default=4096)
 ap.add_argument("--workload", default="c2_grss2013")
+ap.add_argument("--precision", default="3xf16")
 a = ap.parse_args()
 P, C, classes = bench.WORKLOADS[a.workload]
 alg = {**bench.ALG, "batch_size": a.batch}
-eng = E.PatchEngine(P, C, classes, alg, max_batch=a.batch)
+eng = E.PatchEngine(P, C, classes, alg, max_batch=a.batch, precision=a.precision)
 eng.init_variables(1234)
 rng = numpy.random.default_rng(1234)
 x = torch.from_numpy(rng.random((a.batch, P, P, C), dtype=numpy.float32)).cuda()

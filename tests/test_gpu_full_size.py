@@ -22,7 +22,7 @@ ALG0 = {**ALG, "drop_out_ratio": 0.0}
 
 def _engine(max_batch):
     from hypelcnn_b200 import engine as E
-    eng = E.PatchEngine(P, C, CLASSES, ALG0, max_batch=max_batch, precision="3xtf32")
+    eng = E.PatchEngine(P, C, CLASSES, ALG0, max_batch=max_batch, precision="3xf16")
     eng.init_variables(seed=1234)
     return E, eng
 

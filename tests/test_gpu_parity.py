@@ -407,14 +407,15 @@ def test_bf16_fast_mode_deviation(E, case):
     the fp64 oracle is measured and bounded loosely here and reported by bench.py --precision bf16."""
     eng, alg, c, x, y = _make(E, case, precision="bf16")
     ref = R.forward(oracle_variables(eng), torch.tensor(x, dtype=torch.float64), c["classes"], alg, True)
-    logits, recon = eng.forward(dev(x), True, True, seed=0)
+    xd = dev(x)
+    logits, recon = eng.forward(xd, True, True, seed=0)
     err = float((logits.cpu().double() - ref["logits"]).abs().max())
     scale = float(ref["logits"].abs().max())
     pred = E.argmax_confusion(logits).cpu().numpy()
     mismatches = int((pred != D.argmax_lowest(ref["logits"].numpy()).astype(numpy.uint8)).sum())
     print(f"bf16 {case}: max |logit error| {err:.3e} (logit scale {scale:.2f}), argmax mismatches {mismatches}/{len(pred)}")
     assert err < 0.15 * scale and mismatches <= len(pred) // 4
-    loss = eng.loss_backward(dev(x), dev(y)).cpu().numpy()
+    loss = eng.loss_backward(xd, dev(y)).cpu().numpy()
     loss_ref, g_ref, _ = R.loss_and_grads(oracle_variables(eng), torch.tensor(x, dtype=torch.float64),
                                           torch.tensor(y.astype(numpy.int64)), c["classes"], alg)
     assert abs(loss[0] - loss_ref.item()) < 0.05 * abs(loss_ref.item())
