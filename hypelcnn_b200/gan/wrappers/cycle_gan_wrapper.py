@@ -89,6 +89,44 @@ class TensorPool:
         return t
 
 
+class GraphedCall:
+    """A launch-bound chain of small kernels captured ONCE per input shape into a CUDA graph and replayed: one graph
+    launch instead of a few dozen kernel launches per call (a CycleGAN iteration at the reference's batch of 32 is
+    ~40 launches of a few microseconds each).  ``fn(*tensors)`` must be a pure function of its tensor arguments and of
+    device state that lives at fixed addresses (weights, gradient buffers), must not synchronise, and must be
+    idempotent (it is run twice before the capture); its return value — tensors at fixed addresses — is handed back
+    on every call and overwritten by the next one."""
+
+    def __init__(self, fn):
+        self.fn, self.cache = fn, {}
+
+    def __call__(self, *args):
+        key = tuple((tuple(a.shape), a.dtype, a.device) for a in args)
+        entry = self.cache.get(key)
+        if entry is None:
+            static_in = [a.clone() for a in args]
+            side = torch.cuda.Stream(device=args[0].device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                       # lazy initialisation (function attributes) and
+                for _ in range(2):                              # allocator warm-up happen outside the capture
+                    self.fn(*static_in)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self.fn(*static_in)
+            entry = self.cache[key] = (graph, static_in, static_out)
+        graph, static_in, static_out = entry
+        for held, given in zip(static_in, args):
+            held.copy_(given)
+        graph.replay()
+        return static_out
+
+
+def graphs_enabled():
+    import os
+    return os.environ.get("HYP_GAN_GRAPHS", "1") != "0"
+
+
 class GanKernels:
     """The C-ABI calls every GAN trainer chains (needs self.C and self.loss_acc)."""
 
@@ -172,6 +210,12 @@ class CycleGANTrainer(GanKernels):
         self.loss_acc = torch.zeros(4, dtype=torch.float64, device=self.device)
         self.allreduce = None  # set to a parallel.GradientAllReduce for data-parallel training
         self.last = {}
+        # the train ops replay CUDA graphs of the gradient computations (the Adam step and the all-reduce stay outside:
+        # learning rate and step count change every iteration)
+        self.use_graphs = graphs_enabled()
+        self._graph_gen = GraphedCall(self.generator_gradients)
+        self._graph_fakes = GraphedCall(self._discriminator_fakes)
+        self._graph_dis = GraphedCall(self._discriminator_gradients_of)
 
     # ---- views
     def G(self):
@@ -221,23 +265,27 @@ class CycleGANTrainer(GanKernels):
         return loss
 
     def generator_train_op(self, images_x, images_y, lr):
-        loss = self.generator_gradients(images_x, images_y)
+        if self.use_graphs:
+            loss = self._graph_gen(self._rows(images_x), self._rows(images_y))
+        else:
+            loss = self.generator_gradients(images_x, images_y)
         scale = self.allreduce(self.gen_grads) if self.allreduce is not None else 1.0
         self.gen_steps += 1
         E.adam_step(self.gen_params, self.gen_grads, self.gen_m, self.gen_v, lr, self.gen_steps, scale, b1=0.5)
         return loss
 
     # ---- discriminator step
-    def discriminator_gradients(self, images_x, images_y, use_pool=True):
-        x, y = self._rows(images_x), self._rows(images_y)
+    def _discriminator_fakes(self, x, y):
+        """G(x), F(y): what the discriminators are shown as fakes (before the tensor pool)."""
+        gx = self._gen_fwd(x, self.G())[:, 7, :].contiguous()
+        fy = self._gen_fwd(y, self.F())[:, 7, :].contiguous()
+        return gx, fy
+
+    def _discriminator_gradients_of(self, x, y, gx, fy):
         nd = self.nd
         gDY, gDX = self.dis_grads[:nd], self.dis_grads[nd:]
         self.dis_grads.zero_()
         self.loss_acc.zero_()
-        gx = self._gen_fwd(x, self.G())[:, 7, :].contiguous()
-        fy = self._gen_fwd(y, self.F())[:, 7, :].contiguous()
-        if use_pool:
-            gx, fy = self.pool_y(gx), self.pool_x(fy)
         for real, fake, w, gw in ((y, gx, self.DY(), gDY), (x, fy, self.DX(), gDX)):
             for data, target in ((real, 1.0), (fake, 0.0)):            # least_squares_discriminator_loss
                 h, d = self._dis_fwd(data, w)
@@ -252,8 +300,19 @@ class CycleGANTrainer(GanKernels):
         loss[0] = loss[1] + loss[2]
         return loss
 
+    def discriminator_gradients(self, images_x, images_y, use_pool=True, graphs=False):
+        """Fills dis_grads with dL_D / d[D_Y | D_X]; returns the device loss tensor [total, gan, regularisation, -].
+        The fakes pass through tfgan's tensor pool (host-side draws) between the two halves, which is why the graph
+        replay (``graphs``) comes as two graphs around it."""
+        x, y = self._rows(images_x), self._rows(images_y)
+        gx, fy = self._graph_fakes(x, y) if graphs else self._discriminator_fakes(x, y)
+        if use_pool:
+            gx, fy = self.pool_y(gx), self.pool_x(fy)
+        return self._graph_dis(x, y, gx, fy) if graphs else self._discriminator_gradients_of(x, y, gx, fy)
+
     def discriminator_train_op(self, images_x, images_y, lr):
-        loss = self.discriminator_gradients(images_x, images_y)
+        loss = self.discriminator_gradients(images_x, images_y, graphs=True) if self.use_graphs else \
+            self.discriminator_gradients(images_x, images_y)
         scale = self.allreduce(self.dis_grads) if self.allreduce is not None else 1.0
         self.dis_steps += 1
         E.adam_step(self.dis_params, self.dis_grads, self.dis_m, self.dis_v, lr, self.dis_steps, scale, b1=0.5)

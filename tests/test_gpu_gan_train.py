@@ -155,3 +155,26 @@ def test_single_direction_gan_gradients_and_registry(swap):
     assert t.global_step == 1 and t.gen_steps == 1 and t.dis_steps == 1
     with pytest.raises(KeyError):
         get_wrapper("no_such_gan", flags)
+
+
+def test_graph_replay_equals_eager_train_ops():
+    """The train ops replay CUDA graphs of the gradient computations (one graph launch instead of ~40 kernel launches per
+    iteration): same losses, same gradients and the same weights after a few iterations as the eager chain."""
+    x, y = _data(32, 64, seed=4)
+    eager, graphed = _trainer(pool_size=0), _trainer(pool_size=0)
+    eager.use_graphs, graphed.use_graphs = False, True
+    for step in range(1, 5):
+        x2, y2 = x * (1.0 + 0.01 * step), y * (1.0 - 0.01 * step)           # fresh inputs into the graphs' static buffers
+        le, lg = eager.generator_train_op(x2, y2, 2e-4), graphed.generator_train_op(x2, y2, 2e-4)
+        assert torch.allclose(le, lg.to(le.dtype), rtol=1e-5, atol=1e-7)
+        assert _rel(graphed.gen_grads, eager.gen_grads.double().cpu()) < 1e-5   # block-level atomics: order differs
+        le, lg = eager.discriminator_train_op(x2, y2, 1e-4), graphed.discriminator_train_op(x2, y2, 1e-4)
+        assert torch.allclose(le, lg.to(le.dtype), rtol=1e-5, atol=1e-7)
+        assert _rel(graphed.dis_grads, eager.dis_grads.double().cpu()) < 1e-5
+    assert _rel(graphed.gen_params, eager.gen_params.double().cpu()) < 1e-4
+    assert _rel(graphed.dis_params, eager.dis_params.double().cpu()) < 1e-4
+    assert len(graphed._graph_gen.cache) == 1 and len(graphed._graph_dis.cache) == 1
+    # with the tensor pool between the two discriminator graphs
+    pooled = _trainer(pool_size=2)
+    for step in range(6):
+        assert torch.isfinite(pooled.discriminator_train_op(x, y, 1e-4)).all()
