@@ -1115,7 +1115,11 @@ static int tc_backward(hyp_model& m, const uint8_t* labels, int64_t B, float* lo
                     1.f, gz_inv);
     if (rc) return rc;
     if (m.tensors[L.in_t].needs_grad) {
-      rc = tc_run(m, T.dg, tc_grad(m, L.in_t), nullptr, 0, ginit[L.in_t] ? EPI_ACCUM : EPI_STORE, "tc_gemm_kernel/dgrad",
+      // A gradient tensor that already holds contributions is accumulated into with fire-and-forget vector reductions
+      // (red.global.add.v4.f32: every element belongs to exactly one tile of the launch, so the result is the same as
+      // load + add + store, without the load's latency inside the epilogue).  HYP_DGRAD_RMW=1: load + add + store.
+      static const bool dgrad_rmw = getenv("HYP_DGRAD_RMW") && getenv("HYP_DGRAD_RMW")[0] == '1';
+      rc = tc_run(m, T.dg, tc_grad(m, L.in_t), nullptr, 0, ginit[L.in_t] ? (dgrad_rmw ? EPI_ACCUM : EPI_ATOMIC) : EPI_STORE, "tc_gemm_kernel/dgrad",
                   layer_flops(L, B), st, L.scope.c_str(), 1.f / S.w_scale, gz_inv);
       if (rc) return rc;
       ginit[L.in_t] = 1;

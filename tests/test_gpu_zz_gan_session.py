@@ -72,18 +72,22 @@ def test_run_session(tmp_path, gan_type, pairing, capsys):
     if gan_type == "cycle_gan":
         assert any(numpy.abs(ckpt[n]).sum() > 0 for n in names)              # the zero-initialised generator moved
     assert "Validation metrics for shadowed #11" in capsys.readouterr().out
-    # the final state is always written, and a second run over the same log dir continues from it: generators,
-    # discriminators, Adam moments and the step clocks (MonitoredTrainingSession(checkpoint_dir=log_dir))
-    final = numpy.load(os.path.join(log_dir, "model.ckpt-120.npz"))
+    # the final state is always written (the pair stream may end before --step iterations), and a second run over the
+    # same log dir continues from it: generators, discriminators, Adam moments and the step clocks
+    # (MonitoredTrainingSession(checkpoint_dir=log_dir))
+    last_step = max(int(f[len("model.ckpt-"):-len(".npz")]) for f in os.listdir(log_dir) if f.startswith("model.ckpt-"))
+    assert 100 < last_step <= 120
+    final = numpy.load(os.path.join(log_dir, f"model.ckpt-{last_step}.npz"))
     state_keys = [n for n in final.files if "train_state/" in n]
     assert any(n.endswith("dis_params") for n in state_keys) and any(n.endswith("_m") for n in state_keys)
     if gan_type != "dcl_gan":
-        flags.step = 7
-        run_session(vars(flags), base, loader=_loader())
+        run_session(vars(flags), base, loader=_loader())                     # same flags: as many iterations again
         assert "Restored" in capsys.readouterr().out
-        again = numpy.load(os.path.join(log_dir, "model.ckpt-127.npz"))
-        assert int(again["global_step"]) == 127
+        resumed = max(int(f[len("model.ckpt-"):-len(".npz")]) for f in os.listdir(log_dir) if f.startswith("model.ckpt-"))
+        assert resumed > last_step
+        again = numpy.load(os.path.join(log_dir, f"model.ckpt-{resumed}.npz"))
+        assert int(again["global_step"]) == resumed
         moved = [n for n in state_keys if n.endswith("dis_params") and not numpy.array_equal(final[n], again[n])]
         assert moved                                                         # training went on from the restored weights
         steps = [n for n in state_keys if n.endswith("gen_steps") or n.endswith("clock_gen")]
-        assert steps and all(int(again[n]) == int(final[n]) + 7 for n in steps)
+        assert steps and all(int(again[n]) == int(final[n]) + resumed - last_step for n in steps)
