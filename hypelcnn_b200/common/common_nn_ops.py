@@ -428,18 +428,17 @@ def create_metric_tensors(labels, y_conv, class_range, name_prefix, device=None)
 
 
 def calculate_class_accuracies_using_confusion(confusion_matrix, class_range):
-    """Reference: common/common_nn_ops.py:280-292 (host numpy on a 15x15 matrix)."""
-    class_space = class_range.stop
-    class_precisions = numpy.zeros(class_space)
-    class_recall = numpy.zeros(class_space)
-    for index in class_range:
-        total_ground_truths = numpy.sum(confusion_matrix[index, :])
-        if total_ground_truths != 0:
-            class_recall[index] = confusion_matrix[index, index] / total_ground_truths
-        total_predictions = numpy.sum(confusion_matrix[:, index])
-        if total_predictions != 0:
-            class_precisions[index] = confusion_matrix[index, index] / total_predictions
-    return class_recall[class_range], class_precisions[class_range]
+    """Per-class recall (diagonal / row sums: ground truths) and precision (diagonal / column sums: predictions) of a
+    confusion matrix, 0 where a class never occurs; only the classes of ``class_range`` are returned
+    (reference: common/common_nn_ops.py:280-292)."""
+    matrix = numpy.asarray(confusion_matrix, dtype=numpy.float64)
+    hits = numpy.diagonal(matrix)
+
+    def ratio(totals):
+        return numpy.divide(hits, totals, out=numpy.zeros_like(hits), where=totals != 0)
+
+    picked = numpy.arange(class_range.start, class_range.stop, class_range.step)
+    return ratio(matrix.sum(axis=1))[picked], ratio(matrix.sum(axis=0))[picked]
 
 
 def calculate_accuracy(sess, nn_params, class_range):

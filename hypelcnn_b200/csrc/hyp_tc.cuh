@@ -79,22 +79,7 @@ struct alignas(16) TcTile {
   TcColBlock cb[TC_MAX_CB];
 };
 
-// EPI_EVAL (K-major only): the inference epilogue — BatchNorm with the moving statistics (or + bias), activation and the
-// residual adds on the accumulator, written straight as the next layer's input (value plane + operand planes): the
-// pre-BN tensor never touches HBM and no separate normalisation pass runs.
-enum { EPI_STORE = 0, EPI_ACCUM = 1, EPI_ATOMIC = 2, EPI_EVAL = 3 };
-
-struct TcEval {
-  const float *mean, *rstd, *beta;  // per output channel of the layer (column block's stats_col = its first channel)
-  const float* res0;                // residual source value planes [rows][ld]; idx == NULL: identity channel map
-  const int* idx0;
-  const float* res1;
-  const int* idx1;
-  float* lo;                        // operand region of the output tensor (`out` is its value plane)
-  size_t op_plane;
-  int32_t ld0, ld1, act;            // act: 0 none, 1 leaky relu, 2 sigmoid (hyp_common.cuh Act)
-  float alpha;
-};
+enum { EPI_STORE = 0, EPI_ACCUM = 1, EPI_ATOMIC = 2 };
 
 // operand formats: how the two GEMM operands are stored and multiplied
 //   OP_TF32X3 : two fp32 planes (value, TF32 remainder), 3 kind::tf32 MMAs per K step of 8      (fp32-accurate)
@@ -122,7 +107,6 @@ struct TcParams {
   int32_t stages;
   int32_t ntiles;     // tiles of this launch (multiple of the CTA group size)
   unsigned long long* timing;  // nullable: [CTA][8] cycle counters (HYP_TC_TIMING diagnostics)
-  TcEval ev;                   // EPI_EVAL only
 };
 
 // b_rows = B rows held by ONE CTA per stage and plane
@@ -397,57 +381,8 @@ __device__ __forceinline__ void mbar_expect_tx_u(uint32_t pred, uint32_t bar, ui
       ::"r"(bar), "r"(bytes), "r"(pred) : "memory");
 }
 
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-__device__ __forceinline__ float tf32_lo_of(float a) { return tf32_rna(a - __uint_as_float(__float_as_uint(a) & 0xffffe000u)); }
-// 16-bit operand formats.  OP_F16X3: hi = fp16(x), lo = fp16(x - hi) — 22 significand bits as long as lo stays a
-// normal fp16 number (|x| >= 2^-3); below that the absolute error is bounded by half the subnormal spacing, 2^-25, so
-// tensors are scaled to O(1)..O(2^10) magnitudes before the split (see hyp_tc_engine.cuh).  OP_BF16: one bf16 plane.
-__device__ __forceinline__ void split_f16(float x, uint16_t& hi, uint16_t& lo) {
-  const __half h = __float2half_rn(x);
-  hi = __half_as_ushort(h);
-  lo = __half_as_ushort(__float2half_rn(x - __half2float(h)));
-}
-__device__ __forceinline__ uint16_t to_bf16(float x) { return __bfloat16_as_ushort(__float2bfloat16_rn(x)); }
-// the planes of 4 consecutive elements, 8 bytes per plane; `planes` points at element 0 of plane 0
-__device__ __forceinline__ void store_op16x4(uint16_t* planes, size_t plane_stride, int op, float v0, float v1, float v2, float v3) {
-  if (op == OP_F16X3) {
-    uint16_t h[4], l[4];
-    split_f16(v0, h[0], l[0]); split_f16(v1, h[1], l[1]); split_f16(v2, h[2], l[2]); split_f16(v3, h[3], l[3]);
-    *reinterpret_cast<uint2*>(planes) = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
-    *reinterpret_cast<uint2*>(planes + plane_stride) = make_uint2(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16));
-  } else {
-    *reinterpret_cast<uint2*>(planes) = make_uint2(to_bf16(v0) | ((uint32_t)to_bf16(v1) << 16),
-                                                   to_bf16(v2) | ((uint32_t)to_bf16(v3) << 16));
-  }
-}
-__device__ __forceinline__ void store_op16(uint16_t* planes, size_t plane_stride, int op, float v) {
-  if (op == OP_F16X3) {
-    uint16_t h, l;
-    split_f16(v, h, l);
-    planes[0] = h;
-    planes[plane_stride] = l;
-  } else {
-    planes[0] = to_bf16(v);
-  }
-}
 constexpr int TC_STAGE_LD = 20;                            // floats per staged row (16 + pad, keeps float4 alignment)
 constexpr int TC_STAGE_FLOATS = 32 * TC_STAGE_LD;          // per epilogue warp
-
-// one output value of the inference epilogue: normalise (same operation order as tc_bn_apply_kernel, so the fused and
-// the two-pass path agree bit for bit), activate, add the residual sources
-__device__ __forceinline__ float tc_eval_value(const TcEval& e, float z, float mean, float rstd, float beta, int64_t row, int ch) {
-  float y = (z - mean) * rstd + beta;
-  if (e.act == 1) y = fmaxf(y, e.alpha * y);
-  else if (e.act == 2) y = 1.f / (1.f + __expf(-y));
-  float r = 0.f;
-  if (e.res0) r += __ldg(e.res0 + row * e.ld0 + (e.idx0 ? __ldg(e.idx0 + ch) : ch));
-  if (e.res1) r += __ldg(e.res1 + row * e.ld1 + (e.idx1 ? __ldg(e.idx1 + ch) : ch));
-  return y + r;
-}
 
 template <bool MN, int CG, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -779,7 +714,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int cb_tcol = __shfl_sync(0xffffffffu, my_tcol, cb_i);
           const int cb_width = __shfl_sync(0xffffffffu, my_width, cb_i);
           const int64_t cb_off = __shfl_sync(0xffffffffu, my_off, cb_i);
-          const int cb_scol = __shfl_sync(0xffffffffu, my_scol, cb_i);
           if (c0 >= cb_tcol + cb_width) continue;  // padding columns of the block
 #pragma unroll
           for (int k = 0; k < 4; k++)
@@ -805,25 +739,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int i = 0; i < 4; i++) { v[i].x += o[i].x; v[i].y += o[i].y; v[i].z += o[i].z; v[i].w += o[i].w; }
             }
-            if (EPI == EPI_EVAL) {
-              const int ch = cb_scol + ocol;  // layer channel of this lane's first value
-              const int64_t grow0 = (cb_off - cb_scol) / ld_out + (q * 32 + r_lane);  // row of the output tensor
-              float mn[4], rs[4], bt[4];
-#pragma unroll
-              for (int t = 0; t < 4; t++) { mn[t] = __ldg(p.ev.mean + ch + t); rs[t] = __ldg(p.ev.rstd + ch + t); bt[t] = __ldg(p.ev.beta + ch + t); }
-#pragma unroll
-              for (int i = 0; i < 4; i++) {
-                float y[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-#pragma unroll
-                for (int t = 0; t < 4; t++) y[t] = tc_eval_value(p.ev, y[t], mn[t], rs[t], bt[t], grow0 + 8 * i, ch + t);
-                v[i] = make_float4(y[0], y[1], y[2], y[3]);
-                const int64_t idx = (obase - p.out) + i * ostep;
-                if (p.op == OP_TF32X3)
-                  *reinterpret_cast<float4*>(p.ev.lo + idx) = make_float4(tf32_lo_of(y[0]), tf32_lo_of(y[1]), tf32_lo_of(y[2]), tf32_lo_of(y[3]));
-                else
-                  store_op16x4(reinterpret_cast<uint16_t*>(p.ev.lo) + idx, p.ev.op_plane, p.op, y[0], y[1], y[2], y[3]);
-              }
-            }
 #pragma unroll
             for (int i = 0; i < 4; i++) {
               if (EPI == EPI_ATOMIC) atomicAdd(reinterpret_cast<float4*>(obase + i * ostep), v[i]);
@@ -845,14 +760,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int t = 0; t < 4; t++) {
                   if (t < nval) {
                     float x = vv[t];
-                    if (EPI == EPI_EVAL) {
-                      const int chn = cb_scol + ocol + t;
-                      x = tc_eval_value(p.ev, x, __ldg(p.ev.mean + chn), __ldg(p.ev.rstd + chn), __ldg(p.ev.beta + chn),
-                                        (cb_off - cb_scol) / ld_out + (q * 32 + i * 8 + r_lane), chn);
-                      const int64_t idx = (optr - p.out) + t;
-                      if (p.op == OP_TF32X3) p.ev.lo[idx] = tf32_lo_of(x);
-                      else store_op16(reinterpret_cast<uint16_t*>(p.ev.lo) + idx, p.ev.op_plane, p.op, x);
-                    }
                     if (EPI == EPI_ATOMIC) atomicAdd(optr + t, x);
                     else {
                       if (EPI == EPI_ACCUM) x += optr[t];
@@ -1026,10 +933,6 @@ template <bool MN, int CG>
 inline int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, int ntiles, cudaStream_t st) {
   if (p.epi == EPI_STORE) return launch_tc_epi<MN, CG, EPI_STORE>(tmA, tmB, p, ntiles, st);
   if (p.epi == EPI_ACCUM) return launch_tc_epi<MN, CG, EPI_ACCUM>(tmA, tmB, p, ntiles, st);
-  if (p.epi == EPI_EVAL) {
-    if constexpr (!MN && CG == 2) return launch_tc_epi<MN, CG, EPI_EVAL>(tmA, tmB, p, ntiles, st);
-    else return fail(HYP_E_INVALID, "tc gemm: the inference epilogue exists for K-major CTA-pair launches only");
-  }
   return launch_tc_epi<MN, CG, EPI_ATOMIC>(tmA, tmB, p, ntiles, st);
 }
 
@@ -1101,9 +1004,45 @@ inline int launch_tc_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParam
 // ------------------------------------------------------------------------------------------
 // fp32 -> (hi, lo) TF32 planes.  raw_hi = 1 keeps the unrounded value in plane 0 and relies on
 // the tensor core ignoring the 13 low mantissa bits (probe only).
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = tf32_rna(x);
   lo = tf32_rna(x - hi);
+}
+// 16-bit operand formats.  OP_F16X3: hi = fp16(x), lo = fp16(x - hi) — 22 significand bits as long as lo stays a
+// normal fp16 number (|x| >= 2^-3); below that the absolute error is bounded by half the subnormal spacing, 2^-25, so
+// tensors are scaled to O(1)..O(2^10) magnitudes before the split (see hyp_tc_engine.cuh).  OP_BF16: one bf16 plane.
+__device__ __forceinline__ void split_f16(float x, uint16_t& hi, uint16_t& lo) {
+  const __half h = __float2half_rn(x);
+  hi = __half_as_ushort(h);
+  lo = __half_as_ushort(__float2half_rn(x - __half2float(h)));
+}
+__device__ __forceinline__ uint16_t to_bf16(float x) { return __bfloat16_as_ushort(__float2bfloat16_rn(x)); }
+// the planes of 4 consecutive elements, 8 bytes per plane; `planes` points at element 0 of plane 0
+__device__ __forceinline__ void store_op16x4(uint16_t* planes, size_t plane_stride, int op, float v0, float v1, float v2, float v3) {
+  if (op == OP_F16X3) {
+    uint16_t h[4], l[4];
+    split_f16(v0, h[0], l[0]); split_f16(v1, h[1], l[1]); split_f16(v2, h[2], l[2]); split_f16(v3, h[3], l[3]);
+    *reinterpret_cast<uint2*>(planes) = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
+    *reinterpret_cast<uint2*>(planes + plane_stride) = make_uint2(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16));
+  } else {
+    *reinterpret_cast<uint2*>(planes) = make_uint2(to_bf16(v0) | ((uint32_t)to_bf16(v1) << 16),
+                                                   to_bf16(v2) | ((uint32_t)to_bf16(v3) << 16));
+  }
+}
+__device__ __forceinline__ void store_op16(uint16_t* planes, size_t plane_stride, int op, float v) {
+  if (op == OP_F16X3) {
+    uint16_t h, l;
+    split_f16(v, h, l);
+    planes[0] = h;
+    planes[plane_stride] = l;
+  } else {
+    planes[0] = to_bf16(v);
+  }
 }
 __global__ void split_planes16_kernel(const float* __restrict__ src, int64_t rows, int cols, int ld_src, uint16_t* planes,
                                       size_t plane_stride, int ld_dst, int op, float scale) {

@@ -894,13 +894,12 @@ static int tc_plan(hyp_model& m, int64_t B) {
 // formats: 1 / w_scale in forward, 1 / (w_scale * gz scale) in dgrad, 1 / gz scale in wgrad)
 static int tc_run(hyp_model& m, const TcLaunch& l, float* out, float* stats, int stats_ld, int epi, const char* tag,
                   double flops, cudaStream_t st, const char* scope = nullptr, float out_scale = 1.f,
-                  const float* out_scale_ptr = nullptr, const TcEval* ev = nullptr) {
+                  const float* out_scale_ptr = nullptr) {
   if (l.ntiles == 0) return HYP_OK;
   TcState& S = *m.tc;
   TcParams p{};
   p.segs = S.segs_dev; p.tiles = S.tiles_dev + l.tile0; p.out = out; p.stats = stats; p.stats_ld = stats_ld;
   p.op = S.op; p.out_scale = out_scale; p.out_scale_ptr = out_scale_ptr;
-  if (ev) p.ev = *ev;
   p.epi = epi; p.b_rows = l.b_rows; p.bn = l.bn; p.chunk_kb = 0; p.stages = 0;
   static const bool per_layer = getenv("HYP_PROF_LAYERS") != nullptr;
   std::string full = tag;
@@ -962,29 +961,6 @@ static int tc_forward(hyp_model& m, const float* x, int64_t B, bool training, bo
     const TcTensor& tout = S.tt[L.out_t];
     const int64_t rows = B * tout.PP;
     float* Z = reinterpret_cast<float*>(m.ws + T.z_off);
-    // Inference: BatchNorm with the moving statistics (or the bias), activation and the residual adds run inside the
-    // GEMM epilogue, which writes the layer's output planes directly (no z round trip, no tc_bn_apply pass).  Layers
-    // with an LRN behind them or split over two GEMMs (DUALCNN's two-input FC) keep the two-pass form.
-    static const bool fuse_off = getenv("HYP_EVAL_UNFUSED") && getenv("HYP_EVAL_UNFUSED")[0] == '1';
-    if (!training && !L.lrn && L.share == 0 && T.fwd.cg == 2 && !fuse_off) {
-      float* mean = reinterpret_cast<float*>(m.ws + T.mean_off);
-      float* rstd = reinterpret_cast<float*>(m.ws + T.rstd_off);
-      if (!L.bias_mode) {
-        TC_PROF("bn_finalize_kernel", 32.0 * L.Cout,
-                (bn_finalize_kernel<<<(unsigned)cdiv(L.Cout, 128), 128, 0, st>>>(
-                    nullptr, L.Cout, (double)rows, m.d.bn_eps, m.d.bn_decay, m.state + L.mm_off,
-                    m.state + L.mm_off + L.Cout, mean, rstd, 0, 0)));
-      }
-      TcEval ev{};
-      ev.mean = mean; ev.rstd = rstd; ev.beta = m.params + L.beta_off;
-      ev.lo = tc_plane1(m, L.out_t); ev.op_plane = tout.plane_elems; ev.act = L.act; ev.alpha = m.d.lrelu_alpha;
-      if (L.res.size() > 0) { ev.res0 = tc_plane0(m, L.res[0].src); ev.idx0 = L.res[0].idx; ev.ld0 = S.tt[L.res[0].src].Cp; }
-      if (L.res.size() > 1) { ev.res1 = tc_plane0(m, L.res[1].src); ev.idx1 = L.res[1].idx; ev.ld1 = S.tt[L.res[1].src].Cp; }
-      rc = tc_run(m, T.fwd, tc_plane0(m, L.out_t), nullptr, L.Cout, EPI_EVAL, "tc_gemm_kernel/fwd_eval", layer_flops(L, B), st,
-                  L.scope.c_str(), 1.f / S.w_scale, nullptr, &ev);
-      if (rc) return rc;
-      continue;
-    }
     rc = tc_run(m, T.fwd, Z, (training && !L.bias_mode) ? part : nullptr, L.Cout, L.share == 2 ? EPI_ACCUM : EPI_STORE,
                 "tc_gemm_kernel/fwd", layer_flops(L, B), st, L.scope.c_str(), 1.f / S.w_scale);
     if (rc) return rc;
