@@ -384,8 +384,10 @@ __device__ __forceinline__ void mbar_expect_tx_u(uint32_t pred, uint32_t bar, ui
 constexpr int TC_STAGE_LD = 20;                            // floats per staged row (16 + pad, keeps float4 alignment)
 constexpr int TC_STAGE_FLOATS = 32 * TC_STAGE_LD;          // per epilogue warp
 
+// 320 threads x 200 registers = 64 000 of the SM's 65 536: one CTA per SM (shared memory decides that anyway) and the
+// epilogue's 128-column register accumulator without spills (__launch_bounds__(320, 1) made ptxas stop at 168)
 template <bool MN, int CG, int EPI>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __maxnreg__(200)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -642,6 +644,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m_valid = h0.z, ncb = h0.w, ld_out = h1.x, stats_row = h1.y, total_kb = h1.z, n_cols = h2.z, nbp = h2.w;
       int my_bp_kb = 0x7fffffff, my_bp_n = 0;
       if (lane < nbp) { my_bp_kb = __ldg(&T->bp_kb[lane]); my_bp_n = __ldg(&T->bp_n[lane]); }
+      const int my_bp_n_first = __shfl_sync(0xffffffffu, my_bp_n, 0);  // MMA width at K block 0
       int my_tcol = 0x7fffffff, my_width = 0, my_scol = 0;
       int64_t my_off = 0;
       if (lane < ncb) {
@@ -652,74 +655,39 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // the two column halves split the tile's accumulator columns (multiples of 32 each)
       const int hw = ((n_cols + 63) >> 6) << 5;
       const int cbase = half * hw;
-      float acc[TC_MAX_COLS / 2];
-#pragma unroll
-      for (int i = 0; i < TC_MAX_COLS / 2; i++) acc[i] = 0.f;
-      {
-        const int nchunks = (total_kb + CH - 1) / CH;
-        for (int c = 0; c < nchunks; c++, gchunk++) {
-          const uint32_t buf = gchunk & 1u;
-          // columns the chunk accumulated = MMA width at its first K block (widths never increase inside a tile)
-          const uint32_t bpm = __ballot_sync(0xffffffffu, my_bp_kb <= c * CH);
-          const int n_c = __shfl_sync(0xffffffffu, my_bp_n, 31 - __clz((int)(bpm | 1u)));
-          long long t0 = p.timing ? clock64() : 0;
-          mbar_wait(tfull_bar(buf), (gchunk >> 1) & 1u);
-          if (p.timing) { const long long t1 = clock64(); tm_wait_tfull += t1 - t0; t0 = t1; }
-          tc_fence_after();
-#pragma unroll
-          for (int g = 0; g < 4; g++) {
-            const int tc0 = cbase + g * 32;
-            if (g * 32 < hw && tc0 < n_c) {
-              float v[32];
-              tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC_MAX_COLS + tc0), v);
-              if (tc0 + 32 <= n_c) {
-#pragma unroll
-                for (int j = 0; j < 32; j++) acc[g * 32 + j] += v[j];
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; j++) acc[g * 32 + j] += (tc0 + j < n_c) ? v[j] : 0.f;
-              }
-            }
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            const uint32_t tb = buf ? tempty_remote1 : tempty_remote0;
-            if (CG == 2)  // TMEM reads are complete (tcgen05.wait::ld): no memory ordering needed, skip the release fence
-              asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(tb) : "memory");
-            else
-              asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tb) : "memory");
-          }
-          if (p.timing) tm_drain += clock64() - t0;
-        }
-      }
-      const long long t_store0 = p.timing ? clock64() : 0;
-      // ---- write the tile.  Each warp stages 32 rows x 16 columns in smem and writes them back as
-      //      row segments (4 lanes x float4 = 64 contiguous bytes per row, 8 rows per instruction), so
-      //      global stores / read-modify-writes are sector-complete instead of one row per lane.
-      //      Column blocks map accumulator columns to output columns; they start at multiples of 16.
+      // ---- one 16-column slab of the tile: a16 = this lane's row, accumulator columns [c0, c0 + 16).  Each warp stages
+      //      32 rows x 16 columns in smem and writes them back as row segments (4 lanes x float4 = 64 contiguous bytes
+      //      per row, 8 rows per instruction), so global stores / read-modify-writes are sector-complete instead of
+      //      one row per lane.  Column blocks map accumulator columns to output columns; they start at multiples of 16.
       const int r_lane = lane >> 2, c4 = (lane & 3) * 4;
       const bool all_rows = m_valid == TC_BM;
-#pragma unroll
-      for (int g = 0; g < 4; g++) {
-        const int tc0 = cbase + g * 32;
-        if (g * 32 >= hw || tc0 >= n_cols) continue;  // warp-uniform
-#pragma unroll
-        for (int hh = 0; hh < 2; hh++) {
-          const int c0 = tc0 + hh * 16;  // first accumulator column of this 16-column slab
-          // column block holding the slab: blocks are listed by increasing tcol
-          const uint32_t cbm = __ballot_sync(0xffffffffu, my_tcol <= c0);
-          if (cbm == 0) continue;
-          const int cb_i = 31 - __clz((int)cbm);
-          const int cb_tcol = __shfl_sync(0xffffffffu, my_tcol, cb_i);
-          const int cb_width = __shfl_sync(0xffffffffu, my_width, cb_i);
-          const int64_t cb_off = __shfl_sync(0xffffffffu, my_off, cb_i);
-          if (c0 >= cb_tcol + cb_width) continue;  // padding columns of the block
+      int one_tcol = 0, one_width = 0;
+      int64_t one_off = 0;
+      if (ncb == 1) {  // the common case (1x1 convolutions, FC layers, every dgrad): no per-slab lookup
+        one_tcol = __shfl_sync(0xffffffffu, my_tcol, 0);
+        one_width = __shfl_sync(0xffffffffu, my_width, 0);
+        one_off = __shfl_sync(0xffffffffu, my_off, 0);
+      }
+      auto store_slab = [&](const float* a16, const int c0) {
+          // column block holding the slab: blocks are listed by increasing tcol (one block: uniform registers)
+          int cb_tcol = one_tcol, cb_width = one_width;
+          int64_t cb_off = one_off;
+          if (ncb != 1) {
+            const uint32_t cbm = __ballot_sync(0xffffffffu, my_tcol <= c0);
+            if (cbm == 0) return;
+            const int cb_i = 31 - __clz((int)cbm);
+            cb_tcol = __shfl_sync(0xffffffffu, my_tcol, cb_i);
+            cb_width = __shfl_sync(0xffffffffu, my_width, cb_i);
+            cb_off = __shfl_sync(0xffffffffu, my_off, cb_i);
+          } else if (c0 < cb_tcol) {
+            return;
+          }
+          if (c0 >= cb_tcol + cb_width) return;  // padding columns of the block
 #pragma unroll
           for (int k = 0; k < 4; k++)
             *reinterpret_cast<float4*>(st + lane * TC_STAGE_LD + 4 * k) =
-                make_float4(acc[g * 32 + hh * 16 + 4 * k] * oscale, acc[g * 32 + hh * 16 + 4 * k + 1] * oscale,
-                            acc[g * 32 + hh * 16 + 4 * k + 2] * oscale, acc[g * 32 + hh * 16 + 4 * k + 3] * oscale);
+                make_float4(a16[4 * k] * oscale, a16[4 * k + 1] * oscale,
+                            a16[4 * k + 2] * oscale, a16[4 * k + 3] * oscale);
           __syncwarp();
           const int ocol = c0 + c4 - cb_tcol;             // output column of this lane's 4 values
           float* const obase = p.out + cb_off + (int64_t)(q * 32 + r_lane) * ld_out + ocol;
@@ -795,7 +763,107 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             s_part[((u16 ? 1 : 0) * 4 + q) * TC_MAX_COLS + c0 + c4 + which] = w1;
           }
           __syncwarp();  // the staging rows are rewritten by the next slab
+      };
+      const int nchunks = (total_kb + CH - 1) / CH;
+      if (nchunks == 1) {
+        // ---- single-chunk tiles (K <= chunk_kb blocks: the 1x1 convolutions): straight from TMEM to the slabs, 32
+        //      columns at a time, no register accumulator; the TMEM buffer is handed back after the last read
+        const uint32_t buf = gchunk & 1u;
+        const int n_c = my_bp_n_first;
+        long long t0 = p.timing ? clock64() : 0;
+        mbar_wait(tfull_bar(buf), (gchunk >> 1) & 1u);
+        if (p.timing) { const long long t1 = clock64(); tm_wait_tfull += t1 - t0; t0 = t1; }
+        tc_fence_after();
+        gchunk++;
+        int last_g = -1;
+#pragma unroll
+        for (int g = 0; g < 4; g++)
+          if (g * 32 < hw && cbase + g * 32 < n_c) last_g = g;
+        if (last_g < 0) {  // this warp's column half is empty: only the hand-back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            const uint32_t tb = buf ? tempty_remote1 : tempty_remote0;
+            if (CG == 2) asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(tb) : "memory");
+            else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tb) : "memory");
+          }
         }
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+          const int tc0 = cbase + g * 32;
+          if (g * 32 < hw && tc0 < n_c) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC_MAX_COLS + tc0), v);
+            if (g == last_g) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                const uint32_t tb = buf ? tempty_remote1 : tempty_remote0;
+                if (CG == 2)  // TMEM reads are complete (tcgen05.wait::ld): no memory ordering needed, skip the release fence
+                  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(tb) : "memory");
+                else
+                  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tb) : "memory");
+              }
+            }
+            if (tc0 + 32 > n_c) {  // columns the MMAs never wrote
+#pragma unroll
+              for (int j = 0; j < 32; j++) v[j] = (tc0 + j < n_c) ? v[j] : 0.f;
+            }
+            if (tc0 < n_cols) store_slab(v, tc0);
+            if (tc0 + 16 < n_cols) store_slab(v + 16, tc0 + 16);
+          }
+        }
+        if (p.timing) tm_store += clock64() - t0;
+      } else {
+      float acc[TC_MAX_COLS / 2];
+#pragma unroll
+      for (int i = 0; i < TC_MAX_COLS / 2; i++) acc[i] = 0.f;
+      {
+        for (int c = 0; c < nchunks; c++, gchunk++) {
+          const uint32_t buf = gchunk & 1u;
+          // columns the chunk accumulated = MMA width at its first K block (widths never increase inside a tile)
+          const uint32_t bpm = __ballot_sync(0xffffffffu, my_bp_kb <= c * CH);
+          const int n_c = __shfl_sync(0xffffffffu, my_bp_n, 31 - __clz((int)(bpm | 1u)));
+          long long t0 = p.timing ? clock64() : 0;
+          mbar_wait(tfull_bar(buf), (gchunk >> 1) & 1u);
+          if (p.timing) { const long long t1 = clock64(); tm_wait_tfull += t1 - t0; t0 = t1; }
+          tc_fence_after();
+#pragma unroll
+          for (int g = 0; g < 4; g++) {
+            const int tc0 = cbase + g * 32;
+            if (g * 32 < hw && tc0 < n_c) {
+              float v[32];
+              tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC_MAX_COLS + tc0), v);
+              if (tc0 + 32 <= n_c) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) acc[g * 32 + j] += v[j];
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++) acc[g * 32 + j] += (tc0 + j < n_c) ? v[j] : 0.f;
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            const uint32_t tb = buf ? tempty_remote1 : tempty_remote0;
+            if (CG == 2)  // TMEM reads are complete (tcgen05.wait::ld): no memory ordering needed, skip the release fence
+              asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(tb) : "memory");
+            else
+              asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tb) : "memory");
+          }
+          if (p.timing) tm_drain += clock64() - t0;
+        }
+      }
+      const long long t_store0 = p.timing ? clock64() : 0;
+#pragma unroll
+      for (int g = 0; g < 4; g++) {
+        const int tc0 = cbase + g * 32;
+        if (g * 32 >= hw || tc0 >= n_cols) continue;  // warp-uniform
+        store_slab(acc + g * 32, tc0);
+        if (tc0 + 16 < n_cols) store_slab(acc + g * 32 + 16, tc0 + 16);
+      }
+      if (p.timing) tm_store += clock64() - t_store0;
       }
       if (EPI == EPI_STORE && p.stats) {
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -818,7 +886,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");  // s_part is reused by the next tile
       }
-      if (p.timing) { tm_store += clock64() - t_store0; tm_tiles++; }
+      if (p.timing) tm_tiles++;
     }
     if (p.timing && warp == 2 && lane == 0) {
       p.timing[blockIdx.x * 8 + 4] = (unsigned long long)tm_wait_tfull;
