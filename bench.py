@@ -299,8 +299,9 @@ def run_native(args):
             # tensor-pipe work per useful MAC relative to one bf16 MMA: 3 tf32 MMAs at half rate / 3 f16 MMAs / 1
             pipe_factor = {"3xtf32": 6, "3xf16": 3, "bf16": 1}.get(args.precision)
             traffic, traffic_src = None, None
-            tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
-            if args.precision == "3xtf32" and args.workload == "c2_grss2013" and B == 4096 and os.path.exists(tp):
+            # ncu dram bytes per GEMM launch of the same workload, from the committed launch list of that precision
+            tp = os.path.join(ROOT, "profiles", {"3xtf32": "r01_gemm_traffic.json", "3xf16": "r02_gemm_traffic.json"}.get(args.precision, "none"))
+            if args.workload == "c2_grss2013" and B == 4096 and os.path.exists(tp):
                 t = json.load(open(tp))  # dram__bytes_read.sum + dram__bytes_write.sum, averaged per GEMM launch (ncu)
                 traffic, traffic_src = t["gemm_dram_bytes_per_launch"], t["source"]
             roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",

@@ -116,8 +116,8 @@ struct hyp_model {
   const float* last_x = nullptr;
   hyp::tc::TcState* tc = nullptr;  // tensor-core engine state (HYP_PRECISION_3XTF32)
   // gradient-ready notification (hyp_model_set_grad_notify)
-  cudaEvent_t notify_event = nullptr;
-  int64_t notify_offset = 0;
+  struct Notify { cudaEvent_t event; int64_t offset; };
+  std::vector<Notify> notify;
 };
 
 namespace hyp {
@@ -585,11 +585,13 @@ static double layer_flops(const Layer& L, int64_t B) {
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static inline int ew_grid(int64_t total) { return (int)std::min<int64_t>(cdiv(total, 256), 148 * 16); }
 
-// records the notify event once every layer whose parameters start at or above notify_offset is done
+// records a registered event once every layer whose parameters start at or above its offset is done (backward walks
+// the layers last to first, parameters are laid out in layer order)
 static void grad_notify(const hyp_model& m, int li, cudaStream_t st) {
-  if (!m.notify_event) return;
-  const bool here = m.layers[li].w_off[0] >= m.notify_offset && (li == 0 || m.layers[li - 1].w_off[0] < m.notify_offset);
-  if (here) cudaEventRecord(m.notify_event, st);
+  for (const hyp_model::Notify& n : m.notify) {
+    const bool here = m.layers[li].w_off[0] >= n.offset && (li == 0 || m.layers[li - 1].w_off[0] < n.offset);
+    if (here) cudaEventRecord(n.event, st);
+  }
 }
 
 static const float* act_ptr(const hyp_model& m, int t, const float* x) {
@@ -958,9 +960,18 @@ int hyp_model_loss_backward(hyp_model* m, const float* x, const uint8_t* labels,
 
 int hyp_model_set_grad_notify(hyp_model* m, int64_t param_offset, void* event) {
   HYP_CHECK_ARG(m, "null model");
-  HYP_CHECK_ARG(!event || (param_offset >= 0 && param_offset <= m->n_params), "param_offset out of range");
-  m->notify_event = static_cast<cudaEvent_t>(event);
-  m->notify_offset = param_offset;
+  if (!event) {  // no event: forget every registration
+    m->notify.clear();
+    return HYP_OK;
+  }
+  HYP_CHECK_ARG(param_offset >= 0 && param_offset < m->n_params, "param_offset outside the parameter buffer");
+  for (hyp_model::Notify& n : m->notify)
+    if (n.event == static_cast<cudaEvent_t>(event)) {
+      n.offset = param_offset;
+      return HYP_OK;
+    }
+  HYP_CHECK_ARG(m->notify.size() < 8, "at most 8 gradient notifications");
+  m->notify.push_back({static_cast<cudaEvent_t>(event), param_offset});
   return HYP_OK;
 }
 

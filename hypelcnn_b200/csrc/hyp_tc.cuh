@@ -13,8 +13,10 @@
 //   MN = false : A [rows, K] and B [n, K] are K-major (forward, dgrad)
 //   MN = true  : A [K, rows] and B [K, n] are MN-major (wgrad: K runs over batch rows)
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..9 = epilogue (TMEM chunks -> fp32 register sums -> global, per-tile BatchNorm
+// Warp roles (384 threads = three warpgroups): warpgroup 0 = warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer,
+// warps 2..3 idle; warpgroups 1..2 = warps 4..11 epilogue.  The first warpgroup hands most of its registers back
+// (setmaxnreg.dec 104), the epilogue warpgroups take them (setmaxnreg.inc 200): the epilogue keeps a 128-column fp32
+// accumulator per thread and spilled at the 168 registers a uniform 384-thread CTA gets.  Epilogue (TMEM chunks -> fp32 register sums -> global, per-tile BatchNorm
 // partial sums).
 #pragma once
 #include <cuda.h>
@@ -31,7 +33,8 @@ namespace hyp {
 namespace tc {
 
 constexpr int TC_EPI_WARPS = 8;
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_EPI_WARP0 = 4;            // first epilogue warp (warpgroup-aligned)
+constexpr int TC_THREADS = 32 * (TC_EPI_WARP0 + TC_EPI_WARPS);
 constexpr int TC_BM = 128;
 constexpr int TC_KB = 32;                  // fp32 elements of K per pipeline stage
 constexpr int TC_PLANE_A = TC_BM * 128;    // bytes of one A plane per stage
@@ -384,10 +387,8 @@ __device__ __forceinline__ void mbar_expect_tx_u(uint32_t pred, uint32_t bar, ui
 constexpr int TC_STAGE_LD = 20;                            // floats per staged row (16 + pad, keeps float4 alignment)
 constexpr int TC_STAGE_FLOATS = 32 * TC_STAGE_LD;          // per epilogue warp
 
-// 320 threads x 200 registers = 64 000 of the SM's 65 536: one CTA per SM (shared memory decides that anyway) and the
-// epilogue's 128-column register accumulator without spills (__launch_bounds__(320, 1) made ptxas stop at 168)
 template <bool MN, int CG, int EPI>
-__global__ void __maxnreg__(200)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -447,6 +448,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = uni(*reinterpret_cast<volatile uint32_t*>(tmem_slot));
 
+  if (warp < TC_EPI_WARP0) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
   if (warp == 0) {
     // ===================== TMA producer (one warp per CTA, one elected lane issues) =====================
     const uint32_t pred = elect_one_pred();
@@ -623,12 +626,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         p.timing[blockIdx.x * 8 + 3] = (unsigned long long)tm_wait_tempty;
       }
     }
+  }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
     // ===================== epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves =====================
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - TC_EPI_WARP0) >> 2;
     const int row = q * 32 + lane;
-    float* st = s_stage + (warp - 2) * TC_STAGE_FLOATS;
+    float* st = s_stage + (warp - TC_EPI_WARP0) * TC_STAGE_FLOATS;
     uint32_t gchunk = 0;
     long long tm_wait_tfull = 0, tm_store = 0, tm_drain = 0, tm_tiles = 0;
     const float oscale = p.out_scale * (p.out_scale_ptr ? __ldg(p.out_scale_ptr) : 1.f);
@@ -867,7 +872,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (EPI == EPI_STORE && p.stats) {
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        const int t = threadIdx.x - 64;
+        const int t = threadIdx.x - 32 * TC_EPI_WARP0;
         float* srow = p.stats + (size_t)stats_row * 2 * p.stats_ld;
         for (int b = 0; b < (m_valid > 0 ? ncb : 0); b++) {  // phantom tiles (m_valid == 0) own no statistics row
           const int b_tcol = __shfl_sync(0xffffffffu, my_tcol, b), b_width = __shfl_sync(0xffffffffu, my_width, b);
@@ -888,7 +893,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (p.timing) tm_tiles++;
     }
-    if (p.timing && warp == 2 && lane == 0) {
+    if (p.timing && warp == TC_EPI_WARP0 && lane == 0) {
       p.timing[blockIdx.x * 8 + 4] = (unsigned long long)tm_wait_tfull;
       p.timing[blockIdx.x * 8 + 5] = (unsigned long long)tm_store;
       p.timing[blockIdx.x * 8 + 6] = (unsigned long long)tm_drain;

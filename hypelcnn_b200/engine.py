@@ -59,7 +59,7 @@ class PatchEngine:
         self.global_step = 0
         self._max_batch = 0
         self.params = self.grads = self.state = self.adam_m = self.adam_v = self.workspace = None
-        self._notify_event = self._comm_stream = None
+        self._notify_events = self._comm_stream = self._notify_handle = None
         self._create(int(max_batch))
 
     # ------------------------------------------------------------------ lifecycle
@@ -304,28 +304,49 @@ class PatchEngine:
         seed = self.global_step if seed is None else seed
         self.forward_inplace(x, True, True, seed)
         overlap = allreduce is not None and getattr(allreduce, "overlap", False)
-        if overlap:
-            # the FC / decoder gradients (the tail of the flat buffer, ~70 % of it) are final early in backward:
-            # their all-reduce runs on the communication stream while the conv layers are still going backward
-            if self._notify_event is None:
-                self._notify_event = torch.cuda.Event()
-                self._notify_event.record()  # materialises the cudaEvent_t
+        splits = self.grad_split_offsets if overlap else []
+        if overlap and splits:
+            # Parameters are laid out in layer order and backward walks the layers last to first: the piece of the flat
+            # gradient buffer behind each split point is final long before backward ends.  Its all-reduce runs on the
+            # communication stream meanwhile; only the head (the six spectral 1x1 convolutions, 2 MB) is reduced after
+            # the last layer's backward.
+            if self._notify_events is None:
+                self._notify_events = [torch.cuda.Event() for _ in splits]
+                for ev in self._notify_events:
+                    ev.record()  # materialises the cudaEvent_t
                 self._comm_stream = torch.cuda.Stream(device=self.device)
-            N.check(N.lib().hyp_model_set_grad_notify(self._handle, self.grad_split_offset,
-                                                      ctypes.c_void_p(self._notify_event.cuda_event)))
+                self._notify_handle = None
+            if self._notify_handle != self._handle.value:   # a re-created native model (capacity growth) forgets them
+                for off, ev in zip(splits, self._notify_events):
+                    N.check(N.lib().hyp_model_set_grad_notify(self._handle, off, ctypes.c_void_p(ev.cuda_event)))
+                self._notify_handle = self._handle.value
         loss = self.loss_backward(x, labels)
         scale = 1.0
-        if overlap:
+        if overlap and splits:
             main = torch.cuda.current_stream()
-            self._comm_stream.wait_event(self._notify_event)
+            end = self.grads.numel()
             with torch.cuda.stream(self._comm_stream):
-                allreduce(self.grads[self.grad_split_offset:])
-            scale = allreduce(self.grads[:self.grad_split_offset])
+                for off, ev in zip(splits, self._notify_events):      # tail first: that is the order they become final
+                    self._comm_stream.wait_event(ev)
+                    allreduce(self.grads[off:end])
+                    end = off
+            scale = allreduce(self.grads[:end])
             main.wait_stream(self._comm_stream)
         elif allreduce is not None:
             scale = allreduce(self.grads)
         self.adam_step(grad_scale=scale)
         return loss
+
+    @property
+    def grad_split_offsets(self):
+        """Split points of the overlapped gradient all-reduce, largest first: the first parameter of the FC block (the
+        FC / decoder tail, ~70 % of the buffer, is final once fc_0's backward has run) and the first parameter of the
+        spatial levels (final once connector_0's backward has run)."""
+        offs = [self.grad_split_offset]
+        level = [off for name, (kind, off, shape) in self.variables.items() if kind == 0 and len(shape) == 4 and shape[0] > 1]
+        if level and 0 < min(level) < offs[0]:
+            offs.append(min(level))
+        return [o for o in offs if o > 0]
 
     @property
     def grad_split_offset(self):

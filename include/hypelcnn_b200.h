@@ -149,7 +149,9 @@ int hyp_model_loss_backward(hyp_model* m, const float* x, const uint8_t* labels,
 /* Overlap of the gradient all-reduce with the rest of backward (multi-GPU).  Parameters are laid
  * out in layer order and backward walks the layers last to first, so the tail [param_offset, n_params) of the
  * flat gradient buffer is final as soon as the first layer at or above param_offset has been processed:
- * hyp_model_loss_backward then records `event` (a cudaEvent_t) on its stream.  event == NULL clears it. */
+ * hyp_model_loss_backward then records `event` (a cudaEvent_t) on its stream.  Up to 8 events with different offsets
+ * can be registered (one call each; calling again with a registered event moves its offset): the buffer is then reduced
+ * in as many pieces, each as soon as it is final.  event == NULL forgets all registrations. */
 int hyp_model_set_grad_notify(hyp_model* m, int64_t param_offset, void* event);
 
 /* TF1 AdamOptimizer (ApplyAdam): lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m += (g-m)(1-b1);
