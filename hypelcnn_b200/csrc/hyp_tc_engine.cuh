@@ -924,11 +924,6 @@ static int tc_run(hyp_model& m, const TcLaunch& l, float* out, float* stats, int
     HYP_LAUNCHED();                               \
   } while (0)
 
-// rows per block for the one-column-per-thread kernels: about 8 resident blocks per SM over the whole grid
-static inline int tc_rows_per_block(int64_t rows, int cols) {
-  const int64_t xblocks = cdiv(cols, 128), want = std::max<int64_t>(1, 148 * 8 / xblocks);
-  return (int)std::max<int64_t>(8, cdiv(cdiv(rows, want), 8) * 8);
-}
 static inline int tc_grid(int64_t total) { return (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(total, 256), 148 * 16)); }
 
 static int tc_forward(hyp_model& m, const float* x, int64_t B, bool training, bool update_moving, uint64_t seed,
@@ -944,7 +939,7 @@ static int tc_forward(hyp_model& m, const float* x, int64_t B, bool training, bo
       const Tensor& tn = m.tensors[t];
       const TcTensor& tx = S.tt[t];
       TC_PROF("tc_prep_input_kernel", 12.0 * B * tx.PP * tx.C,
-              (tc_prep_input_kernel<<<tc_grid(B * tx.PP * tx.C), 256, 0, st>>>(
+              (tc_prep_input_kernel<<<tc_grid(B * tx.PP * cdiv(tx.C, 4) * 8), 256, 0, st>>>(
                   x, (int)B, m.d.patch, m.d.channels, tn.x_c0, tn.x_crop, tn.P, tx.C, tx.Cp, tc_plane0(m, (int)t),
                   tc_plane1(m, (int)t), S.op, tx.plane_elems)));
     }
@@ -994,11 +989,8 @@ static int tc_forward(hyp_model& m, const float* x, int64_t B, bool training, bo
       p.res1 = tc_plane0(m, L.res[1].src); p.idx1 = L.res[1].idx; p.ld1 = S.tt[L.res[1].src].Cp;
     }
     const double bytes = 4.0 * rows * L.Cout * (3 + L.res.size());
-    if (L.Cout % 4 == 0) {  // (a 2-D row-lane form of this kernel measured 15 % slower: the flat float4 walk keeps more rows in flight)
-      TC_PROF("tc_bn_apply_kernel", bytes, (tc_bn_apply_kernel<4><<<tc_grid(rows * (L.Cout / 4)), 256, 0, st>>>(p)));
-    } else {
-      TC_PROF("tc_bn_apply_kernel", bytes, (tc_bn_apply_kernel<1><<<tc_grid(rows * L.Cout), 256, 0, st>>>(p)));
-    }
+    // (a 2-D row-lane form of this kernel measured 15 % slower: the flat float4 walk keeps more rows in flight)
+    TC_PROF("tc_bn_apply_kernel", bytes, (tc_bn_apply_kernel<4><<<tc_grid(rows * cdiv(L.Cout, 4)), 256, 0, st>>>(p)));
     if (L.lrn) {
       TC_PROF("tc_lrn_fwd_kernel", 16.0 * rows * L.Cout,
               (tc_lrn_fwd_kernel<<<tc_grid(rows * 32), 256, 8 * L.Cout * sizeof(float), st>>>(
@@ -1078,14 +1070,10 @@ static int tc_backward(hyp_model& m, const uint8_t* labels, int64_t B, float* lo
                                                                          m.grads + L.beta_off, L.bias_mode ? 1 : 0, p.rstd,
                                                                          S.op == OP_F16X3 ? reinterpret_cast<unsigned int*>(gzs) : nullptr);
     HYP_LAUNCHED();
-    if (p.fpad == 0 || (p.f % 4 == 0 && p.ft % 4 == 0 && p.fpad % 4 == 0)) {
+    {
       const EwGrid ga = ew_grid2(p.gcols, rows);
       TC_PROF("tc_bn_bwd_apply_kernel", 4.0 * rows * (2.0 * L.Cout + 2.0 * p.gcols),
               TC_EW_DISPATCH(ga, tc_bn_bwd_apply_v4_kernel, p, ga.rpb));
-    } else {  // slot widths that break float4 alignment: scalar form
-      TC_PROF("tc_bn_bwd_apply_kernel", 4.0 * rows * (2.0 * L.Cout + 2.0 * p.gcols),
-              (tc_bn_bwd_apply_kernel<<<dim3((unsigned)cdiv(p.gcols, 128), (unsigned)cdiv(rows, tc_rows_per_block(rows, p.gcols))), 256,
-                                        0, st>>>(p, tc_rows_per_block(rows, p.gcols))));
     }
     for (const Resid& r : L.res) {
       const Tensor& src = m.tensors[r.src];

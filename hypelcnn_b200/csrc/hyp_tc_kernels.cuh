@@ -45,10 +45,13 @@ __global__ void __launch_bounds__(256) tc_prep_input_kernel(const float* __restr
     const int ph = pos / P, pw = pos - ph * P;
     const float* src = x + (((int64_t)b * P0 + ph + crop) * P0 + pw + crop) * C0 + c0;
     const int64_t o = ((int64_t)pos * B + b) * ld;
-    for (int c = lane; c < C; c += 32) {
-      const float v = __ldg(src + c);
-      hi[o + c] = v;
-      tc_store_operand(lo, op_plane, op, o + c, v);
+    // 4 channels per lane: the source row (C floats at an arbitrary 4-byte phase) is read element-wise, the planes
+    // are written 16 / 8 bytes at a time (rows of the planes are 16-byte aligned; columns C..ld-1 are padding)
+    for (int c = 4 * lane; c < C; c += 128) {
+      const float v0 = __ldg(src + c), v1 = c + 1 < C ? __ldg(src + c + 1) : 0.f;
+      const float v2 = c + 2 < C ? __ldg(src + c + 2) : 0.f, v3 = c + 3 < C ? __ldg(src + c + 3) : 0.f;
+      *reinterpret_cast<float4*>(hi + o + c) = make_float4(v0, v1, v2, v3);
+      tc_store_operand4(lo, op_plane, op, o + c, v0, v1, v2, v3);
     }
   }
 }
@@ -173,7 +176,7 @@ __device__ __forceinline__ void tc_bn_apply_load(const TcApplyArgs& p, int64_t i
       it.r[0] += t.x; it.r[1 % VEC] += t.y; it.r[2 % VEC] += t.z; it.r[3 % VEC] += t.w;
     } else {
 #pragma unroll
-      for (int j = 0; j < VEC; j++) it.r[j] += p.res0[it.m * p.ld0 + (p.idx0 ? p.idx0[it.c0 + j] : it.c0 + j)];
+      for (int j = 0; j < VEC; j++) it.r[j] += p.res0[it.m * p.ld0 + (p.idx0 ? p.idx0[min(it.c0 + j, p.C - 1)] : it.c0 + j)];
     }
   }
   if (p.res1) {
@@ -182,7 +185,7 @@ __device__ __forceinline__ void tc_bn_apply_load(const TcApplyArgs& p, int64_t i
       it.r[0] += t.x; it.r[1 % VEC] += t.y; it.r[2 % VEC] += t.z; it.r[3 % VEC] += t.w;
     } else {
 #pragma unroll
-      for (int j = 0; j < VEC; j++) it.r[j] += p.res1[it.m * p.ld1 + (p.idx1 ? p.idx1[it.c0 + j] : it.c0 + j)];
+      for (int j = 0; j < VEC; j++) it.r[j] += p.res1[it.m * p.ld1 + (p.idx1 ? p.idx1[min(it.c0 + j, p.C - 1)] : it.c0 + j)];
     }
   }
 }
@@ -191,7 +194,7 @@ template <int VEC>
 __device__ __forceinline__ void tc_bn_apply_finish(const TcApplyArgs& p, TcApplyItem<VEC>& it) {
 #pragma unroll
   for (int j = 0; j < VEC; j++) {
-    const int c = it.c0 + j;
+    const int c = min(it.c0 + j, p.C - 1);  // columns C..ldo-1 of the last group are padding (their value is unused)
     float y = (it.v[j] - p.mean[c]) * p.rstd[c] + p.beta[c];
     y = act_fwd(y, p.act, p.alpha);
     if (p.keep < 1.f) y = (philox_uniform(p.seed, p.stream_id, (uint64_t)(it.m * p.C + c)) < p.keep) ? y / p.keep : 0.f;
@@ -246,20 +249,6 @@ struct TcBnBwdArgs {
   int nt, ft;         //   q = R-1 - slot/nt, jt = slot % nt (n < min(ft, f - jt*ft)); fpad == 0: identity
 };
 
-__device__ __forceinline__ float tc_bn_gy(const TcBnBwdArgs& p, int64_t m, int c, float& zhat) {
-  zhat = (p.z[m * p.ldz + c] - p.mean[c]) * p.rstd[c];
-  const float y = zhat + p.beta[c];
-  float g = p.gout[m * p.ldg + c];
-  if (p.keep < 1.f) g = (philox_uniform(p.seed, p.stream_id, (uint64_t)(m * p.C + c)) < p.keep) ? g / p.keep : 0.f;
-  if (p.act == ACT_LRELU) {
-    g = (y > 0.f) ? g : g * p.alpha;
-  } else if (p.act == ACT_SIGMOID) {
-    const float s = 1.f / (1.f + __expf(-y));
-    g = g * s * (1.f - s);
-  }
-  return g;
-}
-
 // OP_F16X3: gz is multiplied by a power of two before the fp16 split so that its largest possible magnitude lands just
 // below 2^15 (fp16 tops out at 65504; remainders of values >= 2^-3 stay normal fp16 numbers).  The bound comes from the
 // backward statistics pass (tc_bn_bwd_finalize8_kernel); the inverse goes to the dgrad / wgrad epilogues.
@@ -291,58 +280,6 @@ __device__ __forceinline__ void tc_publish_gz_scale(const TcBnBwdArgs& p, float 
   if (p.gz_scale_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
     p.gz_scale_out[0] = scale;
     p.gz_scale_out[1] = 1.f / scale;
-  }
-}
-
-// gz = rstd * (g_y - mean(g_y) - zhat * mean(g_y * zhat)), written as operand planes in the
-// column order the dgrad / wgrad GEMMs want
-// scalar form for slot widths that break float4 alignment: one gz column per thread (128 columns x 2 row lanes per
-// block), so the slot -> channel mapping and the per-channel constants are computed once and the row loop keeps four
-// independent loads of gout and z in flight; grid = (ceil(gcols / 128), row blocks)
-__global__ void __launch_bounds__(256) tc_bn_bwd_apply_kernel(const TcBnBwdArgs p, int rows_per_block) {
-  const int j = blockIdx.x * 128 + (threadIdx.x & 127), ty = threadIdx.x >> 7;
-  const float gscale = tc_gz_scale(p);
-  tc_publish_gz_scale(p, gscale);
-  if (j >= p.gcols) return;
-  int c = j;
-  bool valid = j < p.C;
-  if (p.fpad) {
-    const int slot = j / p.fpad, n = j - slot * p.fpad;
-    const int jt = slot % p.nt;
-    valid = slot < p.R * p.nt && n < min(p.ft, p.f - jt * p.ft);
-    c = (p.R - 1 - slot / p.nt) * p.f + jt * p.ft + n;
-  }
-  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
-  const int64_t r1 = min((int64_t)p.rows, r0 + rows_per_block);
-  if (!valid) {
-    for (int64_t r = r0 + ty; r < r1; r += 2) tc_store_gz(p, r * p.ldgz + j, 1.f, 0.f);
-    return;
-  }
-  const float mean = p.mean[c], rstd = p.rstd[c], beta = p.beta[c], s1 = p.s1[c], s2 = p.s2[c];
-  for (int64_t r = r0 + ty; r < r1; r += 8) {
-    float g[4], z[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int64_t rr = r + 2 * u;
-      if (rr < r1) { g[u] = p.gout[rr * p.ldg + c]; z[u] = p.z[rr * p.ldz + c]; }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int64_t rr = r + 2 * u;
-      if (rr < r1) {
-        const float zhat = (z[u] - mean) * rstd;
-        const float y = zhat + beta;
-        float gy = g[u];
-        if (p.keep < 1.f) gy = (philox_uniform(p.seed, p.stream_id, (uint64_t)(rr * p.C + c)) < p.keep) ? gy / p.keep : 0.f;
-        if (p.act == ACT_LRELU) {
-          gy = (y > 0.f) ? gy : gy * p.alpha;
-        } else if (p.act == ACT_SIGMOID) {
-          const float sg = 1.f / (1.f + __expf(-y));
-          gy = gy * sg * (1.f - sg);
-        }
-        tc_store_gz(p, rr * p.ldgz + j, gscale, rstd * (gy - s1 - zhat * s2));
-      }
-    }
   }
 }
 
@@ -455,16 +392,16 @@ __global__ void __launch_bounds__(256) tc_bn_bwd_apply_v4_kernel(const TcBnBwdAr
   tc_publish_gz_scale(p, gscale);
   if (j0 >= p.gcols) return;
   int c0 = j0;
-  bool valid = j0 < p.C;
+  int nv = min(4, p.C - j0);  // valid values of this thread's 4 columns (<= 0: padding only)
   if (p.fpad) {
     const int slot = j0 / p.fpad, n = j0 - slot * p.fpad;
     const int jt = slot % p.nt;
-    valid = slot < p.R * p.nt && n < min(p.ft, p.f - jt * p.ft);
+    nv = slot < p.R * p.nt ? min(4, min(p.ft, p.f - jt * p.ft) - n) : 0;  // a slot's tail columns are padding
     c0 = (p.R - 1 - slot / p.nt) * p.f + jt * p.ft + n;
   }
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
   const int64_t r1 = min((int64_t)p.rows, r0 + rows_per_block);
-  if (!valid) {  // padding columns of the slot layout: zeros
+  if (nv <= 0) {  // padding columns of the slot layout: zeros
     for (int64_t r = r0 + ty; r < r1; r += TY) tc_store_gz4(p, r * p.ldgz + j0, 1.f, 0.f, 0.f, 0.f, 0.f);
     return;
   }
@@ -474,21 +411,22 @@ __global__ void __launch_bounds__(256) tc_bn_bwd_apply_v4_kernel(const TcBnBwdAr
   tc_load_ch4(p.beta, c0, p.C, beta);
   tc_load_ch4(p.s1, c0, p.C, s1);
   tc_load_ch4(p.s2, c0, p.C, s2);
-  const bool c_aligned = (c0 & 3) == 0;  // level slots with f % 4 == 0 keep float4 alignment of the source row
+  // float4 loads need 4 valid, 16-byte aligned source values (level slots with f % 4 == 0 keep the alignment)
+  const bool vec = nv == 4 && (c0 & 3) == 0;
   for (int64_t r = r0 + ty; r < r1; r += 4 * TY) {
     float4 gv[4], zv[4];
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       const int64_t rr = r + u * TY;
       if (rr < r1) {
-        if (c_aligned) {
+        if (vec) {
           gv[u] = *reinterpret_cast<const float4*>(p.gout + rr * p.ldg + c0);
           zv[u] = *reinterpret_cast<const float4*>(p.z + rr * p.ldz + c0);
         } else {
           const float* gp = p.gout + rr * p.ldg + c0;
           const float* zp = p.z + rr * p.ldz + c0;
-          gv[u] = make_float4(gp[0], gp[1], gp[2], gp[3]);
-          zv[u] = make_float4(zp[0], zp[1], zp[2], zp[3]);
+          gv[u] = make_float4(gp[0], nv > 1 ? gp[1] : 0.f, nv > 2 ? gp[2] : 0.f, nv > 3 ? gp[3] : 0.f);
+          zv[u] = make_float4(zp[0], nv > 1 ? zp[1] : 0.f, nv > 2 ? zp[2] : 0.f, nv > 3 ? zp[3] : 0.f);
         }
       }
     }
@@ -499,7 +437,7 @@ __global__ void __launch_bounds__(256) tc_bn_bwd_apply_v4_kernel(const TcBnBwdAr
         const Gy4 y = tc_bn_gy4(p, rr, c0, gv[u], zv[u], mean, rstd, beta);
         float v[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) v[k] = (c0 + k < p.C) ? rstd[k] * (y.g[k] - s1[k] - y.zh[k] * s2[k]) : 0.f;
+        for (int k = 0; k < 4; k++) v[k] = k < nv ? rstd[k] * (y.g[k] - s1[k] - y.zh[k] * s2[k]) : 0.f;
         tc_store_gz4(p, rr * p.ldgz + j0, gscale, v[0], v[1], v[2], v[3]);
       }
     }

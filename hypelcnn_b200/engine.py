@@ -343,7 +343,8 @@ class PatchEngine:
         FC / decoder tail, ~70 % of the buffer, is final once fc_0's backward has run) and the first parameter of the
         spatial levels (final once connector_0's backward has run)."""
         offs = [self.grad_split_offset]
-        level = [off for name, (kind, off, shape) in self.variables.items() if kind == 0 and len(shape) == 4 and shape[0] > 1]
+        # (a level is ONE layer of the engine: its split point is the level's first variable, the 1x1 kernel)
+        level = [off for name, (kind, off, shape) in self.variables.items() if kind == 0 and "/connector_0_conv" in name]
         if level and 0 < min(level) < offs[0]:
             offs.append(min(level))
         return [o for o in offs if o > 0]
