@@ -106,6 +106,8 @@ _PROTOS = {
     "hyp_gan_discriminator_backward": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P]),
     "hyp_gan_loss_grad": (_I, [_I, _P, _P, _F, _F, _L, _P, _I, _P, _P]),
     "hyp_gan_l2_regularizer": (_I, [_P, _P, _L, _F, _P, _P]),
+    "hyp_gan_cycle_generator_step": (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "hyp_gan_cycle_discriminator_step": (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _F, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P]),
     "hyp_gan_generator_backward_enc": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P]),
     "hyp_gan_feature_discriminator_weight_count": (_L, [_I, _I, _I]),
     "hyp_gan_feature_discriminator_forward": (_I, [_P, _L, _I, _I, _I, _P, _P, _P, _P]),

@@ -383,6 +383,17 @@ __global__ void __launch_bounds__(256) tc_bn_bwd_reduce_v4_kernel(const TcBnBwdA
 
 // gz = rstd * (g_y - mean(g_y) - zhat * mean(g_y * zhat)) -> (value, lo) planes.  Level layers (fpad > 0,
 // f % 4 == 0) write slot-ordered columns: gz column j = slot * fpad + n holds channel (R-1-slot) * f + n.
+// row[c0 .. c0 + 3] for any c0 (the row itself is 16-byte aligned)
+__device__ __forceinline__ float4 tc_load4_shifted(const float* __restrict__ row, int c0) {
+  const int base = c0 & ~3, sh = c0 & 3;
+  const float4 a = *reinterpret_cast<const float4*>(row + base);
+  if (sh == 0) return a;
+  const float4 b = *reinterpret_cast<const float4*>(row + base + 4);
+  if (sh == 1) return make_float4(a.y, a.z, a.w, b.x);
+  if (sh == 2) return make_float4(a.z, a.w, b.x, b.y);
+  return make_float4(a.w, b.x, b.y, b.z);
+}
+
 template <int TX>
 __global__ void __launch_bounds__(256) tc_bn_bwd_apply_v4_kernel(const TcBnBwdArgs p, int rows_per_block) {
   constexpr int TY = 256 / TX;
@@ -411,8 +422,7 @@ __global__ void __launch_bounds__(256) tc_bn_bwd_apply_v4_kernel(const TcBnBwdAr
   tc_load_ch4(p.beta, c0, p.C, beta);
   tc_load_ch4(p.s1, c0, p.C, s1);
   tc_load_ch4(p.s2, c0, p.C, s2);
-  // float4 loads need 4 valid, 16-byte aligned source values (level slots with f % 4 == 0 keep the alignment)
-  const bool vec = nv == 4 && (c0 & 3) == 0;
+  const bool vec = (c0 & 3) == 0;  // level slots with f % 4 == 0 keep the 16-byte alignment of the source row
   for (int64_t r = r0 + ty; r < r1; r += 4 * TY) {
     float4 gv[4], zv[4];
 #pragma unroll
@@ -423,10 +433,11 @@ __global__ void __launch_bounds__(256) tc_bn_bwd_apply_v4_kernel(const TcBnBwdAr
           gv[u] = *reinterpret_cast<const float4*>(p.gout + rr * p.ldg + c0);
           zv[u] = *reinterpret_cast<const float4*>(p.z + rr * p.ldz + c0);
         } else {
-          const float* gp = p.gout + rr * p.ldg + c0;
-          const float* zp = p.z + rr * p.ldz + c0;
-          gv[u] = make_float4(gp[0], nv > 1 ? gp[1] : 0.f, nv > 2 ? gp[2] : 0.f, nv > 3 ? gp[3] : 0.f);
-          zv[u] = make_float4(zp[0], nv > 1 ? zp[1] : 0.f, nv > 2 ? zp[2] : 0.f, nv > 3 ? zp[3] : 0.f);
+          // source channels at an arbitrary 4-byte phase (level kernels with f % 4 != 0): two aligned 16-byte loads
+          // and a shift instead of four 4-byte loads per tensor.  The second load may run a few floats past the row
+          // (into the next row / the padding behind the tensor inside the workspace); those values are never used.
+          gv[u] = tc_load4_shifted(p.gout + rr * p.ldg, c0);
+          zv[u] = tc_load4_shifted(p.z + rr * p.ldz, c0);
         }
       }
     }

@@ -89,47 +89,33 @@ class TensorPool:
         return t
 
 
-class GraphedCall:
-    """A launch-bound chain of small kernels captured ONCE per input shape into a CUDA graph and replayed: one graph
-    launch instead of a few dozen kernel launches per call (a CycleGAN iteration at the reference's batch of 32 is
-    ~40 launches of a few microseconds each).  ``fn(*tensors)`` must be a pure function of its tensor arguments and of
-    device state that lives at fixed addresses (weights, gradient buffers), must not synchronise, and must be
-    idempotent (it is run twice before the capture); its return value — tensors at fixed addresses — is handed back
-    on every call and overwritten by the next one."""
+class DeviceTensorPool:
+    """tfgan.features.tensor_pool for the fused discriminator step: the stored tensors live in ONE device buffer
+    [pool_size, rows, bands]; the host only draws what TensorPool draws (same generator, same order) and hands the
+    kernel a (mode, slot) pair — 0: no pool, 1: store the fresh fakes into ``slot`` and use them, 2: use ``slot`` and
+    replace it."""
 
-    def __init__(self, fn):
-        self.fn, self.cache = fn, {}
+    def __init__(self, pool_size=50, pooling_probability=0.5, seed=1234):
+        self.size, self.p, self.filled, self.buffer = pool_size, pooling_probability, 0, None
+        self.rng = numpy.random.default_rng(seed)
 
-    def __call__(self, *args):
-        key = tuple((tuple(a.shape), a.dtype, a.device) for a in args)
-        entry = self.cache.get(key)
-        if entry is None:
-            static_in = [a.clone() for a in args]
-            side = torch.cuda.Stream(device=args[0].device)
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):                       # lazy initialisation (function attributes) and
-                for _ in range(2):                              # allocator warm-up happen outside the capture
-                    self.fn(*static_in)
-            torch.cuda.current_stream().wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                static_out = self.fn(*static_in)
-            entry = self.cache[key] = (graph, static_in, static_out)
-        graph, static_in, static_out = entry
-        for held, given in zip(static_in, args):
-            held.copy_(given)
-        graph.replay()
-        return static_out
+    def draw(self, rows, bands, device):
+        if self.size == 0:
+            return None, 0, 0
+        if self.buffer is None or self.buffer.shape[1:] != (rows, bands):     # a new batch shape starts a new pool
+            self.buffer = torch.empty((self.size, rows, bands), dtype=torch.float32, device=device)
+            self.filled = 0
+        if self.filled < self.size:
+            self.filled += 1
+            return self.buffer, 1, self.filled - 1
+        if self.rng.random() < self.p:
+            return self.buffer, 2, int(self.rng.integers(0, self.size))
+        return self.buffer, 0, 0
 
 
-# graph replay pays where the kernels are launch-bound; at large batches the eager chain (whose kernels the host queues
-# far ahead of the device) measured faster (batch 16 384: 2.8 ms eager, 3.9 ms replayed)
-GRAPH_MAX_ROWS = 2048
-
-
-def graphs_enabled():
+def fused_steps_enabled():
     import os
-    return os.environ.get("HYP_GAN_GRAPHS", "1") != "0"
+    return os.environ.get("HYP_GAN_FUSED", "1") != "0"
 
 
 class GanKernels:
@@ -215,12 +201,12 @@ class CycleGANTrainer(GanKernels):
         self.loss_acc = torch.zeros(4, dtype=torch.float64, device=self.device)
         self.allreduce = None  # set to a parallel.GradientAllReduce for data-parallel training
         self.last = {}
-        # the train ops replay CUDA graphs of the gradient computations (the Adam step and the all-reduce stay outside:
-        # learning rate and step count change every iteration)
-        self.use_graphs = graphs_enabled()
-        self._graph_gen = GraphedCall(self.generator_gradients)
-        self._graph_fakes = GraphedCall(self._discriminator_fakes)
-        self._graph_dis = GraphedCall(self._discriminator_gradients_of)
+        # the train ops compute all gradients of a step in ONE kernel each (hyp_gan_cycle_generator_step /
+        # hyp_gan_cycle_discriminator_step); the per-op chain below (generator_gradients / discriminator_gradients) is
+        # what they are tested against and what other band counts fall back to
+        self.use_fused = fused_steps_enabled() and self.C % 8 == 0 and 8 <= self.C <= 64
+        self.dev_pool_y, self.dev_pool_x = DeviceTensorPool(pool_size, seed=seed), DeviceTensorPool(pool_size, seed=seed + 1)
+        self._outs = None
 
     # ---- views
     def G(self):
@@ -269,9 +255,40 @@ class CycleGANTrainer(GanKernels):
         loss[0] = loss[1] + loss[2] + loss[3]
         return loss
 
+    def generator_gradients_fused(self, images_x, images_y):
+        """generator_gradients in one launch (hyp_gan_cycle_generator_step)."""
+        x, y = self._rows(images_x), self._rows(images_y)
+        if self._outs is None or self._outs[0].shape != x.shape:
+            self._outs = [torch.empty_like(x) for _ in range(4)]
+        gx, fy, rx, ry = self._outs
+        self.gen_grads.zero_()
+        self.loss_acc.zero_()
+        ng = self.ng
+        N.check(N.lib().hyp_gan_cycle_generator_step(
+            _p(x), _p(y), x.shape[0], self.C, _p(self.G()), _p(self.F()), _p(self.DY()), _p(self.DX()), self.w_cyc,
+            self.w_id, _p(self.gen_grads[:ng]), _p(self.gen_grads[ng:]), ctypes.c_void_p(self.loss_acc.data_ptr()),
+            _p(gx), _p(fy), _p(rx), _p(ry), _st()))
+        self.last = {"generated_y": gx, "generated_x": fy, "reconstructed_x": rx, "reconstructed_y": ry}
+        return self.loss_acc.clone()
+
+    def discriminator_gradients_fused(self, images_x, images_y, use_pool=True):
+        """discriminator_gradients in one launch (hyp_gan_cycle_discriminator_step): fakes, tensor pool, both
+        discriminators on real and fake, regulariser."""
+        x, y = self._rows(images_x), self._rows(images_y)
+        nd = self.nd
+        self.dis_grads.zero_()
+        self.loss_acc.zero_()
+        pool_y = self.dev_pool_y.draw(x.shape[0], self.C, x.device) if use_pool else (None, 0, 0)
+        pool_x = self.dev_pool_x.draw(x.shape[0], self.C, x.device) if use_pool else (None, 0, 0)
+        N.check(N.lib().hyp_gan_cycle_discriminator_step(
+            _p(x), _p(y), x.shape[0], self.C, _p(self.G()), _p(self.F()), _p(self.DY()), _p(self.DX()), self.reg,
+            _p(self.dis_grads[:nd]), _p(self.dis_grads[nd:]), ctypes.c_void_p(self.loss_acc.data_ptr()),
+            _p(pool_y[0]), pool_y[1], pool_y[2], _p(pool_x[0]), pool_x[1], pool_x[2], _st()))
+        return self.loss_acc.clone()
+
     def generator_train_op(self, images_x, images_y, lr):
-        if self.use_graphs and images_x.shape[0] <= GRAPH_MAX_ROWS:
-            loss = self._graph_gen(self._rows(images_x), self._rows(images_y))
+        if self.use_fused:
+            loss = self.generator_gradients_fused(images_x, images_y)
         else:
             loss = self.generator_gradients(images_x, images_y)
         scale = self.allreduce(self.gen_grads) if self.allreduce is not None else 1.0
@@ -280,17 +297,17 @@ class CycleGANTrainer(GanKernels):
         return loss
 
     # ---- discriminator step
-    def _discriminator_fakes(self, x, y):
-        """G(x), F(y): what the discriminators are shown as fakes (before the tensor pool)."""
-        gx = self._gen_fwd(x, self.G())[:, 7, :].contiguous()
-        fy = self._gen_fwd(y, self.F())[:, 7, :].contiguous()
-        return gx, fy
-
-    def _discriminator_gradients_of(self, x, y, gx, fy):
+    def discriminator_gradients(self, images_x, images_y, use_pool=True):
+        """Fills dis_grads with dL_D / d[D_Y | D_X]; returns the device loss tensor [total, gan, regularisation, -]."""
+        x, y = self._rows(images_x), self._rows(images_y)
         nd = self.nd
         gDY, gDX = self.dis_grads[:nd], self.dis_grads[nd:]
         self.dis_grads.zero_()
         self.loss_acc.zero_()
+        gx = self._gen_fwd(x, self.G())[:, 7, :].contiguous()
+        fy = self._gen_fwd(y, self.F())[:, 7, :].contiguous()
+        if use_pool:
+            gx, fy = self.pool_y(gx), self.pool_x(fy)
         for real, fake, w, gw in ((y, gx, self.DY(), gDY), (x, fy, self.DX(), gDX)):
             for data, target in ((real, 1.0), (fake, 0.0)):            # least_squares_discriminator_loss
                 h, d = self._dis_fwd(data, w)
@@ -305,19 +322,8 @@ class CycleGANTrainer(GanKernels):
         loss[0] = loss[1] + loss[2]
         return loss
 
-    def discriminator_gradients(self, images_x, images_y, use_pool=True, graphs=False):
-        """Fills dis_grads with dL_D / d[D_Y | D_X]; returns the device loss tensor [total, gan, regularisation, -].
-        The fakes pass through tfgan's tensor pool (host-side draws) between the two halves, which is why the graph
-        replay (``graphs``) comes as two graphs around it."""
-        x, y = self._rows(images_x), self._rows(images_y)
-        gx, fy = self._graph_fakes(x, y) if graphs else self._discriminator_fakes(x, y)
-        if use_pool:
-            gx, fy = self.pool_y(gx), self.pool_x(fy)
-        return self._graph_dis(x, y, gx, fy) if graphs else self._discriminator_gradients_of(x, y, gx, fy)
-
     def discriminator_train_op(self, images_x, images_y, lr):
-        loss = self.discriminator_gradients(images_x, images_y, graphs=True) \
-            if self.use_graphs and images_x.shape[0] <= GRAPH_MAX_ROWS else \
+        loss = self.discriminator_gradients_fused(images_x, images_y) if self.use_fused else \
             self.discriminator_gradients(images_x, images_y)
         scale = self.allreduce(self.dis_grads) if self.allreduce is not None else 1.0
         self.dis_steps += 1

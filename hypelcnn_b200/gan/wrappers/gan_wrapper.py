@@ -20,7 +20,7 @@ class GANTrainer(CycleGANTrainer):
 
     def __init__(self, bands, swap_inputs, discriminator_reg_scale=1e-5, device=None, seed=1234, pool_size=50):
         super().__init__(bands, 0.0, 0.0, False, discriminator_reg_scale, device, seed, pool_size)
-        self.use_graphs = False      # the one-directional GAN's short launch chains run eagerly
+        self.use_fused = False       # the fused step kernels are CycleGAN's; the one-directional GAN chains per-op kernels
         self.swap = bool(swap_inputs)
 
     def _pick(self, images_x, images_y):

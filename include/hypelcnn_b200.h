@@ -207,6 +207,34 @@ int hyp_gan_loss_grad(int mode, const float* a, const float* b, float target, fl
 /* slim l2_regularizer(scale) on a weight range: loss_acc += scale * sum(w^2)/2, grads += scale * w (grads nullable) */
 int hyp_gan_l2_regularizer(const float* weights, float* grads, int64_t n, float scale, double* loss_acc, void* stream);
 
+/* ---- fused CycleGAN train ops (gan/wrappers/cycle_gan_wrapper.py:189-333 over gan/shadow_data_models.py:43-123): ONE kernel per
+ * train op instead of a chain of per-op launches (a train iteration at the reference's batch of 32 is launch latency).
+ * Flat weight buffers as in the per-op entry points above; bands a multiple of 8 in 8..64.
+ *
+ * generator step: grad_g / grad_f += d L_G / d [G (x -> y) | F (y -> x)] with
+ *   L_G = 0.5 mean (D_Y(G x) - 1)^2 + 0.5 mean (D_X(F y) - 1)^2                       -> loss_acc[1]
+ *       + cycle_weight    * (mean |F(G x) - x| + mean |G(F y) - y|)                   -> loss_acc[2]
+ *       + 2 identity_weight * (mean |G(x) - x| + mean |F(y) - y|)                     -> loss_acc[3]
+ * (tfgan counts the cycle term once per partial model with weight / 2 each; the "identity" terms apply each generator
+ * to its own domain's input, as the reference does).  The discriminators are frozen.  gen_y = G(x), gen_x = F(y),
+ * rec_x = F(G x), rec_y = G(F y): nullable [rows][bands] outputs.  loss_acc: device double[4], += ; [0] gets the
+ * total of both entry points' terms. */
+int hyp_gan_cycle_generator_step(const float* x, const float* y, int64_t rows, int bands, const float* w_g, const float* w_f,
+                                 const float* w_dy, const float* w_dx, float cycle_weight, float identity_weight,
+                                 float* grad_g, float* grad_f, double* loss_acc, float* gen_y, float* gen_x, float* rec_x,
+                                 float* rec_y, void* stream);
+/* discriminator step: grad_dy / grad_dx += d L_D / d [D_Y | D_X] with
+ *   L_D = sum over both domains of 0.5 mean (D(real) - 1)^2 + 0.5 mean D(fake)^2      -> loss_acc[1]
+ *       + reg_scale * sum w^2 / 2 over the two hidden layers' weight matrices          -> loss_acc[2]
+ * fake = G(x) / F(y) computed here with the current generators, passed through tfgan.features.tensor_pool kept on the
+ * device: pool_y / pool_x [slots][rows][bands]; pool_mode 0 = no pool, 1 = store the fresh fakes into pool_slot and use
+ * them (pool still filling), 2 = use what pool_slot holds and replace it by the fresh fakes.  The caller draws mode and
+ * slot (host RNG, as the reference's pool does). */
+int hyp_gan_cycle_discriminator_step(const float* x, const float* y, int64_t rows, int bands, const float* w_g,
+                                     const float* w_f, const float* w_dy, const float* w_dx, float reg_scale, float* grad_dy,
+                                     float* grad_dx, double* loss_acc, float* pool_y, int pool_mode_y, int pool_slot_y,
+                                     float* pool_x, int pool_mode_x, int pool_slot_x, void* stream);
+
 /* ---- CUT / DCLGAN / DCL-CycleGAN (gan/wrappers/cut_wrapper.py:256-420, dcl_gan_wrapper.py, dcl_cycle_gan_wrapper.py).
  * generator backward that also takes the gradient of the ENCODER output net4 (generator_fn(create_only_encoder=True),
  * gan/shadow_data_models.py:43-75): gout (dL/dnet7) nullable -> only net1..net4 are differentiated; gout_enc nullable */

@@ -157,24 +157,50 @@ def test_single_direction_gan_gradients_and_registry(swap):
         get_wrapper("no_such_gan", flags)
 
 
-def test_graph_replay_equals_eager_train_ops():
-    """The train ops replay CUDA graphs of the gradient computations (one graph launch instead of ~40 kernel launches per
-    iteration): same losses, same gradients and the same weights after a few iterations as the eager chain."""
+@pytest.mark.parametrize("bands,n,identity", [(64, 32, True), (64, 301, True), (32, 37, False), (16, 5, True)])
+def test_fused_step_kernels_equal_the_per_op_chain(bands, n, identity):
+    """hyp_gan_cycle_generator_step / hyp_gan_cycle_discriminator_step (one kernel per train op) against the chain of
+    per-op kernels that the oracle tests pin: same losses, same gradients, same generated spectra."""
+    x, y = _data(n, bands, seed=4)
+    t = _trainer(bands, pool_size=0, use_identity_loss=identity)
+    assert t.use_fused
+    want_loss = t.generator_gradients(x, y).clone()
+    want_grads, want_last = t.gen_grads.clone(), {k: v.clone() for k, v in t.last.items()}
+    got_loss = t.generator_gradients_fused(x, y)
+    assert torch.allclose(got_loss, want_loss, rtol=2e-5, atol=1e-7), (got_loss, want_loss)
+    assert _rel(t.gen_grads, want_grads.double().cpu()) < 2e-5
+    for key, value in want_last.items():
+        assert torch.allclose(t.last[key], value, rtol=1e-6, atol=1e-7), key
+    want_loss = t.discriminator_gradients(x, y, use_pool=False).clone()
+    want_grads = t.dis_grads.clone()
+    got_loss = t.discriminator_gradients_fused(x, y, use_pool=False)
+    assert torch.allclose(got_loss, want_loss, rtol=2e-5, atol=1e-7), (got_loss, want_loss)
+    assert _rel(t.dis_grads, want_grads.double().cpu()) < 2e-5
+
+
+def test_device_tensor_pool_follows_the_host_pool():
+    """The fused discriminator step keeps tfgan's tensor pool on the device; the host draws (mode, slot) exactly like
+    TensorPool draws: over a run with changing inputs both paths see the same fakes, i.e. produce the same gradients."""
+    eager, fused = _trainer(pool_size=3), _trainer(pool_size=3)
+    assert fused.use_fused
+    used_pool = False
+    for step in range(12):
+        x, y = _data(32, 64, seed=10 + step)
+        want = eager.discriminator_gradients(x, y).clone()
+        got = fused.discriminator_gradients_fused(x, y)
+        assert torch.allclose(got, want, rtol=2e-5, atol=1e-7), step
+        assert _rel(fused.dis_grads, eager.dis_grads.double().cpu()) < 2e-5, step
+        used_pool = used_pool or fused.dev_pool_y.filled == 3
+    assert used_pool
+
+
+def test_fused_train_ops_train_like_the_chain():
     x, y = _data(32, 64, seed=4)
-    eager, graphed = _trainer(pool_size=0), _trainer(pool_size=0)
-    eager.use_graphs, graphed.use_graphs = False, True
+    chain, fused = _trainer(pool_size=0), _trainer(pool_size=0)
+    chain.use_fused = False
     for step in range(1, 5):
-        x2, y2 = x * (1.0 + 0.01 * step), y * (1.0 - 0.01 * step)           # fresh inputs into the graphs' static buffers
-        le, lg = eager.generator_train_op(x2, y2, 2e-4), graphed.generator_train_op(x2, y2, 2e-4)
-        assert torch.allclose(le, lg.to(le.dtype), rtol=1e-5, atol=1e-7)
-        assert _rel(graphed.gen_grads, eager.gen_grads.double().cpu()) < 1e-5   # block-level atomics: order differs
-        le, lg = eager.discriminator_train_op(x2, y2, 1e-4), graphed.discriminator_train_op(x2, y2, 1e-4)
-        assert torch.allclose(le, lg.to(le.dtype), rtol=1e-5, atol=1e-7)
-        assert _rel(graphed.dis_grads, eager.dis_grads.double().cpu()) < 1e-5
-    assert _rel(graphed.gen_params, eager.gen_params.double().cpu()) < 1e-4
-    assert _rel(graphed.dis_params, eager.dis_params.double().cpu()) < 1e-4
-    assert len(graphed._graph_gen.cache) == 1 and len(graphed._graph_dis.cache) == 1
-    # with the tensor pool between the two discriminator graphs
-    pooled = _trainer(pool_size=2)
-    for step in range(6):
-        assert torch.isfinite(pooled.discriminator_train_op(x, y, 1e-4)).all()
+        x2, y2 = x * (1.0 + 0.01 * step), y * (1.0 - 0.01 * step)
+        assert torch.allclose(chain.generator_train_op(x2, y2, 2e-4), fused.generator_train_op(x2, y2, 2e-4), rtol=1e-4, atol=1e-7)
+        assert torch.allclose(chain.discriminator_train_op(x2, y2, 1e-4), fused.discriminator_train_op(x2, y2, 1e-4), rtol=1e-4, atol=1e-7)
+    assert _rel(fused.gen_params, chain.gen_params.double().cpu()) < 1e-4
+    assert _rel(fused.dis_params, chain.dis_params.double().cpu()) < 1e-4
