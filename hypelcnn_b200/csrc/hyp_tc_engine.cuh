@@ -114,12 +114,6 @@ static inline EwGrid ew_grid2(int cols, int64_t rows) {
   g.rblocks = (int)cdiv(rows, g.rpb);
   return g;
 }
-#define TC_EW_DISPATCH(G, KERNEL, ...)                                                             \
-  do {                                                                                             \
-    if ((G).TX == 32) KERNEL<32><<<dim3((G).gx, (G).rblocks), 256, 0, st>>>(__VA_ARGS__);          \
-    else if ((G).TX == 16) KERNEL<16><<<dim3((G).gx, (G).rblocks), 256, 0, st>>>(__VA_ARGS__);     \
-    else KERNEL<8><<<dim3((G).gx, (G).rblocks), 256, 0, st>>>(__VA_ARGS__);                        \
-  } while (0)
 
 // ---- static layout: workspace offsets, packed-weight offsets, pack jobs ------------------------
 static int tc_layout(hyp_model& m) {
@@ -1065,15 +1059,35 @@ static int tc_backward(hyp_model& m, const uint8_t* labels, int64_t B, float* lo
     p.gcols = T.kind == 1 ? T.Gp : L.Cout;
     p.fpad = T.kind == 1 ? T.fpad : 0; p.f = T.f; p.R = T.R; p.nt = T.nt; p.ft = T.ft;
     const EwGrid gr = ew_grid2(L.Cout, rows);
-    TC_PROF("tc_bn_bwd_reduce_kernel", 8.0 * rows * L.Cout, TC_EW_DISPATCH(gr, tc_bn_bwd_reduce_v4_kernel, p, gr.rpb));
+    const bool drop = p.keep < 1.f;
+#define TC_REDUCE_LAUNCH(TXV)                                                                                         \
+  do {                                                                                                                \
+    if (drop) tc_bn_bwd_reduce_v4_kernel<TXV, true><<<dim3(gr.gx, gr.rblocks), 256, 0, st>>>(p, gr.rpb);              \
+    else tc_bn_bwd_reduce_v4_kernel<TXV, false><<<dim3(gr.gx, gr.rblocks), 256, 0, st>>>(p, gr.rpb);                  \
+  } while (0)
+    g_prof.begin(st, "tc_bn_bwd_reduce_kernel", 0.0, 8.0 * rows * L.Cout);
+    if (gr.TX == 32) TC_REDUCE_LAUNCH(32); else if (gr.TX == 16) TC_REDUCE_LAUNCH(16); else TC_REDUCE_LAUNCH(8);
+    g_prof.end(st);
+    HYP_LAUNCHED();
+#undef TC_REDUCE_LAUNCH
     tc_bn_bwd_finalize8_kernel<<<(unsigned)cdiv(L.Cout, 8), 8 * FIN_LANES, 0, st>>>(bpart, gr.rblocks, L.Cout, (double)rows, s1, s2,
                                                                          m.grads + L.beta_off, L.bias_mode ? 1 : 0, p.rstd,
                                                                          S.op == OP_F16X3 ? reinterpret_cast<unsigned int*>(gzs) : nullptr);
     HYP_LAUNCHED();
     {
       const EwGrid ga = ew_grid2(p.gcols, rows);
-      TC_PROF("tc_bn_bwd_apply_kernel", 4.0 * rows * (2.0 * L.Cout + 2.0 * p.gcols),
-              TC_EW_DISPATCH(ga, tc_bn_bwd_apply_v4_kernel, p, ga.rpb));
+      const bool shift = p.fpad != 0 && (p.f % 4 != 0 || p.ft % 4 != 0);
+#define TC_APPLY_LAUNCH(TXV)                                                                                          \
+  do {                                                                                                                \
+    if (drop) tc_bn_bwd_apply_v4_kernel<TXV, false, true><<<dim3(ga.gx, ga.rblocks), 256, 0, st>>>(p, ga.rpb);        \
+    else if (shift) tc_bn_bwd_apply_v4_kernel<TXV, true, false><<<dim3(ga.gx, ga.rblocks), 256, 0, st>>>(p, ga.rpb);  \
+    else tc_bn_bwd_apply_v4_kernel<TXV, false, false><<<dim3(ga.gx, ga.rblocks), 256, 0, st>>>(p, ga.rpb);            \
+  } while (0)
+      g_prof.begin(st, "tc_bn_bwd_apply_kernel", 0.0, 4.0 * rows * (2.0 * L.Cout + 2.0 * p.gcols));
+      if (ga.TX == 32) TC_APPLY_LAUNCH(32); else if (ga.TX == 16) TC_APPLY_LAUNCH(16); else TC_APPLY_LAUNCH(8);
+      g_prof.end(st);
+      HYP_LAUNCHED();
+#undef TC_APPLY_LAUNCH
     }
     for (const Resid& r : L.res) {
       const Tensor& src = m.tensors[r.src];

@@ -290,6 +290,9 @@ __device__ __forceinline__ void tc_publish_gz_scale(const TcBnBwdArgs& p, float 
 // is no per-element index division.  Rows are 16-byte aligned (ld % 4 == 0); the channel tail
 // (C % 4 != 0) is masked per element.
 struct Gy4 { float g[4], zh[4]; };
+// DROP = false: the layer has no dropout (every conv layer): the Philox recomputation of the mask is compiled out,
+// which is most of the kernels' registers
+template <bool DROP>
 __device__ __forceinline__ Gy4 tc_bn_gy4(const TcBnBwdArgs& p, int64_t m, int c0, const float4 gv, const float4 zv,
                                          const float (&mean)[4], const float (&rstd)[4], const float (&beta)[4]) {
   Gy4 r;
@@ -299,7 +302,7 @@ __device__ __forceinline__ Gy4 tc_bn_gy4(const TcBnBwdArgs& p, int64_t m, int c0
     const float zhat = (z_in[k] - mean[k]) * rstd[k];
     const float y = zhat + beta[k];
     float g = g_in[k];
-    if (p.keep < 1.f) g = (philox_uniform(p.seed, p.stream_id, (uint64_t)(m * p.C + c0 + k)) < p.keep) ? g / p.keep : 0.f;
+    if (DROP && p.keep < 1.f) g = (philox_uniform(p.seed, p.stream_id, (uint64_t)(m * p.C + c0 + k)) < p.keep) ? g / p.keep : 0.f;
     if (p.act == ACT_LRELU) {
       g = (y > 0.f) ? g : g * p.alpha;
     } else if (p.act == ACT_SIGMOID) {
@@ -316,7 +319,7 @@ __device__ __forceinline__ void tc_load_ch4(const float* __restrict__ src, int c
   for (int k = 0; k < 4; k++) v[k] = (c0 + k < C) ? src[c0 + k] : 0.f;
 }
 
-template <int TX>
+template <int TX, bool DROP>
 __global__ void __launch_bounds__(256) tc_bn_bwd_reduce_v4_kernel(const TcBnBwdArgs p, int rows_per_block) {
   constexpr int TY = 256 / TX;
   __shared__ float sh[4][TY][TX * 4 + 4];
@@ -345,7 +348,7 @@ __global__ void __launch_bounds__(256) tc_bn_bwd_reduce_v4_kernel(const TcBnBwdA
       for (int u = 0; u < 4; u++) {
         const int64_t rr = r + u * TY;
         if (rr < r1) {
-          const Gy4 y = tc_bn_gy4(p, rr, c0, gv[u], zv[u], mean, rstd, beta);
+          const Gy4 y = tc_bn_gy4<DROP>(p, rr, c0, gv[u], zv[u], mean, rstd, beta);
 #pragma unroll
           for (int k = 0; k < 4; k++) {
             a1[k] += y.g[k];
@@ -394,8 +397,9 @@ __device__ __forceinline__ float4 tc_load4_shifted(const float* __restrict__ row
   return make_float4(a.w, b.x, b.y, b.z);
 }
 
-template <int TX>
-__global__ void __launch_bounds__(256) tc_bn_bwd_apply_v4_kernel(const TcBnBwdArgs p, int rows_per_block) {
+// SHIFT: the source channels of a thread's 4 columns may start at any 4-byte phase (level kernels with f % 4 != 0)
+template <int TX, bool SHIFT, bool DROP>
+__global__ void __launch_bounds__(256, 2) tc_bn_bwd_apply_v4_kernel(const TcBnBwdArgs p, int rows_per_block) {
   constexpr int TY = 256 / TX;
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const int j0 = (blockIdx.x * TX + tx) * 4;  // first gz column of this thread
@@ -422,7 +426,7 @@ __global__ void __launch_bounds__(256) tc_bn_bwd_apply_v4_kernel(const TcBnBwdAr
   tc_load_ch4(p.beta, c0, p.C, beta);
   tc_load_ch4(p.s1, c0, p.C, s1);
   tc_load_ch4(p.s2, c0, p.C, s2);
-  const bool vec = (c0 & 3) == 0;  // level slots with f % 4 == 0 keep the 16-byte alignment of the source row
+  const bool vec = !SHIFT || (c0 & 3) == 0;  // level slots with f % 4 == 0 keep the 16-byte alignment of the source row
   for (int64_t r = r0 + ty; r < r1; r += 4 * TY) {
     float4 gv[4], zv[4];
 #pragma unroll
@@ -445,7 +449,7 @@ __global__ void __launch_bounds__(256) tc_bn_bwd_apply_v4_kernel(const TcBnBwdAr
     for (int u = 0; u < 4; u++) {
       const int64_t rr = r + u * TY;
       if (rr < r1) {
-        const Gy4 y = tc_bn_gy4(p, rr, c0, gv[u], zv[u], mean, rstd, beta);
+        const Gy4 y = tc_bn_gy4<DROP>(p, rr, c0, gv[u], zv[u], mean, rstd, beta);
         float v[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) v[k] = k < nv ? rstd[k] * (y.g[k] - s1[k] - y.zh[k] * s2[k]) : 0.f;
