@@ -76,7 +76,6 @@ if rank == 0:
     print(json.dumps({"metric": "whole-scene classification, pixels/s (HYPELCNN eval, GRSS2013 shape)", "pixels": pixels,
                       "n_gpus": world, "batch": args.batch, "device_ms": device_ms, "wall_ms": wall_ms,
                       "pixels_per_s": pixels / device_ms * 1e3, "precision": model.precision,
-                      "eval_epilogue": "two-pass" if os.environ.get("HYP_EVAL_UNFUSED") == "1" else "fused",
                       "class_map_digest": digest,
                       "useful_TFLOP_per_s": pixels * 151.28e6 / device_ms / 1e9}))   # eval graph: 157.16 - 5.88 MFLOP of decoder
 if world > 1:
