@@ -1431,7 +1431,10 @@ int hyp_model_debug_tensor(hyp_model* m, const char* name, int what, float** ptr
     float* dst = reinterpret_cast<float*>(m->ws + S.dbg_off);
     const int64_t total = m->last_B * T.PP * T.C;
     HYP_CUDA(cudaDeviceSynchronize());
-    tc_extract_kernel<<<tc_grid(total), 256>>>(src, T.Cp, (int)m->last_B, T.PP, T.C, dst);
+    if (src) tc_extract_kernel<<<tc_grid(total), 256>>>(src, T.Cp, (int)m->last_B, T.PP, T.C, dst);
+    else  // an activation without a value plane: rebuilt from its operand planes
+      tc_extract_planes_kernel<<<tc_grid(total), 256>>>(reinterpret_cast<const uint16_t*>(tc_plane1(*m, t)), T.plane_elems, T.Cp,
+                                                        (int)m->last_B, T.PP, T.C, dst);
     HYP_LAUNCHED();
     HYP_CUDA(cudaDeviceSynchronize());
     *ptr = dst;

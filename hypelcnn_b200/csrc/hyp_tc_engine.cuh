@@ -21,7 +21,12 @@ namespace tc {
 
 struct TcTensor {
   int PP, C, Cp;
-  size_t a_off = 0;          // plane 0 (bytes in workspace); plane 1 follows at +plane_elems floats
+  // fp32 value plane (bytes in workspace) and, behind it, the operand region.  3xF16 models drop the value plane of
+  // the HYPELCNN-internal tensors (has_value = false): residual readers rebuild the value from the fp16 (hi, lo)
+  // planes — 22 significand bits, the precision every GEMM of the mode sees anyway — which saves 4 of the 8 bytes
+  // tc_bn_apply writes per element.
+  size_t a_off = 0, o_off = 0;
+  bool has_value = true;
   size_t plane_elems = 0;
   size_t g_off = 0;
 };
@@ -89,10 +94,10 @@ inline int r4(int v) { return (int)align_up((size_t)v, 4); }
 namespace hyp {
 namespace tc {
 
-static float* tc_plane0(const hyp_model& m, int t) {
-  return reinterpret_cast<float*>(m.ws + m.tc->tt[t].a_off);
+static float* tc_plane0(const hyp_model& m, int t) {  // fp32 value plane, nullptr where it is not kept
+  return m.tc->tt[t].has_value ? reinterpret_cast<float*>(m.ws + m.tc->tt[t].a_off) : nullptr;
 }
-static float* tc_plane1(const hyp_model& m, int t) { return tc_plane0(m, t) + m.tc->tt[t].plane_elems; }
+static float* tc_plane1(const hyp_model& m, int t) { return reinterpret_cast<float*>(m.ws + m.tc->tt[t].o_off); }
 static float* tc_grad(const hyp_model& m, int t) { return reinterpret_cast<float*>(m.ws + m.tc->tt[t].g_off); }
 // first GEMM operand plane of an activation tensor: the value plane itself (3xTF32) or the 16-bit planes that live in
 // the second region
@@ -138,7 +143,12 @@ static int tc_layout(hyp_model& m) {
     T.C = m.tensors[t].C;
     T.Cp = S.rc(T.C);
     T.plane_elems = align_up(Bm * T.PP * T.Cp, 64);
-    T.a_off = take(2 * T.plane_elems * sizeof(float));
+    // value planes stay for: 3xTF32 (the plane IS an operand) and bf16 (8-bit planes cannot stand in for the value),
+    // DUALCNN / CONCNN (LRN and the two-input FC read them), the model inputs (MSE target), logits and reconstruction
+    T.has_value = S.op != OP_F16X3 || m.d.kind != HYP_MODEL_HYPELCNN || m.tensors[t].external || (int)t == m.logits_t ||
+                  (int)t == m.recon_t;
+    T.a_off = take((T.has_value ? 2 : 1) * T.plane_elems * sizeof(float));
+    T.o_off = T.a_off + (T.has_value ? T.plane_elems * sizeof(float) : 0);
     if (m.tensors[t].needs_grad) T.g_off = take(T.plane_elems * sizeof(float));
   }
   S.tl.resize(m.layers.size());
@@ -977,10 +987,14 @@ static int tc_forward(hyp_model& m, const float* x, int64_t B, bool training, bo
     p.keep = (L.dropout && training) ? keep_prob : 1.f;
     p.seed = seed; p.stream_id = L.drop_stream;
     if (L.res.size() > 0) {
-      p.res0 = tc_plane0(m, L.res[0].src); p.idx0 = L.res[0].idx; p.ld0 = S.tt[L.res[0].src].Cp;
+      const TcTensor& rs = S.tt[L.res[0].src];
+      p.res0 = tc_plane0(m, L.res[0].src); p.idx0 = L.res[0].idx; p.ld0 = rs.Cp; p.has0 = 1;
+      p.res0_op = reinterpret_cast<const uint16_t*>(tc_plane1(m, L.res[0].src)); p.res0_plane = rs.plane_elems;
     }
     if (L.res.size() > 1) {
-      p.res1 = tc_plane0(m, L.res[1].src); p.idx1 = L.res[1].idx; p.ld1 = S.tt[L.res[1].src].Cp;
+      const TcTensor& rs = S.tt[L.res[1].src];
+      p.res1 = tc_plane0(m, L.res[1].src); p.idx1 = L.res[1].idx; p.ld1 = rs.Cp; p.has1 = 1;
+      p.res1_op = reinterpret_cast<const uint16_t*>(tc_plane1(m, L.res[1].src)); p.res1_plane = rs.plane_elems;
     }
     const double bytes = 4.0 * rows * L.Cout * (3 + L.res.size());
     // (a 2-D row-lane form of this kernel measured 15 % slower: the flat float4 walk keeps more rows in flight)

@@ -61,6 +61,18 @@ __global__ void tc_fill_kernel(float* __restrict__ p, int n, float v) {
 }
 
 // position-major [PP][B][ld] -> dense [B][PP][C] (API outputs, tests)
+// the same from the fp16 (hi, lo) operand planes of a tensor that keeps no value plane
+__global__ void tc_extract_planes_kernel(const uint16_t* __restrict__ op, size_t plane, int ld, int B, int PP, int C,
+                                         float* __restrict__ dst) {
+  const int64_t total = (int64_t)B * PP * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t bp = i / C;
+    const int c = (int)(i - bp * C);
+    const int b = (int)(bp / PP), pos = (int)(bp - (int64_t)b * PP);
+    const int64_t at = ((int64_t)pos * B + b) * ld + c;
+    dst[i] = __half2float(__ushort_as_half(op[at])) + __half2float(__ushort_as_half(op[at + plane]));
+  }
+}
 __global__ void tc_extract_kernel(const float* __restrict__ src, int ld, int B, int PP, int C, float* __restrict__ dst) {
   const int64_t total = (int64_t)B * PP * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -142,12 +154,18 @@ struct TcApplyArgs {
   float alpha, keep;
   uint64_t seed;
   uint32_t stream_id;
-  const float* res0;  // residual source plane 0 [rows][ld0]; idx0 == NULL: identity
+  // residual sources [rows][ld]; idx == NULL: identity channel map.  res = the source's fp32 value plane, or NULL
+  // when it keeps none: the value is then rebuilt from its fp16 (hi, lo) operand planes res_op / res_plane
+  const float* res0;
   const int* idx0;
-  int ld0;
+  int ld0, has0;
+  const uint16_t* res0_op;
+  size_t res0_plane;
   const float* res1;
   const int* idx1;
-  int ld1;
+  int ld1, has1;
+  const uint16_t* res1_op;
+  size_t res1_plane;
 };
 
 // out = dropout(act(bn(z))) + res0[:, idx0] + res1[:, idx1]; VEC channels per thread
@@ -157,6 +175,35 @@ struct TcApplyItem {
   int c0;
   float v[VEC], r[VEC];
 };
+// hi + lo of the fp16 operand planes = the value to 22 significand bits
+__device__ __forceinline__ float tc_value_of_planes(const uint16_t* op, size_t plane, int64_t idx) {
+  return __half2float(__ushort_as_half(op[idx])) + __half2float(__ushort_as_half(op[idx + plane]));
+}
+template <int VEC>
+__device__ __forceinline__ void tc_bn_apply_residual(const float* res, const uint16_t* op, size_t plane, const int* idx, int ld,
+                                                     int C, TcApplyItem<VEC>& it) {
+  if (res) {
+    if (VEC == 4 && !idx) {
+      const float4 t = *reinterpret_cast<const float4*>(res + it.m * ld + it.c0);
+      it.r[0] += t.x; it.r[1 % VEC] += t.y; it.r[2 % VEC] += t.z; it.r[3 % VEC] += t.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < VEC; j++) it.r[j] += res[it.m * ld + (idx ? idx[min(it.c0 + j, C - 1)] : it.c0 + j)];
+    }
+  } else if (VEC == 4 && !idx) {
+    const uint2 h = *reinterpret_cast<const uint2*>(op + it.m * ld + it.c0);
+    const uint2 l = *reinterpret_cast<const uint2*>(op + plane + it.m * ld + it.c0);
+    const __half2 h0 = *reinterpret_cast<const __half2*>(&h.x), h1 = *reinterpret_cast<const __half2*>(&h.y);
+    const __half2 l0 = *reinterpret_cast<const __half2*>(&l.x), l1 = *reinterpret_cast<const __half2*>(&l.y);
+    it.r[0] += __low2float(h0) + __low2float(l0);
+    it.r[1 % VEC] += __high2float(h0) + __high2float(l0);
+    it.r[2 % VEC] += __low2float(h1) + __low2float(l1);
+    it.r[3 % VEC] += __high2float(h1) + __high2float(l1);
+  } else {
+#pragma unroll
+    for (int j = 0; j < VEC; j++) it.r[j] += tc_value_of_planes(op, plane, it.m * ld + (idx ? idx[min(it.c0 + j, C - 1)] : it.c0 + j));
+  }
+}
 // issue every global load of one item (z and the residual sources) ...
 template <int VEC>
 __device__ __forceinline__ void tc_bn_apply_load(const TcApplyArgs& p, int64_t i, int cq, TcApplyItem<VEC>& it) {
@@ -170,24 +217,8 @@ __device__ __forceinline__ void tc_bn_apply_load(const TcApplyArgs& p, int64_t i
   }
 #pragma unroll
   for (int j = 0; j < VEC; j++) it.r[j] = 0.f;
-  if (p.res0) {
-    if (VEC == 4 && !p.idx0) {
-      const float4 t = *reinterpret_cast<const float4*>(p.res0 + it.m * p.ld0 + it.c0);
-      it.r[0] += t.x; it.r[1 % VEC] += t.y; it.r[2 % VEC] += t.z; it.r[3 % VEC] += t.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < VEC; j++) it.r[j] += p.res0[it.m * p.ld0 + (p.idx0 ? p.idx0[min(it.c0 + j, p.C - 1)] : it.c0 + j)];
-    }
-  }
-  if (p.res1) {
-    if (VEC == 4 && !p.idx1) {
-      const float4 t = *reinterpret_cast<const float4*>(p.res1 + it.m * p.ld1 + it.c0);
-      it.r[0] += t.x; it.r[1 % VEC] += t.y; it.r[2 % VEC] += t.z; it.r[3 % VEC] += t.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < VEC; j++) it.r[j] += p.res1[it.m * p.ld1 + (p.idx1 ? p.idx1[min(it.c0 + j, p.C - 1)] : it.c0 + j)];
-    }
-  }
+  if (p.has0) tc_bn_apply_residual<VEC>(p.res0, p.res0_op, p.res0_plane, p.idx0, p.ld0, p.C, it);
+  if (p.has1) tc_bn_apply_residual<VEC>(p.res1, p.res1_op, p.res1_plane, p.idx1, p.ld1, p.C, it);
 }
 // ... then normalise, activate, drop out, add the residuals and write the two planes
 template <int VEC>
@@ -201,10 +232,10 @@ __device__ __forceinline__ void tc_bn_apply_finish(const TcApplyArgs& p, TcApply
     it.v[j] = y + it.r[j];
   }
   if (VEC == 4) {
-    *reinterpret_cast<float4*>(p.hi + it.m * p.ldo + it.c0) = make_float4(it.v[0], it.v[1 % VEC], it.v[2 % VEC], it.v[3 % VEC]);
+    if (p.hi) *reinterpret_cast<float4*>(p.hi + it.m * p.ldo + it.c0) = make_float4(it.v[0], it.v[1 % VEC], it.v[2 % VEC], it.v[3 % VEC]);
     tc_store_operand4(p.lo, p.op_plane, p.op, it.m * p.ldo + it.c0, it.v[0], it.v[1 % VEC], it.v[2 % VEC], it.v[3 % VEC]);
   } else {
-    p.hi[it.m * p.ldo + it.c0] = it.v[0];
+    if (p.hi) p.hi[it.m * p.ldo + it.c0] = it.v[0];
     tc_store_operand(p.lo, p.op_plane, p.op, it.m * p.ldo + it.c0, it.v[0]);
   }
 }

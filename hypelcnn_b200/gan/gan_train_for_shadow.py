@@ -309,15 +309,15 @@ def run_session(params, base_log_path, loader=None):
     validation_sample_count = flags.validation_sample_count
     neighborhood = 0
 
+    # under torchrun: the pairs are strided over the ranks, every train op all-reduces its gradient buffer once; the
+    # samplers draw from the global generators, so every rank seeds them alike before the pair list is built.  First
+    # thing of all: it selects this rank's GPU, and the scene must be loaded onto THAT device.
+    rank, _, world = parallel.init_from_env()
+    parallel.sync_split_seed()
     if loader is None:
         loader = get_loader_from_name(flags.loader_name, flags.path)
     data_set = loader.load_data(neighborhood, True)
     shadow_map, shadow_ratio = loader.load_shadow_map(neighborhood, data_set)
-
-    # under torchrun: the pairs are strided over the ranks, every train op all-reduces its gradient buffer once; the
-    # samplers draw from the global generators, so every rank seeds them alike before the pair list is built
-    rank, _, world = parallel.init_from_env()
-    parallel.sync_split_seed()
     input_iterator = load_op(flags.batch_size, flags.step, loader, data_set, shadow_map, shadow_ratio,
                              flags.regularization_support_rate, flags.pairing_method)
     input_iterator = shard_pair_iterator(input_iterator, rank, world)
