@@ -326,6 +326,11 @@ struct GsDisStepArgs {
   float *pool_y, *pool_x;
   int mode_y, slot_y, mode_x, slot_x;
 };
+// Weight gradients: a warp that accumulated its rank-1 updates h (x) d with shared-memory atomics would issue C * C of
+// them per layer and pass, one after the other (measured: most of the step at batch 32).  Instead every warp only keeps
+// the vectors of its four discriminator passes (x, h1, h2, d1, d2, dout) and, once per round, ALL threads of the block
+// sum the outer products, each thread owning whole weight elements — no atomics inside the block.
+constexpr int GS_SAVE_PER_PASS = 6;  // vectors of C floats kept per pass: x, h1, h2, d2, d1, dout
 __global__ void __launch_bounds__(GS_WARPS * 32) gan_cycle_dstep_kernel(const GsDisStepArgs a) {
   extern __shared__ float sm[];
   const int C = a.C, H = C / 2, ng = gs_gen_nweights(C), ngp = (ng + 3) & ~3, nd = gs_disc_nweights(C), ndp = (nd + 3) & ~3;
@@ -341,47 +346,77 @@ __global__ void __launch_bounds__(GS_WARPS * 32) gan_cycle_dstep_kernel(const Gs
   const GsDisc DX = gs_disc_load(dsm + dfl, a.wDX, C);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* pw = dsm + 2 * dfl + warp * (8 + 3 + 2 + 1) * C;   // generator nets [8][C], discriminator [3][C], d2, d1, dout
-  float *nets = pw, *dv = pw + 8 * C, *d2 = dv + 3 * C, *d1 = d2 + C, *dout = d1 + C;
+  float* nets = dsm + 2 * dfl + warp * 8 * C;                                   // generator nets [8][C]
+  float* save = dsm + 2 * dfl + GS_WARPS * 8 * C;                               // [warp][side][pass][6][C]
+  const int pass_fl = GS_SAVE_PER_PASS * C;
   const float s_gan = 1.f / ((float)a.rows * H);
   float l_gan = 0.f;
-  for (int64_t r = (int64_t)blockIdx.x * GS_WARPS + warp; r < a.rows; r += (int64_t)gridDim.x * GS_WARPS) {
-    for (int side = 0; side < 2; side++) {  // 0: D_Y on (y real, G(x) fake); 1: D_X on (x real, F(y) fake)
-      const float* real = (side == 0 ? a.y : a.x) + r * C;
-      const float* src = (side == 0 ? a.x : a.y) + r * C;
-      const GsDisc& D = side == 0 ? DY : DX;
-      float* gw = side == 0 ? gwY : gwX;
-      for (int c = lane; c < C; c += 32) nets[c] = src[c];
-      __syncwarp();
-      gs_gen_forward(side == 0 ? wG : wF, nets, C, lane);
-      const int mode = side == 0 ? a.mode_y : a.mode_x;
-      float* slot = (side == 0 ? a.pool_y : a.pool_x);
-      if (slot) slot += ((size_t)(side == 0 ? a.slot_y : a.slot_x) * a.rows + r) * C;
-      for (int pass = 0; pass < 2; pass++) {  // real -> 1, fake -> 0 (least_squares_discriminator_loss)
-        for (int c = lane; c < C; c += 32) {
-          float v;
-          if (pass == 0) {
-            v = real[c];
-          } else {
-            const float fresh = nets[7 * C + c];
-            v = fresh;
-            if (mode == 2) v = slot[c];
-            if (mode != 0) slot[c] = fresh;
+  const int64_t stride = (int64_t)gridDim.x * GS_WARPS;
+  for (int64_t r0 = (int64_t)blockIdx.x * GS_WARPS; r0 < a.rows; r0 += stride) {  // block-uniform rounds
+    const int64_t r = r0 + warp;
+    const bool valid = r < a.rows;
+    if (valid) {
+      for (int side = 0; side < 2; side++) {  // 0: D_Y on (y real, G(x) fake); 1: D_X on (x real, F(y) fake)
+        const float* real = (side == 0 ? a.y : a.x) + r * C;
+        const float* src = (side == 0 ? a.x : a.y) + r * C;
+        const GsDisc& D = side == 0 ? DY : DX;
+        for (int c = lane; c < C; c += 32) nets[c] = src[c];
+        __syncwarp();
+        gs_gen_forward(side == 0 ? wG : wF, nets, C, lane);
+        const int mode = side == 0 ? a.mode_y : a.mode_x;
+        float* slot = (side == 0 ? a.pool_y : a.pool_x);
+        if (slot) slot += ((size_t)(side == 0 ? a.slot_y : a.slot_x) * a.rows + r) * C;
+        for (int pass = 0; pass < 2; pass++) {  // real -> 1, fake -> 0 (least_squares_discriminator_loss)
+          float* dv = save + ((warp * 2 + side) * 2 + pass) * pass_fl;  // x, h1, h2 | d2 | d1 | dout
+          float *d2 = dv + 3 * C, *d1 = dv + 4 * C, *dout = dv + 5 * C;
+          for (int c = lane; c < C; c += 32) {
+            float v;
+            if (pass == 0) {
+              v = real[c];
+            } else {
+              const float fresh = nets[7 * C + c];
+              v = fresh;
+              if (mode == 2) v = slot[c];
+              if (mode != 0) slot[c] = fresh;
+            }
+            dv[c] = v;
           }
-          dv[c] = v;
+          __syncwarp();
+          gs_disc_forward(D, dv, dout, C, lane);
+          const float target = pass == 0 ? 1.f : 0.f;
+          for (int j = lane; j < H; j += 32) {
+            const float d = dout[j] - target;
+            l_gan += 0.5f * s_gan * d * d;
+            dout[j] = s_gan * d;
+          }
+          __syncwarp();
+          gs_disc_backward(D, dv, dout, d2, d1, nullptr, nullptr, C, lane);
         }
-        __syncwarp();
-        gs_disc_forward(D, dv, dout, C, lane);
-        const float target = pass == 0 ? 1.f : 0.f;
-        for (int j = lane; j < H; j += 32) {
-          const float d = dout[j] - target;
-          l_gan += 0.5f * s_gan * d * d;
-          dout[j] = s_gan * d;
-        }
-        __syncwarp();
-        gs_disc_backward(D, dv, dout, d2, d1, nullptr, gw, C, lane);
       }
     }
+    __syncthreads();
+    // ---- outer products of this round's rows: thread e owns weight elements e, e + blockDim, ...
+    const int nvalid = (int)min((int64_t)GS_WARPS, a.rows - r0);
+    for (int side = 0; side < 2; side++) {
+      float* gw = side == 0 ? gwY : gwX;
+      for (int e = threadIdx.x; e < nd; e += blockDim.x) {
+        // dense layout: W1 [C][C] | b1 [C] | W2 [C][C] | b2 [C] | W3 [C][H] | b3 [H];  vectors per pass: x 0, h1 1, h2 2, d2 3, d1 4, dout 5
+        int e2 = e, in_vec, out_vec, i, j;
+        bool bias = false;
+        if (e2 < C * C + C) { in_vec = 0; out_vec = 4; bias = e2 >= C * C; i = e2 / C; j = bias ? e2 - C * C : e2 - i * C; }
+        else if ((e2 -= C * C + C) < C * C + C) { in_vec = 1; out_vec = 3; bias = e2 >= C * C; i = e2 / C; j = bias ? e2 - C * C : e2 - i * C; }
+        else { e2 -= C * C + C; in_vec = 2; out_vec = 5; bias = e2 >= C * H; i = e2 / H; j = bias ? e2 - C * H : e2 - i * H; }
+        float acc = 0.f;
+        for (int w = 0; w < nvalid; w++)
+#pragma unroll
+          for (int pass = 0; pass < 2; pass++) {
+            const float* dv = save + ((w * 2 + side) * 2 + pass) * pass_fl;
+            acc += (bias ? 1.f : dv[in_vec * C + i]) * dv[out_vec * C + j];
+          }
+        gw[e] += acc;
+      }
+    }
+    __syncthreads();
   }
   l_gan = warp_sum(l_gan);
   if (lane == 0 && a.loss_acc) {
@@ -425,7 +460,7 @@ static size_t gs_gstep_smem(int C) {
 static size_t gs_dstep_smem(int C) {
   const int ngp = (gs_gen_nweights(C) + 3) & ~3, ndp = (gs_disc_nweights(C) + 3) & ~3;
   const int dfl = (2 * C * (C + 1) + C * (C / 2 + 1) + 2 * C + C / 2 + 3) & ~3;
-  return (size_t)(2 * ngp + 2 * ndp + 2 * dfl + GS_WARPS * 14 * C) * sizeof(float);
+  return (size_t)(2 * ngp + 2 * ndp + 2 * dfl + GS_WARPS * (8 + 4 * 6) * C) * sizeof(float);
 }
 
 }  // namespace hyp

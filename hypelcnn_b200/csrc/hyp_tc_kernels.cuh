@@ -206,9 +206,9 @@ __device__ __forceinline__ void tc_bn_apply_residual(const float* res, const uin
 }
 // issue every global load of one item (z and the residual sources) ...
 template <int VEC>
-__device__ __forceinline__ void tc_bn_apply_load(const TcApplyArgs& p, int64_t i, int cq, TcApplyItem<VEC>& it) {
-  it.m = i / cq;
-  it.c0 = (int)(i - it.m * cq) * VEC;
+__device__ __forceinline__ void tc_bn_apply_load(const TcApplyArgs& p, int64_t m, int cg, TcApplyItem<VEC>& it) {
+  it.m = m;
+  it.c0 = cg * VEC;
   if (VEC == 4) {
     const float4 t = *reinterpret_cast<const float4*>(p.z + it.m * p.ldz + it.c0);
     it.v[0] = t.x; it.v[1 % VEC] = t.y; it.v[2 % VEC] = t.z; it.v[3 % VEC] = t.w;
@@ -246,13 +246,26 @@ __global__ void __launch_bounds__(256) tc_bn_apply_kernel(const TcApplyArgs p) {
   const int cq = (p.C + VEC - 1) / VEC;
   const int64_t total = p.rows * cq;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 2 * stride) {
+  // item i = (row m, channel group cg); the walk advances (m, cg) by the constant stride with a carry instead of
+  // dividing a 64-bit index per item (the emulated 64-bit division was most of this kernel's instructions)
+  const int64_t dm = stride / cq;
+  const int dc = (int)(stride - dm * cq);
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t m = i / cq;
+  int cg = (int)(i - m * cq);
+  for (; i < total; i += 2 * stride) {
     TcApplyItem<VEC> a, b;
     const bool two = i + stride < total;
-    tc_bn_apply_load<VEC>(p, i, cq, a);
-    if (two) tc_bn_apply_load<VEC>(p, i + stride, cq, b);
+    int64_t m2 = m + dm;
+    int cg2 = cg + dc;
+    if (cg2 >= cq) { cg2 -= cq; m2++; }
+    tc_bn_apply_load<VEC>(p, m, cg, a);
+    if (two) tc_bn_apply_load<VEC>(p, m2, cg2, b);
     tc_bn_apply_finish<VEC>(p, a);
     if (two) tc_bn_apply_finish<VEC>(p, b);
+    m = m2 + dm;
+    cg = cg2 + dc;
+    if (cg >= cq) { cg -= cq; m++; }
   }
 }
 
