@@ -126,8 +126,9 @@ static int tc_layout(hyp_model& m) {
   TcState& S = *m.tc;
   S.op = m.d.precision_mode == HYP_PRECISION_3XF16 ? OP_F16X3 : (m.d.precision_mode == HYP_PRECISION_BF16 ? OP_BF16 : OP_TF32X3);
   S.kbe = op_kbe(S.op);
-  // weights are O(1e-2): x 2^8 puts their fp16 remainders into the normal range (|w| must stay below 255)
-  S.w_scale = S.op == OP_F16X3 ? 256.f : 1.f;
+  // weights are O(1e-2): x 2^6 puts the fp16 remainders of everything above 2e-3 into the normal range (smaller weights
+  // keep an absolute error below 2^-31, far under the scale of the tensor) and leaves room up to |w| = 1023
+  S.w_scale = S.op == OP_F16X3 ? 64.f : 1.f;
   const size_t Bm = (size_t)m.d.max_batch;
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -989,11 +990,13 @@ static int tc_forward(hyp_model& m, const float* x, int64_t B, bool training, bo
     if (L.res.size() > 0) {
       const TcTensor& rs = S.tt[L.res[0].src];
       p.res0 = tc_plane0(m, L.res[0].src); p.idx0 = L.res[0].idx; p.ld0 = rs.Cp; p.has0 = 1;
+      p.pat0 = L.res[0].pattern == 2 ? 2 : (L.res[0].pattern == 3 && L.res[0].step == 2 ? 3 : 0);
       p.res0_op = reinterpret_cast<const uint16_t*>(tc_plane1(m, L.res[0].src)); p.res0_plane = rs.plane_elems;
     }
     if (L.res.size() > 1) {
       const TcTensor& rs = S.tt[L.res[1].src];
       p.res1 = tc_plane0(m, L.res[1].src); p.idx1 = L.res[1].idx; p.ld1 = rs.Cp; p.has1 = 1;
+      p.pat1 = L.res[1].pattern == 2 ? 2 : (L.res[1].pattern == 3 && L.res[1].step == 2 ? 3 : 0);
       p.res1_op = reinterpret_cast<const uint16_t*>(tc_plane1(m, L.res[1].src)); p.res1_plane = rs.plane_elems;
     }
     const double bytes = 4.0 * rows * L.Cout * (3 + L.res.size());

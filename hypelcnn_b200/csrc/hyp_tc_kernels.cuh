@@ -156,14 +156,16 @@ struct TcApplyArgs {
   uint32_t stream_id;
   // residual sources [rows][ld]; idx == NULL: identity channel map.  res = the source's fp32 value plane, or NULL
   // when it keeps none: the value is then rebuilt from its fp16 (hi, lo) operand planes res_op / res_plane
+  // pat: 0 generic idx table, 2 = tf.repeat by 2 (idx[j] = j / 2), 3 = strided gather with step 2 (idx[j] = 2 j): the
+  // two regular maps are read with vector loads instead of one indexed scalar load per element
   const float* res0;
   const int* idx0;
-  int ld0, has0;
+  int ld0, has0, pat0;
   const uint16_t* res0_op;
   size_t res0_plane;
   const float* res1;
   const int* idx1;
-  int ld1, has1;
+  int ld1, has1, pat1;
   const uint16_t* res1_op;
   size_t res1_plane;
 };
@@ -179,30 +181,52 @@ struct TcApplyItem {
 __device__ __forceinline__ float tc_value_of_planes(const uint16_t* op, size_t plane, int64_t idx) {
   return __half2float(__ushort_as_half(op[idx])) + __half2float(__ushort_as_half(op[idx + plane]));
 }
+__device__ __forceinline__ float tc_half_bits(uint32_t w, int hi) { return __half2float(__ushort_as_half((unsigned short)(hi ? w >> 16 : w & 0xffffu))); }
 template <int VEC>
 __device__ __forceinline__ void tc_bn_apply_residual(const float* res, const uint16_t* op, size_t plane, const int* idx, int ld,
-                                                     int C, TcApplyItem<VEC>& it) {
-  if (res) {
-    if (VEC == 4 && !idx) {
+                                                     int C, int pat, TcApplyItem<VEC>& it) {
+  float add[VEC];
+  if (VEC == 4 && !idx) {  // identity: the same 4 channels
+    if (res) {
       const float4 t = *reinterpret_cast<const float4*>(res + it.m * ld + it.c0);
-      it.r[0] += t.x; it.r[1 % VEC] += t.y; it.r[2 % VEC] += t.z; it.r[3 % VEC] += t.w;
+      add[0] = t.x; add[1 % VEC] = t.y; add[2 % VEC] = t.z; add[3 % VEC] = t.w;
     } else {
-#pragma unroll
-      for (int j = 0; j < VEC; j++) it.r[j] += res[it.m * ld + (idx ? idx[min(it.c0 + j, C - 1)] : it.c0 + j)];
+      const uint2 h = *reinterpret_cast<const uint2*>(op + it.m * ld + it.c0);
+      const uint2 l = *reinterpret_cast<const uint2*>(op + plane + it.m * ld + it.c0);
+      add[0] = tc_half_bits(h.x, 0) + tc_half_bits(l.x, 0); add[1 % VEC] = tc_half_bits(h.x, 1) + tc_half_bits(l.x, 1);
+      add[2 % VEC] = tc_half_bits(h.y, 0) + tc_half_bits(l.y, 0); add[3 % VEC] = tc_half_bits(h.y, 1) + tc_half_bits(l.y, 1);
     }
-  } else if (VEC == 4 && !idx) {
-    const uint2 h = *reinterpret_cast<const uint2*>(op + it.m * ld + it.c0);
-    const uint2 l = *reinterpret_cast<const uint2*>(op + plane + it.m * ld + it.c0);
-    const __half2 h0 = *reinterpret_cast<const __half2*>(&h.x), h1 = *reinterpret_cast<const __half2*>(&h.y);
-    const __half2 l0 = *reinterpret_cast<const __half2*>(&l.x), l1 = *reinterpret_cast<const __half2*>(&l.y);
-    it.r[0] += __low2float(h0) + __low2float(l0);
-    it.r[1 % VEC] += __high2float(h0) + __high2float(l0);
-    it.r[2 % VEC] += __low2float(h1) + __low2float(l1);
-    it.r[3 % VEC] += __high2float(h1) + __high2float(l1);
+  } else if (VEC == 4 && pat == 2 && it.c0 + 4 <= C) {  // repeat by 2: source channels c0 / 2, c0 / 2 + 1
+    float a, b;
+    if (res) {
+      const float2 t = *reinterpret_cast<const float2*>(res + it.m * ld + it.c0 / 2);
+      a = t.x; b = t.y;
+    } else {
+      const uint32_t h = *reinterpret_cast<const uint32_t*>(op + it.m * ld + it.c0 / 2);
+      const uint32_t l = *reinterpret_cast<const uint32_t*>(op + plane + it.m * ld + it.c0 / 2);
+      a = tc_half_bits(h, 0) + tc_half_bits(l, 0); b = tc_half_bits(h, 1) + tc_half_bits(l, 1);
+    }
+    add[0] = a; add[1 % VEC] = a; add[2 % VEC] = b; add[3 % VEC] = b;
+  } else if (VEC == 4 && pat == 3 && it.c0 + 4 <= C) {  // stride 2: source channels 2 c0, 2 c0 + 2, 2 c0 + 4, 2 c0 + 6
+    if (res) {
+      const float4 t = *reinterpret_cast<const float4*>(res + it.m * ld + 2 * it.c0);
+      const float4 u = *reinterpret_cast<const float4*>(res + it.m * ld + 2 * it.c0 + 4);
+      add[0] = t.x; add[1 % VEC] = t.z; add[2 % VEC] = u.x; add[3 % VEC] = u.z;
+    } else {
+      const uint4 h = *reinterpret_cast<const uint4*>(op + it.m * ld + 2 * it.c0);
+      const uint4 l = *reinterpret_cast<const uint4*>(op + plane + it.m * ld + 2 * it.c0);
+      add[0] = tc_half_bits(h.x, 0) + tc_half_bits(l.x, 0); add[1 % VEC] = tc_half_bits(h.y, 0) + tc_half_bits(l.y, 0);
+      add[2 % VEC] = tc_half_bits(h.z, 0) + tc_half_bits(l.z, 0); add[3 % VEC] = tc_half_bits(h.w, 0) + tc_half_bits(l.w, 0);
+    }
   } else {
 #pragma unroll
-    for (int j = 0; j < VEC; j++) it.r[j] += tc_value_of_planes(op, plane, it.m * ld + (idx ? idx[min(it.c0 + j, C - 1)] : it.c0 + j));
+    for (int j = 0; j < VEC; j++) {
+      const int64_t at = it.m * ld + (idx ? idx[min(it.c0 + j, C - 1)] : it.c0 + j);
+      add[j] = res ? res[at] : tc_value_of_planes(op, plane, at);
+    }
   }
+#pragma unroll
+  for (int j = 0; j < VEC; j++) it.r[j] += add[j];
 }
 // issue every global load of one item (z and the residual sources) ...
 template <int VEC>
@@ -217,8 +241,8 @@ __device__ __forceinline__ void tc_bn_apply_load(const TcApplyArgs& p, int64_t m
   }
 #pragma unroll
   for (int j = 0; j < VEC; j++) it.r[j] = 0.f;
-  if (p.has0) tc_bn_apply_residual<VEC>(p.res0, p.res0_op, p.res0_plane, p.idx0, p.ld0, p.C, it);
-  if (p.has1) tc_bn_apply_residual<VEC>(p.res1, p.res1_op, p.res1_plane, p.idx1, p.ld1, p.C, it);
+  if (p.has0) tc_bn_apply_residual<VEC>(p.res0, p.res0_op, p.res0_plane, p.idx0, p.ld0, p.C, p.pat0, it);
+  if (p.has1) tc_bn_apply_residual<VEC>(p.res1, p.res1_op, p.res1_plane, p.idx1, p.ld1, p.C, p.pat1, it);
 }
 // ... then normalise, activate, drop out, add the residuals and write the two planes
 template <int VEC>
