@@ -193,21 +193,16 @@ __device__ __forceinline__ void gather_issue(const GatherArgs& p, const T* __res
     bx = x / 2 + p.nb - p.nb / 2;
     by = y / 2 + p.nb - p.nb / 2;
   }
-  // Window row / column -> scene offset, once per warp: lane l < S holds the pixel offset of window row l (reflected
-  // at the border, times the scene width), lane S + l that of window column l; a pixel's address is then two shuffles
-  // and an add instead of two reflections and a 64-bit multiply per thread and pixel.  (S <= 15: 2 S lanes suffice.)
-  const int lane = (int)threadIdx.x & 31;
-  int off = 0;
-  if (lane < S) off = reflect_sym(by + (half_res ? lane / 2 : lane) - p.nb, p.Hc) * p.Wc;
-  else if (lane < 2 * S) off = reflect_sym(bx + (half_res ? (lane - S) / 2 : lane - S) - p.nb, p.Wc);
-  {
+  if (active) {
     const int dy = rows_per_iter / S, dx = rows_per_iter - dy * S;  // one step of rows_per_iter pixels in (row, column)
     int py = slot / S, px = slot - py * S;
 #pragma unroll
     for (int u = 0; u < GATHER_PF; u++) {
-      const bool in = slot + u * rows_per_iter < npix;   // the shuffles run on every lane, the load only where needed
-      const int pixel = __shfl_sync(0xffffffffu, off, in ? py : 0) + __shfl_sync(0xffffffffu, off, in ? S + px : 0);
-      if (active && in) L.raw[u] = __ldg(reinterpret_cast<const uint4*>(casi + (size_t)pixel * p.C) + chunk);
+      if (slot + u * rows_per_iter < npix) {
+        const int ry = reflect_sym(by + (half_res ? py / 2 : py) - p.nb, p.Hc);
+        const int rx = reflect_sym(bx + (half_res ? px / 2 : px) - p.nb, p.Wc);
+        L.raw[u] = __ldg(reinterpret_cast<const uint4*>(casi + ((size_t)ry * p.Wc + rx) * p.C) + chunk);
+      }
       py += dy;
       px += dx;
       if (px >= S) { px -= S; py++; }
@@ -318,12 +313,17 @@ __global__ void __launch_bounds__(GATHER_THREADS, 4) gather_rows_kernel(const Ga
     // ---- stream the image out, 16 bytes per store
     float4* const gvec = reinterpret_cast<float4*>(gout - shift);
     const int nvec = (shift + total + 3) >> 2;
-    const int v_first = shift ? 1 : 0, v_last = (shift + total) >> 2;   // vectors [v_first, v_last) are whole
-    for (int v = v_first + (int)threadIdx.x; v < v_last; v += GATHER_THREADS) __stcs(gvec + v, gather_smem4[v]);
-    if (threadIdx.x < 8) {  // the partial first / last vector of the patch, element-wise
-      const int v = threadIdx.x < 4 ? 0 : nvec - 1, t = threadIdx.x & 3, e = 4 * v - shift + t;
-      const bool partial = threadIdx.x < 4 ? shift != 0 : (v_last != nvec && (nvec > 1 || shift == 0));
-      if (partial && e >= 0 && e < total) __stcs(gout + e, sm[4 * v + t]);
+    for (int v = threadIdx.x; v < nvec; v += GATHER_THREADS) {
+      const float4 val = gather_smem4[v];
+      const int e0 = 4 * v - shift;  // patch element of val.x
+      if (e0 >= 0 && e0 + 4 <= total) {
+        __stcs(gvec + v, val);
+      } else {
+        const float f[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+          if (e0 + t >= 0 && e0 + t < total) __stcs(gout + e0 + t, f[t]);
+      }
     }
     __syncthreads();
   }
