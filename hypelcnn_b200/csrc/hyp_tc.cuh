@@ -53,7 +53,9 @@ struct alignas(16) TcSeg {
   int32_t nk;          // K blocks of TC_KB
   int32_t n_mma;       // N of this segment's MMAs: multiple of 16 in [16, 256]
   int32_t nb;          // B boxes per K block and plane
-  int32_t pad[3];
+  int32_t ks_last;     // K steps (quarters of a K block) the LAST K block of the segment needs: 1..4, 0 = 4.  The tail of
+                       // a K range that is not a multiple of the block is zero padding: its MMAs are skipped
+  int32_t pad[2];
 };
 
 struct alignas(16) TcColBlock {
@@ -558,11 +560,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           hdr0 = __ldg(hp); hdr1 = __ldg(hp + 1);
         }
         int2 sN[4];  // (nk, n_mma) of segment lane + 32 i
+        int sK[4];   // ks_last
 #pragma unroll
         for (int i = 0; i < 4; i++) {
           sN[i] = make_int2(0, 0);
-          if (lane + 32 * i < seg_count)
+          sK[i] = 0;
+          if (lane + 32 * i < seg_count) {
             sN[i] = __ldg(reinterpret_cast<const int2*>(&p.segs[seg_begin + lane + 32 * i].nk));
+            sK[i] = __ldg(&p.segs[seg_begin + lane + 32 * i].ks_last);
+          }
         }
         uint32_t accum = 0;
         int kcount = 0;  // K blocks of this tile issued so far
@@ -571,6 +577,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int rs = si >> 5, src = si & 31;
           const int2 wN = rs == 0 ? sN[0] : (rs == 1 ? sN[1] : (rs == 2 ? sN[2] : sN[3]));
           const int snk = __shfl_sync(0xffffffffu, wN.x, src);
+          const int wK = rs == 0 ? sK[0] : (rs == 1 ? sK[1] : (rs == 2 ? sK[2] : sK[3]));
+          const int sks = __shfl_sync(0xffffffffu, wK, src);
           const uint32_t idesc = make_idesc(__shfl_sync(0xffffffffu, wN.y, src), MN, CG, ab_fmt);
           for (int kb = 0; kb < snk; kb++, kcount++) {
             if (kcount % CH == 0) {  // new chunk: its TMEM buffer must have been drained
@@ -587,9 +595,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t a_lo = a_hi + (TC_PLANE_A >> 4);
             const uint32_t b_hi = a_hi + (npl * TC_PLANE_A >> 4);
             const uint32_t b_lo = b_hi + (b_plane >> 4);
+            const int nks = (kb == snk - 1 && sks != 0) ? sks : 4;
             if (p.op == OP_TF32X3) {
 #pragma unroll
               for (int ks = 0; ks < 4; ks++) {
+                if (ks >= nks) break;
                 const uint32_t o = (uint32_t)ks * ks_step;
                 mma_tf32_u<CG>(pred, tmem_d, a_lo + o, b_hi + o, desc_hi32, idesc, accum);
                 mma_tf32_u<CG>(pred, tmem_d, a_hi + o, b_lo + o, desc_hi32, idesc, 1);
@@ -599,6 +609,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else if (p.op == OP_F16X3) {
 #pragma unroll
               for (int ks = 0; ks < 4; ks++) {
+                if (ks >= nks) break;
                 const uint32_t o = (uint32_t)ks * ks_step;
                 mma_f16_u<CG>(pred, tmem_d, a_lo + o, b_hi + o, desc_hi32, idesc, accum);
                 mma_f16_u<CG>(pred, tmem_d, a_hi + o, b_lo + o, desc_hi32, idesc, 1);
@@ -608,6 +619,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else {
 #pragma unroll
               for (int ks = 0; ks < 4; ks++) {
+                if (ks >= nks) break;
                 mma_f16_u<CG>(pred, tmem_d, a_hi + (uint32_t)ks * ks_step, b_hi + (uint32_t)ks * ks_step, desc_hi32, idesc, accum);
                 accum = 1;
               }

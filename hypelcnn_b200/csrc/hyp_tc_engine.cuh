@@ -105,9 +105,15 @@ static void* tc_operand(const hyp_model& m, int t) {
   return m.tc->op == OP_TF32X3 ? static_cast<void*>(tc_plane0(m, t)) : static_cast<void*>(tc_plane1(m, t));
 }
 
+// HYP_SWEEP_ZIGZAG=0: every element-wise pass sweeps ascending (diagnostic: the L2 carry-over between passes is lost)
+static inline int tc_zigzag() {
+  static const int v = [] { const char* e = getenv("HYP_SWEEP_ZIGZAG"); return (e && e[0] == '0') ? 0 : 1; }();
+  return v;
+}
+
 // launch shape of the vectorised elementwise kernels: TX column groups of 4 channels per block row,
-// 256 / TX row lanes, `rblocks` row blocks of `rpb` rows
-struct EwGrid { int TX, gx, rblocks, rpb; };
+// 256 / TX row lanes, `rblocks` block rows sweeping the tensor's rows together (tc_sweep_row)
+struct EwGrid { int TX, gx, rblocks; };
 static inline EwGrid ew_grid2(int cols, int64_t rows) {
   EwGrid g;
   const int c4 = (int)cdiv(cols, 4);
@@ -115,8 +121,7 @@ static inline EwGrid ew_grid2(int cols, int64_t rows) {
   g.gx = (int)cdiv(c4, g.TX);
   const int TY = 256 / g.TX;
   int64_t rb = std::max<int64_t>(1, std::min<int64_t>(cdiv(rows, 4 * TY), cdiv(tc_sm_count() * 8, g.gx)));
-  g.rpb = (int)cdiv(rows, rb);
-  g.rblocks = (int)cdiv(rows, g.rpb);
+  g.rblocks = (int)rb;
   return g;
 }
 
@@ -337,6 +342,12 @@ static void finish_launch(PlanBuf& pb, TcLaunch& l) {
 // wgrad (MN-major) launches run as CTA pairs over two adjacent 128-row tiles of the M side when their count is even
 // (the pair shares its gz columns); B rows reserved per stage: boxes of kb columns covering n / cg columns, per CTA
 static inline int wg_cg(int mt) { return (mt % 2 == 0) ? 2 : 1; }
+// K steps the last K block of a K-major segment needs when its K range holds `k_elems` real elements (TcSeg.ks_last)
+static inline int tc_ks_last(int64_t k_elems, int64_t nk, int kb) {
+  if (cdiv(k_elems, kb) != nk) return 0;  // whole padding blocks behind the data: not expected, keep every step
+  const int rem = (int)(k_elems % kb);
+  return rem ? (int)cdiv(rem, kb / 4) : 4;
+}
 static inline int wg_brows(int n_mma, int cg, int kb) { return cg * (int)cdiv(n_mma / cg, kb) * kb; }
 
 // K-major launches run as CTA pairs (cta_group::2): consecutive tiles (2i, 2i+1) must share their
@@ -505,6 +516,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
       for (int j = 0; j < ntn; j++) {
         TcSeg s{};
         s.b1 = j * nw; s.nk = T.Kp / KB; s.n_mma = r16(std::min(nw, Cout - j * nw)); s.nb = 1;
+        s.ks_last = tc_ks_last(Cin, s.nk, KB);
         pb.segs.push_back(s);
       }
       const int nrt = (int)cdiv(rows_out, 128);
@@ -536,6 +548,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
         for (int j = 0; j < ntn; j++) {
           TcSeg s{};
           s.b1 = j * nw; s.nk = T.wd_ld / KB; s.n_mma = r16(std::min(nw, Cin - j * nw)); s.nb = 1;
+          s.ks_last = tc_ks_last(Cout, s.nk, KB);
           pb.segs.push_back(s);
         }
         for (int rt2 = 0; rt2 < nrt; rt2 += CG)
@@ -622,6 +635,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
             const int tap = (dy + h) * TW + (dx + h);
             TcSeg s{};
             s.a2 = p + dy * P + dx; s.b1 = tap * NS * fpad; s.nk = T.Kp / KB; s.n_mma = nbx * fpad; s.nb = nbx;
+            s.ks_last = tc_ks_last(Cin, s.nk, KB);
             pb.segs.push_back(s);
           }
           const int nseg = (int)pb.segs.size() - seg0;
@@ -673,6 +687,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
               TcSeg s{};
               s.a2 = p - (dy * P + dx); s.b1 = tap * T.Cq + j * nw;
               s.nk = (int)cdiv((R - ring) * nt * fpad, KB); s.n_mma = r16(std::min(nw, Cin - j * nw)); s.nb = 1;
+              s.ks_last = tc_ks_last((R - ring) * nt * fpad, s.nk, KB);
               tkb += s.nk;
               pb.segs.push_back(s);
             }
@@ -784,6 +799,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
           TcSeg s{};
           s.a2 = pos; s.b0 = pos * T.Kp; s.b1 = j * nw; s.nk = T.Kp / KB;
           s.n_mma = r16(std::min(nw, Cout - j * nw)); s.nb = 1;
+          s.ks_last = tc_ks_last(Ct, s.nk, KB);
           pb.segs.push_back(s);
         }
       for (int bt2 = 0; bt2 < nbt; bt2 += CG)
@@ -816,6 +832,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
           for (int jd = 0; jd < dtn; jd++) {
             TcSeg s{};
             s.b1 = pos * T.Cq + jd * dw; s.nk = T.wd_ld / KB; s.n_mma = r16(std::min(dw, Ct - jd * dw)); s.nb = 1;
+            s.ks_last = tc_ks_last(Cout, s.nk, KB);
             pb.segs.push_back(s);
           }
         for (int bt2 = 0; bt2 < nbt; bt2 += CG)
@@ -1001,7 +1018,20 @@ static int tc_forward(hyp_model& m, const float* x, int64_t B, bool training, bo
     }
     const double bytes = 4.0 * rows * L.Cout * (3 + L.res.size());
     // (a 2-D row-lane form of this kernel measured 15 % slower: the flat float4 walk keeps more rows in flight)
-    TC_PROF("tc_bn_apply_kernel", bytes, (tc_bn_apply_kernel<4><<<tc_grid(rows * cdiv(L.Cout, 4)), 256, 0, st>>>(p)));
+    {
+      const EwGrid ga = ew_grid2(L.Cout, rows);
+      const bool drop = p.keep < 1.f;
+#define TC_FWD_APPLY_LAUNCH(TXV)                                                                        \
+  do {                                                                                                  \
+    if (drop) tc_bn_apply_kernel<TXV, true><<<dim3(ga.gx, ga.rblocks), 256, 0, st>>>(p, tc_zigzag());   \
+    else tc_bn_apply_kernel<TXV, false><<<dim3(ga.gx, ga.rblocks), 256, 0, st>>>(p, tc_zigzag());       \
+  } while (0)
+      g_prof.begin(st, "tc_bn_apply_kernel", 0.0, bytes);
+      if (ga.TX == 32) TC_FWD_APPLY_LAUNCH(32); else if (ga.TX == 16) TC_FWD_APPLY_LAUNCH(16); else TC_FWD_APPLY_LAUNCH(8);
+      g_prof.end(st);
+      HYP_LAUNCHED();
+#undef TC_FWD_APPLY_LAUNCH
+    }
     if (L.lrn) {
       TC_PROF("tc_lrn_fwd_kernel", 16.0 * rows * L.Cout,
               (tc_lrn_fwd_kernel<<<tc_grid(rows * 32), 256, 8 * L.Cout * sizeof(float), st>>>(
@@ -1075,12 +1105,40 @@ static int tc_backward(hyp_model& m, const uint8_t* labels, int64_t B, float* lo
     if (S.op == OP_F16X3) { p.gmax_bits = reinterpret_cast<unsigned int*>(gzs); p.gz_scale_out = gzs + 1; }
     p.gcols = T.kind == 1 ? T.Gp : L.Cout;
     p.fpad = T.kind == 1 ? T.fpad : 0; p.f = T.f; p.R = T.R; p.nt = T.nt; p.ft = T.ft;
+    // Pass order and sweep directions over this layer's gradient tensor: residual pushes (alternating, the last one
+    // descending), statistics ascending, gz descending -- each pass starts on the rows the previous one left in L2, and
+    // the dgrad / wgrad GEMMs that follow start at row 0, where gz was written last.
+    const int zz = tc_zigzag();
+    int n_push = 0;
+    for (const Resid& r : L.res) n_push += m.tensors[r.src].needs_grad ? 1 : 0;
+    for (const Resid& r : L.res) {
+      const Tensor& src = m.tensors[r.src];
+      if (!src.needs_grad) continue;
+      const int resid_rev = zz ? (n_push--) & 1 : 0;
+      const EwGrid gs = ew_grid2(src.C, rows);
+      const double bytes = 4.0 * rows * (L.Cout + (ginit[r.src] ? 2.0 : 1.0) * src.C);
+      const int mode = r.identity ? 0 : (r.pattern == 2 ? 2 : (r.pattern == 3 ? 3 : 1));
+#define TC_RESID_LAUNCH(TXV, MODEV)                                                                              \
+  tc_resid_bwd_v4_kernel<TXV, MODEV><<<dim3(gs.gx, gs.rblocks), 256, 0, st>>>(                                  \
+      p.gout, tout.Cp, tc_grad(m, r.src), S.tt[r.src].Cp, src.C, r.lo, r.hi, rows, ginit[r.src], resid_rev, r.step)
+#define TC_RESID_TX(MODEV)                                                                                       \
+  do {                                                                                                           \
+    if (gs.TX == 32) TC_RESID_LAUNCH(32, MODEV); else if (gs.TX == 16) TC_RESID_LAUNCH(16, MODEV); else TC_RESID_LAUNCH(8, MODEV); \
+  } while (0)
+      g_prof.begin(st, "tc_resid_bwd_kernel", 0.0, bytes);
+      if (mode == 0) TC_RESID_TX(0); else if (mode == 2) TC_RESID_TX(2); else if (mode == 3) TC_RESID_TX(3); else TC_RESID_TX(1);
+      g_prof.end(st);
+      HYP_LAUNCHED();
+#undef TC_RESID_TX
+#undef TC_RESID_LAUNCH
+      ginit[r.src] = 1;
+    }
     const EwGrid gr = ew_grid2(L.Cout, rows);
     const bool drop = p.keep < 1.f;
 #define TC_REDUCE_LAUNCH(TXV)                                                                                         \
   do {                                                                                                                \
-    if (drop) tc_bn_bwd_reduce_v4_kernel<TXV, true><<<dim3(gr.gx, gr.rblocks), 256, 0, st>>>(p, gr.rpb);              \
-    else tc_bn_bwd_reduce_v4_kernel<TXV, false><<<dim3(gr.gx, gr.rblocks), 256, 0, st>>>(p, gr.rpb);                  \
+    if (drop) tc_bn_bwd_reduce_v4_kernel<TXV, true><<<dim3(gr.gx, gr.rblocks), 256, 0, st>>>(p, 0);                   \
+    else tc_bn_bwd_reduce_v4_kernel<TXV, false><<<dim3(gr.gx, gr.rblocks), 256, 0, st>>>(p, 0);                       \
   } while (0)
     g_prof.begin(st, "tc_bn_bwd_reduce_kernel", 0.0, 8.0 * rows * L.Cout);
     if (gr.TX == 32) TC_REDUCE_LAUNCH(32); else if (gr.TX == 16) TC_REDUCE_LAUNCH(16); else TC_REDUCE_LAUNCH(8);
@@ -1096,36 +1154,15 @@ static int tc_backward(hyp_model& m, const uint8_t* labels, int64_t B, float* lo
       const bool shift = p.fpad != 0 && (p.f % 4 != 0 || p.ft % 4 != 0);
 #define TC_APPLY_LAUNCH(TXV)                                                                                          \
   do {                                                                                                                \
-    if (drop) tc_bn_bwd_apply_v4_kernel<TXV, false, true><<<dim3(ga.gx, ga.rblocks), 256, 0, st>>>(p, ga.rpb);        \
-    else if (shift) tc_bn_bwd_apply_v4_kernel<TXV, true, false><<<dim3(ga.gx, ga.rblocks), 256, 0, st>>>(p, ga.rpb);  \
-    else tc_bn_bwd_apply_v4_kernel<TXV, false, false><<<dim3(ga.gx, ga.rblocks), 256, 0, st>>>(p, ga.rpb);            \
+    if (drop) tc_bn_bwd_apply_v4_kernel<TXV, false, true><<<dim3(ga.gx, ga.rblocks), 256, 0, st>>>(p, zz);            \
+    else if (shift) tc_bn_bwd_apply_v4_kernel<TXV, true, false><<<dim3(ga.gx, ga.rblocks), 256, 0, st>>>(p, zz);      \
+    else tc_bn_bwd_apply_v4_kernel<TXV, false, false><<<dim3(ga.gx, ga.rblocks), 256, 0, st>>>(p, zz);                \
   } while (0)
       g_prof.begin(st, "tc_bn_bwd_apply_kernel", 0.0, 4.0 * rows * (2.0 * L.Cout + 2.0 * p.gcols));
       if (ga.TX == 32) TC_APPLY_LAUNCH(32); else if (ga.TX == 16) TC_APPLY_LAUNCH(16); else TC_APPLY_LAUNCH(8);
       g_prof.end(st);
       HYP_LAUNCHED();
 #undef TC_APPLY_LAUNCH
-    }
-    for (const Resid& r : L.res) {
-      const Tensor& src = m.tensors[r.src];
-      if (!src.needs_grad) continue;
-      const EwGrid gs = ew_grid2(src.C, rows);
-      const double bytes = 4.0 * rows * (L.Cout + (ginit[r.src] ? 2.0 : 1.0) * src.C);
-      const int mode = r.identity ? 0 : (r.pattern == 2 ? 2 : (r.pattern == 3 ? 3 : 1));
-#define TC_RESID_LAUNCH(TXV, MODEV)                                                                              \
-  tc_resid_bwd_v4_kernel<TXV, MODEV><<<dim3(gs.gx, gs.rblocks), 256, 0, st>>>(                                  \
-      p.gout, tout.Cp, tc_grad(m, r.src), S.tt[r.src].Cp, src.C, r.lo, r.hi, rows, ginit[r.src], gs.rpb, r.step)
-#define TC_RESID_TX(MODEV)                                                                                       \
-  do {                                                                                                           \
-    if (gs.TX == 32) TC_RESID_LAUNCH(32, MODEV); else if (gs.TX == 16) TC_RESID_LAUNCH(16, MODEV); else TC_RESID_LAUNCH(8, MODEV); \
-  } while (0)
-      g_prof.begin(st, "tc_resid_bwd_kernel", 0.0, bytes);
-      if (mode == 0) TC_RESID_TX(0); else if (mode == 2) TC_RESID_TX(2); else if (mode == 3) TC_RESID_TX(3); else TC_RESID_TX(1);
-      g_prof.end(st);
-      HYP_LAUNCHED();
-#undef TC_RESID_TX
-#undef TC_RESID_LAUNCH
-      ginit[r.src] = 1;
     }
     }
     // (a two-input FC's first part reuses the gz planes of the second part, processed just before: same scale slot)

@@ -141,6 +141,18 @@ __global__ void __launch_bounds__(256) tc_pack_weights_kernel(const PackJob* __r
   }
 }
 
+// Row sweep of the 2-D element-wise kernels: rows go in groups of G; block row y takes groups y, y + gridDim.y, ... so the
+// whole grid moves through the tensor as one narrow front, ascending or (rev) descending.  Consecutive passes over the
+// same tensors alternate the direction: a pass then starts on the rows its predecessor touched last, which are still
+// in the 126 MB L2.
+__device__ __forceinline__ int64_t tc_sweep_groups(int64_t rows, int G) { return (rows + G - 1) / G; }
+__device__ __forceinline__ int64_t tc_sweep_row(int64_t i, int64_t ng, int rev, int G) { return (rev ? ng - 1 - i : i) * G; }
+
+__device__ __forceinline__ void tc_load_ch4(const float* __restrict__ src, int c0, int C, float (&v)[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) v[k] = (c0 + k < C) ? src[c0 + k] : 0.f;
+}
+
 struct TcApplyArgs {
   const float* z;  // [rows][ldz] pre-BN
   int ldz;
@@ -244,52 +256,47 @@ __device__ __forceinline__ void tc_bn_apply_load(const TcApplyArgs& p, int64_t m
   if (p.has0) tc_bn_apply_residual<VEC>(p.res0, p.res0_op, p.res0_plane, p.idx0, p.ld0, p.C, p.pat0, it);
   if (p.has1) tc_bn_apply_residual<VEC>(p.res1, p.res1_op, p.res1_plane, p.idx1, p.ld1, p.C, p.pat1, it);
 }
-// ... then normalise, activate, drop out, add the residuals and write the two planes
-template <int VEC>
-__device__ __forceinline__ void tc_bn_apply_finish(const TcApplyArgs& p, TcApplyItem<VEC>& it) {
+// ... then normalise, activate, drop out, add the residuals and write the two planes.  The thread keeps its four
+// channels' statistics in registers across its rows: loading them per element was most of the kernel's L1 traffic
+// (16 sectors per request in the flat form) and a third of its instructions
+template <bool DROP>
+__device__ __forceinline__ void tc_bn_apply_finish(const TcApplyArgs& p, TcApplyItem<4>& it, const float* mean, const float* rstd,
+                                                   const float* beta) {
 #pragma unroll
-  for (int j = 0; j < VEC; j++) {
-    const int c = min(it.c0 + j, p.C - 1);  // columns C..ldo-1 of the last group are padding (their value is unused)
-    float y = (it.v[j] - p.mean[c]) * p.rstd[c] + p.beta[c];
+  for (int j = 0; j < 4; j++) {
+    float y = (it.v[j] - mean[j]) * rstd[j] + beta[j];
     y = act_fwd(y, p.act, p.alpha);
-    if (p.keep < 1.f) y = (philox_uniform(p.seed, p.stream_id, (uint64_t)(it.m * p.C + c)) < p.keep) ? y / p.keep : 0.f;
+    if (DROP) {
+      const int c = min(it.c0 + j, p.C - 1);  // columns C..ldo-1 of the last group are padding (their value is unused)
+      y = (philox_uniform(p.seed, p.stream_id, (uint64_t)(it.m * p.C + c)) < p.keep) ? y / p.keep : 0.f;
+    }
     it.v[j] = y + it.r[j];
   }
-  if (VEC == 4) {
-    if (p.hi) *reinterpret_cast<float4*>(p.hi + it.m * p.ldo + it.c0) = make_float4(it.v[0], it.v[1 % VEC], it.v[2 % VEC], it.v[3 % VEC]);
-    tc_store_operand4(p.lo, p.op_plane, p.op, it.m * p.ldo + it.c0, it.v[0], it.v[1 % VEC], it.v[2 % VEC], it.v[3 % VEC]);
-  } else {
-    if (p.hi) p.hi[it.m * p.ldo + it.c0] = it.v[0];
-    tc_store_operand(p.lo, p.op_plane, p.op, it.m * p.ldo + it.c0, it.v[0]);
-  }
+  if (p.hi) *reinterpret_cast<float4*>(p.hi + it.m * p.ldo + it.c0) = make_float4(it.v[0], it.v[1], it.v[2], it.v[3]);
+  tc_store_operand4(p.lo, p.op_plane, p.op, it.m * p.ldo + it.c0, it.v[0], it.v[1], it.v[2], it.v[3]);
 }
-// two items per thread and iteration, all loads issued before the first dependent instruction (four items measured
-// 35 % slower: the item array goes to local memory)
-template <int VEC>
-__global__ void __launch_bounds__(256) tc_bn_apply_kernel(const TcApplyArgs p) {
-  const int cq = (p.C + VEC - 1) / VEC;
-  const int64_t total = p.rows * cq;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  // item i = (row m, channel group cg); the walk advances (m, cg) by the constant stride with a carry instead of
-  // dividing a 64-bit index per item (the emulated 64-bit division was most of this kernel's instructions)
-  const int64_t dm = stride / cq;
-  const int dc = (int)(stride - dm * cq);
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t m = i / cq;
-  int cg = (int)(i - m * cq);
-  for (; i < total; i += 2 * stride) {
-    TcApplyItem<VEC> a, b;
-    const bool two = i + stride < total;
-    int64_t m2 = m + dm;
-    int cg2 = cg + dc;
-    if (cg2 >= cq) { cg2 -= cq; m2++; }
-    tc_bn_apply_load<VEC>(p, m, cg, a);
-    if (two) tc_bn_apply_load<VEC>(p, m2, cg2, b);
-    tc_bn_apply_finish<VEC>(p, a);
-    if (two) tc_bn_apply_finish<VEC>(p, b);
-    m = m2 + dm;
-    cg = cg2 + dc;
-    if (cg >= cq) { cg -= cq; m++; }
+// block = TX channel groups x 256 / TX row lanes; two rows per thread and iteration, all loads
+// issued before the first dependent instruction (four measured slower: the item array goes to local memory)
+template <int TX, bool DROP>
+__global__ void __launch_bounds__(256, 3) tc_bn_apply_kernel(const TcApplyArgs p, int rev) {
+  constexpr int TY = 256 / TX;
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  const int cg = blockIdx.x * TX + tx;
+  if (cg * 4 >= p.C) return;
+  const int64_t r1 = p.rows, ng = tc_sweep_groups(p.rows, 2 * TY);
+  float mean[4], rstd[4], beta[4];
+  tc_load_ch4(p.mean, cg * 4, p.C, mean);
+  tc_load_ch4(p.rstd, cg * 4, p.C, rstd);
+  tc_load_ch4(p.beta, cg * 4, p.C, beta);
+  for (int64_t gi = blockIdx.y; gi < ng; gi += gridDim.y) {
+    const int64_t r = tc_sweep_row(gi, ng, rev, 2 * TY) + ty;
+    if (r >= r1) continue;
+    TcApplyItem<4> a, b;
+    const bool two = r + TY < r1;
+    tc_bn_apply_load<4>(p, r, cg, a);
+    if (two) tc_bn_apply_load<4>(p, r + TY, cg, b);
+    tc_bn_apply_finish<DROP>(p, a, mean, rstd, beta);
+    if (two) tc_bn_apply_finish<DROP>(p, b, mean, rstd, beta);
   }
 }
 
@@ -382,19 +389,14 @@ __device__ __forceinline__ Gy4 tc_bn_gy4(const TcBnBwdArgs& p, int64_t m, int c0
   }
   return r;
 }
-__device__ __forceinline__ void tc_load_ch4(const float* __restrict__ src, int c0, int C, float (&v)[4]) {
-#pragma unroll
-  for (int k = 0; k < 4; k++) v[k] = (c0 + k < C) ? src[c0 + k] : 0.f;
-}
 
 template <int TX, bool DROP>
-__global__ void __launch_bounds__(256) tc_bn_bwd_reduce_v4_kernel(const TcBnBwdArgs p, int rows_per_block) {
+__global__ void __launch_bounds__(256) tc_bn_bwd_reduce_v4_kernel(const TcBnBwdArgs p, int rev) {
   constexpr int TY = 256 / TX;
   __shared__ float sh[4][TY][TX * 4 + 4];
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const int c0 = (blockIdx.x * TX + tx) * 4;
-  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
-  const int64_t r1 = min((int64_t)p.rows, r0 + rows_per_block);
+  const int64_t r1 = p.rows, ng = tc_sweep_groups(p.rows, 4 * TY);
   float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
   float mg[4] = {0.f, 0.f, 0.f, 0.f}, mz[4] = {0.f, 0.f, 0.f, 0.f};  // max |g_y|, max |zhat| (bound of |gz|, OP_F16X3)
   if (c0 < p.C) {
@@ -402,7 +404,8 @@ __global__ void __launch_bounds__(256) tc_bn_bwd_reduce_v4_kernel(const TcBnBwdA
     tc_load_ch4(p.mean, c0, p.C, mean);
     tc_load_ch4(p.rstd, c0, p.C, rstd);
     tc_load_ch4(p.beta, c0, p.C, beta);
-    for (int64_t r = r0 + ty; r < r1; r += 4 * TY) {
+    for (int64_t gi = blockIdx.y; gi < ng; gi += gridDim.y) {
+      const int64_t r = tc_sweep_row(gi, ng, rev, 4 * TY) + ty;
       float4 gv[4], zv[4];
 #pragma unroll
       for (int u = 0; u < 4; u++) {
@@ -467,7 +470,7 @@ __device__ __forceinline__ float4 tc_load4_shifted(const float* __restrict__ row
 
 // SHIFT: the source channels of a thread's 4 columns may start at any 4-byte phase (level kernels with f % 4 != 0)
 template <int TX, bool SHIFT, bool DROP>
-__global__ void __launch_bounds__(256, 2) tc_bn_bwd_apply_v4_kernel(const TcBnBwdArgs p, int rows_per_block) {
+__global__ void __launch_bounds__(256, 2) tc_bn_bwd_apply_v4_kernel(const TcBnBwdArgs p, int rev) {
   constexpr int TY = 256 / TX;
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const int j0 = (blockIdx.x * TX + tx) * 4;  // first gz column of this thread
@@ -482,10 +485,14 @@ __global__ void __launch_bounds__(256, 2) tc_bn_bwd_apply_v4_kernel(const TcBnBw
     nv = slot < p.R * p.nt ? min(4, min(p.ft, p.f - jt * p.ft) - n) : 0;  // a slot's tail columns are padding
     c0 = (p.R - 1 - slot / p.nt) * p.f + jt * p.ft + n;
   }
-  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
-  const int64_t r1 = min((int64_t)p.rows, r0 + rows_per_block);
+  const int64_t r1 = p.rows, ng = tc_sweep_groups(p.rows, 4 * TY);
   if (nv <= 0) {  // padding columns of the slot layout: zeros
-    for (int64_t r = r0 + ty; r < r1; r += TY) tc_store_gz4(p, r * p.ldgz + j0, 1.f, 0.f, 0.f, 0.f, 0.f);
+    for (int64_t gi = blockIdx.y; gi < ng; gi += gridDim.y) {
+      const int64_t r = tc_sweep_row(gi, ng, rev, 4 * TY) + ty;
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (r + u * TY < r1) tc_store_gz4(p, (r + u * TY) * p.ldgz + j0, 1.f, 0.f, 0.f, 0.f, 0.f);
+    }
     return;
   }
   float mean[4], rstd[4], beta[4], s1[4], s2[4];
@@ -495,7 +502,8 @@ __global__ void __launch_bounds__(256, 2) tc_bn_bwd_apply_v4_kernel(const TcBnBw
   tc_load_ch4(p.s1, c0, p.C, s1);
   tc_load_ch4(p.s2, c0, p.C, s2);
   const bool vec = !SHIFT || (c0 & 3) == 0;  // level slots with f % 4 == 0 keep the 16-byte alignment of the source row
-  for (int64_t r = r0 + ty; r < r1; r += 4 * TY) {
+  for (int64_t gi = blockIdx.y; gi < ng; gi += gridDim.y) {
+    const int64_t r = tc_sweep_row(gi, ng, rev, 4 * TY) + ty;
     float4 gv[4], zv[4];
 #pragma unroll
     for (int u = 0; u < 4; u++) {
@@ -535,20 +543,20 @@ template <int TX, int MODE>
 __global__ void __launch_bounds__(256) tc_resid_bwd_v4_kernel(const float* __restrict__ gout, int ldg, float* __restrict__ gsrc,
                                                               int lds, int Csrc, const int* __restrict__ lo,
                                                               const int* __restrict__ hi, int64_t rows, int accumulate,
-                                                              int rows_per_block, int step) {
+                                                              int rev, int step) {
   constexpr int TY = 256 / TX;
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const int c0 = (blockIdx.x * TX + tx) * 4;
   if (c0 >= Csrc) return;
-  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
-  const int64_t r1 = min(rows, r0 + rows_per_block);
+  const int64_t r1 = rows, ng = tc_sweep_groups(rows, 2 * TY);
   int jl[4] = {0, 0, 0, 0}, jh[4] = {0, 0, 0, 0};
   if (MODE == 1) {
 #pragma unroll
     for (int k = 0; k < 4; k++)
       if (c0 + k < Csrc) { jl[k] = lo[c0 + k]; jh[k] = hi[c0 + k]; }
   }
-  for (int64_t r = r0 + ty; r < r1; r += 2 * TY) {
+  for (int64_t gi = blockIdx.y; gi < ng; gi += gridDim.y) {
+    const int64_t r = tc_sweep_row(gi, ng, rev, 2 * TY) + ty;
     float4 acc[2], old[2];
 #pragma unroll
     for (int u = 0; u < 2; u++) {
