@@ -27,21 +27,6 @@ constexpr int GS_MAX_C = 64;
 __host__ __device__ inline int gs_gen_nweights(int C) { return (C + C / 2 + C / 4 + C / 8 + C / 4 + C / 2 + C) + 7; }
 __host__ __device__ inline int gs_disc_nweights(int C) { return C * C + C + C * C + C + C * (C / 2) + C / 2; }
 
-// sum_i a[i * sa] * b[i * sb], four independent accumulators: the per-pair work is a chain of short dot products, and a
-// single accumulator would serialise every one of them on the FMA latency
-__device__ __forceinline__ float gs_dot(const float* a, int sa, const float* b, int sb, int n) {
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int i = 0;
-  for (; i + 4 <= n; i += 4) {
-    s0 += a[i * sa] * b[i * sb];
-    s1 += a[(i + 1) * sa] * b[(i + 1) * sb];
-    s2 += a[(i + 2) * sa] * b[(i + 2) * sb];
-    s3 += a[(i + 3) * sa] * b[(i + 3) * sb];
-  }
-  for (; i < n; i++) s0 += a[i * sa] * b[i * sb];
-  return (s0 + s1) + (s2 + s3);
-}
-
 // ---- generator, one warp per spectrum -------------------------------------------------------------------------
 // nets [8][C]: net0 = input (already in place) .. net7 = output.  w: layer weights w[K] b, in layer order.
 __device__ __forceinline__ void gs_gen_forward(const float* __restrict__ w, float* nets, int C, int lane) {
@@ -55,8 +40,9 @@ __device__ __forceinline__ void gs_gen_forward(const float* __restrict__ w, floa
     const float* p2 = nets + (l > 0 ? l - 1 : 0) * C;
     float* cur = nets + (l + 1) * C;
     for (int c = lane; c < C; c += 32) {
+      float s = bias;
       const int t0 = max(0, left - c), t1 = min(k, C + left - c);
-      float s = bias + gs_dot(wl + t0, 1, p1 + c + t0 - left, 1, t1 - t0);
+      for (int t = t0; t < t1; t++) s += wl[t] * p1[c + t - left];
       if (l == 6) s = tanhf(s);
       else {
         s = fmaxf(s, 0.1f * s);
@@ -110,12 +96,16 @@ __device__ __forceinline__ void gs_gen_backward(const float* __restrict__ w, flo
     bsum = warp_sum(bsum);
     if (lane == 0) atomicAdd(&gw[woff[l - 1] + k], bsum);
     for (int t = lane; t < k; t += 32) {  // dW_l[t] = sum_c dpre[c] * in[c + t - left]
+      float s = 0.f;
       const int c0 = max(0, left - t), c1 = min(C, C + left - t);
-      atomicAdd(&gw[woff[l - 1] + t], gs_dot(dpre + c0, 1, in + c0 + t - left, 1, c1 - c0));
+      for (int c = c0; c < c1; c++) s += dpre[c] * in[c + t - left];
+      atomicAdd(&gw[woff[l - 1] + t], s);
     }
     for (int cp = lane; cp < C; cp += 32) {  // dL/dnet_{l-1}[c'] += sum_t w[t] * dpre[c' - t + left]
+      float s = 0.f;
       const int t0 = max(0, cp + left - (C - 1)), t1 = min(k, cp + left + 1);
-      Gin[cp] += gs_dot(wl + t0, 1, dpre + cp - t0 + left, -1, t1 - t0);
+      for (int t = t0; t < t1; t++) s += wl[t] * dpre[cp - t + left];
+      Gin[cp] += s;
     }
     __syncwarp();
   }
@@ -151,17 +141,21 @@ __device__ __forceinline__ GsDisc gs_disc_load(float* dst, const float* __restri
 __device__ __forceinline__ void gs_disc_forward(const GsDisc& d, float* v, float* out, int C, int lane) {
   const int H = C / 2;
   for (int j = lane; j < C; j += 32) {
-    const float s = d.b1[j] + gs_dot(v, 1, d.W1 + j, d.LW, C);
+    float s = d.b1[j];
+    for (int i = 0; i < C; i++) s += v[i] * d.W1[i * d.LW + j];
     v[C + j] = fmaxf(s, 0.1f * s);
   }
   __syncwarp();
   for (int j = lane; j < C; j += 32) {
-    const float s = d.b2[j] + gs_dot(v + C, 1, d.W2 + j, d.LW, C);
+    float s = d.b2[j];
+    for (int i = 0; i < C; i++) s += v[C + i] * d.W2[i * d.LW + j];
     v[2 * C + j] = fmaxf(s, 0.1f * s);
   }
   __syncwarp();
   for (int j = lane; j < H; j += 32) {
-    out[j] = d.b3[j] + gs_dot(v + 2 * C, 1, d.W3 + j, d.LH, C);
+    float s = d.b3[j];
+    for (int i = 0; i < C; i++) s += v[2 * C + i] * d.W3[i * d.LH + j];
+    out[j] = s;
   }
   __syncwarp();
 }
@@ -173,7 +167,9 @@ __device__ __forceinline__ void gs_disc_backward(const GsDisc& d, const float* v
   const float *xs = v, *h1 = v + C, *h2 = v + 2 * C;
   float *gW1 = gw, *gb1 = gW1 + C * C, *gW2 = gb1 + C, *gb2 = gW2 + C * C, *gW3 = gb2 + C, *gb3 = gW3 + C * H;
   for (int i = lane; i < C; i += 32) {
-    d2[i] = gs_dot(d.W3 + i * d.LH, 1, dout, 1, H) * (h2[i] > 0.f ? 1.f : 0.1f);
+    float s = 0.f;
+    for (int j = 0; j < H; j++) s += d.W3[i * d.LH + j] * dout[j];
+    d2[i] = s * (h2[i] > 0.f ? 1.f : 0.1f);
   }
   if (gw) {
     for (int j = lane; j < H; j += 32) {
@@ -183,7 +179,9 @@ __device__ __forceinline__ void gs_disc_backward(const GsDisc& d, const float* v
   }
   __syncwarp();
   for (int i = lane; i < C; i += 32) {
-    d1[i] = gs_dot(d.W2 + i * d.LW, 1, d2, 1, C) * (h1[i] > 0.f ? 1.f : 0.1f);
+    float s = 0.f;
+    for (int j = 0; j < C; j++) s += d.W2[i * d.LW + j] * d2[j];
+    d1[i] = s * (h1[i] > 0.f ? 1.f : 0.1f);
   }
   if (gw) {
     for (int j = lane; j < C; j += 32) {
@@ -194,7 +192,9 @@ __device__ __forceinline__ void gs_disc_backward(const GsDisc& d, const float* v
   __syncwarp();
   if (gin) {
     for (int i = lane; i < C; i += 32) {
-      gin[i] = gs_dot(d.W1 + i * d.LW, 1, d1, 1, C);
+      float s = 0.f;
+      for (int j = 0; j < C; j++) s += d.W1[i * d.LW + j] * d1[j];
+      gin[i] = s;
     }
   }
   if (gw) {

@@ -1016,22 +1016,10 @@ static int tc_forward(hyp_model& m, const float* x, int64_t B, bool training, bo
       p.pat1 = L.res[1].pattern == 2 ? 2 : (L.res[1].pattern == 3 && L.res[1].step == 2 ? 3 : 0);
       p.res1_op = reinterpret_cast<const uint16_t*>(tc_plane1(m, L.res[1].src)); p.res1_plane = rs.plane_elems;
     }
-    const double bytes = 4.0 * rows * L.Cout * (3 + L.res.size());
-    // (a 2-D row-lane form of this kernel measured 15 % slower: the flat float4 walk keeps more rows in flight)
-    {
-      const EwGrid ga = ew_grid2(L.Cout, rows);
-      const bool drop = p.keep < 1.f;
-#define TC_FWD_APPLY_LAUNCH(TXV)                                                                        \
-  do {                                                                                                  \
-    if (drop) tc_bn_apply_kernel<TXV, true><<<dim3(ga.gx, ga.rblocks), 256, 0, st>>>(p, tc_zigzag());   \
-    else tc_bn_apply_kernel<TXV, false><<<dim3(ga.gx, ga.rblocks), 256, 0, st>>>(p, tc_zigzag());       \
-  } while (0)
-      g_prof.begin(st, "tc_bn_apply_kernel", 0.0, bytes);
-      if (ga.TX == 32) TC_FWD_APPLY_LAUNCH(32); else if (ga.TX == 16) TC_FWD_APPLY_LAUNCH(16); else TC_FWD_APPLY_LAUNCH(8);
-      g_prof.end(st);
-      HYP_LAUNCHED();
-#undef TC_FWD_APPLY_LAUNCH
-    }
+    const double bytes = 4.0 * rows * L.Cout * ((p.hi ? 3 : 2) + L.res.size());
+    // (a 2-D row-lane form with the channel statistics held in registers measured 7-15 % slower, twice: the flat float4
+    // walk keeps more rows in flight, and the kernel is bound by memory latency, not by its instruction count)
+    TC_PROF("tc_bn_apply_kernel", bytes, (tc_bn_apply_kernel<4><<<tc_grid(rows * cdiv(L.Cout, 4)), 256, 0, st>>>(p)));
     if (L.lrn) {
       TC_PROF("tc_lrn_fwd_kernel", 16.0 * rows * L.Cout,
               (tc_lrn_fwd_kernel<<<tc_grid(rows * 32), 256, 8 * L.Cout * sizeof(float), st>>>(

@@ -256,47 +256,52 @@ __device__ __forceinline__ void tc_bn_apply_load(const TcApplyArgs& p, int64_t m
   if (p.has0) tc_bn_apply_residual<VEC>(p.res0, p.res0_op, p.res0_plane, p.idx0, p.ld0, p.C, p.pat0, it);
   if (p.has1) tc_bn_apply_residual<VEC>(p.res1, p.res1_op, p.res1_plane, p.idx1, p.ld1, p.C, p.pat1, it);
 }
-// ... then normalise, activate, drop out, add the residuals and write the two planes.  The thread keeps its four
-// channels' statistics in registers across its rows: loading them per element was most of the kernel's L1 traffic
-// (16 sectors per request in the flat form) and a third of its instructions
-template <bool DROP>
-__device__ __forceinline__ void tc_bn_apply_finish(const TcApplyArgs& p, TcApplyItem<4>& it, const float* mean, const float* rstd,
-                                                   const float* beta) {
+// ... then normalise, activate, drop out, add the residuals and write the two planes
+template <int VEC>
+__device__ __forceinline__ void tc_bn_apply_finish(const TcApplyArgs& p, TcApplyItem<VEC>& it) {
 #pragma unroll
-  for (int j = 0; j < 4; j++) {
-    float y = (it.v[j] - mean[j]) * rstd[j] + beta[j];
+  for (int j = 0; j < VEC; j++) {
+    const int c = min(it.c0 + j, p.C - 1);  // columns C..ldo-1 of the last group are padding (their value is unused)
+    float y = (it.v[j] - p.mean[c]) * p.rstd[c] + p.beta[c];
     y = act_fwd(y, p.act, p.alpha);
-    if (DROP) {
-      const int c = min(it.c0 + j, p.C - 1);  // columns C..ldo-1 of the last group are padding (their value is unused)
-      y = (philox_uniform(p.seed, p.stream_id, (uint64_t)(it.m * p.C + c)) < p.keep) ? y / p.keep : 0.f;
-    }
+    if (p.keep < 1.f) y = (philox_uniform(p.seed, p.stream_id, (uint64_t)(it.m * p.C + c)) < p.keep) ? y / p.keep : 0.f;
     it.v[j] = y + it.r[j];
   }
-  if (p.hi) *reinterpret_cast<float4*>(p.hi + it.m * p.ldo + it.c0) = make_float4(it.v[0], it.v[1], it.v[2], it.v[3]);
-  tc_store_operand4(p.lo, p.op_plane, p.op, it.m * p.ldo + it.c0, it.v[0], it.v[1], it.v[2], it.v[3]);
+  if (VEC == 4) {
+    if (p.hi) *reinterpret_cast<float4*>(p.hi + it.m * p.ldo + it.c0) = make_float4(it.v[0], it.v[1 % VEC], it.v[2 % VEC], it.v[3 % VEC]);
+    tc_store_operand4(p.lo, p.op_plane, p.op, it.m * p.ldo + it.c0, it.v[0], it.v[1 % VEC], it.v[2 % VEC], it.v[3 % VEC]);
+  } else {
+    if (p.hi) p.hi[it.m * p.ldo + it.c0] = it.v[0];
+    tc_store_operand(p.lo, p.op_plane, p.op, it.m * p.ldo + it.c0, it.v[0]);
+  }
 }
-// block = TX channel groups x 256 / TX row lanes; two rows per thread and iteration, all loads
-// issued before the first dependent instruction (four measured slower: the item array goes to local memory)
-template <int TX, bool DROP>
-__global__ void __launch_bounds__(256, 3) tc_bn_apply_kernel(const TcApplyArgs p, int rev) {
-  constexpr int TY = 256 / TX;
-  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
-  const int cg = blockIdx.x * TX + tx;
-  if (cg * 4 >= p.C) return;
-  const int64_t r1 = p.rows, ng = tc_sweep_groups(p.rows, 2 * TY);
-  float mean[4], rstd[4], beta[4];
-  tc_load_ch4(p.mean, cg * 4, p.C, mean);
-  tc_load_ch4(p.rstd, cg * 4, p.C, rstd);
-  tc_load_ch4(p.beta, cg * 4, p.C, beta);
-  for (int64_t gi = blockIdx.y; gi < ng; gi += gridDim.y) {
-    const int64_t r = tc_sweep_row(gi, ng, rev, 2 * TY) + ty;
-    if (r >= r1) continue;
-    TcApplyItem<4> a, b;
-    const bool two = r + TY < r1;
-    tc_bn_apply_load<4>(p, r, cg, a);
-    if (two) tc_bn_apply_load<4>(p, r + TY, cg, b);
-    tc_bn_apply_finish<DROP>(p, a, mean, rstd, beta);
-    if (two) tc_bn_apply_finish<DROP>(p, b, mean, rstd, beta);
+// two items per thread and iteration, all loads issued before the first dependent instruction (four items measured
+// 35 % slower: the item array goes to local memory)
+template <int VEC>
+__global__ void __launch_bounds__(256) tc_bn_apply_kernel(const TcApplyArgs p) {
+  const int cq = (p.C + VEC - 1) / VEC;
+  const int64_t total = p.rows * cq;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  // item i = (row m, channel group cg); the walk advances (m, cg) by the constant stride with a carry instead of
+  // dividing a 64-bit index per item (the emulated 64-bit division was most of this kernel's instructions)
+  const int64_t dm = stride / cq;
+  const int dc = (int)(stride - dm * cq);
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t m = i / cq;
+  int cg = (int)(i - m * cq);
+  for (; i < total; i += 2 * stride) {
+    TcApplyItem<VEC> a, b;
+    const bool two = i + stride < total;
+    int64_t m2 = m + dm;
+    int cg2 = cg + dc;
+    if (cg2 >= cq) { cg2 -= cq; m2++; }
+    tc_bn_apply_load<VEC>(p, m, cg, a);
+    if (two) tc_bn_apply_load<VEC>(p, m2, cg2, b);
+    tc_bn_apply_finish<VEC>(p, a);
+    if (two) tc_bn_apply_finish<VEC>(p, b);
+    m = m2 + dm;
+    cg = cg2 + dc;
+    if (cg >= cq) { cg -= cq; m++; }
   }
 }
 
