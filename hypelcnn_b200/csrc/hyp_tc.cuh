@@ -43,7 +43,7 @@ constexpr int TC_MAX_BP = 8;               // distinct MMA widths per tile
 constexpr int TC_MAX_SEGS = 128;           // segments per tile (held in registers across a warp's lanes)
 constexpr int TC_MAX_CB = 8;               // column blocks per tile           // accumulator columns per tile
 constexpr int TC_SMEM_LIMIT = 226 * 1024;
-// after the stage ring: barriers + TMEM slot (256 B), statistics partials [2][4][256] floats, epilogue staging
+// after the stage ring: epilogue staging, statistics partials [2][4][256] floats, barriers + TMEM slot (256 B)
 // [8 warps][32 rows][20 floats]
 constexpr int TC_SMEM_FIXED = 256 + 2 * 4 * TC_MAX_COLS * 4 + TC_EPI_WARPS * 32 * 20 * 4;
 
@@ -112,6 +112,10 @@ struct TcParams {
   int32_t stages;
   int32_t ntiles;     // tiles of this launch (multiple of the CTA group size)
   unsigned long long* timing;  // nullable: [CTA][8] cycle counters (HYP_TC_TIMING diagnostics)
+  int32_t out_cols;   // extent of the 2-D view behind tma_out
+  int64_t out_rows;
+  int32_t tma_out;    // 1: tiles with one column block hand their 32 x 16 slabs to the TMA unit through the third tensor
+                      // map (a 2-D fp32 view of `out`): plain tile store for EPI_STORE, f32 add reduction for EPI_ATOMIC
 };
 
 // b_rows = B rows held by ONE CTA per stage and plane
@@ -391,7 +395,8 @@ constexpr int TC_STAGE_FLOATS = 32 * TC_STAGE_LD;          // per epilogue warp
 
 template <bool MN, int CG, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmO, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // swizzle atoms are 1024-byte aligned
@@ -402,10 +407,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int mnb = kbe;                          // MN-major boxes: mnb columns x kbe rows (32 x 32 fp32, 64 x 64 16-bit)
   const uint32_t mn_box_bytes = (uint32_t)kbe * 128u;
   const uint32_t stage_bytes = npl * (TC_PLANE_A + b_plane);
-  const uint32_t bar_base = base + (uint32_t)p.stages * stage_bytes;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (size_t)p.stages * stage_bytes + 192);
-  float* s_part = reinterpret_cast<float*>(gen + (size_t)p.stages * stage_bytes + 256);  // [2][4][TC_MAX_COLS]
-  float* s_stage = s_part + 2 * 4 * TC_MAX_COLS;                                         // [8 warps][32][TC_STAGE_LD]
+  // after the ring: epilogue staging [8 warps][2560 B] (512-byte aligned: the TMA slabs are SWIZZLE_64B boxes), the
+  // statistics partials [2][4][TC_MAX_COLS], then barriers + TMEM slot (256 B)
+  const uint32_t fixed_head = (uint32_t)(TC_EPI_WARPS * TC_STAGE_FLOATS * 4 + 2 * 4 * TC_MAX_COLS * 4);
+  const uint32_t bar_base = base + (uint32_t)p.stages * stage_bytes + fixed_head;
+  float* s_stage = reinterpret_cast<float*>(gen + (size_t)p.stages * stage_bytes);       // [8 warps][32][TC_STAGE_LD]
+  float* s_part = s_stage + TC_EPI_WARPS * TC_STAGE_FLOATS;                              // [2][4][TC_MAX_COLS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (size_t)p.stages * stage_bytes + fixed_head + 192);
   auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(p.stages + s); };
   auto tfull_bar = [&](int b) { return bar_base + 8u * (uint32_t)(2 * p.stages + b); };
@@ -424,6 +432,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    if (p.tma_out) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmO)) : "memory");
     for (int s = 0; s < p.stages; s++) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -685,6 +694,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         one_width = __shfl_sync(0xffffffffu, my_width, 0);
         one_off = __shfl_sync(0xffffffffu, my_off, 0);
       }
+      // TMA slabs: (column, row) of the tile's first element in the 2-D view of `out`
+      //      (rows past m_valid and columns past the block's width must fall outside the view, where the unit clips
+      //      them; phantom tiles and odd tiles in the middle of a tensor keep the plain path)
+      bool use_tma = false;
+      int tma_row0 = 0, tma_col0 = 0;
+      if (p.tma_out != 0 && ncb == 1 && EPI != EPI_ACCUM && m_valid > 0) {
+        tma_row0 = (int)(one_off / ld_out);
+        tma_col0 = (int)(one_off - (int64_t)tma_row0 * ld_out);
+        use_tma = (m_valid == TC_BM || tma_row0 + m_valid == p.out_rows) &&
+                  ((one_width & 15) == 0 || tma_col0 + one_width == p.out_cols) && one_tcol == 0;
+      }
+      const uint32_t st_u32 = smem_u32(st);
       auto store_slab = [&](const float* a16, const int c0) {
           // column block holding the slab: blocks are listed by increasing tcol (one block: uniform registers)
           int cb_tcol = one_tcol, cb_width = one_width;
@@ -700,16 +721,60 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             return;
           }
           if (c0 >= cb_tcol + cb_width) return;  // padding columns of the block
+          if (p.tma_out) {  // the TMA unit may still be reading the staging rows of this warp's previous slab
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+          }
+          const int ocol = c0 + c4 - cb_tcol;             // output column of this lane's 4 values
+          float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+          if (use_tma) {
+            // ---- the slab leaves through the TMA unit: dense 32 x 64-byte rows in the SWIZZLE_64B pattern (16-byte
+            //      chunk index ^ (row >> 1) & 3: conflict-free for the row-per-lane writes and for the statistics
+            //      reads below), one tile store / f32 add reduction per slab.  The warp never waits on a global store;
+            //      rows and columns outside the tensor are clipped by the unit.
+            const uint32_t sw = ((uint32_t)lane >> 1) & 3u;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_u32 + (uint32_t)lane * 64u + (((uint32_t)k ^ sw) << 4)),
+                           "f"(a16[4 * k] * oscale), "f"(a16[4 * k + 1] * oscale), "f"(a16[4 * k + 2] * oscale),
+                           "f"(a16[4 * k + 3] * oscale) : "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              const int tc = tma_col0 + (c0 - cb_tcol), tr = tma_row0 + q * 32;
+              if (EPI == EPI_ATOMIC)
+                asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
+                             ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(tc), "r"(tr), "r"(st_u32) : "memory");
+              else
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                             ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(tc), "r"(tr), "r"(st_u32) : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            if (EPI == EPI_STORE && p.stats) {
+              const uint32_t rsw = ((uint32_t)r_lane >> 1) & 3u;  // rows i * 8 + r_lane share (row >> 1) & 3
+              const int nval = min(4, cb_width - ocol);
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                float4 v4;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v4.x), "=f"(v4.y), "=f"(v4.z), "=f"(v4.w)
+                             : "r"(st_u32 + (uint32_t)(i * 8 + r_lane) * 64u + ((((uint32_t)lane & 3u) ^ rsw) << 4)) : "memory");
+                if (all_rows || q * 32 + i * 8 + r_lane < m_valid) {
+                  const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                  for (int t = 0; t < 4; t++)
+                    if (t < nval) { s1[t] += vv[t]; s2[t] += vv[t] * vv[t]; }
+                }
+              }
+            }
+          } else {
 #pragma unroll
           for (int k = 0; k < 4; k++)
             *reinterpret_cast<float4*>(st + lane * TC_STAGE_LD + 4 * k) =
                 make_float4(a16[4 * k] * oscale, a16[4 * k + 1] * oscale,
                             a16[4 * k + 2] * oscale, a16[4 * k + 3] * oscale);
           __syncwarp();
-          const int ocol = c0 + c4 - cb_tcol;             // output column of this lane's 4 values
           float* const obase = p.out + cb_off + (int64_t)(q * 32 + r_lane) * ld_out + ocol;
           const int64_t ostep = (int64_t)8 * ld_out;     // rows advance by 8 per pass
-          float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
           // warp-uniform fast path: whole slab valid, every lane's 4 values 16-byte aligned in the output
           const bool fast = all_rows && (c0 + 16 <= cb_tcol + cb_width) && ((ld_out & 3) == 0) &&
                             ((reinterpret_cast<uintptr_t>(p.out + cb_off + (c0 - cb_tcol)) & 15) == 0);
@@ -756,6 +821,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
               }
             }
+          }
           }
           if (EPI == EPI_STORE && p.stats) {
             // the 8 lanes that share this lane's 4 columns (lane >> 2 = row lane) hold 8 partial sums each
@@ -905,6 +971,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (p.timing) tm_tiles++;
     }
+    // the staging rows must outlive the TMA unit's reads (global completion is the kernel boundary's business)
+    if (p.tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     if (p.timing && warp == TC_EPI_WARP0 && lane == 0) {
       p.timing[blockIdx.x * 8 + 4] = (unsigned long long)tm_wait_tfull;
       p.timing[blockIdx.x * 8 + 5] = (unsigned long long)tm_store;
@@ -967,6 +1035,20 @@ inline int make_map(CUtensorMap* map, const void* base, const uint64_t dims[4], 
   return HYP_OK;
 }
 
+// 2-D fp32 view of a GEMM output for the epilogue's TMA slabs: `cols` valid columns (the unit clips what lies beyond),
+// rows `ld` floats apart, boxes of 32 rows x 16 columns in the SWIZZLE_64B smem pattern
+inline int make_out_map(CUtensorMap* map, const float* base, uint64_t cols, uint64_t rows, uint64_t ld) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail(HYP_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  if ((ld * 4) % 16 || (reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(HYP_E_INVALID, "output tensor map: rows are not 16-byte aligned");
+  cuuint64_t gd[2] = {cols, rows}, gs[1] = {ld * 4};
+  cuuint32_t bx[2] = {16, 32}, es[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(HYP_E_CUDA, "cuTensorMapEncodeTiled (output map) failed with CUresult " + std::to_string((int)r));
+  return HYP_OK;
+}
+
 constexpr int TC_DEFAULT_CHUNK_KB = 8;  // 96 MMAs per TMEM chunk: error ~2e-6 of max|D|; 12 already fails the 3e-6 building-block test
 
 static thread_local const char* g_tc_timing_tag = nullptr;  // label of the next launch in HYP_TC_TIMING output
@@ -1012,17 +1094,22 @@ inline int tc_sm_count() {
 
 // CG = 2: tiles 2i, 2i+1 form a pair sharing its segment list (ntiles even); tmB boxes hold bn/2 rows
 template <bool MN, int CG, int EPI>
-inline int launch_tc_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, int ntiles, cudaStream_t st);
+inline int launch_tc_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, int ntiles, cudaStream_t st,
+                         const CUtensorMap* tmO);
 
+// tmO: optional 2-D view of p.out (make_out_map); with it, tiles of one column block store through the TMA unit
 template <bool MN, int CG>
-inline int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, int ntiles, cudaStream_t st) {
-  if (p.epi == EPI_STORE) return launch_tc_epi<MN, CG, EPI_STORE>(tmA, tmB, p, ntiles, st);
-  if (p.epi == EPI_ACCUM) return launch_tc_epi<MN, CG, EPI_ACCUM>(tmA, tmB, p, ntiles, st);
-  return launch_tc_epi<MN, CG, EPI_ATOMIC>(tmA, tmB, p, ntiles, st);
+inline int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, int ntiles, cudaStream_t st,
+                     const CUtensorMap* tmO = nullptr) {
+  if (p.epi == EPI_STORE) return launch_tc_epi<MN, CG, EPI_STORE>(tmA, tmB, p, ntiles, st, tmO);
+  if (p.epi == EPI_ACCUM) return launch_tc_epi<MN, CG, EPI_ACCUM>(tmA, tmB, p, ntiles, st, nullptr);
+  return launch_tc_epi<MN, CG, EPI_ATOMIC>(tmA, tmB, p, ntiles, st, tmO);
 }
 
 template <bool MN, int CG, int EPI>
-inline int launch_tc_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, int ntiles, cudaStream_t st) {
+inline int launch_tc_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, int ntiles, cudaStream_t st,
+                         const CUtensorMap* tmO) {
+  p.tma_out = tmO ? 1 : 0;
   if (ntiles <= 0) return HYP_OK;
   if (ntiles % CG) return fail(HYP_E_INVALID, "tc gemm: tile count is not a multiple of the CTA group size");
   if (p.b_rows % (8 * CG)) return fail(HYP_E_INVALID, "tc gemm: B rows must be a multiple of 8 per CTA");
@@ -1060,7 +1147,7 @@ inline int launch_tc_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParam
     HYP_CUDA(cudaMemsetAsync(tbuf, 0, (size_t)groups * CG * 8 * sizeof(unsigned long long), st));
     p.timing = tbuf;
   }
-  HYP_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<MN, CG, EPI>, tmA, tmB, p));
+  HYP_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<MN, CG, EPI>, tmA, tmB, tmO ? *tmO : tmA, p));
   HYP_LAUNCHED();
   if (timing_on) {
     std::vector<unsigned long long> h((size_t)groups * CG * 8);

@@ -33,6 +33,10 @@ struct TcTensor {
 
 struct TcLaunch {
   CUtensorMap tmA, tmB;
+  CUtensorMap tmO;        // 2-D view of the output for the epilogue's TMA slabs (make_out_map)
+  bool tma_out = false;
+  int out_cols = 0;
+  int64_t out_rows = 0;
   int tile0 = 0, ntiles = 0;
   int b_rows = 0, bn = 0;
   bool mn = false;
@@ -338,6 +342,14 @@ static void finish_launch(PlanBuf& pb, TcLaunch& l) {
   schedule_tiles(pb.tiles, (size_t)l.tile0, pb.segs, l.cg, l.windowed || !l.mn);
   l.ntiles = (int)pb.tiles.size() - l.tile0;
 }
+// the launch's output as a 2-D fp32 view [rows][ld] with `cols` valid columns: its one-column-block tiles store
+// through the TMA unit (tc_gemm_kernel, store_slab)
+static int out_view(TcLaunch& l, const float* base, int cols, int64_t rows, int ld) {
+  const int rc = make_out_map(&l.tmO, base, (uint64_t)cols, (uint64_t)rows, (uint64_t)ld);
+  if (rc) return rc;
+  l.tma_out = true; l.out_cols = cols; l.out_rows = rows;
+  return HYP_OK;
+}
 
 // wgrad (MN-major) launches run as CTA pairs over two adjacent 128-row tiles of the M side when their count is even
 // (the pair shares its gz columns); B rows reserved per stage: boxes of kb columns covering n / cg columns, per CTA
@@ -536,6 +548,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
           close_pair_run(pb.tiles, run, nrt * 128);
         }
       finish_launch(pb, T.fwd);
+      if ((rc = out_view(T.fwd, reinterpret_cast<const float*>(m.ws + T.z_off), Cout, rows_out, tout.Cp))) return rc;
       T.stats_rows = nrt;
       // ---------------- dgrad ----------------
       if (need_dgrad) {
@@ -566,6 +579,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
             close_pair_run(pb.tiles, run, nrt * 128);
           }
         finish_launch(pb, T.dg);
+        if ((rc = out_view(T.dg, tc_grad(m, L.in_t), Cin, rows_in, tin.Cp))) return rc;
       }
       // ---------------- wgrad ----------------
       {
@@ -710,6 +724,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
             close_pair_run(pb.tiles, run, nbt * 128);
           }
         finish_launch(pb, T.dg);
+        if ((rc = out_view(T.dg, tc_grad(m, L.in_t), Cin, rows_in, tin.Cp))) return rc;
       }
       // ---------------- wgrad ----------------
       {
@@ -818,6 +833,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
           close_pair_run(pb.tiles, run, nbt * 128);
         }
       finish_launch(pb, T.fwd);
+      if ((rc = out_view(T.fwd, reinterpret_cast<const float*>(m.ws + T.z_off), Cout, rows_out, tout.Cp))) return rc;
       T.stats_rows = nbt;
       // ---------------- dgrad ----------------
       if (need_dgrad) {
@@ -851,6 +867,7 @@ static int tc_plan(hyp_model& m, int64_t B) {
               close_pair_run(pb.tiles, run, nbt * 128);
             }
         finish_launch(pb, T.dg);
+        if ((rc = out_view(T.dg, tc_grad(m, L.in_t), Ct, rows_in, tin.Cp))) return rc;
       }
       // ---------------- wgrad ----------------
       {
@@ -930,10 +947,13 @@ static int tc_run(hyp_model& m, const TcLaunch& l, float* out, float* stats, int
   if (timing_on && !per_layer && scope) full += std::string("/") + scope;
   g_tc_timing_tag = full.c_str();
   g_prof.begin(st, full.c_str(), flops, 0.0);
-  const int rc = l.mn ? (l.cg == 2 ? launch_tc<true, 2>(l.tmA, l.tmB, p, l.ntiles, st)
-                                   : launch_tc<true, 1>(l.tmA, l.tmB, p, l.ntiles, st))
-                      : (l.cg == 2 ? launch_tc<false, 2>(l.tmA, l.tmB, p, l.ntiles, st)
-                                   : launch_tc<false, 1>(l.tmA, l.tmB, p, l.ntiles, st));
+  static const bool tma_off = getenv("HYP_TC_TMA_STORE") && getenv("HYP_TC_TMA_STORE")[0] == '0';  // diagnostic: plain stores
+  const CUtensorMap* tmO = (l.tma_out && !tma_off && epi != EPI_ACCUM) ? &l.tmO : nullptr;
+  p.out_cols = l.out_cols; p.out_rows = l.out_rows;
+  const int rc = l.mn ? (l.cg == 2 ? launch_tc<true, 2>(l.tmA, l.tmB, p, l.ntiles, st, tmO)
+                                   : launch_tc<true, 1>(l.tmA, l.tmB, p, l.ntiles, st, tmO))
+                      : (l.cg == 2 ? launch_tc<false, 2>(l.tmA, l.tmB, p, l.ntiles, st, tmO)
+                                   : launch_tc<false, 1>(l.tmA, l.tmB, p, l.ntiles, st, tmO));
   g_prof.end(st);
   return rc;
 }
