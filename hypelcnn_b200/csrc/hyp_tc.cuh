@@ -114,8 +114,8 @@ struct TcParams {
   unsigned long long* timing;  // nullable: [CTA][8] cycle counters (HYP_TC_TIMING diagnostics)
   int32_t out_cols;   // extent of the 2-D view behind tma_out
   int64_t out_rows;
-  int32_t tma_out;    // 1: tiles with one column block hand their 32 x 16 slabs to the TMA unit through the third tensor
-                      // map (a 2-D fp32 view of `out`): plain tile store for EPI_STORE, f32 add reduction for EPI_ATOMIC
+  int32_t tma_out;    // 1 (EPI_ATOMIC only): tiles with one column block hand their 32 x 16 slabs to the TMA unit as f32
+                      // add reductions through the third tensor map (a 2-D fp32 view of `out`)
 };
 
 // b_rows = B rows held by ONE CTA per stage and plane
@@ -699,7 +699,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       //      them; phantom tiles and odd tiles in the middle of a tensor keep the plain path)
       bool use_tma = false;
       int tma_row0 = 0, tma_col0 = 0;
-      if (p.tma_out != 0 && ncb == 1 && EPI != EPI_ACCUM && m_valid > 0) {
+      if (p.tma_out != 0 && ncb == 1 && EPI == EPI_ATOMIC && m_valid > 0) {
         tma_row0 = (int)(one_off / ld_out);
         tma_col0 = (int)(one_off - (int64_t)tma_row0 * ld_out);
         use_tma = (m_valid == TC_BM || tma_row0 + m_valid == p.out_rows) &&
@@ -729,9 +729,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
           if (use_tma) {
             // ---- the slab leaves through the TMA unit: dense 32 x 64-byte rows in the SWIZZLE_64B pattern (16-byte
-            //      chunk index ^ (row >> 1) & 3: conflict-free for the row-per-lane writes and for the statistics
-            //      reads below), one tile store / f32 add reduction per slab.  The warp never waits on a global store;
-            //      rows and columns outside the tensor are clipped by the unit.
+            //      chunk index ^ (row >> 1) & 3: conflict-free for the row-per-lane writes), one f32 add reduction
+            //      (cp.reduce.async.bulk.tensor) per slab.  The warp never waits on a global atomic; rows and columns
+            //      outside the tensor are clipped by the unit.
             const uint32_t sw = ((uint32_t)lane >> 1) & 3u;
 #pragma unroll
             for (int k = 0; k < 4; k++)
@@ -742,29 +742,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) {
               const int tc = tma_col0 + (c0 - cb_tcol), tr = tma_row0 + q * 32;
-              if (EPI == EPI_ATOMIC)
-                asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
-                             ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(tc), "r"(tr), "r"(st_u32) : "memory");
-              else
-                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
-                             ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(tc), "r"(tr), "r"(st_u32) : "memory");
+              asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
+                           ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(tc), "r"(tr), "r"(st_u32) : "memory");
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-            if (EPI == EPI_STORE && p.stats) {
-              const uint32_t rsw = ((uint32_t)r_lane >> 1) & 3u;  // rows i * 8 + r_lane share (row >> 1) & 3
-              const int nval = min(4, cb_width - ocol);
-#pragma unroll
-              for (int i = 0; i < 4; i++) {
-                float4 v4;
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v4.x), "=f"(v4.y), "=f"(v4.z), "=f"(v4.w)
-                             : "r"(st_u32 + (uint32_t)(i * 8 + r_lane) * 64u + ((((uint32_t)lane & 3u) ^ rsw) << 4)) : "memory");
-                if (all_rows || q * 32 + i * 8 + r_lane < m_valid) {
-                  const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-                  for (int t = 0; t < 4; t++)
-                    if (t < nval) { s1[t] += vv[t]; s2[t] += vv[t] * vv[t]; }
-                }
-              }
             }
           } else {
 #pragma unroll
@@ -847,6 +827,72 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           __syncwarp();  // the staging rows are rewritten by the next slab
       };
+      // ---- 32 accumulator columns of the lane's row at once, for tiles with one column block: the warp stages 16 rows x
+      //      128 bytes per pass and writes FOUR ROWS x 128 BYTES per instruction -- whole lines.  The 16-column slabs
+      //      above touch eight half lines per instruction, and the store path's cost follows the number of lines an
+      //      instruction touches, not its bytes (a lane-per-row 32-byte store form measured slower still).
+      //      Returns false when the block is not whole (edge tiles, odd widths): the caller falls back to two slabs.
+      auto store_block32 = [&](const float* a32, const int c0) -> bool {
+        if (ncb != 1 || use_tma || !all_rows || c0 < one_tcol || c0 + 32 > one_tcol + one_width || (ld_out & 3) != 0 ||
+            (reinterpret_cast<uintptr_t>(p.out + one_off + (c0 - one_tcol)) & 15) != 0)
+          return false;
+        if (p.tma_out) {
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+        }
+        constexpr int LD32 = 36;  // floats per staged row (32 + pad: conflict-free 16-byte accesses both ways)
+        const int r4 = lane >> 3, c8 = (lane & 7) * 4;
+        float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          if ((lane >> 4) == h) {
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+              *reinterpret_cast<float4*>(st + (lane & 15) * LD32 + 4 * k) =
+                  make_float4(a32[4 * k] * oscale, a32[4 * k + 1] * oscale, a32[4 * k + 2] * oscale, a32[4 * k + 3] * oscale);
+          }
+          __syncwarp();
+          float* const obase = p.out + one_off + (int64_t)(q * 32 + h * 16 + r4) * ld_out + (c0 - one_tcol) + c8;
+          const int64_t ostep = (int64_t)4 * ld_out;
+          float4 v[4];
+#pragma unroll
+          for (int i = 0; i < 4; i++) v[i] = *reinterpret_cast<const float4*>(st + (i * 4 + r4) * LD32 + c8);
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            if (EPI == EPI_ACCUM) {
+              const float4 o = *reinterpret_cast<const float4*>(obase + i * ostep);
+              v[i].x += o.x; v[i].y += o.y; v[i].z += o.z; v[i].w += o.w;
+            }
+            if (EPI == EPI_ATOMIC) atomicAdd(reinterpret_cast<float4*>(obase + i * ostep), v[i]);
+            else *reinterpret_cast<float4*>(obase + i * ostep) = v[i];
+            if (EPI == EPI_STORE) {
+              s1[0] += v[i].x; s1[1] += v[i].y; s1[2] += v[i].z; s1[3] += v[i].w;
+              s2[0] += v[i].x * v[i].x; s2[1] += v[i].y * v[i].y; s2[2] += v[i].z * v[i].z; s2[3] += v[i].w * v[i].w;
+            }
+          }
+          __syncwarp();  // the staging rows are rewritten by the next pass
+        }
+        if (EPI == EPI_STORE && p.stats) {
+          // the 4 lanes that share this lane's 4 columns (lane >> 3 = row lane) hold 8 partial sums each; a halving
+          // butterfly leaves each of them with TWO fully reduced values
+          const bool u16 = (lane & 16) != 0, u8 = (lane & 8) != 0;
+          float w4[4], w2[2];
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const float keep = u16 ? s2[k] : s1[k], send = u16 ? s1[k] : s2[k];
+            w4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+          }
+#pragma unroll
+          for (int k = 0; k < 2; k++) {
+            const float keep = u8 ? w4[2 + k] : w4[k], send = u8 ? w4[k] : w4[2 + k];
+            w2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
+          float* sp = s_part + ((u16 ? 1 : 0) * 4 + q) * TC_MAX_COLS + c0 + c8 + (u8 ? 2 : 0);
+          sp[0] = w2[0];
+          sp[1] = w2[1];
+        }
+        return true;
+      };
       const int nchunks = (total_kb + CH - 1) / CH;
       if (nchunks == 1) {
         // ---- single-chunk tiles (K <= chunk_kb blocks: the 1x1 convolutions): straight from TMEM to the slabs, 32
@@ -892,8 +938,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < 32; j++) v[j] = (tc0 + j < n_c) ? v[j] : 0.f;
             }
-            if (tc0 < n_cols) store_slab(v, tc0);
-            if (tc0 + 16 < n_cols) store_slab(v + 16, tc0 + 16);
+            if (!store_block32(v, tc0)) {
+              if (tc0 < n_cols) store_slab(v, tc0);
+              if (tc0 + 16 < n_cols) store_slab(v + 16, tc0 + 16);
+            }
           }
         }
         if (p.timing) tm_store += clock64() - t0;
@@ -943,8 +991,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int g = 0; g < 4; g++) {
         const int tc0 = cbase + g * 32;
         if (g * 32 >= hw || tc0 >= n_cols) continue;  // warp-uniform
-        store_slab(acc + g * 32, tc0);
-        if (tc0 + 16 < n_cols) store_slab(acc + g * 32 + 16, tc0 + 16);
+        if (!store_block32(acc + g * 32, tc0)) {
+          store_slab(acc + g * 32, tc0);
+          if (tc0 + 16 < n_cols) store_slab(acc + g * 32 + 16, tc0 + 16);
+        }
       }
       if (p.timing) tm_store += clock64() - t_store0;
       }
@@ -1097,11 +1147,12 @@ template <bool MN, int CG, int EPI>
 inline int launch_tc_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, int ntiles, cudaStream_t st,
                          const CUtensorMap* tmO);
 
-// tmO: optional 2-D view of p.out (make_out_map); with it, tiles of one column block store through the TMA unit
+// tmO: optional 2-D view of p.out (make_out_map); with it, EPI_ATOMIC tiles of one column block accumulate through the
+// TMA unit (measured: plain stores are better off as 128-byte row blocks from the warps, profiles/r02_store_paths.md)
 template <bool MN, int CG>
 inline int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, int ntiles, cudaStream_t st,
                      const CUtensorMap* tmO = nullptr) {
-  if (p.epi == EPI_STORE) return launch_tc_epi<MN, CG, EPI_STORE>(tmA, tmB, p, ntiles, st, tmO);
+  if (p.epi == EPI_STORE) return launch_tc_epi<MN, CG, EPI_STORE>(tmA, tmB, p, ntiles, st, nullptr);
   if (p.epi == EPI_ACCUM) return launch_tc_epi<MN, CG, EPI_ACCUM>(tmA, tmB, p, ntiles, st, nullptr);
   return launch_tc_epi<MN, CG, EPI_ATOMIC>(tmA, tmB, p, ntiles, st, tmO);
 }

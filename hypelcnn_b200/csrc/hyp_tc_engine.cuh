@@ -342,7 +342,7 @@ static void finish_launch(PlanBuf& pb, TcLaunch& l) {
   schedule_tiles(pb.tiles, (size_t)l.tile0, pb.segs, l.cg, l.windowed || !l.mn);
   l.ntiles = (int)pb.tiles.size() - l.tile0;
 }
-// the launch's output as a 2-D fp32 view [rows][ld] with `cols` valid columns: its one-column-block tiles store
+// the launch's output as a 2-D fp32 view [rows][ld] with `cols` valid columns: its one-column-block tiles accumulate
 // through the TMA unit (tc_gemm_kernel, store_slab)
 static int out_view(TcLaunch& l, const float* base, int cols, int64_t rows, int ld) {
   const int rc = make_out_map(&l.tmO, base, (uint64_t)cols, (uint64_t)rows, (uint64_t)ld);
@@ -548,7 +548,6 @@ static int tc_plan(hyp_model& m, int64_t B) {
           close_pair_run(pb.tiles, run, nrt * 128);
         }
       finish_launch(pb, T.fwd);
-      if ((rc = out_view(T.fwd, reinterpret_cast<const float*>(m.ws + T.z_off), Cout, rows_out, tout.Cp))) return rc;
       T.stats_rows = nrt;
       // ---------------- dgrad ----------------
       if (need_dgrad) {
@@ -833,7 +832,6 @@ static int tc_plan(hyp_model& m, int64_t B) {
           close_pair_run(pb.tiles, run, nbt * 128);
         }
       finish_launch(pb, T.fwd);
-      if ((rc = out_view(T.fwd, reinterpret_cast<const float*>(m.ws + T.z_off), Cout, rows_out, tout.Cp))) return rc;
       T.stats_rows = nbt;
       // ---------------- dgrad ----------------
       if (need_dgrad) {
@@ -947,8 +945,9 @@ static int tc_run(hyp_model& m, const TcLaunch& l, float* out, float* stats, int
   if (timing_on && !per_layer && scope) full += std::string("/") + scope;
   g_tc_timing_tag = full.c_str();
   g_prof.begin(st, full.c_str(), flops, 0.0);
-  static const bool tma_off = getenv("HYP_TC_TMA_STORE") && getenv("HYP_TC_TMA_STORE")[0] == '0';  // diagnostic: plain stores
-  const CUtensorMap* tmO = (l.tma_out && !tma_off && epi != EPI_ACCUM) ? &l.tmO : nullptr;
+  // dgrad accumulations (EPI_ATOMIC) leave through the TMA unit as f32 add reductions; HYP_TC_TMA_STORE=0: red.global
+  static const bool tma_off = getenv("HYP_TC_TMA_STORE") && getenv("HYP_TC_TMA_STORE")[0] == '0';
+  const CUtensorMap* tmO = (l.tma_out && !tma_off && epi == EPI_ATOMIC) ? &l.tmO : nullptr;
   p.out_cols = l.out_cols; p.out_rows = l.out_rows;
   const int rc = l.mn ? (l.cg == 2 ? launch_tc<true, 2>(l.tmA, l.tmB, p, l.ntiles, st, tmO)
                                    : launch_tc<true, 1>(l.tmA, l.tmB, p, l.ntiles, st, tmO))
