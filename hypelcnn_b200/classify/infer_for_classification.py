@@ -142,7 +142,9 @@ def build_parser():
 
 def main(argv=None):
     flags, _ = build_parser().parse_known_args(argv)
-    return run(flags)
+    result = run(flags)
+    parallel.finish()
+    return result
 
 
 if __name__ == "__main__":

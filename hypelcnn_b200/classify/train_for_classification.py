@@ -159,7 +159,9 @@ def run(flags):
 def main(argv=None):
     flags, _ = build_parser().parse_known_args(argv)
     print("Running on training mode")
-    return run(flags)
+    result = run(flags)
+    parallel.finish()
+    return result
 
 
 if __name__ == "__main__":

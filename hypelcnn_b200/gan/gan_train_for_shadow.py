@@ -372,6 +372,7 @@ def main(argv=None):
         flags = update_flags_from_json(flags, flags.flag_config_file)
     print("Running on training mode")
     print("Output divergence values:", run_session(params=dict(vars(flags)), base_log_path=flags.base_log_path))
+    parallel.finish()
 
 
 if __name__ == "__main__":

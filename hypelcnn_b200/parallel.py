@@ -29,6 +29,19 @@ def init_from_env(backend=None):
     return rank, local, world
 
 
+def finish():
+    """End of a data-parallel run: wait for this rank's device work, meet the other ranks, drop the process group.
+    All-reduces are asynchronous on the stream: a rank whose host loop has run ahead and simply returns would tear its
+    communicator down while the peers still wait in the collectives it only enqueued (seen as a hang of the two-rank
+    GAN app).  No-op for a single process."""
+    if not dist.is_initialized():
+        return
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def sync_split_seed(group=None):
     """Same train / validation / test split on every rank.  The loaders draw their splits from numpy's and Python's
     global generators (sklearn's StratifiedShuffleSplit without a random_state, numpy.random.shuffle), which every

@@ -76,8 +76,13 @@ def _worker(rank, world, port, out_dir):
         numpy.save(os.path.join(out_dir, f"split_{tag}_val_{rank}.npy"), val)
     # ---- stop decisions are collective ----
     assert P.collective_any(rank == 1) is True and P.collective_any(False) is False
-    dist.barrier()
-    dist.destroy_process_group()
+    # ---- the end of a run: a rank that is done early waits for its peers before the group goes away ----
+    import time
+    if rank == 1:
+        time.sleep(0.5)
+    P.finish()
+    assert not dist.is_initialized()
+    P.finish()  # idempotent
 
 
 def test_two_rank_gradient_allreduce_and_sharding(tmp_path):
