@@ -52,7 +52,8 @@ def ncu_raw(path):
 # ------------------------------------------------------------------------------------------------------------ gather
 def gather():
     trips = [("r2a", "vector kernel v1: warp = pixel row, rotated stores"), ("r2b", "lanes = neighbouring pixels, 2^23 conversion"),
-             ("r2d", "software pipeline: next patch's loads issued before the store phase")]
+             ("r2d", "software pipeline: next patch's loads issued before the store phase"),
+             ("r2z", "final trip: the same kernel (a shuffle-addressed variant measured 20 % slower and was dropped)")]
     lines = ["# Round 2 — patch gather (`hyp_gather_patches`): element-wise `gather_kernel` vs vector `gather_rows_kernel`", "",
              "Workload S-gather of SURVEY §8d: GRSS2013-shaped scene 349 x 1905 x 144 uint16 + fp32 LiDAR, neighborhood 3 (7x7x145 fp32 patches).",
              "GB/s = algorithmic bytes / CUDA-event time; algorithmic bytes per patch = 49 x (145 x 4 written + 144 x 2 + 4 read) = 42 728",
@@ -67,21 +68,21 @@ def gather():
         seen = True
         r = d["results"]
         for ver, name in (("v1", "`gather_kernel` (element-wise, round 1)"), ("v2", f"`gather_rows_kernel` ({what})")):
-            if f"{ver}_random_4096" in r and (ver == "v2" or trip == "r2a"):
+            if f"{ver}_random_4096" in r and (ver == "v2" or trip in ("r2a", "r2z")):
                 a, b = r[f"{ver}_random_4096"], r[f"{ver}_whole_scene"]
                 lines.append(f"| {trip} | {name} | {a['ms']:.4f} | {a['GB_per_s']:.0f} | {a['GB_per_s'] / 6551:.2f} | {b['ms']:.2f} | "
                              f"{b['GB_per_s']:.0f} | {b['GB_per_s'] / 6551:.2f} |")
     if not seen:
         return
-    d18 = whole_json(os.path.join(OUT, "r2a", "gather_2018.json"))
+    d18 = whole_json(os.path.join(OUT, "r2z", "gather_2018.json")) or whole_json(os.path.join(OUT, "r2a", "gather_2018.json"))
     if d18:
         r = d18["results"]
-        lines += ["", "GRSS2018-shaped scene (601 x 2384 x 48 uint16, LiDAR at twice the resolution, 11x11x49 patches, 35 816 B per patch), trip r2a:",
+        lines += ["", "GRSS2018-shaped scene (601 x 2384 x 48 uint16, LiDAR at twice the resolution, 11x11x49 patches, 35 816 B per patch):",
                   "", "| kernel | random 4 096 GB/s | whole scene GB/s |", "|---|---|---|"]
         for ver in ("v1", "v2"):
             lines.append(f"| {ver} | {r[f'{ver}_random_4096']['GB_per_s']:.0f} | {r[f'{ver}_whole_scene']['GB_per_s']:.0f} |")
     benches = []
-    for trip in ("r2d", "r2b", "r2a"):
+    for trip in ("r2z", "r2d", "r2b", "r2a"):
         for f in ("bench_gather_c2.log", "bench_gather_c2_64k.log", "bench_gather_c3.log"):
             j = last_json(os.path.join(OUT, trip, f))
             if j and not any(b["config"] == j["config"] for b in benches):
@@ -94,7 +95,7 @@ def gather():
             lines.append(f"| {j['config']['workload']} | {j['config']['targets_per_step']} | {j['ms_per_step']:.4f} | {j['value']:.3g} | "
                          f"{j['roofline']['achieved']:.0f} | {j['roofline']['frac']:.2f} | {j['e2e']['value']:.3g} |")
         json.dump(benches, open(os.path.join(PROF, "r02_gather_bench.json"), "w"), indent=1)
-    for trip in ("r2b", "r2a"):
+    for trip in ("r2z", "r2b", "r2a"):
         raw = os.path.join(OUT, trip, "gather_raw.csv")
         if os.path.exists(raw):
             v = ncu_raw(raw)
@@ -119,7 +120,7 @@ def gather():
 
 # ------------------------------------------------------------------------------------------------------ launch list
 def launches():
-    src = newest("r2k/launches_3xf16.csv", "r2j/launches_3xf16.csv", "r2i/launches_3xf16.csv", "r2d/launches_3xf16.csv")
+    src = newest("r2z/launches_3xf16.csv", "r2k/launches_3xf16.csv", "r2j/launches_3xf16.csv", "r2i/launches_3xf16.csv", "r2d/launches_3xf16.csv")
     if not src:
         return
     rows = [r for r in csv.reader(open(src)) if len(r) > 10]
@@ -176,7 +177,7 @@ def launches():
 
 # ------------------------------------------------------------------------------------------------- ncu --set full
 def full():
-    d = newest("r2k/fwd_conv_enc_2.raw.csv", "r2j/fwd_conv_enc_2.raw.csv", "r2g/fwd_conv_enc_2.raw.csv")
+    d = newest("r2z/fwd_conv_enc_2.raw.csv", "r2k/fwd_conv_enc_2.raw.csv", "r2j/fwd_conv_enc_2.raw.csv", "r2g/fwd_conv_enc_2.raw.csv")
     if not d:
         return
     base = os.path.dirname(d)
@@ -215,9 +216,9 @@ def full():
 # ------------------------------------------------------------------------------------------------- bench lines
 def benches():
     modes = []
-    for prec, files in (("3xtf32", ["r2k/bench_tf32.log", "r2h/bench_tf32.log", "r2c/bench_3xtf32.log"]),
-                        ("3xf16", ["r2k/bench.log", "r2j/bench.log", "r2i/bench.log", "r2h/bench2.log", "r2g/bench.log", "r2c/bench_3xf16.log"]),
-                        ("bf16", ["r2k/bench_bf16.log", "r2c/bench_bf16.log"])):
+    for prec, files in (("3xtf32", ["r2z/bench_tf32.log", "r2k/bench_tf32.log", "r2h/bench_tf32.log", "r2c/bench_3xtf32.log"]),
+                        ("3xf16", ["r2z/bench.log", "r2k/bench.log", "r2j/bench.log", "r2i/bench.log", "r2h/bench2.log", "r2g/bench.log", "r2c/bench_3xf16.log"]),
+                        ("bf16", ["r2z/bench_bf16.log", "r2k/bench_bf16.log", "r2c/bench_bf16.log"])):
         p = newest(*files)
         j = last_json(p) if p else None
         if j:
@@ -236,36 +237,51 @@ def benches():
                        f"{j['kernel_breakdown_ms_per_step'].get('tc_gemm_kernel', 0):.2f} | {j['roofline']['achieved']:.1f} | {j['roofline']['frac']:.3f} | "
                        f"{par.get('max_abs_logit_error', float('nan')):.2e} | {par.get('argmax_mismatches', 'n/a')} |")
         open(os.path.join(PROF, "r02_precision_modes.md"), "w").write("\n".join(out) + "\n")
-    head = newest("r2k/bench.log", "r2j/bench.log", "r2i/bench.log", "r2h/bench2.log", "r2g/bench.log")
+    head = newest("r2z/bench.log", "r2k/bench.log", "r2j/bench.log", "r2i/bench.log", "r2h/bench2.log", "r2g/bench.log")
     if head and last_json(head):
         open(os.path.join(PROF, "r02_bench.json"), "w").write(json.dumps(last_json(head)) + "\n")
-    c3 = [last_json(p) for p in (newest("r2k/bench_c3_51.log", "r2g/bench_c3_51.log"), newest("r2k/bench_c3_49.log", "r2g/bench_c3_49.log"),
-                                 newest("r2k/bench_c3_51_8gpu.log", "r2m/bench_c3_51_8gpu.log")) if p]
+    c3 = [last_json(p) for p in (newest("r2z/bench_c3_51.log", "r2k/bench_c3_51.log", "r2g/bench_c3_51.log"),
+                                 newest("r2z/bench_c3_49.log", "r2k/bench_c3_49.log", "r2g/bench_c3_49.log"),
+                                 newest("r2y/bench_c3_51_8gpu.log", "r2k/bench_c3_51_8gpu.log", "r2m/bench_c3_51_8gpu.log")) if p]
     c3 = [j for j in c3 if j]
     if c3:
         json.dump(c3, open(os.path.join(PROF, "r02_c3_bench.json"), "w"), indent=1)
-    inf = [last_json(p) for p in (newest("r2k/inference.json", "r2f/inference_twopass.json"), newest("r2m/inference_8gpu.json", "r2k/inference_8gpu.json"),
-                                  newest("r2a/inference.json")) if p]
+    inf = [last_json(p) for p in (newest("r2z/inference.json", "r2k/inference.json", "r2f/inference_twopass.json"),
+                                  newest("r2y/inference_8gpu.json", "r2m/inference_8gpu.json", "r2k/inference_8gpu.json")) if p]
     inf = [j for j in inf if j]
     if inf:
         json.dump(inf, open(os.path.join(PROF, "r02_inference.json"), "w"), indent=1)
     gan = []
-    for p in (newest("r2k/gan_graphs.json", "r2e/gan_graphs.json"), newest("r2e/gan_eager.json")):
+    for p, how in ((newest("r2z/gan.json"), "fused step kernels (one launch per train op) up to 1024 pairs, per-op chain above"),
+                   (newest("r2z/gan_chain.json"), "per-op kernel chain (HYP_GAN_FUSED=0)"),
+                   (newest("r2y/gan_8gpu.json"), "8 GPUs, fused step kernels / per-op chain, one gradient all-reduce per train op")):
         if p:
             for line in open(p).read().strip().split("\n"):
                 if line.startswith("{"):
                     j = json.loads(line)
-                    j["launch"] = "CUDA-graph replay (batch <= 2048)" if "graphs" in p else "eager launches (HYP_GAN_GRAPHS=0)"
+                    j["launch"] = how
                     gan.append(j)
     if gan:
         json.dump(gan, open(os.path.join(PROF, "r02_gan_bench.json"), "w"), indent=1)
-    for src, dst in (("r2k/tc_timing.log", "r02_role_timing_3xf16.txt"), ("r2j/tc_timing.log", "r02_role_timing_3xf16.txt"),
+    multi = {}
+    for key, path in (("headline_8gpu", "r2y/bench_8gpu.log"), ("headline_2gpu", "r2y/bench_2gpu.log"), ("headline_1gpu", "r2z/bench.log"),
+                      ("c3_51_8gpu", "r2y/bench_c3_51_8gpu.log"), ("inference_8gpu", "r2y/inference_8gpu.json"),
+                      ("reference_arm_1gpu_box", "r2z/bench_reference.log")):
+        j = last_json(os.path.join(OUT, path))
+        if j:
+            multi[key] = j
+    if multi:
+        json.dump(multi, open(os.path.join(PROF, "r02_multi_gpu.json"), "w"), indent=1)
+    hb = last_json(os.path.join(OUT, "r2z/hbm_mix.json"))
+    if hb:
+        json.dump(hb, open(os.path.join(PROF, "r02_hbm_mix.json"), "w"), indent=1)
+    for src, dst in (("r2z/tc_timing.log", "r02_role_timing_3xf16.txt"), ("r2k/tc_timing.log", "r02_role_timing_3xf16.txt"), ("r2j/tc_timing.log", "r02_role_timing_3xf16.txt"),
                      ("r2h/tc_timing.log", "r02_role_timing_3xf16.txt"), ("r2e/tc_timing.log", "r02_role_timing_3xf16.txt")):
         p = os.path.join(OUT, src)
         if os.path.exists(p):
             open(os.path.join(PROF, dst), "w").write("".join(l for l in open(p) if "tc_timing" in l))
             break
-    for src, dst in (("r2k/prof_layers.json", "r02_prof_layers_3xf16.json"), ("r2h/prof_layers.json", "r02_prof_layers_3xf16.json"),
+    for src, dst in (("r2z/prof_layers.json", "r02_prof_layers_3xf16.json"), ("r2k/prof_layers.json", "r02_prof_layers_3xf16.json"), ("r2h/prof_layers.json", "r02_prof_layers_3xf16.json"),
                      ("r2d/prof_layers_3xf16.json", "r02_prof_layers_3xf16.json")):
         p = os.path.join(OUT, src)
         if os.path.exists(p):
@@ -276,10 +292,12 @@ def benches():
 def sanitizer():
     out = ["# Round 2 — compute-sanitizer over the kernel tests and a train step", ""]
     found = False
-    for name, path, cmd in (("memcheck, GEMM building block", "r2a/sanitizer_memcheck_tc.log", "compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_tc.py -x -q"),
-                            ("memcheck, one HYPELCNN train step (C2 shape, batch 256, 3xF16)", "r2f/sanitizer_memcheck_step.log", "compute-sanitizer --tool memcheck python scripts/one_step.py --steps 1 --batch 256"),
-                            ("racecheck, GEMM building block (CTA pairs, K-major and MN-major, 3xTF32 and 3xF16)", "r2f/sanitizer_racecheck_tc.log",
-                             "compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_tc.py -q -k <CTA-pair subset>")):
+    for name, path, cmd in (("memcheck, GEMM building block", "r2z/sanitizer_memcheck_tc.log", "compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_tc.py -x -q"),
+                            ("memcheck, one HYPELCNN train step (C2 shape, batch 256, 3xF16)", "r2z/sanitizer_memcheck_step.log", "compute-sanitizer --tool memcheck python scripts/one_step.py --steps 1 --batch 256"),
+                            ("racecheck, GEMM building block (CTA pairs, K-major and MN-major, 3xTF32 and 3xF16)", "r2z/sanitizer_racecheck_tc.log",
+                             "compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_tc.py -q -k <CTA-pair subset>"),
+                            ("racecheck, one HYPELCNN train step (C2 shape, batch 128, 3xF16: 32-column store blocks, TMA add reductions, every element-wise kernel)",
+                             "r2z/sanitizer_racecheck_step.log", "compute-sanitizer --tool racecheck python scripts/one_step.py --steps 1 --batch 128")):
         p = os.path.join(OUT, path)
         if not os.path.exists(p):
             continue
@@ -300,9 +318,13 @@ def sanitizer():
 
 
 def tests_log():
-    p = newest("r2m/pytest_gpu.log", "r2k/pytest_gpu.log", "r2f/pytest_gpu.log")
+    p = newest("r2z/pytest_gpu.log", "r2m/pytest_gpu.log", "r2k/pytest_gpu.log", "r2f/pytest_gpu.log")
     if p:
-        shutil.copy(p, os.path.join(PROF, "r02_gpu_tests.log"))
+        text = open(p).read()
+        sm = newest("r2z/smoke.log")
+        if sm:
+            text += "\n__graft_entry__.smoke(): " + open(sm).read().strip().split("\n")[-1] + "\n"
+        open(os.path.join(PROF, "r02_gpu_tests.log"), "w").write(text)
 
 
 for fn in (gather, launches, full, benches, sanitizer, tests_log):
