@@ -327,6 +327,18 @@ def tests_log():
         open(os.path.join(PROF, "r02_gpu_tests.log"), "w").write(text)
 
 
-for fn in (gather, launches, full, benches, sanitizer, tests_log):
+def dp_apps():
+    out = []
+    for title, path in (("python -m torch.distributed.run --nproc-per-node 2 -m hypelcnn_b200.gan.gan_train_for_shadow (cycle_gan, batch 32, 120 steps)", "r2x/dp_gan.log"),
+                        ("python -m torch.distributed.run --nproc-per-node 2 -m hypelcnn_b200.classify.train_for_classification (HYPELCNN, 40 steps)", "r2y/dp_classify.log")):
+        p = os.path.join(OUT, path)
+        if os.path.exists(p):
+            keep = [l.rstrip()[:200] for l in open(p) if re.search(r"Output divergence|Best common|Validation result|Mean testing accuracy|Restored|Traceback|Error", l)]
+            out += [f"## {title}", ""] + keep[-8:] + [""]
+    if out:
+        open(os.path.join(PROF, "r02_dp_apps.log"), "w").write("\n".join(out) + "\n")
+
+
+for fn in (gather, launches, full, benches, sanitizer, tests_log, dp_apps):
     fn()
 print("\n".join(sorted(f for f in os.listdir(PROF) if f.startswith("r02"))))
