@@ -270,6 +270,14 @@ def benches():
         j = last_json(os.path.join(OUT, path))
         if j:
             multi[key] = j
+    # trip r2w: does the overlapped all-reduce take SMs from the persistent GEMMs?  Fewer NCCL CTAs only make it slower
+    ctas = {}
+    for v in ("default", "8", "4", "2"):
+        j = last_json(os.path.join(OUT, f"r2w/bench_8gpu_ctas_{v}.log"))
+        if j:
+            ctas[f"NCCL_MAX_CTAS={v}"] = {"ms_per_step": j["ms_per_step"], "value": j["value"], "e2e": j["e2e"]["value"], "clocks": j.get("clocks")}
+    if ctas:
+        multi["headline_8gpu_nccl_cta_budget"] = ctas
     if multi:
         json.dump(multi, open(os.path.join(PROF, "r02_multi_gpu.json"), "w"), indent=1)
     hb = last_json(os.path.join(OUT, "r2z/hbm_mix.json"))
