@@ -1138,6 +1138,13 @@ inline int tc_sm_count() {
     int dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    // HYP_TC_SMS: SMs the persistent GEMMs (and the grids sized after them) may occupy.  A GEMM CTA takes a whole SM
+    // (64 K registers), so a collective running beside the backward pass cannot share one: data-parallel runs can
+    // leave its CTAs a few SMs instead of letting them displace GEMM CTAs into a second wave.
+    if (const char* e = getenv("HYP_TC_SMS")) {
+      const int v = atoi(e);
+      if (v >= 2 && v <= sms) sms = v & ~1;
+    }
   }
   return sms;
 }

@@ -276,6 +276,10 @@ def benches():
         j = last_json(os.path.join(OUT, f"r2w/bench_8gpu_ctas_{v}.log"))
         if j:
             ctas[f"NCCL_MAX_CTAS={v}"] = {"ms_per_step": j["ms_per_step"], "value": j["value"], "e2e": j["e2e"]["value"], "clocks": j.get("clocks")}
+    for sms, c in (("144", "4"), ("140", "8"), ("132", "default")):  # ... and leaving it SMs of its own does not help either
+        j = last_json(os.path.join(OUT, f"r2w/bench_8gpu_sms_{sms}_ctas_{c}.log"))
+        if j:
+            ctas[f"HYP_TC_SMS={sms} NCCL_MAX_CTAS={c}"] = {"ms_per_step": j["ms_per_step"], "value": j["value"], "e2e": j["e2e"]["value"], "clocks": j.get("clocks")}
     if ctas:
         multi["headline_8gpu_nccl_cta_budget"] = ctas
     if multi:
