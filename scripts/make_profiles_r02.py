@@ -1,4 +1,4 @@
-"""Round-2 profile summaries: turns what the GPU trips left under gpurun_out/ (scripts_gpu_r2*.sh) into the tracked files
+"""Round-2 profile summaries: turns what the GPU trips left under gpurun_out/ (scripts/gpu_trips/scripts_gpu_r2*.sh) into the tracked files
 under profiles/.  Every section is skipped when its inputs are absent, so the script can be re-run after each trip.
     python scripts/make_profiles_r02.py"""
 import collections
