@@ -55,8 +55,13 @@ struct alignas(16) TcSeg {
   int32_t nb;          // B boxes per K block and plane
   int32_t ks_last;     // K steps (quarters of a K block) the LAST K block of the segment needs: 1..4, 0 = 4.  The tail of
                        // a K range that is not a multiple of the block is zero padding: its MMAs are skipped
-  int32_t pad[2];
+  int32_t nsets;       // MN-major only: 2..4 = the segment multiplies its A tile with that many B sets (one MMA group
+                       // each, accumulator columns [s * n_mma, (s + 1) * n_mma)); the sets share b0 / b1 / n_mma and
+                       // differ in b2: set 0 reads b2, set s > 0 reads byte s - 1 of b2x.  0 / 1 = one set.
+                       // A b2 outside the tensor is a set without a contribution (the TMA unit fills zeros).
+  int32_t b2x;
 };
+constexpr int TC_MAX_SETS = 4;
 
 struct alignas(16) TcColBlock {
   int32_t tcol;       // first accumulator column (multiple of 16; blocks are listed by increasing tcol)
@@ -502,6 +507,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int sb1 = __shfl_sync(0xffffffffu, wB.x, src) + b1_add, sb2 = __shfl_sync(0xffffffffu, wB.y, src);
         const int snk = __shfl_sync(0xffffffffu, wB.z, src), sn = __shfl_sync(0xffffffffu, wB.w, src);
         const int snb = __shfl_sync(0xffffffffu, wC.x, src);
+        const int nsets = MN ? max(1, __shfl_sync(0xffffffffu, wC.z, src)) : 1;
+        const int sb2x = __shfl_sync(0xffffffffu, wC.w, src);
         // B boxes this CTA loads: K-major boxes of bn/CG rows, MN-major boxes of 32 columns
         const uint32_t b_box_bytes = MN ? mn_box_bytes : (uint32_t)(p.bn / CG) * 128u;
         // MN-major: this CTA's half of the N columns starts at column rank * n / CG and is loaded as mnb-column boxes
@@ -510,7 +517,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int b_col0 = MN ? (int)rank * (sn / CG) : 0;
         const int b_row0 = MN ? 0 : (int)rank * (sn / CG);          // first B row
         (void)snb;
-        const uint32_t tx_cta = npl * (TC_PLANE_A + (uint32_t)nb * b_box_bytes);
+        const uint32_t tx_cta = npl * (TC_PLANE_A + (uint32_t)(nsets * nb) * b_box_bytes);
         const int a_boxes = TC_BM / mnb;  // MN-major A: boxes of mnb columns
         for (int kb = 0; kb < snk; kb++) {
           { const long long t0 = p.timing ? clock64() : 0; mbar_wait(empty_bar(stage), phase ^ 1u); if (p.timing) tm_wait_empty += clock64() - t0; }
@@ -528,9 +535,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else {
               for (int i = 0; i < a_boxes; i++)
                 tma_load_4d_u<CG>(pred, a_s + pl * TC_PLANE_A + i * mn_box_bytes, &tmA, fb, sa0 + i * mnb, sa1 + kb * kbe, sa2, pl);
-              for (int j = 0; j < nb; j++)
-                tma_load_4d_u<CG>(pred, b_s + pl * b_plane + j * mn_box_bytes, &tmB, fb, sb0 + b_col0 + j * mnb, sb1 + kb * kbe,
-                                  sb2, pl);
+              for (int sx = 0; sx < nsets; sx++) {
+                const int b2s = sx == 0 ? sb2 : ((sb2x >> (8 * (sx - 1))) & 0xff);
+                for (int j = 0; j < nb; j++)
+                  tma_load_4d_u<CG>(pred, b_s + pl * b_plane + (sx * nb + j) * mn_box_bytes, &tmB, fb, sb0 + b_col0 + j * mnb,
+                                    sb1 + kb * kbe, b2s, pl);
+              }
             }
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -569,14 +579,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           hdr0 = __ldg(hp); hdr1 = __ldg(hp + 1);
         }
         int2 sN[4];  // (nk, n_mma) of segment lane + 32 i
-        int sK[4];   // ks_last
+        int2 sK[4];  // (ks_last, nsets)
 #pragma unroll
         for (int i = 0; i < 4; i++) {
           sN[i] = make_int2(0, 0);
-          sK[i] = 0;
+          sK[i] = make_int2(0, 0);
           if (lane + 32 * i < seg_count) {
             sN[i] = __ldg(reinterpret_cast<const int2*>(&p.segs[seg_begin + lane + 32 * i].nk));
-            sK[i] = __ldg(&p.segs[seg_begin + lane + 32 * i].ks_last);
+            const int4 w3 = __ldg(reinterpret_cast<const int4*>(&p.segs[seg_begin + lane + 32 * i].nb));  // nb ks_last nsets b2x
+            sK[i] = make_int2(w3.y, w3.z);
           }
         }
         uint32_t accum = 0;
@@ -586,9 +597,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int rs = si >> 5, src = si & 31;
           const int2 wN = rs == 0 ? sN[0] : (rs == 1 ? sN[1] : (rs == 2 ? sN[2] : sN[3]));
           const int snk = __shfl_sync(0xffffffffu, wN.x, src);
-          const int wK = rs == 0 ? sK[0] : (rs == 1 ? sK[1] : (rs == 2 ? sK[2] : sK[3]));
-          const int sks = __shfl_sync(0xffffffffu, wK, src);
-          const uint32_t idesc = make_idesc(__shfl_sync(0xffffffffu, wN.y, src), MN, CG, ab_fmt);
+          const int2 wK = rs == 0 ? sK[0] : (rs == 1 ? sK[1] : (rs == 2 ? sK[2] : sK[3]));
+          const int sks = __shfl_sync(0xffffffffu, wK.x, src);
+          const int nsets = MN ? max(1, __shfl_sync(0xffffffffu, wK.y, src)) : 1;
+          const int sn = __shfl_sync(0xffffffffu, wN.y, src);
+          const uint32_t idesc = make_idesc(sn, MN, CG, ab_fmt);
+          // B sets of the segment (MN-major): boxes of set s start nb boxes behind those of set s - 1
+          const uint32_t set_step = MN ? (uint32_t)((sn / CG + mnb - 1) / mnb) * (mn_box_bytes >> 4) : 0u;
           for (int kb = 0; kb < snk; kb++, kcount++) {
             if (kcount % CH == 0) {  // new chunk: its TMEM buffer must have been drained
               buf = gchunk & 1u;
@@ -605,34 +620,40 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t b_hi = a_hi + (npl * TC_PLANE_A >> 4);
             const uint32_t b_lo = b_hi + (b_plane >> 4);
             const int nks = (kb == snk - 1 && sks != 0) ? sks : 4;
-            if (p.op == OP_TF32X3) {
+            for (int sx = 0; sx < nsets; sx++) {  // one MMA group per B set; they share the A tile of the stage
+              const uint32_t td = tmem_d + (uint32_t)(sx * sn);
+              const uint32_t bh = b_hi + (uint32_t)sx * set_step, bl = b_lo + (uint32_t)sx * set_step;
+              uint32_t acc = accum;
+              if (p.op == OP_TF32X3) {
 #pragma unroll
-              for (int ks = 0; ks < 4; ks++) {
-                if (ks >= nks) break;
-                const uint32_t o = (uint32_t)ks * ks_step;
-                mma_tf32_u<CG>(pred, tmem_d, a_lo + o, b_hi + o, desc_hi32, idesc, accum);
-                mma_tf32_u<CG>(pred, tmem_d, a_hi + o, b_lo + o, desc_hi32, idesc, 1);
-                mma_tf32_u<CG>(pred, tmem_d, a_hi + o, b_hi + o, desc_hi32, idesc, 1);
-                accum = 1;
-              }
-            } else if (p.op == OP_F16X3) {
+                for (int ks = 0; ks < 4; ks++) {
+                  if (ks >= nks) break;
+                  const uint32_t o = (uint32_t)ks * ks_step;
+                  mma_tf32_u<CG>(pred, td, a_lo + o, bh + o, desc_hi32, idesc, acc);
+                  mma_tf32_u<CG>(pred, td, a_hi + o, bl + o, desc_hi32, idesc, 1);
+                  mma_tf32_u<CG>(pred, td, a_hi + o, bh + o, desc_hi32, idesc, 1);
+                  acc = 1;
+                }
+              } else if (p.op == OP_F16X3) {
 #pragma unroll
-              for (int ks = 0; ks < 4; ks++) {
-                if (ks >= nks) break;
-                const uint32_t o = (uint32_t)ks * ks_step;
-                mma_f16_u<CG>(pred, tmem_d, a_lo + o, b_hi + o, desc_hi32, idesc, accum);
-                mma_f16_u<CG>(pred, tmem_d, a_hi + o, b_lo + o, desc_hi32, idesc, 1);
-                mma_f16_u<CG>(pred, tmem_d, a_hi + o, b_hi + o, desc_hi32, idesc, 1);
-                accum = 1;
-              }
-            } else {
+                for (int ks = 0; ks < 4; ks++) {
+                  if (ks >= nks) break;
+                  const uint32_t o = (uint32_t)ks * ks_step;
+                  mma_f16_u<CG>(pred, td, a_lo + o, bh + o, desc_hi32, idesc, acc);
+                  mma_f16_u<CG>(pred, td, a_hi + o, bl + o, desc_hi32, idesc, 1);
+                  mma_f16_u<CG>(pred, td, a_hi + o, bh + o, desc_hi32, idesc, 1);
+                  acc = 1;
+                }
+              } else {
 #pragma unroll
-              for (int ks = 0; ks < 4; ks++) {
-                if (ks >= nks) break;
-                mma_f16_u<CG>(pred, tmem_d, a_hi + (uint32_t)ks * ks_step, b_hi + (uint32_t)ks * ks_step, desc_hi32, idesc, accum);
-                accum = 1;
+                for (int ks = 0; ks < 4; ks++) {
+                  if (ks >= nks) break;
+                  mma_f16_u<CG>(pred, td, a_hi + (uint32_t)ks * ks_step, bh + (uint32_t)ks * ks_step, desc_hi32, idesc, acc);
+                  acc = 1;
+                }
               }
             }
+            accum = 1;
             tc_commit_u<CG>(pred, empty_bar(stage));  // frees the stage (in both CTAs) once these MMAs have read it
             if (kcount % CH == CH - 1 || kcount == total_kb - 1) {
               tc_commit_u<CG>(pred, tfull_bar(buf));
@@ -1106,7 +1127,8 @@ static thread_local const char* g_tc_timing_tag = nullptr;  // label of the next
 // fills n_cols and the MMA-width breakpoints of every tile; checks the limits the kernel relies on
 inline int tc_finalize_tiles(std::vector<TcTile>& tiles, const std::vector<TcSeg>& segs) {
   static_assert(sizeof(TcSeg) == 48 && sizeof(TcColBlock) == 32 && offsetof(TcTile, bp_kb) == 48 &&
-                    offsetof(TcTile, cb) == 48 + 8 * TC_MAX_BP && offsetof(TcSeg, nk) == 24,
+                    offsetof(TcTile, cb) == 48 + 8 * TC_MAX_BP && offsetof(TcSeg, nk) == 24 && offsetof(TcSeg, nb) == 32 &&
+                    offsetof(TcSeg, nsets) == 40,
                 "descriptor layouts are read as raw words by the kernel");
   for (TcTile& t : tiles) {
     if (t.seg_count > TC_MAX_SEGS) return fail(HYP_E_UNSUPPORTED, "tc gemm: more than 128 segments in one tile");
@@ -1115,14 +1137,16 @@ inline int tc_finalize_tiles(std::vector<TcTile>& tiles, const std::vector<TcSeg
     int kb = 0, last = -1;
     for (int i = 0; i < t.seg_count; i++) {
       const TcSeg& sg = segs[t.seg_begin + i];
-      t.n_cols = std::max(t.n_cols, sg.n_mma);
-      if (sg.n_mma != last) {
-        if (last >= 0 && sg.n_mma > last) return fail(HYP_E_INVALID, "tc gemm: segment widths must not increase");
+      const int width = sg.n_mma * std::max(1, sg.nsets);  // accumulator columns the segment's MMA groups cover
+      if (sg.nsets > TC_MAX_SETS || width > TC_MAX_COLS) return fail(HYP_E_INVALID, "tc gemm: too many B sets in one segment");
+      t.n_cols = std::max(t.n_cols, width);
+      if (width != last) {
+        if (last >= 0 && width > last) return fail(HYP_E_INVALID, "tc gemm: segment widths must not increase");
         if (t.nbp == TC_MAX_BP) return fail(HYP_E_UNSUPPORTED, "tc gemm: too many distinct MMA widths in one tile");
         t.bp_kb[t.nbp] = kb;
-        t.bp_n[t.nbp] = sg.n_mma;
+        t.bp_n[t.nbp] = width;
         t.nbp++;
-        last = sg.n_mma;
+        last = width;
       }
       kb += sg.nk;
     }

@@ -386,7 +386,10 @@ static void close_pair_run(std::vector<TcTile>& tiles, size_t run_begin, int oob
 //       end up with fewer units get empty tiles.
 static double tile_cost(const TcTile& t, const std::vector<TcSeg>& segs) {
   double c = 1500.0;  // epilogue
-  for (int i = 0; i < t.seg_count; i++) c += (double)segs[t.seg_begin + i].nk * (256.0 + segs[t.seg_begin + i].n_mma);
+  for (int i = 0; i < t.seg_count; i++) {
+    const TcSeg& sg = segs[t.seg_begin + i];
+    c += (double)sg.nk * (256.0 + (double)sg.n_mma * std::max(1, sg.nsets));
+  }
   return c;
 }
 // the assignment itself, on plain (cost, unit) pairs: lists[g] = the units of group g in execution order
@@ -745,23 +748,58 @@ static int tc_plan(hyp_model& m, int64_t B) {
         while (nslice < nkb && level_bytes / nslice > slice_bytes) nslice *= 2;
         const int slice_kb = (int)cdiv(nkb, nslice);
         nslice = (int)cdiv(nkb, slice_kb);
-        // tile = (slice, chunk of output positions, tap, slot group, M tile).  Order: slice, then position chunk, then
-        // tap: the taps of one chunk reuse its gz rows back to back and the slice's activation rows stay L2-resident
-        // across chunks (every position is in every other's 7x7 neighbourhood).
+        // tile = (slice, chunk of source positions, tap group, slot group, M tile).  Order: slice, then position chunk,
+        // then tap group: the groups of one chunk reuse its activation rows back to back and the slice's gz rows stay
+        // L2-resident across chunks (every position is in every other's 7x7 neighbourhood).
+        // Tap groups: the taps of one ring multiply the same slot prefix, and neighbouring taps read almost the same
+        // activation rows.  A group of neighbouring taps of a ring (two by default) shares ONE A tile per (source
+        // position, K block) and multiplies it with the group's gz tiles (B sets, TcSeg.nsets): the activation
+        // traffic per tap, which is what paces these launches (L2 -> SM), drops by the group size.  A tap whose output
+        // position falls outside the patch for some source position reads an out-of-bounds gz position: zeros.
+        // Measured (C2, 4096 patches, ms per launch of the three levels): 1 set 0.60 / 0.86 / 0.38, 2 sets 0.55 / 0.73 /
+        // 0.35, 3 sets 0.56 / 0.78 / 0.37, 4 sets 0.58 / 0.76 / 0.37 -- beyond two, the stage ring shrinks to two stages and
+        // the zero-filled border sets cost more MMAs than the shared tile saves.
+        static const int max_sets = getenv("HYP_WG_TAP_SETS") ? std::max(1, std::min(TC_MAX_SETS, atoi(getenv("HYP_WG_TAP_SETS")))) : 2;
+        struct TapGroup { std::vector<std::pair<int, int>> t; int ring; };
+        std::vector<TapGroup> groups;
+        for (int ring = 0; ring <= h; ring++) {
+          // the ring's taps in perimeter order (neighbours in the list are neighbours in the window)
+          std::vector<std::pair<int, int>> per;
+          if (ring == 0) per.push_back({0, 0});
+          else {
+            for (int dx = -ring; dx < ring; dx++) per.push_back({-ring, dx});
+            for (int dy = -ring; dy < ring; dy++) per.push_back({dy, ring});
+            for (int dx = ring; dx > -ring; dx--) per.push_back({ring, dx});
+            for (int dy = ring; dy > -ring; dy--) per.push_back({dy, -ring});
+          }
+          const int slots = std::min(NS, (R - ring) * nt);  // (one slot group per tile below: sets only when ngroups == 1)
+          int gsz = 1;
+          if (ngroups == 1 && slots > 0 && PP < 255)  // (positions travel as bytes in TcSeg.b2x, 255 = out of bounds)
+            gsz = std::max(1, std::min(std::min(max_sets, TC_MAX_COLS / (slots * fpad)), TC_MAX_CB / slots));
+          for (size_t i = 0; i < per.size(); i += gsz) {
+            TapGroup g;
+            g.ring = ring;
+            for (size_t j = i; j < std::min(per.size(), i + gsz); j++) g.t.push_back(per[j]);
+            groups.push_back(g);
+          }
+        }
         const int cgw = T.wg.cg;
-        const int pc = (int)std::min<int64_t>(PP, std::max<int64_t>(1, cdiv((int64_t)PP * taps.size() * mt * ngroups / cgw,
+        const int pc = (int)std::min<int64_t>(PP, std::max<int64_t>(1, cdiv((int64_t)PP * groups.size() * mt * ngroups / cgw,
                                                                         4 * (tc_sm_count() / cgw))));
         for (int sl = 0; sl < nslice; sl++) {
           const int kb0 = sl * slice_kb, kbn = std::min(slice_kb, nkb - kb0);
           for (int pc0 = 0; pc0 < PP; pc0 += pc)
-            for (auto& tp : taps) {
-              const int dy = tp.first, dx = tp.second, ring = std::max(std::abs(dy), std::abs(dx));
-              std::vector<int> ps;  // output positions of the chunk whose tap source is inside the patch
-              for (int p = pc0; p < std::min(PP, pc0 + pc); p++) {
-                const int ph = p / P, pw = p % P;
-                if (ph + dy >= 0 && ph + dy < P && pw + dx >= 0 && pw + dx < P) ps.push_back(p);
+            for (const TapGroup& tg : groups) {
+              const int ring = tg.ring, nset = (int)tg.t.size();
+              // source (activation) positions of the chunk that feed at least one tap of the group
+              std::vector<int> qs;
+              for (int q = pc0; q < std::min(PP, pc0 + pc); q++) {
+                const int qh = q / P, qw = q % P;
+                bool any = false;
+                for (auto& tp : tg.t) any = any || (qh - tp.first >= 0 && qh - tp.first < P && qw - tp.second >= 0 && qw - tp.second < P);
+                if (any) qs.push_back(q);
               }
-              if (ps.empty()) continue;
+              if (qs.empty()) continue;
               for (int g = 0; g < ngroups; g++) {
                 const int s0 = g * spg, s1 = std::min(std::min(NS, s0 + spg), (R - ring) * nt);
                 if (s1 <= s0) continue;
@@ -770,25 +808,35 @@ static int tc_plan(hyp_model& m, int64_t B) {
                   TcTile t = blank_tile();
                   t.seg_begin = (int)pb.segs.size();
                   t.a0_add = im * 128;
-                  for (int pp : ps) {
+                  for (int q : qs) {
+                    const int qh = q / P, qw = q % P;
                     TcSeg s{};
-                    s.a1 = kb0 * KB; s.a2 = pp + dy * P + dx;
-                    s.b0 = s0 * fpad; s.b1 = kb0 * KB; s.b2 = pp;
+                    s.a1 = kb0 * KB; s.a2 = q;
+                    s.b0 = s0 * fpad; s.b1 = kb0 * KB;
                     s.nk = kbn; s.n_mma = r16(ncols); s.nb = (int)cdiv(s.n_mma, KB);
-                    T.wg.b_rows = std::max(T.wg.b_rows, wg_brows(s.n_mma, T.wg.cg, KB));
+                    s.nsets = nset;
+                    for (int j = 0; j < nset; j++) {
+                      const int ph = qh - tg.t[j].first, pw = qw - tg.t[j].second;
+                      const int pos = (ph >= 0 && ph < P && pw >= 0 && pw < P) ? ph * P + pw : 255;  // 255 >= PP: out of bounds
+                      if (j == 0) s.b2 = pos; else s.b2x |= pos << (8 * (j - 1));
+                    }
+                    T.wg.b_rows = std::max(T.wg.b_rows, nset * wg_brows(s.n_mma, T.wg.cg, KB));
                     t.total_kb += s.nk;
                     pb.segs.push_back(s);
                   }
                   t.seg_count = (int)pb.segs.size() - t.seg_begin;
                   t.m_valid = std::min(128, Cin - im * 128);
                   t.ld_out = f;
-                  t.ncb = s1 - s0;
-                  for (int s = s0; s < s1; s++) {
-                    const int q = T.slot_q(s), k = 2 * q + 1;
-                    TcColBlock& cb = t.cb[s - s0];
-                    cb.tcol = (s - s0) * fpad; cb.width = T.slot_w(s);
-                    cb.out_off = L.w_off[q] + (int64_t)((dy + q) * k + (dx + q)) * Cin * f + (int64_t)im * 128 * f +
-                                 (s % nt) * T.ft;
+                  t.ncb = nset * (s1 - s0);
+                  for (int j = 0; j < nset; j++) {
+                    const int dy = tg.t[j].first, dx = tg.t[j].second;
+                    for (int sidx = s0; sidx < s1; sidx++) {
+                      const int q = T.slot_q(sidx), k = 2 * q + 1;
+                      TcColBlock& cb = t.cb[j * (s1 - s0) + (sidx - s0)];
+                      cb.tcol = j * r16(ncols) + (sidx - s0) * fpad; cb.width = T.slot_w(sidx);
+                      cb.out_off = L.w_off[q] + (int64_t)((dy + q) * k + (dx + q)) * Cin * f + (int64_t)im * 128 * f +
+                                   (sidx % nt) * T.ft;
+                    }
                   }
                   pb.tiles.push_back(t);
                 }
