@@ -284,6 +284,9 @@ def benches():
         multi["headline_8gpu_nccl_cta_budget"] = ctas
     if multi:
         json.dump(multi, open(os.path.join(PROF, "r02_multi_gpu.json"), "w"), indent=1)
+    tp = last_json(os.path.join(OUT, "r2z/tensor_peaks.json"))
+    if tp:
+        json.dump(tp, open(os.path.join(PROF, "r02_tensor_peaks.json"), "w"), indent=1)
     hb = last_json(os.path.join(OUT, "r2z/hbm_mix.json"))
     if hb:
         json.dump(hb, open(os.path.join(PROF, "r02_hbm_mix.json"), "w"), indent=1)
