@@ -119,6 +119,7 @@ _PROTOS = {
     "hyp_crc32c": (_I, [_P, ctypes.c_uint64, _P]),
     "hyp_tiff_lzw_decode": (_I, [_P, ctypes.c_uint64, _P, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]),
     "hyp_debug_schedule": (_I, [_P, _I, _I, _I, _P, _P]),
+    "hyp_debug_level_tap_groups": (_I, [_I, _I, _I, _I, _I, _P, _I, ctypes.POINTER(_I)]),
     "hyp_debug_tc_gemm": (_I, [_I, _P, _P, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P]),
     "hyp_model_dropout_mask": (_I, [_P, ctypes.c_char_p, ctypes.c_uint64, _L, _P, _P]),
 }

@@ -1280,6 +1280,33 @@ int hyp_debug_schedule(const double* costs, int units, int groups, int windowed,
   return HYP_OK;
 }
 
+// host-only: the tap groups of a level's wgrad launch and the gz position every (group, set, source position) reads
+// (tests/test_schedule.py).  Rows of `out`: group, set, dy, dx, source position q, output position (255 = outside the
+// patch); one row per set of every (group, q) the launch visits.
+int hyp_debug_level_tap_groups(int P, int R, int nt, int fpad, int max_sets, int32_t* out, int cap_rows, int* rows_out) {
+  HYP_CHECK_ARG(P >= 1 && R >= 1 && nt >= 1 && fpad >= 16 && fpad % 16 == 0 && max_sets >= 1 && rows_out, "bad argument");
+  const int h = std::min(R - 1, P - 1), NS = R * nt, PP = P * P;
+  const int spg = std::min(std::min(256 / fpad, tc::TC_MAX_CB), NS), ngroups = (int)cdiv(NS, spg);  // as tc_plan
+  const std::vector<tc::TapGroup> groups = tc::level_tap_groups(h, R, nt, NS, fpad, ngroups, PP, std::min(max_sets, tc::TC_MAX_SETS));
+  int n = 0;
+  for (size_t g = 0; g < groups.size(); g++)
+    for (int q = 0; q < PP; q++) {
+      bool any = false;
+      for (auto& tp : groups[g].t) any = any || tc::tap_output_position(P, q, tp.first, tp.second) != 255;
+      if (!any) continue;
+      for (size_t j = 0; j < groups[g].t.size(); j++) {
+        if (out && n < cap_rows) {
+          int32_t* r = out + (size_t)n * 6;
+          r[0] = (int32_t)g; r[1] = (int32_t)j; r[2] = groups[g].t[j].first; r[3] = groups[g].t[j].second; r[4] = q;
+          r[5] = tc::tap_output_position(P, q, groups[g].t[j].first, groups[g].t[j].second);
+        }
+        n++;
+      }
+    }
+  *rows_out = n;
+  return HYP_OK;
+}
+
 int hyp_debug_tc_gemm(int mn_flags, const float* A, const float* B, int M, int N, int K, float* D, float* stats,
                       int raw_hi, int bn, int ksplit, int chunk_kb, void* stream) {
   using namespace hyp::tc;

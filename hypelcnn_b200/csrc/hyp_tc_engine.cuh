@@ -490,6 +490,44 @@ static void n_tiling(int total, int& ntn, int& nw) {
   nw = r16((int)cdiv(total, ntn));
 }
 
+// ---- level wgrad tap groups ---------------------------------------------------------------------
+// The taps of one ring multiply the same slot prefix, and neighbouring taps read almost the same activation rows.  A
+// group of neighbouring taps of a ring shares ONE A tile per (source position, K block) and multiplies it with the
+// group's gz tiles (B sets, TcSeg.nsets).  h = tap radius, R kernels, nt N tiles per kernel, NS slots of fpad columns,
+// ngroups slot groups per position (sets only when there is one), PP positions, max_sets taps per group at most.
+struct TapGroup { std::vector<std::pair<int, int>> t; int ring; };
+static std::vector<TapGroup> level_tap_groups(int h, int R, int nt, int NS, int fpad, int ngroups, int PP, int max_sets) {
+  std::vector<TapGroup> groups;
+  for (int ring = 0; ring <= h; ring++) {
+    // the ring's taps in perimeter order (neighbours in the list are neighbours in the window)
+    std::vector<std::pair<int, int>> per;
+    if (ring == 0) per.push_back({0, 0});
+    else {
+      for (int dx = -ring; dx < ring; dx++) per.push_back({-ring, dx});
+      for (int dy = -ring; dy < ring; dy++) per.push_back({dy, ring});
+      for (int dx = ring; dx > -ring; dx--) per.push_back({ring, dx});
+      for (int dy = ring; dy > -ring; dy--) per.push_back({dy, -ring});
+    }
+    const int slots = std::min(NS, (R - ring) * nt);
+    int gsz = 1;
+    if (ngroups == 1 && slots > 0 && PP < 255)  // (positions travel as bytes in TcSeg.b2x, 255 = out of bounds)
+      gsz = std::max(1, std::min(std::min(max_sets, TC_MAX_COLS / (slots * fpad)), TC_MAX_CB / slots));
+    for (size_t i = 0; i < per.size(); i += gsz) {
+      TapGroup g;
+      g.ring = ring;
+      for (size_t j = i; j < std::min(per.size(), i + gsz); j++) g.t.push_back(per[j]);
+      groups.push_back(g);
+    }
+  }
+  return groups;
+}
+// gz (output) position that tap (dy, dx) pairs with source position q of a P x P patch; 255 = outside the patch (an
+// out-of-bounds TMA coordinate: the set contributes zeros)
+static inline int tap_output_position(int P, int q, int dy, int dx) {
+  const int ph = q / P - dy, pw = q % P - dx;
+  return (ph >= 0 && ph < P && pw >= 0 && pw < P) ? ph * P + pw : 255;
+}
+
 static int tc_plan(hyp_model& m, int64_t B) {
   TcState& S = *m.tc;
   if (S.planned_B == B) return HYP_OK;
@@ -751,38 +789,13 @@ static int tc_plan(hyp_model& m, int64_t B) {
         // tile = (slice, chunk of source positions, tap group, slot group, M tile).  Order: slice, then position chunk,
         // then tap group: the groups of one chunk reuse its activation rows back to back and the slice's gz rows stay
         // L2-resident across chunks (every position is in every other's 7x7 neighbourhood).
-        // Tap groups: the taps of one ring multiply the same slot prefix, and neighbouring taps read almost the same
-        // activation rows.  A group of neighbouring taps of a ring (two by default) shares ONE A tile per (source
-        // position, K block) and multiplies it with the group's gz tiles (B sets, TcSeg.nsets): the activation
-        // traffic per tap, which is what paces these launches (L2 -> SM), drops by the group size.  A tap whose output
-        // position falls outside the patch for some source position reads an out-of-bounds gz position: zeros.
+        // Tap groups (level_tap_groups above), two taps by default: the activation traffic per tap, which paces these
+        // launches together with the MMA stream, drops by the group size.
         // Measured (C2, 4096 patches, ms per launch of the three levels): 1 set 0.60 / 0.86 / 0.38, 2 sets 0.55 / 0.73 /
         // 0.35, 3 sets 0.56 / 0.78 / 0.37, 4 sets 0.58 / 0.76 / 0.37 -- beyond two, the stage ring shrinks to two stages and
         // the zero-filled border sets cost more MMAs than the shared tile saves.
         static const int max_sets = getenv("HYP_WG_TAP_SETS") ? std::max(1, std::min(TC_MAX_SETS, atoi(getenv("HYP_WG_TAP_SETS")))) : 2;
-        struct TapGroup { std::vector<std::pair<int, int>> t; int ring; };
-        std::vector<TapGroup> groups;
-        for (int ring = 0; ring <= h; ring++) {
-          // the ring's taps in perimeter order (neighbours in the list are neighbours in the window)
-          std::vector<std::pair<int, int>> per;
-          if (ring == 0) per.push_back({0, 0});
-          else {
-            for (int dx = -ring; dx < ring; dx++) per.push_back({-ring, dx});
-            for (int dy = -ring; dy < ring; dy++) per.push_back({dy, ring});
-            for (int dx = ring; dx > -ring; dx--) per.push_back({ring, dx});
-            for (int dy = ring; dy > -ring; dy--) per.push_back({dy, -ring});
-          }
-          const int slots = std::min(NS, (R - ring) * nt);  // (one slot group per tile below: sets only when ngroups == 1)
-          int gsz = 1;
-          if (ngroups == 1 && slots > 0 && PP < 255)  // (positions travel as bytes in TcSeg.b2x, 255 = out of bounds)
-            gsz = std::max(1, std::min(std::min(max_sets, TC_MAX_COLS / (slots * fpad)), TC_MAX_CB / slots));
-          for (size_t i = 0; i < per.size(); i += gsz) {
-            TapGroup g;
-            g.ring = ring;
-            for (size_t j = i; j < std::min(per.size(), i + gsz); j++) g.t.push_back(per[j]);
-            groups.push_back(g);
-          }
-        }
+        const std::vector<TapGroup> groups = level_tap_groups(h, R, nt, NS, fpad, ngroups, PP, max_sets);
         const int cgw = T.wg.cg;
         const int pc = (int)std::min<int64_t>(PP, std::max<int64_t>(1, cdiv((int64_t)PP * groups.size() * mt * ngroups / cgw,
                                                                         4 * (tc_sm_count() / cgw))));
@@ -794,9 +807,8 @@ static int tc_plan(hyp_model& m, int64_t B) {
               // source (activation) positions of the chunk that feed at least one tap of the group
               std::vector<int> qs;
               for (int q = pc0; q < std::min(PP, pc0 + pc); q++) {
-                const int qh = q / P, qw = q % P;
                 bool any = false;
-                for (auto& tp : tg.t) any = any || (qh - tp.first >= 0 && qh - tp.first < P && qw - tp.second >= 0 && qw - tp.second < P);
+                for (auto& tp : tg.t) any = any || tap_output_position(P, q, tp.first, tp.second) != 255;
                 if (any) qs.push_back(q);
               }
               if (qs.empty()) continue;
@@ -809,15 +821,13 @@ static int tc_plan(hyp_model& m, int64_t B) {
                   t.seg_begin = (int)pb.segs.size();
                   t.a0_add = im * 128;
                   for (int q : qs) {
-                    const int qh = q / P, qw = q % P;
                     TcSeg s{};
                     s.a1 = kb0 * KB; s.a2 = q;
                     s.b0 = s0 * fpad; s.b1 = kb0 * KB;
                     s.nk = kbn; s.n_mma = r16(ncols); s.nb = (int)cdiv(s.n_mma, KB);
                     s.nsets = nset;
                     for (int j = 0; j < nset; j++) {
-                      const int ph = qh - tg.t[j].first, pw = qw - tg.t[j].second;
-                      const int pos = (ph >= 0 && ph < P && pw >= 0 && pw < P) ? ph * P + pw : 255;  // 255 >= PP: out of bounds
+                      const int pos = tap_output_position(P, q, tg.t[j].first, tg.t[j].second);  // 255 >= PP: out of bounds
                       if (j == 0) s.b2 = pos; else s.b2x |= pos << (8 * (j - 1));
                     }
                     T.wg.b_rows = std::max(T.wg.b_rows, nset * wg_brows(s.n_mma, T.wg.cg, KB));

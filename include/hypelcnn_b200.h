@@ -296,6 +296,13 @@ int hyp_tiff_lzw_decode(const void* data, uint64_t len, void* out, uint64_t out_
 int hyp_debug_schedule(const double* costs, int units, int groups, int windowed, int32_t* group_of_unit,
                        int32_t* rank_in_group);
 
+/* Debug / test hook, host only: the tap groups of a level's wgrad launch (hyp_tc_engine.cuh level_tap_groups; level =
+ * R kernels 1x1 .. (2R-1)x(2R-1) of nt x fpad filter columns each on P x P patches) and, per group and source
+ * (activation) position q the launch visits, the gz position each of the group's taps reads.  Rows of out (6 int32):
+ * group, set, dy, dx, q, output position (255 = outside the patch: that set reads zeros).  rows_out = rows produced
+ * (rows beyond cap_rows are counted, not written). */
+int hyp_debug_level_tap_groups(int P, int R, int nt, int fpad, int max_sets, int32_t* out, int cap_rows, int* rows_out);
+
 /* probe of the tcgen05/TMA segment-GEMM building block used by the tensor-core precision
  * modes.  mn bit 0 = 0: A[M,K], B[N,K] -> D = A*B^T (K-major); 1: A[K,M], B[K,N]
  * -> D = A^T*B (MN-major).  mn bit 1: run as CTA pairs (tcgen05 cta_group::2).  mn bits 2..3: operand format

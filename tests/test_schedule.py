@@ -86,3 +86,45 @@ def test_load_spread_on_the_c2_launch_shapes(lib):
 
 def test_bad_arguments_are_rejected(lib):
     assert lib.hyp_debug_schedule(None, 3, 2, 1, None, None) == N.HYP_E_INVALID
+
+
+def tap_group_rows(lib, P, R, nt, fpad, max_sets):
+    n = ctypes.c_int(0)
+    N.check(lib.hyp_debug_level_tap_groups(P, R, nt, fpad, max_sets, None, 0, ctypes.byref(n)))
+    out = numpy.empty((n.value, 6), dtype=numpy.int32)
+    N.check(lib.hyp_debug_level_tap_groups(P, R, nt, fpad, max_sets, out.ctypes.data_as(ctypes.c_void_p), n.value, ctypes.byref(n)))
+    return out
+
+
+@pytest.mark.parametrize("P,R,nt,fpad,max_sets", [(7, 4, 1, 32, 2), (7, 4, 1, 16, 2), (7, 4, 1, 16, 4), (7, 4, 1, 64, 2),
+                                                  (11, 6, 1, 32, 2), (3, 3, 1, 16, 4), (7, 4, 1, 32, 1), (5, 2, 2, 128, 2)])
+def test_level_wgrad_tap_groups_cover_every_tap_and_position_once(lib, P, R, nt, fpad, max_sets):
+    """Every tap of the level belongs to exactly one (group, set); over the source positions a group visits, a tap reads
+    exactly the output positions p with p + tap inside the patch (each once), everything else is the out-of-bounds
+    marker; no visited position is all out of bounds; the group's accumulator fits the kernel's limits."""
+    rows = tap_group_rows(lib, P, R, nt, fpad, max_sets)
+    h = min(R - 1, P - 1)
+    taps = {}
+    for g, j, dy, dx, q, pos in rows.tolist():
+        taps.setdefault((dy, dx), set()).add((g, j))
+    assert set(taps) == {(dy, dx) for dy in range(-h, h + 1) for dx in range(-h, h + 1)}
+    assert all(len(v) == 1 for v in taps.values())
+    for (dy, dx), owner in taps.items():
+        (g, j), = owner
+        mine = rows[(rows[:, 0] == g) & (rows[:, 1] == j)]
+        got = sorted((int(q), int(p)) for q, p in mine[:, 4:6] if p != 255)
+        want = sorted(((y + dy) * P + (x + dx), y * P + x) for y in range(P) for x in range(P)
+                      if 0 <= y + dy < P and 0 <= x + dx < P)
+        assert got == want, (dy, dx)
+        assert len(set(mine[:, 4].tolist())) == len(mine)                      # one row per visited source position
+    for g in set(rows[:, 0].tolist()):
+        grp = rows[rows[:, 0] == g]
+        nset = len(set(grp[:, 1].tolist()))
+        ring = max(abs(int(grp[0, 2])), abs(int(grp[0, 3])))
+        assert all(max(abs(int(dy)), abs(int(dx))) == ring for dy, dx in grp[:, 2:4])   # one ring per group
+        slots = min(R * nt, (R - ring) * nt)
+        assert nset <= max_sets and (nset == 1 or (nset * slots * fpad <= 256 and nset * slots <= 8))
+        for q in set(grp[:, 4].tolist()):
+            assert (grp[grp[:, 4] == q][:, 5] != 255).any()                     # a visited position feeds some tap
+    if max_sets > 1 and fpad * R * nt <= 128:
+        assert max(len(set(rows[rows[:, 0] == g][:, 1].tolist())) for g in set(rows[:, 0].tolist())) > 1
